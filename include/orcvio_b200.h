@@ -1,0 +1,207 @@
+/*
+ * orcvio_b200 -- C ABI of the B200-native OrcVIO filter-update path.
+ *
+ * The reference has no plugin/FFI layer: callers link liborcvio_estimator and call
+ * the C++ class orcvio::OrcVIO directly (reference include/orcvio/orcvio.h:39-119,
+ * CMakeLists.txt:76-83).  This header is the C-ABI shape of that class for the hot
+ * path: plain pointers and sizes, column-major double matrices where the reference
+ * passes Eigen::MatrixXd, no C++/torch types.  INTEGRATION.md shows the thin
+ * Eigen facade a maintainer would put on top to keep the class signature.
+ *
+ * Every entry point runs its arithmetic in hand-written sm_100a CUDA kernels
+ * (orcvio_b200/csrc).  There is no CPU fallback: without a CUDA device every compute
+ * call returns ORCVIO_ERR_NO_DEVICE and prints the reason to stderr.
+ */
+#ifndef ORCVIO_B200_H
+#define ORCVIO_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ORCVIO_OK 0
+#define ORCVIO_ERR_NO_DEVICE -1
+#define ORCVIO_ERR_ARG -2
+#define ORCVIO_ERR_CONFIG -3
+#define ORCVIO_ERR_UNSUPPORTED -4
+#define ORCVIO_ERR_CUDA -5
+#define ORCVIO_ERR_CAPACITY -6
+
+/* One tracked image feature: field-for-field MonoFeatureMeasurement
+ * (reference include/orcvio/feat/feature_msg.h:14-44). */
+typedef struct {
+  unsigned long long id;
+  double u, v;
+  double u_init, v_init;
+  double u_vel, v_vel;
+  double u_init_vel, v_init_vel;
+} OrcvioFeature;
+
+/* One IMU sample: ImuData (reference include/sensors/ImuData.hpp:16-39). */
+typedef struct {
+  double t;
+  double gyro[3];
+  double acc[3];
+} OrcvioImu;
+
+/* Snapshot of the IMU state and of what the reference's getters return
+ * (getTbw/getVel/getPpose/getPvel, reference src/orcvio.cpp:2962-3026). */
+typedef struct {
+  long long state_id;
+  double time;
+  double R[9];        /* body->world, row-major */
+  double p[3];
+  double v[3];
+  double bg[3];
+  double ba[3];
+  double P_pose[36];  /* [p, theta] ordering, row-major (getPpose) */
+  double P_vel[9];
+  int n_clones;
+  int dim;            /* covariance dimension D = 22 + 6 n_clones */
+  int n_map_features; /* size of the map server */
+} OrcvioState;
+
+/* Per-frame counters for parity tests (which features were consumed and how). */
+typedef struct {
+  int n_candidates_lost;     /* MSCKF candidates of removeLostFeatures */
+  int n_tri_invalid_lost;
+  int n_gate_pass_lost;
+  int n_candidates_prune;
+  int n_tri_invalid_prune;
+  int n_gate_pass_prune;
+  int n_removed_clones;
+  long long removed_ids[2];
+  int zupt;
+} OrcvioFrameStats;
+
+typedef struct orcvio_handle orcvio_handle;
+typedef struct orcvio_batch orcvio_batch;
+
+/* ---- orcvio::OrcVIO class mirror ------------------------------------------------- */
+/* OrcVIO::OrcVIO(std::string& config_file), src/orcvio.cpp:45-50 */
+orcvio_handle* orcvio_create(const char* config_yaml_path);
+void orcvio_destroy(orcvio_handle* h);
+/* OrcVIO::initialize(), src/orcvio.cpp:418-497.  1 = ok, 0 = yaml unreadable/unsupported. */
+int orcvio_initialize(orcvio_handle* h);
+/* initial_use_gt semantics (src/orcvio.cpp:514-544) for configs whose yaml has no GT block:
+ * the static/dynamic initialisers are out of scope, so the caller supplies the state. */
+int orcvio_set_initial_state(orcvio_handle* h, double t, const double quat_xyzw[4], const double p[3],
+                             const double v[3], const double bg[3], const double ba[3]);
+/* OrcVIO::processFeatures(msg, imu_msg_buffer), src/orcvio.cpp:500-661.
+ * `imu` is the caller's buffer of *n_imu samples; like the reference the consumed prefix is
+ * erased: the remaining samples are moved to the front and *n_imu is updated.
+ * Returns 1 (published), 0 (not yet initialised / no IMU ahead of the image), <0 error. */
+int orcvio_process_features(orcvio_handle* h, double t_img, const OrcvioFeature* feats, int n_feats,
+                            OrcvioImu* imu, int* n_imu);
+int orcvio_get_state(orcvio_handle* h, OrcvioState* out);
+/* state_server.state_cov, column-major D x D (symmetric).  cap = capacity in doubles. */
+int orcvio_get_cov(orcvio_handle* h, double* P, int cap, int* D);
+/* getSwPoses, src/orcvio.cpp:3030-3042: per clone R (9, row-major) + p (3); ids optional. */
+int orcvio_get_window(orcvio_handle* h, double* poses12, long long* ids, double* times, int cap);
+/* getMSCKFMapPointPositions, src/orcvio.cpp:3059-3062 */
+int orcvio_get_map_points(orcvio_handle* h, long long* ids, double* xyz, int cap);
+int orcvio_get_frame_stats(orcvio_handle* h, OrcvioFrameStats* out);
+/* per-candidate log of the last frame: ids, phase (0 lost / 1 prune), status bits
+ * (1 = triangulation valid, 2 = gate pass), gamma. */
+int orcvio_get_candidate_log(orcvio_handle* h, long long* ids, int* phase, int* status, double* gamma,
+                             int cap);
+
+/* OrcVIO::constructObjectResidualJacobians, src/orcvio.cpp:2017-2151.
+ * jac_sensor: rows x 6, Hf: rows x odim, res: rows (all column-major, in); outputs
+ * Hx_out (rows x D), Hf_out (rows x odim), res_out with *rows_out valid rows.
+ * Returns 1 if at least one timestamp is in the window, 0 otherwise. */
+int orcvio_construct_object_jacobians(orcvio_handle* h, const double* jac_sensor, int rows,
+                                      const double* timestamps, int n_ts, const double* Hf, int odim,
+                                      const double* res, const int* zs_num, const double* cam_pose_se3,
+                                      double* Hx_out, double* Hf_out, double* res_out, int* rows_out);
+/* OrcVIO::removeLostObjects, src/orcvio.cpp:2154-2193.  Returns 1 updated, 0 rejected
+ * (status_out: 0 updated, 1 empty, 2 disabled, 3 nullspace fail, 4 gate fail, 5 nan). */
+int orcvio_remove_lost_objects(orcvio_handle* h, const double* Hx, const double* Hf, const double* res,
+                               int rows, int odim, int* status_out, double* gamma_out);
+/* test hooks, include/orcvio/orcvio.h:101-119 */
+int orcvio_set_state_cov(orcvio_handle* h, int imu_dim, int num_clone);
+int orcvio_set_win_pose_timestamps(orcvio_handle* h, const double* ts, int n);
+int orcvio_fix_dcampose_dimupose_to_i(orcvio_handle* h);
+/* overwrite the full filter state (parity tests start both sides from one snapshot) */
+int orcvio_set_cov(orcvio_handle* h, const double* P, int D);
+
+/* ---- multi-trajectory batch: n independent filters advanced in lock-step -- */
+orcvio_batch* orcvio_batch_create(const char* config_yaml_path, int n_filters);
+void orcvio_batch_destroy(orcvio_batch* b);
+int orcvio_batch_set_initial_state(orcvio_batch* b, int i, double t, const double quat_xyzw[4],
+                                   const double p[3], const double v[3], const double bg[3],
+                                   const double ba[3]);
+/* One frame for every filter.  feats/imu are concatenated per filter with CSR offsets
+ * (n_filters + 1 entries).  imu_used[i] receives the number of consumed IMU samples
+ * (the prefix the reference would erase).  published[i] = processFeatures' return. */
+int orcvio_batch_process(orcvio_batch* b, const double* t_img, const OrcvioFeature* feats,
+                         const int* feat_off, const OrcvioImu* imu, const int* imu_off, int* imu_used,
+                         int* published);
+int orcvio_batch_get_state(orcvio_batch* b, int i, OrcvioState* out);
+int orcvio_batch_get_cov(orcvio_batch* b, int i, double* P, int cap, int* D);
+int orcvio_batch_get_frame_stats(orcvio_batch* b, int i, OrcvioFrameStats* out);
+/* consumed MSCKF features (gate-passed, both phases) summed over filters since creation */
+long long orcvio_batch_feature_updates(orcvio_batch* b);
+/* number of kernel launches issued since creation */
+long long orcvio_batch_kernel_launches(orcvio_batch* b);
+
+/* ---- stage-level entry points on a frozen snapshot (parity tests, stress bench) ------- */
+/* Stage 1: Feature::checkMotion + triangulate_position (feature.hpp:353-396, 583-719) for
+ * n_feat features; feature f uses observations [feat_off[f], feat_off[f+1]) whose camera
+ * poses are cam_R (row-major 3x3, cam->world) / cam_t of clone obs_clone[k].
+ * out_pos: world positions (3 per feature), out_status bit0 = valid, out_iters: outer/inner
+ * iteration counts (2 per feature) for control-flow parity. */
+int orcvio_triangulate(const double* cam_R, const double* cam_t, int n_clones, const int* feat_off,
+                       const int* obs_clone, const double* obs_z, int n_feat, double translation_threshold,
+                       double cost_threshold, double init_final_dist_threshold, double* out_pos,
+                       int* out_status, int* out_iters, double* out_cost);
+
+/* Stages 1,2,4,5 on one frozen window ("stack -> compress -> update"):
+ * triangulate every feature, Jacobian + nullspace + gate, QR compression, EKF update of
+ * (state, P).  clone_R/clone_p: body poses; P: D x D with D = 22 + 6 n_clones.
+ * flags: bit0 use_larvio, bit1 use_left_perturbation, bit2 discard_large_update.
+ * Outputs (any may be NULL): P_out, delta_x (D), status per feature (bit0 tri valid, bit1
+ * gate pass), gamma per feature, positions, R_thin (6N x 6N column-major) and r_thin (6N),
+ * updated clone poses (N x 12).  timings_us[8]: device time per stage measured with CUDA
+ * events (tri, jac+gate, qr tiles, qr chain, update, total) when non-NULL. */
+int orcvio_snapshot_update(const double* clone_R, const double* clone_p, int n_clones,
+                           const double* R_b2c, const double* t_c_b, const double* P_in,
+                           const int* feat_off, const int* obs_clone, const double* obs_z, int n_feat,
+                           int flags, double noise_feature_var, double chi2_p,
+                           double translation_threshold, double cost_threshold,
+                           double init_final_dist_threshold, double* P_out, double* delta_x,
+                           int* status, double* gamma, double* positions, double* R_thin,
+                           double* r_thin, double* clone_out, float* timings_us, int repeat);
+
+/* Stage 2 only, for element-wise parity of J1 (measurementJacobian_msckf, orcvio.cpp:1071-1168):
+ * per observation H_x (2x6), H_e (2x6), H_f (2x3), r (2), row-major. */
+int orcvio_measurement_jacobians(const double* clone_R, const double* clone_p, int n_clones,
+                                 const double* R_b2c, const double* t_c_b, const double* positions,
+                                 const int* feat_off, const int* obs_clone, const double* obs_z,
+                                 int n_feat, int flags, double* Hx, double* He, double* Hf, double* r);
+
+/* Stage 3 (O1-O4): keypoint + bbox residuals and Jacobians of one object over T frames.
+ * frames_wTc: T x 16 (row-major 4x4), wTo 16, shape 3, kps K x 3, zs T x K x 2 (NaN = not
+ * observed), zb T x 4.  flags: bit0 left perturbation, bit1 new bbox residual.
+ * Outputs: fvec (rows), fjac_cam (rows x 6, column-major), fjac_obj (rows x (9+3K),
+ * column-major), zs_num (T), cam_pose_se3 (6 x T column-major), rows_out. */
+int orcvio_object_residuals(const double* frames_wTc, int T, const double* wTo, const double* shape,
+                            const double* kps, int K, const double* zs, const double* zb, int flags,
+                            double* fvec, double* fjac_cam, double* fjac_obj, int* zs_num,
+                            double* cam_pose_se3, int* rows_out);
+
+/* Stage 6: IMU propagation of (state, P) over n samples (processModel, orcvio.cpp:727-823).
+ * state16: R(9) v(3) p(3) + time at [15]; biases bg, ba; flags as above.
+ * noise4: gyro, acc, gyro-bias, acc-bias variances. */
+int orcvio_propagate(double* state16, const double* bg, const double* ba, const double* gyro_old,
+                     const double* acc_old, const OrcvioImu* imu, int n, double* P, int D, int flags,
+                     const double* noise4);
+
+/* device / build info */
+int orcvio_device_count(void);
+const char* orcvio_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ORCVIO_B200_H */

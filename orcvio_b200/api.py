@@ -1,0 +1,407 @@
+"""ctypes binding of liborcvio_b200.so: a host-side mirror of the reference's
+`orcvio::OrcVIO` class (include/orcvio/orcvio.h:39-119) plus the batch and stage-level
+entry points declared in include/orcvio_b200.h.
+
+Everything numerical happens in the CUDA library; this module only marshals NumPy arrays.
+If the library is missing it is built on import (nvcc); if it cannot be loaded the import
+fails loudly -- there is no Python/NumPy fallback path.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import build as _build
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIBPATH = os.path.join(_HERE, "lib", "liborcvio_b200.so")
+
+
+class OrcvioFeature(C.Structure):
+    _fields_ = [("id", C.c_ulonglong), ("u", C.c_double), ("v", C.c_double),
+                ("u_init", C.c_double), ("v_init", C.c_double),
+                ("u_vel", C.c_double), ("v_vel", C.c_double),
+                ("u_init_vel", C.c_double), ("v_init_vel", C.c_double)]
+
+
+class OrcvioImu(C.Structure):
+    _fields_ = [("t", C.c_double), ("gyro", C.c_double * 3), ("acc", C.c_double * 3)]
+
+
+class OrcvioState(C.Structure):
+    _fields_ = [("state_id", C.c_longlong), ("time", C.c_double), ("R", C.c_double * 9),
+                ("p", C.c_double * 3), ("v", C.c_double * 3), ("bg", C.c_double * 3),
+                ("ba", C.c_double * 3), ("P_pose", C.c_double * 36), ("P_vel", C.c_double * 9),
+                ("n_clones", C.c_int), ("dim", C.c_int), ("n_map_features", C.c_int)]
+
+
+class OrcvioFrameStats(C.Structure):
+    _fields_ = [("n_candidates_lost", C.c_int), ("n_tri_invalid_lost", C.c_int),
+                ("n_gate_pass_lost", C.c_int), ("n_candidates_prune", C.c_int),
+                ("n_tri_invalid_prune", C.c_int), ("n_gate_pass_prune", C.c_int),
+                ("n_removed_clones", C.c_int), ("removed_ids", C.c_longlong * 2), ("zupt", C.c_int)]
+
+
+FEAT_DTYPE = np.dtype([("id", "<u8"), ("u", "<f8"), ("v", "<f8"), ("u_init", "<f8"), ("v_init", "<f8"),
+                       ("u_vel", "<f8"), ("v_vel", "<f8"), ("u_init_vel", "<f8"), ("v_init_vel", "<f8")])
+IMU_DTYPE = np.dtype([("t", "<f8"), ("gyro", "<f8", 3), ("acc", "<f8", 3)])
+assert FEAT_DTYPE.itemsize == C.sizeof(OrcvioFeature) and IMU_DTYPE.itemsize == C.sizeof(OrcvioImu)
+
+_lib = None
+
+
+def lib():
+    """Load (building first if needed) the CUDA library.  Raises if that is impossible."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(_LIBPATH):
+        _build.build()
+    L = C.CDLL(_LIBPATH)
+    dp, ip, vp = C.POINTER(C.c_double), C.POINTER(C.c_int), C.c_void_p
+    L.orcvio_create.restype = vp
+    L.orcvio_create.argtypes = [C.c_char_p]
+    L.orcvio_destroy.argtypes = [vp]
+    L.orcvio_initialize.argtypes = [vp]
+    L.orcvio_set_initial_state.argtypes = [vp, C.c_double, dp, dp, dp, dp, dp]
+    L.orcvio_process_features.argtypes = [vp, C.c_double, vp, C.c_int, vp, ip]
+    L.orcvio_get_state.argtypes = [vp, C.POINTER(OrcvioState)]
+    L.orcvio_get_cov.argtypes = [vp, dp, C.c_int, ip]
+    L.orcvio_set_cov.argtypes = [vp, dp, C.c_int]
+    L.orcvio_get_window.argtypes = [vp, dp, C.POINTER(C.c_longlong), dp, C.c_int]
+    L.orcvio_get_frame_stats.argtypes = [vp, C.POINTER(OrcvioFrameStats)]
+    L.orcvio_get_candidate_log.argtypes = [vp, C.POINTER(C.c_longlong), ip, ip, dp, C.c_int]
+    L.orcvio_batch_create.restype = vp
+    L.orcvio_batch_create.argtypes = [C.c_char_p, C.c_int]
+    L.orcvio_batch_destroy.argtypes = [vp]
+    L.orcvio_batch_set_initial_state.argtypes = [vp, C.c_int, C.c_double, dp, dp, dp, dp, dp]
+    L.orcvio_batch_process.argtypes = [vp, dp, vp, ip, vp, ip, ip, ip]
+    L.orcvio_batch_get_state.argtypes = [vp, C.c_int, C.POINTER(OrcvioState)]
+    L.orcvio_batch_get_cov.argtypes = [vp, C.c_int, dp, C.c_int, ip]
+    L.orcvio_batch_get_frame_stats.argtypes = [vp, C.c_int, C.POINTER(OrcvioFrameStats)]
+    L.orcvio_batch_feature_updates.restype = C.c_longlong
+    L.orcvio_batch_feature_updates.argtypes = [vp]
+    L.orcvio_batch_kernel_launches.restype = C.c_longlong
+    L.orcvio_batch_kernel_launches.argtypes = [vp]
+    L.orcvio_batch_set_profiling.argtypes = [vp, C.c_int]
+    L.orcvio_batch_get_phase_times.argtypes = [vp, dp, C.POINTER(C.c_longlong)]
+    L.orcvio_chi2_quantile.restype = C.c_double
+    L.orcvio_chi2_quantile.argtypes = [C.c_double, C.c_int]
+    L.orcvio_version.restype = C.c_char_p
+    L.orcvio_triangulate.argtypes = [dp, dp, C.c_int, ip, ip, dp, C.c_int, C.c_double, C.c_double,
+                                     C.c_double, dp, ip, ip, dp]
+    L.orcvio_snapshot_update.argtypes = [dp, dp, C.c_int, dp, dp, dp, ip, ip, dp, C.c_int, C.c_int,
+                                         C.c_double, C.c_double, C.c_double, C.c_double, C.c_double,
+                                         dp, dp, ip, dp, dp, dp, dp, dp, C.POINTER(C.c_float), C.c_int]
+    L.orcvio_measurement_jacobians.argtypes = [dp, dp, C.c_int, dp, dp, dp, ip, ip, dp, C.c_int, C.c_int,
+                                               dp, dp, dp, dp]
+    L.orcvio_object_residuals.argtypes = [dp, C.c_int, dp, dp, dp, C.c_int, dp, dp, C.c_int, dp, dp, dp,
+                                          ip, dp, ip]
+    L.orcvio_construct_object_jacobians.argtypes = [vp, dp, C.c_int, dp, C.c_int, dp, C.c_int, dp, ip, dp,
+                                                    dp, dp, dp, ip]
+    L.orcvio_remove_lost_objects.argtypes = [vp, dp, dp, dp, C.c_int, C.c_int, ip, dp]
+    L.orcvio_set_state_cov.argtypes = [vp, C.c_int, C.c_int]
+    L.orcvio_set_win_pose_timestamps.argtypes = [vp, dp, C.c_int]
+    L.orcvio_fix_dcampose_dimupose_to_i.argtypes = [vp]
+    L.orcvio_propagate.argtypes = [dp, dp, dp, dp, dp, vp, C.c_int, dp, C.c_int, C.c_int, dp]
+    _lib = L
+    return L
+
+
+def _dp(a):
+    return a.ctypes.data_as(C.POINTER(C.c_double)) if a is not None else None
+
+
+def _ip(a):
+    return a.ctypes.data_as(C.POINTER(C.c_int)) if a is not None else None
+
+
+def _f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def _i32(a):
+    return np.ascontiguousarray(a, dtype=np.int32)
+
+
+def feats_array(feats):
+    """(k, 9) float array [id,u,v,u_init,v_init,u_vel,v_vel,u_init_vel,v_init_vel] -> struct array."""
+    feats = np.asarray(feats, dtype=np.float64).reshape(-1, 9)
+    out = np.zeros(feats.shape[0], dtype=FEAT_DTYPE)
+    out["id"] = feats[:, 0].astype(np.uint64)
+    for k, name in enumerate(FEAT_DTYPE.names[1:], start=1):
+        out[name] = feats[:, k]
+    return out
+
+
+def imu_array(imu):
+    """(n, 7) float array [t, w, a] -> struct array."""
+    imu = np.asarray(imu, dtype=np.float64).reshape(-1, 7)
+    out = np.zeros(imu.shape[0], dtype=IMU_DTYPE)
+    out["t"] = imu[:, 0]
+    out["gyro"] = imu[:, 1:4]
+    out["acc"] = imu[:, 4:7]
+    return out
+
+
+class OrcVIO:
+    """Mirror of orcvio::OrcVIO for the filter-update path (same method names)."""
+
+    def __init__(self, config_file):
+        self._L = lib()
+        self._h = self._L.orcvio_create(str(config_file).encode())
+        self._imu = np.zeros(0, dtype=IMU_DTYPE)     # the caller-owned imu_msg_buffer
+
+    def __del__(self):
+        try:
+            if self._h:
+                self._L.orcvio_destroy(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+    def initialize(self):
+        return bool(self._L.orcvio_initialize(self._h))
+
+    def set_initial_state(self, t, quat_xyzw, p, v, bg=(0, 0, 0), ba=(0, 0, 0)):
+        a = [_f64(x) for x in (quat_xyzw, p, v, bg, ba)]
+        return self._L.orcvio_set_initial_state(self._h, float(t), *[_dp(x) for x in a])
+
+    def push_imu(self, imu):
+        """Append samples to the IMU buffer (the reference's caller does imu_msg_buffer.push_back)."""
+        self._imu = np.concatenate([self._imu, imu_array(imu)])
+
+    def processFeatures(self, t_img, feats):
+        f = feats if (isinstance(feats, np.ndarray) and feats.dtype == FEAT_DTYPE) else feats_array(feats)
+        n = C.c_int(len(self._imu))
+        buf = np.ascontiguousarray(self._imu)
+        rc = self._L.orcvio_process_features(self._h, float(t_img), f.ctypes.data, len(f), buf.ctypes.data,
+                                             C.byref(n))
+        if rc < 0:
+            raise RuntimeError(f"orcvio_process_features failed: {rc}")
+        self._imu = buf[:n.value].copy()
+        return bool(rc)
+
+    def state(self):
+        s = OrcvioState()
+        rc = self._L.orcvio_get_state(self._h, C.byref(s))
+        if rc != 0:
+            raise RuntimeError(f"orcvio_get_state failed: {rc}")
+        return s
+
+    def cov(self):
+        d = C.c_int(0)
+        self._L.orcvio_get_cov(self._h, None, 0, C.byref(d))
+        P = np.zeros((d.value, d.value))
+        rc = self._L.orcvio_get_cov(self._h, _dp(P), P.size, C.byref(d))
+        if rc != 0:
+            raise RuntimeError(f"orcvio_get_cov failed: {rc}")
+        return P
+
+    def set_cov(self, P):
+        P = _f64(P)
+        return self._L.orcvio_set_cov(self._h, _dp(P), P.shape[0])
+
+    def window(self):
+        cap = 64
+        poses = np.zeros((cap, 12))
+        ids = np.zeros(cap, dtype=np.int64)
+        times = np.zeros(cap)
+        n = self._L.orcvio_get_window(self._h, _dp(poses), ids.ctypes.data_as(C.POINTER(C.c_longlong)),
+                                      _dp(times), cap)
+        return poses[:n], ids[:n], times[:n]
+
+    def frame_stats(self):
+        s = OrcvioFrameStats()
+        self._L.orcvio_get_frame_stats(self._h, C.byref(s))
+        return s
+
+    def candidate_log(self, cap=65536):
+        ids = np.zeros(cap, dtype=np.int64)
+        ph = np.zeros(cap, dtype=np.int32)
+        st = np.zeros(cap, dtype=np.int32)
+        g = np.zeros(cap)
+        n = self._L.orcvio_get_candidate_log(self._h, ids.ctypes.data_as(C.POINTER(C.c_longlong)), _ip(ph),
+                                             _ip(st), _dp(g), cap)
+        return ids[:n], ph[:n], st[:n], g[:n]
+
+    # -- object path (stage 3, filter side)
+    def setStateCov(self, imu_dim, num_clone):
+        return self._L.orcvio_set_state_cov(self._h, imu_dim, num_clone)
+
+    def setWinPoseTimestamps(self, ts):
+        ts = _f64(ts)
+        return self._L.orcvio_set_win_pose_timestamps(self._h, _dp(ts), len(ts))
+
+    def fixDcamposeDimuposeToI(self):
+        return self._L.orcvio_fix_dcampose_dimupose_to_i(self._h)
+
+    def constructObjectResidualJacobians(self, jac_sensor, timestamps, Hf, res, zs_num, cam_pose_se3):
+        jac = np.asfortranarray(jac_sensor, dtype=np.float64)
+        Hf_ = np.asfortranarray(Hf, dtype=np.float64)
+        res_ = _f64(res)
+        ts = _f64(timestamps)
+        zn = _i32(zs_num)
+        se3 = np.asfortranarray(cam_pose_se3, dtype=np.float64)
+        rows, odim = Hf_.shape
+        d = C.c_int(0)
+        self._L.orcvio_get_cov(self._h, None, 0, C.byref(d))
+        Hx_o = np.zeros((rows, d.value), order="F")
+        Hf_o = np.zeros((rows, odim), order="F")
+        res_o = np.zeros(rows)
+        ro = C.c_int(0)
+        flag = self._L.orcvio_construct_object_jacobians(
+            self._h, _dp(jac), rows, _dp(ts), len(ts), _dp(Hf_), odim, _dp(res_), _ip(zn), _dp(se3),
+            _dp(Hx_o), _dp(Hf_o), _dp(res_o), C.byref(ro))
+        if flag < 0:
+            raise RuntimeError(f"orcvio_construct_object_jacobians failed: {flag}")
+        n = ro.value
+        return bool(flag), Hx_o[:n], Hf_o[:n], res_o[:n]
+
+    def removeLostObjects(self, Hx, Hf, res):
+        Hx_ = np.asfortranarray(Hx, dtype=np.float64)
+        Hf_ = np.asfortranarray(Hf, dtype=np.float64)
+        res_ = _f64(res)
+        st = C.c_int(0)
+        g = C.c_double(0)
+        rc = self._L.orcvio_remove_lost_objects(self._h, _dp(Hx_), _dp(Hf_), _dp(res_), Hx_.shape[0],
+                                                Hf_.shape[1], C.byref(st), C.byref(g))
+        if rc < 0:
+            raise RuntimeError(f"orcvio_remove_lost_objects failed: {rc}")
+        return st.value, g.value
+
+
+class Batch:
+    """n independent filters advanced in lock-step (multi-trajectory mode)."""
+
+    def __init__(self, config_file, n):
+        self._L = lib()
+        self.n = n
+        self._h = self._L.orcvio_batch_create(str(config_file).encode(), n)
+        if not self._h:
+            raise RuntimeError("orcvio_batch_create failed (no CUDA device or unsupported config)")
+
+    def __del__(self):
+        try:
+            if self._h:
+                self._L.orcvio_batch_destroy(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+    def set_initial_state(self, i, t, quat_xyzw, p, v, bg=(0, 0, 0), ba=(0, 0, 0)):
+        a = [_f64(x) for x in (quat_xyzw, p, v, bg, ba)]
+        return self._L.orcvio_batch_set_initial_state(self._h, i, float(t), *[_dp(x) for x in a])
+
+    def process(self, t_img, feats, feat_off, imu, imu_off):
+        """feats / imu: struct arrays concatenated over filters, *_off CSR offsets (n+1)."""
+        t_img = _f64(t_img)
+        feat_off = _i32(feat_off)
+        imu_off = _i32(imu_off)
+        used = np.zeros(self.n, dtype=np.int32)
+        pub = np.zeros(self.n, dtype=np.int32)
+        rc = self._L.orcvio_batch_process(self._h, _dp(t_img), feats.ctypes.data, _ip(feat_off),
+                                          imu.ctypes.data, _ip(imu_off), _ip(used), _ip(pub))
+        if rc != 0:
+            raise RuntimeError(f"orcvio_batch_process failed: {rc}")
+        return used, pub
+
+    def state(self, i):
+        s = OrcvioState()
+        self._L.orcvio_batch_get_state(self._h, i, C.byref(s))
+        return s
+
+    def cov(self, i):
+        d = C.c_int(0)
+        self._L.orcvio_batch_get_cov(self._h, i, None, 0, C.byref(d))
+        P = np.zeros((d.value, d.value))
+        self._L.orcvio_batch_get_cov(self._h, i, _dp(P), P.size, C.byref(d))
+        return P
+
+    def frame_stats(self, i):
+        s = OrcvioFrameStats()
+        self._L.orcvio_batch_get_frame_stats(self._h, i, C.byref(s))
+        return s
+
+    def feature_updates(self):
+        return int(self._L.orcvio_batch_feature_updates(self._h))
+
+    def kernel_launches(self):
+        return int(self._L.orcvio_batch_kernel_launches(self._h))
+
+    def set_profiling(self, on):
+        self._L.orcvio_batch_set_profiling(self._h, int(on))
+
+    def phase_times(self):
+        ms = np.zeros(6)
+        n = np.zeros(6, dtype=np.int64)
+        self._L.orcvio_batch_get_phase_times(self._h, _dp(ms), n.ctypes.data_as(C.POINTER(C.c_longlong)))
+        names = ["tri", "jac_gate", "qr_tiles", "qr_chain", "update", "propagate"]
+        return {k: (float(ms[i]), int(n[i])) for i, k in enumerate(names)}
+
+
+# ---------------------------------------------------------------- stage-level calls
+def triangulate(cam_R, cam_t, feat_off, obs_clone, obs_z, translation_threshold=-1.0,
+                cost_threshold=4.7673e-4, init_final_dist_threshold=5.0):
+    L = lib()
+    cam_R, cam_t, obs_z = _f64(cam_R).reshape(-1, 9), _f64(cam_t).reshape(-1, 3), _f64(obs_z).reshape(-1, 2)
+    feat_off, obs_clone = _i32(feat_off), _i32(obs_clone)
+    nf = len(feat_off) - 1
+    pos = np.zeros((nf, 3))
+    st = np.zeros(nf, dtype=np.int32)
+    it = np.zeros((nf, 2), dtype=np.int32)
+    cost = np.zeros(nf)
+    rc = L.orcvio_triangulate(_dp(cam_R), _dp(cam_t), cam_R.shape[0], _ip(feat_off), _ip(obs_clone), _dp(obs_z),
+                              nf, translation_threshold, cost_threshold, init_final_dist_threshold, _dp(pos),
+                              _ip(st), _ip(it), _dp(cost))
+    if rc != 0:
+        raise RuntimeError(f"orcvio_triangulate failed: {rc}")
+    return pos, st, it, cost
+
+
+def snapshot_update(snap, flags=0, noise_var=None, chi2_p=0.95, translation_threshold=-1.0,
+                    cost_threshold=4.7673e-4, init_final_dist_threshold=5.0, repeat=1):
+    """snap: dict from synth.stress_snapshot (clone_R, clone_p, P, R_b2c, t_c_b, feat_off, ...)."""
+    L = lib()
+    N = int(snap["n_clones"])
+    D = 22 + 6 * N
+    clone_R, clone_p = _f64(snap["clone_R"]).reshape(N, 9), _f64(snap["clone_p"]).reshape(N, 3)
+    Rbc, tcb = _f64(snap["R_b2c"]).reshape(9), _f64(snap["t_c_b"]).reshape(3)
+    P = np.asfortranarray(snap["P"], dtype=np.float64)
+    feat_off, obs_clone = _i32(snap["feat_off"]), _i32(snap["obs_clone"])
+    obs_z = _f64(snap["obs_z"]).reshape(-1, 2)
+    nf = len(feat_off) - 1
+    out = dict(P=np.zeros((D, D), order="F"), delta_x=np.zeros(D), status=np.zeros(nf, dtype=np.int32),
+               gamma=np.zeros(nf), positions=np.zeros((nf, 3)), R_thin=np.zeros((6 * N, 6 * N), order="F"),
+               r_thin=np.zeros(6 * N), clones=np.zeros((N, 12)), timings_us=np.zeros(8, dtype=np.float32))
+    if noise_var is None:
+        noise_var = float(snap["cfg"]["noise_feature"]) ** 2
+    rc = L.orcvio_snapshot_update(
+        _dp(clone_R), _dp(clone_p), N, _dp(Rbc), _dp(tcb), _dp(P), _ip(feat_off), _ip(obs_clone), _dp(obs_z),
+        nf, flags, noise_var, chi2_p, translation_threshold, cost_threshold, init_final_dist_threshold,
+        _dp(out["P"]), _dp(out["delta_x"]), _ip(out["status"]), _dp(out["gamma"]), _dp(out["positions"]),
+        _dp(out["R_thin"]), _dp(out["r_thin"]), _dp(out["clones"]),
+        out["timings_us"].ctypes.data_as(C.POINTER(C.c_float)), repeat)
+    if rc != 0:
+        raise RuntimeError(f"orcvio_snapshot_update failed: {rc}")
+    return out
+
+
+def measurement_jacobians(clone_R, clone_p, R_b2c, t_c_b, positions, feat_off, obs_clone, obs_z, flags=0):
+    L = lib()
+    clone_R, clone_p = _f64(clone_R).reshape(-1, 9), _f64(clone_p).reshape(-1, 3)
+    positions, obs_z = _f64(positions).reshape(-1, 3), _f64(obs_z).reshape(-1, 2)
+    feat_off, obs_clone = _i32(feat_off), _i32(obs_clone)
+    Rbc, tcb = _f64(R_b2c).reshape(9), _f64(t_c_b).reshape(3)
+    no = len(obs_clone)
+    Hx, He, Hf, r = np.zeros((no, 2, 6)), np.zeros((no, 2, 6)), np.zeros((no, 2, 3)), np.zeros((no, 2))
+    rc = L.orcvio_measurement_jacobians(_dp(clone_R), _dp(clone_p), clone_R.shape[0], _dp(Rbc), _dp(tcb),
+                                        _dp(positions), _ip(feat_off), _ip(obs_clone), _dp(obs_z),
+                                        len(feat_off) - 1, flags, _dp(Hx), _dp(He), _dp(Hf), _dp(r))
+    if rc != 0:
+        raise RuntimeError(f"orcvio_measurement_jacobians failed: {rc}")
+    return Hx, He, Hf, r
+
+
+def chi2_quantile(p, dof):
+    return float(lib().orcvio_chi2_quantile(float(p), int(dof)))

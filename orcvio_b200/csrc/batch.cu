@@ -1,0 +1,1144 @@
+// Host orchestration of a batch of filters.  See batch.h.
+//
+// Mirrors, function by function, the host-visible control flow of the reference:
+//   processFeatures        src/orcvio.cpp:500-661
+//   batchImuProcessing     :664-724   (sample selection on the host, arithmetic in k_propagate)
+//   addFeatureObservations :1016-1068
+//   stateAugmentation      :930-1013  (bookkeeping here, covariance in k_augment)
+//   removeLostFeatures     :2196-2579 (classification here; triangulation, Jacobians, gate,
+//                                      compression and update on the GPU)
+//   findRedundantImuStates :2582-2626
+//   pruneImuStateBuffer    :2629-2959
+#include "batch.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+
+namespace ob {
+
+#define CK(call)                                                                                  \
+  do {                                                                                            \
+    cudaError_t e__ = (call);                                                                     \
+    if (e__ != cudaSuccess) {                                                                     \
+      std::fprintf(stderr, "[orcvio_b200] CUDA error %s at %s:%d\n", cudaGetErrorString(e__),     \
+                   __FILE__, __LINE__);                                                           \
+      err_ = cudaGetErrorString(e__);                                                             \
+      ok_ = false;                                                                                \
+    }                                                                                             \
+  } while (0)
+
+struct Batch::PhaseWork {
+  std::vector<Cand> cands;
+  std::vector<int> obs_clone;
+  std::vector<double> obs_z;
+  std::vector<Tile> tiles;
+  std::vector<FilterWork> fw;
+  std::vector<int> small_list, large_list;
+  size_t hblk_total = 0, rows_total = 0, tileout_total = 0, tile_smem_doubles = 0;
+  int wmax_blk = 1;
+  int maxN = 0;
+  std::vector<int> cand_begin;   // per filter, size B + 1
+  bool any_active = false;
+  std::vector<int> extra_ints;   // uploaded alongside (clone removal indices)
+  const int* d_extra = nullptr;
+};
+
+static constexpr int WTILE_MAX_BLK = 8;   // widest clone window a tile may span (blocks)
+
+Batch::Batch(const Params& p, int n) : p_(p), B_(n) {
+  ok_ = true;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    err_ = "no CUDA device: orcvio_b200 has no CPU fallback";
+    std::fprintf(stderr, "[orcvio_b200] %s\n", err_.c_str());
+    ok_ = false;
+    return;
+  }
+  Ncap_ = p_.sw_size + 1;
+  if (Ncap_ > ORCVIO_MAX_OBS) {
+    err_ = "sw_size too large (max 31)";
+    ok_ = false;
+    return;
+  }
+  ldp_ = ((ORCVIO_LEG + 6 * Ncap_ + 7) / 8) * 8;
+  ldr_ = ((6 * Ncap_ + 1 + 7) / 8) * 8;
+  ldt_ = ldp_;
+  Fcap_ = 4096;
+  flags_ = (p_.use_larvio_flag ? FL_LARVIO : 0) | (p_.use_left_perturbation_flag ? FL_LEFT : 0) |
+           (p_.discard_large_update_flag ? FL_DISCARD_LARGE : 0);
+  tricfg_.translation_threshold = p_.feature_translation_threshold;
+  tricfg_.huber_epsilon = 0.01;
+  tricfg_.estimation_precision = 5e-7;
+  tricfg_.initial_damping = 1e-3;
+  tricfg_.outer_max = 10;
+  tricfg_.inner_max = 10;
+  tricfg_.cost_threshold = p_.feature_cost_threshold;
+  tricfg_.init_final_dist_threshold = p_.init_final_dist_threshold;
+  f_.resize(B_);
+  for (auto& F : f_) {
+    F.imu_mirror.assign(IM_STRIDE, 0.0);
+    F.clone_mirror.assign((size_t)Ncap_ * CL_STRIDE, 0.0);
+    F.free_slots.reserve(Fcap_);
+    for (int s = Fcap_ - 1; s >= 0; --s) F.free_slots.push_back(s);
+  }
+  CK(cudaStreamCreate(&stream_));
+  for (auto& e : ev_) CK(cudaEventCreate(&e));
+  const size_t nB = (size_t)B_;
+  CK(cudaMalloc(&dP_, nB * ldp_ * ldp_ * sizeof(double)));
+  CK(cudaMemset(dP_, 0, nB * ldp_ * ldp_ * sizeof(double)));
+  CK(cudaMalloc(&dImu_, nB * IM_STRIDE * sizeof(double)));
+  CK(cudaMemset(dImu_, 0, nB * IM_STRIDE * sizeof(double)));
+  CK(cudaMalloc(&dClones_, nB * Ncap_ * CL_STRIDE * sizeof(double)));
+  CK(cudaMemset(dClones_, 0, nB * Ncap_ * CL_STRIDE * sizeof(double)));
+  CK(cudaMalloc(&dFpos_, nB * Fcap_ * FP_STRIDE * sizeof(double)));
+  CK(cudaMemset(dFpos_, 0, nB * Fcap_ * FP_STRIDE * sizeof(double)));
+  CK(cudaMalloc(&dFgen_, nB * Fcap_ * sizeof(long long)));
+  CK(cudaMemset(dFgen_, 0xFF, nB * Fcap_ * sizeof(long long)));
+  const int ncap = 6 * Ncap_;
+  CK(cudaMalloc(&dR_, nB * (size_t)(ncap + 1) * ldr_ * sizeof(double)));
+  CK(cudaMalloc(&dS_, nB * (size_t)(ncap + 1) * ldr_ * sizeof(double)));
+  CK(cudaMalloc(&dRthin_, nB * ldr_ * sizeof(double)));
+  CK(cudaMalloc(&dYv_, nB * ldr_ * sizeof(double)));
+  CK(cudaMalloc(&dT_, nB * (size_t)ncap * ldt_ * sizeof(double)));
+  CK(cudaMalloc(&dDx_, nB * ldp_ * sizeof(double)));
+  CK(cudaMemset(dDx_, 0, nB * ldp_ * sizeof(double)));
+  CK(cudaMalloc(&dErr_, sizeof(int)));
+  CK(cudaMemset(dErr_, 0, sizeof(int)));
+  // global fallback front for very wide windows (long tracks): 2*(6 Ncap)+8 rows
+  front_stride_ = (size_t)(2 * ncap + 8) * (size_t)(256 + 2);
+  CK(cudaMalloc(&dFront_, nB * front_stride_ * sizeof(double)));
+  chi2_host_.assign(500, 0.0);
+  for (int i = 1; i < 500; ++i) chi2_host_[i] = chi2_quantile(p_.chi_square_threshold_feat, i);
+  CK(cudaMalloc(&dChi2_, 500 * sizeof(double)));
+  CK(cudaMemcpy(dChi2_, chi2_host_.data(), 500 * sizeof(double), cudaMemcpyHostToDevice));
+  CK(cudaMallocHost(&hImu_, nB * IM_STRIDE * sizeof(double)));
+  CK(cudaMallocHost(&hClones_, nB * Ncap_ * CL_STRIDE * sizeof(double)));
+  CK(cudaMallocHost(&hDx_, nB * ldp_ * sizeof(double)));
+  std::memset(hImu_, 0, nB * IM_STRIDE * sizeof(double));
+}
+
+Batch::~Batch() {
+  cudaDeviceSynchronize();
+  cudaFree(dP_); cudaFree(dImu_); cudaFree(dClones_); cudaFree(dFpos_); cudaFree(dFgen_);
+  cudaFree(dR_); cudaFree(dS_); cudaFree(dRthin_); cudaFree(dYv_); cudaFree(dT_); cudaFree(dDx_);
+  cudaFree(dErr_); cudaFree(dFront_); cudaFree(dChi2_);
+  cudaFree(dHblk_); cudaFree(dRblk_); cudaFree(dTileOut_); cudaFree(dStatus_); cudaFree(dGamma_);
+  if (blob_.dev) cudaFree(blob_.dev);
+  if (blob_.pinned) cudaFreeHost(blob_.pinned);
+  cudaFreeHost(hImu_); cudaFreeHost(hClones_); cudaFreeHost(hDx_);
+  if (hStatus_) cudaFreeHost(hStatus_);
+  if (hGamma_) cudaFreeHost(hGamma_);
+  for (auto& e : ev_) cudaEventDestroy(e);
+  if (stream_) cudaStreamDestroy(stream_);
+}
+
+void Batch::set_initial_state(int i, double t, const double* q, const double* p, const double* v,
+                              const double* bg, const double* ba) {
+  FilterHost& F = f_[i];
+  F.has_init = true;
+  F.init_t = t;
+  for (int k = 0; k < 4; ++k) F.init_q[k] = q[k];
+  for (int k = 0; k < 3; ++k) {
+    F.init_p[k] = p[k];
+    F.init_v[k] = v[k];
+    F.init_bg[k] = bg ? bg[k] : 0.0;
+    F.init_ba[k] = ba ? ba[k] : 0.0;
+  }
+}
+
+// Write the initial IMU record and covariance of filter i (reference :514-523, :201-225).
+void Batch::init_filter_device(int i) {
+  FilterHost& F = f_[i];
+  double* im = hImu_ + (size_t)i * IM_STRIDE;
+  std::memset(im, 0, IM_STRIDE * sizeof(double));
+  quat_xyzw_to_R(F.init_q, im + IM_R);
+  for (int k = 0; k < 3; ++k) {
+    im[IM_V + k] = F.init_v[k];
+    im[IM_P + k] = F.init_p[k];
+    im[IM_BG + k] = F.init_bg[k];
+    im[IM_BA + k] = F.init_ba[k];
+    im[IM_TCB + k] = p_.t_cam0_imu[k];
+  }
+  for (int k = 0; k < 9; ++k) im[IM_RBC + k] = p_.R_imu_cam0[k];
+  im[IM_TD] = p_.td;
+  im[IM_TIME] = F.init_t;
+  std::vector<double> P((size_t)ldp_ * ldp_, 0.0);
+  auto diag = [&](int a, int b, double v) { for (int k = a; k < b; ++k) P[(size_t)k * ldp_ + k] = v; };
+  diag(0, 3, p_.cov_orientation);
+  diag(3, 6, p_.cov_velocity);
+  diag(6, 9, p_.cov_position);
+  diag(9, 12, p_.cov_gyro_bias);
+  diag(12, 15, p_.cov_acc_bias);
+  CK(cudaMemcpy(dP_ + (size_t)i * ldp_ * ldp_, P.data(), P.size() * sizeof(double), cudaMemcpyHostToDevice));
+}
+
+void Batch::ensure_scratch(size_t n_cand, size_t hblk, size_t rblk, size_t tileout) {
+  auto grow = [&](double*& ptr, size_t& cap, size_t need) {
+    if (need <= cap) return;
+    if (ptr) cudaFree(ptr);
+    cap = need * 2 + 1024;
+    CK(cudaMalloc(&ptr, cap * sizeof(double)));
+  };
+  grow(dHblk_, hblk_cap_, hblk);
+  grow(dRblk_, rblk_cap_, rblk);
+  grow(dTileOut_, tileout_cap_, tileout);
+  if (n_cand > cand_cap_) {
+    if (dStatus_) cudaFree(dStatus_);
+    if (dGamma_) cudaFree(dGamma_);
+    cand_cap_ = n_cand * 2 + 1024;
+    CK(cudaMalloc(&dStatus_, cand_cap_ * sizeof(int)));
+    CK(cudaMalloc(&dGamma_, cand_cap_ * sizeof(double)));
+  }
+  if (n_cand > hcand_cap_) {
+    if (hStatus_) cudaFreeHost(hStatus_);
+    if (hGamma_) cudaFreeHost(hGamma_);
+    hcand_cap_ = n_cand * 2 + 1024;
+    CK(cudaMallocHost(&hStatus_, hcand_cap_ * sizeof(int)));
+    CK(cudaMallocHost(&hGamma_, hcand_cap_ * sizeof(double)));
+  }
+}
+
+void Batch::upload_blob() {
+  if (blob_.used == 0) return;
+  if (blob_.used > blob_.dev_cap) {
+    if (blob_.dev) cudaFree(blob_.dev);
+    blob_.dev_cap = blob_.used * 2 + 4096;
+    CK(cudaMalloc(&blob_.dev, blob_.dev_cap));
+  }
+  if (blob_.used > blob_.pinned_cap) {
+    if (blob_.pinned) cudaFreeHost(blob_.pinned);
+    blob_.pinned_cap = blob_.used * 2 + 4096;
+    CK(cudaMallocHost(&blob_.pinned, blob_.pinned_cap));
+  }
+  std::memcpy(blob_.pinned, blob_.host.data(), blob_.used);
+  CK(cudaMemcpyAsync(blob_.dev, blob_.pinned, blob_.used, cudaMemcpyHostToDevice, stream_));
+}
+
+void Batch::download_mirrors() {
+  CK(cudaMemcpyAsync(hImu_, dImu_, (size_t)B_ * IM_STRIDE * sizeof(double), cudaMemcpyDeviceToHost, stream_));
+  CK(cudaMemcpyAsync(hClones_, dClones_, (size_t)B_ * Ncap_ * CL_STRIDE * sizeof(double),
+                     cudaMemcpyDeviceToHost, stream_));
+}
+
+// ---------------------------------------------------------------------------------------
+// Build tiles for the candidates [c0, c1) of one filter (already sorted by s_blk).
+static void build_tiles(Batch::PhaseWork& w, int fi, int c0, int c1);
+
+struct CandBuild {
+  Cand c;
+  long long id;
+  int kind;
+};
+
+void Batch::run_phase(PhaseWork& w, int phase) {
+  const int nC = (int)w.cands.size();
+  blob_.reset();
+  const size_t o_c = blob_.reserve(sizeof(Cand) * std::max(nC, 1));
+  const size_t o_oc = blob_.reserve(sizeof(int) * std::max<size_t>(w.obs_clone.size(), 1));
+  const size_t o_oz = blob_.reserve(sizeof(double) * std::max<size_t>(w.obs_z.size(), 1));
+  const size_t o_t = blob_.reserve(sizeof(Tile) * std::max<size_t>(w.tiles.size(), 1));
+  const size_t o_f = blob_.reserve(sizeof(FilterWork) * B_);
+  const size_t o_s = blob_.reserve(sizeof(int) * std::max<size_t>(w.small_list.size(), 1));
+  const size_t o_l = blob_.reserve(sizeof(int) * std::max<size_t>(w.large_list.size(), 1));
+  const size_t o_x = blob_.reserve(sizeof(int) * std::max<size_t>(w.extra_ints.size(), 1));
+  char* h = blob_.host.data();
+  if (!w.extra_ints.empty()) std::memcpy(h + o_x, w.extra_ints.data(), sizeof(int) * w.extra_ints.size());
+  if (nC) std::memcpy(h + o_c, w.cands.data(), sizeof(Cand) * nC);
+  if (!w.obs_clone.empty()) std::memcpy(h + o_oc, w.obs_clone.data(), sizeof(int) * w.obs_clone.size());
+  if (!w.obs_z.empty()) std::memcpy(h + o_oz, w.obs_z.data(), sizeof(double) * w.obs_z.size());
+  if (!w.tiles.empty()) std::memcpy(h + o_t, w.tiles.data(), sizeof(Tile) * w.tiles.size());
+  std::memcpy(h + o_f, w.fw.data(), sizeof(FilterWork) * B_);
+  if (!w.small_list.empty()) std::memcpy(h + o_s, w.small_list.data(), sizeof(int) * w.small_list.size());
+  if (!w.large_list.empty()) std::memcpy(h + o_l, w.large_list.data(), sizeof(int) * w.large_list.size());
+  ensure_scratch(std::max(nC, 1), std::max<size_t>(w.hblk_total, 1), std::max<size_t>(w.rows_total, 1),
+                 std::max<size_t>(w.tileout_total, 1));
+  upload_blob();
+  char* d = blob_.dev;
+  const Cand* dC = (const Cand*)(d + o_c);
+  const int* dOc = (const int*)(d + o_oc);
+  const double* dOz = (const double*)(d + o_oz);
+  const Tile* dTiles = (const Tile*)(d + o_t);
+  const FilterWork* dFw = (const FilterWork*)(d + o_f);
+  const int* dSmall = (const int*)(d + o_s);
+  const int* dLarge = (const int*)(d + o_l);
+  w.d_extra = (const int*)(d + o_x);
+
+  int nl = 0;
+  cudaEvent_t* e = ev_;
+  if (profiling_) CK(cudaEventRecord(e[0], stream_));
+  if (want_iters_ && (size_t)nC > iters_cap_) {
+    if (dIters_) cudaFree(dIters_);
+    if (dCost_) cudaFree(dCost_);
+    iters_cap_ = (size_t)nC * 2 + 64;
+    CK(cudaMalloc(&dIters_, iters_cap_ * 2 * sizeof(int)));
+    CK(cudaMalloc(&dCost_, iters_cap_ * sizeof(double)));
+  }
+  if (want_raw_ && w.obs_clone.size() > raw_cap_) {
+    for (double** p : {&dRawHx_, &dRawHe_, &dRawHf_, &dRawR_})
+      if (*p) cudaFree(*p);
+    raw_cap_ = w.obs_clone.size() * 2 + 64;
+    CK(cudaMalloc(&dRawHx_, raw_cap_ * 12 * sizeof(double)));
+    CK(cudaMalloc(&dRawHe_, raw_cap_ * 12 * sizeof(double)));
+    CK(cudaMalloc(&dRawHf_, raw_cap_ * 6 * sizeof(double)));
+    CK(cudaMalloc(&dRawR_, raw_cap_ * 2 * sizeof(double)));
+  }
+  if (nC > 0 && !skip_tri_) {
+    TriArgs ta{};
+    ta.cand = dC; ta.n_cand = nC;
+    ta.clones = dClones_; ta.clone_stride = (size_t)Ncap_ * CL_STRIDE;
+    ta.fpos = dFpos_; ta.fgen = dFgen_; ta.fcap = Fcap_;
+    ta.obs_clone = dOc; ta.obs_z = dOz;
+    ta.cfg = tricfg_;
+    ta.status = dStatus_;
+    ta.iters = want_iters_ ? dIters_ : nullptr;
+    ta.cost = want_iters_ ? dCost_ : nullptr;
+    launch_triangulate(ta, stream_);
+    ++nl;
+  }
+  if (profiling_) CK(cudaEventRecord(e[1], stream_));
+  if (nC > 0 && !skip_jac_) {
+    JacArgs ja{};
+    ja.cand = dC;
+    ja.clones = dClones_; ja.clone_stride = (size_t)Ncap_ * CL_STRIDE;
+    ja.imu = dImu_; ja.fpos = dFpos_; ja.fcap = Fcap_;
+    ja.P = dP_; ja.p_stride = (size_t)ldp_ * ldp_; ja.ldp = ldp_;
+    ja.obs_clone = dOc; ja.obs_z = dOz;
+    ja.flags = flags_; ja.sigma2 = p_.feature_observation_noise; ja.chi2 = dChi2_;
+    ja.status = dStatus_; ja.gamma = dGamma_;
+    ja.hblk = dHblk_; ja.rblk = dRblk_;
+    if (want_raw_) { ja.raw_Hx = dRawHx_; ja.raw_He = dRawHe_; ja.raw_Hf = dRawHf_; ja.raw_r = dRawR_; }
+    JacArgs js = ja, jl = ja;
+    js.cand_list = dSmall; js.n_list = (int)w.small_list.size();
+    jl.cand_list = dLarge; jl.n_list = (int)w.large_list.size();
+    launch_jac_gate(js, jl, stream_);
+    nl += (js.n_list > 0) + (jl.n_list > 0);
+  }
+  if (profiling_) CK(cudaEventRecord(e[2], stream_));
+  if (w.any_active && !skip_update_) {
+    QrArgs qa{};
+    qa.cand = dC; qa.status = dStatus_;
+    qa.hblk = dHblk_; qa.rblk = dRblk_;
+    qa.tiles = dTiles; qa.n_tiles = (int)w.tiles.size();
+    qa.tile_out = dTileOut_;
+    qa.fw = dFw; qa.n_filters = B_;
+    qa.Rm = dR_; qa.rthin = dRthin_; qa.r_stride = (size_t)(6 * Ncap_ + 1) * ldr_; qa.ldr = ldr_;
+    qa.front_scratch = dFront_; qa.front_stride = front_stride_;
+    qa.err = dErr_;
+    launch_qr(qa, w.tile_smem_doubles, w.wmax_blk, 6 * w.maxN, stream_, &nl, profiling_ ? e[3] : nullptr);
+    if (profiling_) CK(cudaEventRecord(e[4], stream_));
+    UpdArgs ua{};
+    ua.fw = dFw; ua.n_filters = B_;
+    ua.P = dP_; ua.p_stride = (size_t)ldp_ * ldp_; ua.ldp = ldp_;
+    ua.Rm = dR_; ua.rthin = dRthin_; ua.r_stride = qa.r_stride; ua.ldr = ldr_;
+    ua.T = dT_; ua.S = dS_; ua.t_stride = (size_t)(6 * Ncap_) * ldt_; ua.ldt = ldt_;
+    ua.yv = dYv_;
+    ua.imu = dImu_; ua.clones = dClones_; ua.clone_stride = (size_t)Ncap_ * CL_STRIDE;
+    ua.dx = dDx_; ua.lddx = ldp_;
+    ua.flags = flags_; ua.sigma2 = p_.feature_observation_noise;
+    launch_update(ua, w.maxN, stream_, &nl);
+    if (profiling_) CK(cudaEventRecord(e[5], stream_));
+  }
+  launches_ += nl;
+  if (nC > 0) {
+    CK(cudaMemcpyAsync(hStatus_, dStatus_, sizeof(int) * nC, cudaMemcpyDeviceToHost, stream_));
+    CK(cudaMemcpyAsync(hGamma_, dGamma_, sizeof(double) * nC, cudaMemcpyDeviceToHost, stream_));
+  }
+  (void)phase;
+}
+
+static void build_tiles(Batch::PhaseWork& w, int fi, int c0, int c1) {
+  FilterWork& fw = w.fw[fi];
+  fw.tile_begin = (int)w.tiles.size();
+  int i = c0;
+  while (i < c1) {
+    Tile t{};
+    t.filter = fi;
+    t.cand_begin = i;
+    t.c0_blk = w.cands[i].s_blk;
+    t.c1_blk = w.cands[i].e_blk + 1;
+    t.rows = 2 * w.cands[i].jac_m - 3;
+    int j = i + 1;
+    while (j < c1) {
+      const Cand& c = w.cands[j];
+      const int nc1 = std::max(t.c1_blk, c.e_blk + 1);
+      const int wblk = nc1 - t.c0_blk;
+      const int own = c.e_blk - c.s_blk + 1;
+      if (wblk > std::max(WTILE_MAX_BLK, own) && c.s_blk != t.c0_blk) break;
+      const int rows = t.rows + 2 * c.jac_m - 3;
+      if (rows > qr_tile_rows_cap(6 * wblk)) break;
+      if (j - i + 1 > QR_THREADS) break;
+      t.c1_blk = nc1;
+      t.rows = rows;
+      ++j;
+    }
+    t.cand_end = j;
+    const int W = 6 * (t.c1_blk - t.c0_blk);
+    t.out_off = (int)w.tileout_total;
+    w.tileout_total += (size_t)W * (W + 1);
+    w.tile_smem_doubles = std::max(w.tile_smem_doubles, (size_t)std::max(t.rows, 1) * (W + 2));
+    w.wmax_blk = std::max(w.wmax_blk, t.c1_blk - t.c0_blk);
+    fw.wmax_blk = std::max(fw.wmax_blk, t.c1_blk - t.c0_blk);
+    w.tiles.push_back(t);
+    i = j;
+  }
+  fw.tile_end = (int)w.tiles.size();
+}
+
+// Append one filter's candidates (sorted by first clone, then id) to the phase work list.
+static void append_candidates(Batch::PhaseWork& w, int fi, std::vector<CandBuild>& cb,
+                              std::vector<CandInfo>& info_out) {
+  std::stable_sort(cb.begin(), cb.end(), [](const CandBuild& a, const CandBuild& b) {
+    if (a.c.s_blk != b.c.s_blk) return a.c.s_blk < b.c.s_blk;
+    return a.id < b.id;
+  });
+  const int c0 = (int)w.cands.size();
+  for (auto& x : cb) {
+    Cand c = x.c;
+    c.filter = fi;
+    const int r = 2 * c.jac_m - 3;
+    c.row_off = (int)w.rows_total;
+    c.hblk_off = (int)w.hblk_total;
+    w.rows_total += (size_t)std::max(r, 0);
+    w.hblk_total += (size_t)std::max(r, 0) * 6 * (c.e_blk - c.s_blk + 1);
+    const int idx = (int)w.cands.size();
+    if (c.jac_m <= 8) w.small_list.push_back(idx);
+    else w.large_list.push_back(idx);
+    w.cands.push_back(c);
+    info_out.push_back(CandInfo{x.id, x.kind});
+  }
+  build_tiles(w, fi, c0, (int)w.cands.size());
+}
+
+int Batch::process(const double* t_img, const OrcvioFeature* feats, const int* feat_off,
+                   const OrcvioImu* imu, const int* imu_off, int* imu_used, int* published) {
+  if (!ok_) return ORCVIO_ERR_CUDA;
+  const int L = ORCVIO_LEG;
+  // ---------------------------------------------------------------- A: propagation inputs
+  std::vector<PropSample> samples;
+  std::vector<int> samp_off(B_ + 1, 0), Dvec(B_, 0), Nvec(B_, 0);
+  bool need_imu_upload = false;
+  for (int fi = 0; fi < B_; ++fi) {
+    FilterHost& F = f_[fi];
+    F.active = false;
+    F.stats = OrcvioFrameStats{};
+    F.stats.removed_ids[0] = F.stats.removed_ids[1] = -1;
+    F.cinfo[0].clear(); F.cinfo[1].clear();
+    F.cstatus[0].clear(); F.cstatus[1].clear();
+    F.cgamma[0].clear(); F.cgamma[1].clear();
+    published[fi] = 0;
+    imu_used[fi] = 0;
+    samp_off[fi + 1] = (int)samples.size();
+    const OrcvioImu* im = imu + imu_off[fi];
+    const int nimu = imu_off[fi + 1] - imu_off[fi];
+    const double ti = t_img[fi];
+    if (!F.first_features) {   // :504-510
+      if (nimu > 0 && (im[0].t - ti - p_.td <= 0.0)) F.first_features = true;
+      else continue;
+    }
+    int prefix = 0;
+    if (!F.gravity_set) {      // :513-563, initial_use_gt branch only
+      if (!F.has_init) continue;
+      int useful = 0;
+      for (int k = 0; k < nimu; ++k) {
+        if (im[k].t > F.init_t) break;
+        ++useful;
+      }
+      if (useful >= nimu) --useful;
+      if (useful < 0) continue;
+      init_filter_device(fi);
+      double* hm = hImu_ + (size_t)fi * IM_STRIDE;
+      for (int k = 0; k < 3; ++k) {
+        hm[IM_GOLD + k] = im[useful].gyro[k];
+        hm[IM_AOLD + k] = im[useful].acc[k];
+      }
+      CK(cudaMemcpy(dImu_ + (size_t)fi * IM_STRIDE, hm, IM_STRIDE * sizeof(double), cudaMemcpyHostToDevice));
+      need_imu_upload = true;
+      prefix = useful;
+      F.gravity_set = true;
+      F.imu_time = F.init_t;
+      F.take_off_stamp = F.init_t;
+    }
+    // batchImuProcessing :664-724
+    const double bound = ti + p_.td;
+    int used = 0;
+    double dt = 0.0;
+    for (int k = prefix; k < nimu; ++k) {
+      const double t = im[k].t;
+      if (t <= F.imu_time) { ++used; continue; }
+      if (t - bound > p_.imu_img_timeTh) break;
+      PropSample s;
+      s.t = t;
+      for (int q = 0; q < 3; ++q) { s.w[q] = im[k].gyro[q]; s.a[q] = im[k].acc[q]; }
+      samples.push_back(s);
+      dt = t - bound;
+      F.imu_time = t;
+      ++used;
+    }
+    samp_off[fi + 1] = (int)samples.size();
+    F.state_id = F.next_state_id++;
+    F.dt = dt;
+    imu_used[fi] = prefix + used;
+    Nvec[fi] = (int)F.clones.size();
+    Dvec[fi] = L + 6 * Nvec[fi];
+    F.active = true;
+    published[fi] = 1;
+
+    // addFeatureObservations :1016-1068
+    if (!p_.prediction_only_flag) {
+      const OrcvioFeature* ft = feats + feat_off[fi];
+      const int nf = feat_off[fi + 1] - feat_off[fi];
+      const long long sid = F.state_id;
+      const int curr_feature_num = (int)F.map_server.size();
+      int tracked = 0;
+      for (int k = 0; k < nf; ++k) {
+        const OrcvioFeature& m = ft[k];
+        const long long id = (long long)m.id;
+        auto it = F.map_server.find(id);
+        if (it == F.map_server.end()) {
+          if (F.free_slots.empty()) {
+            std::fprintf(stderr, "[orcvio_b200] feature table full (capacity %d)\n", Fcap_);
+            return ORCVIO_ERR_CAPACITY;
+          }
+          Track tr;
+          tr.id = id;
+          tr.slot = F.free_slots.back();
+          F.free_slots.pop_back();
+          tr.gen = F.next_gen++;
+          bool have_prev = false;
+          double dt_prev = 0.0;
+          if (!(m.u_init == -1 && m.v_init == -1)) {
+            for (const auto& c : F.clones)
+              if (c.id == sid - 1) { have_prev = true; dt_prev = c.dt; }
+          }
+          if (have_prev) {
+            Obs o{};
+            o.sid = sid - 1;
+            o.z[0] = m.u_init + m.u_init_vel * dt_prev;
+            o.z[1] = m.v_init + m.v_init_vel * dt_prev;
+            o.vel[0] = m.u_init_vel; o.vel[1] = m.v_init_vel;
+            tr.obs.push_back(o);
+          }
+          Obs o{};
+          o.sid = sid;
+          o.z[0] = m.u + m.u_vel * dt;
+          o.z[1] = m.v + m.v_vel * dt;
+          o.vel[0] = m.u_vel; o.vel[1] = m.v_vel;
+          tr.obs.push_back(o);
+          F.map_server.emplace(id, std::move(tr));
+        } else {
+          Obs o{};
+          o.sid = sid;
+          o.z[0] = m.u + m.u_vel * dt;
+          o.z[1] = m.v + m.v_vel * dt;
+          o.vel[0] = m.u_vel; o.vel[1] = m.v_vel;
+          Track& tr = it->second;
+          if (!tr.obs.empty() && tr.obs.back().sid == sid) tr.obs.back() = o;
+          else tr.obs.push_back(o);
+          ++tracked;
+        }
+      }
+      F.tracking_rate = (double)tracked / (double)curr_feature_num;   // 0/0 -> NaN like the reference
+    }
+    // stateAugmentation bookkeeping :937-961
+    F.cur_window_timestamps.push_back(F.imu_time);
+    F.clones.push_back(CloneMeta{F.state_id, F.imu_time, F.dt});
+  }
+  (void)need_imu_upload;
+
+  // ---------------------------------------------------------------- B: propagate + augment
+  {
+    blob_.reset();
+    const size_t o_s = blob_.reserve(sizeof(PropSample) * std::max<size_t>(samples.size(), 1));
+    const size_t o_o = blob_.reserve(sizeof(int) * (B_ + 1));
+    const size_t o_d = blob_.reserve(sizeof(int) * B_);
+    const size_t o_n = blob_.reserve(sizeof(int) * B_);
+    char* h = blob_.host.data();
+    if (!samples.empty()) std::memcpy(h + o_s, samples.data(), sizeof(PropSample) * samples.size());
+    std::memcpy(h + o_o, samp_off.data(), sizeof(int) * (B_ + 1));
+    std::memcpy(h + o_d, Dvec.data(), sizeof(int) * B_);
+    // augmentation only for active filters: N = -1 disables
+    std::vector<int> Naug(B_);
+    for (int fi = 0; fi < B_; ++fi) Naug[fi] = f_[fi].active ? Nvec[fi] : -1;
+    std::memcpy(h + o_n, Naug.data(), sizeof(int) * B_);
+    upload_blob();
+    if (profiling_) CK(cudaEventRecord(ev_[6], stream_));
+    PropArgs pa{};
+    pa.P = dP_; pa.p_stride = (size_t)ldp_ * ldp_; pa.ldp = ldp_;
+    pa.imu = dImu_;
+    pa.samples = (const PropSample*)(blob_.dev + o_s);
+    pa.samp_off = (const int*)(blob_.dev + o_o);
+    pa.D = (const int*)(blob_.dev + o_d);
+    pa.n_filters = B_; pa.flags = flags_;
+    pa.qc[0] = p_.imu_gyro_noise; pa.qc[1] = p_.imu_acc_noise;
+    pa.qc[2] = p_.imu_gyro_bias_noise; pa.qc[3] = p_.imu_acc_bias_noise;
+    launch_propagate(pa, stream_);
+    AugArgs aa{};
+    aa.P = dP_; aa.p_stride = pa.p_stride; aa.ldp = ldp_;
+    aa.imu = dImu_; aa.clones = dClones_; aa.clone_stride = (size_t)Ncap_ * CL_STRIDE;
+    aa.N = (const int*)(blob_.dev + o_n); aa.n_filters = B_;
+    launch_augment(aa, stream_);
+    launches_ += 2;
+    if (profiling_) {
+      CK(cudaEventRecord(ev_[7], stream_));
+    }
+    // the blob is reused by the next phase: wait for the upload + kernels reading it
+    CK(cudaStreamSynchronize(stream_));
+    if (profiling_) {
+      float ms = 0;
+      cudaEventElapsedTime(&ms, ev_[6], ev_[7]);
+      pt_.prop += ms; pt_.n_prop++;
+    }
+  }
+
+  // ---------------------------------------------------------------- C: removeLostFeatures
+  PhaseWork wA;
+  wA.fw.assign(B_, FilterWork{});
+  wA.cand_begin.assign(B_ + 1, 0);
+  for (int fi = 0; fi < B_; ++fi) {
+    FilterHost& F = f_[fi];
+    wA.cand_begin[fi] = (int)wA.cands.size();
+    FilterWork& fw = wA.fw[fi];
+    fw.N = (int)F.clones.size();
+    fw.D = L + 6 * fw.N;
+    fw.active = 0;
+    if (!F.active) continue;
+    wA.maxN = std::max(wA.maxN, fw.N);
+    const long long cur = F.state_id;
+    std::vector<CandBuild> cb;
+    std::vector<long long> invalid;
+    auto clone_index = [&](long long sid) {
+      for (int k = (int)F.clones.size() - 1; k >= 0; --k)
+        if (F.clones[k].id == sid) return k;
+      return -1;
+    };
+    for (auto& kv : F.map_server) {
+      Track& tr = kv.second;
+      const int nobs = (int)tr.obs.size();
+      const bool tracked_now = nobs > 0 && tr.obs.back().sid == cur;
+      if (!tracked_now) {
+        if (nobs < p_.least_Obs_Num) { invalid.push_back(tr.id); continue; }
+      } else {
+        if (!(nobs >= p_.max_track_len)) continue;
+      }
+      CandBuild x{};
+      x.id = tr.id;
+      x.kind = tracked_now ? 1 : 0;
+      Cand& c = x.c;
+      c.slot = tr.slot;
+      c.gen = tr.gen;
+      c.flags = 0;
+      c.jac_off = c.tri_off = (int)wA.obs_clone.size();
+      int s_blk = 1 << 30, e_blk = -1, cnt = 0;
+      for (const Obs& o : tr.obs) {
+        const int ci = clone_index(o.sid);
+        if (ci < 0) continue;
+        wA.obs_clone.push_back(ci);
+        wA.obs_z.push_back(o.z[0]);
+        wA.obs_z.push_back(o.z[1]);
+        s_blk = std::min(s_blk, ci);
+        e_blk = std::max(e_blk, ci);
+        ++cnt;
+      }
+      c.jac_m = cnt;
+      c.tri_m = tracked_now ? cnt - 1 : cnt;   // initializePosition skips the current frame (:414)
+      c.s_blk = s_blk;
+      c.e_blk = e_blk;
+      c.cm_first_clone = wA.obs_clone[c.jac_off];
+      c.cm_last_clone = wA.obs_clone[c.jac_off + (tracked_now ? cnt - 2 : cnt - 1)];
+      c.cm_zu = wA.obs_z[2 * (size_t)c.jac_off];
+      c.cm_zv = wA.obs_z[2 * (size_t)c.jac_off + 1];
+      cb.push_back(x);
+    }
+    for (long long id : invalid) {
+      auto it = F.map_server.find(id);
+      F.free_slots.push_back(it->second.slot);
+      F.map_server.erase(it);
+    }
+    F.stats.n_candidates_lost = (int)cb.size();
+    if (cb.empty()) continue;
+    fw.active = 1;
+    wA.any_active = true;
+    append_candidates(wA, fi, cb, F.cinfo[0]);
+  }
+  wA.cand_begin[B_] = (int)wA.cands.size();
+  cudaEvent_t* e = ev_;
+  run_phase(wA, 0);
+  download_mirrors();
+  CK(cudaStreamSynchronize(stream_));
+  auto account = [&](bool had_update) {
+    if (!profiling_) return;
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e[0], e[1]); pt_.tri += ms; pt_.n_tri++;
+    cudaEventElapsedTime(&ms, e[1], e[2]); pt_.jac += ms; pt_.n_jac++;
+    if (had_update) {
+      cudaEventElapsedTime(&ms, e[2], e[3]); pt_.qr_tiles += ms; pt_.n_qr_tiles++;
+      cudaEventElapsedTime(&ms, e[3], e[4]); pt_.qr_chain += ms; pt_.n_qr_chain++;
+      cudaEventElapsedTime(&ms, e[4], e[5]); pt_.update += ms; pt_.n_update++;
+    }
+  };
+  account(wA.any_active);
+
+  // ---------------------------------------------------------------- E: post-process A, prune
+  PhaseWork wB;
+  wB.fw.assign(B_, FilterWork{});
+  wB.cand_begin.assign(B_ + 1, 0);
+  std::vector<int> rm_idx(2 * (size_t)B_, -1), Nbefore(B_, 0);
+  for (int fi = 0; fi < B_; ++fi) {
+    FilterHost& F = f_[fi];
+    wB.cand_begin[fi] = (int)wB.cands.size();
+    FilterWork& fw = wB.fw[fi];
+    fw.N = (int)F.clones.size();
+    fw.D = L + 6 * fw.N;
+    fw.active = 0;
+    Nbefore[fi] = fw.N;
+    if (!F.active) continue;
+    std::memcpy(F.imu_mirror.data(), hImu_ + (size_t)fi * IM_STRIDE, IM_STRIDE * sizeof(double));
+    std::memcpy(F.clone_mirror.data(), hClones_ + (size_t)fi * Ncap_ * CL_STRIDE,
+                (size_t)Ncap_ * CL_STRIDE * sizeof(double));
+    // results of phase A
+    const int c0 = wA.cand_begin[fi], c1 = wA.cand_begin[fi + 1];
+    for (int c = c0; c < c1; ++c) {
+      const int st = hStatus_[c];
+      const CandInfo& ci = F.cinfo[0][c - c0];
+      F.cstatus[0].push_back(st);
+      F.cgamma[0].push_back(hGamma_[c]);
+      if (!(st & ST_TRI_VALID)) F.stats.n_tri_invalid_lost++;
+      if (st & ST_GATE_PASS) { F.stats.n_gate_pass_lost++; ++feature_updates_; }
+      // lost features are always erased (:2572-2576); tracked-long ones only when they were
+      // initialised and therefore used (:2310-2319)
+      if (ci.kind == 0 || (st & ST_TRI_VALID)) {
+        auto it = F.map_server.find(ci.id);
+        if (it != F.map_server.end()) {
+          F.free_slots.push_back(it->second.slot);
+          F.map_server.erase(it);
+        }
+      }
+    }
+    // pruneImuStateBuffer :2629-2959
+    if ((int)F.clones.size() < p_.sw_size) continue;
+    wB.maxN = std::max(wB.maxN, fw.N);
+    // findRedundantImuStates :2582-2626
+    const int n = (int)F.clones.size();
+    int key_i = n - 4, st_i = key_i + 1, first_i = 0;
+    const double* key = F.clone_mirror.data() + (size_t)key_i * CL_STRIDE;
+    int rm[2];
+    for (int r = 0; r < 2; ++r) {
+      const double* c = F.clone_mirror.data() + (size_t)st_i * CL_STRIDE;
+      const double dx = c[CL_PC] - key[CL_PC], dy = c[CL_PC + 1] - key[CL_PC + 1], dz = c[CL_PC + 2] - key[CL_PC + 2];
+      const double distance = std::sqrt((dx * dx + dy * dy) + dz * dz);
+      double Rr[9];
+      m3_Tmul(c + CL_RC, key + CL_RC, Rr);      // rotation = R_cam^T ; rotation * key_rotation
+      const double angle = angle_axis_angle(Rr);
+      if (angle < p_.rotation_threshold && distance < p_.translation_threshold &&
+          F.tracking_rate > p_.tracking_rate_threshold) {
+        rm[r] = st_i;
+        ++st_i;
+      } else {
+        rm[r] = first_i;
+        ++first_i;
+        st_i -= 2;
+      }
+    }
+    if (rm[0] > rm[1]) std::swap(rm[0], rm[1]);
+    rm_idx[2 * fi] = rm[0];
+    rm_idx[2 * fi + 1] = rm[1];
+    const long long rm_id0 = F.clones[rm[0]].id, rm_id1 = F.clones[rm[1]].id;
+    F.stats.n_removed_clones = 2;
+    F.stats.removed_ids[0] = rm_id0;
+    F.stats.removed_ids[1] = rm_id1;
+    const long long cur = F.state_id;
+    std::vector<CandBuild> cb;
+    auto clone_index = [&](long long sid) {
+      for (int k = (int)F.clones.size() - 1; k >= 0; --k)
+        if (F.clones[k].id == sid) return k;
+      return -1;
+    };
+    for (auto& kv : F.map_server) {
+      Track& tr = kv.second;
+      int inv0 = -1, inv1 = -1;
+      for (int k = 0; k < (int)tr.obs.size(); ++k) {
+        if (tr.obs[k].sid == rm_id0) inv0 = k;
+        if (tr.obs[k].sid == rm_id1) inv1 = k;
+      }
+      if (inv0 < 0 && inv1 < 0) continue;
+      if (inv0 >= 0 && inv1 >= 0) {
+        const int nobs = (int)tr.obs.size();
+        const bool tracked = tr.obs.back().sid == cur;
+        CandBuild x{};
+        x.id = tr.id;
+        x.kind = 2;
+        Cand& c = x.c;
+        c.slot = tr.slot;
+        c.gen = tr.gen;
+        c.flags = 0;
+        c.tri_off = (int)wB.obs_clone.size();
+        for (const Obs& o : tr.obs) {            // initializePosition_AssignAnchor: all obs
+          wB.obs_clone.push_back(clone_index(o.sid));
+          wB.obs_z.push_back(o.z[0]);
+          wB.obs_z.push_back(o.z[1]);
+        }
+        c.tri_m = nobs;
+        c.jac_off = (int)wB.obs_clone.size();
+        const int ks[2] = {inv0, inv1};
+        for (int q = 0; q < 2; ++q) {
+          wB.obs_clone.push_back(clone_index(tr.obs[ks[q]].sid));
+          wB.obs_z.push_back(tr.obs[ks[q]].z[0]);
+          wB.obs_z.push_back(tr.obs[ks[q]].z[1]);
+        }
+        c.jac_m = 2;
+        c.s_blk = rm[0];
+        c.e_blk = rm[1];
+        c.cm_first_clone = wB.obs_clone[c.tri_off];
+        c.cm_last_clone = wB.obs_clone[c.tri_off + (tracked ? nobs - 2 : nobs - 1)];
+        c.cm_zu = tr.obs[0].z[0];
+        c.cm_zv = tr.obs[0].z[1];
+        cb.push_back(x);
+      }
+      // erase the observations of the removed clones (:2842-2844)
+      tr.obs.erase(std::remove_if(tr.obs.begin(), tr.obs.end(),
+                                  [&](const Obs& o) { return o.sid == rm_id0 || o.sid == rm_id1; }),
+                   tr.obs.end());
+    }
+    F.stats.n_candidates_prune = (int)cb.size();
+    if (!cb.empty()) {
+      fw.active = 1;
+      wB.any_active = true;
+      append_candidates(wB, fi, cb, F.cinfo[1]);
+    }
+  }
+  wB.cand_begin[B_] = (int)wB.cands.size();
+  wB.extra_ints = rm_idx;
+  wB.extra_ints.insert(wB.extra_ints.end(), Nbefore.begin(), Nbefore.end());
+  run_phase(wB, 1);
+  // remove the pruned clones from P / clone array (:2875-2956)
+  bool any_rm = false;
+  for (int v : rm_idx) any_rm |= (v >= 0);
+  if (any_rm) {
+    RemoveArgs ra{};
+    ra.P = dP_; ra.p_stride = (size_t)ldp_ * ldp_; ra.ldp = ldp_;
+    ra.clones = dClones_; ra.clone_stride = (size_t)Ncap_ * CL_STRIDE;
+    ra.rm = wB.d_extra; ra.N = wB.d_extra + 2 * B_; ra.n_filters = B_;
+    launch_remove(ra, stream_);
+    ++launches_;
+  }
+  download_mirrors();
+  CK(cudaStreamSynchronize(stream_));
+  account(wB.any_active);
+  int herr = 0;
+  CK(cudaMemcpy(&herr, dErr_, sizeof(int), cudaMemcpyDeviceToHost));
+  if (herr) {
+    std::fprintf(stderr, "[orcvio_b200] QR front overflow\n");
+    return ORCVIO_ERR_CAPACITY;
+  }
+  for (int fi = 0; fi < B_; ++fi) {
+    FilterHost& F = f_[fi];
+    if (!F.active) continue;
+    const int c0 = wB.cand_begin[fi], c1 = wB.cand_begin[fi + 1];
+    for (int c = c0; c < c1; ++c) {
+      const int st = hStatus_[c];
+      F.cstatus[1].push_back(st);
+      F.cgamma[1].push_back(hGamma_[c]);
+      if (!(st & ST_TRI_VALID)) F.stats.n_tri_invalid_prune++;
+      if (st & ST_GATE_PASS) { F.stats.n_gate_pass_prune++; ++feature_updates_; }
+    }
+    if (rm_idx[2 * fi] >= 0) {
+      const int a = rm_idx[2 * fi], b = rm_idx[2 * fi + 1];
+      const double ta = F.clones[a].time, tb = F.clones[b].time;
+      F.cur_window_timestamps.erase(
+          std::remove_if(F.cur_window_timestamps.begin(), F.cur_window_timestamps.end(),
+                         [&](double t) { return t == ta || t == tb; }),
+          F.cur_window_timestamps.end());
+      F.clones.erase(F.clones.begin() + b);
+      F.clones.erase(F.clones.begin() + a);
+    }
+    std::memcpy(F.imu_mirror.data(), hImu_ + (size_t)fi * IM_STRIDE, IM_STRIDE * sizeof(double));
+    std::memcpy(F.clone_mirror.data(), hClones_ + (size_t)fi * Ncap_ * CL_STRIDE,
+                (size_t)Ncap_ * CL_STRIDE * sizeof(double));
+  }
+  return ok_ ? ORCVIO_OK : ORCVIO_ERR_CUDA;
+}
+
+int Batch::get_state(int i, OrcvioState* out) {
+  if (i < 0 || i >= B_) return ORCVIO_ERR_ARG;
+  FilterHost& F = f_[i];
+  std::memset(out, 0, sizeof(*out));
+  out->state_id = F.state_id;
+  const double* im = F.imu_mirror.data();
+  out->time = F.imu_time;
+  for (int k = 0; k < 9; ++k) out->R[k] = im[IM_R + k];
+  for (int k = 0; k < 3; ++k) {
+    out->p[k] = im[IM_P + k];
+    out->v[k] = im[IM_V + k];
+    out->bg[k] = im[IM_BG + k];
+    out->ba[k] = im[IM_BA + k];
+  }
+  out->n_clones = (int)F.clones.size();
+  out->dim = ORCVIO_LEG + 6 * out->n_clones;
+  out->n_map_features = (int)F.map_server.size();
+  double c9[81];
+  CK(cudaMemcpy2D(c9, 9 * sizeof(double), dP_ + (size_t)i * ldp_ * ldp_, ldp_ * sizeof(double),
+                  9 * sizeof(double), 9, cudaMemcpyDeviceToHost));
+  // getPpose :3000-3015: [[P_pp, P_po],[P_op, P_oo]]
+  for (int a = 0; a < 3; ++a)
+    for (int b = 0; b < 3; ++b) {
+      out->P_pose[6 * a + b] = c9[9 * (6 + a) + 6 + b];
+      out->P_pose[6 * a + 3 + b] = c9[9 * (6 + a) + b];
+      out->P_pose[6 * (3 + a) + b] = c9[9 * a + 6 + b];
+      out->P_pose[6 * (3 + a) + 3 + b] = c9[9 * a + b];
+      out->P_vel[3 * a + b] = c9[9 * (3 + a) + 3 + b];
+    }
+  return ORCVIO_OK;
+}
+
+int Batch::get_cov(int i, double* P, int cap, int* D) {
+  if (i < 0 || i >= B_) return ORCVIO_ERR_ARG;
+  const int d = ORCVIO_LEG + 6 * (int)f_[i].clones.size();
+  if (D) *D = d;
+  if (!P) return ORCVIO_OK;
+  if (cap < d * d) return ORCVIO_ERR_ARG;
+  // device is row-major with ld; P is symmetric so the column-major view is identical
+  CK(cudaMemcpy2D(P, d * sizeof(double), dP_ + (size_t)i * ldp_ * ldp_, ldp_ * sizeof(double),
+                  d * sizeof(double), d, cudaMemcpyDeviceToHost));
+  return ORCVIO_OK;
+}
+
+int Batch::set_cov(int i, const double* P, int D) {
+  if (i < 0 || i >= B_ || D > ldp_) return ORCVIO_ERR_ARG;
+  CK(cudaMemcpy2D(dP_ + (size_t)i * ldp_ * ldp_, ldp_ * sizeof(double), P, D * sizeof(double),
+                  D * sizeof(double), D, cudaMemcpyHostToDevice));
+  return ORCVIO_OK;
+}
+
+
+void Batch::override_noise(double sigma2, double chi2_p) {
+  p_.feature_observation_noise = sigma2;
+  if (chi2_p != p_.chi_square_threshold_feat) {
+    p_.chi_square_threshold_feat = chi2_p;
+    for (int i = 1; i < 500; ++i) chi2_host_[i] = chi2_quantile(chi2_p, i);
+    CK(cudaMemcpy(dChi2_, chi2_host_.data(), 500 * sizeof(double), cudaMemcpyHostToDevice));
+  }
+}
+
+// Frozen-window entry: loads clones / P / extrinsics into filter 0 and runs the selected stages.
+int Batch::run_snapshot(const SnapshotIO& io) {
+  if (!ok_) return ORCVIO_ERR_NO_DEVICE;
+  const int N = io.n_clones;
+  if (N < 1 || N > Ncap_ || io.n_feat < 0) return ORCVIO_ERR_ARG;
+  if (io.n_feat > Fcap_) {
+    // grow the feature tables of this (single filter) batch
+    cudaFree(dFpos_); cudaFree(dFgen_);
+    Fcap_ = io.n_feat + 1024;
+    CK(cudaMalloc(&dFpos_, (size_t)B_ * Fcap_ * FP_STRIDE * sizeof(double)));
+    CK(cudaMalloc(&dFgen_, (size_t)B_ * Fcap_ * sizeof(long long)));
+  }
+  const int D = ORCVIO_LEG + 6 * N;
+  // ---- host staging of the window
+  std::vector<double> cl((size_t)N * CL_STRIDE, 0.0), im(IM_STRIDE, 0.0);
+  double Rbc[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1}, tcb[3] = {0, 0, 0};
+  if (io.R_b2c) std::memcpy(Rbc, io.R_b2c, sizeof(Rbc));
+  if (io.t_c_b) std::memcpy(tcb, io.t_c_b, sizeof(tcb));
+  for (int k = 0; k < 9; ++k) im[IM_RBC + k] = Rbc[k];
+  for (int k = 0; k < 3; ++k) im[IM_TCB + k] = tcb[k];
+  for (int c = 0; c < N; ++c) {
+    double* r = cl.data() + (size_t)c * CL_STRIDE;
+    const double* R = io.clone_R + 9 * (size_t)c;
+    const double* p = io.clone_p + 3 * (size_t)c;
+    if (io.poses_are_camera) {
+      // camera poses given directly (triangulation-only entry): body pose unused
+      for (int k = 0; k < 9; ++k) { r[CL_RC + k] = R[k]; r[CL_R + k] = R[k]; }
+      for (int k = 0; k < 3; ++k) { r[CL_PC + k] = p[k]; r[CL_P + k] = p[k]; }
+    } else {
+      for (int k = 0; k < 9; ++k) r[CL_R + k] = R[k];
+      for (int k = 0; k < 3; ++k) r[CL_P + k] = p[k];
+      double Rc[9], t[3];
+      m3_mulT(R, Rbc, Rc);
+      m3_vec(R, tcb, t);
+      for (int k = 0; k < 9; ++k) r[CL_RC + k] = Rc[k];
+      for (int k = 0; k < 3; ++k) r[CL_PC + k] = p[k] + t[k];
+    }
+  }
+  // imu record: current state = newest clone (only used by the state increment)
+  for (int k = 0; k < 9; ++k) im[IM_R + k] = cl[(size_t)(N - 1) * CL_STRIDE + CL_R + k];
+  for (int k = 0; k < 3; ++k) im[IM_P + k] = cl[(size_t)(N - 1) * CL_STRIDE + CL_P + k];
+  std::vector<double> Pld((size_t)ldp_ * ldp_, 0.0);
+  if (io.P_in)
+    for (int i = 0; i < D; ++i)
+      for (int j = 0; j < D; ++j) Pld[(size_t)i * ldp_ + j] = io.P_in[(size_t)j * D + i];   // column-major in
+  FilterHost& F = f_[0];
+  F.clones.clear();
+  for (int c = 0; c < N; ++c) F.clones.push_back(CloneMeta{c, (double)c, 0.0});
+
+  PhaseWork w;
+  w.fw.assign(B_, FilterWork{});
+  w.cand_begin.assign(B_ + 1, 0);
+  FilterWork& fw = w.fw[0];
+  fw.N = N; fw.D = D; fw.active = (io.stages & 4) ? 1 : 0;
+  w.any_active = fw.active;
+  w.maxN = N;
+  std::vector<CandBuild> cb;
+  cb.reserve(io.n_feat);
+  // observations are referenced in place: copy the pools once
+  const int nobs_total = io.feat_off[io.n_feat];
+  w.obs_clone.assign(io.obs_clone, io.obs_clone + nobs_total);
+  w.obs_z.assign(io.obs_z, io.obs_z + 2 * (size_t)nobs_total);
+  for (int f = 0; f < io.n_feat; ++f) {
+    const int o0 = io.feat_off[f], m = io.feat_off[f + 1] - o0;
+    if (m < 1 || m > ORCVIO_MAX_OBS) return ORCVIO_ERR_ARG;
+    CandBuild x{};
+    x.id = f;
+    x.kind = 0;
+    Cand& c = x.c;
+    c.slot = f;
+    c.gen = f + 1;
+    c.flags = CAND_FORCE_TRI;
+    c.tri_off = c.jac_off = o0;
+    c.tri_m = c.jac_m = m;
+    int s = 1 << 30, e = -1;
+    for (int k = 0; k < m; ++k) {
+      const int ci = io.obs_clone[o0 + k];
+      if (ci < 0 || ci >= N) return ORCVIO_ERR_ARG;
+      s = std::min(s, ci);
+      e = std::max(e, ci);
+    }
+    c.s_blk = s; c.e_blk = e;
+    c.cm_first_clone = io.obs_clone[o0];
+    c.cm_last_clone = io.obs_clone[o0 + m - 1];
+    c.cm_zu = io.obs_z[2 * (size_t)o0];
+    c.cm_zv = io.obs_z[2 * (size_t)o0 + 1];
+    cb.push_back(x);
+  }
+  std::vector<CandInfo> info;
+  append_candidates(w, 0, cb, info);
+  const int nC = (int)w.cands.size();
+  // candidate order after sorting -> original feature index
+  std::vector<int> order(nC);
+  for (int c = 0; c < nC; ++c) order[c] = (int)info[c].id;
+
+  // device copies of the pristine window for repeats
+  double *dP0 = nullptr, *dCl0 = nullptr, *dIm0 = nullptr;
+  CK(cudaMalloc(&dP0, Pld.size() * sizeof(double)));
+  CK(cudaMalloc(&dCl0, cl.size() * sizeof(double)));
+  CK(cudaMalloc(&dIm0, im.size() * sizeof(double)));
+  CK(cudaMemcpy(dP0, Pld.data(), Pld.size() * sizeof(double), cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(dCl0, cl.data(), cl.size() * sizeof(double), cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(dIm0, im.data(), im.size() * sizeof(double), cudaMemcpyHostToDevice));
+  std::vector<double> pos_in;
+  if (io.positions_in) {
+    pos_in.assign((size_t)Fcap_ * FP_STRIDE, 0.0);
+    for (int f = 0; f < io.n_feat; ++f)
+      for (int k = 0; k < 3; ++k) pos_in[(size_t)f * FP_STRIDE + k] = io.positions_in[3 * (size_t)f + k];
+  }
+  const bool old_prof = profiling_;
+  profiling_ = true;
+  want_iters_ = io.iters || io.cost;
+  want_raw_ = io.raw_Hx != nullptr;
+  skip_tri_ = !(io.stages & 1);
+  skip_jac_ = !(io.stages & 2);
+  skip_update_ = !(io.stages & 4);
+  double acc[6] = {0, 0, 0, 0, 0, 0};
+  const int reps = std::max(io.repeat, 1);
+  for (int rep = 0; rep < reps; ++rep) {
+    CK(cudaMemcpyAsync(dP_, dP0, Pld.size() * sizeof(double), cudaMemcpyDeviceToDevice, stream_));
+    CK(cudaMemcpyAsync(dClones_, dCl0, cl.size() * sizeof(double), cudaMemcpyDeviceToDevice, stream_));
+    CK(cudaMemcpyAsync(dImu_, dIm0, im.size() * sizeof(double), cudaMemcpyDeviceToDevice, stream_));
+    if (io.positions_in) {
+      CK(cudaMemcpyAsync(dFpos_, pos_in.data(), pos_in.size() * sizeof(double), cudaMemcpyHostToDevice, stream_));
+      // mark every slot initialised with its own generation so the kernels use the given positions
+      std::vector<long long> gens(Fcap_, -1);
+      for (int f = 0; f < io.n_feat; ++f) gens[f] = f + 1;
+      CK(cudaMemcpy(dFgen_, gens.data(), gens.size() * sizeof(long long), cudaMemcpyHostToDevice));
+      if (skip_tri_) {
+        std::vector<int> st(nC, ST_TRI_VALID);
+        ensure_scratch(std::max(nC, 1), 1, 1, 1);
+        CK(cudaMemcpy(dStatus_, st.data(), sizeof(int) * nC, cudaMemcpyHostToDevice));
+      }
+    } else {
+      CK(cudaMemsetAsync(dFgen_, 0xFF, (size_t)Fcap_ * sizeof(long long), stream_));
+    }
+    run_phase(w, 0);
+    CK(cudaStreamSynchronize(stream_));
+    float ms = 0;
+    cudaEventElapsedTime(&ms, ev_[0], ev_[1]); acc[0] += ms;
+    cudaEventElapsedTime(&ms, ev_[1], ev_[2]); acc[1] += ms;
+    if (!skip_update_ && w.any_active) {
+      cudaEventElapsedTime(&ms, ev_[2], ev_[3]); acc[2] += ms;
+      cudaEventElapsedTime(&ms, ev_[3], ev_[4]); acc[3] += ms;
+      cudaEventElapsedTime(&ms, ev_[4], ev_[5]); acc[4] += ms;
+      cudaEventElapsedTime(&ms, ev_[0], ev_[5]); acc[5] += ms;
+    } else {
+      cudaEventElapsedTime(&ms, ev_[0], ev_[2]); acc[5] += ms;
+    }
+  }
+  profiling_ = old_prof;
+  if (io.timings_us)
+    for (int k = 0; k < 6; ++k) io.timings_us[k] = (float)(acc[k] * 1000.0 / reps);
+  // ---- outputs (candidate order -> feature order)
+  if (io.status || io.gamma)
+    for (int c = 0; c < nC; ++c) {
+      if (io.status) io.status[order[c]] = hStatus_[c];
+      if (io.gamma) io.gamma[order[c]] = hGamma_[c];
+    }
+  if (io.iters || io.cost) {
+    std::vector<int> it(2 * (size_t)nC);
+    std::vector<double> cs(nC);
+    CK(cudaMemcpy(it.data(), dIters_, it.size() * sizeof(int), cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(cs.data(), dCost_, cs.size() * sizeof(double), cudaMemcpyDeviceToHost));
+    for (int c = 0; c < nC; ++c) {
+      if (io.iters) { io.iters[2 * order[c]] = it[2 * c]; io.iters[2 * order[c] + 1] = it[2 * c + 1]; }
+      if (io.cost) io.cost[order[c]] = cs[c];
+    }
+  }
+  if (io.positions) {
+    std::vector<double> fp((size_t)io.n_feat * FP_STRIDE);
+    CK(cudaMemcpy(fp.data(), dFpos_, fp.size() * sizeof(double), cudaMemcpyDeviceToHost));
+    for (int f = 0; f < io.n_feat; ++f)
+      for (int k = 0; k < 3; ++k) io.positions[3 * (size_t)f + k] = fp[(size_t)f * FP_STRIDE + k];
+  }
+  if (io.raw_Hx) {
+    const size_t no = (size_t)nobs_total;
+    CK(cudaMemcpy(io.raw_Hx, dRawHx_, no * 12 * sizeof(double), cudaMemcpyDeviceToHost));
+    if (io.raw_He) CK(cudaMemcpy(io.raw_He, dRawHe_, no * 12 * sizeof(double), cudaMemcpyDeviceToHost));
+    if (io.raw_Hf) CK(cudaMemcpy(io.raw_Hf, dRawHf_, no * 6 * sizeof(double), cudaMemcpyDeviceToHost));
+    if (io.raw_r) CK(cudaMemcpy(io.raw_r, dRawR_, no * 2 * sizeof(double), cudaMemcpyDeviceToHost));
+  }
+  if (io.P_out) {
+    std::vector<double> Po((size_t)ldp_ * ldp_);
+    CK(cudaMemcpy(Po.data(), dP_, Po.size() * sizeof(double), cudaMemcpyDeviceToHost));
+    for (int i = 0; i < D; ++i)
+      for (int j = 0; j < D; ++j) io.P_out[(size_t)j * D + i] = Po[(size_t)i * ldp_ + j];
+  }
+  if (io.delta_x) {
+    std::vector<double> dx(ldp_);
+    CK(cudaMemcpy(dx.data(), dDx_, ldp_ * sizeof(double), cudaMemcpyDeviceToHost));
+    for (int i = 0; i < D; ++i) io.delta_x[i] = dx[i];
+  }
+  const int n = 6 * N;
+  if (io.R_thin) {
+    std::vector<double> Rm((size_t)n * ldr_);
+    CK(cudaMemcpy(Rm.data(), dR_, Rm.size() * sizeof(double), cudaMemcpyDeviceToHost));
+    for (int i = 0; i < n; ++i)
+      for (int j = 0; j < n; ++j) io.R_thin[(size_t)j * n + i] = Rm[(size_t)i * ldr_ + j];
+  }
+  if (io.r_thin) CK(cudaMemcpy(io.r_thin, dRthin_, n * sizeof(double), cudaMemcpyDeviceToHost));
+  if (io.clone_out) {
+    std::vector<double> co((size_t)N * CL_STRIDE);
+    CK(cudaMemcpy(co.data(), dClones_, co.size() * sizeof(double), cudaMemcpyDeviceToHost));
+    for (int c = 0; c < N; ++c) {
+      for (int k = 0; k < 9; ++k) io.clone_out[12 * (size_t)c + k] = co[(size_t)c * CL_STRIDE + CL_R + k];
+      for (int k = 0; k < 3; ++k) io.clone_out[12 * (size_t)c + 9 + k] = co[(size_t)c * CL_STRIDE + CL_P + k];
+    }
+  }
+  want_iters_ = want_raw_ = skip_tri_ = skip_jac_ = skip_update_ = false;
+  cudaFree(dP0); cudaFree(dCl0); cudaFree(dIm0);
+  int herr = 0;
+  CK(cudaMemcpy(&herr, dErr_, sizeof(int), cudaMemcpyDeviceToHost));
+  if (herr) return ORCVIO_ERR_CAPACITY;
+  return ok_ ? ORCVIO_OK : ORCVIO_ERR_CUDA;
+}
+
+int Batch::dense_update(int, const double*, const double*, int, double*) { return ORCVIO_ERR_UNSUPPORTED; }
+int Batch::dense_gate(int, const double*, const double*, int, double*) { return ORCVIO_ERR_UNSUPPORTED; }
+
+}  // namespace ob

@@ -1,0 +1,195 @@
+// Host side of the filter: bookkeeping of the reference's OrcVIO class (map server,
+// window of clones, per-frame classification) for a batch of independent filters that
+// advance in lock-step, driving the CUDA kernels.  A single filter is a batch of one.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/orcvio_b200.h"
+#include "config.h"
+#include "kernels.h"
+
+namespace ob {
+
+struct Obs {
+  long long sid;      // state id of the observing clone
+  double z[2];        // (u + u_vel dt, v + v_vel dt)
+  double vel[2];
+};
+
+struct Track {        // struct Feature, reference include/orcvio/feat/feature.hpp:34-265
+  long long id = 0;
+  int slot = -1;
+  long long gen = 0;
+  std::vector<Obs> obs;     // ascending sid (std::map order in the reference)
+};
+
+struct CloneMeta {
+  long long id;
+  double time;
+  double dt;
+};
+
+struct CandInfo {     // host-side twin of a device candidate
+  long long id;
+  int kind;           // 0 lost, 1 tracked-long, 2 prune
+};
+
+struct FilterHost {
+  std::map<long long, Track> map_server;
+  std::vector<CloneMeta> clones;
+  std::vector<int> free_slots;
+  long long next_state_id = 0;
+  long long next_gen = 1;
+  long long state_id = 0;
+  double imu_time = 0.0;
+  double dt = 0.0;
+  double tracking_rate = 0.0;
+  bool first_features = false, gravity_set = false, has_init = false;
+  double init_t = 0, init_q[4] = {0, 0, 0, 1}, init_p[3] = {0, 0, 0}, init_v[3] = {0, 0, 0},
+         init_bg[3] = {0, 0, 0}, init_ba[3] = {0, 0, 0};
+  double take_off_stamp = 0.0;
+  bool active = false;        // took part in the current frame
+  bool if_zupt = false;
+  std::vector<double> imu_mirror;      // IM_STRIDE
+  std::vector<double> clone_mirror;    // Ncap * CL_STRIDE
+  std::vector<double> cur_window_timestamps;
+  OrcvioFrameStats stats{};
+  std::vector<CandInfo> cinfo[2];      // phase 0 (lost) / 1 (prune)
+  std::vector<int> cstatus[2];
+  std::vector<double> cgamma[2];
+  // object-update test hooks (include/orcvio/orcvio.h:101-119)
+  int leg_dim_override = -1;
+  bool dcampose_fixed = false;
+};
+
+struct Blob {                 // one pinned host blob + device twin, carved into sections
+  std::vector<char> host;
+  char* dev = nullptr;
+  size_t dev_cap = 0;
+  char* pinned = nullptr;
+  size_t pinned_cap = 0;
+  size_t used = 0;
+  size_t reserve(size_t bytes) {
+    size_t off = (used + 255) & ~size_t(255);
+    used = off + bytes;
+    if (host.size() < used) host.resize(used * 2);
+    return off;
+  }
+  void reset() { used = 0; }
+};
+
+struct PhaseTimes {
+  double tri = 0, jac = 0, qr_tiles = 0, qr_chain = 0, update = 0, prop = 0, aug = 0, remove = 0;
+  long long n_tri = 0, n_jac = 0, n_qr_tiles = 0, n_qr_chain = 0, n_update = 0, n_prop = 0;
+};
+
+class Batch {
+ public:
+  Batch(const Params& p, int n_filters);
+  ~Batch();
+  bool ok() const { return ok_; }
+  const std::string& error() const { return err_; }
+
+  void set_initial_state(int i, double t, const double* q, const double* p, const double* v,
+                         const double* bg, const double* ba);
+  int process(const double* t_img, const OrcvioFeature* feats, const int* feat_off,
+              const OrcvioImu* imu, const int* imu_off, int* imu_used, int* published);
+  int get_state(int i, OrcvioState* out);
+  int get_cov(int i, double* P, int cap, int* D);
+  int set_cov(int i, const double* P, int D);
+  FilterHost& filter(int i) { return f_[i]; }
+  const Params& params() const { return p_; }
+  long long feature_updates() const { return feature_updates_; }
+  long long kernel_launches() const { return launches_; }
+  double gpu_ms() const { return gpu_ms_; }
+  void set_profiling(bool on) { profiling_ = on; }
+  const PhaseTimes& phase_times() const { return pt_; }
+
+  struct PhaseWork;
+  // Stage-level entry on a frozen window (orcvio_triangulate / orcvio_measurement_jacobians /
+  // orcvio_snapshot_update): loads the window into filter 0 and runs tri -> jac -> qr -> update.
+  struct SnapshotIO {
+    const double* clone_R = nullptr; const double* clone_p = nullptr;   // body poses (or camera poses)
+    bool poses_are_camera = false;
+    int n_clones = 0;
+    const double* R_b2c = nullptr; const double* t_c_b = nullptr;
+    const double* P_in = nullptr;
+    const double* positions_in = nullptr;   // when given: skip triangulation, use these
+    const int* feat_off = nullptr; const int* obs_clone = nullptr; const double* obs_z = nullptr;
+    int n_feat = 0;
+    int stages = 0;                         // bit0 tri, bit1 jac+gate, bit2 qr+update
+    int repeat = 1;
+    double* P_out = nullptr; double* delta_x = nullptr; int* status = nullptr; double* gamma = nullptr;
+    double* positions = nullptr; double* R_thin = nullptr; double* r_thin = nullptr;
+    double* clone_out = nullptr; float* timings_us = nullptr; int* iters = nullptr; double* cost = nullptr;
+    double* raw_Hx = nullptr; double* raw_He = nullptr; double* raw_Hf = nullptr; double* raw_r = nullptr;
+  };
+  int run_snapshot(const SnapshotIO& io);
+  void override_tricfg(double translation_threshold, double cost_threshold, double init_final) {
+    tricfg_.translation_threshold = translation_threshold;
+    tricfg_.cost_threshold = cost_threshold;
+    tricfg_.init_final_dist_threshold = init_final;
+  }
+  void override_noise(double sigma2, double chi2_p);
+  void override_flags(int flags) { flags_ = flags; }
+
+  // generic "update with dense H over the full state" used by the object path
+  // (removeLostObjects -> measurementUpdate_msckf with a dense H_x)
+  int dense_update(int i, const double* Hx_colmajor, const double* res, int rows, double* dx_out);
+  int dense_gate(int i, const double* Hx_colmajor, const double* res, int rows, double* gamma_out);
+
+  int Ncap() const { return Ncap_; }
+  int ldp() const { return ldp_; }
+
+ private:
+  friend struct CApi;
+  bool ok_ = false;
+  std::string err_;
+  Params p_;
+  int B_ = 0, Ncap_ = 0, ldp_ = 0, Fcap_ = 0, ldr_ = 0, ldt_ = 0;
+  int flags_ = 0;
+  std::vector<FilterHost> f_;
+  cudaStream_t stream_ = nullptr;
+  cudaEvent_t ev_[16];
+  // device state
+  double *dP_ = nullptr, *dImu_ = nullptr, *dClones_ = nullptr, *dFpos_ = nullptr;
+  long long* dFgen_ = nullptr;
+  double *dR_ = nullptr, *dRthin_ = nullptr, *dT_ = nullptr, *dS_ = nullptr, *dYv_ = nullptr, *dDx_ = nullptr;
+  double* dChi2_ = nullptr;
+  double* dFront_ = nullptr;
+  size_t front_stride_ = 0;
+  int* dErr_ = nullptr;
+  // growable device scratch
+  double *dHblk_ = nullptr, *dRblk_ = nullptr, *dTileOut_ = nullptr;
+  size_t hblk_cap_ = 0, rblk_cap_ = 0, tileout_cap_ = 0;
+  int* dStatus_ = nullptr;
+  double* dGamma_ = nullptr;
+  size_t cand_cap_ = 0;
+  Blob blob_;
+  // pinned download buffers
+  int* hStatus_ = nullptr;
+  double* hGamma_ = nullptr;
+  size_t hcand_cap_ = 0;
+  double *hImu_ = nullptr, *hClones_ = nullptr, *hDx_ = nullptr;
+  TriCfg tricfg_{};
+  long long feature_updates_ = 0, launches_ = 0;
+  double gpu_ms_ = 0;
+  bool profiling_ = false;
+  PhaseTimes pt_;
+  std::vector<double> chi2_host_;
+
+  void upload_blob();
+  void ensure_scratch(size_t n_cand, size_t hblk, size_t rblk, size_t tileout);
+  void run_phase(PhaseWork& w, int phase);
+  int* dIters_ = nullptr; double* dCost_ = nullptr; size_t iters_cap_ = 0;
+  double *dRawHx_ = nullptr, *dRawHe_ = nullptr, *dRawHf_ = nullptr, *dRawR_ = nullptr; size_t raw_cap_ = 0;
+  bool want_iters_ = false, want_raw_ = false, skip_tri_ = false, skip_update_ = false, skip_jac_ = false;
+  void download_mirrors();
+  void init_filter_device(int i);
+};
+
+}  // namespace ob

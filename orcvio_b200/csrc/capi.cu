@@ -1,0 +1,350 @@
+// extern "C" boundary: see include/orcvio_b200.h.
+#include <cstdio>
+#include <cstring>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "batch.h"
+
+using namespace ob;
+
+struct orcvio_batch {
+  Params params;
+  std::unique_ptr<Batch> batch;
+  int n = 0;
+};
+
+struct orcvio_handle {
+  std::string config_path;
+  orcvio_batch b;
+  bool initialized = false;
+  bool has_init = false;
+  double init_t = 0, init_q[4] = {0, 0, 0, 1}, init_p[3] = {0, 0, 0}, init_v[3] = {0, 0, 0},
+         init_bg[3] = {0, 0, 0}, init_ba[3] = {0, 0, 0};
+};
+
+namespace {
+
+bool check_supported(const Params& p, std::string& why) {
+  if (p.calib_imu) why = "calib_imu_instrinsic=1 (LEG_DIM 46) is not supported";
+  else if (p.estimate_extrin || p.estimate_td) why = "estimate_extrin / estimate_td are not supported";
+  else if (p.if_FEJ) why = "if_FEJ=1 is not supported";
+  else if (p.max_features * p.grid_rows * p.grid_cols != 0)
+    why = "hybrid EKF-SLAM features (max_features_in_one_grid > 0) are not supported yet";
+  else if (p.if_ZUPT_valid) why = "if_ZUPT_valid=1 is not supported yet";
+  else if (!p.use_larvio_flag && !p.use_closed_form_cov_prop_flag)
+    why = "Euler covariance propagation is dimensionally inconsistent in the reference and unsupported";
+  else if (p.use_schmidt) why = "use_schmidt=1 is not supported";
+  else if (p.sw_size < 5 || p.sw_size > 31) why = "sw_size must be in [5, 31]";
+  return why.empty();
+}
+
+int make_batch(orcvio_batch& b, const char* path, int n) {
+  std::string err;
+  if (!load_params(path, b.params, err)) {
+    std::fprintf(stderr, "[orcvio_b200] %s\n", err.c_str());
+    return ORCVIO_ERR_CONFIG;
+  }
+  std::string why;
+  if (!check_supported(b.params, why)) {
+    std::fprintf(stderr, "[orcvio_b200] unsupported configuration: %s\n", why.c_str());
+    return ORCVIO_ERR_UNSUPPORTED;
+  }
+  b.batch.reset(new Batch(b.params, n));
+  b.n = n;
+  if (!b.batch->ok()) return ORCVIO_ERR_NO_DEVICE;
+  if (b.params.initial_use_gt)
+    for (int i = 0; i < n; ++i)
+      b.batch->set_initial_state(i, b.params.initial_state_time, b.params.init_quat, b.params.init_pos,
+                                 b.params.init_vel, b.params.init_bg, b.params.init_ba);
+  return ORCVIO_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int orcvio_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+  return n;
+}
+
+const char* orcvio_version(void) { return "orcvio_b200 0.1 (sm_100a)"; }
+
+double orcvio_chi2_quantile(double p, int dof) { return chi2_quantile(p, dof); }
+
+orcvio_handle* orcvio_create(const char* config_yaml_path) {
+  orcvio_handle* h = new orcvio_handle();
+  h->config_path = config_yaml_path ? config_yaml_path : "";
+  return h;
+}
+
+void orcvio_destroy(orcvio_handle* h) { delete h; }
+
+int orcvio_initialize(orcvio_handle* h) {
+  if (!h) return 0;
+  int rc = make_batch(h->b, h->config_path.c_str(), 1);
+  if (rc != ORCVIO_OK) return 0;
+  if (h->has_init)
+    h->b.batch->set_initial_state(0, h->init_t, h->init_q, h->init_p, h->init_v, h->init_bg, h->init_ba);
+  h->initialized = true;
+  return 1;
+}
+
+int orcvio_set_initial_state(orcvio_handle* h, double t, const double q[4], const double p[3],
+                             const double v[3], const double bg[3], const double ba[3]) {
+  if (!h) return ORCVIO_ERR_ARG;
+  h->has_init = true;
+  h->init_t = t;
+  std::memcpy(h->init_q, q, 4 * sizeof(double));
+  std::memcpy(h->init_p, p, 3 * sizeof(double));
+  std::memcpy(h->init_v, v, 3 * sizeof(double));
+  if (bg) std::memcpy(h->init_bg, bg, 3 * sizeof(double));
+  if (ba) std::memcpy(h->init_ba, ba, 3 * sizeof(double));
+  if (h->initialized) h->b.batch->set_initial_state(0, t, q, p, v, bg, ba);
+  return ORCVIO_OK;
+}
+
+int orcvio_process_features(orcvio_handle* h, double t_img, const OrcvioFeature* feats, int n_feats,
+                            OrcvioImu* imu, int* n_imu) {
+  if (!h || !h->initialized || !n_imu) return ORCVIO_ERR_ARG;
+  int feat_off[2] = {0, n_feats}, imu_off[2] = {0, *n_imu};
+  int used = 0, pub = 0;
+  int rc = h->b.batch->process(&t_img, feats, feat_off, imu, imu_off, &used, &pub);
+  if (rc != ORCVIO_OK) return rc;
+  if (used > 0) {   // erase the consumed prefix like the reference does (src/orcvio.cpp:718-719)
+    std::memmove(imu, imu + used, sizeof(OrcvioImu) * (size_t)(*n_imu - used));
+    *n_imu -= used;
+  }
+  return pub;
+}
+
+int orcvio_get_state(orcvio_handle* h, OrcvioState* out) {
+  if (!h || !h->initialized || !out) return ORCVIO_ERR_ARG;
+  return h->b.batch->get_state(0, out);
+}
+
+int orcvio_get_cov(orcvio_handle* h, double* P, int cap, int* D) {
+  if (!h || !h->initialized) return ORCVIO_ERR_ARG;
+  return h->b.batch->get_cov(0, P, cap, D);
+}
+
+int orcvio_set_cov(orcvio_handle* h, const double* P, int D) {
+  if (!h || !h->initialized) return ORCVIO_ERR_ARG;
+  return h->b.batch->set_cov(0, P, D);
+}
+
+int orcvio_get_window(orcvio_handle* h, double* poses12, long long* ids, double* times, int cap) {
+  if (!h || !h->initialized) return ORCVIO_ERR_ARG;
+  FilterHost& F = h->b.batch->filter(0);
+  const int n = (int)F.clones.size();
+  if (cap < n) return ORCVIO_ERR_ARG;
+  for (int c = 0; c < n; ++c) {
+    const double* r = F.clone_mirror.data() + (size_t)c * CL_STRIDE;
+    if (poses12) {
+      for (int k = 0; k < 9; ++k) poses12[12 * c + k] = r[CL_R + k];
+      for (int k = 0; k < 3; ++k) poses12[12 * c + 9 + k] = r[CL_P + k];
+    }
+    if (ids) ids[c] = F.clones[c].id;
+    if (times) times[c] = F.clones[c].time;
+  }
+  return n;
+}
+
+int orcvio_get_map_points(orcvio_handle* h, long long* ids, double* xyz, int cap) {
+  if (!h || !h->initialized) return ORCVIO_ERR_ARG;
+  FilterHost& F = h->b.batch->filter(0);
+  int n = 0;
+  for (auto& kv : F.map_server) {
+    if (n >= cap) break;
+    if (ids) ids[n] = kv.first;
+    if (xyz) { xyz[3 * n] = xyz[3 * n + 1] = xyz[3 * n + 2] = 0.0; }
+    ++n;
+  }
+  return n;
+}
+
+int orcvio_get_frame_stats(orcvio_handle* h, OrcvioFrameStats* out) {
+  if (!h || !h->initialized || !out) return ORCVIO_ERR_ARG;
+  *out = h->b.batch->filter(0).stats;
+  return ORCVIO_OK;
+}
+
+int orcvio_get_candidate_log(orcvio_handle* h, long long* ids, int* phase, int* status, double* gamma,
+                             int cap) {
+  if (!h || !h->initialized) return ORCVIO_ERR_ARG;
+  FilterHost& F = h->b.batch->filter(0);
+  int n = 0;
+  for (int ph = 0; ph < 2; ++ph)
+    for (size_t k = 0; k < F.cinfo[ph].size() && k < F.cstatus[ph].size(); ++k) {
+      if (n >= cap) return n;
+      if (ids) ids[n] = F.cinfo[ph][k].id;
+      if (phase) phase[n] = ph;
+      if (status) status[n] = F.cstatus[ph][k];
+      if (gamma) gamma[n] = F.cgamma[ph][k];
+      ++n;
+    }
+  return n;
+}
+
+// ---- batch ---------------------------------------------------------------------------
+orcvio_batch* orcvio_batch_create(const char* config_yaml_path, int n_filters) {
+  if (n_filters < 1) return nullptr;
+  orcvio_batch* b = new orcvio_batch();
+  if (make_batch(*b, config_yaml_path, n_filters) != ORCVIO_OK) {
+    delete b;
+    return nullptr;
+  }
+  return b;
+}
+
+void orcvio_batch_destroy(orcvio_batch* b) { delete b; }
+
+int orcvio_batch_set_initial_state(orcvio_batch* b, int i, double t, const double q[4], const double p[3],
+                                   const double v[3], const double bg[3], const double ba[3]) {
+  if (!b || i < 0 || i >= b->n) return ORCVIO_ERR_ARG;
+  b->batch->set_initial_state(i, t, q, p, v, bg, ba);
+  return ORCVIO_OK;
+}
+
+int orcvio_batch_process(orcvio_batch* b, const double* t_img, const OrcvioFeature* feats, const int* feat_off,
+                         const OrcvioImu* imu, const int* imu_off, int* imu_used, int* published) {
+  if (!b) return ORCVIO_ERR_ARG;
+  return b->batch->process(t_img, feats, feat_off, imu, imu_off, imu_used, published);
+}
+
+int orcvio_batch_get_state(orcvio_batch* b, int i, OrcvioState* out) {
+  if (!b || !out) return ORCVIO_ERR_ARG;
+  return b->batch->get_state(i, out);
+}
+
+int orcvio_batch_get_cov(orcvio_batch* b, int i, double* P, int cap, int* D) {
+  if (!b) return ORCVIO_ERR_ARG;
+  return b->batch->get_cov(i, P, cap, D);
+}
+
+int orcvio_batch_get_frame_stats(orcvio_batch* b, int i, OrcvioFrameStats* out) {
+  if (!b || !out || i < 0 || i >= b->n) return ORCVIO_ERR_ARG;
+  *out = b->batch->filter(i).stats;
+  return ORCVIO_OK;
+}
+
+long long orcvio_batch_feature_updates(orcvio_batch* b) { return b ? b->batch->feature_updates() : 0; }
+long long orcvio_batch_kernel_launches(orcvio_batch* b) { return b ? b->batch->kernel_launches() : 0; }
+
+int orcvio_batch_set_profiling(orcvio_batch* b, int on) {
+  if (!b) return ORCVIO_ERR_ARG;
+  b->batch->set_profiling(on != 0);
+  return ORCVIO_OK;
+}
+
+// per-kernel-class device time (ms) and launch counts accumulated while profiling is on:
+// tri, jac, qr_tiles, qr_chain, update, propagate+augment
+int orcvio_batch_get_phase_times(orcvio_batch* b, double* ms6, long long* n6) {
+  if (!b) return ORCVIO_ERR_ARG;
+  const PhaseTimes& t = b->batch->phase_times();
+  if (ms6) { ms6[0] = t.tri; ms6[1] = t.jac; ms6[2] = t.qr_tiles; ms6[3] = t.qr_chain; ms6[4] = t.update; ms6[5] = t.prop; }
+  if (n6) { n6[0] = t.n_tri; n6[1] = t.n_jac; n6[2] = t.n_qr_tiles; n6[3] = t.n_qr_chain; n6[4] = t.n_update; n6[5] = t.n_prop; }
+  return ORCVIO_OK;
+}
+
+// ---- stage-level entry points --------------------------------------------------------
+static std::unique_ptr<Batch> make_snapshot_batch(int n_clones, int flags, double sigma2, double chi2_p,
+                                                  double tthr, double cthr, double ithr) {
+  Params p;
+  p.sw_size = std::max(n_clones, 5);
+  if (p.sw_size > 31) p.sw_size = 31;
+  p.use_larvio_flag = (flags & 1) ? 1 : 0;
+  p.use_left_perturbation_flag = (flags & 2) ? 1 : 0;
+  p.discard_large_update_flag = (flags & 4) ? 1 : 0;
+  p.feature_observation_noise = sigma2;
+  p.chi_square_threshold_feat = chi2_p;
+  p.feature_translation_threshold = tthr;
+  p.feature_cost_threshold = cthr;
+  p.init_final_dist_threshold = ithr;
+  std::unique_ptr<Batch> b(new Batch(p, 1));
+  return b;
+}
+
+int orcvio_triangulate(const double* cam_R, const double* cam_t, int n_clones, const int* feat_off,
+                       const int* obs_clone, const double* obs_z, int n_feat, double translation_threshold,
+                       double cost_threshold, double init_final_dist_threshold, double* out_pos,
+                       int* out_status, int* out_iters, double* out_cost) {
+  if (n_clones > 32) return ORCVIO_ERR_ARG;
+  auto b = make_snapshot_batch(n_clones, 0, 1.0, 0.95, translation_threshold, cost_threshold,
+                               init_final_dist_threshold);
+  if (!b->ok()) return ORCVIO_ERR_NO_DEVICE;
+  Batch::SnapshotIO io;
+  io.clone_R = cam_R; io.clone_p = cam_t; io.poses_are_camera = true; io.n_clones = n_clones;
+  io.feat_off = feat_off; io.obs_clone = obs_clone; io.obs_z = obs_z; io.n_feat = n_feat;
+  io.stages = 1;
+  io.positions = out_pos; io.status = out_status; io.iters = out_iters; io.cost = out_cost;
+  return b->run_snapshot(io);
+}
+
+int orcvio_snapshot_update(const double* clone_R, const double* clone_p, int n_clones, const double* R_b2c,
+                           const double* t_c_b, const double* P_in, const int* feat_off, const int* obs_clone,
+                           const double* obs_z, int n_feat, int flags, double noise_feature_var, double chi2_p,
+                           double translation_threshold, double cost_threshold,
+                           double init_final_dist_threshold, double* P_out, double* delta_x, int* status,
+                           double* gamma, double* positions, double* R_thin, double* r_thin, double* clone_out,
+                           float* timings_us, int repeat) {
+  auto b = make_snapshot_batch(n_clones, flags, noise_feature_var, chi2_p, translation_threshold,
+                               cost_threshold, init_final_dist_threshold);
+  if (!b->ok()) return ORCVIO_ERR_NO_DEVICE;
+  Batch::SnapshotIO io;
+  io.clone_R = clone_R; io.clone_p = clone_p; io.n_clones = n_clones;
+  io.R_b2c = R_b2c; io.t_c_b = t_c_b; io.P_in = P_in;
+  io.feat_off = feat_off; io.obs_clone = obs_clone; io.obs_z = obs_z; io.n_feat = n_feat;
+  io.stages = 7; io.repeat = repeat;
+  io.P_out = P_out; io.delta_x = delta_x; io.status = status; io.gamma = gamma; io.positions = positions;
+  io.R_thin = R_thin; io.r_thin = r_thin; io.clone_out = clone_out; io.timings_us = timings_us;
+  return b->run_snapshot(io);
+}
+
+int orcvio_measurement_jacobians(const double* clone_R, const double* clone_p, int n_clones, const double* R_b2c,
+                                 const double* t_c_b, const double* positions, const int* feat_off,
+                                 const int* obs_clone, const double* obs_z, int n_feat, int flags, double* Hx,
+                                 double* He, double* Hf, double* r) {
+  auto b = make_snapshot_batch(n_clones, flags, 1.0, 0.95, -1.0, 1e300, 1e300);
+  if (!b->ok()) return ORCVIO_ERR_NO_DEVICE;
+  const int D = ORCVIO_LEG + 6 * n_clones;
+  std::vector<double> P((size_t)D * D, 0.0);
+  for (int i = 0; i < D; ++i) P[(size_t)i * D + i] = 1.0;
+  Batch::SnapshotIO io;
+  io.clone_R = clone_R; io.clone_p = clone_p; io.n_clones = n_clones;
+  io.R_b2c = R_b2c; io.t_c_b = t_c_b; io.P_in = P.data();
+  io.positions_in = positions;
+  io.feat_off = feat_off; io.obs_clone = obs_clone; io.obs_z = obs_z; io.n_feat = n_feat;
+  io.stages = 2;
+  io.raw_Hx = Hx; io.raw_He = He; io.raw_Hf = Hf; io.raw_r = r;
+  return b->run_snapshot(io);
+}
+
+int orcvio_propagate(double*, const double*, const double*, const double*, const double*, const OrcvioImu*,
+                     int, double*, int, int, const double*) {
+  return ORCVIO_ERR_UNSUPPORTED;
+}
+
+int orcvio_object_residuals(const double*, int, const double*, const double*, const double*, int,
+                            const double*, const double*, int, double*, double*, double*, int*, double*, int*) {
+  return ORCVIO_ERR_UNSUPPORTED;
+}
+
+int orcvio_construct_object_jacobians(orcvio_handle*, const double*, int, const double*, int, const double*, int,
+                                      const double*, const int*, const double*, double*, double*, double*, int*) {
+  return ORCVIO_ERR_UNSUPPORTED;
+}
+
+int orcvio_remove_lost_objects(orcvio_handle*, const double*, const double*, const double*, int, int, int*,
+                               double*) {
+  return ORCVIO_ERR_UNSUPPORTED;
+}
+
+int orcvio_set_state_cov(orcvio_handle*, int, int) { return ORCVIO_ERR_UNSUPPORTED; }
+int orcvio_set_win_pose_timestamps(orcvio_handle*, const double*, int) { return ORCVIO_ERR_UNSUPPORTED; }
+int orcvio_fix_dcampose_dimupose_to_i(orcvio_handle*) { return ORCVIO_ERR_UNSUPPORTED; }
+
+}  // extern "C"

@@ -1,0 +1,160 @@
+// Shared kernel-side declarations: device data layouts, work-list records, launchers.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include "dmath.cuh"
+
+namespace ob {
+
+// ------------------------------------------------------------------ capacities / layouts
+#define ORCVIO_MAX_OBS 32        // observations per feature == clones in the window (<= 32)
+#define ORCVIO_LEG 22            // LEG_DIM (calib_imu_instrinsic = 0)
+
+// clone record (doubles): body pose + cached camera pose (IMUState_Aug, imu_state.h:100-153)
+constexpr int CL_R = 0;          // R body->world, row-major 3x3
+constexpr int CL_P = 9;          // position
+constexpr int CL_RC = 12;        // orientation_cam = R cam->world
+constexpr int CL_PC = 21;        // position_cam
+constexpr int CL_STRIDE = 24;
+
+// IMU state record (doubles)
+constexpr int IM_R = 0, IM_V = 9, IM_P = 12, IM_BG = 15, IM_BA = 18, IM_RBC = 21, IM_TCB = 30,
+              IM_TD = 33, IM_TIME = 34, IM_ROLD = 35, IM_VOLD = 44, IM_POLD = 47, IM_GOLD = 50,
+              IM_AOLD = 53, IM_DISCARDS = 56, IM_STRIDE = 64;
+
+constexpr int FP_STRIDE = 4;     // feature position slot: x, y, z, pad
+
+// filter flags
+constexpr int FL_LARVIO = 1, FL_LEFT = 2, FL_DISCARD_LARGE = 4;
+
+// candidate status bits
+constexpr int ST_TRI_VALID = 1, ST_GATE_PASS = 2;
+// candidate flags
+constexpr int CAND_FORCE_TRI = 1;
+
+struct TriCfg {                  // Feature::OptimizationConfig, feature.hpp:41-63
+  double translation_threshold, huber_epsilon, estimation_precision, initial_damping;
+  int outer_max, inner_max;
+  double cost_threshold, init_final_dist_threshold;
+};
+
+// One MSCKF candidate feature of one filter (built by the host bookkeeping every frame).
+struct Cand {
+  int filter;                    // filter index inside the batch
+  int slot;                      // feature slot (position table)
+  long long gen;                 // track serial: slot is initialised iff fgen[slot] == gen
+  int flags;
+  int tri_off, tri_m;            // observations used by the triangulation
+  int jac_off, jac_m;            // observations used by the Jacobian / gate
+  int row_off;                   // first row of this feature in its filter's stacked H
+  int hblk_off;                  // offset (doubles) of its compact r x w block
+  int s_blk, e_blk;              // first / last clone index touched by the Jacobian rows
+  int cm_first_clone, cm_last_clone;   // checkMotion: first and last(-or-second-to-last) obs
+  double cm_zu, cm_zv;           // first observation
+};
+
+struct TriArgs {
+  const Cand* cand; int n_cand;
+  const double* clones; size_t clone_stride;     // per-filter stride in doubles
+  double* fpos; long long* fgen; int fcap;       // per-filter feature tables
+  const int* obs_clone; const double* obs_z;
+  TriCfg cfg;
+  int* status; int* iters; double* cost;
+};
+
+struct JacArgs {
+  const Cand* cand; const int* cand_list; int n_list;   // indirection: size-class lists
+  const double* clones; size_t clone_stride;
+  const double* imu; const double* fpos; int fcap;
+  const double* P; size_t p_stride; int ldp;
+  const int* obs_clone; const double* obs_z;
+  int flags; double sigma2; const double* chi2;  // chi2[dof], dof < 500
+  int* status; double* gamma;
+  double* hblk; double* rblk;                    // compact projected blocks / residuals
+  // optional raw per-observation outputs (orcvio_measurement_jacobians)
+  double* raw_Hx; double* raw_He; double* raw_Hf; double* raw_r;
+};
+
+// Row tile of the stacked Jacobian, reduced to an upper-trapezoidal factor by one CTA.
+struct Tile {
+  int filter;
+  int cand_begin, cand_end;      // candidates (sorted by s_blk inside a filter)
+  int rows;                      // rows if every candidate passes the gate
+  int c0_blk, c1_blk;            // clone-block window [c0, c1)
+  int out_off;                   // offset (doubles) of its W x (W+1) output
+};
+
+struct FilterWork {              // per filter, per update
+  int N;                         // clones
+  int D;                         // 22 + 6N
+  int tile_begin, tile_end;      // tiles of this filter, sorted by c0_blk
+  int wmax_blk;                  // widest tile window (blocks)
+  int active;                    // 0: skip this filter's update entirely
+};
+
+struct QrArgs {
+  const Cand* cand; const int* status;
+  const double* hblk; const double* rblk;
+  const Tile* tiles; int n_tiles;
+  double* tile_out;
+  const FilterWork* fw; int n_filters;
+  double* Rm; double* rthin; size_t r_stride; int ldr;   // per-filter R (n x n) and r_thin
+  double* front_scratch; size_t front_stride;            // global fallback for wide fronts
+  int* err;                                              // device error flag (front overflow)
+};
+
+struct UpdArgs {
+  const FilterWork* fw; int n_filters;
+  double* P; size_t p_stride; int ldp;
+  double* Rm; double* rthin; size_t r_stride; int ldr;
+  double* T; double* S; size_t t_stride; int ldt;        // T: n x D, S: n x n (ld = ldr)
+  double* yv;                                            // L^-1 r_thin, per filter (ldr)
+  double* imu; double* clones; size_t clone_stride;
+  double* dx; int lddx;                                  // delta_x log per filter
+  int flags; double sigma2;
+};
+
+struct PropSample { double t, w[3], a[3]; };
+
+struct PropArgs {
+  double* P; size_t p_stride; int ldp;
+  double* imu;
+  const PropSample* samples; const int* samp_off;        // CSR per filter
+  const int* D;                                          // per filter current dimension
+  int n_filters; int flags;
+  double qc[4];                                          // gyro, acc, gyro-bias, acc-bias variances
+};
+
+struct AugArgs {
+  double* P; size_t p_stride; int ldp;
+  const double* imu; double* clones; size_t clone_stride;
+  const int* N; int n_filters;                           // N = clones BEFORE augmentation
+};
+
+struct RemoveArgs {
+  double* P; size_t p_stride; int ldp;
+  double* clones; size_t clone_stride;
+  const int* N;                                          // clones before removal
+  const int* rm;                                         // 2 per filter, ascending, -1 = none
+  int n_filters;
+};
+
+void launch_triangulate(const TriArgs& a, cudaStream_t s);
+void launch_jac_gate(const JacArgs& small_list, const JacArgs& large_list, cudaStream_t s);
+void launch_qr(const QrArgs& a, size_t tile_smem_doubles, int max_w_blk, int max_n, cudaStream_t s,
+               int* launches, cudaEvent_t mid);
+void launch_update(const UpdArgs& a, int max_N, cudaStream_t s, int* launches);
+void launch_propagate(const PropArgs& a, cudaStream_t s);
+void launch_augment(const AugArgs& a, cudaStream_t s);
+void launch_remove(const RemoveArgs& a, cudaStream_t s);
+
+// tile sizing shared by host tiler and kernels
+constexpr int QR_THREADS = 256;
+constexpr int QR_SMEM_BYTES = 200 * 1024;
+inline int qr_tile_rows_cap(int w_cols) {                // rows that fit beside (w_cols+1) columns
+  int ld = w_cols + 2;
+  int cap = QR_SMEM_BYTES / 8 / ld;
+  return cap;
+}
+
+}  // namespace ob
