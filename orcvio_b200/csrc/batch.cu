@@ -341,6 +341,7 @@ void Batch::run_phase(PhaseWork& w, int phase) {
     if (profiling_) CK(cudaEventRecord(e[5], stream_));
   }
   launches_ += nl;
+  if (launch_error_count() > 0) { ok_ = false; err_ = "kernel launch failed"; }
   if (nC > 0) {
     CK(cudaMemcpyAsync(hStatus_, dStatus_, sizeof(int) * nC, cudaMemcpyDeviceToHost, stream_));
     CK(cudaMemcpyAsync(hGamma_, dGamma_, sizeof(double) * nC, cudaMemcpyDeviceToHost, stream_));

@@ -50,18 +50,41 @@ __device__ __forceinline__ void measurement_jacobian(const double* cl, const dou
   double pbf[3] = {pw[0] - p[0], pw[1] - p[1], pw[2] - p[2]};
   double Sk[9], A[9], B[9];
   double sign;
-  if ((flags & FL_LARVIO) || (flags & FL_LEFT)) {
-    // LARVIO (:1147-1149): [R_w2c [p_w - p]x | -R_w2c], H_x = dz * that.  The OrcVIO left
-    // perturbation branch (:1136) reduces algebraically to the same 3x6 with H_x = -dz*(-...) .
+  // The OrcVIO branches go through wTc.inverse() (a general 4x4 inverse, :1136,1140), which
+  // differs from the transpose when the yaml extrinsic rotation is only orthonormal to its
+  // printed digits (kitti_odom.yaml: ~1e-8).  Rinv = (R_w2c^T)^-1 restates that inverse.
+  double Rinv[9];
+  if (!(flags & FL_LARVIO)) {
+    const double* M = Rw2c;   // wTc.linear() = R_w2c^T ; inverse of the transpose = (M^-1)^T
+    double c00 = M[4] * M[8] - M[5] * M[7], c01 = M[5] * M[6] - M[3] * M[8], c02 = M[3] * M[7] - M[4] * M[6];
+    double c10 = M[2] * M[7] - M[1] * M[8], c11 = M[0] * M[8] - M[2] * M[6], c12 = M[1] * M[6] - M[0] * M[7];
+    double c20 = M[1] * M[5] - M[2] * M[4], c21 = M[2] * M[3] - M[0] * M[5], c22 = M[0] * M[4] - M[1] * M[3];
+    double det = (M[0] * c00 + M[1] * c01) + M[2] * c02;
+    // M^-1 = adj(M)/det with adj = cofactor^T ; (M^-1)^T = cofactor/det
+    Rinv[0] = c00 / det; Rinv[1] = c01 / det; Rinv[2] = c02 / det;
+    Rinv[3] = c10 / det; Rinv[4] = c11 / det; Rinv[5] = c12 / det;
+    Rinv[6] = c20 / det; Rinv[7] = c21 / det; Rinv[8] = c22 / det;
+  }
+  if (flags & FL_LARVIO) {
+    // LARVIO (:1147-1149): [R_w2c [p_w - p]x | -R_w2c], H_x = dz * that.
     m3_skew(pbf, Sk);
     m3_mul(Rw2c, Sk, A);
     for (int i = 0; i < 9; ++i) B[i] = -Rw2c[i];
     sign = 1.0;
+  } else if (flags & FL_LEFT) {
+    // OrcVIO left perturbation (:1136): temp * cTw * odot([p_w;1]) * J_L reduces to
+    // [cTw_R [p - p_w]x | cTw_R] and H_x = -dz * that, with cTw_R = wTc.inverse() rotation.
+    m3_skew(pbf, Sk);
+    m3_mul(Rinv, Sk, A);
+    for (int i = 0; i < 9; ++i) B[i] = -Rinv[i];
+    sign = 1.0;
   } else {
-    // OrcVIO right perturbation (:1140-1143): [I, -[p_c]x] * [[-R_bc [t_cb]x, R_w2c],[R_bc, 0]]
-    double St[9], Sp[9], T1[9], T2[9];
+    // OrcVIO right perturbation (:1140-1143): [I, -[p_c']x] * [[-R_bc [t_cb]x, R_w2c],[R_bc, 0]]
+    // with p_c' = (wTc.inverse() * [p_w;1]).head(3)
+    double St[9], Sp[9], T1[9], T2[9], pci[3];
+    m3_vec(Rinv, d, pci);
     m3_skew(tcb, St);
-    m3_skew(pc, Sp);
+    m3_skew(pci, Sp);
     m3_mul(Rbc, St, T1);
     m3_mul(Sp, Rbc, T2);
     for (int i = 0; i < 9; ++i) { A[i] = -T1[i] - T2[i]; B[i] = Rw2c[i]; }
@@ -327,6 +350,7 @@ static void launch_one(const JacArgs& a, cudaStream_t s) {
   }
   int blocks = (a.n_list + tpb - 1) / tpb;
   k_jac_gate<TEAM, MAXM><<<blocks, threads, smem, s>>>(a);
+  check_launch("k_jac_gate");
 }
 
 void launch_jac_gate(const JacArgs& small_list, const JacArgs& large_list, cudaStream_t s) {

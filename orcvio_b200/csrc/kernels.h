@@ -139,6 +139,10 @@ struct RemoveArgs {
   int n_filters;
 };
 
+// Records (and prints) a launch-configuration error; Batch polls launch_error_count().
+void check_launch(const char* name);
+int launch_error_count();
+
 void launch_triangulate(const TriArgs& a, cudaStream_t s);
 void launch_jac_gate(const JacArgs& small_list, const JacArgs& large_list, cudaStream_t s);
 void launch_qr(const QrArgs& a, size_t tile_smem_doubles, int max_w_blk, int max_n, cudaStream_t s,

@@ -349,6 +349,7 @@ void launch_propagate(const PropArgs& a, cudaStream_t s) {
     attr = true;
   }
   k_propagate<<<a.n_filters, 256, smem, s>>>(a);
+  check_launch("k_propagate");
 }
 
 // stateAugmentation: clone the IMU pose, P <- [[P, P J^T],[J P, J P J^T]], J selects theta, p.
@@ -384,7 +385,10 @@ __global__ void __launch_bounds__(256) k_augment(AugArgs a) {
   }
 }
 
-void launch_augment(const AugArgs& a, cudaStream_t s) { k_augment<<<a.n_filters, 256, 0, s>>>(a); }
+void launch_augment(const AugArgs& a, cudaStream_t s) {
+  k_augment<<<a.n_filters, 256, 0, s>>>(a);
+  check_launch("k_augment");
+}
 
 // Delete the rows/columns of up to two clones from P and compact the clone array.
 __global__ void __launch_bounds__(256) k_remove(RemoveArgs a) {
@@ -435,6 +439,7 @@ __global__ void __launch_bounds__(256) k_remove(RemoveArgs a) {
 void launch_remove(const RemoveArgs& a, cudaStream_t s) {
   size_t smem = (size_t)a.ldp * sizeof(double);
   k_remove<<<a.n_filters, 256, smem, s>>>(a);
+  check_launch("k_remove");
 }
 
 }  // namespace ob

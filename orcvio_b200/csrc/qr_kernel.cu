@@ -233,14 +233,16 @@ void launch_qr(const QrArgs& a, size_t tile_smem_doubles, int max_w_blk, int max
                int* launches, cudaEvent_t mid) {
   static bool attr = false;
   if (!attr) {
-    cudaFuncSetAttribute(k_qr_tiles, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    cudaFuncSetAttribute(k_qr_chain, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaFuncSetAttribute(k_qr_tiles, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+    cudaFuncSetAttribute(k_qr_chain, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+    check_launch("qr attributes");
     attr = true;
   }
   if (a.n_tiles > 0) {
     size_t smem = tile_smem_doubles * sizeof(double);
     if (smem < 1024) smem = 1024;
     k_qr_tiles<<<a.n_tiles, QR_THREADS, smem, s>>>(a);
+    check_launch("k_qr_tiles");
     if (launches) ++*launches;
   }
   if (mid) cudaEventRecord(mid, s);
@@ -254,6 +256,7 @@ void launch_qr(const QrArgs& a, size_t tile_smem_doubles, int max_w_blk, int max
   const size_t smem = (size_t)rows_cap * (wcap + 1) * sizeof(double);
   const int use_global = smem > (size_t)QR_SMEM_BYTES ? 1 : 0;
   k_qr_chain<<<a.n_filters, QR_THREADS, use_global ? 0 : smem, s>>>(a, rows_cap, wcap, use_global);
+  check_launch("k_qr_chain");
   if (launches) ++*launches;
 }
 

@@ -14,6 +14,7 @@
 // Why thread-per-feature: the sums over observations must be accumulated in observation
 // order to keep that bit-level agreement, the working set of one feature (<= 32 relative
 // poses) is tiny, and a frame offers hundreds to thousands of independent features.
+#include <cstdio>
 #include "kernels.h"
 
 namespace ob {
@@ -296,11 +297,22 @@ __global__ void __launch_bounds__(128) k_triangulate(TriArgs a) {
   if (a.cost) a.cost[c] = cost;
 }
 
+static int g_launch_errors = 0;
+void check_launch(const char* name) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    ++g_launch_errors;
+    std::fprintf(stderr, "[orcvio_b200] kernel launch failed: %s: %s\n", name, cudaGetErrorString(e));
+  }
+}
+int launch_error_count() { return g_launch_errors; }
+
 void launch_triangulate(const TriArgs& a, cudaStream_t s) {
   if (a.n_cand <= 0) return;
   int threads = 128;
   int blocks = (a.n_cand + threads - 1) / threads;
   k_triangulate<<<blocks, threads, 0, s>>>(a);
+  check_launch("k_triangulate");
 }
 
 }  // namespace ob

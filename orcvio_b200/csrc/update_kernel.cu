@@ -323,16 +323,22 @@ void launch_update(const UpdArgs& a, int max_N, cudaStream_t s, int* launches) {
   }
   dim3 g0((Dmax + GT - 1) / GT, (nmax + GT - 1) / GT, B);
   k_gemm<MODE_RP><<<g0, 256, 0, s>>>(a);
+  check_launch("k_gemm<RP>");
   dim3 g1((nmax + GT - 1) / GT, (nmax + GT - 1) / GT, B);
   k_gemm<MODE_S><<<g1, 256, 0, s>>>(a);
+  check_launch("k_gemm<S>");
   size_t sm_chol = (size_t)2 * (nmax + 1) * (CB + 1) * sizeof(double);
   k_chol_solve<<<B, 256, sm_chol, s>>>(a, nmax);
+  check_launch("k_chol_solve");
   size_t sm_trsm = ((size_t)nmax * (CB + 1) + CB * (CB + 1)) * sizeof(double);
   dim3 g3((Dmax + CB - 1) / CB, B);
   k_trsm<<<g3, 256, sm_trsm, s>>>(a, nmax);
+  check_launch("k_trsm");
   k_apply_dx<<<B, 256, 0, s>>>(a);
+  check_launch("k_apply_dx");
   dim3 g5((Dmax + GT - 1) / GT, (Dmax + GT - 1) / GT, B);
   k_gemm<MODE_P><<<g5, 256, 0, s>>>(a);
+  check_launch("k_gemm<P>");
   if (launches) *launches += 6;
 }
 

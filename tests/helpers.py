@@ -47,8 +47,13 @@ def oracle_from_snapshot(snap, flags, sigma2, chi2_p=0.95, tri=None):
         cl.position = np.array(snap["clone_p"][c], dtype=float)
         cl.R_imu_cam0 = R_b2c
         cl.t_cam0_imu = t_c_b
-        cl.orientation_cam = cl.orientation @ R_b2c.T
-        cl.position_cam = cl.position + cl.orientation @ t_c_b
+        # same association order as the product's ob::m3_mulT / m3_vec so that the camera
+        # poses fed to the bit-exact triangulation comparison are identical doubles
+        R, B = cl.orientation, R_b2c
+        cl.orientation_cam = np.array([[(R[i, 0] * B[j, 0] + R[i, 1] * B[j, 1]) + R[i, 2] * B[j, 2]
+                                        for j in range(3)] for i in range(3)])
+        cl.position_cam = cl.position + np.array(
+            [(R[i, 0] * t_c_b[0] + R[i, 1] * t_c_b[1]) + R[i, 2] * t_c_b[2] for i in range(3)])
         vio.clones[c] = cl
     s = SimpleNamespace(id=N - 1, time=0.0, dt=0.0,
                         orientation=vio.clones[N - 1].orientation.copy(),

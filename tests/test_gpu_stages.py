@@ -59,7 +59,7 @@ def test_triangulation_bit_exact(n_clones, n_feat, max_len, full):
 def test_measurement_jacobians(flags):
     snap = synth.stress_snapshot(20, 80, 6, seed=5)
     sigma2 = 1e-4
-    vio = H.oracle_from_snapshot(snap, flags, sigma2)
+    vio = H.oracle_from_snapshot(snap, flags, sigma2, tri=dict(cost_threshold=1e3, init_final_dist_threshold=1e3))
     rng = np.random.default_rng(0)
     nf = len(snap["feat_off"]) - 1
     # plausible 3-D points: triangulate with the oracle, perturb a little
