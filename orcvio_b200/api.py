@@ -70,6 +70,7 @@ def lib():
     L.orcvio_set_cov.argtypes = [vp, dp, C.c_int]
     L.orcvio_get_window.argtypes = [vp, dp, C.POINTER(C.c_longlong), dp, C.c_int]
     L.orcvio_get_frame_stats.argtypes = [vp, C.POINTER(OrcvioFrameStats)]
+    L.orcvio_get_map_points.argtypes = [vp, C.POINTER(C.c_longlong), dp, C.c_int]
     L.orcvio_get_candidate_log.argtypes = [vp, C.POINTER(C.c_longlong), ip, ip, dp, C.c_int]
     L.orcvio_batch_create.restype = vp
     L.orcvio_batch_create.argtypes = [C.c_char_p, C.c_int]
@@ -215,6 +216,13 @@ class OrcVIO:
         s = OrcvioFrameStats()
         self._L.orcvio_get_frame_stats(self._h, C.byref(s))
         return s
+
+    def map_points(self, cap=65536):
+        """getMSCKFMapPointPositions: (ids, xyz); xyz is NaN for features not yet initialised."""
+        ids = np.zeros(cap, dtype=np.int64)
+        xyz = np.zeros((cap, 3))
+        n = self._L.orcvio_get_map_points(self._h, ids.ctypes.data_as(C.POINTER(C.c_longlong)), _dp(xyz), cap)
+        return ids[:n], xyz[:n]
 
     def candidate_log(self, cap=65536):
         ids = np.zeros(cap, dtype=np.int64)

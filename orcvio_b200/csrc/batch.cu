@@ -905,6 +905,27 @@ int Batch::get_cov(int i, double* P, int cap, int* D) {
   return ORCVIO_OK;
 }
 
+int Batch::get_map_points(int i, long long* ids, double* xyz, int cap) {
+  if (i < 0 || i >= B_) return ORCVIO_ERR_ARG;
+  FilterHost& F = f_[i];
+  std::vector<double> fp((size_t)Fcap_ * FP_STRIDE);
+  std::vector<long long> fg(Fcap_);
+  CK(cudaMemcpy(fp.data(), dFpos_ + (size_t)i * Fcap_ * FP_STRIDE, fp.size() * sizeof(double), cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(fg.data(), dFgen_ + (size_t)i * Fcap_, fg.size() * sizeof(long long), cudaMemcpyDeviceToHost));
+  int n = 0;
+  for (auto& kv : F.map_server) {
+    if (n >= cap) break;
+    const Track& tr = kv.second;
+    if (ids) ids[n] = tr.id;
+    if (xyz) {
+      const bool init = fg[tr.slot] == tr.gen;
+      for (int k = 0; k < 3; ++k) xyz[3 * n + k] = init ? fp[(size_t)tr.slot * FP_STRIDE + k] : NAN;
+    }
+    ++n;
+  }
+  return n;
+}
+
 int Batch::set_cov(int i, const double* P, int D) {
   if (i < 0 || i >= B_ || D > ldp_) return ORCVIO_ERR_ARG;
   CK(cudaMemcpy2D(dP_ + (size_t)i * ldp_ * ldp_, ldp_ * sizeof(double), P, D * sizeof(double),

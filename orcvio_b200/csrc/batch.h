@@ -101,6 +101,8 @@ class Batch {
   int get_state(int i, OrcvioState* out);
   int get_cov(int i, double* P, int cap, int* D);
   int set_cov(int i, const double* P, int D);
+  // getMSCKFMapPointPositions: world positions of the map-server features (NaN = not initialised)
+  int get_map_points(int i, long long* ids, double* xyz, int cap);
   FilterHost& filter(int i) { return f_[i]; }
   const Params& params() const { return p_; }
   long long feature_updates() const { return feature_updates_; }

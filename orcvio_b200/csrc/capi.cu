@@ -155,15 +155,7 @@ int orcvio_get_window(orcvio_handle* h, double* poses12, long long* ids, double*
 
 int orcvio_get_map_points(orcvio_handle* h, long long* ids, double* xyz, int cap) {
   if (!h || !h->initialized) return ORCVIO_ERR_ARG;
-  FilterHost& F = h->b.batch->filter(0);
-  int n = 0;
-  for (auto& kv : F.map_server) {
-    if (n >= cap) break;
-    if (ids) ids[n] = kv.first;
-    if (xyz) { xyz[3 * n] = xyz[3 * n + 1] = xyz[3 * n + 2] = 0.0; }
-    ++n;
-  }
-  return n;
+  return h->b.batch->get_map_points(0, ids, xyz, cap);
 }
 
 int orcvio_get_frame_stats(orcvio_handle* h, OrcvioFrameStats* out) {

@@ -109,6 +109,7 @@ class SynthSpec:
     img_offset: float = 0.001        # image stamps sit 1 ms after an IMU stamp -> dt != 0
     n_landmarks: int = 6000
     drop_prob: float = 0.03          # per-frame chance a track is lost early
+    imu_noise_scale: float = 0.1     # true IMU noise = scale x the (inflated) config densities
     init_prob: float = 0.5           # chance a new track carries u_init/v_init
     gyro_bias: tuple = (0.002, -0.001, 0.0015)
     acc_bias: tuple = (0.02, 0.01, -0.015)
@@ -147,8 +148,8 @@ def make_sequence(spec: SynthSpec):
     t_end = spec.t0 + spec.n_frames * img_dt + 0.05
     n_imu = int(round((t_end - spec.t0 + 0.02) * imu_rate))
     imu = np.zeros((n_imu, 7))
-    sg = float(base["noise_gyro"]) / math.sqrt(dt_imu)
-    sa = float(base["noise_acc"]) / math.sqrt(dt_imu)
+    sg = spec.imu_noise_scale * float(base["noise_gyro"]) / math.sqrt(dt_imu)
+    sa = spec.imu_noise_scale * float(base["noise_acc"]) / math.sqrt(dt_imu)
     for i in range(n_imu):
         t = spec.t0 - 0.01 + i * dt_imu
         _, _, _, w, f = traj.kinematics(t)
