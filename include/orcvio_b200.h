@@ -173,6 +173,31 @@ int orcvio_snapshot_update(const double* clone_R, const double* clone_p, int n_c
                            int* status, double* gamma, double* positions, double* R_thin,
                            double* r_thin, double* clone_out, float* timings_us, int repeat);
 
+/* Persistent form of orcvio_snapshot_update for a stream of frames (no allocation per call):
+ * the same stages 1,2,4,5 -- removeLostFeatures' "stack -> compress -> update" chain,
+ * src/orcvio.cpp:2498-2560 + measurementUpdate_hybrid :1766-1950 -- on one frame.
+ *   orcvio_frame_update : host buffers in, host buffers out (H2D + kernels + D2H), the call a
+ *                         host integration makes per frame;
+ *   orcvio_frame_load / _run / _fetch : upload once, run the kernel chain `repeat` times on the
+ *                         HBM-resident frame (each run restores the pristine window first),
+ *                         device time in microseconds via CUDA events. */
+typedef struct orcvio_frame orcvio_frame;
+orcvio_frame* orcvio_frame_create(int n_clones_cap, int flags, double noise_feature_var, double chi2_p,
+                                  double translation_threshold, double cost_threshold,
+                                  double init_final_dist_threshold);
+void orcvio_frame_destroy(orcvio_frame* f);
+int orcvio_frame_update(orcvio_frame* f, const double* clone_R, const double* clone_p, int n_clones,
+                        const double* R_b2c, const double* t_c_b, const double* P_in, const int* feat_off,
+                        const int* obs_clone, const double* obs_z, int n_feat, double* P_out,
+                        double* delta_x, int* status, double* gamma, double* clone_out);
+int orcvio_frame_load(orcvio_frame* f, const double* clone_R, const double* clone_p, int n_clones,
+                      const double* R_b2c, const double* t_c_b, const double* P_in, const int* feat_off,
+                      const int* obs_clone, const double* obs_z, int n_feat);
+int orcvio_frame_run(orcvio_frame* f, int repeat, float* total_us, float* stage_us6);
+int orcvio_frame_fetch(orcvio_frame* f, double* P_out, double* delta_x, int* status, double* gamma,
+                       double* clone_out);
+long long orcvio_frame_kernel_launches(orcvio_frame* f);
+
 /* Stage 2 only, for element-wise parity of J1 (measurementJacobian_msckf, orcvio.cpp:1071-1168):
  * per observation H_x (2x6), H_e (2x6), H_f (2x3), r (2), row-major. */
 int orcvio_measurement_jacobians(const double* clone_R, const double* clone_p, int n_clones,
@@ -199,7 +224,16 @@ int orcvio_propagate(double* state16, const double* bg, const double* ba, const 
 
 /* device / build info */
 int orcvio_device_count(void);
+/* select the CUDA device used by handles created afterwards on this thread (one process per GPU) */
+int orcvio_set_device(int device);
 const char* orcvio_version(void);
+/* chi-square quantile used for the gating tables (boost::math::quantile(chi_squared(dof), p),
+ * src/orcvio.cpp:481-494) */
+double orcvio_chi2_quantile(double p, int dof);
+/* per-kernel-class device time (ms) and counts accumulated while profiling is on:
+ * tri, jac+gate, qr tiles, qr chain, update, propagate+augment */
+int orcvio_batch_set_profiling(orcvio_batch* b, int on);
+int orcvio_batch_get_phase_times(orcvio_batch* b, double* ms6, long long* n6);
 
 #ifdef __cplusplus
 }

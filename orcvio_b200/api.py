@@ -89,6 +89,7 @@ def lib():
     L.orcvio_chi2_quantile.restype = C.c_double
     L.orcvio_chi2_quantile.argtypes = [C.c_double, C.c_int]
     L.orcvio_version.restype = C.c_char_p
+    L.orcvio_set_device.argtypes = [C.c_int]
     L.orcvio_triangulate.argtypes = [dp, dp, C.c_int, ip, ip, dp, C.c_int, C.c_double, C.c_double,
                                      C.c_double, dp, ip, ip, dp]
     L.orcvio_snapshot_update.argtypes = [dp, dp, C.c_int, dp, dp, dp, ip, ip, dp, C.c_int, C.c_int,
@@ -105,6 +106,16 @@ def lib():
     L.orcvio_set_win_pose_timestamps.argtypes = [vp, dp, C.c_int]
     L.orcvio_fix_dcampose_dimupose_to_i.argtypes = [vp]
     L.orcvio_propagate.argtypes = [dp, dp, dp, dp, dp, vp, C.c_int, dp, C.c_int, C.c_int, dp]
+    fpt = C.POINTER(C.c_float)
+    L.orcvio_frame_create.restype = vp
+    L.orcvio_frame_create.argtypes = [C.c_int, C.c_int] + [C.c_double] * 5
+    L.orcvio_frame_destroy.argtypes = [vp]
+    L.orcvio_frame_update.argtypes = [vp, dp, dp, C.c_int, dp, dp, dp, ip, ip, dp, C.c_int, dp, dp, ip, dp, dp]
+    L.orcvio_frame_load.argtypes = [vp, dp, dp, C.c_int, dp, dp, dp, ip, ip, dp, C.c_int]
+    L.orcvio_frame_run.argtypes = [vp, C.c_int, fpt, fpt]
+    L.orcvio_frame_fetch.argtypes = [vp, dp, dp, ip, dp, dp]
+    L.orcvio_frame_kernel_launches.restype = C.c_longlong
+    L.orcvio_frame_kernel_launches.argtypes = [vp]
     _lib = L
     return L
 
@@ -346,6 +357,94 @@ class Batch:
         self._L.orcvio_batch_get_phase_times(self._h, _dp(ms), n.ctypes.data_as(C.POINTER(C.c_longlong)))
         names = ["tri", "jac_gate", "qr_tiles", "qr_chain", "update", "propagate"]
         return {k: (float(ms[i]), int(n[i])) for i, k in enumerate(names)}
+
+
+class Frame:
+    """Persistent frozen-frame updater (orcvio_frame_*): the 'stack -> compress -> update'
+    chain of removeLostFeatures on one frame, reused for a stream of frames."""
+
+    STAGES = ["tri", "jac_gate", "qr_tiles", "qr_chain", "update", "total"]
+
+    def __init__(self, n_clones_cap=30, flags=0, noise_var=1.0, chi2_p=0.95, translation_threshold=-1.0,
+                 cost_threshold=4.7673e-4, init_final_dist_threshold=5.0):
+        self._L = lib()
+        self._h = self._L.orcvio_frame_create(n_clones_cap, flags, noise_var, chi2_p, translation_threshold,
+                                              cost_threshold, init_final_dist_threshold)
+        if not self._h:
+            raise RuntimeError("orcvio_frame_create failed (no CUDA device: there is no CPU fallback)")
+        self._keep = None
+
+    def __del__(self):
+        try:
+            if self._h:
+                self._L.orcvio_frame_destroy(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+    @staticmethod
+    def _inputs(snap):
+        N = int(snap["n_clones"])
+        return dict(N=N, clone_R=_f64(snap["clone_R"]).reshape(N, 9), clone_p=_f64(snap["clone_p"]).reshape(N, 3),
+                    Rbc=_f64(snap["R_b2c"]).reshape(9), tcb=_f64(snap["t_c_b"]).reshape(3),
+                    P=np.asfortranarray(snap["P"], dtype=np.float64), feat_off=_i32(snap["feat_off"]),
+                    obs_clone=_i32(snap["obs_clone"]), obs_z=_f64(snap["obs_z"]).reshape(-1, 2))
+
+    def _outputs(self, N, nf):
+        D = 22 + 6 * N
+        return dict(P=np.zeros((D, D), order="F"), delta_x=np.zeros(D), status=np.zeros(nf, dtype=np.int32),
+                    gamma=np.zeros(nf), clones=np.zeros((N, 12)))
+
+    def prepare_inputs(self, snap):
+        return self._inputs(snap)
+
+    def update(self, inp, out=None):
+        """Host buffers in -> host buffers out (the per-frame call of a host integration)."""
+        if not isinstance(inp, dict) or "Rbc" not in inp:
+            inp = self._inputs(inp)
+        nf = len(inp["feat_off"]) - 1
+        if out is None:
+            out = self._outputs(inp["N"], nf)
+        rc = self._L.orcvio_frame_update(
+            self._h, _dp(inp["clone_R"]), _dp(inp["clone_p"]), inp["N"], _dp(inp["Rbc"]), _dp(inp["tcb"]),
+            _dp(inp["P"]), _ip(inp["feat_off"]), _ip(inp["obs_clone"]), _dp(inp["obs_z"]), nf,
+            _dp(out["P"]), _dp(out["delta_x"]), _ip(out["status"]), _dp(out["gamma"]), _dp(out["clones"]))
+        if rc != 0:
+            raise RuntimeError(f"orcvio_frame_update failed: {rc}")
+        return out
+
+    def load(self, snap):
+        inp = self._inputs(snap)
+        self._keep = inp
+        nf = len(inp["feat_off"]) - 1
+        rc = self._L.orcvio_frame_load(
+            self._h, _dp(inp["clone_R"]), _dp(inp["clone_p"]), inp["N"], _dp(inp["Rbc"]), _dp(inp["tcb"]),
+            _dp(inp["P"]), _ip(inp["feat_off"]), _ip(inp["obs_clone"]), _dp(inp["obs_z"]), nf)
+        if rc != 0:
+            raise RuntimeError(f"orcvio_frame_load failed: {rc}")
+
+    def run(self, repeat=1, stages=False):
+        """Kernel chain on the resident frame; returns total device microseconds over `repeat`
+        runs (and the mean per-stage microseconds when stages=True)."""
+        tot = C.c_float(0)
+        st = np.zeros(6, dtype=np.float32)
+        rc = self._L.orcvio_frame_run(self._h, repeat, C.byref(tot),
+                                      st.ctypes.data_as(C.POINTER(C.c_float)) if stages else None)
+        if rc != 0:
+            raise RuntimeError(f"orcvio_frame_run failed: {rc}")
+        return (tot.value, dict(zip(self.STAGES, st.tolist()))) if stages else tot.value
+
+    def fetch(self):
+        inp = self._keep
+        out = self._outputs(inp["N"], len(inp["feat_off"]) - 1)
+        rc = self._L.orcvio_frame_fetch(self._h, _dp(out["P"]), _dp(out["delta_x"]), _ip(out["status"]),
+                                        _dp(out["gamma"]), _dp(out["clones"]))
+        if rc != 0:
+            raise RuntimeError(f"orcvio_frame_fetch failed: {rc}")
+        return out
+
+    def kernel_launches(self):
+        return int(self._L.orcvio_frame_kernel_launches(self._h))
 
 
 # ---------------------------------------------------------------- stage-level calls

@@ -70,5 +70,13 @@ def build(force=False, verbose=False):
     return LIB
 
 
+def exported_symbols():
+    """Names of every function declared in include/orcvio_b200.h (the C-ABI contract)."""
+    import re
+    hdr = open(os.path.join(HERE, "..", "include", "orcvio_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    return sorted(set(re.findall(r"\b(orcvio_[a-z0-9_]+)\s*\(", hdr)))
+
+
 if __name__ == "__main__":
     print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv))

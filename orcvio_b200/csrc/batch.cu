@@ -43,6 +43,10 @@ struct Batch::PhaseWork {
   bool any_active = false;
   std::vector<int> extra_ints;   // uploaded alongside (clone removal indices)
   const int* d_extra = nullptr;
+  // device views of the uploaded work lists (valid after stage_phase)
+  const Cand* dC = nullptr; const int* dOc = nullptr; const double* dOz = nullptr;
+  const Tile* dTiles = nullptr; const FilterWork* dFw = nullptr;
+  const int* dSmall = nullptr; const int* dLarge = nullptr;
 };
 
 static constexpr int WTILE_MAX_BLK = 8;   // widest clone window a tile may span (blocks)
@@ -233,6 +237,13 @@ struct CandBuild {
 };
 
 void Batch::run_phase(PhaseWork& w, int phase) {
+  stage_phase(w);
+  launch_phase(w, true);
+  (void)phase;
+}
+
+// Pack the work lists of one phase into the pinned blob and upload them (one H2D copy).
+void Batch::stage_phase(PhaseWork& w) {
   const int nC = (int)w.cands.size();
   blob_.reset();
   const size_t o_c = blob_.reserve(sizeof(Cand) * std::max(nC, 1));
@@ -256,15 +267,23 @@ void Batch::run_phase(PhaseWork& w, int phase) {
                  std::max<size_t>(w.tileout_total, 1));
   upload_blob();
   char* d = blob_.dev;
-  const Cand* dC = (const Cand*)(d + o_c);
-  const int* dOc = (const int*)(d + o_oc);
-  const double* dOz = (const double*)(d + o_oz);
-  const Tile* dTiles = (const Tile*)(d + o_t);
-  const FilterWork* dFw = (const FilterWork*)(d + o_f);
-  const int* dSmall = (const int*)(d + o_s);
-  const int* dLarge = (const int*)(d + o_l);
+  w.dC = (const Cand*)(d + o_c);
+  w.dOc = (const int*)(d + o_oc);
+  w.dOz = (const double*)(d + o_oz);
+  w.dTiles = (const Tile*)(d + o_t);
+  w.dFw = (const FilterWork*)(d + o_f);
+  w.dSmall = (const int*)(d + o_s);
+  w.dLarge = (const int*)(d + o_l);
   w.d_extra = (const int*)(d + o_x);
+}
 
+// Kernel chain of one phase on already staged work lists: triangulate -> Jacobian/nullspace/gate
+// -> QR compression -> EKF update; optionally queues the D2H copy of the per-candidate results.
+void Batch::launch_phase(PhaseWork& w, bool download) {
+  const int nC = (int)w.cands.size();
+  const Cand* dC = w.dC; const int* dOc = w.dOc; const double* dOz = w.dOz;
+  const Tile* dTiles = w.dTiles; const FilterWork* dFw = w.dFw;
+  const int* dSmall = w.dSmall; const int* dLarge = w.dLarge;
   int nl = 0;
   cudaEvent_t* e = ev_;
   if (profiling_) CK(cudaEventRecord(e[0], stream_));
@@ -342,11 +361,10 @@ void Batch::run_phase(PhaseWork& w, int phase) {
   }
   launches_ += nl;
   if (launch_error_count() > 0) { ok_ = false; err_ = "kernel launch failed"; }
-  if (nC > 0) {
+  if (nC > 0 && download) {
     CK(cudaMemcpyAsync(hStatus_, dStatus_, sizeof(int) * nC, cudaMemcpyDeviceToHost, stream_));
     CK(cudaMemcpyAsync(hGamma_, dGamma_, sizeof(double) * nC, cudaMemcpyDeviceToHost, stream_));
   }
-  (void)phase;
 }
 
 static void build_tiles(Batch::PhaseWork& w, int fi, int c0, int c1) {
@@ -943,28 +961,75 @@ void Batch::override_noise(double sigma2, double chi2_p) {
   }
 }
 
-// Frozen-window entry: loads clones / P / extrinsics into filter 0 and runs the selected stages.
-int Batch::run_snapshot(const SnapshotIO& io) {
+// ---------------------------------------------------------------------------------------
+// Frozen-window entry ("stack -> compress -> update" on one frame).
+// prepare: host staging of the window + work lists, one upload;  execute: restore the
+// pristine window (D2D) and run the kernel chain;  fetch: results back to host buffers.
+struct Batch::SnapState {
+  PhaseWork w;
+  std::vector<int> order;          // candidate order after sorting -> caller's feature index
+  std::vector<CandBuild> cb;
+  std::vector<CandInfo> info;
+  int N = 0, D = 0, n_feat = 0, nobs_total = 0;
+  bool has_positions = false;
+  double *dP0 = nullptr, *dCl0 = nullptr, *dIm0 = nullptr, *dPos0 = nullptr;   // pristine window
+  long long* dGen0 = nullptr;
+  size_t pos_cap = 0;
+  double *hP0 = nullptr, *hCl0 = nullptr, *hIm0 = nullptr;                      // pinned staging
+  double* hOut = nullptr;          // pinned download buffer (P, dx, clones)
+  size_t hout_cap = 0;
+  ~SnapState() {
+    cudaFree(dP0); cudaFree(dCl0); cudaFree(dIm0); cudaFree(dPos0); cudaFree(dGen0);
+    if (hP0) cudaFreeHost(hP0);
+    if (hCl0) cudaFreeHost(hCl0);
+    if (hIm0) cudaFreeHost(hIm0);
+    if (hOut) cudaFreeHost(hOut);
+  }
+};
+
+void Batch::SnapDeleter::operator()(SnapState* p) const { delete p; }
+
+int Batch::snapshot_prepare(const SnapshotIO& io) {
   if (!ok_) return ORCVIO_ERR_NO_DEVICE;
   const int N = io.n_clones;
   if (N < 1 || N > Ncap_ || io.n_feat < 0) return ORCVIO_ERR_ARG;
+  if (!snap_) {
+    snap_.reset(new SnapState());
+    SnapState& S = *snap_;
+    CK(cudaMalloc(&S.dP0, (size_t)ldp_ * ldp_ * sizeof(double)));
+    CK(cudaMalloc(&S.dCl0, (size_t)Ncap_ * CL_STRIDE * sizeof(double)));
+    CK(cudaMalloc(&S.dIm0, IM_STRIDE * sizeof(double)));
+    CK(cudaMallocHost(&S.hP0, (size_t)ldp_ * ldp_ * sizeof(double)));
+    CK(cudaMallocHost(&S.hCl0, (size_t)Ncap_ * CL_STRIDE * sizeof(double)));
+    CK(cudaMallocHost(&S.hIm0, IM_STRIDE * sizeof(double)));
+    S.hout_cap = (size_t)ldp_ * ldp_ + ldp_ + (size_t)Ncap_ * CL_STRIDE + (size_t)(6 * Ncap_ + 2) * ldr_;
+    CK(cudaMallocHost(&S.hOut, S.hout_cap * sizeof(double)));
+  }
+  SnapState& S = *snap_;
   if (io.n_feat > Fcap_) {
     // grow the feature tables of this (single filter) batch
+    CK(cudaStreamSynchronize(stream_));
     cudaFree(dFpos_); cudaFree(dFgen_);
     Fcap_ = io.n_feat + 1024;
     CK(cudaMalloc(&dFpos_, (size_t)B_ * Fcap_ * FP_STRIDE * sizeof(double)));
     CK(cudaMalloc(&dFgen_, (size_t)B_ * Fcap_ * sizeof(long long)));
   }
   const int D = ORCVIO_LEG + 6 * N;
+  S.N = N; S.D = D; S.n_feat = io.n_feat;
+  // the staging buffers may still be read by the previous call's async copies
+  CK(cudaStreamSynchronize(stream_));
   // ---- host staging of the window
-  std::vector<double> cl((size_t)N * CL_STRIDE, 0.0), im(IM_STRIDE, 0.0);
+  double* cl = S.hCl0;
+  double* im = S.hIm0;
+  std::memset(cl, 0, (size_t)Ncap_ * CL_STRIDE * sizeof(double));
+  std::memset(im, 0, IM_STRIDE * sizeof(double));
   double Rbc[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1}, tcb[3] = {0, 0, 0};
   if (io.R_b2c) std::memcpy(Rbc, io.R_b2c, sizeof(Rbc));
   if (io.t_c_b) std::memcpy(tcb, io.t_c_b, sizeof(tcb));
   for (int k = 0; k < 9; ++k) im[IM_RBC + k] = Rbc[k];
   for (int k = 0; k < 3; ++k) im[IM_TCB + k] = tcb[k];
   for (int c = 0; c < N; ++c) {
-    double* r = cl.data() + (size_t)c * CL_STRIDE;
+    double* r = cl + (size_t)c * CL_STRIDE;
     const double* R = io.clone_R + 9 * (size_t)c;
     const double* p = io.clone_p + 3 * (size_t)c;
     if (io.poses_are_camera) {
@@ -984,25 +1049,37 @@ int Batch::run_snapshot(const SnapshotIO& io) {
   // imu record: current state = newest clone (only used by the state increment)
   for (int k = 0; k < 9; ++k) im[IM_R + k] = cl[(size_t)(N - 1) * CL_STRIDE + CL_R + k];
   for (int k = 0; k < 3; ++k) im[IM_P + k] = cl[(size_t)(N - 1) * CL_STRIDE + CL_P + k];
-  std::vector<double> Pld((size_t)ldp_ * ldp_, 0.0);
-  if (io.P_in)
-    for (int i = 0; i < D; ++i)
-      for (int j = 0; j < D; ++j) Pld[(size_t)i * ldp_ + j] = io.P_in[(size_t)j * D + i];   // column-major in
+  // P: the caller's matrix is column-major and symmetric, the device copy row-major with ld
+  if (io.P_in) {
+    for (int i = 0; i < D; ++i) {
+      std::memcpy(S.hP0 + (size_t)i * ldp_, io.P_in + (size_t)i * D, D * sizeof(double));
+      for (int j = D; j < ldp_; ++j) S.hP0[(size_t)i * ldp_ + j] = 0.0;
+    }
+    for (int i = D; i < ldp_; ++i) std::memset(S.hP0 + (size_t)i * ldp_, 0, ldp_ * sizeof(double));
+  } else {
+    std::memset(S.hP0, 0, (size_t)ldp_ * ldp_ * sizeof(double));
+  }
+  CK(cudaMemcpyAsync(S.dP0, S.hP0, (size_t)ldp_ * ldp_ * sizeof(double), cudaMemcpyHostToDevice, stream_));
+  CK(cudaMemcpyAsync(S.dCl0, S.hCl0, (size_t)Ncap_ * CL_STRIDE * sizeof(double), cudaMemcpyHostToDevice, stream_));
+  CK(cudaMemcpyAsync(S.dIm0, S.hIm0, IM_STRIDE * sizeof(double), cudaMemcpyHostToDevice, stream_));
   FilterHost& F = f_[0];
   F.clones.clear();
   for (int c = 0; c < N; ++c) F.clones.push_back(CloneMeta{c, (double)c, 0.0});
 
-  PhaseWork w;
+  PhaseWork& w = S.w;
+  w = PhaseWork{};
   w.fw.assign(B_, FilterWork{});
   w.cand_begin.assign(B_ + 1, 0);
   FilterWork& fw = w.fw[0];
   fw.N = N; fw.D = D; fw.active = (io.stages & 4) ? 1 : 0;
   w.any_active = fw.active;
   w.maxN = N;
-  std::vector<CandBuild> cb;
+  std::vector<CandBuild>& cb = S.cb;
+  cb.clear();
   cb.reserve(io.n_feat);
   // observations are referenced in place: copy the pools once
   const int nobs_total = io.feat_off[io.n_feat];
+  S.nobs_total = nobs_total;
   w.obs_clone.assign(io.obs_clone, io.obs_clone + nobs_total);
   w.obs_z.assign(io.obs_z, io.obs_z + 2 * (size_t)nobs_total);
   for (int f = 0; f < io.n_feat; ++f) {
@@ -1031,76 +1108,79 @@ int Batch::run_snapshot(const SnapshotIO& io) {
     c.cm_zv = io.obs_z[2 * (size_t)o0 + 1];
     cb.push_back(x);
   }
-  std::vector<CandInfo> info;
-  append_candidates(w, 0, cb, info);
+  S.info.clear();
+  append_candidates(w, 0, cb, S.info);
   const int nC = (int)w.cands.size();
-  // candidate order after sorting -> original feature index
-  std::vector<int> order(nC);
-  for (int c = 0; c < nC; ++c) order[c] = (int)info[c].id;
+  S.order.resize(nC);
+  for (int c = 0; c < nC; ++c) S.order[c] = (int)S.info[c].id;
 
-  // device copies of the pristine window for repeats
-  double *dP0 = nullptr, *dCl0 = nullptr, *dIm0 = nullptr;
-  CK(cudaMalloc(&dP0, Pld.size() * sizeof(double)));
-  CK(cudaMalloc(&dCl0, cl.size() * sizeof(double)));
-  CK(cudaMalloc(&dIm0, im.size() * sizeof(double)));
-  CK(cudaMemcpy(dP0, Pld.data(), Pld.size() * sizeof(double), cudaMemcpyHostToDevice));
-  CK(cudaMemcpy(dCl0, cl.data(), cl.size() * sizeof(double), cudaMemcpyHostToDevice));
-  CK(cudaMemcpy(dIm0, im.data(), im.size() * sizeof(double), cudaMemcpyHostToDevice));
-  std::vector<double> pos_in;
-  if (io.positions_in) {
-    pos_in.assign((size_t)Fcap_ * FP_STRIDE, 0.0);
+  S.has_positions = io.positions_in != nullptr;
+  if (S.has_positions) {
+    if ((size_t)Fcap_ > S.pos_cap) {
+      cudaFree(S.dPos0); cudaFree(S.dGen0);
+      S.pos_cap = Fcap_;
+      CK(cudaMalloc(&S.dPos0, S.pos_cap * FP_STRIDE * sizeof(double)));
+      CK(cudaMalloc(&S.dGen0, S.pos_cap * sizeof(long long)));
+    }
+    std::vector<double> pos_in((size_t)Fcap_ * FP_STRIDE, 0.0);
     for (int f = 0; f < io.n_feat; ++f)
       for (int k = 0; k < 3; ++k) pos_in[(size_t)f * FP_STRIDE + k] = io.positions_in[3 * (size_t)f + k];
+    // mark every slot initialised with its own generation so the kernels use the given positions
+    std::vector<long long> gens(Fcap_, -1);
+    for (int f = 0; f < io.n_feat; ++f) gens[f] = f + 1;
+    CK(cudaMemcpy(S.dPos0, pos_in.data(), pos_in.size() * sizeof(double), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(S.dGen0, gens.data(), gens.size() * sizeof(long long), cudaMemcpyHostToDevice));
   }
-  const bool old_prof = profiling_;
-  profiling_ = true;
   want_iters_ = io.iters || io.cost;
   want_raw_ = io.raw_Hx != nullptr;
   skip_tri_ = !(io.stages & 1);
   skip_jac_ = !(io.stages & 2);
   skip_update_ = !(io.stages & 4);
-  double acc[6] = {0, 0, 0, 0, 0, 0};
-  const int reps = std::max(io.repeat, 1);
-  for (int rep = 0; rep < reps; ++rep) {
-    CK(cudaMemcpyAsync(dP_, dP0, Pld.size() * sizeof(double), cudaMemcpyDeviceToDevice, stream_));
-    CK(cudaMemcpyAsync(dClones_, dCl0, cl.size() * sizeof(double), cudaMemcpyDeviceToDevice, stream_));
-    CK(cudaMemcpyAsync(dImu_, dIm0, im.size() * sizeof(double), cudaMemcpyDeviceToDevice, stream_));
-    if (io.positions_in) {
-      CK(cudaMemcpyAsync(dFpos_, pos_in.data(), pos_in.size() * sizeof(double), cudaMemcpyHostToDevice, stream_));
-      // mark every slot initialised with its own generation so the kernels use the given positions
-      std::vector<long long> gens(Fcap_, -1);
-      for (int f = 0; f < io.n_feat; ++f) gens[f] = f + 1;
-      CK(cudaMemcpy(dFgen_, gens.data(), gens.size() * sizeof(long long), cudaMemcpyHostToDevice));
-      if (skip_tri_) {
-        std::vector<int> st(nC, ST_TRI_VALID);
-        ensure_scratch(std::max(nC, 1), 1, 1, 1);
-        CK(cudaMemcpy(dStatus_, st.data(), sizeof(int) * nC, cudaMemcpyHostToDevice));
-      }
-    } else {
-      CK(cudaMemsetAsync(dFgen_, 0xFF, (size_t)Fcap_ * sizeof(long long), stream_));
-    }
-    run_phase(w, 0);
-    CK(cudaStreamSynchronize(stream_));
-    float ms = 0;
-    cudaEventElapsedTime(&ms, ev_[0], ev_[1]); acc[0] += ms;
-    cudaEventElapsedTime(&ms, ev_[1], ev_[2]); acc[1] += ms;
-    if (!skip_update_ && w.any_active) {
-      cudaEventElapsedTime(&ms, ev_[2], ev_[3]); acc[2] += ms;
-      cudaEventElapsedTime(&ms, ev_[3], ev_[4]); acc[3] += ms;
-      cudaEventElapsedTime(&ms, ev_[4], ev_[5]); acc[4] += ms;
-      cudaEventElapsedTime(&ms, ev_[0], ev_[5]); acc[5] += ms;
-    } else {
-      cudaEventElapsedTime(&ms, ev_[0], ev_[2]); acc[5] += ms;
-    }
+  stage_phase(w);
+  if (skip_tri_ && nC > 0) {
+    std::vector<int> st(nC, ST_TRI_VALID);
+    CK(cudaMemcpy(dStatus_, st.data(), sizeof(int) * nC, cudaMemcpyHostToDevice));
   }
-  profiling_ = old_prof;
-  if (io.timings_us)
-    for (int k = 0; k < 6; ++k) io.timings_us[k] = (float)(acc[k] * 1000.0 / reps);
-  // ---- outputs (candidate order -> feature order)
+  return ok_ ? ORCVIO_OK : ORCVIO_ERR_CUDA;
+}
+
+// Restore the pristine window and run the kernel chain once (asynchronous on stream_).
+int Batch::snapshot_execute(bool download) {
+  if (!snap_) return ORCVIO_ERR_ARG;
+  SnapState& S = *snap_;
+  CK(cudaMemcpyAsync(dP_, S.dP0, (size_t)ldp_ * ldp_ * sizeof(double), cudaMemcpyDeviceToDevice, stream_));
+  CK(cudaMemcpyAsync(dClones_, S.dCl0, (size_t)Ncap_ * CL_STRIDE * sizeof(double), cudaMemcpyDeviceToDevice, stream_));
+  CK(cudaMemcpyAsync(dImu_, S.dIm0, IM_STRIDE * sizeof(double), cudaMemcpyDeviceToDevice, stream_));
+  if (S.has_positions) {
+    CK(cudaMemcpyAsync(dFpos_, S.dPos0, (size_t)Fcap_ * FP_STRIDE * sizeof(double), cudaMemcpyDeviceToDevice, stream_));
+    CK(cudaMemcpyAsync(dFgen_, S.dGen0, (size_t)Fcap_ * sizeof(long long), cudaMemcpyDeviceToDevice, stream_));
+  } else {
+    CK(cudaMemsetAsync(dFgen_, 0xFF, (size_t)Fcap_ * sizeof(long long), stream_));
+  }
+  launch_phase(S.w, download);
+  return ok_ ? ORCVIO_OK : ORCVIO_ERR_CUDA;
+}
+
+int Batch::snapshot_fetch(const SnapshotIO& io) {
+  if (!snap_) return ORCVIO_ERR_ARG;
+  SnapState& S = *snap_;
+  const int N = S.N, D = S.D, nC = (int)S.w.cands.size();
+  const int n = 6 * N;
+  // queue every download on the stream, then one synchronisation
+  double* hP = S.hOut;
+  double* hDx = hP + (size_t)ldp_ * ldp_;
+  double* hCl = hDx + ldp_;
+  double* hR = hCl + (size_t)Ncap_ * CL_STRIDE;
+  if (io.P_out) CK(cudaMemcpyAsync(hP, dP_, (size_t)D * ldp_ * sizeof(double), cudaMemcpyDeviceToHost, stream_));
+  if (io.delta_x) CK(cudaMemcpyAsync(hDx, dDx_, ldp_ * sizeof(double), cudaMemcpyDeviceToHost, stream_));
+  if (io.clone_out) CK(cudaMemcpyAsync(hCl, dClones_, (size_t)N * CL_STRIDE * sizeof(double), cudaMemcpyDeviceToHost, stream_));
+  if (io.R_thin) CK(cudaMemcpyAsync(hR, dR_, (size_t)n * ldr_ * sizeof(double), cudaMemcpyDeviceToHost, stream_));
+  if (io.r_thin) CK(cudaMemcpyAsync(hR + (size_t)n * ldr_, dRthin_, n * sizeof(double), cudaMemcpyDeviceToHost, stream_));
+  CK(cudaStreamSynchronize(stream_));
   if (io.status || io.gamma)
     for (int c = 0; c < nC; ++c) {
-      if (io.status) io.status[order[c]] = hStatus_[c];
-      if (io.gamma) io.gamma[order[c]] = hGamma_[c];
+      if (io.status) io.status[S.order[c]] = hStatus_[c];
+      if (io.gamma) io.gamma[S.order[c]] = hGamma_[c];
     }
   if (io.iters || io.cost) {
     std::vector<int> it(2 * (size_t)nC);
@@ -1108,56 +1188,78 @@ int Batch::run_snapshot(const SnapshotIO& io) {
     CK(cudaMemcpy(it.data(), dIters_, it.size() * sizeof(int), cudaMemcpyDeviceToHost));
     CK(cudaMemcpy(cs.data(), dCost_, cs.size() * sizeof(double), cudaMemcpyDeviceToHost));
     for (int c = 0; c < nC; ++c) {
-      if (io.iters) { io.iters[2 * order[c]] = it[2 * c]; io.iters[2 * order[c] + 1] = it[2 * c + 1]; }
-      if (io.cost) io.cost[order[c]] = cs[c];
+      if (io.iters) { io.iters[2 * S.order[c]] = it[2 * c]; io.iters[2 * S.order[c] + 1] = it[2 * c + 1]; }
+      if (io.cost) io.cost[S.order[c]] = cs[c];
     }
   }
   if (io.positions) {
-    std::vector<double> fp((size_t)io.n_feat * FP_STRIDE);
+    std::vector<double> fp((size_t)S.n_feat * FP_STRIDE);
     CK(cudaMemcpy(fp.data(), dFpos_, fp.size() * sizeof(double), cudaMemcpyDeviceToHost));
-    for (int f = 0; f < io.n_feat; ++f)
+    for (int f = 0; f < S.n_feat; ++f)
       for (int k = 0; k < 3; ++k) io.positions[3 * (size_t)f + k] = fp[(size_t)f * FP_STRIDE + k];
   }
   if (io.raw_Hx) {
-    const size_t no = (size_t)nobs_total;
+    const size_t no = (size_t)S.nobs_total;
     CK(cudaMemcpy(io.raw_Hx, dRawHx_, no * 12 * sizeof(double), cudaMemcpyDeviceToHost));
     if (io.raw_He) CK(cudaMemcpy(io.raw_He, dRawHe_, no * 12 * sizeof(double), cudaMemcpyDeviceToHost));
     if (io.raw_Hf) CK(cudaMemcpy(io.raw_Hf, dRawHf_, no * 6 * sizeof(double), cudaMemcpyDeviceToHost));
     if (io.raw_r) CK(cudaMemcpy(io.raw_r, dRawR_, no * 2 * sizeof(double), cudaMemcpyDeviceToHost));
   }
-  if (io.P_out) {
-    std::vector<double> Po((size_t)ldp_ * ldp_);
-    CK(cudaMemcpy(Po.data(), dP_, Po.size() * sizeof(double), cudaMemcpyDeviceToHost));
-    for (int i = 0; i < D; ++i)
-      for (int j = 0; j < D; ++j) io.P_out[(size_t)j * D + i] = Po[(size_t)i * ldp_ + j];
-  }
-  if (io.delta_x) {
-    std::vector<double> dx(ldp_);
-    CK(cudaMemcpy(dx.data(), dDx_, ldp_ * sizeof(double), cudaMemcpyDeviceToHost));
-    for (int i = 0; i < D; ++i) io.delta_x[i] = dx[i];
-  }
-  const int n = 6 * N;
-  if (io.R_thin) {
-    std::vector<double> Rm((size_t)n * ldr_);
-    CK(cudaMemcpy(Rm.data(), dR_, Rm.size() * sizeof(double), cudaMemcpyDeviceToHost));
+  if (io.P_out)   // the posterior is exactly symmetric: row-major with ld == column-major D x D
+    for (int i = 0; i < D; ++i) std::memcpy(io.P_out + (size_t)i * D, hP + (size_t)i * ldp_, D * sizeof(double));
+  if (io.delta_x) std::memcpy(io.delta_x, hDx, D * sizeof(double));
+  if (io.R_thin)
     for (int i = 0; i < n; ++i)
-      for (int j = 0; j < n; ++j) io.R_thin[(size_t)j * n + i] = Rm[(size_t)i * ldr_ + j];
-  }
-  if (io.r_thin) CK(cudaMemcpy(io.r_thin, dRthin_, n * sizeof(double), cudaMemcpyDeviceToHost));
-  if (io.clone_out) {
-    std::vector<double> co((size_t)N * CL_STRIDE);
-    CK(cudaMemcpy(co.data(), dClones_, co.size() * sizeof(double), cudaMemcpyDeviceToHost));
+      for (int j = 0; j < n; ++j) io.R_thin[(size_t)j * n + i] = hR[(size_t)i * ldr_ + j];
+  if (io.r_thin) std::memcpy(io.r_thin, hR + (size_t)n * ldr_, n * sizeof(double));
+  if (io.clone_out)
     for (int c = 0; c < N; ++c) {
-      for (int k = 0; k < 9; ++k) io.clone_out[12 * (size_t)c + k] = co[(size_t)c * CL_STRIDE + CL_R + k];
-      for (int k = 0; k < 3; ++k) io.clone_out[12 * (size_t)c + 9 + k] = co[(size_t)c * CL_STRIDE + CL_P + k];
+      for (int k = 0; k < 9; ++k) io.clone_out[12 * (size_t)c + k] = hCl[(size_t)c * CL_STRIDE + CL_R + k];
+      for (int k = 0; k < 3; ++k) io.clone_out[12 * (size_t)c + 9 + k] = hCl[(size_t)c * CL_STRIDE + CL_P + k];
     }
-  }
-  want_iters_ = want_raw_ = skip_tri_ = skip_jac_ = skip_update_ = false;
-  cudaFree(dP0); cudaFree(dCl0); cudaFree(dIm0);
   int herr = 0;
   CK(cudaMemcpy(&herr, dErr_, sizeof(int), cudaMemcpyDeviceToHost));
   if (herr) return ORCVIO_ERR_CAPACITY;
   return ok_ ? ORCVIO_OK : ORCVIO_ERR_CUDA;
+}
+
+// Per-stage device times (us) of the most recent snapshot_execute run with profiling on.
+void Batch::snapshot_stage_times(float* us6) {
+  float ms = 0;
+  const bool upd = !skip_update_ && snap_ && snap_->w.any_active;
+  for (int k = 0; k < 6; ++k) us6[k] = 0.f;
+  cudaEventElapsedTime(&ms, ev_[0], ev_[1]); us6[0] = ms * 1000.f;
+  cudaEventElapsedTime(&ms, ev_[1], ev_[2]); us6[1] = ms * 1000.f;
+  if (upd) {
+    cudaEventElapsedTime(&ms, ev_[2], ev_[3]); us6[2] = ms * 1000.f;
+    cudaEventElapsedTime(&ms, ev_[3], ev_[4]); us6[3] = ms * 1000.f;
+    cudaEventElapsedTime(&ms, ev_[4], ev_[5]); us6[4] = ms * 1000.f;
+    cudaEventElapsedTime(&ms, ev_[0], ev_[5]); us6[5] = ms * 1000.f;
+  } else {
+    cudaEventElapsedTime(&ms, ev_[0], ev_[2]); us6[5] = ms * 1000.f;
+  }
+}
+
+int Batch::run_snapshot(const SnapshotIO& io) {
+  int rc = snapshot_prepare(io);
+  if (rc != ORCVIO_OK) return rc;
+  const bool old_prof = profiling_;
+  profiling_ = true;
+  double acc[6] = {0, 0, 0, 0, 0, 0};
+  const int reps = std::max(io.repeat, 1);
+  for (int rep = 0; rep < reps; ++rep) {
+    snapshot_execute(true);
+    CK(cudaStreamSynchronize(stream_));
+    float us[6];
+    snapshot_stage_times(us);
+    for (int k = 0; k < 6; ++k) acc[k] += us[k];
+  }
+  profiling_ = old_prof;
+  if (io.timings_us)
+    for (int k = 0; k < 6; ++k) io.timings_us[k] = (float)(acc[k] / reps);
+  rc = snapshot_fetch(io);
+  want_iters_ = want_raw_ = skip_tri_ = skip_jac_ = skip_update_ = false;
+  return rc;
 }
 
 int Batch::dense_update(int, const double*, const double*, int, double*) { return ORCVIO_ERR_UNSUPPORTED; }

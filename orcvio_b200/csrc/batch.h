@@ -5,6 +5,7 @@
 #include <cuda_runtime.h>
 
 #include <map>
+#include <memory>
 #include <string>
 #include <vector>
 
@@ -131,6 +132,13 @@ class Batch {
     double* raw_Hx = nullptr; double* raw_He = nullptr; double* raw_Hf = nullptr; double* raw_r = nullptr;
   };
   int run_snapshot(const SnapshotIO& io);
+  // persistent three-step form used by the orcvio_frame_* entry points
+  int snapshot_prepare(const SnapshotIO& io);
+  int snapshot_execute(bool download);
+  int snapshot_fetch(const SnapshotIO& io);
+  void snapshot_stage_times(float* us6);
+  void sync() { cudaStreamSynchronize(stream_); }
+  cudaStream_t stream() const { return stream_; }
   void override_tricfg(double translation_threshold, double cost_threshold, double init_final) {
     tricfg_.translation_threshold = translation_threshold;
     tricfg_.cost_threshold = cost_threshold;
@@ -187,6 +195,11 @@ class Batch {
   void upload_blob();
   void ensure_scratch(size_t n_cand, size_t hblk, size_t rblk, size_t tileout);
   void run_phase(PhaseWork& w, int phase);
+  void stage_phase(PhaseWork& w);
+  void launch_phase(PhaseWork& w, bool download);
+  struct SnapState;
+  struct SnapDeleter { void operator()(SnapState* p) const; };
+  std::unique_ptr<SnapState, SnapDeleter> snap_;
   int* dIters_ = nullptr; double* dCost_ = nullptr; size_t iters_cap_ = 0;
   double *dRawHx_ = nullptr, *dRawHe_ = nullptr, *dRawHf_ = nullptr, *dRawR_ = nullptr; size_t raw_cap_ = 0;
   bool want_iters_ = false, want_raw_ = false, skip_tri_ = false, skip_update_ = false, skip_jac_ = false;

@@ -71,6 +71,14 @@ int orcvio_device_count(void) {
   return n;
 }
 
+int orcvio_set_device(int device) {
+  if (cudaSetDevice(device) != cudaSuccess) {
+    std::fprintf(stderr, "[orcvio_b200] cudaSetDevice(%d) failed\n", device);
+    return ORCVIO_ERR_NO_DEVICE;
+  }
+  return ORCVIO_OK;
+}
+
 const char* orcvio_version(void) { return "orcvio_b200 0.1 (sm_100a)"; }
 
 double orcvio_chi2_quantile(double p, int dof) { return chi2_quantile(p, dof); }
@@ -314,6 +322,115 @@ int orcvio_measurement_jacobians(const double* clone_R, const double* clone_p, i
   io.raw_Hx = Hx; io.raw_He = He; io.raw_Hf = Hf; io.raw_r = r;
   return b->run_snapshot(io);
 }
+
+// ---- persistent frozen-frame handle (bench / stress frame: no allocation per call) -----
+struct orcvio_frame {
+  std::unique_ptr<Batch> b;
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  bool loaded = false;
+};
+
+orcvio_frame* orcvio_frame_create(int n_clones_cap, int flags, double noise_feature_var, double chi2_p,
+                                  double translation_threshold, double cost_threshold,
+                                  double init_final_dist_threshold) {
+  if (n_clones_cap < 1 || n_clones_cap > 31) return nullptr;
+  orcvio_frame* f = new orcvio_frame();
+  f->b = make_snapshot_batch(n_clones_cap, flags, noise_feature_var, chi2_p, translation_threshold,
+                             cost_threshold, init_final_dist_threshold);
+  if (!f->b->ok()) {
+    delete f;
+    return nullptr;
+  }
+  cudaEventCreate(&f->e0);
+  cudaEventCreate(&f->e1);
+  return f;
+}
+
+void orcvio_frame_destroy(orcvio_frame* f) {
+  if (!f) return;
+  if (f->e0) cudaEventDestroy(f->e0);
+  if (f->e1) cudaEventDestroy(f->e1);
+  delete f;
+}
+
+static Batch::SnapshotIO frame_io(const double* clone_R, const double* clone_p, int n_clones,
+                                  const double* R_b2c, const double* t_c_b, const double* P_in,
+                                  const int* feat_off, const int* obs_clone, const double* obs_z, int n_feat) {
+  Batch::SnapshotIO io;
+  io.clone_R = clone_R; io.clone_p = clone_p; io.n_clones = n_clones;
+  io.R_b2c = R_b2c; io.t_c_b = t_c_b; io.P_in = P_in;
+  io.feat_off = feat_off; io.obs_clone = obs_clone; io.obs_z = obs_z; io.n_feat = n_feat;
+  io.stages = 7;
+  return io;
+}
+
+int orcvio_frame_update(orcvio_frame* f, const double* clone_R, const double* clone_p, int n_clones,
+                        const double* R_b2c, const double* t_c_b, const double* P_in, const int* feat_off,
+                        const int* obs_clone, const double* obs_z, int n_feat, double* P_out,
+                        double* delta_x, int* status, double* gamma, double* clone_out) {
+  if (!f || !feat_off || !obs_clone || !obs_z || !clone_R || !clone_p) return ORCVIO_ERR_ARG;
+  Batch::SnapshotIO io = frame_io(clone_R, clone_p, n_clones, R_b2c, t_c_b, P_in, feat_off, obs_clone, obs_z, n_feat);
+  io.P_out = P_out; io.delta_x = delta_x; io.status = status; io.gamma = gamma; io.clone_out = clone_out;
+  int rc = f->b->snapshot_prepare(io);
+  if (rc != ORCVIO_OK) return rc;
+  f->loaded = true;
+  rc = f->b->snapshot_execute(true);
+  if (rc != ORCVIO_OK) return rc;
+  return f->b->snapshot_fetch(io);
+}
+
+int orcvio_frame_load(orcvio_frame* f, const double* clone_R, const double* clone_p, int n_clones,
+                      const double* R_b2c, const double* t_c_b, const double* P_in, const int* feat_off,
+                      const int* obs_clone, const double* obs_z, int n_feat) {
+  if (!f || !feat_off || !obs_clone || !obs_z || !clone_R || !clone_p) return ORCVIO_ERR_ARG;
+  Batch::SnapshotIO io = frame_io(clone_R, clone_p, n_clones, R_b2c, t_c_b, P_in, feat_off, obs_clone, obs_z, n_feat);
+  int rc = f->b->snapshot_prepare(io);
+  f->b->sync();
+  f->loaded = (rc == ORCVIO_OK);
+  return rc;
+}
+
+int orcvio_frame_run(orcvio_frame* f, int repeat, float* total_us, float* stage_us6) {
+  if (!f || !f->loaded || repeat < 1) return ORCVIO_ERR_ARG;
+  Batch& b = *f->b;
+  const long long l0 = b.kernel_launches();
+  if (stage_us6) {
+    double acc[6] = {0, 0, 0, 0, 0, 0};
+    b.set_profiling(true);
+    for (int r = 0; r < repeat; ++r) {
+      b.snapshot_execute(false);
+      b.sync();
+      float us[6];
+      b.snapshot_stage_times(us);
+      for (int k = 0; k < 6; ++k) acc[k] += us[k];
+    }
+    b.set_profiling(false);
+    for (int k = 0; k < 6; ++k) stage_us6[k] = (float)(acc[k] / repeat);
+    if (total_us) *total_us = (float)acc[5];
+  } else {
+    cudaEventRecord(f->e0, b.stream());
+    for (int r = 0; r < repeat; ++r) b.snapshot_execute(false);
+    cudaEventRecord(f->e1, b.stream());
+    b.sync();
+    float ms = 0;
+    cudaEventElapsedTime(&ms, f->e0, f->e1);
+    if (total_us) *total_us = ms * 1000.f;
+  }
+  (void)l0;
+  return b.ok() ? ORCVIO_OK : ORCVIO_ERR_CUDA;
+}
+
+int orcvio_frame_fetch(orcvio_frame* f, double* P_out, double* delta_x, int* status, double* gamma,
+                       double* clone_out) {
+  if (!f || !f->loaded) return ORCVIO_ERR_ARG;
+  Batch::SnapshotIO io;
+  io.P_out = P_out; io.delta_x = delta_x; io.status = status; io.gamma = gamma; io.clone_out = clone_out;
+  // results of the last run: queue the per-candidate download that orcvio_frame_run skipped
+  f->b->snapshot_execute(true);
+  return f->b->snapshot_fetch(io);
+}
+
+long long orcvio_frame_kernel_launches(orcvio_frame* f) { return f ? f->b->kernel_launches() : 0; }
 
 int orcvio_propagate(double*, const double*, const double*, const double*, const double*, const OrcvioImu*,
                      int, double*, int, int, const double*) {
