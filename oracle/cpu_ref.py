@@ -36,7 +36,10 @@ def load():
     L.cpu_ref_frame_update.restype = C.c_int
     L.cpu_ref_frame_update.argtypes = [dp, dp, C.c_int, dp, dp, dp, ip, ip, dp, C.c_int, C.c_int, C.c_double,
                                        C.c_double, C.c_double, C.c_double, C.c_double, dp, dp, ip, dp, dp, dp]
-    L.cpu_ref_time_frames.restype = C.c_double
+    L.cpu_ref_triangulate.restype = C.c_int
+    L.cpu_ref_triangulate.argtypes = [dp, dp, ip, ip, dp, C.c_int, C.c_double, C.c_double, C.c_double, dp, ip, ip, dp]
+    L.cpu_ref_chi2_quantile.restype = C.c_double
+    L.cpu_ref_chi2_quantile.argtypes = [C.c_double, C.c_int]
     return L
 
 

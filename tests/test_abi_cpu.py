@@ -1,0 +1,82 @@
+"""CPU tests of the drop-in boundary: the C-ABI library loads, exports every symbol that
+include/orcvio_b200.h declares, and refuses to compute without a CUDA device (no fallback).
+No compute call is made here."""
+import ctypes
+import os
+
+import pytest
+
+from orcvio_b200 import api, build, configs
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    L = api.lib()
+    syms = build.exported_symbols()
+    assert len(syms) >= 40
+    for s in syms:
+        assert hasattr(L, s), f"{s} declared in include/orcvio_b200.h but not exported"
+    assert b"sm_100a" in L.orcvio_version()
+
+
+def test_struct_layouts_match_header():
+    # sizes the C side uses (9 / 7 doubles; see include/orcvio_b200.h)
+    assert ctypes.sizeof(api.OrcvioFeature) == 72
+    assert ctypes.sizeof(api.OrcvioImu) == 56
+    assert api.FEAT_DTYPE.itemsize == 72 and api.IMU_DTYPE.itemsize == 56
+    # the header compiles as plain C and its struct sizes equal the ctypes mirrors
+    import subprocess
+    import tempfile
+    src = ('#include <stdio.h>\n#include "orcvio_b200.h"\nint main(void){printf("%zu %zu %zu %zu\\n", '
+           'sizeof(OrcvioFeature), sizeof(OrcvioImu), sizeof(OrcvioState), sizeof(OrcvioFrameStats));return 0;}\n')
+    d = tempfile.mkdtemp()
+    with open(os.path.join(d, "t.c"), "w") as fh:
+        fh.write(src)
+    subprocess.check_call(["gcc", "-std=c99", "-I", os.path.join(ROOT, "include"), os.path.join(d, "t.c"),
+                           "-o", os.path.join(d, "t")])
+    sizes = [int(x) for x in subprocess.check_output([os.path.join(d, "t")]).split()]
+    assert sizes == [ctypes.sizeof(api.OrcvioFeature), ctypes.sizeof(api.OrcvioImu),
+                     ctypes.sizeof(api.OrcvioState), ctypes.sizeof(api.OrcvioFrameStats)]
+
+
+def test_product_chi2_quantile_matches_oracle():
+    from oracle import mathutils as mu
+    tab = mu.chi2_table(0.95)
+    for dof in (1, 2, 3, 9, 57, 499):
+        assert abs(api.chi2_quantile(0.95, dof) - tab[dof]) <= 1e-12 * tab[dof]
+
+
+def test_no_device_means_no_compute():
+    """Without a GPU every constructor fails loudly instead of falling back to a CPU path."""
+    L = api.lib()
+    if L.orcvio_device_count() > 0:
+        pytest.skip("a CUDA device is present")
+    with pytest.raises(RuntimeError):
+        api.Frame(20)
+    import helpers as H
+    path = H.write_cfg(configs.make("unity", if_ZUPT_valid=0))
+    with pytest.raises(RuntimeError):
+        api.Batch(path, 2)
+    vio = api.OrcVIO(path)
+    assert vio.initialize() is False
+
+
+def test_configs_match_reference_yaml_when_mounted():
+    ref = "/root/reference/config"
+    if not os.path.isdir(ref):
+        pytest.skip("reference not mounted (GPU box)")
+    cv2 = pytest.importorskip("cv2")
+    for name, fname in (("euroc", "euroc.yaml"), ("unity", "unity.yaml"), ("kitti_odom", "kitti_odom.yaml")):
+        fs = cv2.FileStorage(os.path.join(ref, fname), cv2.FILE_STORAGE_READ)
+        cfg = configs.make(name)
+        for key in ("sw_size", "max_track_len", "noise_feature", "noise_gyro", "noise_acc", "imu_rate",
+                    "use_larvio_flag", "use_left_perturbation_flag", "discard_large_update_flag",
+                    "feature_cost_threshold", "init_final_dist_threshold", "chi_square_threshold_feat",
+                    "max_features_in_one_grid", "if_ZUPT_valid", "least_observation_number",
+                    "rotation_threshold", "translation_threshold", "tracking_rate_threshold"):
+            node = fs.getNode(key)
+            assert not node.empty(), (fname, key)
+            assert abs(node.real() - float(cfg[key])) <= 1e-12 * max(1.0, abs(float(cfg[key]))), (fname, key)
+        T = fs.getNode("T_cam_imu").mat()
+        assert abs(T.ravel() - cfg["T_cam_imu"]).max() < 1e-12
