@@ -159,7 +159,10 @@ int orcvio_triangulate(const double* cam_R, const double* cam_t, int n_clones, c
 /* Stages 1,2,4,5 on one frozen window ("stack -> compress -> update"):
  * triangulate every feature, Jacobian + nullspace + gate, QR compression, EKF update of
  * (state, P).  clone_R/clone_p: body poses; P: D x D with D = 22 + 6 n_clones.
- * flags: bit0 use_larvio, bit1 use_left_perturbation, bit2 discard_large_update.
+ * flags: bit0 use_larvio, bit1 use_left_perturbation, bit2 discard_large_update.  Experimental
+ * selectors: bit3 replaces the QR compression by the normal-equation (information) form (then
+ * R_thin receives G = H^T H and r_thin receives b = H^T r; R^T R == G either way; NOT parity-safe
+ * for ill-conditioned priors), bit4 forces the CTA-level QR of qr_kernel.cu.
  * Outputs (any may be NULL): P_out, delta_x (D), status per feature (bit0 tri valid, bit1
  * gate pass), gamma per feature, positions, R_thin (6N x 6N column-major) and r_thin (6N),
  * updated clone poses (N x 12).  timings_us[8]: device time per stage measured with CUDA
@@ -227,6 +230,9 @@ int orcvio_device_count(void);
 /* select the CUDA device used by handles created afterwards on this thread (one process per GPU) */
 int orcvio_set_device(int device);
 const char* orcvio_version(void);
+/* measured FP64 peaks of the current device (TFLOP/s): plain DFMA and mma.sync m8n8k4 (DMMA);
+ * the roofline denominators for the FP64 kernels (MEASURED_PEAKS.json carries only HBM / bf16) */
+int orcvio_fp64_peak(double* dfma_tflops, double* dmma_tflops);
 /* chi-square quantile used for the gating tables (boost::math::quantile(chi_squared(dof), p),
  * src/orcvio.cpp:481-494) */
 double orcvio_chi2_quantile(double p, int dof);

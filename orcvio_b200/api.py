@@ -90,6 +90,7 @@ def lib():
     L.orcvio_chi2_quantile.argtypes = [C.c_double, C.c_int]
     L.orcvio_version.restype = C.c_char_p
     L.orcvio_set_device.argtypes = [C.c_int]
+    L.orcvio_fp64_peak.argtypes = [dp, dp]
     L.orcvio_triangulate.argtypes = [dp, dp, C.c_int, ip, ip, dp, C.c_int, C.c_double, C.c_double,
                                      C.c_double, dp, ip, ip, dp]
     L.orcvio_snapshot_update.argtypes = [dp, dp, C.c_int, dp, dp, dp, ip, ip, dp, C.c_int, C.c_int,
@@ -508,6 +509,15 @@ def measurement_jacobians(clone_R, clone_p, R_b2c, t_c_b, positions, feat_off, o
     if rc != 0:
         raise RuntimeError(f"orcvio_measurement_jacobians failed: {rc}")
     return Hx, He, Hf, r
+
+
+def fp64_peak():
+    """(DFMA TFLOP/s, DMMA TFLOP/s) measured on the current device."""
+    a, b = C.c_double(0), C.c_double(0)
+    rc = lib().orcvio_fp64_peak(C.byref(a), C.byref(b))
+    if rc != 0:
+        raise RuntimeError(f"orcvio_fp64_peak failed: {rc}")
+    return a.value, b.value
 
 
 def chi2_quantile(p, dof):

@@ -24,6 +24,8 @@ SOURCES = {
     "jac_kernel.cu": [],
     "qr_kernel.cu": [],
     "update_kernel.cu": [],
+    "info_kernel.cu": [],
+    "peak_kernel.cu": [],
     "prop_kernel.cu": [],
     "obj_kernel.cu": [],
     "batch.cu": [],

@@ -14,6 +14,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 namespace ob {
@@ -37,6 +38,10 @@ struct Batch::PhaseWork {
   std::vector<FilterWork> fw;
   std::vector<int> small_list, large_list;
   size_t hblk_total = 0, rows_total = 0, tileout_total = 0, tile_smem_doubles = 0;
+  int rows_cap = 0;              // > 0: row cap of a tile (whitened form); 0: what fits the QR tile
+  int max_tile_rows = 0;
+  size_t arows_total = 0;        // rows of the stacked A matrix (whitened form)
+  int own_wmax_blk = 1;
   int wmax_blk = 1;
   int maxN = 0;
   std::vector<int> cand_begin;   // per filter, size B + 1
@@ -88,6 +93,13 @@ Batch::Batch(const Params& p, int n) : p_(p), B_(n) {
     for (int s = Fcap_ - 1; s >= 0; --s) F.free_slots.push_back(s);
   }
   CK(cudaStreamCreate(&stream_));
+  CK(cudaStreamCreate(&stream2_));
+  CK(cudaEventCreateWithFlags(&ev_fork_, cudaEventDisableTiming));
+  CK(cudaEventCreateWithFlags(&ev_join_, cudaEventDisableTiming));
+  {
+    const char* e = std::getenv("ORCVIO_COMPRESS");
+    compress_qr_ = e && std::string(e) == "qr";
+  }
   for (auto& e : ev_) CK(cudaEventCreate(&e));
   const size_t nB = (size_t)B_;
   CK(cudaMalloc(&dP_, nB * ldp_ * ldp_ * sizeof(double)));
@@ -108,6 +120,9 @@ Batch::Batch(const Params& p, int n) : p_(p), B_(n) {
   CK(cudaMalloc(&dT_, nB * (size_t)ncap * ldt_ * sizeof(double)));
   CK(cudaMalloc(&dDx_, nB * ldp_ * sizeof(double)));
   CK(cudaMemset(dDx_, 0, nB * ldp_ * sizeof(double)));
+  CK(cudaMalloc(&dLs_, nB * ORCVIO_LEG * ORCVIO_LEG * sizeof(double)));
+  CK(cudaMalloc(&dFilterRows_, nB * sizeof(int)));
+  CK(cudaMemset(dFilterRows_, 0, nB * sizeof(int)));
   CK(cudaMalloc(&dErr_, sizeof(int)));
   CK(cudaMemset(dErr_, 0, sizeof(int)));
   // global fallback front for very wide windows (long tracks): 2*(6 Ncap)+8 rows
@@ -128,6 +143,8 @@ Batch::~Batch() {
   cudaFree(dP_); cudaFree(dImu_); cudaFree(dClones_); cudaFree(dFpos_); cudaFree(dFgen_);
   cudaFree(dR_); cudaFree(dS_); cudaFree(dRthin_); cudaFree(dYv_); cudaFree(dT_); cudaFree(dDx_);
   cudaFree(dErr_); cudaFree(dFront_); cudaFree(dChi2_);
+  cudaFree(dAmat_); cudaFree(dPart_);
+  cudaFree(dLs_); cudaFree(dTileRows_); cudaFree(dFilterRows_);
   cudaFree(dHblk_); cudaFree(dRblk_); cudaFree(dTileOut_); cudaFree(dStatus_); cudaFree(dGamma_);
   if (blob_.dev) cudaFree(blob_.dev);
   if (blob_.pinned) cudaFreeHost(blob_.pinned);
@@ -135,6 +152,9 @@ Batch::~Batch() {
   if (hStatus_) cudaFreeHost(hStatus_);
   if (hGamma_) cudaFreeHost(hGamma_);
   for (auto& e : ev_) cudaEventDestroy(e);
+  if (ev_fork_) cudaEventDestroy(ev_fork_);
+  if (ev_join_) cudaEventDestroy(ev_join_);
+  if (stream2_) cudaStreamDestroy(stream2_);
   if (stream_) cudaStreamDestroy(stream_);
 }
 
@@ -287,6 +307,11 @@ void Batch::launch_phase(PhaseWork& w, bool download) {
   int nl = 0;
   cudaEvent_t* e = ev_;
   if (profiling_) CK(cudaEventRecord(e[0], stream_));
+  const bool do_update = w.any_active && !skip_update_;
+  // the whitened form keeps its column of L in registers: windows wider than 8 clone blocks (long
+  // tracks, never with the shipped max_track_len 6) take the QR path
+  const bool use_qr = compress_qr_ || w.wmax_blk > 8;
+  if (do_update && !use_qr) CK(cudaEventRecord(ev_fork_, stream_));
   if (want_iters_ && (size_t)nC > iters_cap_) {
     if (dIters_) cudaFree(dIters_);
     if (dCost_) cudaFree(dCost_);
@@ -335,7 +360,7 @@ void Batch::launch_phase(PhaseWork& w, bool download) {
     nl += (js.n_list > 0) + (jl.n_list > 0);
   }
   if (profiling_) CK(cudaEventRecord(e[2], stream_));
-  if (w.any_active && !skip_update_) {
+  if (do_update) {
     QrArgs qa{};
     qa.cand = dC; qa.status = dStatus_;
     qa.hblk = dHblk_; qa.rblk = dRblk_;
@@ -345,8 +370,6 @@ void Batch::launch_phase(PhaseWork& w, bool download) {
     qa.Rm = dR_; qa.rthin = dRthin_; qa.r_stride = (size_t)(6 * Ncap_ + 1) * ldr_; qa.ldr = ldr_;
     qa.front_scratch = dFront_; qa.front_stride = front_stride_;
     qa.err = dErr_;
-    launch_qr(qa, w.tile_smem_doubles, w.wmax_blk, 6 * w.maxN, stream_, &nl, profiling_ ? e[3] : nullptr);
-    if (profiling_) CK(cudaEventRecord(e[4], stream_));
     UpdArgs ua{};
     ua.fw = dFw; ua.n_filters = B_;
     ua.P = dP_; ua.p_stride = (size_t)ldp_ * ldp_; ua.ldp = ldp_;
@@ -356,7 +379,39 @@ void Batch::launch_phase(PhaseWork& w, bool download) {
     ua.imu = dImu_; ua.clones = dClones_; ua.clone_stride = (size_t)Ncap_ * CL_STRIDE;
     ua.dx = dDx_; ua.lddx = ldp_;
     ua.flags = flags_; ua.sigma2 = p_.feature_observation_noise;
-    launch_update(ua, w.maxN, stream_, &nl);
+    if (use_qr) {
+      launch_qr(qa, w.tile_smem_doubles, w.wmax_blk, 6 * w.maxN, stream_, &nl, profiling_ ? e[3] : nullptr);
+      if (profiling_) CK(cudaEventRecord(e[4], stream_));
+      launch_update(ua, w.maxN, stream_, &nl);
+    } else {
+      if (w.tiles.size() > tilerows_cap_) {
+        if (dTileRows_) cudaFree(dTileRows_);
+        tilerows_cap_ = w.tiles.size() * 2 + 64;
+        CK(cudaMalloc(&dTileRows_, tilerows_cap_ * sizeof(int)));
+      }
+      int max_arows = 0;
+      for (const FilterWork& f : w.fw) max_arows = std::max(max_arows, f.arows);
+      const int nt64 = (6 * w.maxN + 1 + 63) / 64, pairs = nt64 * (nt64 + 1) / 2;
+      const int chunks = std::max(1, (max_arows + SYRK_KC - 1) / SYRK_KC);
+      const size_t need_a = (w.arows_total + 16) * (size_t)ldr_;
+      if (need_a > amat_cap_) {
+        if (dAmat_) cudaFree(dAmat_);
+        amat_cap_ = need_a * 2;
+        CK(cudaMalloc(&dAmat_, amat_cap_ * sizeof(double)));
+      }
+      const size_t need_p = (size_t)B_ * chunks * pairs * 4096;
+      if (need_p > part_cap_) {
+        if (dPart_) cudaFree(dPart_);
+        part_cap_ = need_p * 2;
+        CK(cudaMalloc(&dPart_, part_cap_ * sizeof(double)));
+      }
+      InfoBufs ib{};
+      ib.Ls = dLs_; ib.Amat = dAmat_; ib.part = dPart_;
+      ib.kc = SYRK_KC; ib.max_chunks = chunks; ib.max_pairs = pairs;
+      ib.tile_rows = dTileRows_; ib.filter_rows = dFilterRows_;
+      launch_info_update(qa, ua, ib, (int)w.tiles.size(), w.max_tile_rows, w.wmax_blk, w.maxN, max_arows, stream_,
+                         stream2_, ev_fork_, ev_join_, profiling_ ? e[3] : nullptr, profiling_ ? e[4] : nullptr, &nl);
+    }
     if (profiling_) CK(cudaEventRecord(e[5], stream_));
   }
   launches_ += nl;
@@ -370,6 +425,7 @@ void Batch::launch_phase(PhaseWork& w, bool download) {
 static void build_tiles(Batch::PhaseWork& w, int fi, int c0, int c1) {
   FilterWork& fw = w.fw[fi];
   fw.tile_begin = (int)w.tiles.size();
+  fw.arow0 = (int)w.arows_total;
   int i = c0;
   while (i < c1) {
     Tile t{};
@@ -386,7 +442,9 @@ static void build_tiles(Batch::PhaseWork& w, int fi, int c0, int c1) {
       const int own = c.e_blk - c.s_blk + 1;
       if (wblk > std::max(WTILE_MAX_BLK, own) && c.s_blk != t.c0_blk) break;
       const int rows = t.rows + 2 * c.jac_m - 3;
-      if (rows > qr_tile_rows_cap(6 * wblk)) break;
+      int cap = qr_tile_rows_cap(6 * wblk);
+      if (w.rows_cap > 0) cap = std::min(w.rows_cap, QR_SMEM_BYTES / 8 / ((6 * wblk + 4) & ~3));
+      if (rows > cap) break;
       if (j - i + 1 > QR_THREADS) break;
       t.c1_blk = nc1;
       t.rows = rows;
@@ -395,14 +453,18 @@ static void build_tiles(Batch::PhaseWork& w, int fi, int c0, int c1) {
     t.cand_end = j;
     const int W = 6 * (t.c1_blk - t.c0_blk);
     t.out_off = (int)w.tileout_total;
+    t.arow = (int)w.arows_total;
+    w.arows_total += (size_t)t.rows;
     w.tileout_total += (size_t)W * (W + 1);
     w.tile_smem_doubles = std::max(w.tile_smem_doubles, (size_t)std::max(t.rows, 1) * (W + 2));
+    w.max_tile_rows = std::max(w.max_tile_rows, t.rows);
     w.wmax_blk = std::max(w.wmax_blk, t.c1_blk - t.c0_blk);
     fw.wmax_blk = std::max(fw.wmax_blk, t.c1_blk - t.c0_blk);
     w.tiles.push_back(t);
     i = j;
   }
   fw.tile_end = (int)w.tiles.size();
+  fw.arows = (int)w.arows_total - fw.arow0;
 }
 
 // Append one filter's candidates (sorted by first clone, then id) to the phase work list.
@@ -421,6 +483,7 @@ static void append_candidates(Batch::PhaseWork& w, int fi, std::vector<CandBuild
     c.hblk_off = (int)w.hblk_total;
     w.rows_total += (size_t)std::max(r, 0);
     w.hblk_total += (size_t)std::max(r, 0) * 6 * (c.e_blk - c.s_blk + 1);
+    w.own_wmax_blk = std::max(w.own_wmax_blk, c.e_blk - c.s_blk + 1);
     const int idx = (int)w.cands.size();
     if (c.jac_m <= 8) w.small_list.push_back(idx);
     else w.large_list.push_back(idx);
@@ -613,6 +676,7 @@ int Batch::process(const double* t_img, const OrcvioFeature* feats, const int* f
 
   // ---------------------------------------------------------------- C: removeLostFeatures
   PhaseWork wA;
+  wA.rows_cap = compress_qr_ ? 0 : AFORM_TILE_ROWS;
   wA.fw.assign(B_, FilterWork{});
   wA.cand_begin.assign(B_ + 1, 0);
   for (int fi = 0; fi < B_; ++fi) {
@@ -701,6 +765,7 @@ int Batch::process(const double* t_img, const OrcvioFeature* feats, const int* f
 
   // ---------------------------------------------------------------- E: post-process A, prune
   PhaseWork wB;
+  wB.rows_cap = compress_qr_ ? 0 : AFORM_TILE_ROWS;
   wB.fw.assign(B_, FilterWork{});
   wB.cand_begin.assign(B_ + 1, 0);
   std::vector<int> rm_idx(2 * (size_t)B_, -1), Nbefore(B_, 0);
@@ -1068,6 +1133,7 @@ int Batch::snapshot_prepare(const SnapshotIO& io) {
 
   PhaseWork& w = S.w;
   w = PhaseWork{};
+  w.rows_cap = compress_qr_ ? 0 : AFORM_TILE_ROWS;
   w.fw.assign(B_, FilterWork{});
   w.cand_begin.assign(B_ + 1, 0);
   FilterWork& fw = w.fw[0];

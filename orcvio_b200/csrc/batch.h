@@ -146,6 +146,8 @@ class Batch {
   }
   void override_noise(double sigma2, double chi2_p);
   void override_flags(int flags) { flags_ = flags; }
+  void set_compress_qr(bool on) { compress_qr_ = on; }
+  bool compress_qr() const { return compress_qr_; }
 
   // generic "update with dense H over the full state" used by the object path
   // (removeLostObjects -> measurementUpdate_msckf with a dense H_x)
@@ -163,7 +165,14 @@ class Batch {
   int B_ = 0, Ncap_ = 0, ldp_ = 0, Fcap_ = 0, ldr_ = 0, ldt_ = 0;
   int flags_ = 0;
   std::vector<FilterHost> f_;
-  cudaStream_t stream_ = nullptr;
+  cudaStream_t stream_ = nullptr, stream2_ = nullptr;
+  cudaEvent_t ev_fork_ = nullptr, ev_join_ = nullptr;
+  bool compress_qr_ = false;          // true: QR tiles + chain (qr_kernel.cu); false: whitened form (info_kernel.cu)
+  double *dAmat_ = nullptr, *dPart_ = nullptr;
+  size_t amat_cap_ = 0, part_cap_ = 0;
+  double* dLs_ = nullptr;
+  int *dTileRows_ = nullptr, *dFilterRows_ = nullptr;
+  size_t tilerows_cap_ = 0;
   cudaEvent_t ev_[16];
   // device state
   double *dP_ = nullptr, *dImu_ = nullptr, *dClones_ = nullptr, *dFpos_ = nullptr;

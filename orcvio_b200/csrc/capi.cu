@@ -265,6 +265,7 @@ static std::unique_ptr<Batch> make_snapshot_batch(int n_clones, int flags, doubl
   p.feature_cost_threshold = cthr;
   p.init_final_dist_threshold = ithr;
   std::unique_ptr<Batch> b(new Batch(p, 1));
+  if (flags & 8) b->set_compress_qr(true);     // bit3: QR tiles + chain (qr_kernel.cu) instead of the whitened form
   return b;
 }
 

@@ -1,0 +1,651 @@
+// Stages 4+5, default path -- measurement compression in the whitened ("A") form and the EKF
+// update written around it.
+//
+// Reference: OrcVIO::measurementUpdate_msckf / measurementUpdate_hybrid
+// (src/orcvio.cpp:1654-1763, 1766-1950): when rows > cols the stacked H (M x (L+6N)) is
+// compressed with SuiteSparseQR to H_thin = (Q^T H).topRows, then
+//     S = H P H^T + s^2 I,  K = P H^T S^-1,  dx = K r,  P <- (I - K H) P,  P <- (P + P^T)/2.
+// On a GPU the QR is a chain of ~6N dependent Householder steps per clone block (pure latency:
+// qr_kernel.cu, kept as the selectable alternative, needs milliseconds on the stress frame).
+// This path produces the same posterior from massively parallel dense kernels:
+//   P = F F^T                 Cholesky of the prior in the order [clones | IMU]  (k_chol_prior,
+//                             on a second stream, overlapped with triangulation + Jacobians);
+//                             F_1 = first 6N columns, F_2 = the rest, L = F[clones, clones]
+//   A = H' L                  every gated, nullspace-projected row times L        (k_aform)
+//   W = s^2 I + A^T A, v = A^T r'                                                 (k_syrk, k_syrk_reduce)
+//   W = C C^T, Y = C^-1 F_1^T, y = C^-1 v     Cholesky with F_1 and v carried as extra rows
+//                                              (k_chol_w_solve, strips of F_1 on separate SMs)
+//   dx = Y^T y                                                                    (k_dx)
+//   P+ = s^2 Y^T Y + F_2 F_2^T                                                    (k_pinfo)
+// Derivation: with A = H L the gain is K = F_1 (A^T A + s^2 I)^-1 A^T (push-through identity),
+// hence dx = F_1 W^-1 A^T r and P+ = P - F_1 (I - s^2 W^-1) F_1^T = s^2 F_1 W^-1 F_1^T + F_2 F_2^T:
+// exactly the reference's posterior, symmetric positive semidefinite by construction (the
+// reference's trailing (P + P^T)/2 is the identity on it).
+// Numerics: H' L is formed ROW BY ROW before anything is squared.  A VIO prior has a large
+// common-mode variance (global position / yaw) along which every row of H' is (numerically) zero;
+// multiplying by L first performs that cancellation inside one row (error eps |h| |L|), whereas
+// forming G = H'^T H' first and then L^T G L loses a factor ~rows (measured 2e-9 vs 1e-12 on the
+// Unity-shaped sequence; DESIGN.md "numerics").
+#include "kernels.h"
+
+namespace ob {
+
+__device__ __forceinline__ int pk(int i, int j) { return (i * (i + 1) >> 1) + j; }
+
+// ---------------------------------------------------------------- blocked Cholesky (one CTA)
+// A: packed lower m x m in shared memory (row i at A + i(i+1)/2).  X: `nx` extra dense rows of
+// length m (right-hand sides carried along: X <- X C^-T).  Panels of CHB columns: every thread
+// factors the CHB x CHB diagonal block redundantly in registers (no barrier inside a panel),
+// solves its own row against it, then the trailing matrix gets a rank-CHB update with 4x4
+// register tiles.  Two barriers per panel.  tol != nullptr: pivots <= tol[k] are treated as exact
+// zeros (semidefinite prior: exactly-zero and duplicated states give zero columns).
+constexpr int CHB = 8;
+constexpr int CHOL_THREADS = 512;
+constexpr int CHOL_MAXR = ORCVIO_LEG + 6 * ORCVIO_MAX_OBS + 24;   // rows incl. extra rows, padded
+
+template <class ColOut>
+__device__ void cta_cholesky_blocked(double* __restrict__ A, double* __restrict__ X,
+                                     double (*__restrict__ PT)[CHOL_MAXR], const double* __restrict__ tol,
+                                     int m, int nx, ColOut out) {
+  const int tid = threadIdx.x, nt = blockDim.x;
+  const int mrows = m + nx;
+  auto rowp = [&](int i) -> double* { return (i < m) ? (A + pk(i, 0)) : (X + (size_t)(i - m) * m); };
+  for (int k0 = 0; k0 < m; k0 += CHB) {
+    const int nb = min(CHB, m - k0);
+    __syncthreads();                                   // trailing update of the previous panel done
+    // ---- diagonal block, redundantly per thread, in registers (static indices only)
+    double d[CHB][CHB];
+#pragma unroll
+    for (int a = 0; a < CHB; ++a)
+#pragma unroll
+      for (int b = 0; b <= a; ++b) d[a][b] = (a < nb && b < nb) ? A[pk(k0 + a, k0 + b)] : (a == b ? 1.0 : 0.0);
+    double inv[CHB];
+#pragma unroll
+    for (int c = 0; c < CHB; ++c) {
+      const double p = d[c][c];
+      const bool ok = tol ? (c < nb ? p > tol[k0 + c] : true) : true;
+      const double l = ok ? sqrt(p) : 0.0;
+      inv[c] = ok ? 1.0 / l : 0.0;
+      d[c][c] = l;
+#pragma unroll
+      for (int a = c + 1; a < CHB; ++a) d[a][c] *= inv[c];
+#pragma unroll
+      for (int a = c + 1; a < CHB; ++a)
+#pragma unroll
+        for (int b = c + 1; b <= a; ++b) d[a][b] -= d[a][c] * d[b][c];
+    }
+    if (tid == 0) {
+#pragma unroll
+      for (int a = 0; a < CHB; ++a)
+#pragma unroll
+        for (int b = 0; b <= a; ++b)
+          if (a < nb) out(k0 + a, k0 + b, d[a][b]);
+    }
+    // ---- rows below the block: x <- x L_d^-T
+    for (int i = k0 + nb + tid; i < mrows; i += nt) {
+      const double* ri = rowp(i) + k0;
+      double x[CHB];
+#pragma unroll
+      for (int c = 0; c < CHB; ++c) x[c] = (c < nb) ? ri[c] : 0.0;
+#pragma unroll
+      for (int c = 0; c < CHB; ++c) {
+        double s = x[c];
+#pragma unroll
+        for (int q = 0; q < c; ++q) s -= x[q] * d[c][q];
+        x[c] = s * inv[c];
+      }
+#pragma unroll
+      for (int c = 0; c < CHB; ++c) {
+        PT[c][i] = x[c];
+        if (c < nb) out(i, k0 + c, x[c]);
+      }
+    }
+    __syncthreads();
+    // ---- trailing update: A[i][j] -= sum_c PT[c][i] PT[c][j],  k0+nb <= j <= min(i, m-1)
+    const int r0 = k0 + nb;
+    const int R = mrows - r0;                 // rows left
+    const int Cn = m - r0;                    // columns left
+    if (R <= 0 || Cn <= 0) continue;          // (nb < CHB only for the last panel: r0 % 8 == 0 here)
+    const int TR = (R + 3) >> 2, TC = (Cn + 3) >> 2;
+    const int full = TC * (TC + 1) / 2;       // tiles of the triangular part (ti < TC)
+    const int ntile = full + (TR - TC) * TC;
+    for (int t = tid; t < ntile; t += nt) {
+      int ti, tj;
+      if (t < full) {
+        ti = (int)((sqrtf(8.0f * (float)t + 1.0f) - 1.0f) * 0.5f);
+        while (ti * (ti + 1) / 2 > t) --ti;
+        while ((ti + 1) * (ti + 2) / 2 <= t) ++ti;
+        tj = t - ti * (ti + 1) / 2;
+      } else {
+        const int u = t - full;
+        ti = TC + u / TC;
+        tj = u - (u / TC) * TC;
+      }
+      const int i0 = r0 + 4 * ti, j0 = r0 + 4 * tj;
+      double av[4][4];
+      double* rp[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int i = i0 + u;
+        rp[u] = rowp(min(i, mrows - 1));
+#pragma unroll
+        for (int v = 0; v < 4; ++v) {
+          const int j = j0 + v;
+          av[u][v] = (i < mrows && j < m && j <= i) ? rp[u][j] : 0.0;
+        }
+      }
+#pragma unroll
+      for (int c = 0; c < CHB; ++c) {
+        const double2 a01 = *reinterpret_cast<const double2*>(&PT[c][i0]);
+        const double2 a23 = *reinterpret_cast<const double2*>(&PT[c][i0 + 2]);
+        const double2 b01 = *reinterpret_cast<const double2*>(&PT[c][j0]);
+        const double2 b23 = *reinterpret_cast<const double2*>(&PT[c][j0 + 2]);
+        const double pa[4] = {a01.x, a01.y, a23.x, a23.y};
+        const double pb[4] = {b01.x, b01.y, b23.x, b23.y};
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+#pragma unroll
+          for (int v = 0; v < 4; ++v) av[u][v] -= pa[u] * pb[v];
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int i = i0 + u;
+#pragma unroll
+        for (int v = 0; v < 4; ++v) {
+          const int j = j0 + v;
+          if (i < mrows && j < m && j <= i) rp[u][j] = av[u][v];
+        }
+      }
+    }
+  }
+  __syncthreads();
+}
+
+// ---------------------------------------------------------------- prior factor
+// P = F F^T in the order [clone columns 22..D-1 | IMU columns 0..21].  Outputs
+//   FT (n x ldt, UpdArgs::T): FT[k][c] = F[perm(c)][k] for k < n, c = original column index,
+//   Ls (22 x 22): the trailing factor of the IMU block given the clones (F_2 F_2^T = Ls Ls^T).
+__global__ void __launch_bounds__(CHOL_THREADS) k_chol_prior(UpdArgs a, double* Ls_all) {
+  extern __shared__ double sm[];
+  __shared__ __align__(16) double panel[CHB][CHOL_MAXR];
+  const int fi = blockIdx.x;
+  const FilterWork fw = a.fw[fi];
+  if (!fw.active) return;
+  const int D = fw.D, n = 6 * fw.N, L = ORCVIO_LEG;
+  const double* P = a.P + (size_t)fi * a.p_stride;
+  double* FT = a.T + (size_t)fi * a.t_stride;
+  double* Ls = Ls_all + (size_t)fi * L * L;
+  double* A = sm;
+  double* tol = A + (size_t)D * (D + 1) / 2;
+  const int tid = threadIdx.x, nt = blockDim.x;
+  const int warp = tid >> 5, lane = tid & 31, nw = nt >> 5;
+  auto orig = [&](int q) { return q < n ? L + q : q - n; };
+  for (int i = warp; i < D; i += nw) {
+    const double* Pi = P + (size_t)orig(i) * a.ldp;
+    double* Ai = A + pk(i, 0);
+    for (int j = lane; j <= i; j += 32) Ai[j] = Pi[orig(j)];
+  }
+  for (int i = tid; i < L * L; i += nt) Ls[i] = 0.0;
+  // entries above the diagonal of F are structural zeros: FT[k][orig(i)] = 0 for i < k
+  for (int e = tid; e < n * n; e += nt) {
+    const int k = e / n, i = e - k * n;
+    if (i < k) FT[(size_t)k * a.ldt + L + i] = 0.0;
+  }
+  __syncthreads();
+  for (int i = tid; i < D; i += nt) tol[i] = 1e-12 * fabs(A[pk(i, i)]);
+  const int ldt = a.ldt;
+  cta_cholesky_blocked(A, nullptr, panel, tol, D, 0, [&](int i, int k, double l) {
+    if (k < n) FT[(size_t)k * ldt + orig(i)] = l;
+    else Ls[(size_t)(i - n) * L + (k - n)] = l;
+  });
+}
+
+// ---------------------------------------------------------------- A = [H' L | r']
+// One CTA per row tile (features sorted by first clone; window [c0, c1) of clone blocks).
+// The gated rows are assembled densely in shared memory; thread j owns column j of A and keeps
+// its column of L (the window rows) in registers.
+constexpr int AF_THREADS = 192;
+constexpr int AF_WMAX = 6 * 8;              // widest window handled by this kernel (clone blocks x 6)
+
+__global__ void __launch_bounds__(AF_THREADS) k_aform(QrArgs a, const double* FT_all, size_t t_stride, int ldt,
+                                                      double* Amat, int lda, int* tile_rows) {
+  extern __shared__ double smem[];
+  __shared__ int rowbase[256];
+  __shared__ int wsum[8];
+  const Tile tl = a.tiles[blockIdx.x];
+  const FilterWork fw = a.fw[tl.filter];
+  const int n = 6 * fw.N;
+  const int W = 6 * (tl.c1_blk - tl.c0_blk);
+  const int Wp = W + 2;                      // even stride, column W = residual
+  const int tid = threadIdx.x, nt = blockDim.x;
+  const int warp = tid >> 5, lane = tid & 31, nw = nt >> 5;
+  const int nc = tl.cand_end - tl.cand_begin;      // host guarantees nc <= 256
+  // ---- row bases of the gated candidates (block scan)
+  int total = 0;
+  for (int base = 0; base < nc; base += nt) {
+    const int q = base + tid;
+    int r = 0;
+    if (q < nc) {
+      const int c = tl.cand_begin + q;
+      if (a.status[c] & ST_GATE_PASS) r = 2 * a.cand[c].jac_m - 3;
+    }
+    int incl = r;
+    for (int o = 1; o < 32; o <<= 1) {
+      const int v = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += v;
+    }
+    if (lane == 31) wsum[warp] = incl;
+    __syncthreads();
+    int off = total;
+    for (int w2 = 0; w2 < warp; ++w2) off += wsum[w2];
+    if (q < nc) rowbase[q] = (r > 0) ? (off + incl - r) : -1;
+    for (int w2 = 0; w2 < nw; ++w2) total += wsum[w2];
+    __syncthreads();
+  }
+  const int m = total;
+  if (tid == 0) tile_rows[blockIdx.x] = m;
+  for (int e = tid; e < m * Wp; e += nt) smem[e] = 0.0;
+  __syncthreads();
+  for (int q = warp; q < nc; q += nw) {
+    if (rowbase[q] < 0) continue;
+    const int c = tl.cand_begin + q;
+    const Cand cd = a.cand[c];
+    const int r = 2 * cd.jac_m - 3;
+    const int w = 6 * (cd.e_blk - cd.s_blk + 1);
+    const int coff = 6 * (cd.s_blk - tl.c0_blk);
+    const double* hb = a.hblk + cd.hblk_off;
+    for (int e = lane; e < r * w; e += 32) {
+      const int i = e / w, j = e - i * w;
+      smem[(size_t)(rowbase[q] + i) * Wp + coff + j] = hb[e];
+    }
+    for (int i = lane; i < r; i += 32) smem[(size_t)(rowbase[q] + i) * Wp + W] = a.rblk[cd.row_off + i];
+  }
+  __syncthreads();
+  // ---- thread j: column j of A for every row of the tile
+  const double* FT = FT_all + (size_t)tl.filter * t_stride;
+  double* Arow = Amat + (size_t)tl.arow * lda;
+  const int rows_ub = tl.rows;
+  for (int j = tid; j <= n; j += nt) {
+    if (j == n) {                                      // residual column
+      for (int row = 0; row < rows_ub; ++row) Arow[(size_t)row * lda + n] = (row < m) ? smem[(size_t)row * Wp + W] : 0.0;
+      continue;
+    }
+    double Lw[AF_WMAX];
+    // L[k][j] = FT[j][22 + k], k = 6 c0 + c  (zero above the diagonal: k < j)
+    const double* src = FT + (size_t)j * ldt + ORCVIO_LEG + 6 * tl.c0_blk;
+#pragma unroll
+    for (int c = 0; c < AF_WMAX; ++c) Lw[c] = (c < W) ? src[c] : 0.0;
+    const bool zero_col = (j >= 6 * tl.c1_blk);        // every window row lies above the diagonal
+    for (int row = 0; row < rows_ub; ++row) {
+      double s0 = 0.0, s1 = 0.0;
+      if (row < m && !zero_col) {
+        const double* hr = smem + (size_t)row * Wp;
+#pragma unroll
+        for (int c = 0; c < AF_WMAX; c += 2) {
+          if (c < W) {
+            const double2 h2 = *reinterpret_cast<const double2*>(hr + c);
+            s0 += h2.x * Lw[c];
+            s1 += h2.y * Lw[c + 1];
+          }
+        }
+      }
+      Arow[(size_t)row * lda + j] = s0 + s1;
+    }
+  }
+  // padding columns (n, lda) are never read
+}
+
+// ---------------------------------------------------------------- W_aug partials = A^T A
+// 64 x 64 output tiles (upper tile pairs), split over row chunks; 256 threads x 4x4 registers.
+constexpr int SY_T = 64, SY_KS = 16;
+
+__global__ void __launch_bounds__(256) k_syrk(const FilterWork* fws, const double* Amat, int lda, double* part,
+                                              int kc, int max_chunks, int max_pairs) {
+  const int fi = blockIdx.z;
+  const FilterWork fw = fws[fi];
+  if (!fw.active) return;
+  const int n1 = 6 * fw.N + 1;
+  const int nt_ = (n1 + SY_T - 1) / SY_T;
+  // pair index -> (I, J), I <= J
+  int I = 0, J = 0, pidx = blockIdx.x;
+  {
+    int cnt = 0;
+    bool found = false;
+    for (int ii = 0; ii < nt_ && !found; ++ii)
+      for (int jj = ii; jj < nt_; ++jj) {
+        if (cnt == pidx) { I = ii; J = jj; found = true; break; }
+        ++cnt;
+      }
+    if (!found) return;
+  }
+  const int chunk = blockIdx.y;
+  const int row_begin = chunk * kc;
+  if (row_begin >= fw.arows) return;
+  const int row_end = min(fw.arows, row_begin + kc);
+  const double* A = Amat + (size_t)fw.arow0 * lda;
+  __shared__ __align__(16) double As[SY_KS][SY_T];
+  __shared__ __align__(16) double Bs[SY_KS][SY_T];
+  const int tid = threadIdx.x;
+  const int tx = tid & 15, ty = tid >> 4;
+  double acc[4][4];
+#pragma unroll
+  for (int u = 0; u < 4; ++u)
+#pragma unroll
+    for (int v = 0; v < 4; ++v) acc[u][v] = 0.0;
+  // loader mapping: 16 rows x 64 cols = 512 double2; thread loads 2 double2 per matrix
+  const int lr = tid >> 5, lc = (tid & 31) * 2;       // row 0..7 (+8), column pair
+  const int i0 = I * SY_T, j0 = J * SY_T;
+  const double2 z2 = make_double2(0.0, 0.0);
+  const bool ci_ok = (i0 + lc < lda), cj_ok = (j0 + lc < lda);
+  auto fetch = [&](int r0, double2& a0, double2& a1, double2& b0, double2& b1) {
+    const int ra = r0 + lr, rb = r0 + lr + 8;
+    a0 = a1 = b0 = b1 = z2;
+    if (ra < row_end) {
+      if (ci_ok) a0 = *reinterpret_cast<const double2*>(A + (size_t)ra * lda + i0 + lc);
+      if (cj_ok) b0 = *reinterpret_cast<const double2*>(A + (size_t)ra * lda + j0 + lc);
+    }
+    if (rb < row_end) {
+      if (ci_ok) a1 = *reinterpret_cast<const double2*>(A + (size_t)rb * lda + i0 + lc);
+      if (cj_ok) b1 = *reinterpret_cast<const double2*>(A + (size_t)rb * lda + j0 + lc);
+    }
+  };
+  double2 a0, a1, b0, b1;
+  fetch(row_begin, a0, a1, b0, b1);
+  for (int r0 = row_begin; r0 < row_end; r0 += SY_KS) {
+    __syncthreads();
+    *reinterpret_cast<double2*>(&As[lr][lc]) = a0;
+    *reinterpret_cast<double2*>(&As[lr + 8][lc]) = a1;
+    *reinterpret_cast<double2*>(&Bs[lr][lc]) = b0;
+    *reinterpret_cast<double2*>(&Bs[lr + 8][lc]) = b1;
+    __syncthreads();
+    if (r0 + SY_KS < row_end) fetch(r0 + SY_KS, a0, a1, b0, b1);     // in flight during the FMAs below
+#pragma unroll
+    for (int kk = 0; kk < SY_KS; ++kk) {
+      const double2 x0 = *reinterpret_cast<const double2*>(&As[kk][4 * ty]);
+      const double2 x1 = *reinterpret_cast<const double2*>(&As[kk][4 * ty + 2]);
+      const double2 y0 = *reinterpret_cast<const double2*>(&Bs[kk][4 * tx]);
+      const double2 y1 = *reinterpret_cast<const double2*>(&Bs[kk][4 * tx + 2]);
+      const double av[4] = {x0.x, x0.y, x1.x, x1.y};
+      const double bv[4] = {y0.x, y0.y, y1.x, y1.y};
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+#pragma unroll
+        for (int v = 0; v < 4; ++v) acc[u][v] += av[u] * bv[v];
+    }
+  }
+  double* out = part + (((size_t)fi * max_chunks + chunk) * max_pairs + pidx) * (SY_T * SY_T);
+#pragma unroll
+  for (int u = 0; u < 4; ++u)
+#pragma unroll
+    for (int v = 0; v < 4; ++v) out[(4 * ty + u) * SY_T + 4 * tx + v] = acc[u][v];
+}
+
+// W_aug (lower, (n+1) x ldr in UpdArgs::S): sum of the chunk partials + s^2 on the first n diagonal
+// entries; row n = v = A^T r'.  Also the number of gated rows per filter.
+__global__ void __launch_bounds__(256) k_syrk_reduce(UpdArgs a, const double* part, int kc, int max_chunks,
+                                                     int max_pairs, const Tile* tiles, const int* tile_rows,
+                                                     int* filter_rows) {
+  const int fi = blockIdx.y;
+  const FilterWork fw = a.fw[fi];
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (!fw.active) {
+    if (e == 0) filter_rows[fi] = 0;
+    return;
+  }
+  if (e == 0) {
+    int rows = 0;
+    for (int t = fw.tile_begin; t < fw.tile_end; ++t) rows += tile_rows[t];
+    filter_rows[fi] = rows;
+  }
+  const int n = 6 * fw.N, n1 = n + 1;
+  if (e >= n1 * n1) return;
+  const int i = e / n1, j = e - i * n1;
+  if (j > i) return;                                   // lower triangle: i >= j  -> tile pair (J, I)
+  const int nt_ = (n1 + SY_T - 1) / SY_T;
+  const int TI = j / SY_T, TJ = i / SY_T;              // TI <= TJ
+  int pidx = 0;
+  for (int ii = 0; ii < TI; ++ii) pidx += nt_ - ii;
+  pidx += TJ - TI;
+  const int nchunks = (fw.arows + kc - 1) / kc;
+  double s = 0.0;
+  for (int c = 0; c < nchunks; ++c)
+    s += part[(((size_t)fi * max_chunks + c) * max_pairs + pidx) * (SY_T * SY_T) + (j - TI * SY_T) * SY_T + (i - TJ * SY_T)];
+  if (i == j && i < n) s += a.sigma2;
+  double* S = a.S + (size_t)fi * a.r_stride;
+  S[(size_t)i * a.ldr + j] = s;
+}
+
+// ---------------------------------------------------------------- W = C C^T with F_1, v carried
+// grid (strips, filters).  Every CTA factors W (redundantly -- the factorisation is latency, not
+// throughput) and carries its strip of CS rows of F_1 (and strip 0 the vector v) through it:
+// the strip leaves as the matching columns of Y = C^-1 F_1^T, v leaves as y = C^-1 v.
+constexpr int CS = 16;
+
+__global__ void __launch_bounds__(CHOL_THREADS) k_chol_w_solve(UpdArgs a) {
+  extern __shared__ double sm[];
+  __shared__ __align__(16) double panel[CHB][CHOL_MAXR];
+  const int fi = blockIdx.y;
+  const FilterWork fw = a.fw[fi];
+  if (!fw.active) return;
+  const int n = 6 * fw.N, D = fw.D;
+  const int d0 = blockIdx.x * CS;
+  if (d0 >= D) return;
+  const int nd = min(CS, D - d0);
+  const bool has_v = (blockIdx.x == 0);
+  const int nx = nd + (has_v ? 1 : 0);
+  const double* S = a.S + (size_t)fi * a.r_stride;
+  double* T = a.T + (size_t)fi * a.t_stride;
+  double* yv = a.yv + (size_t)fi * a.ldr;
+  double* A = sm;
+  double* X = A + (size_t)n * (n + 1) / 2;
+  const int tid = threadIdx.x, nt = blockDim.x;
+  const int warp = tid >> 5, lane = tid & 31, nw = nt >> 5;
+  for (int i = warp; i < n; i += nw) {
+    const double* Si = S + (size_t)i * a.ldr;
+    double* Ai = A + pk(i, 0);
+    for (int j = lane; j <= i; j += 32) Ai[j] = Si[j];
+  }
+  // extra rows: X[e][k] = F_1[d0 + e][k] = FT[k][d0 + e];  last row (strip 0): v[k] = S[n][k]
+  for (int e = tid; e < n * nd; e += nt) {
+    const int k = e / nd, q = e - k * nd;
+    X[(size_t)q * n + k] = T[(size_t)k * a.ldt + d0 + q];
+  }
+  if (has_v)
+    for (int k = tid; k < n; k += nt) X[(size_t)nd * n + k] = S[(size_t)n * a.ldr + k];
+  const int ldt = a.ldt;
+  cta_cholesky_blocked(A, X, panel, nullptr, n, nx, [&](int i, int k, double l) {
+    if (i < n) return;
+    const int q = i - n;
+    if (q < nd) T[(size_t)k * ldt + d0 + q] = l;       // Y[k][d0 + q]
+    else yv[k] = l;
+  });
+}
+
+// ---------------------------------------------------------------- dx = Y^T y and the state increment
+// (incrementState_IMUCam, src/orcvio.cpp:4468-4567; same arithmetic as update_kernel.cu k_apply_dx)
+__global__ void __launch_bounds__(512) k_dx(UpdArgs a) {
+  __shared__ double partial[16][ORCVIO_LEG + 6 * ORCVIO_MAX_OBS + 2];
+  __shared__ double dxs[ORCVIO_LEG + 6 * ORCVIO_MAX_OBS + 2];
+  __shared__ int s_apply;
+  const int fi = blockIdx.x;
+  const FilterWork fw = a.fw[fi];
+  if (!fw.active) return;
+  const int n = 6 * fw.N, D = fw.D;
+  const double* Y = a.T + (size_t)fi * a.t_stride;
+  const double* yv = a.yv + (size_t)fi * a.ldr;
+  double* imu = a.imu + (size_t)fi * IM_STRIDE;
+  double* clones = a.clones + (size_t)fi * a.clone_stride;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  // warp w sums rows k = w, w+32, ... ; lanes over columns
+  for (int i = lane; i < D; i += 32) {
+    double s = 0.0;
+    for (int k = warp; k < n; k += 16) s += Y[(size_t)k * a.ldt + i] * yv[k];
+    partial[warp][i] = s;
+  }
+  __syncthreads();
+  for (int i = tid; i < D; i += blockDim.x) {
+    double s = 0.0;
+#pragma unroll 8
+    for (int w2 = 0; w2 < 16; ++w2) s += partial[w2][i];
+    dxs[i] = s;
+    if (a.dx) a.dx[(size_t)fi * a.lddx + i] = s;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    double nv = sqrt((dxs[3] * dxs[3] + dxs[4] * dxs[4]) + dxs[5] * dxs[5]);
+    double np = sqrt((dxs[6] * dxs[6] + dxs[7] * dxs[7]) + dxs[8] * dxs[8]);
+    int apply = 1;
+    if ((nv > 1.0 || np > 1.5) && (a.flags & FL_DISCARD_LARGE)) {
+      apply = 0;
+      imu[IM_DISCARDS] += 1.0;
+    }
+    s_apply = apply;
+    if (a.dx) a.dx[(size_t)fi * a.lddx + a.lddx - 1] = (double)apply;
+    if (apply) {
+      const bool left = (a.flags & FL_LARVIO) || (a.flags & FL_LEFT);
+      double Rt[9], Rn[9];
+      so3_exp(dxs, Rt);
+      if (left) m3_mul(Rt, imu + IM_R, Rn);
+      else m3_mul(imu + IM_R, Rt, Rn);
+      for (int i = 0; i < 9; ++i) imu[IM_R + i] = Rn[i];
+      for (int i = 0; i < 3; ++i) {
+        imu[IM_V + i] += dxs[3 + i];
+        imu[IM_P + i] += dxs[6 + i];
+        imu[IM_BG + i] += dxs[9 + i];
+        imu[IM_BA + i] += dxs[12 + i];
+      }
+      double dq[3] = {dxs[15] / 2.0, dxs[16] / 2.0, dxs[17] / 2.0};
+      double n2 = (dq[0] * dq[0] + dq[1] * dq[1]) + dq[2] * dq[2];
+      double qw, qs = 1.0;
+      if (n2 <= 1) qw = sqrt(1 - n2);
+      else { qw = 1; qs = 1.0 / sqrt(1 + n2); }
+      double Rq[9], Rb[9];
+      quat_wxyz_to_R(qw * qs, dq[0] * qs, dq[1] * qs, dq[2] * qs, Rq);
+      m3_mulT(imu + IM_RBC, Rq, Rb);
+      for (int i = 0; i < 9; ++i) imu[IM_RBC + i] = Rb[i];
+      for (int i = 0; i < 3; ++i) imu[IM_TCB + i] += dxs[18 + i];
+      imu[IM_TD] += dxs[21];
+    }
+  }
+  __syncthreads();
+  if (!s_apply) return;
+  if (tid < fw.N) {
+    const bool left = (a.flags & FL_LARVIO) || (a.flags & FL_LEFT);
+    double* c = clones + (size_t)tid * CL_STRIDE;
+    const double* d = dxs + ORCVIO_LEG + 6 * tid;
+    double Rt[9], Rn[9];
+    so3_exp(d, Rt);
+    if (left) m3_mul(Rt, c + CL_R, Rn);
+    else m3_mul(c + CL_R, Rt, Rn);
+    for (int i = 0; i < 9; ++i) c[CL_R + i] = Rn[i];
+    for (int i = 0; i < 3; ++i) c[CL_P + i] += d[3 + i];
+    double Rc[9], t[3];
+    m3_mulT(Rn, imu + IM_RBC, Rc);
+    m3_vec(Rn, imu + IM_TCB, t);
+    for (int i = 0; i < 9; ++i) c[CL_RC + i] = Rc[i];
+    for (int i = 0; i < 3; ++i) c[CL_PC + i] = c[CL_P + i] + t[i];
+  }
+}
+
+// ---------------------------------------------------------------- P+ = s^2 Y^T Y + F_2 F_2^T
+// 32 x 32 output tile per CTA; both strips of Y (n x 32) are staged in shared memory with one
+// round trip, then the k loop runs without barriers.
+constexpr int PT = 32;
+
+__global__ void __launch_bounds__(256) k_pinfo(UpdArgs a, const double* Ls_all, const int* filter_rows) {
+  extern __shared__ double sm[];
+  const int fi = blockIdx.z;
+  const FilterWork fw = a.fw[fi];
+  if (!fw.active || filter_rows[fi] == 0) return;       // no gated rows: posterior == prior, P untouched
+  const int n = 6 * fw.N, D = fw.D, L = ORCVIO_LEG;
+  const int i0 = blockIdx.y * PT, j0 = blockIdx.x * PT;
+  if (i0 >= D || j0 >= D) return;
+  const double* Y = a.T + (size_t)fi * a.t_stride;
+  double* P = a.P + (size_t)fi * a.p_stride;
+  double* Ys_i = sm;                       // [n][PT]
+  double* Ys_j = sm + (size_t)n * PT;
+  const int tid = threadIdx.x;
+  for (int e = tid; e < n * PT; e += 256) {
+    const int k = e / PT, c = e - k * PT;
+    Ys_i[e] = (i0 + c < D) ? Y[(size_t)k * a.ldt + i0 + c] : 0.0;
+    Ys_j[e] = (j0 + c < D) ? Y[(size_t)k * a.ldt + j0 + c] : 0.0;
+  }
+  __syncthreads();
+  const int tx = tid & 15, ty = tid >> 4;
+  double acc[2][2] = {{0, 0}, {0, 0}};
+#pragma unroll 4
+  for (int k = 0; k < n; ++k) {
+    const double2 av = *reinterpret_cast<const double2*>(Ys_i + (size_t)k * PT + 2 * ty);
+    const double2 bv = *reinterpret_cast<const double2*>(Ys_j + (size_t)k * PT + 2 * tx);
+    acc[0][0] += av.x * bv.x; acc[0][1] += av.x * bv.y;
+    acc[1][0] += av.y * bv.x; acc[1][1] += av.y * bv.y;
+  }
+  const double* Ls = Ls_all + (size_t)fi * L * L;
+  for (int u = 0; u < 2; ++u)
+    for (int v = 0; v < 2; ++v) {
+      const int i = i0 + 2 * ty + u, j = j0 + 2 * tx + v;
+      if (i >= D || j >= D) continue;
+      double s = a.sigma2 * acc[u][v];
+      if (i < L && j < L) {
+        double t = 0.0;
+        for (int q = 0; q < L; ++q) t += Ls[i * L + q] * Ls[j * L + q];
+        s += t;
+      }
+      P[(size_t)i * a.ldp + j] = s;
+    }
+}
+
+void launch_info_update(const QrArgs& q, const UpdArgs& u, const InfoBufs& ib, int n_tiles, int max_tile_rows,
+                        int max_w_blk, int max_N, int max_arows, cudaStream_t s, cudaStream_t s2,
+                        cudaEvent_t fork, cudaEvent_t join, cudaEvent_t mid1, cudaEvent_t mid2, int* launches) {
+  const int nmax = 6 * max_N, Dmax = ORCVIO_LEG + nmax;
+  const int B = u.n_filters;
+  static bool attr = false;
+  if (!attr) {
+    cudaFuncSetAttribute(k_aform, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+    cudaFuncSetAttribute(k_chol_prior, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(k_chol_w_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(k_pinfo, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+    check_launch("info attributes");
+    attr = true;
+  }
+  // prior factor on the second stream: depends only on P, overlaps triangulation / Jacobians
+  // (the caller recorded `fork` on s before launching them)
+  cudaStreamWaitEvent(s2, fork, 0);
+  const size_t sm_prior = ((size_t)Dmax * (Dmax + 1) / 2 + (size_t)Dmax + 16) * sizeof(double);
+  k_chol_prior<<<B, CHOL_THREADS, sm_prior, s2>>>(u, ib.Ls);
+  check_launch("k_chol_prior");
+  cudaEventRecord(join, s2);
+  cudaStreamWaitEvent(s, join, 0);
+  const int lda = u.ldr;
+  if (n_tiles > 0) {
+    const int W = 6 * max_w_blk;
+    const size_t smem = (size_t)std::max(max_tile_rows, 1) * (W + 2) * sizeof(double);
+    k_aform<<<n_tiles, AF_THREADS, smem, s>>>(q, u.T, u.t_stride, u.ldt, ib.Amat, lda, ib.tile_rows);
+    check_launch("k_aform");
+  }
+  if (mid1) cudaEventRecord(mid1, s);
+  const int nt_ = (nmax + 1 + SY_T - 1) / SY_T;
+  const int pairs = nt_ * (nt_ + 1) / 2;
+  const int kc = ib.kc;
+  const int chunks = std::max(1, (max_arows + kc - 1) / kc);
+  dim3 gs(pairs, chunks, B);
+  k_syrk<<<gs, 256, 0, s>>>(q.fw, ib.Amat, lda, ib.part, kc, ib.max_chunks, ib.max_pairs);
+  check_launch("k_syrk");
+  dim3 gr(((nmax + 1) * (nmax + 1) + 255) / 256, B);
+  k_syrk_reduce<<<gr, 256, 0, s>>>(u, ib.part, kc, ib.max_chunks, ib.max_pairs, q.tiles, ib.tile_rows, ib.filter_rows);
+  check_launch("k_syrk_reduce");
+  const size_t sm_w = ((size_t)nmax * (nmax + 1) / 2 + (size_t)(CS + 1) * nmax + 16) * sizeof(double);
+  dim3 gw((Dmax + CS - 1) / CS, B);
+  k_chol_w_solve<<<gw, CHOL_THREADS, sm_w, s>>>(u);
+  check_launch("k_chol_w_solve");
+  if (mid2) cudaEventRecord(mid2, s);
+  k_dx<<<B, 512, 0, s>>>(u);
+  check_launch("k_dx");
+  dim3 g5((Dmax + PT - 1) / PT, (Dmax + PT - 1) / PT, B);
+  k_pinfo<<<g5, 256, (size_t)2 * nmax * PT * sizeof(double), s>>>(u, ib.Ls, ib.filter_rows);
+  check_launch("k_pinfo");
+  if (launches) *launches += 6 + (n_tiles > 0 ? 1 : 0);
+}
+
+}  // namespace ob

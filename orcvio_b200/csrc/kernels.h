@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <cstdint>
+#include <algorithm>
 #include "dmath.cuh"
 
 namespace ob {
@@ -82,6 +83,7 @@ struct Tile {
   int rows;                      // rows if every candidate passes the gate
   int c0_blk, c1_blk;            // clone-block window [c0, c1)
   int out_off;                   // offset (doubles) of its W x (W+1) output
+  int arow;                      // first row of this tile in the stacked A matrix (whitened form)
 };
 
 struct FilterWork {              // per filter, per update
@@ -90,6 +92,7 @@ struct FilterWork {              // per filter, per update
   int tile_begin, tile_end;      // tiles of this filter, sorted by c0_blk
   int wmax_blk;                  // widest tile window (blocks)
   int active;                    // 0: skip this filter's update entirely
+  int arow0, arows;              // rows of this filter in the stacked A matrix (upper bound)
 };
 
 struct QrArgs {
@@ -112,6 +115,16 @@ struct UpdArgs {
   double* imu; double* clones; size_t clone_stride;
   double* dx; int lddx;                                  // delta_x log per filter
   int flags; double sigma2;
+};
+
+// scratch of the whitened-form update (info_kernel.cu)
+struct InfoBufs {
+  double* Ls;            // per filter 22 x 22 : IMU block factor given the clones
+  double* Amat;          // stacked A = [H' L | r'], lda = ldr
+  double* part;          // split-K partials of A^T A: [filter][chunk][pair][64 x 64]
+  int kc, max_chunks, max_pairs;
+  int* tile_rows;        // gated rows per tile
+  int* filter_rows;      // gated rows per filter (0 -> posterior == prior, P is left untouched)
 };
 
 struct PropSample { double t, w[3], a[3]; };
@@ -148,6 +161,10 @@ void launch_jac_gate(const JacArgs& small_list, const JacArgs& large_list, cudaS
 void launch_qr(const QrArgs& a, size_t tile_smem_doubles, int max_w_blk, int max_n, cudaStream_t s,
                int* launches, cudaEvent_t mid);
 void launch_update(const UpdArgs& a, int max_N, cudaStream_t s, int* launches);
+void launch_update_tail(const UpdArgs& a, int max_N, cudaStream_t s);   // k_trsm + k_apply_dx
+void launch_info_update(const QrArgs& q, const UpdArgs& u, const InfoBufs& ib, int n_tiles, int max_tile_rows,
+                        int max_w_blk, int max_N, int max_arows, cudaStream_t s, cudaStream_t s2,
+                        cudaEvent_t fork, cudaEvent_t join, cudaEvent_t mid1, cudaEvent_t mid2, int* launches);
 void launch_propagate(const PropArgs& a, cudaStream_t s);
 void launch_augment(const AugArgs& a, cudaStream_t s);
 void launch_remove(const RemoveArgs& a, cudaStream_t s);
@@ -155,6 +172,8 @@ void launch_remove(const RemoveArgs& a, cudaStream_t s);
 // tile sizing shared by host tiler and kernels
 constexpr int QR_THREADS = 256;
 constexpr int QR_SMEM_BYTES = 200 * 1024;
+constexpr int AFORM_TILE_ROWS = 128;    // row cap of a tile of the whitened-form path
+constexpr int SYRK_KC = 512;            // rows per split-K chunk of A^T A
 inline int qr_tile_rows_cap(int w_cols) {                // rows that fit beside (w_cols+1) columns
   int ld = w_cols + 2;
   int cap = QR_SMEM_BYTES / 8 / ld;

@@ -1,0 +1,65 @@
+// FP64 peak micro-benchmarks (roofline denominators that MEASURED_PEAKS.json does not carry):
+// dependent-chain-free DFMA throughput and mma.sync m8n8k4 f64 (DMMA) throughput.
+#include <cuda_runtime.h>
+#include "../../include/orcvio_b200.h"
+
+namespace {
+
+__global__ void __launch_bounds__(256) k_dfma_peak(double* out, int iters, double seed) {
+  double a0 = seed + threadIdx.x, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6,
+         a7 = a0 + 7;
+  const double b = 1.0000001, c = 1e-9;
+  for (int i = 0; i < iters; ++i) {
+    a0 = fma(a0, b, c); a1 = fma(a1, b, c); a2 = fma(a2, b, c); a3 = fma(a3, b, c);
+    a4 = fma(a4, b, c); a5 = fma(a5, b, c); a6 = fma(a6, b, c); a7 = fma(a7, b, c);
+  }
+  out[blockIdx.x * blockDim.x + threadIdx.x] = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
+}
+
+__global__ void __launch_bounds__(256) k_dmma_peak(double* out, int iters, double seed) {
+  double a = seed + threadIdx.x * 1e-3, b = 1.0 + threadIdx.x * 1e-6;
+  double c0 = 0, c1 = 0, d0 = 0, d1 = 0, e0 = 0, e1 = 0, f0 = 0, f1 = 0;
+  for (int i = 0; i < iters; ++i) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(e0), "+d"(e1) : "d"(a), "d"(b));
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(f0), "+d"(f1) : "d"(a), "d"(b));
+  }
+  out[blockIdx.x * blockDim.x + threadIdx.x] = ((c0 + c1) + (d0 + d1)) + ((e0 + e1) + (f0 + f1));
+}
+
+}  // namespace
+
+extern "C" int orcvio_fp64_peak(double* dfma_tflops, double* dmma_tflops) {
+  int dev = 0, sms = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return ORCVIO_ERR_NO_DEVICE;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int blocks = sms * 8, threads = 256, iters = 8192;
+  double* out = nullptr;
+  if (cudaMalloc(&out, (size_t)blocks * threads * sizeof(double)) != cudaSuccess) return ORCVIO_ERR_CUDA;
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  float ms = 0;
+  for (int rep = 0; rep < 2; ++rep) {
+    cudaEventRecord(e0);
+    k_dfma_peak<<<blocks, threads>>>(out, iters, 1.0);
+    cudaEventRecord(e1);
+    cudaEventSynchronize(e1);
+    cudaEventElapsedTime(&ms, e0, e1);
+  }
+  if (dfma_tflops) *dfma_tflops = 2.0 * 8 * iters * (double)blocks * threads / (ms * 1e-3) / 1e12;
+  for (int rep = 0; rep < 2; ++rep) {
+    cudaEventRecord(e0);
+    k_dmma_peak<<<blocks, threads>>>(out, iters, 1.0);
+    cudaEventRecord(e1);
+    cudaEventSynchronize(e1);
+    cudaEventElapsedTime(&ms, e0, e1);
+  }
+  // one warp-level m8n8k4 = 8*8*4 MACs = 512 flop
+  if (dmma_tflops) *dmma_tflops = 512.0 * 4 * iters * (double)blocks * (threads / 32) / (ms * 1e-3) / 1e12;
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(out);
+  return cudaGetLastError() == cudaSuccess ? ORCVIO_OK : ORCVIO_ERR_CUDA;
+}

@@ -312,6 +312,22 @@ __global__ void __launch_bounds__(256) k_apply_dx(UpdArgs a) {
   }
 }
 
+void launch_update_tail(const UpdArgs& a, int max_N, cudaStream_t s) {
+  const int nmax = 6 * max_N, Dmax = ORCVIO_LEG + nmax;
+  const int B = a.n_filters;
+  static bool attr = false;
+  if (!attr) {
+    cudaFuncSetAttribute(k_trsm, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    attr = true;
+  }
+  size_t sm_trsm = ((size_t)nmax * (CB + 1) + CB * (CB + 1)) * sizeof(double);
+  dim3 g3((Dmax + CB - 1) / CB, B);
+  k_trsm<<<g3, 256, sm_trsm, s>>>(a, nmax);
+  check_launch("k_trsm");
+  k_apply_dx<<<B, 256, 0, s>>>(a);
+  check_launch("k_apply_dx");
+}
+
 void launch_update(const UpdArgs& a, int max_N, cudaStream_t s, int* launches) {
   const int nmax = 6 * max_N, Dmax = ORCVIO_LEG + nmax;
   const int B = a.n_filters;

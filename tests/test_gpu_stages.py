@@ -90,16 +90,17 @@ def _compare_update(snap, flags, sigma2, tri, out, ref):
     assert rel.max() < 1e-9, f"gamma rel err {rel.max()}"
     assert np.array_equal(out["status"] & 2, ref["status"] & 2), "gate decisions differ"
     assert (ref["status"] & 2).sum() > 0
-    # compressed factor: R^T R == H^T H, R^T r_thin == H^T r  (basis invariant)
-    Hs = ref["H"][:, 22:]
-    R = out["R_thin"]
-    G_ref = Hs.T @ Hs
-    G = R.T @ R
-    assert np.abs(G - G_ref).max() <= 1e-10 * np.abs(G_ref).max()
-    b_ref = Hs.T @ ref["r"]
-    b = R.T @ out["r_thin"]
-    assert np.abs(b - b_ref).max() <= 1e-10 * max(np.abs(b_ref).max(), 1e-300)
-    assert np.abs(np.tril(R, -1)).max() == 0.0
+    if flags & FL_QR:
+        # QR path: compressed factor with R^T R == H^T H, R^T r_thin == H^T r  (basis invariant)
+        Hs = ref["H"][:, 22:]
+        R = out["R_thin"]
+        G_ref = Hs.T @ Hs
+        b_ref = Hs.T @ ref["r"]
+        G = R.T @ R
+        b = R.T @ out["r_thin"]
+        assert np.abs(np.tril(R, -1)).max() == 0.0
+        assert np.abs(G - G_ref).max() <= 1e-10 * np.abs(G_ref).max()
+        assert np.abs(b - b_ref).max() <= 1e-10 * max(np.abs(b_ref).max(), 1e-300)
     # posterior
     dx_ref = ref["delta_x"]
     assert np.abs(out["delta_x"] - dx_ref).max() <= 1e-9 * np.abs(dx_ref).max()
@@ -108,20 +109,26 @@ def _compare_update(snap, flags, sigma2, tri, out, ref):
     assert np.abs(out["P"] - out["P"].T).max() == 0.0
 
 
+FL_QR = 8      # default (0): whitened-form compression (info_kernel.cu); 8: QR tiles + chain
+
+
+@pytest.mark.parametrize("compress", [0, FL_QR])
 @pytest.mark.parametrize("flags,n_clones,n_feat,max_len,full", [
     (0, 20, 300, 6, False),
     (H.FL_LARVIO, 20, 60, 6, False),      # fewer rows than columns: no-compression case
     (H.FL_LEFT, 30, 800, 6, False),
     (0, 10, 40, 6, True),                 # long tracks (m = N): wide-window path
+    (0, 30, 2000, 6, False),
 ])
-def test_snapshot_update(flags, n_clones, n_feat, max_len, full):
+def test_snapshot_update(flags, n_clones, n_feat, max_len, full, compress):
+    flags = flags | compress
     snap = synth.stress_snapshot(n_clones, n_feat, max_len, seed=11, full_tracks=full)
     sigma2 = 0.002 ** 2 * 4
     tri = dict(cost_threshold=1e-3, init_final_dist_threshold=100.0)
     out = api.snapshot_update(snap, flags=flags, noise_var=sigma2, translation_threshold=-1.0,
                               cost_threshold=tri["cost_threshold"],
                               init_final_dist_threshold=tri["init_final_dist_threshold"])
-    ref = H.oracle_snapshot_update(snap, flags, sigma2, tri=dict(translation_threshold=-1.0, **tri))
+    ref = H.oracle_snapshot_update(snap, flags & 7, sigma2, tri=dict(translation_threshold=-1.0, **tri))
     _compare_update(snap, flags, sigma2, tri, out, ref)
     # clone poses after the state increment
     vio = ref["vio"]
