@@ -247,6 +247,7 @@ class OrcVIO:
 
     # -- object path (stage 3, filter side)
     def setStateCov(self, imu_dim, num_clone):
+        self._dim_override = imu_dim + 6 * num_clone
         return self._L.orcvio_set_state_cov(self._h, imu_dim, num_clone)
 
     def setWinPoseTimestamps(self, ts):
@@ -266,6 +267,8 @@ class OrcVIO:
         rows, odim = Hf_.shape
         d = C.c_int(0)
         self._L.orcvio_get_cov(self._h, None, 0, C.byref(d))
+        if getattr(self, "_dim_override", None):
+            d = C.c_int(self._dim_override)
         Hx_o = np.zeros((rows, d.value), order="F")
         Hf_o = np.zeros((rows, odim), order="F")
         res_o = np.zeros(rows)
@@ -449,6 +452,51 @@ class Frame:
 
 
 # ---------------------------------------------------------------- stage-level calls
+def object_residuals(frames_wTc, wTo, shape, kps, zs, zb, left=True, new_residual=False):
+    """Stage 3 functor evaluation (O1-O4): returns dict(fvec, fjac_cam, fjac_obj, zs_num, cam_pose_se3)."""
+    L = lib()
+    frames = _f64(frames_wTc).reshape(-1, 16)
+    T = frames.shape[0]
+    kps = _f64(kps).reshape(-1, 3)
+    K = kps.shape[0]
+    zs = _f64(zs).reshape(T, K, 2)
+    zb = _f64(zb).reshape(T, 4)
+    wTo, shape = _f64(wTo).reshape(16), _f64(shape).reshape(3)
+    cap = 2 * K * T + 4 * T
+    odim = 9 + 3 * K
+    fvec = np.zeros(cap)
+    jc = np.zeros(cap * 6)
+    jo = np.zeros(cap * odim)
+    zn = np.zeros(T, dtype=np.int32)
+    xi = np.zeros((6, T), order="F")
+    rows = C.c_int(0)
+    rc = L.orcvio_object_residuals(_dp(frames), T, _dp(wTo), _dp(shape), _dp(kps), K, _dp(zs), _dp(zb),
+                                   (1 if left else 0) | (2 if new_residual else 0), _dp(fvec), _dp(jc), _dp(jo),
+                                   _ip(zn), _dp(xi), C.byref(rows))
+    if rc != 0:
+        raise RuntimeError(f"orcvio_object_residuals failed: {rc}")
+    r = rows.value
+    return dict(fvec=fvec[:r].copy(), fjac_cam=jc[:r * 6].reshape(6, r).T.copy(),
+                fjac_obj=jo[:r * odim].reshape(odim, r).T.copy(), zs_num=zn, cam_pose_se3=np.array(xi))
+
+
+def propagate(R, v, p, t, bg, ba, gyro_old, acc_old, imu, P, flags, noise4):
+    """Stage 6 stand-alone: (R, v, p, t, P) after the IMU samples `imu` ((n,7) rows [t, w, a])."""
+    L = lib()
+    st = np.zeros(16)
+    st[:9] = _f64(R).reshape(9)
+    st[9:12] = v
+    st[12:15] = p
+    st[15] = t
+    Pm = np.ascontiguousarray(P, dtype=np.float64).copy()
+    arr = imu_array(imu)
+    rc = L.orcvio_propagate(_dp(st), _dp(_f64(bg)), _dp(_f64(ba)), _dp(_f64(gyro_old)), _dp(_f64(acc_old)),
+                            arr.ctypes.data, len(arr), _dp(Pm), Pm.shape[0], flags, _dp(_f64(noise4)))
+    if rc != 0:
+        raise RuntimeError(f"orcvio_propagate failed: {rc}")
+    return st[:9].reshape(3, 3).copy(), st[9:12].copy(), st[12:15].copy(), float(st[15]), Pm
+
+
 def triangulate(cam_R, cam_t, feat_off, obs_clone, obs_z, translation_threshold=-1.0,
                 cost_threshold=4.7673e-4, init_final_dist_threshold=5.0):
     L = lib()

@@ -1328,7 +1328,4 @@ int Batch::run_snapshot(const SnapshotIO& io) {
   return rc;
 }
 
-int Batch::dense_update(int, const double*, const double*, int, double*) { return ORCVIO_ERR_UNSUPPORTED; }
-int Batch::dense_gate(int, const double*, const double*, int, double*) { return ORCVIO_ERR_UNSUPPORTED; }
-
 }  // namespace ob

@@ -64,6 +64,7 @@ struct FilterHost {
   std::vector<double> cgamma[2];
   // object-update test hooks (include/orcvio/orcvio.h:101-119)
   int leg_dim_override = -1;
+  int num_clone_override = -1;
   bool dcampose_fixed = false;
 };
 
@@ -149,10 +150,17 @@ class Batch {
   void set_compress_qr(bool on) { compress_qr_ = on; }
   bool compress_qr() const { return compress_qr_; }
 
-  // generic "update with dense H over the full state" used by the object path
-  // (removeLostObjects -> measurementUpdate_msckf with a dense H_x)
-  int dense_update(int i, const double* Hx_colmajor, const double* res, int rows, double* dx_out);
-  int dense_gate(int i, const double* Hx_colmajor, const double* res, int rows, double* gamma_out);
+  // stage 3, filter side (objects.cu)
+  int construct_object_jacobians(int fi, const double* jac_sensor, int rows, const double* timestamps, int n_ts,
+                                 const double* Hf, int odim, const double* res, const int* zs_num,
+                                 const double* cam_pose_se3, double* Hx_out, double* Hf_out, double* res_out,
+                                 int* rows_out);
+  int object_update(int fi, const double* Hx, const double* Hf, const double* res, int rows, int odim,
+                    int* status_out, double* gamma_out);
+  // stage 6 stand-alone (objects.cu)
+  int propagate_standalone(double* state16, const double* bg, const double* ba, const double* gyro_old,
+                           const double* acc_old, const OrcvioImu* imu, int n, double* P, int D,
+                           const double* noise4);
 
   int Ncap() const { return Ncap_; }
   int ldp() const { return ldp_; }
@@ -215,5 +223,9 @@ class Batch {
   void download_mirrors();
   void init_filter_device(int i);
 };
+
+int object_residuals(const double* frames_wTc, int T, const double* wTo, const double* shape, const double* kps,
+                     int K, const double* zs, const double* zb, int flags, double* fvec, double* fjac_cam,
+                     double* fjac_obj, int* zs_num, double* cam_pose_se3, int* rows_out);
 
 }  // namespace ob

@@ -433,28 +433,61 @@ int orcvio_frame_fetch(orcvio_frame* f, double* P_out, double* delta_x, int* sta
 
 long long orcvio_frame_kernel_launches(orcvio_frame* f) { return f ? f->b->kernel_launches() : 0; }
 
-int orcvio_propagate(double*, const double*, const double*, const double*, const double*, const OrcvioImu*,
-                     int, double*, int, int, const double*) {
-  return ORCVIO_ERR_UNSUPPORTED;
+int orcvio_propagate(double* state16, const double* bg, const double* ba, const double* gyro_old,
+                     const double* acc_old, const OrcvioImu* imu, int n, double* P, int D, int flags,
+                     const double* noise4) {
+  if (!state16 || !P || !noise4 || (n > 0 && !imu)) return ORCVIO_ERR_ARG;
+  if (D < ORCVIO_LEG || (D - ORCVIO_LEG) % 6 != 0) return ORCVIO_ERR_ARG;
+  auto b = make_snapshot_batch((D - ORCVIO_LEG) / 6, flags, 1.0, 0.95, -1.0, 1e300, 1e300);
+  if (!b->ok()) return ORCVIO_ERR_NO_DEVICE;
+  return b->propagate_standalone(state16, bg, ba, gyro_old, acc_old, imu, n, P, D, noise4);
 }
 
-int orcvio_object_residuals(const double*, int, const double*, const double*, const double*, int,
-                            const double*, const double*, int, double*, double*, double*, int*, double*, int*) {
-  return ORCVIO_ERR_UNSUPPORTED;
+int orcvio_object_residuals(const double* frames_wTc, int T, const double* wTo, const double* shape,
+                            const double* kps, int K, const double* zs, const double* zb, int flags, double* fvec,
+                            double* fjac_cam, double* fjac_obj, int* zs_num, double* cam_pose_se3, int* rows_out) {
+  if (!frames_wTc || !wTo || !shape || !kps || !zs || !zb) return ORCVIO_ERR_ARG;
+  return object_residuals(frames_wTc, T, wTo, shape, kps, K, zs, zb, flags, fvec, fjac_cam, fjac_obj, zs_num,
+                          cam_pose_se3, rows_out);
 }
 
-int orcvio_construct_object_jacobians(orcvio_handle*, const double*, int, const double*, int, const double*, int,
-                                      const double*, const int*, const double*, double*, double*, double*, int*) {
-  return ORCVIO_ERR_UNSUPPORTED;
+int orcvio_construct_object_jacobians(orcvio_handle* h, const double* jac_sensor, int rows, const double* timestamps,
+                                      int n_ts, const double* Hf, int odim, const double* res, const int* zs_num,
+                                      const double* cam_pose_se3, double* Hx_out, double* Hf_out, double* res_out,
+                                      int* rows_out) {
+  if (!h || !h->initialized || !jac_sensor || !timestamps || !Hf || !res || !zs_num || !cam_pose_se3)
+    return ORCVIO_ERR_ARG;
+  return h->b.batch->construct_object_jacobians(0, jac_sensor, rows, timestamps, n_ts, Hf, odim, res, zs_num,
+                                                cam_pose_se3, Hx_out, Hf_out, res_out, rows_out);
 }
 
-int orcvio_remove_lost_objects(orcvio_handle*, const double*, const double*, const double*, int, int, int*,
-                               double*) {
-  return ORCVIO_ERR_UNSUPPORTED;
+int orcvio_remove_lost_objects(orcvio_handle* h, const double* Hx, const double* Hf, const double* res, int rows,
+                               int odim, int* status_out, double* gamma_out) {
+  if (!h || !h->initialized) return ORCVIO_ERR_ARG;
+  if (rows > 0 && (!Hx || !Hf || !res)) return ORCVIO_ERR_ARG;
+  return h->b.batch->object_update(0, Hx, Hf, res, rows, odim, status_out, gamma_out);
 }
 
-int orcvio_set_state_cov(orcvio_handle*, int, int) { return ORCVIO_ERR_UNSUPPORTED; }
-int orcvio_set_win_pose_timestamps(orcvio_handle*, const double*, int) { return ORCVIO_ERR_UNSUPPORTED; }
-int orcvio_fix_dcampose_dimupose_to_i(orcvio_handle*) { return ORCVIO_ERR_UNSUPPORTED; }
+/* test hooks, include/orcvio/orcvio.h:101-119 */
+int orcvio_set_state_cov(orcvio_handle* h, int imu_dim, int num_clone) {
+  if (!h || !h->initialized || imu_dim < 1 || num_clone < 0) return ORCVIO_ERR_ARG;
+  FilterHost& F = h->b.batch->filter(0);
+  F.leg_dim_override = imu_dim;             // the reference hook overwrites LEG_DIM too (orcvio.h:101-107)
+  F.num_clone_override = num_clone;
+  return ORCVIO_OK;
+}
+
+int orcvio_set_win_pose_timestamps(orcvio_handle* h, const double* ts, int n) {
+  if (!h || !h->initialized || (n > 0 && !ts)) return ORCVIO_ERR_ARG;
+  FilterHost& F = h->b.batch->filter(0);
+  F.cur_window_timestamps.assign(ts, ts + n);
+  return ORCVIO_OK;
+}
+
+int orcvio_fix_dcampose_dimupose_to_i(orcvio_handle* h) {
+  if (!h || !h->initialized) return ORCVIO_ERR_ARG;
+  h->b.batch->filter(0).dcampose_fixed = true;
+  return ORCVIO_OK;
+}
 
 }  // extern "C"

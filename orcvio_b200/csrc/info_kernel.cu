@@ -295,6 +295,25 @@ __global__ void __launch_bounds__(AF_THREADS) k_aform(QrArgs a, const double* FT
   // padding columns (n, lda) are never read
 }
 
+// Dense variant for the object update: A = [Hp L | r'] for a projected dense block Hp (rows x n,
+// row-major with leading dimension ldh, residual in column n).
+__global__ void __launch_bounds__(256) k_aform_dense(const double* Hp, int ldh, int rows, int n, const double* FT,
+                                                     int ldt, double* Amat, int lda) {
+  const int row = blockIdx.x;
+  if (row >= rows) return;
+  const double* h = Hp + (size_t)row * ldh;
+  for (int j = threadIdx.x; j <= n; j += blockDim.x) {
+    if (j == n) { Amat[(size_t)row * lda + n] = h[n]; continue; }
+    // L[k][j] = FT[j][22 + k], zero for k < j
+    const double* src = FT + (size_t)j * ldt + ORCVIO_LEG;
+    double s0 = 0.0, s1 = 0.0;
+    int k = j;
+    for (; k + 1 < n; k += 2) { s0 += h[k] * src[k]; s1 += h[k + 1] * src[k + 1]; }
+    if (k < n) s0 += h[k] * src[k];
+    Amat[(size_t)row * lda + j] = s0 + s1;
+  }
+}
+
 // ---------------------------------------------------------------- W_aug partials = A^T A
 // 64 x 64 output tiles (upper tile pairs), split over row chunks; 256 threads x 4x4 registers.
 constexpr int SY_T = 64, SY_KS = 16;
@@ -394,7 +413,8 @@ __global__ void __launch_bounds__(256) k_syrk_reduce(UpdArgs a, const double* pa
   }
   if (e == 0) {
     int rows = 0;
-    for (int t = fw.tile_begin; t < fw.tile_end; ++t) rows += tile_rows[t];
+    if (tiles == nullptr) rows = fw.arows;             // dense (object) update: every row counts
+    else for (int t = fw.tile_begin; t < fw.tile_end; ++t) rows += tile_rows[t];
     filter_rows[fi] = rows;
   }
   const int n = 6 * fw.N, n1 = n + 1;
@@ -595,20 +615,61 @@ __global__ void __launch_bounds__(256) k_pinfo(UpdArgs a, const double* Ls_all, 
     }
 }
 
+static void info_attrs() {
+  static bool attr = false;
+  if (attr) return;
+  cudaFuncSetAttribute(k_aform, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+  cudaFuncSetAttribute(k_chol_prior, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  cudaFuncSetAttribute(k_chol_w_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  cudaFuncSetAttribute(k_pinfo, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+  check_launch("info attributes");
+  attr = true;
+}
+
+// Object update, first half (removeLostObjects -> measurementUpdate_msckf with a dense block):
+// prior factor, A = Hp L, W = s^2 I + A^T A, Cholesky with F_1 / v carried.  Leaves Y in u.T,
+// y in u.yv and W_aug's corner r'^T r' untouched in u.S[n][n]:
+//   gamma = r'^T (Hp P Hp^T + s^2 I)^-1 r' = (r'^T r' - y^T y) / s^2      (Woodbury).
+void launch_info_dense_factor(const UpdArgs& u, const InfoBufs& ib, const double* Hp, int ldh, int rows, int N,
+                              cudaStream_t s) {
+  info_attrs();
+  const int n = 6 * N, D = ORCVIO_LEG + n;
+  const size_t sm_prior = ((size_t)D * (D + 1) / 2 + (size_t)D + 16) * sizeof(double);
+  k_chol_prior<<<1, CHOL_THREADS, sm_prior, s>>>(u, ib.Ls);
+  check_launch("k_chol_prior");
+  k_aform_dense<<<rows, 256, 0, s>>>(Hp, ldh, rows, n, u.T, u.ldt, ib.Amat, u.ldr);
+  check_launch("k_aform_dense");
+  const int nt_ = (n + 1 + SY_T - 1) / SY_T, pairs = nt_ * (nt_ + 1) / 2;
+  const int chunks = std::max(1, (rows + ib.kc - 1) / ib.kc);
+  dim3 gs(pairs, chunks, 1);
+  k_syrk<<<gs, 256, 0, s>>>(u.fw, ib.Amat, u.ldr, ib.part, ib.kc, ib.max_chunks, ib.max_pairs);
+  check_launch("k_syrk");
+  dim3 gr(((n + 1) * (n + 1) + 255) / 256, 1);
+  k_syrk_reduce<<<gr, 256, 0, s>>>(u, ib.part, ib.kc, ib.max_chunks, ib.max_pairs, nullptr, ib.tile_rows, ib.filter_rows);
+  check_launch("k_syrk_reduce");
+  const size_t sm_w = ((size_t)n * (n + 1) / 2 + (size_t)(CS + 1) * n + 16) * sizeof(double);
+  dim3 gw((D + CS - 1) / CS, 1);
+  k_chol_w_solve<<<gw, CHOL_THREADS, sm_w, s>>>(u);
+  check_launch("k_chol_w_solve");
+}
+
+// Object update, second half (after the gate passed): dx, state increment, P+.
+void launch_info_dense_apply(const UpdArgs& u, const InfoBufs& ib, int N, cudaStream_t s) {
+  info_attrs();
+  const int D = ORCVIO_LEG + 6 * N;
+  k_dx<<<1, 512, 0, s>>>(u);
+  check_launch("k_dx");
+  dim3 g5((D + PT - 1) / PT, (D + PT - 1) / PT, 1);
+  k_pinfo<<<g5, 256, (size_t)2 * 6 * N * PT * sizeof(double), s>>>(u, ib.Ls, ib.filter_rows);
+  check_launch("k_pinfo");
+}
+
 void launch_info_update(const QrArgs& q, const UpdArgs& u, const InfoBufs& ib, int n_tiles, int max_tile_rows,
                         int max_w_blk, int max_N, int max_arows, cudaStream_t s, cudaStream_t s2,
                         cudaEvent_t fork, cudaEvent_t join, cudaEvent_t mid1, cudaEvent_t mid2, int* launches) {
   const int nmax = 6 * max_N, Dmax = ORCVIO_LEG + nmax;
   const int B = u.n_filters;
-  static bool attr = false;
-  if (!attr) {
-    cudaFuncSetAttribute(k_aform, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
-    cudaFuncSetAttribute(k_chol_prior, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    cudaFuncSetAttribute(k_chol_w_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    cudaFuncSetAttribute(k_pinfo, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
-    check_launch("info attributes");
-    attr = true;
-  }
+  info_attrs();
   // prior factor on the second stream: depends only on P, overlaps triangulation / Jacobians
   // (the caller recorded `fork` on s before launching them)
   cudaStreamWaitEvent(s2, fork, 0);

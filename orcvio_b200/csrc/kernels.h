@@ -165,6 +165,17 @@ void launch_update_tail(const UpdArgs& a, int max_N, cudaStream_t s);   // k_trs
 void launch_info_update(const QrArgs& q, const UpdArgs& u, const InfoBufs& ib, int n_tiles, int max_tile_rows,
                         int max_w_blk, int max_N, int max_arows, cudaStream_t s, cudaStream_t s2,
                         cudaEvent_t fork, cudaEvent_t join, cudaEvent_t mid1, cudaEvent_t mid2, int* launches);
+void launch_info_dense_factor(const UpdArgs& u, const InfoBufs& ib, const double* Hp, int ldh, int rows, int N,
+                              cudaStream_t s);
+void launch_info_dense_apply(const UpdArgs& u, const InfoBufs& ib, int N, cudaStream_t s);
+void launch_project_dense(double* M, int rows, int ld, int nelim, int ncols, cudaStream_t s);
+void launch_object_rows(const double* frames_wTc, int T, const double* wTo, const double* shape, const double* kps,
+                        int K, const double* zs, const double* zb, int flags, const int* kp_row_off, int rows_kp,
+                        int rows, double* fvec, double* fjac_cam, double* fjac_obj, double* cam_pose_se3,
+                        cudaStream_t s);
+void launch_object_construct(const double* jac_sensor, const double* Hf, const double* res, int rows_in, int odim,
+                             const int* map5, const double* dcam_dimu, int n_kept, int leg, int D, int rows_out,
+                             double* Hx_out, double* Hf_out, double* res_out, cudaStream_t s);
 void launch_propagate(const PropArgs& a, cudaStream_t s);
 void launch_augment(const AugArgs& a, cudaStream_t s);
 void launch_remove(const RemoveArgs& a, cudaStream_t s);

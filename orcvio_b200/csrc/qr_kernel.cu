@@ -47,11 +47,11 @@ struct Front {
 // CTA-wide Householder triangularisation of the logical rows [0, m) of `f` over the columns
 // [c0, c1) plus the right-hand-side column.  On exit the block is upper
 // trapezoidal (entries below the diagonal are zeroed).  All threads of the CTA call this.
-__device__ void cta_householder(const Front& f, int m, int c0, int c1, double* sh) {
+__device__ void cta_householder(const Front& f, int m, int c0, int c1, double* sh, int nelim = -1) {
   const int tid = threadIdx.x, nt = blockDim.x;
   const int warp = tid >> 5, lane = tid & 31, nw = nt >> 5;
   const int ncol = c1 - c0;
-  const int steps = min(ncol, m - 1);
+  const int steps = min(nelim >= 0 ? nelim : ncol, m - 1);
   for (int k = 0; k < steps; ++k) {
     const int ck = c0 + k;
     // sigma = sum_{i>k} a(i,ck)^2 : warp partial sums -> shared
@@ -227,6 +227,22 @@ __global__ void __launch_bounds__(QR_THREADS) k_qr_chain(QrArgs a, int front_row
       }
     }
   }
+}
+
+// Left-nullspace projection of a dense block (removeLostObjects, src/orcvio.cpp:2162 ->
+// nullspace_project_inplace_svd, math_utils.hpp:287-312): M = [H_f | H_x | r] (rows x ncols,
+// row-major in global memory); Householder-eliminates the first `nelim` columns and applies the
+// reflections to every column.  Rows [nelim, rows) of the trailing columns are A^T H_x, A^T r for
+// an orthonormal basis A of null(H_f^T) (any basis gives the same gate value and posterior).
+__global__ void __launch_bounds__(QR_THREADS) k_project_dense(double* M, int rows, int ld, int nelim, int ncols) {
+  __shared__ double red[32];
+  Front f{M, ld, rows, 0, 0x7fffffff, ncols - 1};
+  cta_householder(f, rows, 0, ncols - 1, red, nelim);
+}
+
+void launch_project_dense(double* M, int rows, int ld, int nelim, int ncols, cudaStream_t s) {
+  k_project_dense<<<1, QR_THREADS, 0, s>>>(M, rows, ld, nelim, ncols);
+  check_launch("k_project_dense");
 }
 
 void launch_qr(const QrArgs& a, size_t tile_smem_doubles, int max_w_blk, int max_n, cudaStream_t s,
