@@ -285,6 +285,29 @@ void Batch::stage_phase(PhaseWork& w) {
   if (!w.large_list.empty()) std::memcpy(h + o_l, w.large_list.data(), sizeof(int) * w.large_list.size());
   ensure_scratch(std::max(nC, 1), std::max<size_t>(w.hblk_total, 1), std::max<size_t>(w.rows_total, 1),
                  std::max<size_t>(w.tileout_total, 1));
+  if (!compress_qr_) {          // scratch of the whitened-form path, grown outside any timed region
+    if (w.tiles.size() > tilerows_cap_) {
+      if (dTileRows_) cudaFree(dTileRows_);
+      tilerows_cap_ = w.tiles.size() * 2 + 64;
+      CK(cudaMalloc(&dTileRows_, tilerows_cap_ * sizeof(int)));
+    }
+    int max_arows = 0;
+    for (const FilterWork& f : w.fw) max_arows = std::max(max_arows, f.arows);
+    const int nt64 = (6 * w.maxN + 1 + 63) / 64, pairs = nt64 * (nt64 + 1) / 2;
+    const int chunks = std::max(1, (max_arows + SYRK_KC - 1) / SYRK_KC);
+    const size_t need_a = (w.arows_total + 16) * (size_t)ldr_;
+    if (need_a > amat_cap_) {
+      if (dAmat_) cudaFree(dAmat_);
+      amat_cap_ = need_a * 2;
+      CK(cudaMalloc(&dAmat_, amat_cap_ * sizeof(double)));
+    }
+    const size_t need_p = (size_t)B_ * chunks * pairs * 4096;
+    if (need_p > part_cap_) {
+      if (dPart_) cudaFree(dPart_);
+      part_cap_ = need_p * 2;
+      CK(cudaMalloc(&dPart_, part_cap_ * sizeof(double)));
+    }
+  }
   upload_blob();
   char* d = blob_.dev;
   w.dC = (const Cand*)(d + o_c);
@@ -384,27 +407,10 @@ void Batch::launch_phase(PhaseWork& w, bool download) {
       if (profiling_) CK(cudaEventRecord(e[4], stream_));
       launch_update(ua, w.maxN, stream_, &nl);
     } else {
-      if (w.tiles.size() > tilerows_cap_) {
-        if (dTileRows_) cudaFree(dTileRows_);
-        tilerows_cap_ = w.tiles.size() * 2 + 64;
-        CK(cudaMalloc(&dTileRows_, tilerows_cap_ * sizeof(int)));
-      }
       int max_arows = 0;
       for (const FilterWork& f : w.fw) max_arows = std::max(max_arows, f.arows);
       const int nt64 = (6 * w.maxN + 1 + 63) / 64, pairs = nt64 * (nt64 + 1) / 2;
       const int chunks = std::max(1, (max_arows + SYRK_KC - 1) / SYRK_KC);
-      const size_t need_a = (w.arows_total + 16) * (size_t)ldr_;
-      if (need_a > amat_cap_) {
-        if (dAmat_) cudaFree(dAmat_);
-        amat_cap_ = need_a * 2;
-        CK(cudaMalloc(&dAmat_, amat_cap_ * sizeof(double)));
-      }
-      const size_t need_p = (size_t)B_ * chunks * pairs * 4096;
-      if (need_p > part_cap_) {
-        if (dPart_) cudaFree(dPart_);
-        part_cap_ = need_p * 2;
-        CK(cudaMalloc(&dPart_, part_cap_ * sizeof(double)));
-      }
       InfoBufs ib{};
       ib.Ls = dLs_; ib.Amat = dAmat_; ib.part = dPart_;
       ib.kc = SYRK_KC; ib.max_chunks = chunks; ib.max_pairs = pairs;
