@@ -233,6 +233,8 @@ const char* orcvio_version(void);
 /* measured FP64 peaks of the current device (TFLOP/s): plain DFMA and mma.sync m8n8k4 (DMMA);
  * the roofline denominators for the FP64 kernels (MEASURED_PEAKS.json carries only HBM / bf16) */
 int orcvio_fp64_peak(double* dfma_tflops, double* dmma_tflops);
+/* dependent-chain latencies in cycles: DFMA, sqrt, divide, rsqrt, shared load, __syncthreads(512), shuffle */
+int orcvio_latency_probe(double* cycles7);
 /* chi-square quantile used for the gating tables (boost::math::quantile(chi_squared(dof), p),
  * src/orcvio.cpp:481-494) */
 double orcvio_chi2_quantile(double p, int dof);

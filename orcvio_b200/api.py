@@ -91,6 +91,7 @@ def lib():
     L.orcvio_version.restype = C.c_char_p
     L.orcvio_set_device.argtypes = [C.c_int]
     L.orcvio_fp64_peak.argtypes = [dp, dp]
+    L.orcvio_latency_probe.argtypes = [dp]
     L.orcvio_triangulate.argtypes = [dp, dp, C.c_int, ip, ip, dp, C.c_int, C.c_double, C.c_double,
                                      C.c_double, dp, ip, ip, dp]
     L.orcvio_snapshot_update.argtypes = [dp, dp, C.c_int, dp, dp, dp, ip, ip, dp, C.c_int, C.c_int,
@@ -566,6 +567,15 @@ def fp64_peak():
     if rc != 0:
         raise RuntimeError(f"orcvio_fp64_peak failed: {rc}")
     return a.value, b.value
+
+
+def latency_probe():
+    """Dependent-chain latencies (cycles): dict(dfma, sqrt, div, rsqrt, lds, syncthreads512, shfl64)."""
+    out = np.zeros(7)
+    rc = lib().orcvio_latency_probe(_dp(out))
+    if rc != 0:
+        raise RuntimeError(f"orcvio_latency_probe failed: {rc}")
+    return dict(zip(["dfma", "sqrt", "div", "rsqrt", "lds", "syncthreads512", "shfl64"], out.tolist()))
 
 
 def chi2_quantile(p, dof):

@@ -331,9 +331,7 @@ void Batch::launch_phase(PhaseWork& w, bool download) {
   cudaEvent_t* e = ev_;
   if (profiling_) CK(cudaEventRecord(e[0], stream_));
   const bool do_update = w.any_active && !skip_update_;
-  // the whitened form keeps its column of L in registers: windows wider than 8 clone blocks (long
-  // tracks, never with the shipped max_track_len 6) take the QR path
-  const bool use_qr = compress_qr_ || w.wmax_blk > 8;
+  const bool use_qr = compress_qr_;
   if (do_update && !use_qr) CK(cudaEventRecord(ev_fork_, stream_));
   if (want_iters_ && (size_t)nC > iters_cap_) {
     if (dIters_) cudaFree(dIters_);
@@ -446,7 +444,8 @@ static void build_tiles(Batch::PhaseWork& w, int fi, int c0, int c1) {
       const int nc1 = std::max(t.c1_blk, c.e_blk + 1);
       const int wblk = nc1 - t.c0_blk;
       const int own = c.e_blk - c.s_blk + 1;
-      if (wblk > std::max(WTILE_MAX_BLK, own) && c.s_blk != t.c0_blk) break;
+      const int wlim = (w.rows_cap > 0) ? 6 : WTILE_MAX_BLK;   // whitened form: keep the 36-column kernel
+      if (wblk > std::max(wlim, own) && c.s_blk != t.c0_blk) break;
       const int rows = t.rows + 2 * c.jac_m - 3;
       int cap = qr_tile_rows_cap(6 * wblk);
       if (w.rows_cap > 0) cap = std::min(w.rows_cap, QR_SMEM_BYTES / 8 / ((6 * wblk + 4) & ~3));

@@ -42,45 +42,72 @@ __device__ __forceinline__ int pk(int i, int j) { return (i * (i + 1) >> 1) + j;
 constexpr int CHB = 8;
 constexpr int CHOL_THREADS = 512;
 constexpr int CHOL_MAXR = ORCVIO_LEG + 6 * ORCVIO_MAX_OBS + 24;   // rows incl. extra rows, padded
+constexpr int CHOL_MAXT = (CHOL_MAXR + 3) / 4;                    // 4-row tiles per dimension
 
+struct CholShared {                       // static shared memory of one factorisation
+  double PT[CHB][CHOL_MAXR];              // current panel, transposed: PT[c][row]
+  double dblk[CHB][CHB];                  // factored diagonal block (lower)
+  double dinv[CHB];                       // 1 / diagonal (0 for skipped pivots)
+  unsigned short tdec[CHOL_MAXT * (CHOL_MAXT + 1) / 2][2];   // triangle tile index -> (ti, tj)
+};
+
+// Must be called by all threads once before cta_cholesky_blocked (fills the tile decode table).
+__device__ __forceinline__ void chol_shared_init(CholShared& cs) {
+  for (int ti = threadIdx.x; ti < CHOL_MAXT; ti += blockDim.x)
+    for (int tj = 0; tj <= ti; ++tj) {
+      const int t = ti * (ti + 1) / 2 + tj;
+      cs.tdec[t][0] = (unsigned short)ti;
+      cs.tdec[t][1] = (unsigned short)tj;
+    }
+}
+
+// Factor the nb x nb diagonal block at k0 (thread-local, registers) and publish it.
 template <class ColOut>
-__device__ void cta_cholesky_blocked(double* __restrict__ A, double* __restrict__ X,
-                                     double (*__restrict__ PT)[CHOL_MAXR], const double* __restrict__ tol,
-                                     int m, int nx, ColOut out) {
+__device__ __forceinline__ void chol_diag_block(const double* __restrict__ A, CholShared& cs,
+                                                const double* __restrict__ tol, int k0, int nb, ColOut& out) {
+  double d[CHB][CHB];
+#pragma unroll
+  for (int a = 0; a < CHB; ++a)
+#pragma unroll
+    for (int b = 0; b <= a; ++b) d[a][b] = (a < nb && b < nb) ? A[pk(k0 + a, k0 + b)] : (a == b ? 1.0 : 0.0);
+#pragma unroll
+  for (int c = 0; c < CHB; ++c) {
+    const double p = d[c][c];
+    const bool ok = tol ? (c < nb ? p > tol[k0 + c] : true) : (p > 0.0);
+    const double iv = ok ? rsqrt(p) : 0.0;          // 1/l; l = p * (1/sqrt(p))
+    cs.dinv[c] = iv;
+    d[c][c] = p * iv;
+#pragma unroll
+    for (int a = c + 1; a < CHB; ++a) d[a][c] *= iv;
+#pragma unroll
+    for (int a = c + 1; a < CHB; ++a)
+#pragma unroll
+      for (int b = c + 1; b <= a; ++b) d[a][b] -= d[a][c] * d[b][c];
+  }
+#pragma unroll
+  for (int a = 0; a < CHB; ++a)
+#pragma unroll
+    for (int b = 0; b <= a; ++b) {
+      cs.dblk[a][b] = d[a][b];
+      if (a < nb) out(k0 + a, k0 + b, d[a][b]);
+    }
+}
+
+// Look-ahead: while warps 1.. apply the rank-CHB update of panel p to the trailing matrix, warp 0
+// updates the next diagonal block first and factors it, so the dependent chain of CHB pivots
+// (sqrt / divide latency) is off the critical path.
+template <class ColOut>
+__device__ void cta_cholesky_blocked(double* __restrict__ A, double* __restrict__ X, CholShared& cs,
+                                     const double* __restrict__ tol, int m, int nx, ColOut out) {
   const int tid = threadIdx.x, nt = blockDim.x;
+  const int warp = tid >> 5, lane = tid & 31;
   const int mrows = m + nx;
   auto rowp = [&](int i) -> double* { return (i < m) ? (A + pk(i, 0)) : (X + (size_t)(i - m) * m); };
+  __syncthreads();
+  if (tid == 0) chol_diag_block(A, cs, tol, 0, min(CHB, m), out);
   for (int k0 = 0; k0 < m; k0 += CHB) {
     const int nb = min(CHB, m - k0);
-    __syncthreads();                                   // trailing update of the previous panel done
-    // ---- diagonal block, redundantly per thread, in registers (static indices only)
-    double d[CHB][CHB];
-#pragma unroll
-    for (int a = 0; a < CHB; ++a)
-#pragma unroll
-      for (int b = 0; b <= a; ++b) d[a][b] = (a < nb && b < nb) ? A[pk(k0 + a, k0 + b)] : (a == b ? 1.0 : 0.0);
-    double inv[CHB];
-#pragma unroll
-    for (int c = 0; c < CHB; ++c) {
-      const double p = d[c][c];
-      const bool ok = tol ? (c < nb ? p > tol[k0 + c] : true) : true;
-      const double l = ok ? sqrt(p) : 0.0;
-      inv[c] = ok ? 1.0 / l : 0.0;
-      d[c][c] = l;
-#pragma unroll
-      for (int a = c + 1; a < CHB; ++a) d[a][c] *= inv[c];
-#pragma unroll
-      for (int a = c + 1; a < CHB; ++a)
-#pragma unroll
-        for (int b = c + 1; b <= a; ++b) d[a][b] -= d[a][c] * d[b][c];
-    }
-    if (tid == 0) {
-#pragma unroll
-      for (int a = 0; a < CHB; ++a)
-#pragma unroll
-        for (int b = 0; b <= a; ++b)
-          if (a < nb) out(k0 + a, k0 + b, d[a][b]);
-    }
+    __syncthreads();                                   // diagonal block of this panel published
     // ---- rows below the block: x <- x L_d^-T
     for (int i = k0 + nb + tid; i < mrows; i += nt) {
       const double* ri = rowp(i) + k0;
@@ -91,12 +118,12 @@ __device__ void cta_cholesky_blocked(double* __restrict__ A, double* __restrict_
       for (int c = 0; c < CHB; ++c) {
         double s = x[c];
 #pragma unroll
-        for (int q = 0; q < c; ++q) s -= x[q] * d[c][q];
-        x[c] = s * inv[c];
+        for (int q = 0; q < c; ++q) s -= x[q] * cs.dblk[c][q];
+        x[c] = s * cs.dinv[c];
       }
 #pragma unroll
       for (int c = 0; c < CHB; ++c) {
-        PT[c][i] = x[c];
+        cs.PT[c][i] = x[c];
         if (c < nb) out(i, k0 + c, x[c]);
       }
     }
@@ -107,53 +134,79 @@ __device__ void cta_cholesky_blocked(double* __restrict__ A, double* __restrict_
     const int Cn = m - r0;                    // columns left
     if (R <= 0 || Cn <= 0) continue;          // (nb < CHB only for the last panel: r0 % 8 == 0 here)
     const int TR = (R + 3) >> 2, TC = (Cn + 3) >> 2;
+    if (warp == 0) {
+      // tiles (0,0), (1,0), (1,1) -- they hold the next diagonal block (and, near the end, rows of
+      // the carried right-hand sides) -- then the factorisation of that block
+      const int nb2 = min(CHB, m - r0);
+      const int bd = (TC >= 2) ? 8 : 4;
+      for (int e = lane; e < bd * bd; e += 32) {
+        const int a2 = e / bd, b2 = e - a2 * bd;
+        const int i = r0 + a2, j = r0 + b2;
+        if (i < mrows && j < m && j <= i) {
+          double acc = 0.0;
+#pragma unroll
+          for (int c = 0; c < CHB; ++c) acc += cs.PT[c][i] * cs.PT[c][j];
+          rowp(i)[j] -= acc;
+        }
+      }
+      __syncwarp();
+      if (lane == 0) chol_diag_block(A, cs, tol, r0, nb2, out);
+      continue;
+    }
     const int full = TC * (TC + 1) / 2;       // tiles of the triangular part (ti < TC)
     const int ntile = full + (TR - TC) * TC;
-    for (int t = tid; t < ntile; t += nt) {
+    // tiles 0, 1, 2 = (0,0), (1,0), (1,1) are the next diagonal block (warp 0 above)
+    const int skip = (TC >= 2) ? 3 : 1;
+    for (int t = skip + (tid - 32); t < ntile; t += nt - 32) {
       int ti, tj;
       if (t < full) {
-        ti = (int)((sqrtf(8.0f * (float)t + 1.0f) - 1.0f) * 0.5f);
-        while (ti * (ti + 1) / 2 > t) --ti;
-        while ((ti + 1) * (ti + 2) / 2 <= t) ++ti;
-        tj = t - ti * (ti + 1) / 2;
+        ti = cs.tdec[t][0];
+        tj = cs.tdec[t][1];
       } else {
         const int u = t - full;
         ti = TC + u / TC;
         tj = u - (u / TC) * TC;
       }
       const int i0 = r0 + 4 * ti, j0 = r0 + 4 * tj;
-      double av[4][4];
-      double* rp[4];
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const int i = i0 + u;
-        rp[u] = rowp(min(i, mrows - 1));
-#pragma unroll
-        for (int v = 0; v < 4; ++v) {
-          const int j = j0 + v;
-          av[u][v] = (i < mrows && j < m && j <= i) ? rp[u][j] : 0.0;
-        }
-      }
+      double pa[CHB][4], pb[CHB][4];
 #pragma unroll
       for (int c = 0; c < CHB; ++c) {
-        const double2 a01 = *reinterpret_cast<const double2*>(&PT[c][i0]);
-        const double2 a23 = *reinterpret_cast<const double2*>(&PT[c][i0 + 2]);
-        const double2 b01 = *reinterpret_cast<const double2*>(&PT[c][j0]);
-        const double2 b23 = *reinterpret_cast<const double2*>(&PT[c][j0 + 2]);
-        const double pa[4] = {a01.x, a01.y, a23.x, a23.y};
-        const double pb[4] = {b01.x, b01.y, b23.x, b23.y};
-#pragma unroll
-        for (int u = 0; u < 4; ++u)
-#pragma unroll
-          for (int v = 0; v < 4; ++v) av[u][v] -= pa[u] * pb[v];
+        const double2 a01 = *reinterpret_cast<const double2*>(&cs.PT[c][i0]);
+        const double2 a23 = *reinterpret_cast<const double2*>(&cs.PT[c][i0 + 2]);
+        const double2 b01 = *reinterpret_cast<const double2*>(&cs.PT[c][j0]);
+        const double2 b23 = *reinterpret_cast<const double2*>(&cs.PT[c][j0 + 2]);
+        pa[c][0] = a01.x; pa[c][1] = a01.y; pa[c][2] = a23.x; pa[c][3] = a23.y;
+        pb[c][0] = b01.x; pb[c][1] = b01.y; pb[c][2] = b23.x; pb[c][3] = b23.y;
       }
+      double s[4][4];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const int i = i0 + u;
+      for (int u = 0; u < 4; ++u)
 #pragma unroll
         for (int v = 0; v < 4; ++v) {
-          const int j = j0 + v;
-          if (i < mrows && j < m && j <= i) rp[u][j] = av[u][v];
+          double acc = 0.0;
+#pragma unroll
+          for (int c = 0; c < CHB; ++c) acc += pa[c][u] * pb[c][v];
+          s[u][v] = acc;
+        }
+      if (tj < ti && i0 + 3 < mrows && j0 + 3 < m) {
+        // interior tile: no guards
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          double* rp = rowp(i0 + u) + j0;
+          const double v0 = rp[0], v1 = rp[1], v2 = rp[2], v3 = rp[3];
+          rp[0] = v0 - s[u][0]; rp[1] = v1 - s[u][1]; rp[2] = v2 - s[u][2]; rp[3] = v3 - s[u][3];
+        }
+      } else {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int i = i0 + u;
+          if (i >= mrows) continue;
+          double* rp = rowp(i);
+#pragma unroll
+          for (int v = 0; v < 4; ++v) {
+            const int j = j0 + v;
+            if (j < m && j <= i) rp[j] -= s[u][v];
+          }
         }
       }
     }
@@ -167,10 +220,11 @@ __device__ void cta_cholesky_blocked(double* __restrict__ A, double* __restrict_
 //   Ls (22 x 22): the trailing factor of the IMU block given the clones (F_2 F_2^T = Ls Ls^T).
 __global__ void __launch_bounds__(CHOL_THREADS) k_chol_prior(UpdArgs a, double* Ls_all) {
   extern __shared__ double sm[];
-  __shared__ __align__(16) double panel[CHB][CHOL_MAXR];
+  __shared__ __align__(16) CholShared cs;
   const int fi = blockIdx.x;
   const FilterWork fw = a.fw[fi];
   if (!fw.active) return;
+  chol_shared_init(cs);
   const int D = fw.D, n = 6 * fw.N, L = ORCVIO_LEG;
   const double* P = a.P + (size_t)fi * a.p_stride;
   double* FT = a.T + (size_t)fi * a.t_stride;
@@ -194,7 +248,7 @@ __global__ void __launch_bounds__(CHOL_THREADS) k_chol_prior(UpdArgs a, double* 
   __syncthreads();
   for (int i = tid; i < D; i += nt) tol[i] = 1e-12 * fabs(A[pk(i, i)]);
   const int ldt = a.ldt;
-  cta_cholesky_blocked(A, nullptr, panel, tol, D, 0, [&](int i, int k, double l) {
+  cta_cholesky_blocked(A, nullptr, cs, tol, D, 0, [&](int i, int k, double l) {
     if (k < n) FT[(size_t)k * ldt + orig(i)] = l;
     else Ls[(size_t)(i - n) * L + (k - n)] = l;
   });
@@ -205,8 +259,8 @@ __global__ void __launch_bounds__(CHOL_THREADS) k_chol_prior(UpdArgs a, double* 
 // The gated rows are assembled densely in shared memory; thread j owns column j of A and keeps
 // its column of L (the window rows) in registers.
 constexpr int AF_THREADS = 192;
-constexpr int AF_WMAX = 6 * 8;              // widest window handled by this kernel (clone blocks x 6)
 
+template <int WMAX>          // widest window handled (clone blocks x 6): 36 (max_track_len 6) or 48
 __global__ void __launch_bounds__(AF_THREADS) k_aform(QrArgs a, const double* FT_all, size_t t_stride, int ldt,
                                                       double* Amat, int lda, int* tile_rows) {
   extern __shared__ double smem[];
@@ -216,7 +270,9 @@ __global__ void __launch_bounds__(AF_THREADS) k_aform(QrArgs a, const double* FT
   const FilterWork fw = a.fw[tl.filter];
   const int n = 6 * fw.N;
   const int W = 6 * (tl.c1_blk - tl.c0_blk);
-  const int Wp = W + 2;                      // even stride, column W = residual
+  const int nchunk = (W + WMAX - 1) / WMAX;  // windows wider than WMAX columns are processed in chunks
+  const int WR = nchunk * WMAX;              // column of the residual
+  const int Wp = WR + 2;                     // even stride, zero padded
   const int tid = threadIdx.x, nt = blockDim.x;
   const int warp = tid >> 5, lane = tid & 31, nw = nt >> 5;
   const int nc = tl.cand_end - tl.cand_begin;      // host guarantees nc <= 256
@@ -244,7 +300,9 @@ __global__ void __launch_bounds__(AF_THREADS) k_aform(QrArgs a, const double* FT
   }
   const int m = total;
   if (tid == 0) tile_rows[blockIdx.x] = m;
-  for (int e = tid; e < m * Wp; e += nt) smem[e] = 0.0;
+  const int rows_ub = tl.rows;
+  const int rows4 = (rows_ub + 3) & ~3;      // rows are processed four at a time
+  for (int e = tid; e < rows4 * Wp; e += nt) smem[e] = 0.0;
   __syncthreads();
   for (int q = warp; q < nc; q += nw) {
     if (rowbase[q] < 0) continue;
@@ -258,38 +316,46 @@ __global__ void __launch_bounds__(AF_THREADS) k_aform(QrArgs a, const double* FT
       const int i = e / w, j = e - i * w;
       smem[(size_t)(rowbase[q] + i) * Wp + coff + j] = hb[e];
     }
-    for (int i = lane; i < r; i += 32) smem[(size_t)(rowbase[q] + i) * Wp + W] = a.rblk[cd.row_off + i];
+    for (int i = lane; i < r; i += 32) smem[(size_t)(rowbase[q] + i) * Wp + WR] = a.rblk[cd.row_off + i];
   }
   __syncthreads();
   // ---- thread j: column j of A for every row of the tile
   const double* FT = FT_all + (size_t)tl.filter * t_stride;
   double* Arow = Amat + (size_t)tl.arow * lda;
-  const int rows_ub = tl.rows;
   for (int j = tid; j <= n; j += nt) {
     if (j == n) {                                      // residual column
-      for (int row = 0; row < rows_ub; ++row) Arow[(size_t)row * lda + n] = (row < m) ? smem[(size_t)row * Wp + W] : 0.0;
+      for (int row = 0; row < rows_ub; ++row) Arow[(size_t)row * lda + n] = smem[(size_t)row * Wp + WR];
       continue;
     }
-    double Lw[AF_WMAX];
-    // L[k][j] = FT[j][22 + k], k = 6 c0 + c  (zero above the diagonal: k < j)
-    const double* src = FT + (size_t)j * ldt + ORCVIO_LEG + 6 * tl.c0_blk;
+    if (j >= 6 * tl.c1_blk) {                          // every window row lies above the diagonal of L
+      for (int row = 0; row < rows_ub; ++row) Arow[(size_t)row * lda + j] = 0.0;
+      continue;
+    }
+    for (int ch = 0; ch < nchunk; ++ch) {
+      double Lw[WMAX];
+      // L[k][j] = FT[j][22 + k], k = 6 c0 + ch WMAX + c  (zero above the diagonal: k < j)
+      const double* src = FT + (size_t)j * ldt + ORCVIO_LEG + 6 * tl.c0_blk + ch * WMAX;
 #pragma unroll
-    for (int c = 0; c < AF_WMAX; ++c) Lw[c] = (c < W) ? src[c] : 0.0;
-    const bool zero_col = (j >= 6 * tl.c1_blk);        // every window row lies above the diagonal
-    for (int row = 0; row < rows_ub; ++row) {
-      double s0 = 0.0, s1 = 0.0;
-      if (row < m && !zero_col) {
-        const double* hr = smem + (size_t)row * Wp;
+      for (int c = 0; c < WMAX; ++c) Lw[c] = (ch * WMAX + c < W) ? src[c] : 0.0;
+      for (int row = 0; row < rows4; row += 4) {
+        const double* h0 = smem + (size_t)row * Wp + ch * WMAX;
+        double s[4][2] = {{0, 0}, {0, 0}, {0, 0}, {0, 0}};
 #pragma unroll
-        for (int c = 0; c < AF_WMAX; c += 2) {
-          if (c < W) {
-            const double2 h2 = *reinterpret_cast<const double2*>(hr + c);
-            s0 += h2.x * Lw[c];
-            s1 += h2.y * Lw[c + 1];
+        for (int c = 0; c < WMAX; c += 2) {
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const double2 h2 = *reinterpret_cast<const double2*>(h0 + (size_t)u * Wp + c);
+            s[u][0] += h2.x * Lw[c];
+            s[u][1] += h2.y * Lw[c + 1];
           }
         }
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+          if (row + u < rows_ub) {
+            double* dst = Arow + (size_t)(row + u) * lda + j;
+            *dst = (ch == 0) ? (s[u][0] + s[u][1]) : (*dst + (s[u][0] + s[u][1]));
+          }
       }
-      Arow[(size_t)row * lda + j] = s0 + s1;
     }
   }
   // padding columns (n, lda) are never read
@@ -380,10 +446,12 @@ __global__ void __launch_bounds__(256) k_syrk(const FilterWork* fws, const doubl
     if (r0 + SY_KS < row_end) fetch(r0 + SY_KS, a0, a1, b0, b1);     // in flight during the FMAs below
 #pragma unroll
     for (int kk = 0; kk < SY_KS; ++kk) {
-      const double2 x0 = *reinterpret_cast<const double2*>(&As[kk][4 * ty]);
-      const double2 x1 = *reinterpret_cast<const double2*>(&As[kk][4 * ty + 2]);
-      const double2 y0 = *reinterpret_cast<const double2*>(&Bs[kk][4 * tx]);
-      const double2 y1 = *reinterpret_cast<const double2*>(&Bs[kk][4 * tx + 2]);
+      // thread (tx, ty) owns rows {2ty, 2ty+1, 32+2ty, 33+2ty} x cols {2tx, 2tx+1, 32+2tx, 33+2tx}:
+      // a half-warp reads 256 contiguous bytes of Bs per double2 load (no bank conflicts)
+      const double2 x0 = *reinterpret_cast<const double2*>(&As[kk][2 * ty]);
+      const double2 x1 = *reinterpret_cast<const double2*>(&As[kk][32 + 2 * ty]);
+      const double2 y0 = *reinterpret_cast<const double2*>(&Bs[kk][2 * tx]);
+      const double2 y1 = *reinterpret_cast<const double2*>(&Bs[kk][32 + 2 * tx]);
       const double av[4] = {x0.x, x0.y, x1.x, x1.y};
       const double bv[4] = {y0.x, y0.y, y1.x, y1.y};
 #pragma unroll
@@ -396,7 +464,8 @@ __global__ void __launch_bounds__(256) k_syrk(const FilterWork* fws, const doubl
 #pragma unroll
   for (int u = 0; u < 4; ++u)
 #pragma unroll
-    for (int v = 0; v < 4; ++v) out[(4 * ty + u) * SY_T + 4 * tx + v] = acc[u][v];
+    for (int v = 0; v < 4; ++v)
+      out[((u < 2 ? 0 : 32) + 2 * ty + (u & 1)) * SY_T + (v < 2 ? 0 : 32) + 2 * tx + (v & 1)] = acc[u][v];
 }
 
 // W_aug (lower, (n+1) x ldr in UpdArgs::S): sum of the chunk partials + s^2 on the first n diagonal
@@ -419,7 +488,7 @@ __global__ void __launch_bounds__(256) k_syrk_reduce(UpdArgs a, const double* pa
   }
   const int n = 6 * fw.N, n1 = n + 1;
   if (e >= n1 * n1) return;
-  const int i = e / n1, j = e - i * n1;
+  const int j = e / n1, i = e - j * n1;                // i fastest: the partial tiles are read contiguously
   if (j > i) return;                                   // lower triangle: i >= j  -> tile pair (J, I)
   const int nt_ = (n1 + SY_T - 1) / SY_T;
   const int TI = j / SY_T, TJ = i / SY_T;              // TI <= TJ
@@ -443,13 +512,14 @@ constexpr int CS = 16;
 
 __global__ void __launch_bounds__(CHOL_THREADS) k_chol_w_solve(UpdArgs a) {
   extern __shared__ double sm[];
-  __shared__ __align__(16) double panel[CHB][CHOL_MAXR];
+  __shared__ __align__(16) CholShared cs;
   const int fi = blockIdx.y;
   const FilterWork fw = a.fw[fi];
   if (!fw.active) return;
   const int n = 6 * fw.N, D = fw.D;
   const int d0 = blockIdx.x * CS;
   if (d0 >= D) return;
+  chol_shared_init(cs);
   const int nd = min(CS, D - d0);
   const bool has_v = (blockIdx.x == 0);
   const int nx = nd + (has_v ? 1 : 0);
@@ -473,7 +543,7 @@ __global__ void __launch_bounds__(CHOL_THREADS) k_chol_w_solve(UpdArgs a) {
   if (has_v)
     for (int k = tid; k < n; k += nt) X[(size_t)nd * n + k] = S[(size_t)n * a.ldr + k];
   const int ldt = a.ldt;
-  cta_cholesky_blocked(A, X, panel, nullptr, n, nx, [&](int i, int k, double l) {
+  cta_cholesky_blocked(A, X, cs, nullptr, n, nx, [&](int i, int k, double l) {
     if (i < n) return;
     const int q = i - n;
     if (q < nd) T[(size_t)k * ldt + d0 + q] = l;       // Y[k][d0 + q]
@@ -618,7 +688,8 @@ __global__ void __launch_bounds__(256) k_pinfo(UpdArgs a, const double* Ls_all, 
 static void info_attrs() {
   static bool attr = false;
   if (attr) return;
-  cudaFuncSetAttribute(k_aform, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+  cudaFuncSetAttribute(k_aform<36>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+  cudaFuncSetAttribute(k_aform<48>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024);
   cudaFuncSetAttribute(k_chol_prior, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
   cudaFuncSetAttribute(k_chol_w_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
   cudaFuncSetAttribute(k_pinfo, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
@@ -680,9 +751,15 @@ void launch_info_update(const QrArgs& q, const UpdArgs& u, const InfoBufs& ib, i
   cudaStreamWaitEvent(s, join, 0);
   const int lda = u.ldr;
   if (n_tiles > 0) {
-    const int W = 6 * max_w_blk;
-    const size_t smem = (size_t)std::max(max_tile_rows, 1) * (W + 2) * sizeof(double);
-    k_aform<<<n_tiles, AF_THREADS, smem, s>>>(q, u.T, u.t_stride, u.ldt, ib.Amat, lda, ib.tile_rows);
+    const int rows4 = (std::max(max_tile_rows, 1) + 3) & ~3;
+    if (max_w_blk <= 6) {
+      k_aform<36><<<n_tiles, AF_THREADS, (size_t)rows4 * 38 * sizeof(double), s>>>(q, u.T, u.t_stride, u.ldt, ib.Amat,
+                                                                                lda, ib.tile_rows);
+    } else {
+      const int wr = ((6 * max_w_blk + 47) / 48) * 48;
+      k_aform<48><<<n_tiles, AF_THREADS, (size_t)rows4 * (wr + 2) * sizeof(double), s>>>(q, u.T, u.t_stride, u.ldt,
+                                                                                      ib.Amat, lda, ib.tile_rows);
+    }
     check_launch("k_aform");
   }
   if (mid1) cudaEventRecord(mid1, s);

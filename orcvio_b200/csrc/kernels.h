@@ -183,7 +183,7 @@ void launch_remove(const RemoveArgs& a, cudaStream_t s);
 // tile sizing shared by host tiler and kernels
 constexpr int QR_THREADS = 256;
 constexpr int QR_SMEM_BYTES = 200 * 1024;
-constexpr int AFORM_TILE_ROWS = 128;    // row cap of a tile of the whitened-form path
+constexpr int AFORM_TILE_ROWS = 64;     // row cap of a tile of the whitened-form path
 constexpr int SYRK_KC = 512;            // rows per split-K chunk of A^T A
 inline int qr_tile_rows_cap(int w_cols) {                // rows that fit beside (w_cols+1) columns
   int ld = w_cols + 2;

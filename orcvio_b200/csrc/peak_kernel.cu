@@ -28,7 +28,68 @@ __global__ void __launch_bounds__(256) k_dmma_peak(double* out, int iters, doubl
   out[blockIdx.x * blockDim.x + threadIdx.x] = ((c0 + c1) + (d0 + d1)) + ((e0 + e1) + (f0 + f1));
 }
 
+// Dependent-chain latencies (cycles per operation) of the FP64 building blocks the factorisation
+// kernels are made of: out[0] DFMA, [1] sqrt, [2] divide, [3] rsqrt, [4] shared-memory load,
+// [5] __syncthreads with 512 threads, [6] warp shuffle (64-bit).
+__global__ void __launch_bounds__(512) k_latency(double* out, double seed) {
+  __shared__ double sm[64];
+  const int tid = threadIdx.x;
+  if (tid < 64) sm[tid] = (double)((tid + 1) & 63);
+  __syncthreads();
+  const int N = 256;
+  double x = seed + 1.5;
+  long long t0 = clock64();
+  for (int i = 0; i < N; ++i) x = fma(x, 1.0000001, 1e-9);
+  long long t1 = clock64();
+  double r0 = (double)(t1 - t0) / N;
+  double y = seed + 2.0;
+  t0 = clock64();
+  for (int i = 0; i < N; ++i) y = sqrt(y + 3.0);
+  t1 = clock64();
+  double r1 = (double)(t1 - t0) / N;
+  double z = seed + 2.0;
+  t0 = clock64();
+  for (int i = 0; i < N; ++i) z = 1.0 / (z + 0.5);
+  t1 = clock64();
+  double r2 = (double)(t1 - t0) / N;
+  double w = seed + 2.0;
+  t0 = clock64();
+  for (int i = 0; i < N; ++i) w = rsqrt(w + 3.0);
+  t1 = clock64();
+  double r3 = (double)(t1 - t0) / N;
+  int idx = tid & 63;
+  t0 = clock64();
+  for (int i = 0; i < N; ++i) idx = (int)sm[idx];
+  t1 = clock64();
+  double r4 = (double)(t1 - t0) / N;
+  t0 = clock64();
+  for (int i = 0; i < N; ++i) __syncthreads();
+  t1 = clock64();
+  double r5 = (double)(t1 - t0) / N;
+  double v = x;
+  t0 = clock64();
+  for (int i = 0; i < N; ++i) v = __shfl_xor_sync(0xffffffffu, v, 1) + 1.0;
+  t1 = clock64();
+  double r6 = (double)(t1 - t0) / N;
+  if (tid == 0) {
+    out[0] = r0; out[1] = r1; out[2] = r2; out[3] = r3; out[4] = r4; out[5] = r5; out[6] = r6;
+    out[7] = x + y + z + w + idx + v;
+  }
+}
+
 }  // namespace
+
+extern "C" int orcvio_latency_probe(double* cycles7) {
+  double* out = nullptr;
+  if (cudaMalloc(&out, 8 * sizeof(double)) != cudaSuccess) return ORCVIO_ERR_NO_DEVICE;
+  k_latency<<<1, 512>>>(out, 0.25);
+  k_latency<<<1, 512>>>(out, 0.25);
+  double h[8];
+  cudaMemcpy(h, out, sizeof(h), cudaMemcpyDeviceToHost);
+  cudaFree(out);
+  for (int i = 0; i < 7; ++i) cycles7[i] = h[i];
+  return cudaGetLastError() == cudaSuccess ? ORCVIO_OK : ORCVIO_ERR_CUDA;
+}
 
 extern "C" int orcvio_fp64_peak(double* dfma_tflops, double* dmma_tflops) {
   int dev = 0, sms = 0;

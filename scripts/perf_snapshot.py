@@ -3,6 +3,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 from orcvio_b200 import api, synth
 print('fp64 peak (DFMA, DMMA) TFLOP/s:', api.fp64_peak())
+print('latency probe (cycles):', api.latency_probe())
 flags = int(sys.argv[1]) if len(sys.argv) > 1 else 0
 for (N, F, L, full) in [(20, 300, 6, False), (30, 1000, 6, False), (30, 2000, 6, False), (30, 4096, 6, False), (30, 256, 6, True)]:
     snap = synth.stress_snapshot(N, F, L, seed=1, full_tracks=full)
