@@ -235,6 +235,11 @@ const char* orcvio_version(void);
 int orcvio_fp64_peak(double* dfma_tflops, double* dmma_tflops);
 /* dependent-chain latencies in cycles: DFMA, sqrt, divide, rsqrt, shared load, __syncthreads(512), shuffle */
 int orcvio_latency_probe(double* cycles7);
+/* test / profiling hook: the one-CTA Cholesky both factorisation kernels are built on (csrc/chol.cuh).
+ * A: m x m SPD row-major, X: nx x m carried rows; L: m x m lower factor, Xs = X C^-T; prof: 64 x 8
+ * clock64() stamps per 8-column panel (may be NULL); us: mean kernel time over `reps` launches. */
+int orcvio_chol_probe(int m, int nx, const double* A, const double* X, double* L, double* Xs,
+                      long long* prof, int reps, float* us);
 /* chi-square quantile used for the gating tables (boost::math::quantile(chi_squared(dof), p),
  * src/orcvio.cpp:481-494) */
 double orcvio_chi2_quantile(double p, int dof);

@@ -92,6 +92,8 @@ def lib():
     L.orcvio_set_device.argtypes = [C.c_int]
     L.orcvio_fp64_peak.argtypes = [dp, dp]
     L.orcvio_latency_probe.argtypes = [dp]
+    L.orcvio_chol_probe.argtypes = [C.c_int, C.c_int, dp, dp, dp, dp, C.POINTER(C.c_longlong), C.c_int,
+                                    C.POINTER(C.c_float)]
     L.orcvio_triangulate.argtypes = [dp, dp, C.c_int, ip, ip, dp, C.c_int, C.c_double, C.c_double,
                                      C.c_double, dp, ip, ip, dp]
     L.orcvio_snapshot_update.argtypes = [dp, dp, C.c_int, dp, dp, dp, ip, ip, dp, C.c_int, C.c_int,
@@ -576,6 +578,23 @@ def latency_probe():
     if rc != 0:
         raise RuntimeError(f"orcvio_latency_probe failed: {rc}")
     return dict(zip(["dfma", "sqrt", "div", "rsqrt", "lds", "syncthreads512", "shfl64"], out.tolist()))
+
+
+def chol_probe(A, X=None, reps=10):
+    """Runs csrc/chol.cuh on one SPD matrix: returns (L, X C^-T, per-panel clock stamps, mean us)."""
+    A = np.ascontiguousarray(A, dtype=np.float64)
+    m = A.shape[0]
+    nx = 0 if X is None else X.shape[0]
+    Xc = np.ascontiguousarray(X if X is not None else np.zeros((1, m)), dtype=np.float64)
+    L = np.zeros((m, m))
+    Xs = np.zeros_like(Xc)
+    prof = np.zeros((64, 8), dtype=np.int64)
+    us = C.c_float(0)
+    rc = lib().orcvio_chol_probe(m, nx, _dp(A), _dp(Xc), _dp(L), _dp(Xs),
+                                 prof.ctypes.data_as(C.POINTER(C.c_longlong)), int(reps), C.byref(us))
+    if rc != 0:
+        raise RuntimeError(f"orcvio_chol_probe failed: {rc}")
+    return L, (Xs if X is not None else None), prof, us.value
 
 
 def chi2_quantile(p, dof):

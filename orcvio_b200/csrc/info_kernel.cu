@@ -27,192 +27,9 @@
 // forming G = H'^T H' first and then L^T G L loses a factor ~rows (measured 2e-9 vs 1e-12 on the
 // Unity-shaped sequence; DESIGN.md "numerics").
 #include "kernels.h"
+#include "chol.cuh"
 
 namespace ob {
-
-__device__ __forceinline__ int pk(int i, int j) { return (i * (i + 1) >> 1) + j; }
-
-// ---------------------------------------------------------------- blocked Cholesky (one CTA)
-// A: packed lower m x m in shared memory (row i at A + i(i+1)/2).  X: `nx` extra dense rows of
-// length m (right-hand sides carried along: X <- X C^-T).  Panels of CHB columns: every thread
-// factors the CHB x CHB diagonal block redundantly in registers (no barrier inside a panel),
-// solves its own row against it, then the trailing matrix gets a rank-CHB update with 4x4
-// register tiles.  Two barriers per panel.  tol != nullptr: pivots <= tol[k] are treated as exact
-// zeros (semidefinite prior: exactly-zero and duplicated states give zero columns).
-constexpr int CHB = 8;
-constexpr int CHOL_THREADS = 512;
-constexpr int CHOL_MAXR = ORCVIO_LEG + 6 * ORCVIO_MAX_OBS + 24;   // rows incl. extra rows, padded
-constexpr int CHOL_MAXT = (CHOL_MAXR + 3) / 4;                    // 4-row tiles per dimension
-
-struct CholShared {                       // static shared memory of one factorisation
-  double PT[CHB][CHOL_MAXR];              // current panel, transposed: PT[c][row]
-  double dblk[CHB][CHB];                  // factored diagonal block (lower)
-  double dinv[CHB];                       // 1 / diagonal (0 for skipped pivots)
-  unsigned short tdec[CHOL_MAXT * (CHOL_MAXT + 1) / 2][2];   // triangle tile index -> (ti, tj)
-};
-
-// Must be called by all threads once before cta_cholesky_blocked (fills the tile decode table).
-__device__ __forceinline__ void chol_shared_init(CholShared& cs) {
-  for (int ti = threadIdx.x; ti < CHOL_MAXT; ti += blockDim.x)
-    for (int tj = 0; tj <= ti; ++tj) {
-      const int t = ti * (ti + 1) / 2 + tj;
-      cs.tdec[t][0] = (unsigned short)ti;
-      cs.tdec[t][1] = (unsigned short)tj;
-    }
-}
-
-// Factor the nb x nb diagonal block at k0 (thread-local, registers) and publish it.
-template <class ColOut>
-__device__ __forceinline__ void chol_diag_block(const double* __restrict__ A, CholShared& cs,
-                                                const double* __restrict__ tol, int k0, int nb, ColOut& out) {
-  double d[CHB][CHB];
-#pragma unroll
-  for (int a = 0; a < CHB; ++a)
-#pragma unroll
-    for (int b = 0; b <= a; ++b) d[a][b] = (a < nb && b < nb) ? A[pk(k0 + a, k0 + b)] : (a == b ? 1.0 : 0.0);
-#pragma unroll
-  for (int c = 0; c < CHB; ++c) {
-    const double p = d[c][c];
-    const bool ok = tol ? (c < nb ? p > tol[k0 + c] : true) : (p > 0.0);
-    const double iv = ok ? rsqrt(p) : 0.0;          // 1/l; l = p * (1/sqrt(p))
-    cs.dinv[c] = iv;
-    d[c][c] = p * iv;
-#pragma unroll
-    for (int a = c + 1; a < CHB; ++a) d[a][c] *= iv;
-#pragma unroll
-    for (int a = c + 1; a < CHB; ++a)
-#pragma unroll
-      for (int b = c + 1; b <= a; ++b) d[a][b] -= d[a][c] * d[b][c];
-  }
-#pragma unroll
-  for (int a = 0; a < CHB; ++a)
-#pragma unroll
-    for (int b = 0; b <= a; ++b) {
-      cs.dblk[a][b] = d[a][b];
-      if (a < nb) out(k0 + a, k0 + b, d[a][b]);
-    }
-}
-
-// Look-ahead: while warps 1.. apply the rank-CHB update of panel p to the trailing matrix, warp 0
-// updates the next diagonal block first and factors it, so the dependent chain of CHB pivots
-// (sqrt / divide latency) is off the critical path.
-template <class ColOut>
-__device__ void cta_cholesky_blocked(double* __restrict__ A, double* __restrict__ X, CholShared& cs,
-                                     const double* __restrict__ tol, int m, int nx, ColOut out) {
-  const int tid = threadIdx.x, nt = blockDim.x;
-  const int warp = tid >> 5, lane = tid & 31;
-  const int mrows = m + nx;
-  auto rowp = [&](int i) -> double* { return (i < m) ? (A + pk(i, 0)) : (X + (size_t)(i - m) * m); };
-  __syncthreads();
-  if (tid == 0) chol_diag_block(A, cs, tol, 0, min(CHB, m), out);
-  for (int k0 = 0; k0 < m; k0 += CHB) {
-    const int nb = min(CHB, m - k0);
-    __syncthreads();                                   // diagonal block of this panel published
-    // ---- rows below the block: x <- x L_d^-T
-    for (int i = k0 + nb + tid; i < mrows; i += nt) {
-      const double* ri = rowp(i) + k0;
-      double x[CHB];
-#pragma unroll
-      for (int c = 0; c < CHB; ++c) x[c] = (c < nb) ? ri[c] : 0.0;
-#pragma unroll
-      for (int c = 0; c < CHB; ++c) {
-        double s = x[c];
-#pragma unroll
-        for (int q = 0; q < c; ++q) s -= x[q] * cs.dblk[c][q];
-        x[c] = s * cs.dinv[c];
-      }
-#pragma unroll
-      for (int c = 0; c < CHB; ++c) {
-        cs.PT[c][i] = x[c];
-        if (c < nb) out(i, k0 + c, x[c]);
-      }
-    }
-    __syncthreads();
-    // ---- trailing update: A[i][j] -= sum_c PT[c][i] PT[c][j],  k0+nb <= j <= min(i, m-1)
-    const int r0 = k0 + nb;
-    const int R = mrows - r0;                 // rows left
-    const int Cn = m - r0;                    // columns left
-    if (R <= 0 || Cn <= 0) continue;          // (nb < CHB only for the last panel: r0 % 8 == 0 here)
-    const int TR = (R + 3) >> 2, TC = (Cn + 3) >> 2;
-    if (warp == 0) {
-      // tiles (0,0), (1,0), (1,1) -- they hold the next diagonal block (and, near the end, rows of
-      // the carried right-hand sides) -- then the factorisation of that block
-      const int nb2 = min(CHB, m - r0);
-      const int bd = (TC >= 2) ? 8 : 4;
-      for (int e = lane; e < bd * bd; e += 32) {
-        const int a2 = e / bd, b2 = e - a2 * bd;
-        const int i = r0 + a2, j = r0 + b2;
-        if (i < mrows && j < m && j <= i) {
-          double acc = 0.0;
-#pragma unroll
-          for (int c = 0; c < CHB; ++c) acc += cs.PT[c][i] * cs.PT[c][j];
-          rowp(i)[j] -= acc;
-        }
-      }
-      __syncwarp();
-      if (lane == 0) chol_diag_block(A, cs, tol, r0, nb2, out);
-      continue;
-    }
-    const int full = TC * (TC + 1) / 2;       // tiles of the triangular part (ti < TC)
-    const int ntile = full + (TR - TC) * TC;
-    // tiles 0, 1, 2 = (0,0), (1,0), (1,1) are the next diagonal block (warp 0 above)
-    const int skip = (TC >= 2) ? 3 : 1;
-    for (int t = skip + (tid - 32); t < ntile; t += nt - 32) {
-      int ti, tj;
-      if (t < full) {
-        ti = cs.tdec[t][0];
-        tj = cs.tdec[t][1];
-      } else {
-        const int u = t - full;
-        ti = TC + u / TC;
-        tj = u - (u / TC) * TC;
-      }
-      const int i0 = r0 + 4 * ti, j0 = r0 + 4 * tj;
-      double pa[CHB][4], pb[CHB][4];
-#pragma unroll
-      for (int c = 0; c < CHB; ++c) {
-        const double2 a01 = *reinterpret_cast<const double2*>(&cs.PT[c][i0]);
-        const double2 a23 = *reinterpret_cast<const double2*>(&cs.PT[c][i0 + 2]);
-        const double2 b01 = *reinterpret_cast<const double2*>(&cs.PT[c][j0]);
-        const double2 b23 = *reinterpret_cast<const double2*>(&cs.PT[c][j0 + 2]);
-        pa[c][0] = a01.x; pa[c][1] = a01.y; pa[c][2] = a23.x; pa[c][3] = a23.y;
-        pb[c][0] = b01.x; pb[c][1] = b01.y; pb[c][2] = b23.x; pb[c][3] = b23.y;
-      }
-      double s[4][4];
-#pragma unroll
-      for (int u = 0; u < 4; ++u)
-#pragma unroll
-        for (int v = 0; v < 4; ++v) {
-          double acc = 0.0;
-#pragma unroll
-          for (int c = 0; c < CHB; ++c) acc += pa[c][u] * pb[c][v];
-          s[u][v] = acc;
-        }
-      if (tj < ti && i0 + 3 < mrows && j0 + 3 < m) {
-        // interior tile: no guards
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          double* rp = rowp(i0 + u) + j0;
-          const double v0 = rp[0], v1 = rp[1], v2 = rp[2], v3 = rp[3];
-          rp[0] = v0 - s[u][0]; rp[1] = v1 - s[u][1]; rp[2] = v2 - s[u][2]; rp[3] = v3 - s[u][3];
-        }
-      } else {
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const int i = i0 + u;
-          if (i >= mrows) continue;
-          double* rp = rowp(i);
-#pragma unroll
-          for (int v = 0; v < 4; ++v) {
-            const int j = j0 + v;
-            if (j < m && j <= i) rp[j] -= s[u][v];
-          }
-        }
-      }
-    }
-  }
-  __syncthreads();
-}
 
 // ---------------------------------------------------------------- prior factor
 // P = F F^T in the order [clone columns 22..D-1 | IMU columns 0..21].  Outputs
@@ -224,31 +41,28 @@ __global__ void __launch_bounds__(CHOL_THREADS) k_chol_prior(UpdArgs a, double* 
   const int fi = blockIdx.x;
   const FilterWork fw = a.fw[fi];
   if (!fw.active) return;
-  chol_shared_init(cs);
   const int D = fw.D, n = 6 * fw.N, L = ORCVIO_LEG;
+  const int Tm = (D + 7) >> 3;
   const double* P = a.P + (size_t)fi * a.p_stride;
   double* FT = a.T + (size_t)fi * a.t_stride;
   double* Ls = Ls_all + (size_t)fi * L * L;
   double* A = sm;
-  double* tol = A + (size_t)D * (D + 1) / 2;
+  double* tol = A + chol_smem_doubles(D, 0);
   const int tid = threadIdx.x, nt = blockDim.x;
   const int warp = tid >> 5, lane = tid & 31, nw = nt >> 5;
   auto orig = [&](int q) { return q < n ? L + q : q - n; };
-  for (int i = warp; i < D; i += nw) {
-    const double* Pi = P + (size_t)orig(i) * a.ldp;
-    double* Ai = A + pk(i, 0);
-    for (int j = lane; j <= i; j += 32) Ai[j] = Pi[orig(j)];
-  }
+  chol_init(A, cs, D, 0);
+  __syncthreads();
+  const int ldp = a.ldp;
+  chol_load_rows(A, D, 0, D, [&](int i, int j) { return P[(size_t)orig(i) * ldp + orig(j)]; });
+  for (int i = tid; i < D; i += nt) tol[i] = 1e-12 * fabs(P[(size_t)orig(i) * (ldp + 1)]);
   for (int i = tid; i < L * L; i += nt) Ls[i] = 0.0;
   // entries above the diagonal of F are structural zeros: FT[k][orig(i)] = 0 for i < k
-  for (int e = tid; e < n * n; e += nt) {
-    const int k = e / n, i = e - k * n;
-    if (i < k) FT[(size_t)k * a.ldt + L + i] = 0.0;
-  }
-  __syncthreads();
-  for (int i = tid; i < D; i += nt) tol[i] = 1e-12 * fabs(A[pk(i, i)]);
+  for (int k = warp; k < n; k += nw)
+    for (int i = lane; i < k; i += 32) FT[(size_t)k * a.ldt + L + i] = 0.0;
+  cta_cholesky(A, cs, tol, D, 0);
   const int ldt = a.ldt;
-  cta_cholesky_blocked(A, nullptr, cs, tol, D, 0, [&](int i, int k, double l) {
+  chol_for_rows(A, D, 0, 0, [&](int i, int k, double l) {
     if (k < n) FT[(size_t)k * ldt + orig(i)] = l;
     else Ls[(size_t)(i - n) * L + (k - n)] = l;
   });
@@ -519,7 +333,6 @@ __global__ void __launch_bounds__(CHOL_THREADS) k_chol_w_solve(UpdArgs a) {
   const int n = 6 * fw.N, D = fw.D;
   const int d0 = blockIdx.x * CS;
   if (d0 >= D) return;
-  chol_shared_init(cs);
   const int nd = min(CS, D - d0);
   const bool has_v = (blockIdx.x == 0);
   const int nx = nd + (has_v ? 1 : 0);
@@ -527,24 +340,21 @@ __global__ void __launch_bounds__(CHOL_THREADS) k_chol_w_solve(UpdArgs a) {
   double* T = a.T + (size_t)fi * a.t_stride;
   double* yv = a.yv + (size_t)fi * a.ldr;
   double* A = sm;
-  double* X = A + (size_t)n * (n + 1) / 2;
+  const int Tm = (n + 7) >> 3;
   const int tid = threadIdx.x, nt = blockDim.x;
   const int warp = tid >> 5, lane = tid & 31, nw = nt >> 5;
-  for (int i = warp; i < n; i += nw) {
-    const double* Si = S + (size_t)i * a.ldr;
-    double* Ai = A + pk(i, 0);
-    for (int j = lane; j <= i; j += 32) Ai[j] = Si[j];
-  }
-  // extra rows: X[e][k] = F_1[d0 + e][k] = FT[k][d0 + e];  last row (strip 0): v[k] = S[n][k]
-  for (int e = tid; e < n * nd; e += nt) {
-    const int k = e / nd, q = e - k * nd;
-    X[(size_t)q * n + k] = T[(size_t)k * a.ldt + d0 + q];
-  }
-  if (has_v)
-    for (int k = tid; k < n; k += nt) X[(size_t)nd * n + k] = S[(size_t)n * a.ldr + k];
+  chol_init(A, cs, n, nx);
+  __syncthreads();
+  const int ldr = a.ldr, ldt0 = a.ldt;
+  // triangle rows: W;  carried rows: row n + q = F_1[d0 + q][:] = FT[:][d0 + q];  last row (strip 0): v = S[n][:]
+  chol_load_rows(A, n, 0, n + nx, [&](int i, int j) {
+    if (i < n) return S[(size_t)i * ldr + j];
+    const int q = i - n;
+    return q < nd ? T[(size_t)j * ldt0 + d0 + q] : S[(size_t)n * ldr + j];
+  });
+  cta_cholesky(A, cs, nullptr, n, nx);
   const int ldt = a.ldt;
-  cta_cholesky_blocked(A, X, cs, nullptr, n, nx, [&](int i, int k, double l) {
-    if (i < n) return;
+  chol_for_rows(A, n, nx, n, [&](int i, int k, double l) {
     const int q = i - n;
     if (q < nd) T[(size_t)k * ldt + d0 + q] = l;       // Y[k][d0 + q]
     else yv[k] = l;
@@ -690,8 +500,8 @@ static void info_attrs() {
   if (attr) return;
   cudaFuncSetAttribute(k_aform<36>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
   cudaFuncSetAttribute(k_aform<48>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024);
-  cudaFuncSetAttribute(k_chol_prior, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-  cudaFuncSetAttribute(k_chol_w_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  cudaFuncSetAttribute(k_chol_prior, cudaFuncAttributeMaxDynamicSharedMemorySize, 193 * 1024);
+  cudaFuncSetAttribute(k_chol_w_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, 193 * 1024);
   cudaFuncSetAttribute(k_pinfo, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
   check_launch("info attributes");
   attr = true;
@@ -705,7 +515,7 @@ void launch_info_dense_factor(const UpdArgs& u, const InfoBufs& ib, const double
                               cudaStream_t s) {
   info_attrs();
   const int n = 6 * N, D = ORCVIO_LEG + n;
-  const size_t sm_prior = ((size_t)D * (D + 1) / 2 + (size_t)D + 16) * sizeof(double);
+  const size_t sm_prior = (chol_smem_doubles(D, 0) + (size_t)D + 2) * sizeof(double);
   k_chol_prior<<<1, CHOL_THREADS, sm_prior, s>>>(u, ib.Ls);
   check_launch("k_chol_prior");
   k_aform_dense<<<rows, 256, 0, s>>>(Hp, ldh, rows, n, u.T, u.ldt, ib.Amat, u.ldr);
@@ -718,7 +528,7 @@ void launch_info_dense_factor(const UpdArgs& u, const InfoBufs& ib, const double
   dim3 gr(((n + 1) * (n + 1) + 255) / 256, 1);
   k_syrk_reduce<<<gr, 256, 0, s>>>(u, ib.part, ib.kc, ib.max_chunks, ib.max_pairs, nullptr, ib.tile_rows, ib.filter_rows);
   check_launch("k_syrk_reduce");
-  const size_t sm_w = ((size_t)n * (n + 1) / 2 + (size_t)(CS + 1) * n + 16) * sizeof(double);
+  const size_t sm_w = chol_smem_doubles(n, CS + 1) * sizeof(double);
   dim3 gw((D + CS - 1) / CS, 1);
   k_chol_w_solve<<<gw, CHOL_THREADS, sm_w, s>>>(u);
   check_launch("k_chol_w_solve");
@@ -744,7 +554,7 @@ void launch_info_update(const QrArgs& q, const UpdArgs& u, const InfoBufs& ib, i
   // prior factor on the second stream: depends only on P, overlaps triangulation / Jacobians
   // (the caller recorded `fork` on s before launching them)
   cudaStreamWaitEvent(s2, fork, 0);
-  const size_t sm_prior = ((size_t)Dmax * (Dmax + 1) / 2 + (size_t)Dmax + 16) * sizeof(double);
+  const size_t sm_prior = (chol_smem_doubles(Dmax, 0) + (size_t)Dmax + 2) * sizeof(double);
   k_chol_prior<<<B, CHOL_THREADS, sm_prior, s2>>>(u, ib.Ls);
   check_launch("k_chol_prior");
   cudaEventRecord(join, s2);
@@ -773,7 +583,7 @@ void launch_info_update(const QrArgs& q, const UpdArgs& u, const InfoBufs& ib, i
   dim3 gr(((nmax + 1) * (nmax + 1) + 255) / 256, B);
   k_syrk_reduce<<<gr, 256, 0, s>>>(u, ib.part, kc, ib.max_chunks, ib.max_pairs, q.tiles, ib.tile_rows, ib.filter_rows);
   check_launch("k_syrk_reduce");
-  const size_t sm_w = ((size_t)nmax * (nmax + 1) / 2 + (size_t)(CS + 1) * nmax + 16) * sizeof(double);
+  const size_t sm_w = chol_smem_doubles(nmax, CS + 1) * sizeof(double);
   dim3 gw((Dmax + CS - 1) / CS, B);
   k_chol_w_solve<<<gw, CHOL_THREADS, sm_w, s>>>(u);
   check_launch("k_chol_w_solve");

@@ -2,6 +2,8 @@
 // dependent-chain-free DFMA throughput and mma.sync m8n8k4 f64 (DMMA) throughput.
 #include <cuda_runtime.h>
 #include "../../include/orcvio_b200.h"
+#include "kernels.h"
+#include "chol.cuh"
 
 namespace {
 
@@ -78,6 +80,75 @@ __global__ void __launch_bounds__(512) k_latency(double* out, double seed) {
 }
 
 }  // namespace
+
+// Stand-alone run of the one-CTA Cholesky (chol.cuh) on a caller-supplied SPD matrix: the unit test
+// and the per-phase clock profile of the routine both factorisation kernels are built on.
+namespace ob {
+template <bool PROF>
+__global__ void __launch_bounds__(CHOL_THREADS) k_chol_probe(const double* Ain, const double* Xin, int m, int nx,
+                                                             double* Lout, double* Xout, long long* prof) {
+  extern __shared__ double sm[];
+  __shared__ __align__(16) CholShared cs;
+  double* A = sm;
+  const int Tm = (m + 7) >> 3;
+  chol_init(A, cs, m, nx);
+  __syncthreads();
+  for (int e = threadIdx.x; e < m * m; e += blockDim.x) {
+    const int i = e / m, j = e - i * m;
+    if (j <= i) A[chol_at(i, j, Tm)] = Ain[e];
+  }
+  for (int e = threadIdx.x; e < nx * m; e += blockDim.x) {
+    const int q = e / m, k = e - q * m;
+    A[chol_at(m + q, k, Tm)] = Xin[e];
+  }
+  cta_cholesky<PROF>(A, cs, nullptr, m, nx, prof);
+  chol_for_rows(A, m, nx, 0, [&](int i, int k, double l) {
+    if (i < m) Lout[(size_t)i * m + k] = l;
+    else Xout[(size_t)(i - m) * m + k] = l;
+  });
+}
+}  // namespace ob
+
+extern "C" int orcvio_chol_probe(int m, int nx, const double* A, const double* X, double* L, double* Xs,
+                                 long long* prof, int reps, float* us) {
+  using namespace ob;
+  if (m < 1 || m > ORCVIO_LEG + 6 * ORCVIO_MAX_OBS || nx < 0 || m + nx > CHOL_MAXR - 8 ||
+      chol_smem_doubles(m, nx) * sizeof(double) > 193 * 1024) return ORCVIO_ERR_ARG;
+  double *dA = nullptr, *dX = nullptr, *dL = nullptr, *dXs = nullptr;
+  long long* dprof = nullptr;
+  const size_t nA = (size_t)m * m, nX = (size_t)std::max(nx, 1) * m;
+  if (cudaMalloc(&dA, nA * 8) != cudaSuccess) return ORCVIO_ERR_NO_DEVICE;
+  cudaMalloc(&dX, nX * 8);
+  cudaMalloc(&dL, nA * 8);
+  cudaMalloc(&dXs, nX * 8);
+  cudaMalloc(&dprof, 64 * 8 * sizeof(long long));
+  cudaMemcpy(dA, A, nA * 8, cudaMemcpyHostToDevice);
+  if (nx > 0) cudaMemcpy(dX, X, (size_t)nx * m * 8, cudaMemcpyHostToDevice);
+  cudaMemset(dL, 0, nA * 8);
+  cudaMemset(dprof, 0, 64 * 8 * sizeof(long long));
+  const size_t smem = chol_smem_doubles(m, nx) * sizeof(double);
+  cudaFuncSetAttribute(k_chol_probe<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 193 * 1024);
+  cudaFuncSetAttribute(k_chol_probe<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 193 * 1024);
+  k_chol_probe<true><<<1, CHOL_THREADS, smem>>>(dA, dX, m, nx, dL, dXs, dprof);
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  k_chol_probe<false><<<1, CHOL_THREADS, smem>>>(dA, dX, m, nx, dL, dXs, dprof);
+  cudaEventRecord(e0);
+  for (int r = 0; r < reps; ++r) k_chol_probe<false><<<1, CHOL_THREADS, smem>>>(dA, dX, m, nx, dL, dXs, dprof);
+  cudaEventRecord(e1);
+  cudaEventSynchronize(e1);
+  float ms = 0;
+  cudaEventElapsedTime(&ms, e0, e1);
+  if (us) *us = 1e3f * ms / std::max(reps, 1);
+  cudaMemcpy(L, dL, nA * 8, cudaMemcpyDeviceToHost);
+  if (nx > 0) cudaMemcpy(Xs, dXs, (size_t)nx * m * 8, cudaMemcpyDeviceToHost);
+  if (prof) cudaMemcpy(prof, dprof, 64 * 8 * sizeof(long long), cudaMemcpyDeviceToHost);
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(dA); cudaFree(dX); cudaFree(dL); cudaFree(dXs); cudaFree(dprof);
+  return cudaGetLastError() == cudaSuccess ? ORCVIO_OK : ORCVIO_ERR_CUDA;
+}
 
 extern "C" int orcvio_latency_probe(double* cycles7) {
   double* out = nullptr;
