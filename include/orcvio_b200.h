@@ -71,7 +71,9 @@ typedef struct {
   int n_gate_pass_prune;
   int n_removed_clones;
   long long removed_ids[2];
-  int zupt;
+  int zupt;                  /* 1: the frame took a zero-velocity update (checkZUPTFeat / checkZUPTIMU) */
+  double zupt_chi2;          /* checkZUPTIMU only: chi2 of the stationarity test and |v| it was compared with */
+  double zupt_vnorm;
 } OrcvioFrameStats;
 
 typedef struct orcvio_handle orcvio_handle;

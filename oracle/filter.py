@@ -843,7 +843,12 @@ class OracleVIO:
 
     def checkZUPTIMU(self):
         """:3129-3323."""
+        self.zupt_info = None
         if len(self.imu_recent_zupt) < 2:
+            return False
+        if (self.imu_state.id - 1) not in self.clones:
+            # the reference would default-construct a clone through std::map::operator[] here (:3345-3346)
+            # and corrupt its window; a one-clone window never takes a ZUPT in this restatement
             return False
         sigma_w_2 = 1.6968e-04 ** 2
         sigma_a_2 = 2.0000e-3 ** 2
@@ -884,6 +889,7 @@ class OracleVIO:
         else:
             from scipy.stats import chi2 as c2
             chk = float(c2.ppf(0.95, dof))
+        self.zupt_info = (chi2, float(np.linalg.norm(self.imu_state.velocity)))
         if chi2 > chk or np.linalg.norm(self.imu_state.velocity) > 0.25:
             return False
         self.measurementUpdate_ZUPT_vpq()

@@ -39,7 +39,8 @@ class OrcvioFrameStats(C.Structure):
     _fields_ = [("n_candidates_lost", C.c_int), ("n_tri_invalid_lost", C.c_int),
                 ("n_gate_pass_lost", C.c_int), ("n_candidates_prune", C.c_int),
                 ("n_tri_invalid_prune", C.c_int), ("n_gate_pass_prune", C.c_int),
-                ("n_removed_clones", C.c_int), ("removed_ids", C.c_longlong * 2), ("zupt", C.c_int)]
+                ("n_removed_clones", C.c_int), ("removed_ids", C.c_longlong * 2), ("zupt", C.c_int),
+                ("zupt_chi2", C.c_double), ("zupt_vnorm", C.c_double)]
 
 
 FEAT_DTYPE = np.dtype([("id", "<u8"), ("u", "<f8"), ("v", "<f8"), ("u_init", "<f8"), ("v_init", "<f8"),

@@ -27,6 +27,7 @@ SOURCES = {
     "info_kernel.cu": [],
     "peak_kernel.cu": [],
     "prop_kernel.cu": [],
+    "zupt_kernel.cu": [],
     "obj_kernel.cu": [],
     "batch.cu": [],
     "objects.cu": [],

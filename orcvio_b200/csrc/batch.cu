@@ -132,6 +132,16 @@ Batch::Batch(const Params& p, int n) : p_(p), B_(n) {
   for (int i = 1; i < 500; ++i) chi2_host_[i] = chi2_quantile(p_.chi_square_threshold_feat, i);
   CK(cudaMalloc(&dChi2_, 500 * sizeof(double)));
   CK(cudaMemcpy(dChi2_, chi2_host_.data(), 500 * sizeof(double), cudaMemcpyHostToDevice));
+  if (p_.if_ZUPT_valid) {
+    chi2_zupt_host_.assign(500, 0.0);
+    if (!p_.if_use_feature_zupt_flag)
+      for (int i = 1; i < 500; ++i) chi2_zupt_host_[i] = chi2_quantile(0.95, i);
+    CK(cudaMalloc(&dZuptDec_, nB * sizeof(int)));
+    CK(cudaMalloc(&dZuptInfo_, nB * 2 * sizeof(double)));
+    CK(cudaMallocHost(&hZuptDec_, nB * sizeof(int)));
+    CK(cudaMallocHost(&hZuptInfo_, nB * 2 * sizeof(double)));
+    std::memset(hZuptDec_, 0, nB * sizeof(int));
+  }
   CK(cudaMallocHost(&hImu_, nB * IM_STRIDE * sizeof(double)));
   CK(cudaMallocHost(&hClones_, nB * Ncap_ * CL_STRIDE * sizeof(double)));
   CK(cudaMallocHost(&hDx_, nB * ldp_ * sizeof(double)));
@@ -145,6 +155,10 @@ Batch::~Batch() {
   cudaFree(dErr_); cudaFree(dFront_); cudaFree(dChi2_);
   cudaFree(dAmat_); cudaFree(dPart_);
   cudaFree(dLs_); cudaFree(dTileRows_); cudaFree(dFilterRows_);
+  if (dZuptDec_) cudaFree(dZuptDec_);
+  if (dZuptInfo_) cudaFree(dZuptInfo_);
+  if (hZuptDec_) cudaFreeHost(hZuptDec_);
+  if (hZuptInfo_) cudaFreeHost(hZuptInfo_);
   cudaFree(dHblk_); cudaFree(dRblk_); cudaFree(dTileOut_); cudaFree(dStatus_); cudaFree(dGamma_);
   if (blob_.dev) cudaFree(blob_.dev);
   if (blob_.pinned) cudaFreeHost(blob_.pinned);
@@ -474,7 +488,7 @@ static void build_tiles(Batch::PhaseWork& w, int fi, int c0, int c1) {
 
 // Append one filter's candidates (sorted by first clone, then id) to the phase work list.
 static void append_candidates(Batch::PhaseWork& w, int fi, std::vector<CandBuild>& cb,
-                              std::vector<CandInfo>& info_out) {
+                              std::vector<CandInfo>& info_out, bool tri_only = false) {
   std::stable_sort(cb.begin(), cb.end(), [](const CandBuild& a, const CandBuild& b) {
     if (a.c.s_blk != b.c.s_blk) return a.c.s_blk < b.c.s_blk;
     return a.id < b.id;
@@ -483,19 +497,21 @@ static void append_candidates(Batch::PhaseWork& w, int fi, std::vector<CandBuild
   for (auto& x : cb) {
     Cand c = x.c;
     c.filter = fi;
-    const int r = 2 * c.jac_m - 3;
+    const int r = tri_only ? 0 : 2 * c.jac_m - 3;
     c.row_off = (int)w.rows_total;
     c.hblk_off = (int)w.hblk_total;
     w.rows_total += (size_t)std::max(r, 0);
     w.hblk_total += (size_t)std::max(r, 0) * 6 * (c.e_blk - c.s_blk + 1);
-    w.own_wmax_blk = std::max(w.own_wmax_blk, c.e_blk - c.s_blk + 1);
     const int idx = (int)w.cands.size();
-    if (c.jac_m <= 8) w.small_list.push_back(idx);
-    else w.large_list.push_back(idx);
+    if (!tri_only) {
+      w.own_wmax_blk = std::max(w.own_wmax_blk, c.e_blk - c.s_blk + 1);
+      if (c.jac_m <= 8) w.small_list.push_back(idx);
+      else w.large_list.push_back(idx);
+    }
     w.cands.push_back(c);
     info_out.push_back(CandInfo{x.id, x.kind});
   }
-  build_tiles(w, fi, c0, (int)w.cands.size());
+  if (!tri_only) build_tiles(w, fi, c0, (int)w.cands.size());
 }
 
 int Batch::process(const double* t_img, const OrcvioFeature* feats, const int* feat_off,
@@ -624,6 +640,13 @@ int Batch::process(const double* t_img, const OrcvioFeature* feats, const int* f
           if (!tr.obs.empty() && tr.obs.back().sid == sid) tr.obs.back() = o;
           else tr.obs.push_back(o);
           ++tracked;
+          if (p_.if_ZUPT_valid && p_.if_use_feature_zupt_flag) {     // :1052-1058
+            for (const Obs& po : tr.obs)
+              if (po.sid == sid - 1) {
+                const double du = m.u - po.z[0], dv = m.v - po.z[1];
+                F.coarse_feature_dis.push_back(std::sqrt(du * du + dv * dv));
+              }
+          }
         }
       }
       F.tracking_rate = (double)tracked / (double)curr_feature_num;   // 0/0 -> NaN like the reference
@@ -649,6 +672,43 @@ int Batch::process(const double* t_img, const OrcvioFeature* feats, const int* f
     std::vector<int> Naug(B_);
     for (int fi = 0; fi < B_; ++fi) Naug[fi] = f_[fi].active ? Nvec[fi] : -1;
     std::memcpy(h + o_n, Naug.data(), sizeof(int) * B_);
+    // ZUPT (:583-592): the feature test (checkZUPTFeat :3081-3125) is a host decision on the sorted
+    // track displacements; the IMU test (checkZUPTIMU) needs P and runs inside k_zupt.
+    size_t o_zm = 0, o_zn = 0, o_zc = 0;
+    bool any_zupt = false;
+    if (p_.if_ZUPT_valid) {
+      std::vector<int> zmode(B_, 0), zN(B_, -1);
+      std::vector<double> zchk(B_, 0.0);
+      for (int fi = 0; fi < B_; ++fi) {
+        FilterHost& F = f_[fi];
+        F.if_zupt = false;
+        if (!F.active) continue;
+        zN[fi] = Nvec[fi] + 1;
+        if (p_.if_use_feature_zupt_flag) {
+          std::vector<double>& d = F.coarse_feature_dis;
+          if (d.size() >= 20) {
+            std::sort(d.begin(), d.end());
+            if (d[d.size() - 9] < p_.zupt_max_feature_dis) zmode[fi] = 1;
+          }
+          d.clear();
+        } else {
+          const int cnt = samp_off[fi + 1] - samp_off[fi];
+          if (cnt >= 2) {
+            zmode[fi] = 2;
+            const int dof = 6 * (cnt - 1);
+            zchk[fi] = dof < 500 ? chi2_zupt_host_[dof] : chi2_quantile(0.95, dof);
+          }
+        }
+        any_zupt |= zmode[fi] != 0;
+      }
+      o_zm = blob_.reserve(sizeof(int) * B_);
+      o_zn = blob_.reserve(sizeof(int) * B_);
+      o_zc = blob_.reserve(sizeof(double) * B_);
+      h = blob_.host.data();
+      std::memcpy(h + o_zm, zmode.data(), sizeof(int) * B_);
+      std::memcpy(h + o_zn, zN.data(), sizeof(int) * B_);
+      std::memcpy(h + o_zc, zchk.data(), sizeof(double) * B_);
+    }
     upload_blob();
     if (profiling_) CK(cudaEventRecord(ev_[6], stream_));
     PropArgs pa{};
@@ -667,6 +727,23 @@ int Batch::process(const double* t_img, const OrcvioFeature* feats, const int* f
     aa.N = (const int*)(blob_.dev + o_n); aa.n_filters = B_;
     launch_augment(aa, stream_);
     launches_ += 2;
+    if (any_zupt) {
+      ZuptArgs za{};
+      za.P = dP_; za.p_stride = pa.p_stride; za.ldp = ldp_;
+      za.imu = dImu_; za.clones = dClones_; za.clone_stride = aa.clone_stride;
+      za.samples = pa.samples; za.samp_off = pa.samp_off;
+      za.N = (const int*)(blob_.dev + o_zn);
+      za.mode = (const int*)(blob_.dev + o_zm);
+      za.chi2_check = (const double*)(blob_.dev + o_zc);
+      za.decision = dZuptDec_; za.info = dZuptInfo_;
+      za.dx = dDx_; za.lddx = ldp_;
+      za.n_filters = B_; za.flags = flags_;
+      za.noise_v = p_.zupt_noise_v; za.noise_p = p_.zupt_noise_p; za.noise_q = p_.zupt_noise_q;
+      launch_zupt(za, stream_);
+      ++launches_;
+      CK(cudaMemcpyAsync(hZuptDec_, dZuptDec_, sizeof(int) * B_, cudaMemcpyDeviceToHost, stream_));
+      CK(cudaMemcpyAsync(hZuptInfo_, dZuptInfo_, sizeof(double) * 2 * B_, cudaMemcpyDeviceToHost, stream_));
+    }
     if (profiling_) {
       CK(cudaEventRecord(ev_[7], stream_));
     }
@@ -676,6 +753,18 @@ int Batch::process(const double* t_img, const OrcvioFeature* feats, const int* f
       float ms = 0;
       cudaEventElapsedTime(&ms, ev_[6], ev_[7]);
       pt_.prop += ms; pt_.n_prop++;
+    }
+    if (any_zupt) {
+      for (int fi = 0; fi < B_; ++fi) {
+        FilterHost& F = f_[fi];
+        if (!F.active) continue;
+        F.if_zupt = hZuptDec_[fi] != 0;
+        F.zupt_chi2 = hZuptInfo_[2 * fi];
+        F.zupt_vnorm = hZuptInfo_[2 * fi + 1];
+        F.stats.zupt = F.if_zupt ? 1 : 0;
+        F.stats.zupt_chi2 = F.zupt_chi2;
+        F.stats.zupt_vnorm = F.zupt_vnorm;
+      }
     }
   }
 
@@ -746,6 +835,12 @@ int Batch::process(const double* t_img, const OrcvioFeature* feats, const int* f
     }
     F.stats.n_candidates_lost = (int)cb.size();
     if (cb.empty()) continue;
+    if (F.if_zupt) {
+      // :2564-2569: under ZUPT the candidates are still initialised (and the failures erased) but
+      // no Jacobian is stacked and no update runs
+      append_candidates(wA, fi, cb, F.cinfo[0], true);
+      continue;
+    }
     fw.active = 1;
     wA.any_active = true;
     append_candidates(wA, fi, cb, F.cinfo[0]);
@@ -806,6 +901,21 @@ int Batch::process(const double* t_img, const OrcvioFeature* feats, const int* f
       }
     }
     // pruneImuStateBuffer :2629-2959
+    if (F.if_zupt) {
+      // :2633-2639: a stationary frame drops the previous clone (id - 1) and uses nothing
+      const int n = (int)F.clones.size();
+      if (n < 2) continue;
+      rm_idx[2 * fi] = n - 2;
+      const long long rm_id = F.clones[n - 2].id;
+      F.stats.n_removed_clones = 1;
+      F.stats.removed_ids[0] = rm_id;
+      for (auto& kv : F.map_server) {
+        Track& tr = kv.second;
+        tr.obs.erase(std::remove_if(tr.obs.begin(), tr.obs.end(), [&](const Obs& o) { return o.sid == rm_id; }),
+                     tr.obs.end());
+      }
+      continue;
+    }
     if ((int)F.clones.size() < p_.sw_size) continue;
     wB.maxN = std::max(wB.maxN, fw.N);
     // findRedundantImuStates :2582-2626
@@ -934,12 +1044,12 @@ int Batch::process(const double* t_img, const OrcvioFeature* feats, const int* f
     }
     if (rm_idx[2 * fi] >= 0) {
       const int a = rm_idx[2 * fi], b = rm_idx[2 * fi + 1];
-      const double ta = F.clones[a].time, tb = F.clones[b].time;
+      const double ta = F.clones[a].time, tb = b >= 0 ? F.clones[b].time : ta;
       F.cur_window_timestamps.erase(
           std::remove_if(F.cur_window_timestamps.begin(), F.cur_window_timestamps.end(),
                          [&](double t) { return t == ta || t == tb; }),
           F.cur_window_timestamps.end());
-      F.clones.erase(F.clones.begin() + b);
+      if (b >= 0) F.clones.erase(F.clones.begin() + b);
       F.clones.erase(F.clones.begin() + a);
     }
     std::memcpy(F.imu_mirror.data(), hImu_ + (size_t)fi * IM_STRIDE, IM_STRIDE * sizeof(double));

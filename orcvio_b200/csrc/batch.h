@@ -55,6 +55,8 @@ struct FilterHost {
   double take_off_stamp = 0.0;
   bool active = false;        // took part in the current frame
   bool if_zupt = false;
+  std::vector<double> coarse_feature_dis;   // checkZUPTFeat input, filled by addFeatureObservations (:1052-1058)
+  double zupt_chi2 = 0.0, zupt_vnorm = 0.0;  // checkZUPTIMU diagnostics of the last frame
   std::vector<double> imu_mirror;      // IM_STRIDE
   std::vector<double> clone_mirror;    // Ncap * CL_STRIDE
   std::vector<double> cur_window_timestamps;
@@ -208,6 +210,9 @@ class Batch {
   bool profiling_ = false;
   PhaseTimes pt_;
   std::vector<double> chi2_host_;
+  std::vector<double> chi2_zupt_host_;     // chi_squared_table_zupt (p = 0.95, :482-493)
+  int* dZuptDec_ = nullptr; double* dZuptInfo_ = nullptr;
+  int* hZuptDec_ = nullptr; double* hZuptInfo_ = nullptr;
 
   void upload_blob();
   void ensure_scratch(size_t n_cand, size_t hblk, size_t rblk, size_t tileout);

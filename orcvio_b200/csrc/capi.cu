@@ -32,7 +32,6 @@ bool check_supported(const Params& p, std::string& why) {
   else if (p.if_FEJ) why = "if_FEJ=1 is not supported";
   else if (p.max_features * p.grid_rows * p.grid_cols != 0)
     why = "hybrid EKF-SLAM features (max_features_in_one_grid > 0) are not supported yet";
-  else if (p.if_ZUPT_valid) why = "if_ZUPT_valid=1 is not supported yet";
   else if (!p.use_larvio_flag && !p.use_closed_form_cov_prop_flag)
     why = "Euler covariance propagation is dimensionally inconsistent in the reference and unsupported";
   else if (p.use_schmidt) why = "use_schmidt=1 is not supported";

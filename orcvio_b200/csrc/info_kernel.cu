@@ -27,6 +27,7 @@
 // forming G = H'^T H' first and then L^T G L loses a factor ~rows (measured 2e-9 vs 1e-12 on the
 // Unity-shaped sequence; DESIGN.md "numerics").
 #include "kernels.h"
+#include "increment.cuh"
 #include "chol.cuh"
 
 namespace ob {
@@ -366,7 +367,6 @@ __global__ void __launch_bounds__(CHOL_THREADS) k_chol_w_solve(UpdArgs a) {
 __global__ void __launch_bounds__(512) k_dx(UpdArgs a) {
   __shared__ double partial[16][ORCVIO_LEG + 6 * ORCVIO_MAX_OBS + 2];
   __shared__ double dxs[ORCVIO_LEG + 6 * ORCVIO_MAX_OBS + 2];
-  __shared__ int s_apply;
   const int fi = blockIdx.x;
   const FilterWork fw = a.fw[fi];
   if (!fw.active) return;
@@ -391,60 +391,7 @@ __global__ void __launch_bounds__(512) k_dx(UpdArgs a) {
     if (a.dx) a.dx[(size_t)fi * a.lddx + i] = s;
   }
   __syncthreads();
-  if (tid == 0) {
-    double nv = sqrt((dxs[3] * dxs[3] + dxs[4] * dxs[4]) + dxs[5] * dxs[5]);
-    double np = sqrt((dxs[6] * dxs[6] + dxs[7] * dxs[7]) + dxs[8] * dxs[8]);
-    int apply = 1;
-    if ((nv > 1.0 || np > 1.5) && (a.flags & FL_DISCARD_LARGE)) {
-      apply = 0;
-      imu[IM_DISCARDS] += 1.0;
-    }
-    s_apply = apply;
-    if (a.dx) a.dx[(size_t)fi * a.lddx + a.lddx - 1] = (double)apply;
-    if (apply) {
-      const bool left = (a.flags & FL_LARVIO) || (a.flags & FL_LEFT);
-      double Rt[9], Rn[9];
-      so3_exp(dxs, Rt);
-      if (left) m3_mul(Rt, imu + IM_R, Rn);
-      else m3_mul(imu + IM_R, Rt, Rn);
-      for (int i = 0; i < 9; ++i) imu[IM_R + i] = Rn[i];
-      for (int i = 0; i < 3; ++i) {
-        imu[IM_V + i] += dxs[3 + i];
-        imu[IM_P + i] += dxs[6 + i];
-        imu[IM_BG + i] += dxs[9 + i];
-        imu[IM_BA + i] += dxs[12 + i];
-      }
-      double dq[3] = {dxs[15] / 2.0, dxs[16] / 2.0, dxs[17] / 2.0};
-      double n2 = (dq[0] * dq[0] + dq[1] * dq[1]) + dq[2] * dq[2];
-      double qw, qs = 1.0;
-      if (n2 <= 1) qw = sqrt(1 - n2);
-      else { qw = 1; qs = 1.0 / sqrt(1 + n2); }
-      double Rq[9], Rb[9];
-      quat_wxyz_to_R(qw * qs, dq[0] * qs, dq[1] * qs, dq[2] * qs, Rq);
-      m3_mulT(imu + IM_RBC, Rq, Rb);
-      for (int i = 0; i < 9; ++i) imu[IM_RBC + i] = Rb[i];
-      for (int i = 0; i < 3; ++i) imu[IM_TCB + i] += dxs[18 + i];
-      imu[IM_TD] += dxs[21];
-    }
-  }
-  __syncthreads();
-  if (!s_apply) return;
-  if (tid < fw.N) {
-    const bool left = (a.flags & FL_LARVIO) || (a.flags & FL_LEFT);
-    double* c = clones + (size_t)tid * CL_STRIDE;
-    const double* d = dxs + ORCVIO_LEG + 6 * tid;
-    double Rt[9], Rn[9];
-    so3_exp(d, Rt);
-    if (left) m3_mul(Rt, c + CL_R, Rn);
-    else m3_mul(c + CL_R, Rt, Rn);
-    for (int i = 0; i < 9; ++i) c[CL_R + i] = Rn[i];
-    for (int i = 0; i < 3; ++i) c[CL_P + i] += d[3 + i];
-    double Rc[9], t[3];
-    m3_mulT(Rn, imu + IM_RBC, Rc);
-    m3_vec(Rn, imu + IM_TCB, t);
-    for (int i = 0; i < 9; ++i) c[CL_RC + i] = Rc[i];
-    for (int i = 0; i < 3; ++i) c[CL_PC + i] = c[CL_P + i] + t[i];
-  }
+  cta_increment_state(dxs, imu, clones, fw.N, a.flags, a.dx ? &a.dx[(size_t)fi * a.lddx + a.lddx - 1] : nullptr);
 }
 
 // ---------------------------------------------------------------- P+ = s^2 Y^T Y + F_2 F_2^T

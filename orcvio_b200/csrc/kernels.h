@@ -152,6 +152,21 @@ struct RemoveArgs {
   int n_filters;
 };
 
+// Zero-velocity update (zupt_kernel.cu): checkZUPTIMU + measurementUpdate_ZUPT_vpq, src/orcvio.cpp:3129-3454
+struct ZuptArgs {
+  double* P; size_t p_stride; int ldp;
+  double* imu; double* clones; size_t clone_stride;
+  const PropSample* samples; const int* samp_off;        // imu_recent_zupt = the samples of this frame
+  const int* N;                                          // clones AFTER augmentation (< 2: no ZUPT)
+  const int* mode;                                       // 0 none, 1 update (feature test passed), 2 IMU chi2 test
+  const double* chi2_check;                              // per filter chi2 threshold of the IMU test
+  int* decision;                                         // out: 1 = the ZUPT update was applied
+  double* info;                                          // out, 2 per filter: chi2, |v| of the IMU test
+  double* dx; int lddx;
+  int n_filters; int flags;
+  double noise_v, noise_p, noise_q;                      // zupt_noise_{v,p,q}^2
+};
+
 // Records (and prints) a launch-configuration error; Batch polls launch_error_count().
 void check_launch(const char* name);
 int launch_error_count();
@@ -179,6 +194,7 @@ void launch_object_construct(const double* jac_sensor, const double* Hf, const d
 void launch_propagate(const PropArgs& a, cudaStream_t s);
 void launch_augment(const AugArgs& a, cudaStream_t s);
 void launch_remove(const RemoveArgs& a, cudaStream_t s);
+void launch_zupt(const ZuptArgs& a, cudaStream_t s);
 
 // tile sizing shared by host tiler and kernels
 constexpr int QR_THREADS = 256;

@@ -57,6 +57,24 @@ class Trajectory:
     phase: float = 0.0
     amp: float = 1.0
     R_b2c: np.ndarray = None
+    stops: tuple = ()                # (t_begin, t_end) intervals during which the platform stands still
+    stop_ramp: float = 0.4           # seconds of smooth deceleration / acceleration around a stop
+
+    def _warp(self, t):
+        """Trajectory time tau(t): tau' = 1 outside the stops, 0 inside, C^2 ramps in between."""
+        tau = t
+        r = self.stop_ramp
+        for (a, b) in self.stops:
+            def ramp_int(x):         # integral of the smootherstep 6x^5-15x^4+10x^3 on [0, x]
+                x = min(max(x, 0.0), 1.0)
+                return x ** 6 - 3 * x ** 5 + 2.5 * x ** 4
+            # bump(t) = s((t-a)/r) on [a, a+r], 1 on [a+r, b-r], 1 - s((t-(b-r))/r) on [b-r, b]
+            up = r * ramp_int((t - a) / r)
+            flat = min(max(t - (a + r), 0.0), max(b - r - (a + r), 0.0))
+            x = min(max((t - (b - r)) / r, 0.0), 1.0)
+            down = r * (x - ramp_int(x))
+            tau -= up + flat + down
+        return tau
 
     @staticmethod
     def _cam_frame(psi):
@@ -64,6 +82,8 @@ class Trajectory:
         return np.array([[s, 0.0, c], [-c, 0.0, s], [0.0, -1.0, 0.0]])   # columns x_c, y_c, z_c
 
     def pose(self, t):
+        if self.stops:
+            t = self._warp(t)
         if self.kind == "kitti":
             v0 = 10.0 * self.speed
             k = 0.05
@@ -114,6 +134,7 @@ class SynthSpec:
     gyro_bias: tuple = (0.002, -0.001, 0.0015)
     acc_bias: tuple = (0.02, 0.01, -0.015)
     overrides: dict = field(default_factory=dict)
+    stops: tuple = ()                # stand-still intervals (ZUPT test sequences)
 
 
 def _extrinsics(cfg):
@@ -134,7 +155,7 @@ def make_sequence(spec: SynthSpec):
     dt_imu = 1.0 / imu_rate
     R_b2c, t_c_b = _extrinsics(base)
     traj = Trajectory(kind=kind, speed=1.0 + 0.05 * ((k * 7) % 5), phase=0.37 * k,
-                      amp=1.0 + 0.03 * (k % 4), R_b2c=R_b2c)
+                      amp=1.0 + 0.03 * (k % 4), R_b2c=R_b2c, stops=tuple(spec.stops))
     fx, fy = base["intrinsics"]["fx"], base["intrinsics"]["fy"]
     cx, cy = base["intrinsics"]["cx"], base["intrinsics"]["cy"]
     x_min, x_max = -cx / fx, (base["resolution_width"] - cx) / fx

@@ -21,9 +21,15 @@ import helpers as H
 pytestmark = pytest.mark.gpu
 
 CASES = [
-    ("unity", dict(if_ZUPT_valid=0), 45, 120, 6000),
-    ("euroc", dict(if_ZUPT_valid=0, max_features_in_one_grid=0), 45, 120, 6000),
-    ("kitti_odom", dict(max_features_in_one_grid=0), 40, 250, 20000),
+    ("unity", dict(if_ZUPT_valid=0), 45, 120, 6000, {}),
+    ("euroc", dict(if_ZUPT_valid=0, max_features_in_one_grid=0), 45, 120, 6000, {}),
+    ("kitti_odom", dict(max_features_in_one_grid=0), 40, 250, 20000, {}),
+    # ZUPT: a stand-still interval in the trajectory.  euroc.yaml uses the feature test
+    # (checkZUPTFeat; the synthetic pixel noise needs a wider displacement bound than 2e-3), unity.yaml the
+    # IMU chi-square test (checkZUPTIMU; its hard-coded noise constants need a quieter synthetic IMU).
+    ("euroc", dict(max_features_in_one_grid=0, zupt_max_feature_dis=0.03), 40, 120, 6000,
+     dict(stops=((11.0, 12.6),))),
+    ("unity", dict(), 40, 120, 6000, dict(stops=((11.0, 12.6),), imu_noise_scale=0.01)),
 ]
 
 
@@ -77,6 +83,10 @@ def _compare_decisions(fi, vio, ref):
         if not lg:
             assert not gpu_valid
             continue
+        if lg[0].get("zupt"):               # stationary frame: candidates are initialised, nothing is gated
+            assert gpu_valid == set(lg[0]["candidates"]), f"frame {fi} {kind}: candidate sets differ (ZUPT)"
+            assert not any(gpu_pass.values())
+            continue
         ref_gate = lg[0]["gate"]            # the oracle logs the features that survived triangulation
         assert gpu_valid == set(ref_gate.keys()), f"frame {fi} {kind}: candidate sets differ"
         gg = {int(i): x for i, x in zip(ids[sel], gamma[sel])}
@@ -113,11 +123,13 @@ def _compare_state(fi, vio, ref):
         np.testing.assert_allclose(poses[c][9:], cl.position, rtol=1e-9, atol=1e-9)
 
 
-@pytest.mark.parametrize("config,overrides,n_frames,feats,n_landmarks", CASES)
-def test_sequence_parity_per_update(config, overrides, n_frames, feats, n_landmarks):
+@pytest.mark.parametrize("config,overrides,n_frames,feats,n_landmarks,spec_kw", CASES)
+def test_sequence_parity_per_update(config, overrides, n_frames, feats, n_landmarks, spec_kw):
     seq = synth.make_sequence(synth.SynthSpec(config=config, seed=0, n_frames=n_frames,
                                               feats_per_frame=feats, overrides=overrides,
-                                              n_landmarks=n_landmarks))
+                                              n_landmarks=n_landmarks, **spec_kw))
+    zupt_on = bool(seq["cfg"]["if_ZUPT_valid"])
+    n_zupt = 0
     vio = api.OrcVIO(H.write_cfg(seq["cfg"]))
     assert vio.initialize()
     oracle_iter = H.run_oracle_sequence(seq)
@@ -133,12 +145,22 @@ def test_sequence_parity_per_update(config, overrides, n_frames, feats, n_landma
         fs = vio.frame_stats()
         prune_log = [l for l in ref.log if l.get("state_id") == ref.imu_state.id and l["kind"] == "prune"]
         if prune_log:
-            assert sorted(fs.removed_ids[:]) == sorted(prune_log[0]["rm_ids"]), f"frame {fi}: pruned clones differ"
+            assert sorted(i for i in fs.removed_ids[:] if i >= 0) == sorted(prune_log[0]["rm_ids"]), \
+                f"frame {fi}: pruned clones differ"
             n_rm += 1
+        if zupt_on:
+            assert bool(fs.zupt) == bool(ref.if_ZUPT), f"frame {fi}: ZUPT decision differs"
+            n_zupt += int(fs.zupt)
+            info = getattr(ref, "zupt_info", None)
+            if info is not None and not seq["cfg"]["if_use_feature_zupt_flag"]:
+                assert abs(fs.zupt_chi2 - info[0]) <= 1e-9 * abs(info[0]), f"frame {fi}: ZUPT chi2 differs"
+                assert abs(fs.zupt_vnorm - info[1]) <= 1e-9
         _compare_state(fi, vio, ref)
         _sync_oracle_from_gpu(ref, vio)
         p_gpu.append(np.array(vio.state().p))
     assert n_cand > 50 and n_pass > 25 and n_rm > 5
+    if zupt_on:
+        assert n_zupt >= 5
     gt = np.array([g[1] for g in seq["gt"]])
     assert np.linalg.norm(p_gpu[-1] - gt[-1]) < 2.0     # sanity: the filter tracks the synthetic truth
 
