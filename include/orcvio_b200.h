@@ -202,6 +202,9 @@ int orcvio_frame_run(orcvio_frame* f, int repeat, float* total_us, float* stage_
 int orcvio_frame_fetch(orcvio_frame* f, double* P_out, double* delta_x, int* status, double* gamma,
                        double* clone_out);
 long long orcvio_frame_kernel_launches(orcvio_frame* f);
+/* wall-clock split (us) of the last orcvio_frame_update: host work-list build + uploads, kernel launches,
+ * wait + downloads, total -- explains the gap between the device-timed and the end-to-end figure */
+int orcvio_frame_host_times(orcvio_frame* f, float* us4);
 
 /* Stage 2 only, for element-wise parity of J1 (measurementJacobian_msckf, orcvio.cpp:1071-1168):
  * per observation H_x (2x6), H_e (2x6), H_f (2x3), r (2), row-major. */

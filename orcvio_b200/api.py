@@ -121,6 +121,7 @@ def lib():
     L.orcvio_frame_fetch.argtypes = [vp, dp, dp, ip, dp, dp]
     L.orcvio_frame_kernel_launches.restype = C.c_longlong
     L.orcvio_frame_kernel_launches.argtypes = [vp]
+    L.orcvio_frame_host_times.argtypes = [vp, C.POINTER(C.c_float)]
     _lib = L
     return L
 
@@ -453,6 +454,12 @@ class Frame:
 
     def kernel_launches(self):
         return int(self._L.orcvio_frame_kernel_launches(self._h))
+
+    def host_times(self):
+        """Wall-clock split (us) of the last update(): prepare, launch, wait+fetch, total."""
+        us = (C.c_float * 4)()
+        self._L.orcvio_frame_host_times(self._h, us)
+        return dict(prepare=us[0], launch=us[1], wait_fetch=us[2], total=us[3])
 
 
 # ---------------------------------------------------------------- stage-level calls

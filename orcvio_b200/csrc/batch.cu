@@ -52,6 +52,18 @@ struct Batch::PhaseWork {
   const Cand* dC = nullptr; const int* dOc = nullptr; const double* dOz = nullptr;
   const Tile* dTiles = nullptr; const FilterWork* dFw = nullptr;
   const int* dSmall = nullptr; const int* dLarge = nullptr;
+  // observation pools referenced in place (snapshot entry points): copied straight into the pinned blob
+  const int* ext_obs_clone = nullptr; const double* ext_obs_z = nullptr; size_t ext_nobs = 0;
+  size_t n_obs() const { return ext_obs_clone ? ext_nobs : obs_clone.size(); }
+  void reset() {                 // keep the vectors' capacity across frames
+    cands.clear(); obs_clone.clear(); obs_z.clear(); tiles.clear(); fw.clear();
+    small_list.clear(); large_list.clear(); cand_begin.clear(); extra_ints.clear();
+    hblk_total = rows_total = tileout_total = tile_smem_doubles = 0;
+    rows_cap = 0; max_tile_rows = 0; arows_total = 0; own_wmax_blk = 1; wmax_blk = 1; maxN = 0;
+    any_active = false; d_extra = nullptr;
+    dC = nullptr; dOc = nullptr; dOz = nullptr; dTiles = nullptr; dFw = nullptr; dSmall = dLarge = nullptr;
+    ext_obs_clone = nullptr; ext_obs_z = nullptr; ext_nobs = 0;
+  }
 };
 
 static constexpr int WTILE_MAX_BLK = 8;   // widest clone window a tile may span (blocks)
@@ -245,12 +257,6 @@ void Batch::upload_blob() {
     blob_.dev_cap = blob_.used * 2 + 4096;
     CK(cudaMalloc(&blob_.dev, blob_.dev_cap));
   }
-  if (blob_.used > blob_.pinned_cap) {
-    if (blob_.pinned) cudaFreeHost(blob_.pinned);
-    blob_.pinned_cap = blob_.used * 2 + 4096;
-    CK(cudaMallocHost(&blob_.pinned, blob_.pinned_cap));
-  }
-  std::memcpy(blob_.pinned, blob_.host.data(), blob_.used);
   CK(cudaMemcpyAsync(blob_.dev, blob_.pinned, blob_.used, cudaMemcpyHostToDevice, stream_));
 }
 
@@ -281,18 +287,21 @@ void Batch::stage_phase(PhaseWork& w) {
   const int nC = (int)w.cands.size();
   blob_.reset();
   const size_t o_c = blob_.reserve(sizeof(Cand) * std::max(nC, 1));
-  const size_t o_oc = blob_.reserve(sizeof(int) * std::max<size_t>(w.obs_clone.size(), 1));
-  const size_t o_oz = blob_.reserve(sizeof(double) * std::max<size_t>(w.obs_z.size(), 1));
+  const size_t n_obs = w.n_obs();
+  const size_t o_oc = blob_.reserve(sizeof(int) * std::max<size_t>(n_obs, 1));
+  const size_t o_oz = blob_.reserve(sizeof(double) * std::max<size_t>(2 * n_obs, 1));
   const size_t o_t = blob_.reserve(sizeof(Tile) * std::max<size_t>(w.tiles.size(), 1));
   const size_t o_f = blob_.reserve(sizeof(FilterWork) * B_);
   const size_t o_s = blob_.reserve(sizeof(int) * std::max<size_t>(w.small_list.size(), 1));
   const size_t o_l = blob_.reserve(sizeof(int) * std::max<size_t>(w.large_list.size(), 1));
   const size_t o_x = blob_.reserve(sizeof(int) * std::max<size_t>(w.extra_ints.size(), 1));
-  char* h = blob_.host.data();
+  char* h = blob_.pinned;
   if (!w.extra_ints.empty()) std::memcpy(h + o_x, w.extra_ints.data(), sizeof(int) * w.extra_ints.size());
   if (nC) std::memcpy(h + o_c, w.cands.data(), sizeof(Cand) * nC);
-  if (!w.obs_clone.empty()) std::memcpy(h + o_oc, w.obs_clone.data(), sizeof(int) * w.obs_clone.size());
-  if (!w.obs_z.empty()) std::memcpy(h + o_oz, w.obs_z.data(), sizeof(double) * w.obs_z.size());
+  if (n_obs) {
+    std::memcpy(h + o_oc, w.ext_obs_clone ? w.ext_obs_clone : w.obs_clone.data(), sizeof(int) * n_obs);
+    std::memcpy(h + o_oz, w.ext_obs_z ? w.ext_obs_z : w.obs_z.data(), sizeof(double) * 2 * n_obs);
+  }
   if (!w.tiles.empty()) std::memcpy(h + o_t, w.tiles.data(), sizeof(Tile) * w.tiles.size());
   std::memcpy(h + o_f, w.fw.data(), sizeof(FilterWork) * B_);
   if (!w.small_list.empty()) std::memcpy(h + o_s, w.small_list.data(), sizeof(int) * w.small_list.size());
@@ -334,9 +343,22 @@ void Batch::stage_phase(PhaseWork& w) {
   w.d_extra = (const int*)(d + o_x);
 }
 
+UpdArgs Batch::upd_args(const FilterWork* dFw) const {
+  UpdArgs ua{};
+  ua.fw = dFw; ua.n_filters = B_;
+  ua.P = dP_; ua.p_stride = (size_t)ldp_ * ldp_; ua.ldp = ldp_;
+  ua.Rm = dR_; ua.rthin = dRthin_; ua.r_stride = (size_t)(6 * Ncap_ + 1) * ldr_; ua.ldr = ldr_;
+  ua.T = dT_; ua.S = dS_; ua.t_stride = (size_t)(6 * Ncap_) * ldt_; ua.ldt = ldt_;
+  ua.yv = dYv_;
+  ua.imu = dImu_; ua.clones = dClones_; ua.clone_stride = (size_t)Ncap_ * CL_STRIDE;
+  ua.dx = dDx_; ua.lddx = ldp_;
+  ua.flags = flags_; ua.sigma2 = p_.feature_observation_noise;
+  return ua;
+}
+
 // Kernel chain of one phase on already staged work lists: triangulate -> Jacobian/nullspace/gate
 // -> QR compression -> EKF update; optionally queues the D2H copy of the per-candidate results.
-void Batch::launch_phase(PhaseWork& w, bool download) {
+void Batch::launch_phase(PhaseWork& w, bool download, bool prior_in_flight) {
   const int nC = (int)w.cands.size();
   const Cand* dC = w.dC; const int* dOc = w.dOc; const double* dOz = w.dOz;
   const Tile* dTiles = w.dTiles; const FilterWork* dFw = w.dFw;
@@ -346,7 +368,7 @@ void Batch::launch_phase(PhaseWork& w, bool download) {
   if (profiling_) CK(cudaEventRecord(e[0], stream_));
   const bool do_update = w.any_active && !skip_update_;
   const bool use_qr = compress_qr_;
-  if (do_update && !use_qr) CK(cudaEventRecord(ev_fork_, stream_));
+  if (do_update && !use_qr && !prior_in_flight) CK(cudaEventRecord(ev_fork_, stream_));
   if (want_iters_ && (size_t)nC > iters_cap_) {
     if (dIters_) cudaFree(dIters_);
     if (dCost_) cudaFree(dCost_);
@@ -354,10 +376,10 @@ void Batch::launch_phase(PhaseWork& w, bool download) {
     CK(cudaMalloc(&dIters_, iters_cap_ * 2 * sizeof(int)));
     CK(cudaMalloc(&dCost_, iters_cap_ * sizeof(double)));
   }
-  if (want_raw_ && w.obs_clone.size() > raw_cap_) {
+  if (want_raw_ && w.n_obs() > raw_cap_) {
     for (double** p : {&dRawHx_, &dRawHe_, &dRawHf_, &dRawR_})
       if (*p) cudaFree(*p);
-    raw_cap_ = w.obs_clone.size() * 2 + 64;
+    raw_cap_ = w.n_obs() * 2 + 64;
     CK(cudaMalloc(&dRawHx_, raw_cap_ * 12 * sizeof(double)));
     CK(cudaMalloc(&dRawHe_, raw_cap_ * 12 * sizeof(double)));
     CK(cudaMalloc(&dRawHf_, raw_cap_ * 6 * sizeof(double)));
@@ -405,15 +427,7 @@ void Batch::launch_phase(PhaseWork& w, bool download) {
     qa.Rm = dR_; qa.rthin = dRthin_; qa.r_stride = (size_t)(6 * Ncap_ + 1) * ldr_; qa.ldr = ldr_;
     qa.front_scratch = dFront_; qa.front_stride = front_stride_;
     qa.err = dErr_;
-    UpdArgs ua{};
-    ua.fw = dFw; ua.n_filters = B_;
-    ua.P = dP_; ua.p_stride = (size_t)ldp_ * ldp_; ua.ldp = ldp_;
-    ua.Rm = dR_; ua.rthin = dRthin_; ua.r_stride = qa.r_stride; ua.ldr = ldr_;
-    ua.T = dT_; ua.S = dS_; ua.t_stride = (size_t)(6 * Ncap_) * ldt_; ua.ldt = ldt_;
-    ua.yv = dYv_;
-    ua.imu = dImu_; ua.clones = dClones_; ua.clone_stride = (size_t)Ncap_ * CL_STRIDE;
-    ua.dx = dDx_; ua.lddx = ldp_;
-    ua.flags = flags_; ua.sigma2 = p_.feature_observation_noise;
+    UpdArgs ua = upd_args(dFw);
     if (use_qr) {
       launch_qr(qa, w.tile_smem_doubles, w.wmax_blk, 6 * w.maxN, stream_, &nl, profiling_ ? e[3] : nullptr);
       if (profiling_) CK(cudaEventRecord(e[4], stream_));
@@ -428,7 +442,8 @@ void Batch::launch_phase(PhaseWork& w, bool download) {
       ib.kc = SYRK_KC; ib.max_chunks = chunks; ib.max_pairs = pairs;
       ib.tile_rows = dTileRows_; ib.filter_rows = dFilterRows_;
       launch_info_update(qa, ua, ib, (int)w.tiles.size(), w.max_tile_rows, w.wmax_blk, w.maxN, max_arows, stream_,
-                         stream2_, ev_fork_, ev_join_, profiling_ ? e[3] : nullptr, profiling_ ? e[4] : nullptr, &nl);
+                         stream2_, ev_fork_, ev_join_, profiling_ ? e[3] : nullptr, profiling_ ? e[4] : nullptr, &nl,
+                         prior_in_flight);
     }
     if (profiling_) CK(cudaEventRecord(e[5], stream_));
   }
@@ -664,7 +679,7 @@ int Batch::process(const double* t_img, const OrcvioFeature* feats, const int* f
     const size_t o_o = blob_.reserve(sizeof(int) * (B_ + 1));
     const size_t o_d = blob_.reserve(sizeof(int) * B_);
     const size_t o_n = blob_.reserve(sizeof(int) * B_);
-    char* h = blob_.host.data();
+    char* h = blob_.pinned;
     if (!samples.empty()) std::memcpy(h + o_s, samples.data(), sizeof(PropSample) * samples.size());
     std::memcpy(h + o_o, samp_off.data(), sizeof(int) * (B_ + 1));
     std::memcpy(h + o_d, Dvec.data(), sizeof(int) * B_);
@@ -704,7 +719,7 @@ int Batch::process(const double* t_img, const OrcvioFeature* feats, const int* f
       o_zm = blob_.reserve(sizeof(int) * B_);
       o_zn = blob_.reserve(sizeof(int) * B_);
       o_zc = blob_.reserve(sizeof(double) * B_);
-      h = blob_.host.data();
+      h = blob_.pinned;
       std::memcpy(h + o_zm, zmode.data(), sizeof(int) * B_);
       std::memcpy(h + o_zn, zN.data(), sizeof(int) * B_);
       std::memcpy(h + o_zc, zchk.data(), sizeof(double) * B_);
@@ -1148,8 +1163,7 @@ void Batch::override_noise(double sigma2, double chi2_p) {
 struct Batch::SnapState {
   PhaseWork w;
   std::vector<int> order;          // candidate order after sorting -> caller's feature index
-  std::vector<CandBuild> cb;
-  std::vector<CandInfo> info;
+  std::vector<int> sblk, eblk;     // first / last clone block per feature
   int N = 0, D = 0, n_feat = 0, nobs_total = 0;
   bool has_positions = false;
   double *dP0 = nullptr, *dCl0 = nullptr, *dIm0 = nullptr, *dPos0 = nullptr;   // pristine window
@@ -1158,7 +1172,13 @@ struct Batch::SnapState {
   double *hP0 = nullptr, *hCl0 = nullptr, *hIm0 = nullptr;                      // pinned staging
   double* hOut = nullptr;          // pinned download buffer (P, dx, clones)
   size_t hout_cap = 0;
+  FilterWork* hFw = nullptr; FilterWork* dFw = nullptr;   // (N, D) record for the early prior launch
+  int* hErr = nullptr;
+  bool prior_early = false;
   ~SnapState() {
+    cudaFree(dFw);
+    if (hFw) cudaFreeHost(hFw);
+    if (hErr) cudaFreeHost(hErr);
     cudaFree(dP0); cudaFree(dCl0); cudaFree(dIm0); cudaFree(dPos0); cudaFree(dGen0);
     if (hP0) cudaFreeHost(hP0);
     if (hCl0) cudaFreeHost(hCl0);
@@ -1184,6 +1204,9 @@ int Batch::snapshot_prepare(const SnapshotIO& io) {
     CK(cudaMallocHost(&S.hIm0, IM_STRIDE * sizeof(double)));
     S.hout_cap = (size_t)ldp_ * ldp_ + ldp_ + (size_t)Ncap_ * CL_STRIDE + (size_t)(6 * Ncap_ + 2) * ldr_;
     CK(cudaMallocHost(&S.hOut, S.hout_cap * sizeof(double)));
+    CK(cudaMallocHost(&S.hFw, sizeof(FilterWork)));
+    CK(cudaMalloc(&S.dFw, sizeof(FilterWork)));
+    CK(cudaMallocHost(&S.hErr, sizeof(int)));
   }
   SnapState& S = *snap_;
   if (io.n_feat > Fcap_) {
@@ -1240,6 +1263,21 @@ int Batch::snapshot_prepare(const SnapshotIO& io) {
     std::memset(S.hP0, 0, (size_t)ldp_ * ldp_ * sizeof(double));
   }
   CK(cudaMemcpyAsync(S.dP0, S.hP0, (size_t)ldp_ * ldp_ * sizeof(double), cudaMemcpyHostToDevice, stream_));
+  S.prior_early = false;
+  if ((io.stages & 4) && !compress_qr_ && io.early_prior) {
+    // The prior factor needs only P: put P in place and start k_chol_prior on the second stream now, so it
+    // runs while the host is still building and uploading this frame's work lists.
+    S.hFw[0] = FilterWork{};
+    S.hFw[0].N = N; S.hFw[0].D = D; S.hFw[0].active = 1;
+    CK(cudaMemcpyAsync(S.dFw, S.hFw, sizeof(FilterWork), cudaMemcpyHostToDevice, stream_));
+    CK(cudaMemcpyAsync(dP_, S.dP0, (size_t)ldp_ * ldp_ * sizeof(double), cudaMemcpyDeviceToDevice, stream_));
+    CK(cudaEventRecord(ev_fork_, stream_));
+    InfoBufs ib{};
+    ib.Ls = dLs_;
+    launch_info_prior(upd_args(S.dFw), ib, N, stream2_, ev_fork_, ev_join_);
+    ++launches_;
+    S.prior_early = true;
+  }
   CK(cudaMemcpyAsync(S.dCl0, S.hCl0, (size_t)Ncap_ * CL_STRIDE * sizeof(double), cudaMemcpyHostToDevice, stream_));
   CK(cudaMemcpyAsync(S.dIm0, S.hIm0, IM_STRIDE * sizeof(double), cudaMemcpyHostToDevice, stream_));
   FilterHost& F = f_[0];
@@ -1247,7 +1285,7 @@ int Batch::snapshot_prepare(const SnapshotIO& io) {
   for (int c = 0; c < N; ++c) F.clones.push_back(CloneMeta{c, (double)c, 0.0});
 
   PhaseWork& w = S.w;
-  w = PhaseWork{};
+  w.reset();
   w.rows_cap = compress_qr_ ? 0 : AFORM_TILE_ROWS;
   w.fw.assign(B_, FilterWork{});
   w.cand_begin.assign(B_ + 1, 0);
@@ -1255,26 +1293,19 @@ int Batch::snapshot_prepare(const SnapshotIO& io) {
   fw.N = N; fw.D = D; fw.active = (io.stages & 4) ? 1 : 0;
   w.any_active = fw.active;
   w.maxN = N;
-  std::vector<CandBuild>& cb = S.cb;
-  cb.clear();
-  cb.reserve(io.n_feat);
-  // observations are referenced in place: copy the pools once
-  const int nobs_total = io.feat_off[io.n_feat];
+  // observations are referenced in place and copied once, straight into the pinned upload blob
+  const int nF = io.n_feat;
+  const int nobs_total = io.feat_off[nF];
   S.nobs_total = nobs_total;
-  w.obs_clone.assign(io.obs_clone, io.obs_clone + nobs_total);
-  w.obs_z.assign(io.obs_z, io.obs_z + 2 * (size_t)nobs_total);
-  for (int f = 0; f < io.n_feat; ++f) {
+  w.ext_obs_clone = io.obs_clone; w.ext_obs_z = io.obs_z; w.ext_nobs = (size_t)nobs_total;
+  // candidates sorted by first clone block, then feature index: a counting sort (what
+  // append_candidates' stable sort produces, without the comparison sort)
+  S.sblk.resize(nF);
+  S.eblk.resize(nF);
+  int bucket[ORCVIO_MAX_OBS + 2] = {0};
+  for (int f = 0; f < nF; ++f) {
     const int o0 = io.feat_off[f], m = io.feat_off[f + 1] - o0;
     if (m < 1 || m > ORCVIO_MAX_OBS) return ORCVIO_ERR_ARG;
-    CandBuild x{};
-    x.id = f;
-    x.kind = 0;
-    Cand& c = x.c;
-    c.slot = f;
-    c.gen = f + 1;
-    c.flags = CAND_FORCE_TRI;
-    c.tri_off = c.jac_off = o0;
-    c.tri_m = c.jac_m = m;
     int s = 1 << 30, e = -1;
     for (int k = 0; k < m; ++k) {
       const int ci = io.obs_clone[o0 + k];
@@ -1282,18 +1313,39 @@ int Batch::snapshot_prepare(const SnapshotIO& io) {
       s = std::min(s, ci);
       e = std::max(e, ci);
     }
-    c.s_blk = s; c.e_blk = e;
+    S.sblk[f] = s; S.eblk[f] = e;
+    ++bucket[s + 1];
+  }
+  for (int k = 1; k <= ORCVIO_MAX_OBS + 1; ++k) bucket[k] += bucket[k - 1];
+  S.order.resize(nF);
+  for (int f = 0; f < nF; ++f) S.order[bucket[S.sblk[f]]++] = f;
+  w.cands.resize(nF);
+  for (int pos = 0; pos < nF; ++pos) {
+    const int f = S.order[pos];
+    const int o0 = io.feat_off[f], m = io.feat_off[f + 1] - o0;
+    Cand& c = w.cands[pos];
+    c.filter = 0;
+    c.slot = f;
+    c.gen = f + 1;
+    c.flags = CAND_FORCE_TRI;
+    c.tri_off = c.jac_off = o0;
+    c.tri_m = c.jac_m = m;
+    c.s_blk = S.sblk[f]; c.e_blk = S.eblk[f];
     c.cm_first_clone = io.obs_clone[o0];
     c.cm_last_clone = io.obs_clone[o0 + m - 1];
     c.cm_zu = io.obs_z[2 * (size_t)o0];
     c.cm_zv = io.obs_z[2 * (size_t)o0 + 1];
-    cb.push_back(x);
+    const int r = std::max(2 * m - 3, 0), wb = c.e_blk - c.s_blk + 1;
+    c.row_off = (int)w.rows_total;
+    c.hblk_off = (int)w.hblk_total;
+    w.rows_total += (size_t)r;
+    w.hblk_total += (size_t)r * 6 * wb;
+    w.own_wmax_blk = std::max(w.own_wmax_blk, wb);
+    if (m <= 8) w.small_list.push_back(pos);
+    else w.large_list.push_back(pos);
   }
-  S.info.clear();
-  append_candidates(w, 0, cb, S.info);
-  const int nC = (int)w.cands.size();
-  S.order.resize(nC);
-  for (int c = 0; c < nC; ++c) S.order[c] = (int)S.info[c].id;
+  build_tiles(w, 0, 0, nF);
+  const int nC = nF;
 
   S.has_positions = io.positions_in != nullptr;
   if (S.has_positions) {
@@ -1329,7 +1381,10 @@ int Batch::snapshot_prepare(const SnapshotIO& io) {
 int Batch::snapshot_execute(bool download) {
   if (!snap_) return ORCVIO_ERR_ARG;
   SnapState& S = *snap_;
-  CK(cudaMemcpyAsync(dP_, S.dP0, (size_t)ldp_ * ldp_ * sizeof(double), cudaMemcpyDeviceToDevice, stream_));
+  const bool prior_in_flight = S.prior_early;      // P restored and k_chol_prior started by snapshot_prepare
+  S.prior_early = false;
+  if (!prior_in_flight)
+    CK(cudaMemcpyAsync(dP_, S.dP0, (size_t)ldp_ * ldp_ * sizeof(double), cudaMemcpyDeviceToDevice, stream_));
   CK(cudaMemcpyAsync(dClones_, S.dCl0, (size_t)Ncap_ * CL_STRIDE * sizeof(double), cudaMemcpyDeviceToDevice, stream_));
   CK(cudaMemcpyAsync(dImu_, S.dIm0, IM_STRIDE * sizeof(double), cudaMemcpyDeviceToDevice, stream_));
   if (S.has_positions) {
@@ -1338,7 +1393,7 @@ int Batch::snapshot_execute(bool download) {
   } else {
     CK(cudaMemsetAsync(dFgen_, 0xFF, (size_t)Fcap_ * sizeof(long long), stream_));
   }
-  launch_phase(S.w, download);
+  launch_phase(S.w, download, prior_in_flight);
   return ok_ ? ORCVIO_OK : ORCVIO_ERR_CUDA;
 }
 
@@ -1357,6 +1412,7 @@ int Batch::snapshot_fetch(const SnapshotIO& io) {
   if (io.clone_out) CK(cudaMemcpyAsync(hCl, dClones_, (size_t)N * CL_STRIDE * sizeof(double), cudaMemcpyDeviceToHost, stream_));
   if (io.R_thin) CK(cudaMemcpyAsync(hR, dR_, (size_t)n * ldr_ * sizeof(double), cudaMemcpyDeviceToHost, stream_));
   if (io.r_thin) CK(cudaMemcpyAsync(hR + (size_t)n * ldr_, dRthin_, n * sizeof(double), cudaMemcpyDeviceToHost, stream_));
+  CK(cudaMemcpyAsync(S.hErr, dErr_, sizeof(int), cudaMemcpyDeviceToHost, stream_));
   CK(cudaStreamSynchronize(stream_));
   if (io.status || io.gamma)
     for (int c = 0; c < nC; ++c) {
@@ -1398,9 +1454,7 @@ int Batch::snapshot_fetch(const SnapshotIO& io) {
       for (int k = 0; k < 9; ++k) io.clone_out[12 * (size_t)c + k] = hCl[(size_t)c * CL_STRIDE + CL_R + k];
       for (int k = 0; k < 3; ++k) io.clone_out[12 * (size_t)c + 9 + k] = hCl[(size_t)c * CL_STRIDE + CL_P + k];
     }
-  int herr = 0;
-  CK(cudaMemcpy(&herr, dErr_, sizeof(int), cudaMemcpyDeviceToHost));
-  if (herr) return ORCVIO_ERR_CAPACITY;
+  if (*S.hErr) return ORCVIO_ERR_CAPACITY;
   return ok_ ? ORCVIO_OK : ORCVIO_ERR_CUDA;
 }
 

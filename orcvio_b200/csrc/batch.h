@@ -4,6 +4,7 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include <cstring>
 #include <map>
 #include <memory>
 #include <string>
@@ -71,16 +72,26 @@ struct FilterHost {
 };
 
 struct Blob {                 // one pinned host blob + device twin, carved into sections
-  std::vector<char> host;
   char* dev = nullptr;
   size_t dev_cap = 0;
-  char* pinned = nullptr;
+  char* pinned = nullptr;     // sections are written in place: no pageable staging copy
   size_t pinned_cap = 0;
   size_t used = 0;
   size_t reserve(size_t bytes) {
     size_t off = (used + 255) & ~size_t(255);
+    const size_t old_used = used;
     used = off + bytes;
-    if (host.size() < used) host.resize(used * 2);
+    if (used > pinned_cap) {
+      char* np = nullptr;
+      const size_t ncap = used * 2 + 4096;
+      if (cudaMallocHost(&np, ncap) != cudaSuccess) { used = old_used; return 0; }
+      if (pinned) {
+        if (old_used) std::memcpy(np, pinned, old_used);
+        cudaFreeHost(pinned);
+      }
+      pinned = np;
+      pinned_cap = ncap;
+    }
     return off;
   }
   void reset() { used = 0; }
@@ -128,6 +139,7 @@ class Batch {
     const int* feat_off = nullptr; const int* obs_clone = nullptr; const double* obs_z = nullptr;
     int n_feat = 0;
     int stages = 0;                         // bit0 tri, bit1 jac+gate, bit2 qr+update
+    bool early_prior = false;               // start k_chol_prior as soon as P is uploaded (end-to-end call)
     int repeat = 1;
     double* P_out = nullptr; double* delta_x = nullptr; int* status = nullptr; double* gamma = nullptr;
     double* positions = nullptr; double* R_thin = nullptr; double* r_thin = nullptr;
@@ -218,7 +230,8 @@ class Batch {
   void ensure_scratch(size_t n_cand, size_t hblk, size_t rblk, size_t tileout);
   void run_phase(PhaseWork& w, int phase);
   void stage_phase(PhaseWork& w);
-  void launch_phase(PhaseWork& w, bool download);
+  void launch_phase(PhaseWork& w, bool download, bool prior_in_flight = false);
+  UpdArgs upd_args(const FilterWork* dFw) const;
   struct SnapState;
   struct SnapDeleter { void operator()(SnapState* p) const; };
   std::unique_ptr<SnapState, SnapDeleter> snap_;

@@ -1,6 +1,7 @@
 // extern "C" boundary: see include/orcvio_b200.h.
 #include <cstdio>
 #include <cstring>
+#include <chrono>
 #include <memory>
 #include <string>
 #include <vector>
@@ -328,6 +329,7 @@ struct orcvio_frame {
   std::unique_ptr<Batch> b;
   cudaEvent_t e0 = nullptr, e1 = nullptr;
   bool loaded = false;
+  float host_us[4] = {0, 0, 0, 0};     // last orcvio_frame_update: prepare, launch, wait+fetch, total (wall)
 };
 
 orcvio_frame* orcvio_frame_create(int n_clones_cap, int flags, double noise_feature_var, double chi2_p,
@@ -371,12 +373,29 @@ int orcvio_frame_update(orcvio_frame* f, const double* clone_R, const double* cl
   if (!f || !feat_off || !obs_clone || !obs_z || !clone_R || !clone_p) return ORCVIO_ERR_ARG;
   Batch::SnapshotIO io = frame_io(clone_R, clone_p, n_clones, R_b2c, t_c_b, P_in, feat_off, obs_clone, obs_z, n_feat);
   io.P_out = P_out; io.delta_x = delta_x; io.status = status; io.gamma = gamma; io.clone_out = clone_out;
+  io.early_prior = true;
+  using clk = std::chrono::steady_clock;
+  auto us = [](clk::time_point a, clk::time_point b) {
+    return (float)std::chrono::duration<double, std::micro>(b - a).count();
+  };
+  const auto t0 = clk::now();
   int rc = f->b->snapshot_prepare(io);
   if (rc != ORCVIO_OK) return rc;
   f->loaded = true;
+  const auto t1 = clk::now();
   rc = f->b->snapshot_execute(true);
   if (rc != ORCVIO_OK) return rc;
-  return f->b->snapshot_fetch(io);
+  const auto t2 = clk::now();
+  rc = f->b->snapshot_fetch(io);
+  const auto t3 = clk::now();
+  f->host_us[0] = us(t0, t1); f->host_us[1] = us(t1, t2); f->host_us[2] = us(t2, t3); f->host_us[3] = us(t0, t3);
+  return rc;
+}
+
+int orcvio_frame_host_times(orcvio_frame* f, float* us4) {
+  if (!f || !us4) return ORCVIO_ERR_ARG;
+  for (int k = 0; k < 4; ++k) us4[k] = f->host_us[k];
+  return ORCVIO_OK;
 }
 
 int orcvio_frame_load(orcvio_frame* f, const double* clone_R, const double* clone_p, int n_clones,

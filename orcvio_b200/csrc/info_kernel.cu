@@ -492,19 +492,28 @@ void launch_info_dense_apply(const UpdArgs& u, const InfoBufs& ib, int N, cudaSt
   check_launch("k_pinfo");
 }
 
+// Prior factor on the second stream: it depends only on P, so it overlaps triangulation / Jacobians
+// (and, in the end-to-end call, the host's work-list build).  `fork` was recorded on the main stream
+// once P was in place; `join` is what the main stream waits for before k_aform.
+void launch_info_prior(const UpdArgs& u, const InfoBufs& ib, int max_N, cudaStream_t s2, cudaEvent_t fork,
+                       cudaEvent_t join) {
+  const int Dmax = ORCVIO_LEG + 6 * max_N;
+  info_attrs();
+  cudaStreamWaitEvent(s2, fork, 0);
+  const size_t sm_prior = (chol_smem_doubles(Dmax, 0) + (size_t)Dmax + 2) * sizeof(double);
+  k_chol_prior<<<u.n_filters, CHOL_THREADS, sm_prior, s2>>>(u, ib.Ls);
+  check_launch("k_chol_prior");
+  cudaEventRecord(join, s2);
+}
+
 void launch_info_update(const QrArgs& q, const UpdArgs& u, const InfoBufs& ib, int n_tiles, int max_tile_rows,
                         int max_w_blk, int max_N, int max_arows, cudaStream_t s, cudaStream_t s2,
-                        cudaEvent_t fork, cudaEvent_t join, cudaEvent_t mid1, cudaEvent_t mid2, int* launches) {
+                        cudaEvent_t fork, cudaEvent_t join, cudaEvent_t mid1, cudaEvent_t mid2, int* launches,
+                        bool prior_in_flight) {
   const int nmax = 6 * max_N, Dmax = ORCVIO_LEG + nmax;
   const int B = u.n_filters;
   info_attrs();
-  // prior factor on the second stream: depends only on P, overlaps triangulation / Jacobians
-  // (the caller recorded `fork` on s before launching them)
-  cudaStreamWaitEvent(s2, fork, 0);
-  const size_t sm_prior = (chol_smem_doubles(Dmax, 0) + (size_t)Dmax + 2) * sizeof(double);
-  k_chol_prior<<<B, CHOL_THREADS, sm_prior, s2>>>(u, ib.Ls);
-  check_launch("k_chol_prior");
-  cudaEventRecord(join, s2);
+  if (!prior_in_flight) launch_info_prior(u, ib, max_N, s2, fork, join);
   cudaStreamWaitEvent(s, join, 0);
   const int lda = u.ldr;
   if (n_tiles > 0) {
@@ -540,7 +549,7 @@ void launch_info_update(const QrArgs& q, const UpdArgs& u, const InfoBufs& ib, i
   dim3 g5((Dmax + PT - 1) / PT, (Dmax + PT - 1) / PT, B);
   k_pinfo<<<g5, 256, (size_t)2 * nmax * PT * sizeof(double), s>>>(u, ib.Ls, ib.filter_rows);
   check_launch("k_pinfo");
-  if (launches) *launches += 6 + (n_tiles > 0 ? 1 : 0);
+  if (launches) *launches += 5 + (prior_in_flight ? 0 : 1) + (n_tiles > 0 ? 1 : 0);
 }
 
 }  // namespace ob

@@ -179,7 +179,10 @@ void launch_update(const UpdArgs& a, int max_N, cudaStream_t s, int* launches);
 void launch_update_tail(const UpdArgs& a, int max_N, cudaStream_t s);   // k_trsm + k_apply_dx
 void launch_info_update(const QrArgs& q, const UpdArgs& u, const InfoBufs& ib, int n_tiles, int max_tile_rows,
                         int max_w_blk, int max_N, int max_arows, cudaStream_t s, cudaStream_t s2,
-                        cudaEvent_t fork, cudaEvent_t join, cudaEvent_t mid1, cudaEvent_t mid2, int* launches);
+                        cudaEvent_t fork, cudaEvent_t join, cudaEvent_t mid1, cudaEvent_t mid2, int* launches,
+                        bool prior_in_flight = false);
+void launch_info_prior(const UpdArgs& u, const InfoBufs& ib, int max_N, cudaStream_t s2, cudaEvent_t fork,
+                       cudaEvent_t join);
 void launch_info_dense_factor(const UpdArgs& u, const InfoBufs& ib, const double* Hp, int ldh, int rows, int N,
                               cudaStream_t s);
 void launch_info_dense_apply(const UpdArgs& u, const InfoBufs& ib, int N, cudaStream_t s);

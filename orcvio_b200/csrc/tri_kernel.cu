@@ -1,4 +1,4 @@
-// Stage 1 -- per-feature triangulation kernel (one thread per candidate feature).
+// Stage 1 -- per-feature triangulation kernel (one warp per candidate feature).
 //
 // Computes what Feature::checkMotion + Feature::initializePosition[_AssignAnchor] +
 // Feature::triangulate_position compute in the reference
@@ -11,9 +11,11 @@
 // --fmad=false and every expression is written in one fixed association order; the CPU
 // oracle (oracle/feature.py, oracle/cpu_ref.cpp) uses the same order and agrees bit for bit.
 //
-// Why thread-per-feature: the sums over observations must be accumulated in observation
-// order to keep that bit-level agreement, the working set of one feature (<= 32 relative
-// poses) is tiny, and a frame offers hundreds to thousands of independent features.
+// Parallelisation: one warp per feature, lane k owns observation k (relative pose, Jacobian row,
+// cost term); the per-observation terms are summed in observation order (through shared memory /
+// shuffles) so that every rounding step matches the sequential oracle bit for bit, and one LM
+// iteration costs the latency of ONE observation instead of m.  The kernel is bound by the serial
+// latency of the slowest feature's LM chain (FP64 divide / sqrt), not by HBM or FP64 throughput.
 #include <cstdio>
 #include "kernels.h"
 
@@ -92,43 +94,64 @@ __device__ __forceinline__ double tri_cost(const double* R, const double* t, con
   return d0 * d0 + d1 * d1;
 }
 
+// Relative pose of observation clone `c` w.r.t. the last camera (Rl, tl): feature.hpp:600-612.
+__device__ __forceinline__ void rel_pose(const double* c, const double* Rl, const double* tl, double* R, double* t) {
+  const double* Ri = c + CL_RC;
+  const double* ti = c + CL_PC;
+  double tinv[3], rt[3];
+  m3_Tvec(Ri, ti, tinv);
+  m3_Tmul(Ri, Rl, R);
+  m3_Tvec(Ri, tl, rt);
+  t[0] = rt[0] + (-tinv[0]);
+  t[1] = rt[1] + (-tinv[1]);
+  t[2] = rt[2] + (-tinv[2]);
+}
+
+// sum_{k<m} v_k accumulated in observation order (total = total + v_k), v_k held by lane k
+__device__ __forceinline__ double ordered_sum(double v, int m) {
+  double s = 0.0;
+  for (int k = 0; k < m; ++k) s = s + __shfl_sync(0xffffffffu, v, k);
+  return s;
+}
+
+constexpr int TRI_SM_STRIDE = 13;   // 12 contributions per observation, padded: conflict-free both ways
+
+// One WARP per feature: lane k owns observation k (m <= 32), i.e. its relative pose, its row of the
+// Jacobian and its cost term; the per-observation terms are then added in observation order so that
+// every rounding step matches the sequential oracle.  The 3 x 3 solve and the LM bookkeeping run
+// redundantly on all lanes (warp-uniform control flow).  `sm`: 32 * TRI_SM_STRIDE doubles per warp.
 // Returns status bit0 = valid.  pos_io: previous world position when is_init, result on exit
 // (written only when valid, like the reference's `position = ...` under is_valid_solution).
 __device__ int triangulate_feature(const double* __restrict__ clones, int m,
                                    const int* __restrict__ oc, const double* __restrict__ oz,
                                    bool is_init, double* pos_io, const TriCfg& cfg, int* iters,
-                                   double* cost_out) {
-  double relR[ORCVIO_MAX_OBS * 9];
-  double relt[ORCVIO_MAX_OBS * 3];
+                                   double* cost_out, double* __restrict__ sm) {
+  const int lane = threadIdx.x & 31;
+  const bool act = lane < m;
   const double* cl = clones + (size_t)oc[m - 1] * CL_STRIDE;
   double Rl[9], tl[3];
   for (int i = 0; i < 9; ++i) Rl[i] = cl[CL_RC + i];
   for (int i = 0; i < 3; ++i) tl[i] = cl[CL_PC + i];
-  for (int k = 0; k < m; ++k) {
-    const double* c = clones + (size_t)oc[k] * CL_STRIDE;
-    const double* Ri = c + CL_RC;
-    const double* ti = c + CL_PC;
-    double tinv[3], rt[3];
-    m3_Tvec(Ri, ti, tinv);
-    m3_Tmul(Ri, Rl, relR + 9 * k);
-    m3_Tvec(Ri, tl, rt);
-    relt[3 * k + 0] = rt[0] + (-tinv[0]);
-    relt[3 * k + 1] = rt[1] + (-tinv[1]);
-    relt[3 * k + 2] = rt[2] + (-tinv[2]);
+  double R[9], t[3], zu = 0.0, zv = 0.0;
+  {
+    const int k = act ? lane : 0;
+    rel_pose(clones + (size_t)oc[k] * CL_STRIDE, Rl, tl, R, t);
+    zu = oz[2 * k];
+    zv = oz[2 * k + 1];
   }
   double init[3];
   if (!is_init) {
     // generateInitialGuess(rel pose 0, z_last, z_first), feature.hpp:331-351
-    const double* R = relR;
-    const double* t = relt;
+    double R0[9], t0[3];
+    rel_pose(clones + (size_t)oc[0] * CL_STRIDE, Rl, tl, R0, t0);
     double z1u = oz[2 * (m - 1)], z1v = oz[2 * (m - 1) + 1];
     double z2u = oz[0], z2v = oz[1];
     double mv[3], zz[3] = {z1u, z1v, 1.0};
-    m3_vec(R, zz, mv);
+    m3_vec(R0, zz, mv);
     double A0 = mv[0] - z2u * mv[2];
     double A1 = mv[1] - z2v * mv[2];
-    double b0 = z2u * t[2] - t[0];
-    double b1 = z2v * t[2] - t[1];
+    double b0 = z2u * t0[2] - t0[0];
+    double b1 = z2v * t0[2] - t0[1];
     double inv = 1.0 / (A0 * A0 + A1 * A1);
     double depth = (inv * A0) * b0 + (inv * A1) * b1;
     init[0] = z1u * depth;
@@ -147,16 +170,11 @@ __device__ int triangulate_feature(const double* __restrict__ clones, int m,
   int inner = 0, outer = 0, n_inner_total = 0;
   bool reduced = false;
   double delta_norm = 0.0;
-  double total_cost = 0.0;
-  for (int k = 0; k < m; ++k)
-    total_cost = total_cost + tri_cost(relR + 9 * k, relt + 3 * k, sol, oz[2 * k], oz[2 * k + 1]);
+  double total_cost = ordered_sum(tri_cost(R, t, sol, zu, zv), m);
 
   while (true) {
-    double A[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
-    double b[3] = {0, 0, 0};
-    for (int k = 0; k < m; ++k) {
-      const double* R = relR + 9 * k;
-      const double* t = relt + 3 * k;
+    // this lane's observation: 9 + 3 contributions to A and b
+    {
       double h[3];
       tri_h(R, t, sol, h);
       double W[3][3] = {{R[0], R[1], t[0]}, {R[3], R[4], t[1]}, {R[6], R[7], t[2]}};
@@ -168,25 +186,33 @@ __device__ int triangulate_feature(const double* __restrict__ clones, int m,
         J[0][j] = ih3 * W[0][j] - c0 * W[2][j];
         J[1][j] = ih3 * W[1][j] - c1 * W[2][j];
       }
-      double r0 = h[0] / h[2] - oz[2 * k];
-      double r1 = h[1] / h[2] - oz[2 * k + 1];
+      double r0 = h[0] / h[2] - zu;
+      double r1 = h[1] / h[2] - zv;
       double e = sqrt(r0 * r0 + r1 * r1);
+      double* my = sm + lane * TRI_SM_STRIDE;
       if (e <= cfg.huber_epsilon) {
         for (int a_ = 0; a_ < 3; ++a_) {
-          for (int c_ = 0; c_ < 3; ++c_)
-            A[3 * a_ + c_] = A[3 * a_ + c_] + (J[0][a_] * J[0][c_] + J[1][a_] * J[1][c_]);
-          b[a_] = b[a_] + (J[0][a_] * r0 + J[1][a_] * r1);
+          for (int c_ = 0; c_ < 3; ++c_) my[3 * a_ + c_] = (J[0][a_] * J[0][c_] + J[1][a_] * J[1][c_]);
+          my[9 + a_] = (J[0][a_] * r0 + J[1][a_] * r1);
         }
       } else {
         double w = sqrt(2.0 * cfg.huber_epsilon / e);
         double w2 = w * w;
         for (int a_ = 0; a_ < 3; ++a_) {
           for (int c_ = 0; c_ < 3; ++c_)
-            A[3 * a_ + c_] = A[3 * a_ + c_] + ((w2 * J[0][a_]) * J[0][c_] + (w2 * J[1][a_]) * J[1][c_]);
-          b[a_] = b[a_] + ((w2 * J[0][a_]) * r0 + (w2 * J[1][a_]) * r1);
+            my[3 * a_ + c_] = ((w2 * J[0][a_]) * J[0][c_] + (w2 * J[1][a_]) * J[1][c_]);
+          my[9 + a_] = ((w2 * J[0][a_]) * r0 + (w2 * J[1][a_]) * r1);
         }
       }
     }
+    __syncwarp();
+    double acc = 0.0;           // lane j < 12 sums entry j over the observations, in order
+    if (lane < 12)
+      for (int k = 0; k < m; ++k) acc = acc + sm[k * TRI_SM_STRIDE + lane];
+    __syncwarp();
+    double A[9], b[3];
+    for (int i = 0; i < 9; ++i) A[i] = __shfl_sync(0xffffffffu, acc, i);
+    for (int i = 0; i < 3; ++i) b[i] = __shfl_sync(0xffffffffu, acc, 9 + i);
     while (true) {
       double M[9];
       for (int i = 0; i < 9; ++i) M[i] = A[i];
@@ -197,9 +223,7 @@ __device__ int triangulate_feature(const double* __restrict__ clones, int m,
       ldlt3_solve(M, b, delta);
       double ns[3] = {sol[0] - delta[0], sol[1] - delta[1], sol[2] - delta[2]};
       delta_norm = sqrt((delta[0] * delta[0] + delta[1] * delta[1]) + delta[2] * delta[2]);
-      double new_cost = 0.0;
-      for (int k = 0; k < m; ++k)
-        new_cost = new_cost + tri_cost(relR + 9 * k, relt + 3 * k, ns, oz[2 * k], oz[2 * k + 1]);
+      double new_cost = ordered_sum(tri_cost(R, t, ns, zu, zv), m);
       ++n_inner_total;
       if (new_cost < total_cost) {
         reduced = true;
@@ -221,10 +245,9 @@ __device__ int triangulate_feature(const double* __restrict__ clones, int m,
   }
   double fin[3] = {sol[0] / sol[2], sol[1] / sol[2], 1.0 / sol[2]};
   int valid = 1;
-  for (int k = 0; k < m; ++k) {
-    const double* R = relR + 9 * k;
-    double pz = ((R[6] * fin[0] + R[7] * fin[1]) + R[8] * fin[2]) + relt[3 * k + 2];
-    if (pz <= 0) { valid = 0; break; }
+  {
+    double pz = ((R[6] * fin[0] + R[7] * fin[1]) + R[8] * fin[2]) + t[2];
+    if (__any_sync(0xffffffffu, act && pz <= 0)) valid = 0;
   }
   double normalized_cost = total_cost / (double)(2 * m * m);
   double d0 = fin[0] - init[0], d1 = fin[1] - init[1], d2 = fin[2] - init[2];
@@ -259,10 +282,14 @@ __device__ __forceinline__ bool check_motion(const double* clones, int first_clo
   return sqrt((o0 * o0 + o1 * o1) + o2 * o2) > thr;
 }
 
-// One thread per candidate.  Candidates of all filters of the batch are concatenated;
+// One warp per candidate.  Candidates of all filters of the batch are concatenated;
 // cand.filter selects the clone array / feature-position table of its filter.
-__global__ void __launch_bounds__(128) k_triangulate(TriArgs a) {
-  int c = blockIdx.x * blockDim.x + threadIdx.x;
+constexpr int TRI_WARPS = 4;
+
+__global__ void __launch_bounds__(32 * TRI_WARPS) k_triangulate(TriArgs a) {
+  __shared__ double sm_all[TRI_WARPS][32 * TRI_SM_STRIDE];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int c = blockIdx.x * TRI_WARPS + warp;
   if (c >= a.n_cand) return;
   const Cand cd = a.cand[c];
   const double* clones = a.clones + (size_t)cd.filter * a.clone_stride;
@@ -272,6 +299,7 @@ __global__ void __launch_bounds__(128) k_triangulate(TriArgs a) {
   int iters[2] = {0, 0};
   double cost = 0.0;
   bool is_init = (*fgen == cd.gen);   // initialised earlier in this track's life
+  __syncwarp();                       // every lane has read fgen before lane 0 may overwrite it
   if (is_init && !(cd.flags & CAND_FORCE_TRI)) {
     status = ST_TRI_VALID;
   } else {
@@ -284,17 +312,22 @@ __global__ void __launch_bounds__(128) k_triangulate(TriArgs a) {
                                a.cfg.translation_threshold);
     if (motion && m >= 1) {
       double pos[3] = {fp[0], fp[1], fp[2]};
-      int v = triangulate_feature(clones, m, oc, oz, is_init, pos, a.cfg, iters, &cost);
+      __syncwarp();
+      int v = triangulate_feature(clones, m, oc, oz, is_init, pos, a.cfg, iters, &cost, sm_all[warp]);
       if (v) {
-        fp[0] = pos[0]; fp[1] = pos[1]; fp[2] = pos[2];
-        *fgen = cd.gen;
+        if (lane == 0) {
+          fp[0] = pos[0]; fp[1] = pos[1]; fp[2] = pos[2];
+          *fgen = cd.gen;
+        }
         status = ST_TRI_VALID;
       }
     }
   }
-  a.status[c] = status;
-  if (a.iters) { a.iters[2 * c] = iters[0]; a.iters[2 * c + 1] = iters[1]; }
-  if (a.cost) a.cost[c] = cost;
+  if (lane == 0) {
+    a.status[c] = status;
+    if (a.iters) { a.iters[2 * c] = iters[0]; a.iters[2 * c + 1] = iters[1]; }
+    if (a.cost) a.cost[c] = cost;
+  }
 }
 
 static int g_launch_errors = 0;
@@ -309,9 +342,8 @@ int launch_error_count() { return g_launch_errors; }
 
 void launch_triangulate(const TriArgs& a, cudaStream_t s) {
   if (a.n_cand <= 0) return;
-  int threads = 128;
-  int blocks = (a.n_cand + threads - 1) / threads;
-  k_triangulate<<<blocks, threads, 0, s>>>(a);
+  int blocks = (a.n_cand + TRI_WARPS - 1) / TRI_WARPS;
+  k_triangulate<<<blocks, 32 * TRI_WARPS, 0, s>>>(a);
   check_launch("k_triangulate");
 }
 
