@@ -41,6 +41,9 @@ UNIT = "features/s"
 N_CLONES, N_FEATURES, MAX_TRACK = 30, 4096, 6
 NOISE_VAR = 1.6e-5          # (2 x 0.002)^2: synthetic pixel noise of the KITTI-shaped generator
 TRI = dict(cost_threshold=1e-3, init_final_dist_threshold=100.0)
+# dram__bytes_read.sum + dram__bytes_write.sum of one k_syrk launch from the committed `ncu --set full`
+# capture (profiles/); None until a capture of the current kernel exists
+SYRK_NCU_TRAFFIC = None
 WORKLOAD = f"stress frame: {N_CLONES}-clone window, {N_FEATURES} features, max_track_len {MAX_TRACK} (SURVEY 8d C4a)"
 
 
@@ -70,6 +73,17 @@ def algorithmic_bytes(snap, status, stage):
     if stage == "update":
         return int(24 * D * D)
     return 0
+
+
+def syrk_flops(snap, status):
+    """Algorithmic flops of W = s^2 I + A^T A (k_syrk): one triangle of the (n+1) x (n+1) Gram
+    matrix of the M gated rows of A = [H' L | r'], 2 flops per multiply-add  ->  M (n+1)(n+2).
+    (The reference spends 2 M De^2 - 2/3 De^3 on the Householder QR of the same rows)"""
+    m = np.diff(np.asarray(snap["feat_off"])).astype(np.int64)
+    passed = (np.asarray(status) & 2) != 0
+    M = int((2 * m - 3)[passed].sum())
+    n1 = 6 * int(snap["n_clones"]) + 1
+    return M * n1 * (n1 + 1), M
 
 
 class ClockSampler:
@@ -131,7 +145,7 @@ def reference_arm(args, rank, world):
     n_feat = args.ref_features
     # warm-up + timed steps, each step = one bounded sample (one frame per thread)
     for _ in range(max(args.warmup, 0)):
-        run_cpu_reference(cores, min(n_feat, 256), 1)
+        run_cpu_reference(cores, min(n_feat, 512), 1)
     feats, secs = 0, 0.0
     for k in range(args.steps):
         f, s, kind = run_cpu_reference(cores, n_feat, 1, seed0=100 * k)
@@ -152,10 +166,11 @@ def reference_arm(args, rank, world):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--ref-features", type=int, default=1024, help="features per frame of the CPU sample")
+    ap.add_argument("--ref-features", type=int, default=N_FEATURES, help="features per frame of the CPU sample")
+    ap.add_argument("--ref-repeats", type=int, default=6, help="frames per host thread in the cpu_baseline leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-flush", action="store_true", help="skip the L2 flush (profiling runs only)")
     args = ap.parse_args()
@@ -247,10 +262,18 @@ def main():
             pass
         peak = float(peaks.get("hbm_gbs", 6650.0))
         peak_src = "measured (MEASURED_PEAKS.json hbm_gbs, burst copy)" if peaks else "fallback 6650 GB/s"
-        kern = {k: v for k, v in stages.items() if k != "total"}
-        dom = max(kern, key=kern.get)
-        abytes = algorithmic_bytes(snap, out["status"], dom)
-        achieved = abytes / (kern[dom] * 1e-6) / 1e9
+        # stage split of the whitened-form path (api.Frame.STAGES keeps the generic names):
+        #   qr_tiles = k_aform (+ wait for k_chol_prior), qr_chain = k_syrk + k_chol_w_solve, update = k_pinfo
+        kt = fr.kernel_times()
+        stage_named = dict(tri=stages["tri"], jac_gate=stages["jac_gate"], aform_incl_prior_wait=stages["qr_tiles"],
+                           syrk=kt["syrk"], chol_w_solve=stages["qr_chain"] - kt["syrk"], pinfo_increment=stages["update"],
+                           chol_prior_second_stream=kt["chol_prior"], total=stages["total"])
+        # roofline kernel: k_syrk, the one kernel of the chain with GEMM-sized work (the FP64 tensor-core
+        # compression GEMM of the north star); the other kernels are latency chains
+        dfma_peak, dmma_peak = api.fp64_peak()
+        flops, M_rows = syrk_flops(snap, out["status"])
+        achieved = flops / (kt["syrk"] * 1e-6) / 1e12
+        jac_bytes = algorithmic_bytes(snap, out["status"], "jac_gate")
         h2d = sum(inp[k].nbytes for k in ("clone_R", "clone_p", "Rbc", "tcb", "P", "feat_off", "obs_clone", "obs_z"))
         d2h = sum(out[k].nbytes for k in ("P", "delta_x", "status", "gamma", "clones"))
         line = dict(
@@ -263,21 +286,30 @@ def main():
                         l2="flushed between timed iterations (256 MiB memset)" if not args.no_flush else "not flushed",
                         timing="CUDA events on the launching stream per iteration, max over ranks"),
             us_per_frame=1e6 * secs / args.steps,
-            stage_us={k: round(v, 2) for k, v in stages.items()},
+            stage_us={k: round(v, 2) for k, v in stage_named.items()},
             e2e=dict(value=total_pass * args.steps / secs_e2e, unit=UNIT, h2d_bytes_per_step=int(h2d),
                      d2h_bytes_per_step=int(d2h), us_per_frame=1e6 * secs_e2e / args.steps),
             gpu_launches=int(launches),
-            roofline=dict(bound="hbm", kernel=dom, achieved=achieved, peak=peak, unit="GB/s", frac=achieved / peak,
-                          traffic=None, algorithmic_bytes=abytes, kernel_us=kern[dom], peak_source=peak_src),
+            roofline=dict(bound="tensor", kernel="k_syrk (W = s^2 I + A^T A, mma.sync m8n8k4 f64)", achieved=achieved,
+                          peak=dmma_peak, unit="TFLOP/s", frac=achieved / dmma_peak, traffic=SYRK_NCU_TRAFFIC,
+                          algorithmic_flops=flops, gated_rows=M_rows, kernel_us=kt["syrk"],
+                          peak_source="FP64 DMMA peak measured live on this GPU (orcvio_fp64_peak: mma.sync m8n8k4 "
+                                      "micro-kernel; MEASURED_PEAKS.json carries only bf16 / HBM)",
+                          fp64_dfma_peak=dfma_peak),
+            roofline_hbm=dict(bound="hbm", kernel="k_jac_gate", achieved=jac_bytes / (stages["jac_gate"] * 1e-6) / 1e9,
+                              peak=peak, unit="GB/s", frac=jac_bytes / (stages["jac_gate"] * 1e-6) / 1e9 / peak,
+                              algorithmic_bytes=jac_bytes, kernel_us=stages["jac_gate"], peak_source=peak_src,
+                              note="one frame's working set is L2-resident: latency-bound, not HBM-bound (SURVEY 8d)"),
             clocks=clocks)
         if not args.no_cpu_baseline:
             try:
                 cores = os.cpu_count() or 1
-                f, s, kind = run_cpu_reference(cores, args.ref_features, 1)
+                f, s, kind = run_cpu_reference(cores, args.ref_features, args.ref_repeats)
                 line["cpu_baseline"] = dict(
                     value=f / s, unit=UNIT, cores=cores, kind=kind,
-                    sample=f"{cores} independent frames (one per thread), each {N_CLONES} clones x "
-                           f"{args.ref_features} features, m in [3,{MAX_TRACK}]; {s:.1f} s of CPU wall time")
+                    sample=f"{cores * args.ref_repeats} independent frames ({args.ref_repeats} per host thread), each "
+                           f"{N_CLONES} clones x {args.ref_features} features, m in [3,{MAX_TRACK}]; "
+                           f"{s * cores:.1f} core-seconds of CPU work")
             except Exception as e:       # the baseline is a reported number, never the product path
                 line["cpu_baseline"] = dict(value=None, unit=UNIT, cores=0, kind="port", sample=f"failed: {e}")
         print(json.dumps(line), flush=True)

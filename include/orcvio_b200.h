@@ -205,6 +205,10 @@ long long orcvio_frame_kernel_launches(orcvio_frame* f);
 /* wall-clock split (us) of the last orcvio_frame_update: host work-list build + uploads, kernel launches,
  * wait + downloads, total -- explains the gap between the device-timed and the end-to-end figure */
 int orcvio_frame_host_times(orcvio_frame* f, float* us4);
+/* device time (us, CUDA events, mean over the last profiled orcvio_frame_run) of the two kernels the
+ * stage split does not isolate: us2[0] = k_syrk (W = s^2 I + A^T A on the FP64 tensor cores, the
+ * roofline kernel of bench.py), us2[1] = k_chol_prior (second stream, overlaps stages 1-2) */
+int orcvio_frame_kernel_times(orcvio_frame* f, float* us2);
 
 /* Stage 2 only, for element-wise parity of J1 (measurementJacobian_msckf, orcvio.cpp:1071-1168):
  * per observation H_x (2x6), H_e (2x6), H_f (2x3), r (2), row-major. */

@@ -122,6 +122,7 @@ def lib():
     L.orcvio_frame_kernel_launches.restype = C.c_longlong
     L.orcvio_frame_kernel_launches.argtypes = [vp]
     L.orcvio_frame_host_times.argtypes = [vp, C.POINTER(C.c_float)]
+    L.orcvio_frame_kernel_times.argtypes = [vp, C.POINTER(C.c_float)]
     _lib = L
     return L
 
@@ -460,6 +461,12 @@ class Frame:
         us = (C.c_float * 4)()
         self._L.orcvio_frame_host_times(self._h, us)
         return dict(prepare=us[0], launch=us[1], wait_fetch=us[2], total=us[3])
+
+    def kernel_times(self):
+        """Device microseconds of k_syrk and k_chol_prior in the last run(stages=True)."""
+        us = (C.c_float * 2)()
+        self._L.orcvio_frame_kernel_times(self._h, us)
+        return dict(syrk=us[0], chol_prior=us[1])
 
 
 # ---------------------------------------------------------------- stage-level calls

@@ -135,6 +135,14 @@ Batch::Batch(const Params& p, int n) : p_(p), B_(n) {
   CK(cudaMalloc(&dLs_, nB * ORCVIO_LEG * ORCVIO_LEG * sizeof(double)));
   CK(cudaMalloc(&dFilterRows_, nB * sizeof(int)));
   CK(cudaMemset(dFilterRows_, 0, nB * sizeof(int)));
+  CK(cudaMalloc(&dSyrkCnt_, nB * 16 * sizeof(unsigned int)));
+  CK(cudaMemset(dSyrkCnt_, 0, nB * 16 * sizeof(unsigned int)));
+  {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (cudaDeviceGetAttribute(&n_sm_, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n_sm_ < 1) n_sm_ = 148;
+    if (const char* e = std::getenv("ORCVIO_SYRK_WAVES")) syrk_waves_ = std::max(1, std::atoi(e));
+  }
   CK(cudaMalloc(&dErr_, sizeof(int)));
   CK(cudaMemset(dErr_, 0, sizeof(int)));
   // global fallback front for very wide windows (long tracks): 2*(6 Ncap)+8 rows
@@ -166,7 +174,7 @@ Batch::~Batch() {
   cudaFree(dR_); cudaFree(dS_); cudaFree(dRthin_); cudaFree(dYv_); cudaFree(dT_); cudaFree(dDx_);
   cudaFree(dErr_); cudaFree(dFront_); cudaFree(dChi2_);
   cudaFree(dAmat_); cudaFree(dPart_);
-  cudaFree(dLs_); cudaFree(dTileRows_); cudaFree(dFilterRows_);
+  cudaFree(dLs_); cudaFree(dTileRows_); cudaFree(dFilterRows_); cudaFree(dSyrkCnt_);
   if (dZuptDec_) cudaFree(dZuptDec_);
   if (dZuptInfo_) cudaFree(dZuptInfo_);
   if (hZuptDec_) cudaFreeHost(hZuptDec_);
@@ -314,10 +322,9 @@ void Batch::stage_phase(PhaseWork& w) {
       tilerows_cap_ = w.tiles.size() * 2 + 64;
       CK(cudaMalloc(&dTileRows_, tilerows_cap_ * sizeof(int)));
     }
-    int max_arows = 0;
-    for (const FilterWork& f : w.fw) max_arows = std::max(max_arows, f.arows);
+    int chunks = 1;
+    for (const FilterWork& f : w.fw) chunks = std::max(chunks, syrk_chunks(f.arows, f.N, n_sm_ * syrk_waves_));
     const int nt64 = (6 * w.maxN + 1 + 63) / 64, pairs = nt64 * (nt64 + 1) / 2;
-    const int chunks = std::max(1, (max_arows + SYRK_KC - 1) / SYRK_KC);
     const size_t need_a = (w.arows_total + 16) * (size_t)ldr_;
     if (need_a > amat_cap_) {
       if (dAmat_) cudaFree(dAmat_);
@@ -433,17 +440,17 @@ void Batch::launch_phase(PhaseWork& w, bool download, bool prior_in_flight) {
       if (profiling_) CK(cudaEventRecord(e[4], stream_));
       launch_update(ua, w.maxN, stream_, &nl);
     } else {
-      int max_arows = 0;
-      for (const FilterWork& f : w.fw) max_arows = std::max(max_arows, f.arows);
+      int chunks = 1;
+      for (const FilterWork& f : w.fw) chunks = std::max(chunks, syrk_chunks(f.arows, f.N, n_sm_ * syrk_waves_));
       const int nt64 = (6 * w.maxN + 1 + 63) / 64, pairs = nt64 * (nt64 + 1) / 2;
-      const int chunks = std::max(1, (max_arows + SYRK_KC - 1) / SYRK_KC);
       InfoBufs ib{};
       ib.Ls = dLs_; ib.Amat = dAmat_; ib.part = dPart_;
-      ib.kc = SYRK_KC; ib.max_chunks = chunks; ib.max_pairs = pairs;
+      ib.max_chunks = chunks; ib.max_pairs = pairs; ib.cta_budget = n_sm_ * syrk_waves_; ib.syrk_cnt = dSyrkCnt_;
       ib.tile_rows = dTileRows_; ib.filter_rows = dFilterRows_;
-      launch_info_update(qa, ua, ib, (int)w.tiles.size(), w.max_tile_rows, w.wmax_blk, w.maxN, max_arows, stream_,
+      launch_info_update(qa, ua, ib, (int)w.tiles.size(), w.max_tile_rows, w.wmax_blk, w.maxN, stream_,
                          stream2_, ev_fork_, ev_join_, profiling_ ? e[3] : nullptr, profiling_ ? e[4] : nullptr, &nl,
-                         prior_in_flight);
+                         prior_in_flight, profiling_ ? e[8] : nullptr, profiling_ ? e[9] : nullptr,
+                         profiling_ ? e[10] : nullptr);
     }
     if (profiling_) CK(cudaEventRecord(e[5], stream_));
   }
@@ -1470,6 +1477,11 @@ void Batch::snapshot_stage_times(float* us6) {
     cudaEventElapsedTime(&ms, ev_[3], ev_[4]); us6[3] = ms * 1000.f;
     cudaEventElapsedTime(&ms, ev_[4], ev_[5]); us6[4] = ms * 1000.f;
     cudaEventElapsedTime(&ms, ev_[0], ev_[5]); us6[5] = ms * 1000.f;
+    if (!compress_qr_) {
+      cudaEventElapsedTime(&ms, ev_[3], ev_[8]); last_syrk_us_ = ms * 1000.f;
+      if (cudaEventElapsedTime(&ms, ev_[9], ev_[10]) == cudaSuccess) last_prior_us_ = ms * 1000.f;
+      else (void)cudaGetLastError();
+    }
   } else {
     cudaEventElapsedTime(&ms, ev_[0], ev_[2]); us6[5] = ms * 1000.f;
   }

@@ -152,6 +152,8 @@ class Batch {
   int snapshot_execute(bool download);
   int snapshot_fetch(const SnapshotIO& io);
   void snapshot_stage_times(float* us6);
+  float last_syrk_us() const { return last_syrk_us_; }     // k_syrk / k_chol_prior of the last profiled run
+  float last_prior_us() const { return last_prior_us_; }
   void sync() { cudaStreamSynchronize(stream_); }
   cudaStream_t stream() const { return stream_; }
   void override_tricfg(double translation_threshold, double cost_threshold, double init_final) {
@@ -194,6 +196,9 @@ class Batch {
   size_t amat_cap_ = 0, part_cap_ = 0;
   double* dLs_ = nullptr;
   int *dTileRows_ = nullptr, *dFilterRows_ = nullptr;
+  unsigned int* dSyrkCnt_ = nullptr;   // split-K arrival counters of k_syrk
+  int n_sm_ = 148, syrk_waves_ = 1;
+  float last_syrk_us_ = 0.f, last_prior_us_ = 0.f;
   size_t tilerows_cap_ = 0;
   cudaEvent_t ev_[16];
   // device state

@@ -330,6 +330,7 @@ struct orcvio_frame {
   cudaEvent_t e0 = nullptr, e1 = nullptr;
   bool loaded = false;
   float host_us[4] = {0, 0, 0, 0};     // last orcvio_frame_update: prepare, launch, wait+fetch, total (wall)
+  float kern_us[2] = {0, 0};           // last profiled orcvio_frame_run: k_syrk, k_chol_prior (mean)
 };
 
 orcvio_frame* orcvio_frame_create(int n_clones_cap, int flags, double noise_feature_var, double chi2_p,
@@ -398,6 +399,13 @@ int orcvio_frame_host_times(orcvio_frame* f, float* us4) {
   return ORCVIO_OK;
 }
 
+int orcvio_frame_kernel_times(orcvio_frame* f, float* us2) {
+  if (!f || !us2) return ORCVIO_ERR_ARG;
+  us2[0] = f->kern_us[0];
+  us2[1] = f->kern_us[1];
+  return ORCVIO_OK;
+}
+
 int orcvio_frame_load(orcvio_frame* f, const double* clone_R, const double* clone_p, int n_clones,
                       const double* R_b2c, const double* t_c_b, const double* P_in, const int* feat_off,
                       const int* obs_clone, const double* obs_z, int n_feat) {
@@ -414,7 +422,7 @@ int orcvio_frame_run(orcvio_frame* f, int repeat, float* total_us, float* stage_
   Batch& b = *f->b;
   const long long l0 = b.kernel_launches();
   if (stage_us6) {
-    double acc[6] = {0, 0, 0, 0, 0, 0};
+    double acc[6] = {0, 0, 0, 0, 0, 0}, kacc[2] = {0, 0};
     b.set_profiling(true);
     for (int r = 0; r < repeat; ++r) {
       b.snapshot_execute(false);
@@ -422,8 +430,12 @@ int orcvio_frame_run(orcvio_frame* f, int repeat, float* total_us, float* stage_
       float us[6];
       b.snapshot_stage_times(us);
       for (int k = 0; k < 6; ++k) acc[k] += us[k];
+      kacc[0] += b.last_syrk_us();
+      kacc[1] += b.last_prior_us();
     }
     b.set_profiling(false);
+    f->kern_us[0] = (float)(kacc[0] / repeat);
+    f->kern_us[1] = (float)(kacc[1] / repeat);
     for (int k = 0; k < 6; ++k) stage_us6[k] = (float)(acc[k] / repeat);
     if (total_us) *total_us = (float)acc[5];
   } else {

@@ -195,19 +195,37 @@ __global__ void __launch_bounds__(256) k_aform_dense(const double* Hp, int ldh, 
   }
 }
 
-// ---------------------------------------------------------------- W_aug partials = A^T A
-// 64 x 64 output tiles (upper tile pairs), split over row chunks; 256 threads x 4x4 registers.
-constexpr int SY_T = 64, SY_KS = 16;
+// ---------------------------------------------------------------- W_aug = s^2 I + A^T A  (FP64 tensor cores)
+// grid (tile pairs I <= J, row chunks, filters).  A CTA owns one 64 x 64 tile of A^T A over one chunk of
+// rows: 8 warps x (32 x 16) warp tiles = 4 x 2 accumulator fragments of mma.m8n8k4.f64 per warp, operands
+// staged through shared memory in 32-row slabs (row stride 68 doubles: the four k-rows of a fragment
+// start 8 banks apart, so the 64-bit fragment loads are conflict-free).  Split-K: every chunk stores its
+// partial tile; the LAST chunk to arrive (device-scope counter) adds the partials in chunk order -- a
+// fixed summation order, so the result is bitwise reproducible -- and writes the lower triangle of
+// W_aug ((n+1) x ldr, UpdArgs::S) with s^2 on the first n diagonal entries; row n = v = A^T r'.
+// The rows per chunk adapt to the filter so that pairs x chunks fills the SMs once (syrk_rows_per_chunk).
+constexpr int SY_T = 64, SY_KS = 32, SY_LD = 68;
 
-__global__ void __launch_bounds__(256) k_syrk(const FilterWork* fws, const double* Amat, int lda, double* part,
-                                              int kc, int max_chunks, int max_pairs) {
+__global__ void __launch_bounds__(256) k_syrk(UpdArgs a, const double* __restrict__ Amat, int lda, double* part,
+                                              int max_chunks, int max_pairs, int cta_budget, const Tile* tiles,
+                                              const int* tile_rows, int* filter_rows, unsigned int* counters) {
   const int fi = blockIdx.z;
-  const FilterWork fw = fws[fi];
+  const FilterWork fw = a.fw[fi];
+  const int tid = threadIdx.x;
+  const int pidx = blockIdx.x, chunk = blockIdx.y;
+  if (pidx == 0 && chunk == 0 && tid == 0) {             // gated rows of this filter (k_pinfo skips P when 0)
+    int rows = 0;
+    if (fw.active) {
+      if (tiles == nullptr) rows = fw.arows;             // dense (object) update: every row counts
+      else for (int t = fw.tile_begin; t < fw.tile_end; ++t) rows += tile_rows[t];
+    }
+    filter_rows[fi] = rows;
+  }
   if (!fw.active) return;
-  const int n1 = 6 * fw.N + 1;
+  const int n = 6 * fw.N, n1 = n + 1;
   const int nt_ = (n1 + SY_T - 1) / SY_T;
   // pair index -> (I, J), I <= J
-  int I = 0, J = 0, pidx = blockIdx.x;
+  int I = 0, J = 0;
   {
     int cnt = 0;
     bool found = false;
@@ -218,111 +236,120 @@ __global__ void __launch_bounds__(256) k_syrk(const FilterWork* fws, const doubl
       }
     if (!found) return;
   }
-  const int chunk = blockIdx.y;
+  const int kc = syrk_rows_per_chunk(fw.arows, fw.N, cta_budget);
+  const int nchunks = syrk_chunks(fw.arows, fw.N, cta_budget);
+  if (chunk >= nchunks) return;
   const int row_begin = chunk * kc;
-  if (row_begin >= fw.arows) return;
   const int row_end = min(fw.arows, row_begin + kc);
   const double* A = Amat + (size_t)fw.arow0 * lda;
-  __shared__ __align__(16) double As[SY_KS][SY_T];
-  __shared__ __align__(16) double Bs[SY_KS][SY_T];
-  const int tid = threadIdx.x;
-  const int tx = tid & 15, ty = tid >> 4;
-  double acc[4][4];
+  __shared__ __align__(16) double As[SY_KS][SY_LD];
+  __shared__ __align__(16) double Bs[SY_KS][SY_LD];
+  __shared__ int s_last;
+  const bool diag = (I == J);
+  const double(*Bp)[SY_LD] = diag ? As : Bs;
+  const int warp = tid >> 5, lane = tid & 31;
+  const int fr = lane >> 2, fk = lane & 3;               // fragment row (or column) / k index
+  const int wi = (warp & 1) * 32, wj = (warp >> 1) * 16;
+  double2 acc[4][2];
 #pragma unroll
   for (int u = 0; u < 4; ++u)
 #pragma unroll
-    for (int v = 0; v < 4; ++v) acc[u][v] = 0.0;
-  // loader mapping: 16 rows x 64 cols = 512 double2; thread loads 2 double2 per matrix
-  const int lr = tid >> 5, lc = (tid & 31) * 2;       // row 0..7 (+8), column pair
+    for (int v = 0; v < 2; ++v) acc[u][v] = make_double2(0.0, 0.0);
+  // loader: 32 rows x 64 columns per matrix = 1024 double2, four per thread (rows lr, lr+8, lr+16, lr+24)
+  const int lr = tid >> 5, lc = (tid & 31) * 2;
   const int i0 = I * SY_T, j0 = J * SY_T;
   const double2 z2 = make_double2(0.0, 0.0);
-  const bool ci_ok = (i0 + lc < lda), cj_ok = (j0 + lc < lda);
-  auto fetch = [&](int r0, double2& a0, double2& a1, double2& b0, double2& b1) {
-    const int ra = r0 + lr, rb = r0 + lr + 8;
-    a0 = a1 = b0 = b1 = z2;
-    if (ra < row_end) {
-      if (ci_ok) a0 = *reinterpret_cast<const double2*>(A + (size_t)ra * lda + i0 + lc);
-      if (cj_ok) b0 = *reinterpret_cast<const double2*>(A + (size_t)ra * lda + j0 + lc);
-    }
-    if (rb < row_end) {
-      if (ci_ok) a1 = *reinterpret_cast<const double2*>(A + (size_t)rb * lda + i0 + lc);
-      if (cj_ok) b1 = *reinterpret_cast<const double2*>(A + (size_t)rb * lda + j0 + lc);
+  const bool ci_ok = (i0 + lc < lda), cj_ok = (j0 + lc < lda) && !diag;
+  double2 pa[4], pb[4];
+  auto fetch = [&](int r0) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int r = r0 + lr + 8 * q;
+      pa[q] = pb[q] = z2;
+      if (r < row_end) {
+        if (ci_ok) pa[q] = *reinterpret_cast<const double2*>(A + (size_t)r * lda + i0 + lc);
+        if (cj_ok) pb[q] = *reinterpret_cast<const double2*>(A + (size_t)r * lda + j0 + lc);
+      }
     }
   };
-  double2 a0, a1, b0, b1;
-  fetch(row_begin, a0, a1, b0, b1);
+  fetch(row_begin);
   for (int r0 = row_begin; r0 < row_end; r0 += SY_KS) {
     __syncthreads();
-    *reinterpret_cast<double2*>(&As[lr][lc]) = a0;
-    *reinterpret_cast<double2*>(&As[lr + 8][lc]) = a1;
-    *reinterpret_cast<double2*>(&Bs[lr][lc]) = b0;
-    *reinterpret_cast<double2*>(&Bs[lr + 8][lc]) = b1;
-    __syncthreads();
-    if (r0 + SY_KS < row_end) fetch(r0 + SY_KS, a0, a1, b0, b1);     // in flight during the FMAs below
 #pragma unroll
-    for (int kk = 0; kk < SY_KS; ++kk) {
-      // thread (tx, ty) owns rows {2ty, 2ty+1, 32+2ty, 33+2ty} x cols {2tx, 2tx+1, 32+2tx, 33+2tx}:
-      // a half-warp reads 256 contiguous bytes of Bs per double2 load (no bank conflicts)
-      const double2 x0 = *reinterpret_cast<const double2*>(&As[kk][2 * ty]);
-      const double2 x1 = *reinterpret_cast<const double2*>(&As[kk][32 + 2 * ty]);
-      const double2 y0 = *reinterpret_cast<const double2*>(&Bs[kk][2 * tx]);
-      const double2 y1 = *reinterpret_cast<const double2*>(&Bs[kk][32 + 2 * tx]);
-      const double av[4] = {x0.x, x0.y, x1.x, x1.y};
-      const double bv[4] = {y0.x, y0.y, y1.x, y1.y};
+    for (int q = 0; q < 4; ++q) {
+      *reinterpret_cast<double2*>(&As[lr + 8 * q][lc]) = pa[q];
+      if (!diag) *reinterpret_cast<double2*>(&Bs[lr + 8 * q][lc]) = pb[q];
+    }
+    __syncthreads();
+    if (r0 + SY_KS < row_end) fetch(r0 + SY_KS);          // in flight during the MMAs below
+#pragma unroll
+    for (int k4 = 0; k4 < SY_KS; k4 += 4) {
+      double af[4], bf[2];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) af[u] = As[k4 + fk][wi + 8 * u + fr];
+#pragma unroll
+      for (int v = 0; v < 2; ++v) bf[v] = Bp[k4 + fk][wj + 8 * v + fr];
 #pragma unroll
       for (int u = 0; u < 4; ++u)
 #pragma unroll
-        for (int v = 0; v < 4; ++v) acc[u][v] += av[u] * bv[v];
+        for (int v = 0; v < 2; ++v) dmma884(acc[u][v].x, acc[u][v].y, af[u], bf[v]);
     }
   }
-  double* out = part + (((size_t)fi * max_chunks + chunk) * max_pairs + pidx) * (SY_T * SY_T);
+  // tile element (ii, jj) = W[i0 + ii][j0 + jj]; fragment (u, v): ii = wi + 8u + fr, jj = wj + 8v + 2fk (+1)
+  double* S = a.S + (size_t)fi * a.r_stride;
+  auto emit = [&](int ii, int jj, double s) {            // lower triangle of W_aug: row = larger index
+    const int gi = j0 + jj, gj = i0 + ii;
+    if (gi >= n1 || gj > gi) return;
+    if (gi == gj && gi < n) s += a.sigma2;
+    S[(size_t)gi * a.ldr + gj] = s;
+  };
+  if (nchunks == 1) {
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+#pragma unroll
+      for (int v = 0; v < 2; ++v) {
+        emit(wi + 8 * u + fr, wj + 8 * v + 2 * fk, acc[u][v].x);
+        emit(wi + 8 * u + fr, wj + 8 * v + 2 * fk + 1, acc[u][v].y);
+      }
+    return;
+  }
+  double* base = part + ((size_t)fi * max_chunks * max_pairs + pidx) * (SY_T * SY_T);
+  const size_t cstride = (size_t)max_pairs * (SY_T * SY_T);
+  double* out = base + (size_t)chunk * cstride;
 #pragma unroll
   for (int u = 0; u < 4; ++u)
 #pragma unroll
-    for (int v = 0; v < 4; ++v)
-      out[((u < 2 ? 0 : 32) + 2 * ty + (u & 1)) * SY_T + (v < 2 ? 0 : 32) + 2 * tx + (v & 1)] = acc[u][v];
+    for (int v = 0; v < 2; ++v)
+      *reinterpret_cast<double2*>(out + (wi + 8 * u + fr) * SY_T + wj + 8 * v + 2 * fk) = acc[u][v];
+  __threadfence();
+  __syncthreads();
+  unsigned int* cnt = counters + (size_t)fi * max_pairs + pidx;
+  if (tid == 0) s_last = (atomicAdd(cnt, 1u) == (unsigned int)(nchunks - 1));
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  // last chunk of this tile: sum the partials in chunk order (16 tile elements per thread)
+  double s[16];
+#pragma unroll
+  for (int q = 0; q < 16; ++q) s[q] = 0.0;
+  for (int c = 0; c < nchunks; ++c) {
+    const double* pc = base + (size_t)c * cstride + tid;
+#pragma unroll
+    for (int q = 0; q < 16; ++q) s[q] += __ldcg(pc + 256 * q);
+  }
+#pragma unroll
+  for (int q = 0; q < 16; ++q) {
+    const int e = tid + 256 * q;
+    emit(e >> 6, e & 63, s[q]);
+  }
+  if (tid == 0) *cnt = 0u;                               // ready for the next launch
 }
 
-// W_aug (lower, (n+1) x ldr in UpdArgs::S): sum of the chunk partials + s^2 on the first n diagonal
-// entries; row n = v = A^T r'.  Also the number of gated rows per filter.
-__global__ void __launch_bounds__(256) k_syrk_reduce(UpdArgs a, const double* part, int kc, int max_chunks,
-                                                     int max_pairs, const Tile* tiles, const int* tile_rows,
-                                                     int* filter_rows) {
-  const int fi = blockIdx.y;
-  const FilterWork fw = a.fw[fi];
-  const int e = blockIdx.x * blockDim.x + threadIdx.x;
-  if (!fw.active) {
-    if (e == 0) filter_rows[fi] = 0;
-    return;
-  }
-  if (e == 0) {
-    int rows = 0;
-    if (tiles == nullptr) rows = fw.arows;             // dense (object) update: every row counts
-    else for (int t = fw.tile_begin; t < fw.tile_end; ++t) rows += tile_rows[t];
-    filter_rows[fi] = rows;
-  }
-  const int n = 6 * fw.N, n1 = n + 1;
-  if (e >= n1 * n1) return;
-  const int j = e / n1, i = e - j * n1;                // i fastest: the partial tiles are read contiguously
-  if (j > i) return;                                   // lower triangle: i >= j  -> tile pair (J, I)
-  const int nt_ = (n1 + SY_T - 1) / SY_T;
-  const int TI = j / SY_T, TJ = i / SY_T;              // TI <= TJ
-  int pidx = 0;
-  for (int ii = 0; ii < TI; ++ii) pidx += nt_ - ii;
-  pidx += TJ - TI;
-  const int nchunks = (fw.arows + kc - 1) / kc;
-  double s = 0.0;
-  for (int c = 0; c < nchunks; ++c)
-    s += part[(((size_t)fi * max_chunks + c) * max_pairs + pidx) * (SY_T * SY_T) + (j - TI * SY_T) * SY_T + (i - TJ * SY_T)];
-  if (i == j && i < n) s += a.sigma2;
-  double* S = a.S + (size_t)fi * a.r_stride;
-  S[(size_t)i * a.ldr + j] = s;
-}
-
-// ---------------------------------------------------------------- W = C C^T with F_1, v carried
+// ---------------------------------------------------------------- W = C C^T with F_1, v carried; dx
 // grid (strips, filters).  Every CTA factors W (redundantly -- the factorisation is latency, not
-// throughput) and carries its strip of CS rows of F_1 (and strip 0 the vector v) through it:
-// the strip leaves as the matching columns of Y = C^-1 F_1^T, v leaves as y = C^-1 v.
+// throughput) and carries its strip of CS rows of F_1 plus the vector v through it: the strip
+// leaves as the matching columns of Y = C^-1 F_1^T, v leaves as y = C^-1 v, and the strip's part of
+// dx = Y^T y (src/orcvio.cpp:1820 `dx_leg = K * r_o`) is formed on the spot from the tiles.
 constexpr int CS = 16;
 
 __global__ void __launch_bounds__(CHOL_THREADS) k_chol_w_solve(UpdArgs a) {
@@ -335,19 +362,17 @@ __global__ void __launch_bounds__(CHOL_THREADS) k_chol_w_solve(UpdArgs a) {
   const int d0 = blockIdx.x * CS;
   if (d0 >= D) return;
   const int nd = min(CS, D - d0);
-  const bool has_v = (blockIdx.x == 0);
-  const int nx = nd + (has_v ? 1 : 0);
+  const int nx = nd + 1;
   const double* S = a.S + (size_t)fi * a.r_stride;
   double* T = a.T + (size_t)fi * a.t_stride;
   double* yv = a.yv + (size_t)fi * a.ldr;
   double* A = sm;
   const int Tm = (n + 7) >> 3;
-  const int tid = threadIdx.x, nt = blockDim.x;
-  const int warp = tid >> 5, lane = tid & 31, nw = nt >> 5;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   chol_init(A, cs, n, nx);
   __syncthreads();
   const int ldr = a.ldr, ldt0 = a.ldt;
-  // triangle rows: W;  carried rows: row n + q = F_1[d0 + q][:] = FT[:][d0 + q];  last row (strip 0): v = S[n][:]
+  // triangle rows: W;  carried rows: row n + q = F_1[d0 + q][:] = FT[:][d0 + q];  last row: v = S[n][:]
   chol_load_rows(A, n, 0, n + nx, [&](int i, int j) {
     if (i < n) return S[(size_t)i * ldr + j];
     const int q = i - n;
@@ -355,63 +380,58 @@ __global__ void __launch_bounds__(CHOL_THREADS) k_chol_w_solve(UpdArgs a) {
   });
   cta_cholesky(A, cs, nullptr, n, nx);
   const int ldt = a.ldt;
+  const bool strip0 = (blockIdx.x == 0);
   chol_for_rows(A, n, nx, n, [&](int i, int k, double l) {
     const int q = i - n;
-    if (q < nd) T[(size_t)k * ldt + d0 + q] = l;       // Y[k][d0 + q]
-    else yv[k] = l;
+    if (q < nd) T[(size_t)k * ldt + d0 + q] = l;         // Y[k][d0 + q]
+    else if (strip0) yv[k] = l;
   });
+  // dx[d0 + q] = sum_k Y[k][d0 + q] y[k]: warp q, lanes over k, fixed-order shuffle tree
+  if (warp < nd) {
+    const int iy = n + nd, iq = n + warp;
+    double s0 = 0.0, s1 = 0.0;
+    int k = lane;
+    for (; k + 32 < n; k += 64) {
+      s0 += A[chol_at(iq, k, Tm)] * A[chol_at(iy, k, Tm)];
+      s1 += A[chol_at(iq, k + 32, Tm)] * A[chol_at(iy, k + 32, Tm)];
+    }
+    if (k < n) s0 += A[chol_at(iq, k, Tm)] * A[chol_at(iy, k, Tm)];
+    double sv = s0 + s1;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sv += __shfl_xor_sync(0xffffffffu, sv, o);
+    if (lane == 0) a.dx[(size_t)fi * a.lddx + d0 + warp] = sv;
+  }
 }
 
-// ---------------------------------------------------------------- dx = Y^T y and the state increment
-// (incrementState_IMUCam, src/orcvio.cpp:4468-4567; same arithmetic as update_kernel.cu k_apply_dx)
-__global__ void __launch_bounds__(512) k_dx(UpdArgs a) {
-  __shared__ double partial[16][ORCVIO_LEG + 6 * ORCVIO_MAX_OBS + 2];
-  __shared__ double dxs[ORCVIO_LEG + 6 * ORCVIO_MAX_OBS + 2];
-  const int fi = blockIdx.x;
-  const FilterWork fw = a.fw[fi];
-  if (!fw.active) return;
-  const int n = 6 * fw.N, D = fw.D;
-  const double* Y = a.T + (size_t)fi * a.t_stride;
-  const double* yv = a.yv + (size_t)fi * a.ldr;
-  double* imu = a.imu + (size_t)fi * IM_STRIDE;
-  double* clones = a.clones + (size_t)fi * a.clone_stride;
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  // warp w sums rows k = w, w+32, ... ; lanes over columns
-  for (int i = lane; i < D; i += 32) {
-    double s = 0.0;
-    for (int k = warp; k < n; k += 16) s += Y[(size_t)k * a.ldt + i] * yv[k];
-    partial[warp][i] = s;
-  }
-  __syncthreads();
-  for (int i = tid; i < D; i += blockDim.x) {
-    double s = 0.0;
-#pragma unroll 8
-    for (int w2 = 0; w2 < 16; ++w2) s += partial[w2][i];
-    dxs[i] = s;
-    if (a.dx) a.dx[(size_t)fi * a.lddx + i] = s;
-  }
-  __syncthreads();
-  cta_increment_state(dxs, imu, clones, fw.N, a.flags, a.dx ? &a.dx[(size_t)fi * a.lddx + a.lddx - 1] : nullptr);
-}
-
-// ---------------------------------------------------------------- P+ = s^2 Y^T Y + F_2 F_2^T
+// ---------------------------------------------------------------- P+ = s^2 Y^T Y + F_2 F_2^T and the state increment
 // 32 x 32 output tile per CTA; both strips of Y (n x 32) are staged in shared memory with one
-// round trip, then the k loop runs without barriers.
+// round trip, then the k loop runs without barriers.  One extra CTA per filter (blockIdx.y ==
+// gridDim.y - 1) applies dx to the state (incrementState_IMUCam, src/orcvio.cpp:4468-4567).
 constexpr int PT = 32;
 
 __global__ void __launch_bounds__(256) k_pinfo(UpdArgs a, const double* Ls_all, const int* filter_rows) {
   extern __shared__ double sm[];
   const int fi = blockIdx.z;
   const FilterWork fw = a.fw[fi];
-  if (!fw.active || filter_rows[fi] == 0) return;       // no gated rows: posterior == prior, P untouched
+  if (!fw.active) return;
   const int n = 6 * fw.N, D = fw.D, L = ORCVIO_LEG;
+  const int tid = threadIdx.x;
+  if (blockIdx.y == gridDim.y - 1) {
+    if (blockIdx.x != 0) return;
+    double* dxs = sm;
+    for (int i = tid; i < D; i += blockDim.x) dxs[i] = a.dx[(size_t)fi * a.lddx + i];
+    __syncthreads();
+    cta_increment_state(dxs, a.imu + (size_t)fi * IM_STRIDE, a.clones + (size_t)fi * a.clone_stride, fw.N, a.flags,
+                        &a.dx[(size_t)fi * a.lddx + a.lddx - 1]);
+    return;
+  }
+  if (filter_rows[fi] == 0) return;                     // no gated rows: posterior == prior, P untouched
   const int i0 = blockIdx.y * PT, j0 = blockIdx.x * PT;
   if (i0 >= D || j0 >= D) return;
   const double* Y = a.T + (size_t)fi * a.t_stride;
   double* P = a.P + (size_t)fi * a.p_stride;
   double* Ys_i = sm;                       // [n][PT]
   double* Ys_j = sm + (size_t)n * PT;
-  const int tid = threadIdx.x;
   for (int e = tid; e < n * PT; e += 256) {
     const int k = e / PT, c = e - k * PT;
     Ys_i[e] = (i0 + c < D) ? Y[(size_t)k * a.ldt + i0 + c] : 0.0;
@@ -454,9 +474,25 @@ static void info_attrs() {
   attr = true;
 }
 
+static void launch_syrk(const UpdArgs& u, const InfoBufs& ib, int nmax, int B, const Tile* tiles, cudaStream_t s) {
+  const int nt_ = (nmax + 1 + SY_T - 1) / SY_T;
+  dim3 gs(nt_ * (nt_ + 1) / 2, ib.max_chunks, B);
+  k_syrk<<<gs, 256, 0, s>>>(u, ib.Amat, u.ldr, ib.part, ib.max_chunks, ib.max_pairs, ib.cta_budget, tiles,
+                            ib.tile_rows, ib.filter_rows, ib.syrk_cnt);
+  check_launch("k_syrk");
+}
+
+static void launch_pinfo(const UpdArgs& u, const InfoBufs& ib, int nmax, int B, cudaStream_t s) {
+  const int Dmax = ORCVIO_LEG + nmax;
+  const int g = (Dmax + PT - 1) / PT;
+  dim3 g5(g, g + 1, B);                                  // last row of CTAs: the state increment
+  k_pinfo<<<g5, 256, (size_t)2 * nmax * PT * sizeof(double), s>>>(u, ib.Ls, ib.filter_rows);
+  check_launch("k_pinfo");
+}
+
 // Object update, first half (removeLostObjects -> measurementUpdate_msckf with a dense block):
 // prior factor, A = Hp L, W = s^2 I + A^T A, Cholesky with F_1 / v carried.  Leaves Y in u.T,
-// y in u.yv and W_aug's corner r'^T r' untouched in u.S[n][n]:
+// y in u.yv, dx in u.dx and W_aug's corner r'^T r' untouched in u.S[n][n]:
 //   gamma = r'^T (Hp P Hp^T + s^2 I)^-1 r' = (r'^T r' - y^T y) / s^2      (Woodbury).
 void launch_info_dense_factor(const UpdArgs& u, const InfoBufs& ib, const double* Hp, int ldh, int rows, int N,
                               cudaStream_t s) {
@@ -467,53 +503,43 @@ void launch_info_dense_factor(const UpdArgs& u, const InfoBufs& ib, const double
   check_launch("k_chol_prior");
   k_aform_dense<<<rows, 256, 0, s>>>(Hp, ldh, rows, n, u.T, u.ldt, ib.Amat, u.ldr);
   check_launch("k_aform_dense");
-  const int nt_ = (n + 1 + SY_T - 1) / SY_T, pairs = nt_ * (nt_ + 1) / 2;
-  const int chunks = std::max(1, (rows + ib.kc - 1) / ib.kc);
-  dim3 gs(pairs, chunks, 1);
-  k_syrk<<<gs, 256, 0, s>>>(u.fw, ib.Amat, u.ldr, ib.part, ib.kc, ib.max_chunks, ib.max_pairs);
-  check_launch("k_syrk");
-  dim3 gr(((n + 1) * (n + 1) + 255) / 256, 1);
-  k_syrk_reduce<<<gr, 256, 0, s>>>(u, ib.part, ib.kc, ib.max_chunks, ib.max_pairs, nullptr, ib.tile_rows, ib.filter_rows);
-  check_launch("k_syrk_reduce");
+  launch_syrk(u, ib, n, 1, nullptr, s);
   const size_t sm_w = chol_smem_doubles(n, CS + 1) * sizeof(double);
   dim3 gw((D + CS - 1) / CS, 1);
   k_chol_w_solve<<<gw, CHOL_THREADS, sm_w, s>>>(u);
   check_launch("k_chol_w_solve");
 }
 
-// Object update, second half (after the gate passed): dx, state increment, P+.
+// Object update, second half (after the gate passed): state increment, P+.
 void launch_info_dense_apply(const UpdArgs& u, const InfoBufs& ib, int N, cudaStream_t s) {
   info_attrs();
-  const int D = ORCVIO_LEG + 6 * N;
-  k_dx<<<1, 512, 0, s>>>(u);
-  check_launch("k_dx");
-  dim3 g5((D + PT - 1) / PT, (D + PT - 1) / PT, 1);
-  k_pinfo<<<g5, 256, (size_t)2 * 6 * N * PT * sizeof(double), s>>>(u, ib.Ls, ib.filter_rows);
-  check_launch("k_pinfo");
+  launch_pinfo(u, ib, 6 * N, 1, s);
 }
 
 // Prior factor on the second stream: it depends only on P, so it overlaps triangulation / Jacobians
 // (and, in the end-to-end call, the host's work-list build).  `fork` was recorded on the main stream
 // once P was in place; `join` is what the main stream waits for before k_aform.
 void launch_info_prior(const UpdArgs& u, const InfoBufs& ib, int max_N, cudaStream_t s2, cudaEvent_t fork,
-                       cudaEvent_t join) {
+                       cudaEvent_t join, cudaEvent_t t0, cudaEvent_t t1) {
   const int Dmax = ORCVIO_LEG + 6 * max_N;
   info_attrs();
   cudaStreamWaitEvent(s2, fork, 0);
+  if (t0) cudaEventRecord(t0, s2);
   const size_t sm_prior = (chol_smem_doubles(Dmax, 0) + (size_t)Dmax + 2) * sizeof(double);
   k_chol_prior<<<u.n_filters, CHOL_THREADS, sm_prior, s2>>>(u, ib.Ls);
   check_launch("k_chol_prior");
+  if (t1) cudaEventRecord(t1, s2);
   cudaEventRecord(join, s2);
 }
 
 void launch_info_update(const QrArgs& q, const UpdArgs& u, const InfoBufs& ib, int n_tiles, int max_tile_rows,
-                        int max_w_blk, int max_N, int max_arows, cudaStream_t s, cudaStream_t s2,
-                        cudaEvent_t fork, cudaEvent_t join, cudaEvent_t mid1, cudaEvent_t mid2, int* launches,
-                        bool prior_in_flight) {
+                        int max_w_blk, int max_N, cudaStream_t s, cudaStream_t s2, cudaEvent_t fork,
+                        cudaEvent_t join, cudaEvent_t mid1, cudaEvent_t mid2, int* launches, bool prior_in_flight,
+                        cudaEvent_t mid_syrk, cudaEvent_t prior_t0, cudaEvent_t prior_t1) {
   const int nmax = 6 * max_N, Dmax = ORCVIO_LEG + nmax;
   const int B = u.n_filters;
   info_attrs();
-  if (!prior_in_flight) launch_info_prior(u, ib, max_N, s2, fork, join);
+  if (!prior_in_flight) launch_info_prior(u, ib, max_N, s2, fork, join, prior_t0, prior_t1);
   cudaStreamWaitEvent(s, join, 0);
   const int lda = u.ldr;
   if (n_tiles > 0) {
@@ -529,27 +555,15 @@ void launch_info_update(const QrArgs& q, const UpdArgs& u, const InfoBufs& ib, i
     check_launch("k_aform");
   }
   if (mid1) cudaEventRecord(mid1, s);
-  const int nt_ = (nmax + 1 + SY_T - 1) / SY_T;
-  const int pairs = nt_ * (nt_ + 1) / 2;
-  const int kc = ib.kc;
-  const int chunks = std::max(1, (max_arows + kc - 1) / kc);
-  dim3 gs(pairs, chunks, B);
-  k_syrk<<<gs, 256, 0, s>>>(q.fw, ib.Amat, lda, ib.part, kc, ib.max_chunks, ib.max_pairs);
-  check_launch("k_syrk");
-  dim3 gr(((nmax + 1) * (nmax + 1) + 255) / 256, B);
-  k_syrk_reduce<<<gr, 256, 0, s>>>(u, ib.part, kc, ib.max_chunks, ib.max_pairs, q.tiles, ib.tile_rows, ib.filter_rows);
-  check_launch("k_syrk_reduce");
+  launch_syrk(u, ib, nmax, B, q.tiles, s);
+  if (mid_syrk) cudaEventRecord(mid_syrk, s);
   const size_t sm_w = chol_smem_doubles(nmax, CS + 1) * sizeof(double);
   dim3 gw((Dmax + CS - 1) / CS, B);
   k_chol_w_solve<<<gw, CHOL_THREADS, sm_w, s>>>(u);
   check_launch("k_chol_w_solve");
   if (mid2) cudaEventRecord(mid2, s);
-  k_dx<<<B, 512, 0, s>>>(u);
-  check_launch("k_dx");
-  dim3 g5((Dmax + PT - 1) / PT, (Dmax + PT - 1) / PT, B);
-  k_pinfo<<<g5, 256, (size_t)2 * nmax * PT * sizeof(double), s>>>(u, ib.Ls, ib.filter_rows);
-  check_launch("k_pinfo");
-  if (launches) *launches += 5 + (prior_in_flight ? 0 : 1) + (n_tiles > 0 ? 1 : 0);
+  launch_pinfo(u, ib, nmax, B, s);
+  if (launches) *launches += 3 + (prior_in_flight ? 0 : 1) + (n_tiles > 0 ? 1 : 0);
 }
 
 }  // namespace ob

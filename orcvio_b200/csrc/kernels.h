@@ -122,7 +122,8 @@ struct InfoBufs {
   double* Ls;            // per filter 22 x 22 : IMU block factor given the clones
   double* Amat;          // stacked A = [H' L | r'], lda = ldr
   double* part;          // split-K partials of A^T A: [filter][chunk][pair][64 x 64]
-  int kc, max_chunks, max_pairs;
+  int max_chunks, max_pairs, cta_budget;   // part layout [filter][max_chunks][max_pairs]; SMs x waves
+  unsigned int* syrk_cnt; // split-K arrival counters [filter][pair] (zero between launches)
   int* tile_rows;        // gated rows per tile
   int* filter_rows;      // gated rows per filter (0 -> posterior == prior, P is left untouched)
 };
@@ -178,11 +179,12 @@ void launch_qr(const QrArgs& a, size_t tile_smem_doubles, int max_w_blk, int max
 void launch_update(const UpdArgs& a, int max_N, cudaStream_t s, int* launches);
 void launch_update_tail(const UpdArgs& a, int max_N, cudaStream_t s);   // k_trsm + k_apply_dx
 void launch_info_update(const QrArgs& q, const UpdArgs& u, const InfoBufs& ib, int n_tiles, int max_tile_rows,
-                        int max_w_blk, int max_N, int max_arows, cudaStream_t s, cudaStream_t s2,
-                        cudaEvent_t fork, cudaEvent_t join, cudaEvent_t mid1, cudaEvent_t mid2, int* launches,
-                        bool prior_in_flight = false);
+                        int max_w_blk, int max_N, cudaStream_t s, cudaStream_t s2, cudaEvent_t fork,
+                        cudaEvent_t join, cudaEvent_t mid1, cudaEvent_t mid2, int* launches,
+                        bool prior_in_flight = false, cudaEvent_t mid_syrk = nullptr, cudaEvent_t prior_t0 = nullptr,
+                        cudaEvent_t prior_t1 = nullptr);
 void launch_info_prior(const UpdArgs& u, const InfoBufs& ib, int max_N, cudaStream_t s2, cudaEvent_t fork,
-                       cudaEvent_t join);
+                       cudaEvent_t join, cudaEvent_t t0 = nullptr, cudaEvent_t t1 = nullptr);
 void launch_info_dense_factor(const UpdArgs& u, const InfoBufs& ib, const double* Hp, int ldh, int rows, int N,
                               cudaStream_t s);
 void launch_info_dense_apply(const UpdArgs& u, const InfoBufs& ib, int N, cudaStream_t s);
@@ -203,7 +205,24 @@ void launch_zupt(const ZuptArgs& a, cudaStream_t s);
 constexpr int QR_THREADS = 256;
 constexpr int QR_SMEM_BYTES = 200 * 1024;
 constexpr int AFORM_TILE_ROWS = 64;     // row cap of a tile of the whitened-form path
-constexpr int SYRK_KC = 512;            // rows per split-K chunk of A^T A
+// Split-K plan of W = s^2 I + A^T A for ONE filter (k_syrk): enough (64 x 64 tile pairs x chunks) CTAs to
+// fill `cta_budget` (= SMs x waves), never fewer than 128 rows per chunk, rows per chunk a multiple of 32.
+// A function of the filter alone (its clone count and stacked rows): the chunking fixes the summation
+// order, so a filter gives bit-identical results whether it runs alone or inside a batch.
+__host__ __device__ inline int syrk_rows_per_chunk(int arows, int N, int cta_budget) {
+  const int nt = (6 * N + 1 + 63) / 64, pairs = nt * (nt + 1) / 2;
+  int chunks = arows / 128;
+  const int cap = cta_budget / pairs;
+  if (chunks > cap) chunks = cap;
+  if (chunks < 1) chunks = 1;
+  const int kc = ((arows + chunks - 1) / chunks + 31) / 32 * 32;
+  return kc < 32 ? 32 : kc;
+}
+__host__ __device__ inline int syrk_chunks(int arows, int N, int cta_budget) {
+  const int kc = syrk_rows_per_chunk(arows, N, cta_budget);
+  const int c = (arows + kc - 1) / kc;
+  return c < 1 ? 1 : c;
+}
 inline int qr_tile_rows_cap(int w_cols) {                // rows that fit beside (w_cols+1) columns
   int ld = w_cols + 2;
   int cap = QR_SMEM_BYTES / 8 / ld;

@@ -229,14 +229,14 @@ int Batch::object_update(int fi, const double* Hx, const double* Hf, const doubl
   launch_project_dense(dM.as<double>(), rows, ld, odim, ld, stream_);            // nullspace_project_inplace_svd
   const int prow = rows - odim;
   const int nt64 = (n + 1 + 63) / 64, pairs = nt64 * (nt64 + 1) / 2;
-  const int chunks = std::max(1, (prow + SYRK_KC - 1) / SYRK_KC);
+  const int chunks = syrk_chunks(prow, N, n_sm_ * syrk_waves_);
   const size_t need_a = ((size_t)prow + 16) * ldr_;
   if (need_a > amat_cap_) {
     if (dAmat_) cudaFree(dAmat_);
     amat_cap_ = need_a * 2;
     CKO(cudaMalloc(&dAmat_, amat_cap_ * sizeof(double)));
   }
-  const size_t need_p = (size_t)B_ * chunks * pairs * 4096;
+  const size_t need_p = (size_t)chunks * pairs * 4096;
   if (need_p > part_cap_) {
     if (dPart_) cudaFree(dPart_);
     part_cap_ = need_p * 2;
@@ -260,11 +260,11 @@ int Batch::object_update(int fi, const double* Hx, const double* Hf, const doubl
   ua.flags = flags_; ua.sigma2 = p_.feature_observation_noise;
   InfoBufs ib{};
   ib.Ls = dLs_ + (size_t)fi * ORCVIO_LEG * ORCVIO_LEG; ib.Amat = dAmat_; ib.part = dPart_;
-  ib.kc = SYRK_KC; ib.max_chunks = chunks; ib.max_pairs = pairs;
+  ib.max_chunks = chunks; ib.max_pairs = pairs; ib.cta_budget = n_sm_ * syrk_waves_; ib.syrk_cnt = dSyrkCnt_;
   ib.tile_rows = nullptr; ib.filter_rows = dFilterRows_ + fi;
   const double* Hp = dM.as<double>() + (size_t)odim * ld + odim;
   launch_info_dense_factor(ua, ib, Hp, ld, prow, N, stream_);
-  launches_ += 6;
+  launches_ += 5;
   std::vector<double> y(n);
   double corner = 0.0;
   CKO(cudaMemcpyAsync(y.data(), ua.yv, n * sizeof(double), cudaMemcpyDeviceToHost, stream_));
@@ -284,7 +284,7 @@ int Batch::object_update(int fi, const double* Hx, const double* Hf, const doubl
       if (std::isnan(Hx[(size_t)k * rows + i])) return done(5, 0);
   }
   launch_info_dense_apply(ua, ib, N, stream_);
-  launches_ += 2;
+  launches_ += 1;
   download_mirrors();
   CKO(cudaStreamSynchronize(stream_));
   std::memcpy(F.imu_mirror.data(), hImu_ + (size_t)fi * IM_STRIDE, IM_STRIDE * sizeof(double));
