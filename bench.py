@@ -43,7 +43,7 @@ NOISE_VAR = 1.6e-5          # (2 x 0.002)^2: synthetic pixel noise of the KITTI-
 TRI = dict(cost_threshold=1e-3, init_final_dist_threshold=100.0)
 # dram__bytes_read.sum + dram__bytes_write.sum of one k_syrk launch from the committed `ncu --set full`
 # capture (profiles/); None until a capture of the current kernel exists
-SYRK_NCU_TRAFFIC = None
+SYRK_NCU_TRAFFIC = 37_659_136          # 37.658 MB read + 1 KB written (profiles/r1_ncu_full_summary.csv)
 WORKLOAD = f"stress frame: {N_CLONES}-clone window, {N_FEATURES} features, max_track_len {MAX_TRACK} (SURVEY 8d C4a)"
 
 
