@@ -41,6 +41,7 @@ struct Batch::PhaseWork {
   int rows_cap = 0;              // > 0: row cap of a tile (whitened form); 0: what fits the QR tile
   int max_tile_rows = 0;
   size_t arows_total = 0;        // rows of the stacked A matrix (whitened form)
+  int syrk_units = 1;            // grid of k_syrk: widest split-K plan over the filters
   int own_wmax_blk = 1;
   int wmax_blk = 1;
   int maxN = 0;
@@ -105,7 +106,13 @@ Batch::Batch(const Params& p, int n) : p_(p), B_(n) {
     for (int s = Fcap_ - 1; s >= 0; --s) F.free_slots.push_back(s);
   }
   CK(cudaStreamCreate(&stream_));
-  CK(cudaStreamCreate(&stream2_));
+  {
+    // the prior factor is ONE big CTA (a whole SM's shared memory and registers) competing with the thousands
+    // of small CTAs of the feature kernels: highest priority, so that the block scheduler places it first
+    int lo = 0, hi = 0;
+    cudaDeviceGetStreamPriorityRange(&lo, &hi);
+    CK(cudaStreamCreateWithPriority(&stream2_, cudaStreamDefault, hi));
+  }
   CK(cudaEventCreateWithFlags(&ev_fork_, cudaEventDisableTiming));
   CK(cudaEventCreateWithFlags(&ev_join_, cudaEventDisableTiming));
   {
@@ -135,13 +142,14 @@ Batch::Batch(const Params& p, int n) : p_(p), B_(n) {
   CK(cudaMalloc(&dLs_, nB * ORCVIO_LEG * ORCVIO_LEG * sizeof(double)));
   CK(cudaMalloc(&dFilterRows_, nB * sizeof(int)));
   CK(cudaMemset(dFilterRows_, 0, nB * sizeof(int)));
-  CK(cudaMalloc(&dSyrkCnt_, nB * 16 * sizeof(unsigned int)));
-  CK(cudaMemset(dSyrkCnt_, 0, nB * 16 * sizeof(unsigned int)));
+  CK(cudaMalloc(&dSyrkCnt_, nB * SY_MAXP * (SY_MAXG + 1) * sizeof(unsigned int)));
+  CK(cudaMemset(dSyrkCnt_, 0, nB * SY_MAXP * (SY_MAXG + 1) * sizeof(unsigned int)));
   {
     int dev = 0;
     cudaGetDevice(&dev);
     if (cudaDeviceGetAttribute(&n_sm_, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n_sm_ < 1) n_sm_ = 148;
     if (const char* e = std::getenv("ORCVIO_SYRK_WAVES")) syrk_waves_ = std::max(1, std::atoi(e));
+    syrk_group_ = std::max(1, env_int("ORCVIO_SYRK_GROUP", 8));
   }
   CK(cudaMalloc(&dErr_, sizeof(int)));
   CK(cudaMemset(dErr_, 0, sizeof(int)));
@@ -322,16 +330,16 @@ void Batch::stage_phase(PhaseWork& w) {
       tilerows_cap_ = w.tiles.size() * 2 + 64;
       CK(cudaMalloc(&dTileRows_, tilerows_cap_ * sizeof(int)));
     }
-    int chunks = 1;
-    for (const FilterWork& f : w.fw) chunks = std::max(chunks, syrk_chunks(f.arows, f.N, n_sm_ * syrk_waves_));
-    const int nt64 = (6 * w.maxN + 1 + 63) / 64, pairs = nt64 * (nt64 + 1) / 2;
+    int units = 1;
+    for (const FilterWork& f : w.fw) units = std::max(units, syrk_plan(f, n_sm_ * syrk_waves_).total);
+    w.syrk_units = units;
     const size_t need_a = (w.arows_total + 16) * (size_t)ldr_;
     if (need_a > amat_cap_) {
       if (dAmat_) cudaFree(dAmat_);
       amat_cap_ = need_a * 2;
       CK(cudaMalloc(&dAmat_, amat_cap_ * sizeof(double)));
     }
-    const size_t need_p = (size_t)B_ * chunks * pairs * 4096;
+    const size_t need_p = (size_t)B_ * units * 4096;
     if (need_p > part_cap_) {
       if (dPart_) cudaFree(dPart_);
       part_cap_ = need_p * 2;
@@ -375,7 +383,17 @@ void Batch::launch_phase(PhaseWork& w, bool download, bool prior_in_flight) {
   if (profiling_) CK(cudaEventRecord(e[0], stream_));
   const bool do_update = w.any_active && !skip_update_;
   const bool use_qr = compress_qr_;
-  if (do_update && !use_qr && !prior_in_flight) CK(cudaEventRecord(ev_fork_, stream_));
+  if (do_update && !use_qr && !prior_in_flight) {
+    // the prior factor depends on P alone: start it BEFORE the feature kernels are queued, otherwise its one
+    // big CTA waits for an empty SM behind the first waves of k_triangulate
+    CK(cudaEventRecord(ev_fork_, stream_));
+    InfoBufs ib{};
+    ib.Ls = dLs_;
+    launch_info_prior(upd_args(dFw), ib, w.maxN, stream2_, ev_fork_, ev_join_, profiling_ ? e[9] : nullptr,
+                      profiling_ ? e[10] : nullptr);
+    ++nl;
+    prior_in_flight = true;
+  }
   if (want_iters_ && (size_t)nC > iters_cap_) {
     if (dIters_) cudaFree(dIters_);
     if (dCost_) cudaFree(dCost_);
@@ -440,12 +458,9 @@ void Batch::launch_phase(PhaseWork& w, bool download, bool prior_in_flight) {
       if (profiling_) CK(cudaEventRecord(e[4], stream_));
       launch_update(ua, w.maxN, stream_, &nl);
     } else {
-      int chunks = 1;
-      for (const FilterWork& f : w.fw) chunks = std::max(chunks, syrk_chunks(f.arows, f.N, n_sm_ * syrk_waves_));
-      const int nt64 = (6 * w.maxN + 1 + 63) / 64, pairs = nt64 * (nt64 + 1) / 2;
       InfoBufs ib{};
       ib.Ls = dLs_; ib.Amat = dAmat_; ib.part = dPart_;
-      ib.max_chunks = chunks; ib.max_pairs = pairs; ib.cta_budget = n_sm_ * syrk_waves_; ib.syrk_cnt = dSyrkCnt_;
+      ib.max_units = w.syrk_units; ib.cta_budget = n_sm_ * syrk_waves_; ib.group = syrk_group_; ib.syrk_cnt = dSyrkCnt_;
       ib.tile_rows = dTileRows_; ib.filter_rows = dFilterRows_;
       launch_info_update(qa, ua, ib, (int)w.tiles.size(), w.max_tile_rows, w.wmax_blk, w.maxN, stream_,
                          stream2_, ev_fork_, ev_join_, profiling_ ? e[3] : nullptr, profiling_ ? e[4] : nullptr, &nl,
@@ -506,6 +521,11 @@ static void build_tiles(Batch::PhaseWork& w, int fi, int c0, int c1) {
   }
   fw.tile_end = (int)w.tiles.size();
   fw.arows = (int)w.arows_total - fw.arow0;
+  // staircase of A = [r' | H' L]: a tile with window [c0, c1) fills the columns 0 .. 6 c1 of its rows
+  for (int J = 0; J < SY_MAXT; ++J) fw.jrow0[J] = fw.arows;
+  for (int t = fw.tile_begin; t < fw.tile_end; ++t)
+    for (int J = 0; J < SY_MAXT; ++J)
+      if (6 * w.tiles[t].c1_blk >= SY_TILE * J) fw.jrow0[J] = std::min(fw.jrow0[J], w.tiles[t].arow - fw.arow0);
 }
 
 // Append one filter's candidates (sorted by first clone, then id) to the phase work list.

@@ -197,7 +197,7 @@ class Batch {
   double* dLs_ = nullptr;
   int *dTileRows_ = nullptr, *dFilterRows_ = nullptr;
   unsigned int* dSyrkCnt_ = nullptr;   // split-K arrival counters of k_syrk
-  int n_sm_ = 148, syrk_waves_ = 1;
+  int n_sm_ = 148, syrk_waves_ = 1, syrk_group_ = 8;
   float last_syrk_us_ = 0.f, last_prior_us_ = 0.f;
   size_t tilerows_cap_ = 0;
   cudaEvent_t ev_[16];

@@ -89,36 +89,39 @@ __device__ __forceinline__ void chol_init(double* __restrict__ A, CholShared& cs
     }
 }
 
-// Scatter rows [row_begin, row_end) of the tall matrix into the tiles: value = get(i, j) for
-// j < ncols(i) (ncols(i) = i + 1 for triangle rows, m for carried rows).  Two rows x 7 column chunks
-// of 32 per warp step: 14 independent global loads in flight before the first shared store.
-template <class Get>
-__device__ __forceinline__ void chol_load_rows(double* __restrict__ A, int m, int row_begin, int row_end, Get get) {
+// 1/sqrt(x) for a normal positive x: hardware seed (2^-22) + two Newton steps, branch-free.
+__device__ __forceinline__ double chol_rsqrt(double x) {
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  const double xh = 0.5 * x;
+  double e = fma(-xh * y, y, 0.5);
+  y = fma(y, e, y);
+  e = fma(-xh * y, y, 0.5);
+  return fma(y, e, y);
+}
+
+__device__ __forceinline__ void chol_cp_async8(double* smem_dst, const double* gsrc) {
+  const unsigned int d = (unsigned int)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void chol_cp_async_wait() {
+  asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+}
+
+// Scatter rows [row_begin, row_end) of the tall matrix into the tiles: element (i, j) comes from the global
+// address addr(i, j), j < ncols(i) (ncols(i) = i + 1 for triangle rows, m for carried rows).  Every element is
+// one 8-byte cp.async straight into its tile slot, so ALL loads of the CTA are in flight together (one
+// memory round trip for the whole matrix instead of one per row batch).  The tiles must have been zeroed
+// (chol_init) and made visible (__syncthreads) before; the caller finishes with chol_cp_async_wait() +
+// __syncthreads().
+template <class Addr>
+__device__ __forceinline__ void chol_load_rows(double* __restrict__ A, int m, int row_begin, int row_end, Addr addr) {
   const int Tm = (m + 7) >> 3;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
-  constexpr int NCH = (CHOL_MAXM + 31) / 32;
-  for (int i0 = row_begin + 2 * warp; i0 < row_end; i0 += 2 * nw) {
-    double v[2][NCH];
-#pragma unroll
-    for (int r = 0; r < 2; ++r) {
-      const int i = i0 + r;
-      const int nc = (i < row_end) ? min(i + 1, m) : 0;
-#pragma unroll
-      for (int c = 0; c < NCH; ++c) {
-        const int j = lane + 32 * c;
-        v[r][c] = (j < nc) ? get(i, j) : 0.0;
-      }
-    }
-#pragma unroll
-    for (int r = 0; r < 2; ++r) {
-      const int i = i0 + r;
-      const int nc = (i < row_end) ? min(i + 1, m) : 0;
-#pragma unroll
-      for (int c = 0; c < NCH; ++c) {
-        const int j = lane + 32 * c;
-        if (j < nc) A[chol_at(i, j, Tm)] = v[r][c];
-      }
-    }
+  for (int i = row_begin + warp; i < row_end; i += nw) {
+    const int nc = min(i + 1, m);
+    const int tbase = chol_tile(i >> 3, 0, Tm) * 64 + (i & 7) * 8;
+    for (int j = lane; j < nc; j += 32) chol_cp_async8(A + tbase + (j >> 3) * 64 + (j & 7), addr(i, j));
   }
 }
 
@@ -163,26 +166,38 @@ __device__ void cta_cholesky(double* __restrict__ A, CholShared& cs, const doubl
 #pragma unroll
         for (int b = 0; b < CHB; ++b)
           if (a >= nb || b >= nb) d[b] = (a == b) ? 1.0 : 0.0;
-        // Unscaled (L D L^T) elimination: the dependent chain per pivot is shuffle -> reciprocal ->
-        // multiply -> FMA; the 8 rsqrt that turn it into L = U D^-1/2 run afterwards, in parallel.
-        double ivs[CHB];
+        // Unscaled (L D L^T) elimination, branch-free.  The dependent chain per pivot is
+        //   shuffle -> reciprocal seed -> 2 FMA (one Newton step) -> multiply -> FMA (second Newton step folded
+        //   into w = u / pivot) -> FMA into the next pivot;
+        // thresholds are preloaded, rejected pivots are handled by selects.  The 8 rsqrt that turn the
+        // result into L = U D^-1/2 run afterwards, in parallel.
+        double thr[CHB], ivs[CHB];
+#pragma unroll
+        for (int c = 0; c < CHB; ++c) thr[c] = (tol != nullptr && c < nb) ? tol[k0 + c] : 0.0;
 #pragma unroll
         for (int c = 0; c < CHB; ++c) {
           const double pv = __shfl_sync(0xffffffffu, d[c], c, 8);
-          const bool ok = tol ? (c < nb ? pv > tol[k0 + c] : true) : (pv > 0.0);
-          const double rc = ok ? chol_rcp(pv) : 0.0;
-          ivs[c] = ok ? pv : 0.0;
+          const bool ok = pv > thr[c];
           const double u = d[c];
-          const double w = u * rc;
+          double y0;
+          asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y0) : "d"(pv));
+          const double e = fma(-pv, y0, 1.0);
+          const double y1 = fma(y0, e, y0);                   // 1/pv (1 - e^2)
+          const double e2 = e * e;
+          const double t = u * y1;
+          double w = fma(t, e2, t);                           // u / pv to working precision
+          w = ok ? w : 0.0;
+          ivs[c] = ok ? pv : 0.0;
 #pragma unroll
           for (int b = c + 1; b < CHB; ++b) {
             const double ub = __shfl_sync(0xffffffffu, u, b, 8);
-            d[b] -= w * ub;                                   // meaningful for a >= b
+            d[b] = fma(-w, ub, d[b]);                         // meaningful for a >= b
           }
         }
 #pragma unroll
         for (int c = 0; c < CHB; ++c) {
-          ivs[c] = (ivs[c] > 0.0) ? rsqrt(ivs[c]) : 0.0;
+          const double rs = chol_rsqrt(ivs[c] > 0.0 ? ivs[c] : 1.0);
+          ivs[c] = (ivs[c] > 0.0) ? rs : 0.0;
           d[c] *= ivs[c];
         }
         if (lane < CHB) {
@@ -218,29 +233,39 @@ __device__ void cta_cholesky(double* __restrict__ A, CholShared& cs, const doubl
             dl[c][q] = t.x;
             if (q + 1 < c) dl[c][q + 1] = t.y;
           }
+        // up to two rows per thread (mrows <= 244), both chains in flight together
+        const int i0r = ibase + tid, i1r = i0r + CHOL_PANEL_THREADS;
+        const bool two = i1r < mrows;
+        double* xt0 = A + (size_t)chol_tile(i0r >> 3, p, Tm) * 64 + (i0r & 7) * 8;
+        double* xt1 = two ? A + (size_t)chol_tile(i1r >> 3, p, Tm) * 64 + (i1r & 7) * 8 : xt0;
+        double x0[CHB], x1[CHB];
 #pragma unroll
-        for (int s = 0; s < 2; ++s) {
-          const int i = ibase + tid + s * CHOL_PANEL_THREADS;
-          if (i >= mrows) break;
-          double* xt = A + (size_t)chol_tile(i >> 3, p, Tm) * 64 + (i & 7) * 8;
-          double x[CHB];
+        for (int c = 0; c < CHB; c += 2) {
+          const double2 t0 = *reinterpret_cast<const double2*>(xt0 + c);
+          const double2 t1 = *reinterpret_cast<const double2*>(xt1 + c);
+          x0[c] = t0.x; x0[c + 1] = t0.y;
+          x1[c] = t1.x; x1[c + 1] = t1.y;
+        }
 #pragma unroll
-          for (int c = 0; c < CHB; c += 2) {
-            const double2 t = *reinterpret_cast<const double2*>(xt + c);
-            x[c] = t.x;
-            x[c + 1] = t.y;
+        for (int c = 0; c < CHB; ++c) {
+          if (c >= nb) { x0[c] = 0.0; x1[c] = 0.0; }
+          x0[c] *= di[c];
+          x1[c] *= di[c];
+#pragma unroll
+          for (int q = c + 1; q < CHB; ++q) {
+            x0[q] -= x0[c] * dl[q][c];
+            x1[q] -= x1[c] * dl[q][c];
           }
+        }
 #pragma unroll
-          for (int c = 0; c < CHB; ++c) {
-            if (c >= nb) x[c] = 0.0;
-            x[c] *= di[c];
+        for (int c = 0; c < CHB; ++c) PTn[c][i0r] = x0[c];
 #pragma unroll
-            for (int q = c + 1; q < CHB; ++q) x[q] -= x[c] * dl[q][c];
-          }
+        for (int c = 0; c < CHB; c += 2) *reinterpret_cast<double2*>(xt0 + c) = make_double2(x0[c], x0[c + 1]);
+        if (two) {
 #pragma unroll
-          for (int c = 0; c < CHB; ++c) PTn[c][i] = x[c];
+          for (int c = 0; c < CHB; ++c) PTn[c][i1r] = x1[c];
 #pragma unroll
-          for (int c = 0; c < CHB; c += 2) *reinterpret_cast<double2*>(xt + c) = make_double2(x[c], x[c + 1]);
+          for (int c = 0; c < CHB; c += 2) *reinterpret_cast<double2*>(xt1 + c) = make_double2(x1[c], x1[c + 1]);
         }
       }
       if (PROF && tid == 0) prof[p * 8 + 3] = clock64();
@@ -296,14 +321,23 @@ __device__ void cta_cholesky(double* __restrict__ A, CholShared& cs, const doubl
             tj = p + 1 + (q - (q / nT) * nT);
           }
         }
+        // the A operand depends on the tile row only: it is reloaded when the row changes (row-major
+        // stepping), which takes a quarter of the shared-memory traffic of a tile out of the loop
+        int ti_a = -1;
+        double a0c = 0.0, a1c = 0.0;
         for (int t0 = tw * per; t0 < tend; t0 += IL) {
           double2 cv[IL];
           double a0[IL], a1[IL], b0[IL], b1[IL];
           double2* cp[IL];
 #pragma unroll
           for (int u = 0; u < IL; ++u) {
-            a0[u] = -PTp[fk][ti * 8 + fr];
-            a1[u] = -PTp[fk + 4][ti * 8 + fr];
+            if (ti != ti_a) {
+              a0c = -PTp[fk][ti * 8 + fr];
+              a1c = -PTp[fk + 4][ti * 8 + fr];
+              ti_a = ti;
+            }
+            a0[u] = a0c;
+            a1[u] = a1c;
             b0[u] = PTp[fk][tj * 8 + fr];
             b1[u] = PTp[fk + 4][tj * 8 + fr];
             cp[u] = reinterpret_cast<double2*>(A + (size_t)chol_tile(ti, tj, Tm) * 64) + lane;

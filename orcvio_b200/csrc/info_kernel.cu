@@ -55,12 +55,13 @@ __global__ void __launch_bounds__(CHOL_THREADS) k_chol_prior(UpdArgs a, double* 
   chol_init(A, cs, D, 0);
   __syncthreads();
   const int ldp = a.ldp;
-  chol_load_rows(A, D, 0, D, [&](int i, int j) { return P[(size_t)orig(i) * ldp + orig(j)]; });
+  chol_load_rows(A, D, 0, D, [&](int i, int j) { return P + (size_t)orig(i) * ldp + orig(j); });
   for (int i = tid; i < D; i += nt) tol[i] = 1e-12 * fabs(P[(size_t)orig(i) * (ldp + 1)]);
   for (int i = tid; i < L * L; i += nt) Ls[i] = 0.0;
   // entries above the diagonal of F are structural zeros: FT[k][orig(i)] = 0 for i < k
   for (int k = warp; k < n; k += nw)
     for (int i = lane; i < k; i += 32) FT[(size_t)k * a.ldt + L + i] = 0.0;
+  chol_cp_async_wait();
   cta_cholesky(A, cs, tol, D, 0);
   const int ldt = a.ldt;
   chol_for_rows(A, D, 0, 0, [&](int i, int k, double l) {
@@ -69,25 +70,33 @@ __global__ void __launch_bounds__(CHOL_THREADS) k_chol_prior(UpdArgs a, double* 
   });
 }
 
-// ---------------------------------------------------------------- A = [H' L | r']
-// One CTA per row tile (features sorted by first clone; window [c0, c1) of clone blocks).
-// The gated rows are assembled densely in shared memory; thread j owns column j of A and keeps
-// its column of L (the window rows) in registers.
-constexpr int AF_THREADS = 192;
+// ---------------------------------------------------------------- A = [r' | H' L]   (FP64 tensor cores)
+// One CTA per row tile (features sorted by first clone; window [c0, c1) of clone blocks, <= 64 rows).
+// The gated rows are assembled densely in shared memory (Hs, rows x W); the tile of A is the product
+// Hs (rows x W) * Lwin (W x 6 c1) with Lwin = L[6 c0 .. 6 c1, 0 .. 6 c1): L is lower triangular, so A is
+// structurally zero right of column 6 c1 (the staircase k_syrk exploits).  Every warp owns 8-column
+// fragments of A: the B operand (8 columns of L over the window rows) is read once from the prior factor
+// into registers, the A operand comes from shared memory (row stride == 4 mod 8: conflict-free 64-bit
+// fragment loads), eight m8n8k4 accumulators (64 rows) are in flight per warp.
+// Column layout of A: column 0 = projected residual r', column 1 + j = (H' L)[:, j].
+constexpr int AF_THREADS = 192;              // x 3 CTAs per SM (launch bound): the tiles of a 4096-feature frame in one wave
+constexpr int AF_KS = 9;                     // k-steps (of 4) per register chunk of the B operand: 36 columns
 
-template <int WMAX>          // widest window handled (clone blocks x 6): 36 (max_track_len 6) or 48
-__global__ void __launch_bounds__(AF_THREADS) k_aform(QrArgs a, const double* FT_all, size_t t_stride, int ldt,
+__device__ __forceinline__ int aform_stride(int W) {          // smallest stride >= W with stride % 8 == 4
+  const int k4 = (W + 3) & ~3;
+  return (k4 & 7) == 4 ? k4 : k4 + 4;
+}
+
+__global__ void __launch_bounds__(AF_THREADS, 3) k_aform(QrArgs a, const double* FT_all, size_t t_stride, int ldt,
                                                       double* Amat, int lda, int* tile_rows) {
   extern __shared__ double smem[];
   __shared__ int rowbase[256];
-  __shared__ int wsum[8];
+  __shared__ int wsum[AF_THREADS / 32];
+  __shared__ double res[AFORM_TILE_ROWS];
   const Tile tl = a.tiles[blockIdx.x];
   const FilterWork fw = a.fw[tl.filter];
-  const int n = 6 * fw.N;
   const int W = 6 * (tl.c1_blk - tl.c0_blk);
-  const int nchunk = (W + WMAX - 1) / WMAX;  // windows wider than WMAX columns are processed in chunks
-  const int WR = nchunk * WMAX;              // column of the residual
-  const int Wp = WR + 2;                     // even stride, zero padded
+  const int Wp = aform_stride(W);
   const int tid = threadIdx.x, nt = blockDim.x;
   const int warp = tid >> 5, lane = tid & 31, nw = nt >> 5;
   const int nc = tl.cand_end - tl.cand_begin;      // host guarantees nc <= 256
@@ -115,9 +124,10 @@ __global__ void __launch_bounds__(AF_THREADS) k_aform(QrArgs a, const double* FT
   }
   const int m = total;
   if (tid == 0) tile_rows[blockIdx.x] = m;
-  const int rows_ub = tl.rows;
-  const int rows4 = (rows_ub + 3) & ~3;      // rows are processed four at a time
-  for (int e = tid; e < rows4 * Wp; e += nt) smem[e] = 0.0;
+  const int rows_ub = tl.rows;                     // <= AFORM_TILE_ROWS
+  const int rows8 = (rows_ub + 7) & ~7;
+  for (int e = tid; e < rows8 * Wp; e += nt) smem[e] = 0.0;
+  if (tid < AFORM_TILE_ROWS) res[tid] = 0.0;
   __syncthreads();
   for (int q = warp; q < nc; q += nw) {
     if (rowbase[q] < 0) continue;
@@ -127,93 +137,127 @@ __global__ void __launch_bounds__(AF_THREADS) k_aform(QrArgs a, const double* FT
     const int w = 6 * (cd.e_blk - cd.s_blk + 1);
     const int coff = 6 * (cd.s_blk - tl.c0_blk);
     const double* hb = a.hblk + cd.hblk_off;
+#pragma unroll 4
     for (int e = lane; e < r * w; e += 32) {
       const int i = e / w, j = e - i * w;
       smem[(size_t)(rowbase[q] + i) * Wp + coff + j] = hb[e];
     }
-    for (int i = lane; i < r; i += 32) smem[(size_t)(rowbase[q] + i) * Wp + WR] = a.rblk[cd.row_off + i];
+    for (int i = lane; i < r; i += 32) res[rowbase[q] + i] = a.rblk[cd.row_off + i];
   }
   __syncthreads();
-  // ---- thread j: column j of A for every row of the tile
+  // ---- fragments: A columns [8 cf, 8 cf + 8); A column ac <-> column ac - 1 of L
+  const int ncol_nz = 6 * tl.c1_blk + 1;           // structurally non-zero columns of A for this tile
+  const int ncf = (ncol_nz + 7) >> 3;
+  const int fr = lane >> 2, fk = lane & 3;
   const double* FT = FT_all + (size_t)tl.filter * t_stride;
   double* Arow = Amat + (size_t)tl.arow * lda;
-  for (int j = tid; j <= n; j += nt) {
-    if (j == n) {                                      // residual column
-      for (int row = 0; row < rows_ub; ++row) Arow[(size_t)row * lda + n] = smem[(size_t)row * Wp + WR];
-      continue;
+  const int nrf = rows8 >> 3;                      // row fragments (<= 8)
+  // flat sequence of steps (column fragment, 36-column chunk of the window); the B operand of step s + 1 is
+  // fetched from the prior factor (L2) while the MMAs of step s run
+  const int nchunk = (W + 4 * AF_KS - 1) / (4 * AF_KS);
+  const int nsteps = ((ncf - warp + nw - 1) / nw) * nchunk;      // steps of this warp (ncf > warp, else <= 0)
+  auto load_b = [&](int step, double* b) {
+    const int cf = warp + nw * (step / nchunk), k0 = (step % nchunk) * 4 * AF_KS;
+    const int jl = 8 * cf + fr - 1;                  // column of L behind this lane's B elements
+    const bool jok = (jl >= 0) && (jl < 6 * tl.c1_blk);
+    // L[k][jl] = FT[jl][22 + k] (zero above the diagonal, stored explicitly), k = 6 c0 + window column
+    const double* src = FT + (size_t)(jok ? jl : 0) * ldt + ORCVIO_LEG + 6 * tl.c0_blk;
+#pragma unroll
+    for (int s2 = 0; s2 < AF_KS; ++s2) {
+      const int k = k0 + 4 * s2 + fk;
+      b[s2] = (jok && k < W) ? src[k] : 0.0;
     }
-    if (j >= 6 * tl.c1_blk) {                          // every window row lies above the diagonal of L
-      for (int row = 0; row < rows_ub; ++row) Arow[(size_t)row * lda + j] = 0.0;
-      continue;
+  };
+  double bn[AF_KS];
+  if (nsteps > 0) load_b(0, bn);
+  double2 acc[8];
+  for (int step = 0; step < nsteps; ++step) {
+    const int cf = warp + nw * (step / nchunk), ch = step % nchunk, k0 = ch * 4 * AF_KS;
+    double b[AF_KS];
+#pragma unroll
+    for (int s2 = 0; s2 < AF_KS; ++s2) b[s2] = bn[s2];
+    if (step + 1 < nsteps) load_b(step + 1, bn);
+    if (ch == 0) {
+#pragma unroll
+      for (int u = 0; u < 8; ++u) acc[u] = make_double2(0.0, 0.0);
     }
-    for (int ch = 0; ch < nchunk; ++ch) {
-      double Lw[WMAX];
-      // L[k][j] = FT[j][22 + k], k = 6 c0 + ch WMAX + c  (zero above the diagonal: k < j)
-      const double* src = FT + (size_t)j * ldt + ORCVIO_LEG + 6 * tl.c0_blk + ch * WMAX;
 #pragma unroll
-      for (int c = 0; c < WMAX; ++c) Lw[c] = (ch * WMAX + c < W) ? src[c] : 0.0;
-      for (int row = 0; row < rows4; row += 4) {
-        const double* h0 = smem + (size_t)row * Wp + ch * WMAX;
-        double s[4][2] = {{0, 0}, {0, 0}, {0, 0}, {0, 0}};
+    for (int s2 = 0; s2 < AF_KS; ++s2) {
+      if (k0 + 4 * s2 < W) {
+        const double* hs = smem + (size_t)fr * Wp + k0 + 4 * s2 + fk;
 #pragma unroll
-        for (int c = 0; c < WMAX; c += 2) {
+        for (int u = 0; u < 8; ++u)
+          if (u < nrf) dmma884(acc[u].x, acc[u].y, hs[(size_t)(8 * u) * Wp], b[s2]);
+      }
+    }
+    if (ch == nchunk - 1) {
 #pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            const double2 h2 = *reinterpret_cast<const double2*>(h0 + (size_t)u * Wp + c);
-            s[u][0] += h2.x * Lw[c];
-            s[u][1] += h2.y * Lw[c + 1];
-          }
+      for (int u = 0; u < 8; ++u) {
+        const int row = 8 * u + fr;
+        if (u < nrf && row < rows_ub) {
+          double2 v = acc[u];
+          if (cf == 0 && fk == 0) v.x = res[row];    // column 0: the projected residual
+          *reinterpret_cast<double2*>(Arow + (size_t)row * lda + 8 * cf + 2 * fk) = v;
         }
-#pragma unroll
-        for (int u = 0; u < 4; ++u)
-          if (row + u < rows_ub) {
-            double* dst = Arow + (size_t)(row + u) * lda + j;
-            *dst = (ch == 0) ? (s[u][0] + s[u][1]) : (*dst + (s[u][0] + s[u][1]));
-          }
       }
     }
   }
-  // padding columns (n, lda) are never read
+  // ---- explicit zeros right of the staircase, as far as k_syrk reads this tile's rows: column tile J is read
+  // from row jrow0[J] on, and tiles are not strictly ordered by c1
+  int zend = 8 * ncf;
+  for (int J = 0; J < SY_MAXT; ++J)
+    if (fw.jrow0[J] <= tl.arow - fw.arow0) zend = max(zend, min(lda, SY_TILE * (J + 1)));
+  const int z0 = 8 * ncf, zw = zend - z0;
+  if (zw > 0)
+    for (int e = tid; e < rows_ub * zw; e += nt) {
+      const int row = e / zw, c = e - row * zw;
+      Arow[(size_t)row * lda + z0 + c] = 0.0;
+    }
 }
 
-// Dense variant for the object update: A = [Hp L | r'] for a projected dense block Hp (rows x n,
-// row-major with leading dimension ldh, residual in column n).
+// Dense variant for the object update: A = [r' | Hp L] for a projected dense block Hp (rows x n,
+// row-major with leading dimension ldh, residual in column n of Hp).
 __global__ void __launch_bounds__(256) k_aform_dense(const double* Hp, int ldh, int rows, int n, const double* FT,
                                                      int ldt, double* Amat, int lda) {
   const int row = blockIdx.x;
   if (row >= rows) return;
   const double* h = Hp + (size_t)row * ldh;
   for (int j = threadIdx.x; j <= n; j += blockDim.x) {
-    if (j == n) { Amat[(size_t)row * lda + n] = h[n]; continue; }
+    if (j == n) { Amat[(size_t)row * lda] = h[n]; continue; }
     // L[k][j] = FT[j][22 + k], zero for k < j
     const double* src = FT + (size_t)j * ldt + ORCVIO_LEG;
     double s0 = 0.0, s1 = 0.0;
     int k = j;
     for (; k + 1 < n; k += 2) { s0 += h[k] * src[k]; s1 += h[k + 1] * src[k + 1]; }
     if (k < n) s0 += h[k] * src[k];
-    Amat[(size_t)row * lda + j] = s0 + s1;
+    Amat[(size_t)row * lda + 1 + j] = s0 + s1;
   }
+  // columns (n, lda) of the last column tile must read as zeros in k_syrk
+  for (int c = n + 1 + threadIdx.x; c < lda; c += blockDim.x) Amat[(size_t)row * lda + c] = 0.0;
 }
 
 // ---------------------------------------------------------------- W_aug = s^2 I + A^T A  (FP64 tensor cores)
-// grid (tile pairs I <= J, row chunks, filters).  A CTA owns one 64 x 64 tile of A^T A over one chunk of
-// rows: 8 warps x (32 x 16) warp tiles = 4 x 2 accumulator fragments of mma.m8n8k4.f64 per warp, operands
-// staged through shared memory in 32-row slabs (row stride 68 doubles: the four k-rows of a fragment
-// start 8 banks apart, so the 64-bit fragment loads are conflict-free).  Split-K: every chunk stores its
-// partial tile; the LAST chunk to arrive (device-scope counter) adds the partials in chunk order -- a
-// fixed summation order, so the result is bitwise reproducible -- and writes the lower triangle of
-// W_aug ((n+1) x ldr, UpdArgs::S) with s^2 on the first n diagonal entries; row n = v = A^T r'.
-// The rows per chunk adapt to the filter so that pairs x chunks fills the SMs once (syrk_rows_per_chunk).
-constexpr int SY_T = 64, SY_KS = 32, SY_LD = 68;
+// grid (work units, filters).  A work unit is one 64 x 64 tile (I <= J) of A^T A over one chunk of rows
+// (syrk_plan): pair (I, J) only covers the rows [jrow0[J], arows) -- above them column tile J of A is
+// structurally zero.  8 warps x (32 x 16) warp tiles = 4 x 2 accumulator fragments of mma.m8n8k4.f64 per
+// warp, operands staged through shared memory in 32-row slabs (row stride 68 doubles: the four k-rows of
+// a fragment start 8 banks apart, so the 64-bit fragment loads are conflict-free).
+// Split-K, two levels, no atomics on data: every chunk stores its partial tile; the last chunk of a GROUP
+// to arrive (device-scope counter) adds the group's partials in chunk order and stores the group sum; the
+// last group to arrive adds the group sums in group order.  Grouping is static, so the summation order is
+// fixed and the result is bitwise reproducible.  The final reducer writes the lower triangle of
+// W_aug ((n+1) x ldr, UpdArgs::S): A's column 0 (the residual) maps to row n (v = A^T r', corner r'^T r'),
+// column 1 + j to index j, with s^2 added on the first n diagonal entries.
+constexpr int SY_T = SY_TILE, SY_KS = 32, SY_LD = 68;
 
 __global__ void __launch_bounds__(256) k_syrk(UpdArgs a, const double* __restrict__ Amat, int lda, double* part,
-                                              int max_chunks, int max_pairs, int cta_budget, const Tile* tiles,
+                                              int max_units, int cta_budget, int group, const Tile* tiles,
                                               const int* tile_rows, int* filter_rows, unsigned int* counters) {
-  const int fi = blockIdx.z;
+  const int fi = blockIdx.y;
   const FilterWork fw = a.fw[fi];
   const int tid = threadIdx.x;
-  const int pidx = blockIdx.x, chunk = blockIdx.y;
-  if (pidx == 0 && chunk == 0 && tid == 0) {             // gated rows of this filter (k_pinfo skips P when 0)
+  const int unit = blockIdx.x;
+  if (unit == 0 && tid == 0) {                           // gated rows of this filter (k_pinfo skips P when 0)
     int rows = 0;
     if (fw.active) {
       if (tiles == nullptr) rows = fw.arows;             // dense (object) update: every row counts
@@ -223,23 +267,22 @@ __global__ void __launch_bounds__(256) k_syrk(UpdArgs a, const double* __restric
   }
   if (!fw.active) return;
   const int n = 6 * fw.N, n1 = n + 1;
-  const int nt_ = (n1 + SY_T - 1) / SY_T;
-  // pair index -> (I, J), I <= J
-  int I = 0, J = 0;
+  const SyrkPlan pl = syrk_plan(fw, cta_budget);
+  if (unit >= pl.total) return;
+  // work unit -> pair (I, J), I <= J, and chunk
+  int I = 0, J = 0, pidx = 0;
   {
-    int cnt = 0;
-    bool found = false;
-    for (int ii = 0; ii < nt_ && !found; ++ii)
-      for (int jj = ii; jj < nt_; ++jj) {
-        if (cnt == pidx) { I = ii; J = jj; found = true; break; }
-        ++cnt;
+    int q = 0;
+    for (int ii = 0; ii < pl.nt; ++ii)
+      for (int jj = ii; jj < pl.nt; ++jj) {
+        if (unit >= pl.first[q]) { I = ii; J = jj; pidx = q; }
+        ++q;
       }
-    if (!found) return;
   }
-  const int kc = syrk_rows_per_chunk(fw.arows, fw.N, cta_budget);
-  const int nchunks = syrk_chunks(fw.arows, fw.N, cta_budget);
-  if (chunk >= nchunks) return;
-  const int row_begin = chunk * kc;
+  const int chunk = unit - pl.first[pidx];
+  const int nchunks = pl.first[pidx + 1] - pl.first[pidx];
+  const int kc = pl.kc;
+  const int row_begin = min(fw.arows, fw.jrow0[J] + chunk * kc);
   const int row_end = min(fw.arows, row_begin + kc);
   const double* A = Amat + (size_t)fw.arow0 * lda;
   __shared__ __align__(16) double As[SY_KS][SY_LD];
@@ -295,14 +338,16 @@ __global__ void __launch_bounds__(256) k_syrk(UpdArgs a, const double* __restric
         for (int v = 0; v < 2; ++v) dmma884(acc[u][v].x, acc[u][v].y, af[u], bf[v]);
     }
   }
-  // tile element (ii, jj) = W[i0 + ii][j0 + jj]; fragment (u, v): ii = wi + 8u + fr, jj = wj + 8v + 2fk (+1)
+  // tile element (ii, jj) = (A^T A)[i0 + ii][j0 + jj]; fragment (u, v): ii = wi + 8u + fr, jj = wj + 8v + 2fk (+1)
   double* S = a.S + (size_t)fi * a.r_stride;
-  auto emit = [&](int ii, int jj, double s) {            // lower triangle of W_aug: row = larger index
-    const int gi = j0 + jj, gj = i0 + ii;
-    if (gi >= n1 || gj > gi) return;
-    if (gi == gj && gi < n) s += a.sigma2;
-    S[(size_t)gi * a.ldr + gj] = s;
+  auto emit = [&](int ii, int jj, double s) {
+    const int ga = i0 + ii, gb = j0 + jj;                // columns of A, each unordered pair once: ga <= gb
+    if (gb > n || ga > gb) return;
+    if (ga == 0) { S[(size_t)n * a.ldr + (gb == 0 ? n : gb - 1)] = s; return; }   // v = A^T r', corner r'^T r'
+    if (ga == gb) s += a.sigma2;
+    S[(size_t)(gb - 1) * a.ldr + (ga - 1)] = s;          // lower triangle of W
   };
+  (void)n1;
   if (nchunks == 1) {
 #pragma unroll
     for (int u = 0; u < 4; ++u)
@@ -313,36 +358,74 @@ __global__ void __launch_bounds__(256) k_syrk(UpdArgs a, const double* __restric
       }
     return;
   }
-  double* base = part + ((size_t)fi * max_chunks * max_pairs + pidx) * (SY_T * SY_T);
-  const size_t cstride = (size_t)max_pairs * (SY_T * SY_T);
+  double* base = part + ((size_t)fi * max_units + pl.first[pidx]) * (SY_T * SY_T);
+  const size_t cstride = (size_t)(SY_T * SY_T);
   double* out = base + (size_t)chunk * cstride;
 #pragma unroll
   for (int u = 0; u < 4; ++u)
 #pragma unroll
     for (int v = 0; v < 2; ++v)
       *reinterpret_cast<double2*>(out + (wi + 8 * u + fr) * SY_T + wj + 8 * v + 2 * fk) = acc[u][v];
+  // ---- level 1: the last chunk of a group sums the group (16 tile elements per thread)
+  int gsz = max(group, 1);
+  if ((nchunks + gsz - 1) / gsz > SY_MAXG) gsz = (nchunks + SY_MAXG - 1) / SY_MAXG;
+  const int ngroups = (nchunks + gsz - 1) / gsz;
+  const int g = chunk / gsz;
+  const int c_begin = g * gsz, c_end = min(nchunks, c_begin + gsz);
+  unsigned int* cnt = counters + ((size_t)fi * SY_MAXP + pidx) * (SY_MAXG + 1);
   __threadfence();
   __syncthreads();
-  unsigned int* cnt = counters + (size_t)fi * max_pairs + pidx;
-  if (tid == 0) s_last = (atomicAdd(cnt, 1u) == (unsigned int)(nchunks - 1));
+  if (tid == 0) s_last = (atomicAdd(cnt + 1 + g, 1u) == (unsigned int)(c_end - c_begin - 1));
   __syncthreads();
   if (!s_last) return;
   __threadfence();
-  // last chunk of this tile: sum the partials in chunk order (16 tile elements per thread)
   double s[16];
+  auto sum_slots = [&](int first, int last, int step) {   // slots first, first + step, ... < last, in order
 #pragma unroll
-  for (int q = 0; q < 16; ++q) s[q] = 0.0;
-  for (int c = 0; c < nchunks; ++c) {
-    const double* pc = base + (size_t)c * cstride + tid;
+    for (int q = 0; q < 16; ++q) s[q] = 0.0;
+    int c = first;
+    for (; c + step < last; c += 2 * step) {              // two slots in flight
+      const double* p0 = base + (size_t)c * cstride + tid;
+      const double* p1 = p0 + (size_t)step * cstride;
+      double x0[16], x1[16];
 #pragma unroll
-    for (int q = 0; q < 16; ++q) s[q] += __ldcg(pc + 256 * q);
+      for (int q = 0; q < 16; ++q) x0[q] = __ldcg(p0 + 256 * q);
+#pragma unroll
+      for (int q = 0; q < 16; ++q) x1[q] = __ldcg(p1 + 256 * q);
+#pragma unroll
+      for (int q = 0; q < 16; ++q) s[q] = (s[q] + x0[q]) + x1[q];
+    }
+    if (c < last) {
+      const double* p0 = base + (size_t)c * cstride + tid;
+#pragma unroll
+      for (int q = 0; q < 16; ++q) s[q] += __ldcg(p0 + 256 * q);
+    }
+  };
+  sum_slots(c_begin, c_end, 1);
+  if (ngroups > 1) {
+    // ---- level 2: the group sum replaces the group's first partial; the last group sums the groups
+    double* gout = base + (size_t)c_begin * cstride + tid;
+#pragma unroll
+    for (int q = 0; q < 16; ++q) __stcg(gout + 256 * q, s[q]);
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) {
+      cnt[1 + g] = 0u;
+      s_last = (atomicAdd(cnt, 1u) == (unsigned int)(ngroups - 1));
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    sum_slots(0, nchunks, gsz);
+    if (tid == 0) cnt[0] = 0u;
+  } else if (tid == 0) {
+    cnt[1 + g] = 0u;                                      // ready for the next launch
   }
 #pragma unroll
   for (int q = 0; q < 16; ++q) {
     const int e = tid + 256 * q;
     emit(e >> 6, e & 63, s[q]);
   }
-  if (tid == 0) *cnt = 0u;                               // ready for the next launch
 }
 
 // ---------------------------------------------------------------- W = C C^T with F_1, v carried; dx
@@ -373,11 +456,12 @@ __global__ void __launch_bounds__(CHOL_THREADS) k_chol_w_solve(UpdArgs a) {
   __syncthreads();
   const int ldr = a.ldr, ldt0 = a.ldt;
   // triangle rows: W;  carried rows: row n + q = F_1[d0 + q][:] = FT[:][d0 + q];  last row: v = S[n][:]
-  chol_load_rows(A, n, 0, n + nx, [&](int i, int j) {
-    if (i < n) return S[(size_t)i * ldr + j];
+  chol_load_rows(A, n, 0, n + nx, [&](int i, int j) -> const double* {
+    if (i < n) return S + (size_t)i * ldr + j;
     const int q = i - n;
-    return q < nd ? T[(size_t)j * ldt0 + d0 + q] : S[(size_t)n * ldr + j];
+    return q < nd ? T + (size_t)j * ldt0 + d0 + q : S + (size_t)n * ldr + j;
   });
+  chol_cp_async_wait();
   cta_cholesky(A, cs, nullptr, n, nx);
   const int ldt = a.ldt;
   const bool strip0 = (blockIdx.x == 0);
@@ -432,27 +516,59 @@ __global__ void __launch_bounds__(256) k_pinfo(UpdArgs a, const double* Ls_all, 
   double* P = a.P + (size_t)fi * a.p_stride;
   double* Ys_i = sm;                       // [n][PT]
   double* Ys_j = sm + (size_t)n * PT;
-  for (int e = tid; e < n * PT; e += 256) {
-    const int k = e / PT, c = e - k * PT;
-    Ys_i[e] = (i0 + c < D) ? Y[(size_t)k * a.ldt + i0 + c] : 0.0;
-    Ys_j[e] = (j0 + c < D) ? Y[(size_t)k * a.ldt + j0 + c] : 0.0;
+  // both strips with 16-byte cp.async: every load of the CTA is in flight at once (one L2 round trip)
+  {
+    const int ldt = a.ldt;
+    const bool same = (i0 == j0);
+    for (int e = tid; e < n * (PT / 2); e += 256) {
+      const int k = e / (PT / 2), c = 2 * (e - k * (PT / 2));
+      double* di_ = Ys_i + (size_t)k * PT + c;
+      double* dj_ = Ys_j + (size_t)k * PT + c;
+      if (i0 + c < ldt) {
+        const unsigned int d = (unsigned int)__cvta_generic_to_shared(di_);
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(Y + (size_t)k * ldt + i0 + c) : "memory");
+      } else {
+        *reinterpret_cast<double2*>(di_) = make_double2(0.0, 0.0);
+      }
+      if (same) continue;
+      if (j0 + c < ldt) {
+        const unsigned int d = (unsigned int)__cvta_generic_to_shared(dj_);
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(Y + (size_t)k * ldt + j0 + c) : "memory");
+      } else {
+        *reinterpret_cast<double2*>(dj_) = make_double2(0.0, 0.0);
+      }
+    }
+    asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+    if (same) Ys_j = Ys_i;
   }
   __syncthreads();
   const int tx = tid & 15, ty = tid >> 4;
-  double acc[2][2] = {{0, 0}, {0, 0}};
-#pragma unroll 4
-  for (int k = 0; k < n; ++k) {
+  // four interleaved partial sums per output: the k loop is 4 dependent-FMA chains of n/4 instead of one of n
+  double acc[4][2][2];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) { acc[q][0][0] = acc[q][0][1] = acc[q][1][0] = acc[q][1][1] = 0.0; }
+  int k = 0;
+  for (; k + 3 < n; k += 4) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const double2 av = *reinterpret_cast<const double2*>(Ys_i + (size_t)(k + q) * PT + 2 * ty);
+      const double2 bv = *reinterpret_cast<const double2*>(Ys_j + (size_t)(k + q) * PT + 2 * tx);
+      acc[q][0][0] += av.x * bv.x; acc[q][0][1] += av.x * bv.y;
+      acc[q][1][0] += av.y * bv.x; acc[q][1][1] += av.y * bv.y;
+    }
+  }
+  for (; k < n; ++k) {
     const double2 av = *reinterpret_cast<const double2*>(Ys_i + (size_t)k * PT + 2 * ty);
     const double2 bv = *reinterpret_cast<const double2*>(Ys_j + (size_t)k * PT + 2 * tx);
-    acc[0][0] += av.x * bv.x; acc[0][1] += av.x * bv.y;
-    acc[1][0] += av.y * bv.x; acc[1][1] += av.y * bv.y;
+    acc[0][0][0] += av.x * bv.x; acc[0][0][1] += av.x * bv.y;
+    acc[0][1][0] += av.y * bv.x; acc[0][1][1] += av.y * bv.y;
   }
   const double* Ls = Ls_all + (size_t)fi * L * L;
   for (int u = 0; u < 2; ++u)
     for (int v = 0; v < 2; ++v) {
       const int i = i0 + 2 * ty + u, j = j0 + 2 * tx + v;
       if (i >= D || j >= D) continue;
-      double s = a.sigma2 * acc[u][v];
+      double s = a.sigma2 * ((acc[0][u][v] + acc[1][u][v]) + (acc[2][u][v] + acc[3][u][v]));
       if (i < L && j < L) {
         double t = 0.0;
         for (int q = 0; q < L; ++q) t += Ls[i * L + q] * Ls[j * L + q];
@@ -465,8 +581,7 @@ __global__ void __launch_bounds__(256) k_pinfo(UpdArgs a, const double* Ls_all, 
 static void info_attrs() {
   static bool attr = false;
   if (attr) return;
-  cudaFuncSetAttribute(k_aform<36>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
-  cudaFuncSetAttribute(k_aform<48>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024);
+  cudaFuncSetAttribute(k_aform, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024);
   cudaFuncSetAttribute(k_chol_prior, cudaFuncAttributeMaxDynamicSharedMemorySize, 193 * 1024);
   cudaFuncSetAttribute(k_chol_w_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, 193 * 1024);
   cudaFuncSetAttribute(k_pinfo, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
@@ -474,11 +589,10 @@ static void info_attrs() {
   attr = true;
 }
 
-static void launch_syrk(const UpdArgs& u, const InfoBufs& ib, int nmax, int B, const Tile* tiles, cudaStream_t s) {
-  const int nt_ = (nmax + 1 + SY_T - 1) / SY_T;
-  dim3 gs(nt_ * (nt_ + 1) / 2, ib.max_chunks, B);
-  k_syrk<<<gs, 256, 0, s>>>(u, ib.Amat, u.ldr, ib.part, ib.max_chunks, ib.max_pairs, ib.cta_budget, tiles,
-                            ib.tile_rows, ib.filter_rows, ib.syrk_cnt);
+static void launch_syrk(const UpdArgs& u, const InfoBufs& ib, int B, const Tile* tiles, cudaStream_t s) {
+  dim3 gs(std::max(ib.max_units, 1), B);
+  k_syrk<<<gs, 256, 0, s>>>(u, ib.Amat, u.ldr, ib.part, ib.max_units, ib.cta_budget, ib.group, tiles, ib.tile_rows,
+                            ib.filter_rows, ib.syrk_cnt);
   check_launch("k_syrk");
 }
 
@@ -503,7 +617,7 @@ void launch_info_dense_factor(const UpdArgs& u, const InfoBufs& ib, const double
   check_launch("k_chol_prior");
   k_aform_dense<<<rows, 256, 0, s>>>(Hp, ldh, rows, n, u.T, u.ldt, ib.Amat, u.ldr);
   check_launch("k_aform_dense");
-  launch_syrk(u, ib, n, 1, nullptr, s);
+  launch_syrk(u, ib, 1, nullptr, s);
   const size_t sm_w = chol_smem_doubles(n, CS + 1) * sizeof(double);
   dim3 gw((D + CS - 1) / CS, 1);
   k_chol_w_solve<<<gw, CHOL_THREADS, sm_w, s>>>(u);
@@ -543,19 +657,14 @@ void launch_info_update(const QrArgs& q, const UpdArgs& u, const InfoBufs& ib, i
   cudaStreamWaitEvent(s, join, 0);
   const int lda = u.ldr;
   if (n_tiles > 0) {
-    const int rows4 = (std::max(max_tile_rows, 1) + 3) & ~3;
-    if (max_w_blk <= 6) {
-      k_aform<36><<<n_tiles, AF_THREADS, (size_t)rows4 * 38 * sizeof(double), s>>>(q, u.T, u.t_stride, u.ldt, ib.Amat,
-                                                                                lda, ib.tile_rows);
-    } else {
-      const int wr = ((6 * max_w_blk + 47) / 48) * 48;
-      k_aform<48><<<n_tiles, AF_THREADS, (size_t)rows4 * (wr + 2) * sizeof(double), s>>>(q, u.T, u.t_stride, u.ldt,
-                                                                                      ib.Amat, lda, ib.tile_rows);
-    }
+    const int rows8 = (std::max(max_tile_rows, 1) + 7) & ~7;
+    const int wp = ((6 * max_w_blk + 3) & ~3) + 4;        // >= aform_stride(W) of every tile
+    k_aform<<<n_tiles, AF_THREADS, (size_t)rows8 * wp * sizeof(double), s>>>(q, u.T, u.t_stride, u.ldt, ib.Amat, lda,
+                                                                           ib.tile_rows);
     check_launch("k_aform");
   }
   if (mid1) cudaEventRecord(mid1, s);
-  launch_syrk(u, ib, nmax, B, q.tiles, s);
+  launch_syrk(u, ib, B, q.tiles, s);
   if (mid_syrk) cudaEventRecord(mid_syrk, s);
   const size_t sm_w = chol_smem_doubles(nmax, CS + 1) * sizeof(double);
   dim3 gw((Dmax + CS - 1) / CS, B);

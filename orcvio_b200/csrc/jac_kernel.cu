@@ -117,8 +117,8 @@ __device__ __forceinline__ void measurement_jacobian(const double* cl, const dou
   }
 }
 
-template <int TEAM, int MAXM>
-__global__ void __launch_bounds__(TEAM == 32 ? 128 : 128) k_jac_gate(JacArgs a) {
+template <int TEAM, int MAXM, int MINB>
+__global__ void __launch_bounds__(128, MINB) k_jac_gate(JacArgs a) {
   constexpr int R2 = 2 * MAXM;
   constexpr int LDQ = R2 + 1;
   constexpr int TEAM_DOUBLES = R2 * 6 + R2 * 3 + R2 + 4 + 3 * R2 * LDQ + R2;
@@ -334,7 +334,7 @@ __global__ void __launch_bounds__(TEAM == 32 ? 128 : 128) k_jac_gate(JacArgs a) 
   for (int ro = lane; ro < r; ro += TEAM) rb[ro] = rproj[ro];
 }
 
-template <int TEAM, int MAXM>
+template <int TEAM, int MAXM, int MINB>
 static void launch_one(const JacArgs& a, cudaStream_t s) {
   if (a.n_list <= 0) return;
   constexpr int R2 = 2 * MAXM;
@@ -345,17 +345,25 @@ static void launch_one(const JacArgs& a, cudaStream_t s) {
   size_t smem = (size_t)tpb * TEAM_DOUBLES * sizeof(double);
   static bool attr_set = false;
   if (!attr_set) {
-    cudaFuncSetAttribute(k_jac_gate<TEAM, MAXM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(k_jac_gate<TEAM, MAXM, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     attr_set = true;
   }
   int blocks = (a.n_list + tpb - 1) / tpb;
-  k_jac_gate<TEAM, MAXM><<<blocks, threads, smem, s>>>(a);
+  k_jac_gate<TEAM, MAXM, MINB><<<blocks, threads, smem, s>>>(a);
   check_launch("k_jac_gate");
 }
 
 void launch_jac_gate(const JacArgs& small_list, const JacArgs& large_list, cudaStream_t s) {
-  launch_one<32, 8>(small_list, s);
-  launch_one<128, ORCVIO_MAX_OBS>(large_list, s);
+  static const int minb = env_int("ORCVIO_JAC_MINB", 4);
+  switch (minb) {
+    case 2: launch_one<32, 8, 2>(small_list, s); break;
+    case 3: launch_one<32, 8, 3>(small_list, s); break;
+    case 5: launch_one<32, 8, 5>(small_list, s); break;
+    case 6: launch_one<32, 8, 6>(small_list, s); break;
+    case 8: launch_one<32, 8, 8>(small_list, s); break;
+    default: launch_one<32, 8, 4>(small_list, s); break;   // 128 registers, 4 CTAs per SM: fewest waves (measured)
+  }
+  launch_one<128, ORCVIO_MAX_OBS, 1>(large_list, s);
 }
 
 }  // namespace ob

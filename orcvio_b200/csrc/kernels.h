@@ -93,6 +93,8 @@ struct FilterWork {              // per filter, per update
   int wmax_blk;                  // widest tile window (blocks)
   int active;                    // 0: skip this filter's update entirely
   int arow0, arows;              // rows of this filter in the stacked A matrix (upper bound)
+  int jrow0[4];                  // staircase of A: first row (relative to arow0) with a structural non-zero in
+                                 // column tile J (64 columns) of A; rows above it are skipped by k_syrk
 };
 
 struct QrArgs {
@@ -120,10 +122,10 @@ struct UpdArgs {
 // scratch of the whitened-form update (info_kernel.cu)
 struct InfoBufs {
   double* Ls;            // per filter 22 x 22 : IMU block factor given the clones
-  double* Amat;          // stacked A = [H' L | r'], lda = ldr
-  double* part;          // split-K partials of A^T A: [filter][chunk][pair][64 x 64]
-  int max_chunks, max_pairs, cta_budget;   // part layout [filter][max_chunks][max_pairs]; SMs x waves
-  unsigned int* syrk_cnt; // split-K arrival counters [filter][pair] (zero between launches)
+  double* Amat;          // stacked A = [r' | H' L], lda = ldr (residual in column 0)
+  double* part;          // split-K partials of A^T A: [filter][work unit][64 x 64]
+  int max_units, cta_budget, group;        // part layout [filter][max_units]; SMs x waves; chunks per reduction group
+  unsigned int* syrk_cnt; // split-K arrival counters [filter][SY_MAXP][1 + SY_MAXG] (zero between launches)
   int* tile_rows;        // gated rows per tile
   int* filter_rows;      // gated rows per filter (0 -> posterior == prior, P is left untouched)
 };
@@ -171,6 +173,7 @@ struct ZuptArgs {
 // Records (and prints) a launch-configuration error; Batch polls launch_error_count().
 void check_launch(const char* name);
 int launch_error_count();
+int env_int(const char* name, int dflt);   // tuning knobs (ORCVIO_* environment variables)
 
 void launch_triangulate(const TriArgs& a, cudaStream_t s);
 void launch_jac_gate(const JacArgs& small_list, const JacArgs& large_list, cudaStream_t s);
@@ -205,23 +208,48 @@ void launch_zupt(const ZuptArgs& a, cudaStream_t s);
 constexpr int QR_THREADS = 256;
 constexpr int QR_SMEM_BYTES = 200 * 1024;
 constexpr int AFORM_TILE_ROWS = 64;     // row cap of a tile of the whitened-form path
-// Split-K plan of W = s^2 I + A^T A for ONE filter (k_syrk): enough (64 x 64 tile pairs x chunks) CTAs to
-// fill `cta_budget` (= SMs x waves), never fewer than 128 rows per chunk, rows per chunk a multiple of 32.
-// A function of the filter alone (its clone count and stacked rows): the chunking fixes the summation
-// order, so a filter gives bit-identical results whether it runs alone or inside a batch.
-__host__ __device__ inline int syrk_rows_per_chunk(int arows, int N, int cta_budget) {
-  const int nt = (6 * N + 1 + 63) / 64, pairs = nt * (nt + 1) / 2;
-  int chunks = arows / 128;
-  const int cap = cta_budget / pairs;
-  if (chunks > cap) chunks = cap;
-  if (chunks < 1) chunks = 1;
-  const int kc = ((arows + chunks - 1) / chunks + 31) / 32 * 32;
-  return kc < 32 ? 32 : kc;
-}
-__host__ __device__ inline int syrk_chunks(int arows, int N, int cta_budget) {
-  const int kc = syrk_rows_per_chunk(arows, N, cta_budget);
-  const int c = (arows + kc - 1) / kc;
-  return c < 1 ? 1 : c;
+// Split-K plan of W = s^2 I + A^T A for ONE filter (k_syrk).  A^T A is computed as 64 x 64 tiles (I <= J) over
+// chunks of rows; column tile J of A is structurally zero above row jrow0[J] (features are sorted by first
+// clone and A = H' L with L lower triangular), so pair (I, J) only covers rows [jrow0[J], arows).  The plan
+// picks the rows per chunk (multiple of 32, >= 128) so that the work units of all pairs fill `cta_budget`
+// (= SMs x waves).  A function of the filter alone: the chunking fixes the summation order, so a filter
+// gives bit-identical results whether it runs alone or inside a batch.
+constexpr int SY_TILE = 64, SY_MAXT = 4, SY_MAXP = 10, SY_MAXG = 32;
+struct SyrkPlan {
+  int kc, nt, npairs, total;
+  int first[SY_MAXP + 1];        // first work unit of every pair (pair order: I outer, J >= I inner)
+};
+__host__ __device__ inline SyrkPlan syrk_plan(const FilterWork& fw, int cta_budget) {
+  SyrkPlan p;
+  p.nt = (6 * fw.N + 1 + SY_TILE - 1) / SY_TILE;
+  if (p.nt > SY_MAXT) p.nt = SY_MAXT;
+  p.npairs = p.nt * (p.nt + 1) / 2;
+  int rowsJ[SY_MAXT];
+  long long tot = 0;
+  for (int J = 0; J < p.nt; ++J) {
+    rowsJ[J] = fw.arows - fw.jrow0[J];
+    if (rowsJ[J] < 0) rowsJ[J] = 0;
+    tot += (long long)rowsJ[J] * (J + 1);
+  }
+  int kc = (int)((tot + cta_budget - 1) / cta_budget);
+  kc = (kc + 31) / 32 * 32;
+  if (kc < 128) kc = 128;
+  for (;;) {
+    int total = 0, q = 0;
+    for (int I = 0; I < p.nt; ++I)
+      for (int J = I; J < p.nt; ++J) {
+        int c = (rowsJ[J] + kc - 1) / kc;
+        if (c < 1) c = 1;
+        p.first[q++] = total;
+        total += c;
+      }
+    p.first[q] = total;
+    p.total = total;
+    if (total <= cta_budget || total <= p.npairs) break;
+    kc += 32;
+  }
+  p.kc = kc;
+  return p;
 }
 inline int qr_tile_rows_cap(int w_cols) {                // rows that fit beside (w_cols+1) columns
   int ld = w_cols + 2;

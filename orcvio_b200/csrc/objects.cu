@@ -228,22 +228,21 @@ int Batch::object_update(int fi, const double* Hx, const double* Hf, const doubl
   CKO(cudaMemcpyAsync(dM.p, M.data(), M.size() * sizeof(double), cudaMemcpyHostToDevice, stream_));
   launch_project_dense(dM.as<double>(), rows, ld, odim, ld, stream_);            // nullspace_project_inplace_svd
   const int prow = rows - odim;
-  const int nt64 = (n + 1 + 63) / 64, pairs = nt64 * (nt64 + 1) / 2;
-  const int chunks = syrk_chunks(prow, N, n_sm_ * syrk_waves_);
+  FilterWork fw{};                                       // jrow0 = 0: a dense block has no staircase
+  fw.N = N; fw.D = D; fw.active = 1; fw.arow0 = 0; fw.arows = prow;
+  const int units = syrk_plan(fw, n_sm_ * syrk_waves_).total;
   const size_t need_a = ((size_t)prow + 16) * ldr_;
   if (need_a > amat_cap_) {
     if (dAmat_) cudaFree(dAmat_);
     amat_cap_ = need_a * 2;
     CKO(cudaMalloc(&dAmat_, amat_cap_ * sizeof(double)));
   }
-  const size_t need_p = (size_t)chunks * pairs * 4096;
+  const size_t need_p = (size_t)units * 4096;
   if (need_p > part_cap_) {
     if (dPart_) cudaFree(dPart_);
     part_cap_ = need_p * 2;
     CKO(cudaMalloc(&dPart_, part_cap_ * sizeof(double)));
   }
-  FilterWork fw{};
-  fw.N = N; fw.D = D; fw.active = 1; fw.arow0 = 0; fw.arows = prow;
   CKO(dFw.alloc(sizeof(FilterWork)));
   CKO(cudaMemcpyAsync(dFw.p, &fw, sizeof(fw), cudaMemcpyHostToDevice, stream_));
   const size_t r_stride = (size_t)(6 * Ncap_ + 1) * ldr_;
@@ -260,7 +259,7 @@ int Batch::object_update(int fi, const double* Hx, const double* Hf, const doubl
   ua.flags = flags_; ua.sigma2 = p_.feature_observation_noise;
   InfoBufs ib{};
   ib.Ls = dLs_ + (size_t)fi * ORCVIO_LEG * ORCVIO_LEG; ib.Amat = dAmat_; ib.part = dPart_;
-  ib.max_chunks = chunks; ib.max_pairs = pairs; ib.cta_budget = n_sm_ * syrk_waves_; ib.syrk_cnt = dSyrkCnt_;
+  ib.max_units = units; ib.cta_budget = n_sm_ * syrk_waves_; ib.group = syrk_group_; ib.syrk_cnt = dSyrkCnt_;
   ib.tile_rows = nullptr; ib.filter_rows = dFilterRows_ + fi;
   const double* Hp = dM.as<double>() + (size_t)odim * ld + odim;
   launch_info_dense_factor(ua, ib, Hp, ld, prow, N, stream_);

@@ -17,6 +17,7 @@
 // iteration costs the latency of ONE observation instead of m.  The kernel is bound by the serial
 // latency of the slowest feature's LM chain (FP64 divide / sqrt), not by HBM or FP64 throughput.
 #include <cstdio>
+#include <cstdlib>
 #include "kernels.h"
 
 namespace ob {
@@ -286,7 +287,10 @@ __device__ __forceinline__ bool check_motion(const double* clones, int first_clo
 // cand.filter selects the clone array / feature-position table of its filter.
 constexpr int TRI_WARPS = 4;
 
-__global__ void __launch_bounds__(32 * TRI_WARPS) k_triangulate(TriArgs a) {
+// MINB = resident CTAs per SM the register allocation is held to (launch bound; chosen at run time by
+// tri_min_blocks(): the kernel is one LM latency chain per warp, so whole waves are what cost time).
+template <int MINB>
+__global__ void __launch_bounds__(32 * TRI_WARPS, MINB) k_triangulate(TriArgs a) {
   __shared__ double sm_all[TRI_WARPS][32 * TRI_SM_STRIDE];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int c = blockIdx.x * TRI_WARPS + warp;
@@ -339,11 +343,22 @@ void check_launch(const char* name) {
   }
 }
 int launch_error_count() { return g_launch_errors; }
+int env_int(const char* name, int dflt) {
+  const char* e = std::getenv(name);
+  return e ? std::atoi(e) : dflt;
+}
 
 void launch_triangulate(const TriArgs& a, cudaStream_t s) {
   if (a.n_cand <= 0) return;
   int blocks = (a.n_cand + TRI_WARPS - 1) / TRI_WARPS;
-  k_triangulate<<<blocks, 32 * TRI_WARPS, 0, s>>>(a);
+  static const int minb = env_int("ORCVIO_TRI_MINB", 3);
+  switch (minb) {
+    case 4: k_triangulate<4><<<blocks, 32 * TRI_WARPS, 0, s>>>(a); break;
+    case 5: k_triangulate<5><<<blocks, 32 * TRI_WARPS, 0, s>>>(a); break;
+    case 6: k_triangulate<6><<<blocks, 32 * TRI_WARPS, 0, s>>>(a); break;
+    case 8: k_triangulate<8><<<blocks, 32 * TRI_WARPS, 0, s>>>(a); break;
+    default: k_triangulate<3><<<blocks, 32 * TRI_WARPS, 0, s>>>(a); break;
+  }
   check_launch("k_triangulate");
 }
 
