@@ -128,16 +128,17 @@ __device__ __forceinline__ void chol_load_rows(double* __restrict__ A, int m, in
 // A: tiled (chol_at) tall matrix: m x m lower triangle followed by nx carried rows.
 // On return tile storage holds L (rows < m) and X C^-T (rows >= m).
 // PROF: thread 0 (panel team) / thread 128 (trailing team) log clock64() per phase into prof[p][8].
-template <bool PROF = false>
+template <bool PROF = false, int LAYOUT = 0>
 __device__ void cta_cholesky(double* __restrict__ A, CholShared& cs, const double* __restrict__ tol, int m, int nx,
                              long long* prof = nullptr) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   // Teams by warp scheduler: warps 0, 4, 8, 12 (all on scheduler 0) are the panel team, so the
   // pivot chain never queues behind a 16-cycle DMMA of the trailing team on its FP64 pipe.
-  const bool panel_team = (warp & 3) == 0;
-  const int tid = panel_team ? (warp >> 2) * 32 + lane : -1;          // panel-team thread index
-  const int tw = (warp >> 2) * 3 + (warp & 3) - 1;                      // trailing-team warp index
-  const bool trail_lead = (warp == 1 && lane == 0);
+  // (LAYOUT 1, experiment: panel team = warps 0..3, one per scheduler.)
+  const bool panel_team = LAYOUT == 0 ? (warp & 3) == 0 : warp < 4;
+  const int tid = panel_team ? (LAYOUT == 0 ? (warp >> 2) : warp) * 32 + lane : -1;   // panel-team thread index
+  const int tw = LAYOUT == 0 ? (warp >> 2) * 3 + (warp & 3) - 1 : warp - 4;            // trailing-team warp index
+  const bool trail_lead = ((LAYOUT == 0 ? warp == 1 : warp == 4) && lane == 0);
   const int mrows = m + nx;
   const int Tm = (m + 7) >> 3, Tr = (mrows + 7) >> 3;
   __syncthreads();

@@ -492,8 +492,9 @@ __global__ void __launch_bounds__(CHOL_THREADS) k_chol_w_solve(UpdArgs a) {
 // round trip, then the k loop runs without barriers.  One extra CTA per filter (blockIdx.y ==
 // gridDim.y - 1) applies dx to the state (incrementState_IMUCam, src/orcvio.cpp:4468-4567).
 constexpr int PT = 32;
+constexpr int PI_KG = 4, PI_THREADS = 256 * PI_KG;   // k is split over PI_KG groups of 256 threads (latency, not flops)
 
-__global__ void __launch_bounds__(256) k_pinfo(UpdArgs a, const double* Ls_all, const int* filter_rows) {
+__global__ void __launch_bounds__(PI_THREADS) k_pinfo(UpdArgs a, const double* Ls_all, const int* filter_rows) {
   extern __shared__ double sm[];
   const int fi = blockIdx.z;
   const FilterWork fw = a.fw[fi];
@@ -520,7 +521,7 @@ __global__ void __launch_bounds__(256) k_pinfo(UpdArgs a, const double* Ls_all, 
   {
     const int ldt = a.ldt;
     const bool same = (i0 == j0);
-    for (int e = tid; e < n * (PT / 2); e += 256) {
+    for (int e = tid; e < n * (PT / 2); e += PI_THREADS) {
       const int k = e / (PT / 2), c = 2 * (e - k * (PT / 2));
       double* di_ = Ys_i + (size_t)k * PT + c;
       double* dj_ = Ys_j + (size_t)k * PT + c;
@@ -542,33 +543,54 @@ __global__ void __launch_bounds__(256) k_pinfo(UpdArgs a, const double* Ls_all, 
     if (same) Ys_j = Ys_i;
   }
   __syncthreads();
-  const int tx = tid & 15, ty = tid >> 4;
-  // four interleaved partial sums per output: the k loop is 4 dependent-FMA chains of n/4 instead of one of n
-  double acc[4][2][2];
+  // DFMA is a ~35-cycle dependent op here, so the k loop is pure latency: group kg takes k = kg (mod PI_KG) with two
+  // interleaved chains per output; the groups' partial tiles are added in group order through shared memory
+  const int kg = tid >> 8, t8 = tid & 255;
+  const int tx = t8 & 15, ty = t8 >> 4;
+  double acc2[2][2][2] = {{{0, 0}, {0, 0}}, {{0, 0}, {0, 0}}};
+  {
+    int k = kg;
+    for (; k + PI_KG < n; k += 2 * PI_KG) {
 #pragma unroll
-  for (int q = 0; q < 4; ++q) { acc[q][0][0] = acc[q][0][1] = acc[q][1][0] = acc[q][1][1] = 0.0; }
-  int k = 0;
-  for (; k + 3 < n; k += 4) {
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      const double2 av = *reinterpret_cast<const double2*>(Ys_i + (size_t)(k + q) * PT + 2 * ty);
-      const double2 bv = *reinterpret_cast<const double2*>(Ys_j + (size_t)(k + q) * PT + 2 * tx);
-      acc[q][0][0] += av.x * bv.x; acc[q][0][1] += av.x * bv.y;
-      acc[q][1][0] += av.y * bv.x; acc[q][1][1] += av.y * bv.y;
+      for (int q = 0; q < 2; ++q) {
+        const double2 av = *reinterpret_cast<const double2*>(Ys_i + (size_t)(k + q * PI_KG) * PT + 2 * ty);
+        const double2 bv = *reinterpret_cast<const double2*>(Ys_j + (size_t)(k + q * PI_KG) * PT + 2 * tx);
+        acc2[q][0][0] += av.x * bv.x; acc2[q][0][1] += av.x * bv.y;
+        acc2[q][1][0] += av.y * bv.x; acc2[q][1][1] += av.y * bv.y;
+      }
+    }
+    if (k < n) {
+      const double2 av = *reinterpret_cast<const double2*>(Ys_i + (size_t)k * PT + 2 * ty);
+      const double2 bv = *reinterpret_cast<const double2*>(Ys_j + (size_t)k * PT + 2 * tx);
+      acc2[0][0][0] += av.x * bv.x; acc2[0][0][1] += av.x * bv.y;
+      acc2[0][1][0] += av.y * bv.x; acc2[0][1][1] += av.y * bv.y;
     }
   }
-  for (; k < n; ++k) {
-    const double2 av = *reinterpret_cast<const double2*>(Ys_i + (size_t)k * PT + 2 * ty);
-    const double2 bv = *reinterpret_cast<const double2*>(Ys_j + (size_t)k * PT + 2 * tx);
-    acc[0][0][0] += av.x * bv.x; acc[0][0][1] += av.x * bv.y;
-    acc[0][1][0] += av.y * bv.x; acc[0][1][1] += av.y * bv.y;
+  double acc[2][2];
+#pragma unroll
+  for (int u = 0; u < 2; ++u)
+#pragma unroll
+    for (int v = 0; v < 2; ++v) acc[u][v] = acc2[0][u][v] + acc2[1][u][v];
+  double* red = sm + (size_t)2 * n * PT;               // [PI_KG - 1][256][4]
+  if (kg > 0) {
+    double* r = red + ((size_t)(kg - 1) * 256 + t8) * 4;
+    *reinterpret_cast<double2*>(r) = make_double2(acc[0][0], acc[0][1]);
+    *reinterpret_cast<double2*>(r + 2) = make_double2(acc[1][0], acc[1][1]);
+  }
+  __syncthreads();
+  if (kg > 0) return;
+#pragma unroll
+  for (int g = 0; g < PI_KG - 1; ++g) {
+    const double* r = red + ((size_t)g * 256 + t8) * 4;
+    const double2 r0 = *reinterpret_cast<const double2*>(r), r1 = *reinterpret_cast<const double2*>(r + 2);
+    acc[0][0] += r0.x; acc[0][1] += r0.y; acc[1][0] += r1.x; acc[1][1] += r1.y;
   }
   const double* Ls = Ls_all + (size_t)fi * L * L;
   for (int u = 0; u < 2; ++u)
     for (int v = 0; v < 2; ++v) {
       const int i = i0 + 2 * ty + u, j = j0 + 2 * tx + v;
       if (i >= D || j >= D) continue;
-      double s = a.sigma2 * ((acc[0][u][v] + acc[1][u][v]) + (acc[2][u][v] + acc[3][u][v]));
+      double s = a.sigma2 * acc[u][v];
       if (i < L && j < L) {
         double t = 0.0;
         for (int q = 0; q < L; ++q) t += Ls[i * L + q] * Ls[j * L + q];
@@ -584,7 +606,7 @@ static void info_attrs() {
   cudaFuncSetAttribute(k_aform, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024);
   cudaFuncSetAttribute(k_chol_prior, cudaFuncAttributeMaxDynamicSharedMemorySize, 193 * 1024);
   cudaFuncSetAttribute(k_chol_w_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, 193 * 1024);
-  cudaFuncSetAttribute(k_pinfo, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+  cudaFuncSetAttribute(k_pinfo, cudaFuncAttributeMaxDynamicSharedMemorySize, 140 * 1024);
   check_launch("info attributes");
   attr = true;
 }
@@ -600,7 +622,8 @@ static void launch_pinfo(const UpdArgs& u, const InfoBufs& ib, int nmax, int B, 
   const int Dmax = ORCVIO_LEG + nmax;
   const int g = (Dmax + PT - 1) / PT;
   dim3 g5(g, g + 1, B);                                  // last row of CTAs: the state increment
-  k_pinfo<<<g5, 256, (size_t)2 * nmax * PT * sizeof(double), s>>>(u, ib.Ls, ib.filter_rows);
+  k_pinfo<<<g5, PI_THREADS, ((size_t)2 * nmax * PT + (size_t)(PI_KG - 1) * 256 * 4) * sizeof(double), s>>>(
+      u, ib.Ls, ib.filter_rows);
   check_launch("k_pinfo");
 }
 

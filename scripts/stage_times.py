@@ -15,7 +15,7 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
-KNOBS = ["ORCVIO_TRI_MINB", "ORCVIO_JAC_MINB", "ORCVIO_SYRK_WAVES", "ORCVIO_SYRK_GROUP", "ORCVIO_AFORM"]
+KNOBS = ["ORCVIO_TRI_MINB", "ORCVIO_JAC_MINB", "ORCVIO_SYRK_WAVES", "ORCVIO_SYRK_GROUP", "ORCVIO_TRI_CAP"]
 
 
 def one(n_feat, repeat, flush):
