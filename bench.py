@@ -39,11 +39,13 @@ if ROOT not in sys.path:
 METRIC = "feature_updates_per_sec"
 UNIT = "features/s"
 N_CLONES, N_FEATURES, MAX_TRACK = 30, 4096, 6
+TARGET_FEATURES = 2000      # BASELINE.json north_star: "30-clone, 2000-feature frame runs under 200 us"
 NOISE_VAR = 1.6e-5          # (2 x 0.002)^2: synthetic pixel noise of the KITTI-shaped generator
 TRI = dict(cost_threshold=1e-3, init_final_dist_threshold=100.0)
 # dram__bytes_read.sum + dram__bytes_write.sum of one k_syrk launch from the committed `ncu --set full`
 # capture (profiles/); None until a capture of the current kernel exists
-SYRK_NCU_TRAFFIC = 37_659_136          # 37.658 MB read + 1 KB written (profiles/r1_ncu_full_summary.csv)
+SYRK_NCU_TRAFFIC = 28_166_400          # 28.130 MB read + 36 KB written (profiles/r1_ncu_full_summary.csv): less than the
+                                       # dense 8 M (n+1) B because the zero part of A's staircase is never read
 WORKLOAD = f"stress frame: {N_CLONES}-clone window, {N_FEATURES} features, max_track_len {MAX_TRACK} (SURVEY 8d C4a)"
 
 
@@ -246,6 +248,30 @@ def main():
     barrier()
     clocks = sampler.stop() if rank == 0 else None
 
+    # ---- the north star's target frame (30 clones, 2000 features, target < 200 us), rank 0 only: same chain, same
+    # timing method (CUDA events on the launching stream, L2 flushed), reported beside the headline workload
+    target = None
+    if rank == 0:
+        snap_t = make_frame(seed=0, n_feat=TARGET_FEATURES)
+        fr_t = api.Frame(N_CLONES, 0, NOISE_VAR, 0.95, -1.0, TRI["cost_threshold"], TRI["init_final_dist_threshold"])
+        out_t = fr_t.update(fr_t.prepare_inputs(snap_t))
+        fr_t.load(snap_t)
+        for _ in range(args.warmup):
+            l2_flush()
+            fr_t.run(1)
+        us_t, n_t = 0.0, max(20, min(args.steps, 100))
+        for _ in range(n_t):
+            l2_flush()
+            us_t += fr_t.run(1)
+        _, st_t = fr_t.run(5, stages=True)
+        target = dict(workload=f"{N_CLONES}-clone window, {TARGET_FEATURES} features, max_track_len {MAX_TRACK}",
+                      us_per_frame=us_t / n_t, target_us=200.0, gated_in=int(((out_t["status"] & 2) != 0).sum()),
+                      stage_us=dict(tri=round(st_t["tri"], 2), jac_gate=round(st_t["jac_gate"], 2),
+                                    aform_incl_prior_wait=round(st_t["qr_tiles"], 2),
+                                    syrk_plus_chol_w_solve=round(st_t["qr_chain"], 2),
+                                    pinfo_increment=round(st_t["update"], 2), total=round(st_t["total"], 2)))
+        del fr_t
+
     counts = torch.tensor([float(n_pass), float(N_FEATURES)], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t_val, op=dist.ReduceOp.MAX)
@@ -290,7 +316,7 @@ def main():
             e2e=dict(value=total_pass * args.steps / secs_e2e, unit=UNIT, h2d_bytes_per_step=int(h2d),
                      d2h_bytes_per_step=int(d2h), us_per_frame=1e6 * secs_e2e / args.steps),
             gpu_launches=int(launches),
-            roofline=dict(bound="tensor", kernel="k_syrk (W = s^2 I + A^T A, mma.sync m8n8k4 f64)", achieved=achieved,
+            roofline=dict(bound="tensor", kernel="k_syrk (W = s^2 I + A^T A, staircase-sparse split-K, mma.sync m8n8k4 f64)", achieved=achieved,
                           peak=dmma_peak, unit="TFLOP/s", frac=achieved / dmma_peak, traffic=SYRK_NCU_TRAFFIC,
                           algorithmic_flops=flops, gated_rows=M_rows, kernel_us=kt["syrk"],
                           peak_source="FP64 DMMA peak measured live on this GPU (orcvio_fp64_peak: mma.sync m8n8k4 "
@@ -300,6 +326,7 @@ def main():
                               peak=peak, unit="GB/s", frac=jac_bytes / (stages["jac_gate"] * 1e-6) / 1e9 / peak,
                               algorithmic_bytes=jac_bytes, kernel_us=stages["jac_gate"], peak_source=peak_src,
                               note="one frame's working set is L2-resident: latency-bound, not HBM-bound (SURVEY 8d)"),
+            north_star_frame=target,
             clocks=clocks)
         if not args.no_cpu_baseline:
             try:

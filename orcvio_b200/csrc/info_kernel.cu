@@ -492,7 +492,8 @@ __global__ void __launch_bounds__(CHOL_THREADS) k_chol_w_solve(UpdArgs a) {
 // round trip, then the k loop runs without barriers.  One extra CTA per filter (blockIdx.y ==
 // gridDim.y - 1) applies dx to the state (incrementState_IMUCam, src/orcvio.cpp:4468-4567).
 constexpr int PT = 32;
-constexpr int PI_KG = 4, PI_THREADS = 256 * PI_KG;   // k is split over PI_KG groups of 256 threads (latency, not flops)
+constexpr int PI_LD = 36;                 // strip row stride in doubles (== 4 mod 16: conflict-free 64-bit fragment loads)
+constexpr int PI_THREADS = 1024;          // 32 warps: 16 fragments (8 x 8) of the 32 x 32 tile x 2 halves of k
 
 __global__ void __launch_bounds__(PI_THREADS) k_pinfo(UpdArgs a, const double* Ls_all, const int* filter_rows) {
   extern __shared__ double sm[];
@@ -515,24 +516,25 @@ __global__ void __launch_bounds__(PI_THREADS) k_pinfo(UpdArgs a, const double* L
   if (i0 >= D || j0 >= D) return;
   const double* Y = a.T + (size_t)fi * a.t_stride;
   double* P = a.P + (size_t)fi * a.p_stride;
-  double* Ys_i = sm;                       // [n][PT]
-  double* Ys_j = sm + (size_t)n * PT;
+  const int n4 = (n + 3) & ~3;                          // k padded to the MMA depth (zero rows)
+  double* Ys_i = sm;                                    // [n4][PI_LD]
+  double* Ys_j = sm + (size_t)n4 * PI_LD;
   // both strips with 16-byte cp.async: every load of the CTA is in flight at once (one L2 round trip)
   {
     const int ldt = a.ldt;
     const bool same = (i0 == j0);
-    for (int e = tid; e < n * (PT / 2); e += PI_THREADS) {
+    for (int e = tid; e < n4 * (PT / 2); e += PI_THREADS) {
       const int k = e / (PT / 2), c = 2 * (e - k * (PT / 2));
-      double* di_ = Ys_i + (size_t)k * PT + c;
-      double* dj_ = Ys_j + (size_t)k * PT + c;
-      if (i0 + c < ldt) {
+      double* di_ = Ys_i + (size_t)k * PI_LD + c;
+      double* dj_ = Ys_j + (size_t)k * PI_LD + c;
+      if (k < n && i0 + c < ldt) {
         const unsigned int d = (unsigned int)__cvta_generic_to_shared(di_);
         asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(Y + (size_t)k * ldt + i0 + c) : "memory");
       } else {
         *reinterpret_cast<double2*>(di_) = make_double2(0.0, 0.0);
       }
       if (same) continue;
-      if (j0 + c < ldt) {
+      if (k < n && j0 + c < ldt) {
         const unsigned int d = (unsigned int)__cvta_generic_to_shared(dj_);
         asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(Y + (size_t)k * ldt + j0 + c) : "memory");
       } else {
@@ -543,61 +545,55 @@ __global__ void __launch_bounds__(PI_THREADS) k_pinfo(UpdArgs a, const double* L
     if (same) Ys_j = Ys_i;
   }
   __syncthreads();
-  // DFMA is a ~35-cycle dependent op here, so the k loop is pure latency: group kg takes k = kg (mod PI_KG) with two
-  // interleaved chains per output; the groups' partial tiles are added in group order through shared memory
-  const int kg = tid >> 8, t8 = tid & 255;
-  const int tx = t8 & 15, ty = t8 >> 4;
-  double acc2[2][2][2] = {{{0, 0}, {0, 0}}, {{0, 0}, {0, 0}}};
+  // Y_i^T Y_j on the FP64 tensor cores: warp w owns fragment (w & 15) over half (w >> 4) of k, two accumulators
+  // alternate over the k steps (a dependent DFMA / DMMA costs tens of cycles: the k loop is latency, not flops);
+  // the upper-half warps hand their partial fragment over through shared memory, added in a fixed order
+  const int warp = tid >> 5, lane = tid & 31;
+  const int fr = lane >> 2, fk = lane & 3;
+  const int fidx = warp & 15, half = warp >> 4;
+  const int fi8 = (fidx >> 2) * 8, fj8 = (fidx & 3) * 8;
+  const int ksteps = n4 >> 2, khalf = (ksteps + 1) >> 1;
+  const int ks0 = half * khalf, ks1 = min(ksteps, ks0 + khalf);
+  double2 c0 = make_double2(0.0, 0.0), c1 = make_double2(0.0, 0.0);
   {
-    int k = kg;
-    for (; k + PI_KG < n; k += 2 * PI_KG) {
-#pragma unroll
-      for (int q = 0; q < 2; ++q) {
-        const double2 av = *reinterpret_cast<const double2*>(Ys_i + (size_t)(k + q * PI_KG) * PT + 2 * ty);
-        const double2 bv = *reinterpret_cast<const double2*>(Ys_j + (size_t)(k + q * PI_KG) * PT + 2 * tx);
-        acc2[q][0][0] += av.x * bv.x; acc2[q][0][1] += av.x * bv.y;
-        acc2[q][1][0] += av.y * bv.x; acc2[q][1][1] += av.y * bv.y;
-      }
+    const double* pa = Ys_i + (size_t)fk * PI_LD + fi8 + fr;
+    const double* pb = Ys_j + (size_t)fk * PI_LD + fj8 + fr;
+    int ks = ks0;
+    for (; ks + 1 < ks1; ks += 2) {
+      const double a0 = pa[(size_t)(4 * ks) * PI_LD], b0 = pb[(size_t)(4 * ks) * PI_LD];
+      const double a1 = pa[(size_t)(4 * ks + 4) * PI_LD], b1 = pb[(size_t)(4 * ks + 4) * PI_LD];
+      dmma884(c0.x, c0.y, a0, b0);
+      dmma884(c1.x, c1.y, a1, b1);
     }
-    if (k < n) {
-      const double2 av = *reinterpret_cast<const double2*>(Ys_i + (size_t)k * PT + 2 * ty);
-      const double2 bv = *reinterpret_cast<const double2*>(Ys_j + (size_t)k * PT + 2 * tx);
-      acc2[0][0][0] += av.x * bv.x; acc2[0][0][1] += av.x * bv.y;
-      acc2[0][1][0] += av.y * bv.x; acc2[0][1][1] += av.y * bv.y;
-    }
+    if (ks < ks1) dmma884(c0.x, c0.y, pa[(size_t)(4 * ks) * PI_LD], pb[(size_t)(4 * ks) * PI_LD]);
   }
-  double acc[2][2];
-#pragma unroll
-  for (int u = 0; u < 2; ++u)
-#pragma unroll
-    for (int v = 0; v < 2; ++v) acc[u][v] = acc2[0][u][v] + acc2[1][u][v];
-  double* red = sm + (size_t)2 * n * PT;               // [PI_KG - 1][256][4]
-  if (kg > 0) {
-    double* r = red + ((size_t)(kg - 1) * 256 + t8) * 4;
-    *reinterpret_cast<double2*>(r) = make_double2(acc[0][0], acc[0][1]);
-    *reinterpret_cast<double2*>(r + 2) = make_double2(acc[1][0], acc[1][1]);
-  }
+  double2 acc = make_double2(c0.x + c1.x, c0.y + c1.y);
+  double2* red = reinterpret_cast<double2*>(sm + (size_t)2 * n4 * PI_LD);   // [16 fragments][32 lanes]
+  if (half == 1) red[fidx * 32 + lane] = acc;
   __syncthreads();
-  if (kg > 0) return;
-#pragma unroll
-  for (int g = 0; g < PI_KG - 1; ++g) {
-    const double* r = red + ((size_t)g * 256 + t8) * 4;
-    const double2 r0 = *reinterpret_cast<const double2*>(r), r1 = *reinterpret_cast<const double2*>(r + 2);
-    acc[0][0] += r0.x; acc[0][1] += r0.y; acc[1][0] += r1.x; acc[1][1] += r1.y;
+  if (half == 1) return;
+  {
+    const double2 r = red[fidx * 32 + lane];
+    acc.x += r.x;
+    acc.y += r.y;
   }
+  // fragment element: row i = i0 + fi8 + fr, columns j0 + fj8 + 2 fk (+1)
   const double* Ls = Ls_all + (size_t)fi * L * L;
-  for (int u = 0; u < 2; ++u)
-    for (int v = 0; v < 2; ++v) {
-      const int i = i0 + 2 * ty + u, j = j0 + 2 * tx + v;
-      if (i >= D || j >= D) continue;
-      double s = a.sigma2 * acc[u][v];
-      if (i < L && j < L) {
-        double t = 0.0;
-        for (int q = 0; q < L; ++q) t += Ls[i * L + q] * Ls[j * L + q];
-        s += t;
+  const int i = i0 + fi8 + fr;
+  for (int v = 0; v < 2; ++v) {
+    const int j = j0 + fj8 + 2 * fk + v;
+    if (i >= D || j >= D) continue;
+    double s = a.sigma2 * (v == 0 ? acc.x : acc.y);
+    if (i < L && j < L) {
+      double t0 = 0.0, t1 = 0.0;
+      for (int q = 0; q + 1 < L; q += 2) {
+        t0 += Ls[i * L + q] * Ls[j * L + q];
+        t1 += Ls[i * L + q + 1] * Ls[j * L + q + 1];
       }
-      P[(size_t)i * a.ldp + j] = s;
+      s += t0 + t1;
     }
+    P[(size_t)i * a.ldp + j] = s;
+  }
 }
 
 static void info_attrs() {
@@ -622,8 +618,8 @@ static void launch_pinfo(const UpdArgs& u, const InfoBufs& ib, int nmax, int B, 
   const int Dmax = ORCVIO_LEG + nmax;
   const int g = (Dmax + PT - 1) / PT;
   dim3 g5(g, g + 1, B);                                  // last row of CTAs: the state increment
-  k_pinfo<<<g5, PI_THREADS, ((size_t)2 * nmax * PT + (size_t)(PI_KG - 1) * 256 * 4) * sizeof(double), s>>>(
-      u, ib.Ls, ib.filter_rows);
+  const int n4 = (nmax + 3) & ~3;
+  k_pinfo<<<g5, PI_THREADS, ((size_t)2 * n4 * PI_LD + 16 * 32 * 2) * sizeof(double), s>>>(u, ib.Ls, ib.filter_rows);
   check_launch("k_pinfo");
 }
 

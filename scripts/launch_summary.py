@@ -1,24 +1,23 @@
-"""Summarise an ncu `--metrics gpu__time_duration.sum --csv` launch list per kernel."""
-import collections
+"""Per-kernel summary of an ncu launch list (`--metrics gpu__time_duration.sum --csv --log-file x.csv`).
+
+    python scripts/launch_summary.py gpurun_out/launches.csv > profiles/rN_launch_summary.txt
+"""
 import csv
 import sys
+from collections import OrderedDict
 
-
-def main(path):
-    with open(path) as f:
-        lines = [l for l in f if not l.startswith("==")]
-    agg = collections.OrderedDict()
-    for row in csv.DictReader(lines):
-        k = row["Kernel Name"][:64]
-        v = float(row["Metric Value"].replace(",", ""))
-        u = row["Metric Unit"]
-        v = v / 1000 if u == "ns" else v * 1000 if u == "ms" else v
-        agg.setdefault(k, []).append(v)
-    tot = sum(sum(v) for v in agg.values())
-    print(f"{'kernel':66s} {'n':>4s} {'mean us':>9s} {'min':>8s} {'max':>8s} {'share':>6s}")
-    for k, v in agg.items():
-        print(f"{k:66s} {len(v):4d} {sum(v)/len(v):9.1f} {min(v):8.1f} {max(v):8.1f} {100*sum(v)/tot:5.1f}%")
-
-
-if __name__ == "__main__":
-    main(sys.argv[1])
+rows = [r for r in csv.reader(open(sys.argv[1])) if len(r) > 10]
+hdr = rows[0]
+ix = {h: i for i, h in enumerate(hdr)}
+per = OrderedDict()
+for r in rows[1:]:
+    if r[ix["Metric Name"]] != "gpu__time_duration.sum":
+        continue
+    v = float(r[ix["Metric Value"]])
+    if r[ix["Metric Unit"]] in ("ns", "nsecond"):
+        v /= 1e3
+    per.setdefault(r[ix["Kernel Name"]], []).append(v)
+tot = sum(sum(v) for v in per.values())
+print(f"{'kernel':68s} {'n':>5s} {'mean us':>9s} {'min':>8s} {'max':>8s} {'share':>6s}")
+for k, v in per.items():
+    print(f"{k[:68]:68s} {len(v):5d} {sum(v) / len(v):9.1f} {min(v):8.1f} {max(v):8.1f} {100 * sum(v) / tot:5.1f}%")
