@@ -154,71 +154,65 @@ __device__ void cta_cholesky(double* __restrict__ A, CholShared& cs, const doubl
       if (PROF && tid == 0) prof[p * 8 + 1] = clock64();
       if (PROF) __syncwarp();
       if (warp == 0) {
-        // Every lane factors the whole 8 x 8 block for itself (36 doubles of lower triangle in registers): no
-        // shuffle sits on the pivot chain, which is then  reciprocal seed -> 2 FMA (one Newton step) ->
-        // multiply -> FMA (second Newton step folded into w = u / pivot) -> FMA into the next pivot,  with the
-        // (7 - c)(8 - c)/2 trailing FMAs of a step as independent work around it.  Unscaled (L D L^T)
-        // elimination, branch-free: rejected pivots are handled by selects; the 8 rsqrt that turn the result
-        // into L = U D^-1/2 run afterwards, in parallel.
-        double* dt = A + (size_t)chol_tile(p, p, Tm) * 64;
-        double m_[CHB][CHB];
+        // lane a (mod 8) owns row a of the diagonal tile
+        const int a = lane & 7;
+        double* dt = A + (size_t)chol_tile(p, p, Tm) * 64 + a * 8;
+        double d[CHB];
 #pragma unroll
-        for (int a = 0; a < CHB; ++a)
-#pragma unroll
-          for (int b = 0; b <= a; b += 2) {
-            const double2 t = *reinterpret_cast<const double2*>(dt + a * 8 + b);
-            m_[a][b] = t.x;
-            if (b + 1 <= a) m_[a][b + 1] = t.y;
-          }
-        if (nb < CHB) {
-#pragma unroll
-          for (int a = 0; a < CHB; ++a)
-#pragma unroll
-            for (int b = 0; b <= a; ++b)
-              if (a >= nb || b >= nb) m_[a][b] = (a == b) ? 1.0 : 0.0;
+        for (int b = 0; b < CHB; b += 2) {
+          const double2 t = *reinterpret_cast<const double2*>(dt + b);
+          d[b] = t.x;
+          d[b + 1] = t.y;
         }
+#pragma unroll
+        for (int b = 0; b < CHB; ++b)
+          if (a >= nb || b >= nb) d[b] = (a == b) ? 1.0 : 0.0;
+        // Unscaled (L D L^T) elimination, branch-free.  The dependent chain per pivot is
+        //   shuffle -> reciprocal seed -> 2 FMA (one Newton step) -> multiply -> FMA (second Newton step folded
+        //   into w = u / pivot) -> FMA into the next pivot;
+        // thresholds are preloaded, rejected pivots are handled by selects.  The 8 rsqrt that turn the
+        // result into L = U D^-1/2 run afterwards, in parallel.
         double thr[CHB], ivs[CHB];
 #pragma unroll
         for (int c = 0; c < CHB; ++c) thr[c] = (tol != nullptr && c < nb) ? tol[k0 + c] : 0.0;
 #pragma unroll
         for (int c = 0; c < CHB; ++c) {
-          const double pv = m_[c][c];
+          const double pv = __shfl_sync(0xffffffffu, d[c], c, 8);
           const bool ok = pv > thr[c];
+          const double u = d[c];
           double y0;
           asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y0) : "d"(pv));
           const double e = fma(-pv, y0, 1.0);
           const double y1 = fma(y0, e, y0);                   // 1/pv (1 - e^2)
           const double e2 = e * e;
+          const double t = u * y1;
+          double w = fma(t, e2, t);                           // u / pv to working precision
+          w = ok ? w : 0.0;
           ivs[c] = ok ? pv : 0.0;
-          double w[CHB];
 #pragma unroll
-          for (int a = c + 1; a < CHB; ++a) {
-            const double t = m_[a][c] * y1;
-            const double wa = fma(t, e2, t);                  // u / pv to working precision
-            w[a] = ok ? wa : 0.0;
+          for (int b = c + 1; b < CHB; ++b) {
+            const double ub = __shfl_sync(0xffffffffu, u, b, 8);
+            d[b] = fma(-w, ub, d[b]);                         // meaningful for a >= b
           }
-#pragma unroll
-          for (int a = c + 1; a < CHB; ++a)
-#pragma unroll
-            for (int b = c + 1; b <= a; ++b) m_[a][b] = fma(-w[a], m_[b][c], m_[a][b]);
         }
 #pragma unroll
         for (int c = 0; c < CHB; ++c) {
           const double rs = chol_rsqrt(ivs[c] > 0.0 ? ivs[c] : 1.0);
           ivs[c] = (ivs[c] > 0.0) ? rs : 0.0;
+          d[c] *= ivs[c];
         }
-        // all lanes hold the same block: every lane stores it (same values to the same addresses)
-#pragma unroll
-        for (int a = 0; a < CHB; ++a) {
+        if (lane < CHB) {
 #pragma unroll
           for (int b = 0; b < CHB; b += 2) {
-            const double2 t = make_double2(b <= a ? m_[a][b] * ivs[b] : 0.0, b + 1 <= a ? m_[a][b + 1] * ivs[b + 1] : 0.0);
+            const double2 t = make_double2(b <= a ? d[b] : 0.0, b + 1 <= a ? d[b + 1] : 0.0);
             *reinterpret_cast<double2*>(&cs.dblk[a][b]) = t;
-            if (a < nb) *reinterpret_cast<double2*>(dt + a * 8 + b) = t;   // rows >= nb of this tile are carried rows
+            if (a < nb) *reinterpret_cast<double2*>(dt + b) = t;   // rows >= nb of this tile are carried rows
+          }
+          if (lane == 0) {
+#pragma unroll
+            for (int b = 0; b < CHB; ++b) cs.dinv[b] = ivs[b];
           }
         }
-#pragma unroll
-        for (int b = 0; b < CHB; b += 2) *reinterpret_cast<double2*>(&cs.dinv[b]) = make_double2(ivs[b], ivs[b + 1]);
       }
       if (PROF && tid == 0) prof[p * 8 + 2] = clock64();
       chol_team_barrier();
