@@ -10,6 +10,13 @@
 //   findRedundantImuStates :2582-2626
 //   pruneImuStateBuffer    :2629-2959
 #include "batch.h"
+#include <atomic>
+#include <chrono>
+#include <condition_variable>
+#include <functional>
+#include <mutex>
+#include <thread>
+#include <cstdio>
 
 #include <algorithm>
 #include <cmath>
@@ -55,6 +62,10 @@ struct Batch::PhaseWork {
   const int* dSmall = nullptr; const int* dLarge = nullptr;
   // observation pools referenced in place (snapshot entry points): copied straight into the pinned blob
   const int* ext_obs_clone = nullptr; const double* ext_obs_z = nullptr; size_t ext_nobs = 0;
+  // observation pools already on the device (end-to-end call: uploaded ahead for the early triangulation)
+  const int* pre_dOc = nullptr; const double* pre_dOz = nullptr;
+  bool obs_preuploaded = false;
+  size_t off[8] = {0};           // blob section offsets (stage_pack -> stage_upload)
   size_t n_obs() const { return ext_obs_clone ? ext_nobs : obs_clone.size(); }
   void reset() {                 // keep the vectors' capacity across frames
     cands.clear(); obs_clone.clear(); obs_z.clear(); tiles.clear(); fw.clear();
@@ -64,6 +75,7 @@ struct Batch::PhaseWork {
     any_active = false; d_extra = nullptr;
     dC = nullptr; dOc = nullptr; dOz = nullptr; dTiles = nullptr; dFw = nullptr; dSmall = dLarge = nullptr;
     ext_obs_clone = nullptr; ext_obs_z = nullptr; ext_nobs = 0;
+    pre_dOc = nullptr; pre_dOz = nullptr; obs_preuploaded = false;
   }
 };
 
@@ -182,6 +194,9 @@ Batch::~Batch() {
   cudaFree(dR_); cudaFree(dS_); cudaFree(dRthin_); cudaFree(dYv_); cudaFree(dT_); cudaFree(dDx_);
   cudaFree(dErr_); cudaFree(dFront_); cudaFree(dChi2_);
   cudaFree(dAmat_); cudaFree(dPart_);
+  cudaFree(dStatusF_);
+  if (blob_early_.dev) cudaFree(blob_early_.dev);
+  if (blob_early_.pinned) cudaFreeHost(blob_early_.pinned);
   cudaFree(dLs_); cudaFree(dTileRows_); cudaFree(dFilterRows_); cudaFree(dSyrkCnt_);
   if (dZuptDec_) cudaFree(dZuptDec_);
   if (dZuptInfo_) cudaFree(dZuptInfo_);
@@ -299,11 +314,13 @@ void Batch::run_phase(PhaseWork& w, int phase) {
 }
 
 // Pack the work lists of one phase into the pinned blob and upload them (one H2D copy).
-void Batch::stage_phase(PhaseWork& w) {
+// Host half of the staging: carve the pinned blob and copy the work lists into it (no CUDA call as long as the
+// pinned capacity suffices -- the end-to-end call reserves it up front and runs this on its helper thread).
+void Batch::stage_pack(PhaseWork& w) {
   const int nC = (int)w.cands.size();
   blob_.reset();
   const size_t o_c = blob_.reserve(sizeof(Cand) * std::max(nC, 1));
-  const size_t n_obs = w.n_obs();
+  const size_t n_obs = w.obs_preuploaded ? 0 : w.n_obs();
   const size_t o_oc = blob_.reserve(sizeof(int) * std::max<size_t>(n_obs, 1));
   const size_t o_oz = blob_.reserve(sizeof(double) * std::max<size_t>(2 * n_obs, 1));
   const size_t o_t = blob_.reserve(sizeof(Tile) * std::max<size_t>(w.tiles.size(), 1));
@@ -322,6 +339,15 @@ void Batch::stage_phase(PhaseWork& w) {
   std::memcpy(h + o_f, w.fw.data(), sizeof(FilterWork) * B_);
   if (!w.small_list.empty()) std::memcpy(h + o_s, w.small_list.data(), sizeof(int) * w.small_list.size());
   if (!w.large_list.empty()) std::memcpy(h + o_l, w.large_list.data(), sizeof(int) * w.large_list.size());
+  w.off[0] = o_c; w.off[1] = o_oc; w.off[2] = o_oz; w.off[3] = o_t; w.off[4] = o_f; w.off[5] = o_s; w.off[6] = o_l;
+  w.off[7] = o_x;
+}
+
+// Device half: grow the scratch buffers, upload the blob, publish the device views of the lists.
+void Batch::stage_upload(PhaseWork& w) {
+  const int nC = (int)w.cands.size();
+  const size_t o_c = w.off[0], o_oc = w.off[1], o_oz = w.off[2], o_t = w.off[3], o_f = w.off[4], o_s = w.off[5],
+               o_l = w.off[6], o_x = w.off[7];
   ensure_scratch(std::max(nC, 1), std::max<size_t>(w.hblk_total, 1), std::max<size_t>(w.rows_total, 1),
                  std::max<size_t>(w.tileout_total, 1));
   if (!compress_qr_) {          // scratch of the whitened-form path, grown outside any timed region
@@ -349,13 +375,18 @@ void Batch::stage_phase(PhaseWork& w) {
   upload_blob();
   char* d = blob_.dev;
   w.dC = (const Cand*)(d + o_c);
-  w.dOc = (const int*)(d + o_oc);
-  w.dOz = (const double*)(d + o_oz);
+  w.dOc = w.obs_preuploaded ? w.pre_dOc : (const int*)(d + o_oc);
+  w.dOz = w.obs_preuploaded ? w.pre_dOz : (const double*)(d + o_oz);
   w.dTiles = (const Tile*)(d + o_t);
   w.dFw = (const FilterWork*)(d + o_f);
   w.dSmall = (const int*)(d + o_s);
   w.dLarge = (const int*)(d + o_l);
   w.d_extra = (const int*)(d + o_x);
+}
+
+void Batch::stage_phase(PhaseWork& w) {
+  stage_pack(w);
+  stage_upload(w);
 }
 
 UpdArgs Batch::upd_args(const FilterWork* dFw) const {
@@ -410,7 +441,7 @@ void Batch::launch_phase(PhaseWork& w, bool download, bool prior_in_flight) {
     CK(cudaMalloc(&dRawHf_, raw_cap_ * 6 * sizeof(double)));
     CK(cudaMalloc(&dRawR_, raw_cap_ * 2 * sizeof(double)));
   }
-  if (nC > 0 && !skip_tri_) {
+  if (nC > 0 && !skip_tri_ && !tri_done_early_) {
     TriArgs ta{};
     ta.cand = dC; ta.n_cand = nC;
     ta.clones = dClones_; ta.clone_stride = (size_t)Ncap_ * CL_STRIDE;
@@ -435,6 +466,7 @@ void Batch::launch_phase(PhaseWork& w, bool download, bool prior_in_flight) {
     ja.status = dStatus_; ja.gamma = dGamma_;
     ja.hblk = dHblk_; ja.rblk = dRblk_;
     if (want_raw_) { ja.raw_Hx = dRawHx_; ja.raw_He = dRawHe_; ja.raw_Hf = dRawHf_; ja.raw_r = dRawR_; }
+    ja.tri_status_f = tri_done_early_ ? dStatusF_ : nullptr;
     JacArgs js = ja, jl = ja;
     js.cand_list = dSmall; js.n_list = (int)w.small_list.size();
     jl.cand_list = dLarge; jl.n_list = (int)w.large_list.size();
@@ -470,12 +502,72 @@ void Batch::launch_phase(PhaseWork& w, bool download, bool prior_in_flight) {
     if (profiling_) CK(cudaEventRecord(e[5], stream_));
   }
   launches_ += nl;
+  tri_done_early_ = false;
   if (launch_error_count() > 0) { ok_ = false; err_ = "kernel launch failed"; }
   if (nC > 0 && download) {
     CK(cudaMemcpyAsync(hStatus_, dStatus_, sizeof(int) * nC, cudaMemcpyDeviceToHost, stream_));
     CK(cudaMemcpyAsync(hGamma_, dGamma_, sizeof(double) * nC, cudaMemcpyDeviceToHost, stream_));
   }
 }
+
+// One persistent helper thread for host-side list building (sleeps on a condition variable between frames).
+class HostWorker {
+ public:
+  HostWorker() : th_([this] { loop(); }) {}
+  ~HostWorker() {
+    { std::lock_guard<std::mutex> g(m_); quit_ = true; }
+    cv_.notify_one();
+    th_.join();
+  }
+  void run(std::function<void()> f) {
+    { std::lock_guard<std::mutex> g(m_); job_ = std::move(f); has_job_ = true; }
+    cv_.notify_one();
+  }
+ private:
+  void loop() {
+    for (;;) {
+      std::function<void()> f;
+      {
+        std::unique_lock<std::mutex> g(m_);
+        cv_.wait(g, [this] { return has_job_ || quit_; });
+        if (quit_) return;
+        f = std::move(job_);
+        has_job_ = false;
+      }
+      f();
+    }
+  }
+  std::mutex m_;
+  std::condition_variable cv_;
+  std::function<void()> job_;
+  bool has_job_ = false, quit_ = false;
+  std::thread th_;
+};
+
+// ORCVIO_HOST_PROF=1: wall-clock checkpoints of the end-to-end host path (mean over calls, printed every 64 calls)
+struct HostProf {
+  static constexpr int K = 12;
+  double acc[K] = {0};
+  const char* name[K] = {nullptr};
+  int n = 0, calls = 0;
+  std::chrono::steady_clock::time_point t;
+  bool on = env_int("ORCVIO_HOST_PROF", 0) != 0;
+  void start() { if (on) { t = std::chrono::steady_clock::now(); n = 0; } }
+  void mark(const char* what) {
+    if (!on || n >= K) return;
+    const auto now = std::chrono::steady_clock::now();
+    acc[n] += std::chrono::duration<double, std::micro>(now - t).count();
+    name[n++] = what;
+    t = now;
+  }
+  void done() {
+    if (!on || ++calls % 64) return;
+    std::fprintf(stderr, "[host prof]");
+    for (int i = 0; i < n; ++i) { std::fprintf(stderr, " %s %.1f", name[i], acc[i] / 64); acc[i] = 0; }
+    std::fprintf(stderr, "\n");
+  }
+};
+static HostProf g_hp;
 
 static void build_tiles(Batch::PhaseWork& w, int fi, int c0, int c1) {
   FilterWork& fw = w.fw[fi];
@@ -1202,6 +1294,9 @@ struct Batch::SnapState {
   FilterWork* hFw = nullptr; FilterWork* dFw = nullptr;   // (N, D) record for the early prior launch
   int* hErr = nullptr;
   bool prior_early = false;
+  bool tri_early = false;          // k_triangulate (direct mode) already queued by snapshot_prepare
+  int list_err = 0;                // result of the (possibly threaded) work-list build
+  std::atomic<int> scan_done{0}, lists_done{0};
   ~SnapState() {
     cudaFree(dFw);
     if (hFw) cudaFreeHost(hFw);
@@ -1236,6 +1331,7 @@ int Batch::snapshot_prepare(const SnapshotIO& io) {
     CK(cudaMallocHost(&S.hErr, sizeof(int)));
   }
   SnapState& S = *snap_;
+  g_hp.start();
   if (io.n_feat > Fcap_) {
     // grow the feature tables of this (single filter) batch
     CK(cudaStreamSynchronize(stream_));
@@ -1248,6 +1344,99 @@ int Batch::snapshot_prepare(const SnapshotIO& io) {
   S.N = N; S.D = D; S.n_feat = io.n_feat;
   // the staging buffers may still be read by the previous call's async copies
   CK(cudaStreamSynchronize(stream_));
+  g_hp.mark("sync");
+  PhaseWork& w = S.w;
+  w.reset();
+  w.rows_cap = compress_qr_ ? 0 : AFORM_TILE_ROWS;
+  w.fw.assign(B_, FilterWork{});
+  w.cand_begin.assign(B_ + 1, 0);
+  FilterWork& fw = w.fw[0];
+  fw.N = N; fw.D = D; fw.active = (io.stages & 4) ? 1 : 0;
+  w.any_active = fw.active;
+  w.maxN = N;
+  // observations are referenced in place and copied once, straight into the pinned upload blob
+  const int nF = io.n_feat;
+  const int nobs_total = io.feat_off[nF];
+  S.nobs_total = nobs_total;
+  w.ext_obs_clone = io.obs_clone; w.ext_obs_z = io.obs_z; w.ext_nobs = (size_t)nobs_total;
+  // candidates sorted by first clone block, then feature index: a counting sort (what
+  // append_candidates' stable sort produces, without the comparison sort)
+  // The work lists (validation, counting sort, candidate records, tiles) are pure host work on the caller's
+  // arrays: in the end-to-end call a helper thread builds them while this thread stages P, starts the prior
+  // factor, uploads the observation pools and starts the early triangulation.
+  const bool early_tri = io.early_prior && (io.stages & 1) && (io.stages & 2) && !io.positions_in && !io.iters &&
+                         !io.cost && nF > 0;
+  w.obs_preuploaded = early_tri;
+  blob_.ensure_pinned(4096 + (size_t)std::max(nF, 1) * (sizeof(Cand) + sizeof(Tile) + 2 * sizeof(int)) +
+                      sizeof(FilterWork) * B_ + (early_tri ? 0 : (size_t)nobs_total * 20));
+  S.list_err = ORCVIO_OK;
+  S.scan_done.store(0, std::memory_order_relaxed);
+  S.lists_done.store(0, std::memory_order_relaxed);
+  auto build_lists = [this, &S, &w, io, nF, N]() {
+    int* err = &S.list_err;
+    int bucket[ORCVIO_MAX_OBS + 2] = {0};
+    auto scan = [&]() {
+      S.sblk.resize(nF);
+      S.eblk.resize(nF);
+      for (int f = 0; f < nF; ++f) {
+        const int o0 = io.feat_off[f], m = io.feat_off[f + 1] - o0;
+        if (m < 1 || m > ORCVIO_MAX_OBS) { *err = ORCVIO_ERR_ARG; return; }
+        int s = 1 << 30, e = -1;
+        for (int k = 0; k < m; ++k) {
+          const int ci = io.obs_clone[o0 + k];
+          if (ci < 0 || ci >= N) { *err = ORCVIO_ERR_ARG; return; }
+          s = std::min(s, ci);
+          e = std::max(e, ci);
+        }
+        S.sblk[f] = s; S.eblk[f] = e;
+        ++bucket[s + 1];
+      }
+    };
+    scan();
+    S.scan_done.store(1, std::memory_order_release);
+    if (*err == ORCVIO_OK) {
+      for (int k = 1; k <= ORCVIO_MAX_OBS + 1; ++k) bucket[k] += bucket[k - 1];
+      S.order.resize(nF);
+      for (int f = 0; f < nF; ++f) S.order[bucket[S.sblk[f]]++] = f;
+      w.cands.resize(nF);
+      for (int pos = 0; pos < nF; ++pos) {
+        const int f = S.order[pos];
+        const int o0 = io.feat_off[f], m = io.feat_off[f + 1] - o0;
+        Cand& c = w.cands[pos];
+        c.filter = 0;
+        c.slot = f;
+        c.gen = f + 1;
+        c.flags = CAND_FORCE_TRI;
+        c.tri_off = c.jac_off = o0;
+        c.tri_m = c.jac_m = m;
+        c.s_blk = S.sblk[f]; c.e_blk = S.eblk[f];
+        c.cm_first_clone = io.obs_clone[o0];
+        c.cm_last_clone = io.obs_clone[o0 + m - 1];
+        c.cm_zu = io.obs_z[2 * (size_t)o0];
+        c.cm_zv = io.obs_z[2 * (size_t)o0 + 1];
+        const int r = std::max(2 * m - 3, 0), wb = c.e_blk - c.s_blk + 1;
+        c.row_off = (int)w.rows_total;
+        c.hblk_off = (int)w.hblk_total;
+        w.rows_total += (size_t)r;
+        w.hblk_total += (size_t)r * 6 * wb;
+        w.own_wmax_blk = std::max(w.own_wmax_blk, wb);
+        if (m <= 8) w.small_list.push_back(pos);
+        else w.large_list.push_back(pos);
+      }
+      build_tiles(w, 0, 0, nF);
+    }
+    S.lists_done.store(1, std::memory_order_release);
+  };
+  const bool threaded = io.early_prior && nF >= 512;
+  if (threaded) {
+    if (!worker_) worker_.reset(new HostWorker());
+    worker_->run(build_lists);
+  } else {
+    build_lists();
+  }
+  auto wait_flag = [](std::atomic<int>& f) {
+    while (!f.load(std::memory_order_acquire)) std::this_thread::yield();
+  };
   // ---- host staging of the window
   double* cl = S.hCl0;
   double* im = S.hIm0;
@@ -1289,6 +1478,7 @@ int Batch::snapshot_prepare(const SnapshotIO& io) {
   } else {
     std::memset(S.hP0, 0, (size_t)ldp_ * ldp_ * sizeof(double));
   }
+  g_hp.mark("stageP");
   CK(cudaMemcpyAsync(S.dP0, S.hP0, (size_t)ldp_ * ldp_ * sizeof(double), cudaMemcpyHostToDevice, stream_));
   S.prior_early = false;
   if ((io.stages & 4) && !compress_qr_ && io.early_prior) {
@@ -1307,71 +1497,61 @@ int Batch::snapshot_prepare(const SnapshotIO& io) {
   }
   CK(cudaMemcpyAsync(S.dCl0, S.hCl0, (size_t)Ncap_ * CL_STRIDE * sizeof(double), cudaMemcpyHostToDevice, stream_));
   CK(cudaMemcpyAsync(S.dIm0, S.hIm0, IM_STRIDE * sizeof(double), cudaMemcpyHostToDevice, stream_));
+  g_hp.mark("prior_launch");
   FilterHost& F = f_[0];
   F.clones.clear();
   for (int c = 0; c < N; ++c) F.clones.push_back(CloneMeta{c, (double)c, 0.0});
 
-  PhaseWork& w = S.w;
-  w.reset();
-  w.rows_cap = compress_qr_ ? 0 : AFORM_TILE_ROWS;
-  w.fw.assign(B_, FilterWork{});
-  w.cand_begin.assign(B_ + 1, 0);
-  FilterWork& fw = w.fw[0];
-  fw.N = N; fw.D = D; fw.active = (io.stages & 4) ? 1 : 0;
-  w.any_active = fw.active;
-  w.maxN = N;
-  // observations are referenced in place and copied once, straight into the pinned upload blob
-  const int nF = io.n_feat;
-  const int nobs_total = io.feat_off[nF];
-  S.nobs_total = nobs_total;
-  w.ext_obs_clone = io.obs_clone; w.ext_obs_z = io.obs_z; w.ext_nobs = (size_t)nobs_total;
-  // candidates sorted by first clone block, then feature index: a counting sort (what
-  // append_candidates' stable sort produces, without the comparison sort)
-  S.sblk.resize(nF);
-  S.eblk.resize(nF);
-  int bucket[ORCVIO_MAX_OBS + 2] = {0};
-  for (int f = 0; f < nF; ++f) {
-    const int o0 = io.feat_off[f], m = io.feat_off[f + 1] - o0;
-    if (m < 1 || m > ORCVIO_MAX_OBS) return ORCVIO_ERR_ARG;
-    int s = 1 << 30, e = -1;
-    for (int k = 0; k < m; ++k) {
-      const int ci = io.obs_clone[o0 + k];
-      if (ci < 0 || ci >= N) return ORCVIO_ERR_ARG;
-      s = std::min(s, ci);
-      e = std::max(e, ci);
+  wait_flag(S.scan_done);
+  g_hp.mark("scan_wait");
+  if (S.list_err != ORCVIO_OK) {
+    wait_flag(S.lists_done);
+    return S.list_err;
+  }
+  // Early triangulation (end-to-end call): the inputs are validated, so upload the caller's observation pools
+  // as they are and start k_triangulate in direct mode now -- it runs (beside the prior factor) while the host
+  // sorts the candidates, builds the tiles and uploads the work lists below.
+  S.tri_early = false;
+  if (early_tri) {
+    blob_early_.reset();
+    const size_t e_fo = blob_early_.reserve(sizeof(int) * (size_t)(nF + 1));
+    const size_t e_oc = blob_early_.reserve(sizeof(int) * (size_t)nobs_total);
+    const size_t e_oz = blob_early_.reserve(sizeof(double) * 2 * (size_t)nobs_total);
+    std::memcpy(blob_early_.pinned + e_fo, io.feat_off, sizeof(int) * (size_t)(nF + 1));
+    std::memcpy(blob_early_.pinned + e_oc, io.obs_clone, sizeof(int) * (size_t)nobs_total);
+    std::memcpy(blob_early_.pinned + e_oz, io.obs_z, sizeof(double) * 2 * (size_t)nobs_total);
+    if (blob_early_.used > blob_early_.dev_cap) {
+      if (blob_early_.dev) cudaFree(blob_early_.dev);
+      blob_early_.dev_cap = blob_early_.used * 2 + 4096;
+      CK(cudaMalloc(&blob_early_.dev, blob_early_.dev_cap));
     }
-    S.sblk[f] = s; S.eblk[f] = e;
-    ++bucket[s + 1];
+    if ((size_t)nF > statusf_cap_) {
+      if (dStatusF_) cudaFree(dStatusF_);
+      statusf_cap_ = (size_t)nF * 2 + 1024;
+      CK(cudaMalloc(&dStatusF_, statusf_cap_ * sizeof(int)));
+    }
+    CK(cudaMemcpyAsync(blob_early_.dev, blob_early_.pinned, blob_early_.used, cudaMemcpyHostToDevice, stream_));
+    // the window the kernels work on (snapshot_execute skips these restores for this run)
+    CK(cudaMemcpyAsync(dClones_, S.dCl0, (size_t)Ncap_ * CL_STRIDE * sizeof(double), cudaMemcpyDeviceToDevice, stream_));
+    CK(cudaMemcpyAsync(dImu_, S.dIm0, IM_STRIDE * sizeof(double), cudaMemcpyDeviceToDevice, stream_));
+    CK(cudaMemsetAsync(dFgen_, 0xFF, (size_t)Fcap_ * sizeof(long long), stream_));
+    w.pre_dOc = (const int*)(blob_early_.dev + e_oc);
+    w.pre_dOz = (const double*)(blob_early_.dev + e_oz);
+    TriArgs ta{};
+    ta.cand = nullptr; ta.n_cand = nF;
+    ta.clones = dClones_; ta.clone_stride = (size_t)Ncap_ * CL_STRIDE;
+    ta.fpos = dFpos_; ta.fgen = dFgen_; ta.fcap = Fcap_;
+    ta.obs_clone = w.pre_dOc; ta.obs_z = w.pre_dOz;
+    ta.cfg = tricfg_;
+    ta.status = dStatusF_;
+    ta.feat_off = (const int*)(blob_early_.dev + e_fo);
+    launch_triangulate(ta, stream_);
+    ++launches_;
+    S.tri_early = true;
+    g_hp.mark("tri_early");
   }
-  for (int k = 1; k <= ORCVIO_MAX_OBS + 1; ++k) bucket[k] += bucket[k - 1];
-  S.order.resize(nF);
-  for (int f = 0; f < nF; ++f) S.order[bucket[S.sblk[f]]++] = f;
-  w.cands.resize(nF);
-  for (int pos = 0; pos < nF; ++pos) {
-    const int f = S.order[pos];
-    const int o0 = io.feat_off[f], m = io.feat_off[f + 1] - o0;
-    Cand& c = w.cands[pos];
-    c.filter = 0;
-    c.slot = f;
-    c.gen = f + 1;
-    c.flags = CAND_FORCE_TRI;
-    c.tri_off = c.jac_off = o0;
-    c.tri_m = c.jac_m = m;
-    c.s_blk = S.sblk[f]; c.e_blk = S.eblk[f];
-    c.cm_first_clone = io.obs_clone[o0];
-    c.cm_last_clone = io.obs_clone[o0 + m - 1];
-    c.cm_zu = io.obs_z[2 * (size_t)o0];
-    c.cm_zv = io.obs_z[2 * (size_t)o0 + 1];
-    const int r = std::max(2 * m - 3, 0), wb = c.e_blk - c.s_blk + 1;
-    c.row_off = (int)w.rows_total;
-    c.hblk_off = (int)w.hblk_total;
-    w.rows_total += (size_t)r;
-    w.hblk_total += (size_t)r * 6 * wb;
-    w.own_wmax_blk = std::max(w.own_wmax_blk, wb);
-    if (m <= 8) w.small_list.push_back(pos);
-    else w.large_list.push_back(pos);
-  }
-  build_tiles(w, 0, 0, nF);
+  wait_flag(S.lists_done);
+  g_hp.mark("lists_wait");
   const int nC = nF;
 
   S.has_positions = io.positions_in != nullptr;
@@ -1396,7 +1576,10 @@ int Batch::snapshot_prepare(const SnapshotIO& io) {
   skip_tri_ = !(io.stages & 1);
   skip_jac_ = !(io.stages & 2);
   skip_update_ = !(io.stages & 4);
+  // (packing the blob on the helper thread as well was measured: the H2D copy of lines last written by
+  // another core delays the GPU by ~60 us -- the copy into the pinned blob stays on this thread)
   stage_phase(w);
+  g_hp.mark("stage_blob");
   if (skip_tri_ && nC > 0) {
     std::vector<int> st(nC, ST_TRI_VALID);
     CK(cudaMemcpy(dStatus_, st.data(), sizeof(int) * nC, cudaMemcpyHostToDevice));
@@ -1412,15 +1595,20 @@ int Batch::snapshot_execute(bool download) {
   S.prior_early = false;
   if (!prior_in_flight)
     CK(cudaMemcpyAsync(dP_, S.dP0, (size_t)ldp_ * ldp_ * sizeof(double), cudaMemcpyDeviceToDevice, stream_));
-  CK(cudaMemcpyAsync(dClones_, S.dCl0, (size_t)Ncap_ * CL_STRIDE * sizeof(double), cudaMemcpyDeviceToDevice, stream_));
-  CK(cudaMemcpyAsync(dImu_, S.dIm0, IM_STRIDE * sizeof(double), cudaMemcpyDeviceToDevice, stream_));
-  if (S.has_positions) {
-    CK(cudaMemcpyAsync(dFpos_, S.dPos0, (size_t)Fcap_ * FP_STRIDE * sizeof(double), cudaMemcpyDeviceToDevice, stream_));
-    CK(cudaMemcpyAsync(dFgen_, S.dGen0, (size_t)Fcap_ * sizeof(long long), cudaMemcpyDeviceToDevice, stream_));
-  } else {
-    CK(cudaMemsetAsync(dFgen_, 0xFF, (size_t)Fcap_ * sizeof(long long), stream_));
+  tri_done_early_ = S.tri_early;                    // window restored and k_triangulate started by snapshot_prepare
+  S.tri_early = false;
+  if (!tri_done_early_) {
+    CK(cudaMemcpyAsync(dClones_, S.dCl0, (size_t)Ncap_ * CL_STRIDE * sizeof(double), cudaMemcpyDeviceToDevice, stream_));
+    CK(cudaMemcpyAsync(dImu_, S.dIm0, IM_STRIDE * sizeof(double), cudaMemcpyDeviceToDevice, stream_));
+    if (S.has_positions) {
+      CK(cudaMemcpyAsync(dFpos_, S.dPos0, (size_t)Fcap_ * FP_STRIDE * sizeof(double), cudaMemcpyDeviceToDevice, stream_));
+      CK(cudaMemcpyAsync(dFgen_, S.dGen0, (size_t)Fcap_ * sizeof(long long), cudaMemcpyDeviceToDevice, stream_));
+    } else {
+      CK(cudaMemsetAsync(dFgen_, 0xFF, (size_t)Fcap_ * sizeof(long long), stream_));
+    }
   }
   launch_phase(S.w, download, prior_in_flight);
+  g_hp.mark("launch");
   return ok_ ? ORCVIO_OK : ORCVIO_ERR_CUDA;
 }
 
@@ -1441,6 +1629,7 @@ int Batch::snapshot_fetch(const SnapshotIO& io) {
   if (io.r_thin) CK(cudaMemcpyAsync(hR + (size_t)n * ldr_, dRthin_, n * sizeof(double), cudaMemcpyDeviceToHost, stream_));
   CK(cudaMemcpyAsync(S.hErr, dErr_, sizeof(int), cudaMemcpyDeviceToHost, stream_));
   CK(cudaStreamSynchronize(stream_));
+  g_hp.mark("gpu_wait");
   if (io.status || io.gamma)
     for (int c = 0; c < nC; ++c) {
       if (io.status) io.status[S.order[c]] = hStatus_[c];
@@ -1481,6 +1670,8 @@ int Batch::snapshot_fetch(const SnapshotIO& io) {
       for (int k = 0; k < 9; ++k) io.clone_out[12 * (size_t)c + k] = hCl[(size_t)c * CL_STRIDE + CL_R + k];
       for (int k = 0; k < 3; ++k) io.clone_out[12 * (size_t)c + 9 + k] = hCl[(size_t)c * CL_STRIDE + CL_P + k];
     }
+  g_hp.mark("unpack");
+  g_hp.done();
   if (*S.hErr) return ORCVIO_ERR_CAPACITY;
   return ok_ ? ORCVIO_OK : ORCVIO_ERR_CUDA;
 }

@@ -95,6 +95,15 @@ struct Blob {                 // one pinned host blob + device twin, carved into
     return off;
   }
   void reset() { used = 0; }
+  void ensure_pinned(size_t bytes) {      // grow the pinned half ahead of time (contents are not preserved)
+    if (bytes <= pinned_cap) return;
+    char* np = nullptr;
+    const size_t ncap = bytes * 2 + 4096;
+    if (cudaMallocHost(&np, ncap) != cudaSuccess) return;
+    if (pinned) cudaFreeHost(pinned);
+    pinned = np;
+    pinned_cap = ncap;
+  }
 };
 
 struct PhaseTimes {
@@ -216,6 +225,11 @@ class Batch {
   double* dGamma_ = nullptr;
   size_t cand_cap_ = 0;
   Blob blob_;
+  Blob blob_early_;                    // feat_off + observation pools of the end-to-end call, uploaded ahead
+  int* dStatusF_ = nullptr;            // triangulation status by feature slot (early direct-mode pass)
+  size_t statusf_cap_ = 0;
+  bool tri_done_early_ = false;
+  std::shared_ptr<class HostWorker> worker_;   // helper thread of the end-to-end frame call (batch.cu)
   // pinned download buffers
   int* hStatus_ = nullptr;
   double* hGamma_ = nullptr;
@@ -235,6 +249,8 @@ class Batch {
   void ensure_scratch(size_t n_cand, size_t hblk, size_t rblk, size_t tileout);
   void run_phase(PhaseWork& w, int phase);
   void stage_phase(PhaseWork& w);
+  void stage_pack(PhaseWork& w);
+  void stage_upload(PhaseWork& w);
   void launch_phase(PhaseWork& w, bool download, bool prior_in_flight = false);
   UpdArgs upd_args(const FilterWork* dFw) const;
   struct SnapState;

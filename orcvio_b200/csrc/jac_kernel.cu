@@ -130,7 +130,8 @@ __global__ void __launch_bounds__(128, MINB) k_jac_gate(JacArgs a) {
   if (li >= a.n_list) return;
   const int c = a.cand_list ? a.cand_list[li] : li;
   const Cand cd = a.cand[c];
-  const int st_in = a.status[c];
+  const int st_in = a.tri_status_f ? a.tri_status_f[cd.slot] : a.status[c];
+  if (a.tri_status_f && lane == 0) a.status[c] = st_in;      // status by candidate, as the one-pass flow leaves it
   if (!(st_in & ST_TRI_VALID)) {
     if (lane == 0) a.gamma[c] = -1.0;
     return;

@@ -61,6 +61,10 @@ struct TriArgs {
   const int* obs_clone; const double* obs_z;
   TriCfg cfg;
   int* status; int* iters; double* cost;
+  // direct mode (end-to-end frame call): when feat_off != nullptr the kernel runs over the caller's features in
+  // their own order (candidate c == feature c, slot c, forced triangulation) without any Cand record, so it can
+  // start while the host still sorts the candidates and builds the tiles; status is then indexed by feature
+  const int* feat_off;
 };
 
 struct JacArgs {
@@ -71,6 +75,7 @@ struct JacArgs {
   const int* obs_clone; const double* obs_z;
   int flags; double sigma2; const double* chi2;  // chi2[dof], dof < 500
   int* status; double* gamma;
+  const int* tri_status_f;                       // != nullptr: triangulation status by feature slot (direct mode)
   double* hblk; double* rblk;                    // compact projected blocks / residuals
   // optional raw per-observation outputs (orcvio_measurement_jacobians)
   double* raw_Hx; double* raw_He; double* raw_Hf; double* raw_r;

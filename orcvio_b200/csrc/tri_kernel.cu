@@ -295,7 +295,18 @@ __global__ void __launch_bounds__(32 * TRI_WARPS, MINB) k_triangulate(TriArgs a)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int c = blockIdx.x * TRI_WARPS + warp;
   if (c >= a.n_cand) return;
-  const Cand cd = a.cand[c];
+  Cand cd;
+  if (a.feat_off) {                   // direct mode: feature c of the caller's list
+    const int o0 = a.feat_off[c], m = a.feat_off[c + 1] - o0;
+    cd.filter = 0; cd.slot = c; cd.gen = c + 1; cd.flags = CAND_FORCE_TRI;
+    cd.tri_off = o0; cd.tri_m = m;
+    cd.cm_first_clone = a.obs_clone[o0];
+    cd.cm_last_clone = a.obs_clone[o0 + m - 1];
+    cd.cm_zu = a.obs_z[2 * (size_t)o0];
+    cd.cm_zv = a.obs_z[2 * (size_t)o0 + 1];
+  } else {
+    cd = a.cand[c];
+  }
   const double* clones = a.clones + (size_t)cd.filter * a.clone_stride;
   double* fp = a.fpos + ((size_t)cd.filter * a.fcap + cd.slot) * FP_STRIDE;
   long long* fgen = a.fgen + (size_t)cd.filter * a.fcap + cd.slot;
