@@ -580,7 +580,7 @@ static void build_tiles(Batch::PhaseWork& w, int fi, int c0, int c1) {
     t.cand_begin = i;
     t.c0_blk = w.cands[i].s_blk;
     t.c1_blk = w.cands[i].e_blk + 1;
-    t.rows = 2 * w.cands[i].jac_m - 3;
+    t.rows = std::max(2 * w.cands[i].jac_m - 3, 0);        // a one-observation track has no projected row
     int j = i + 1;
     while (j < c1) {
       const Cand& c = w.cands[j];
@@ -589,7 +589,7 @@ static void build_tiles(Batch::PhaseWork& w, int fi, int c0, int c1) {
       const int own = c.e_blk - c.s_blk + 1;
       const int wlim = (w.rows_cap > 0) ? 6 : WTILE_MAX_BLK;   // whitened form: keep the 36-column kernel
       if (wblk > std::max(wlim, own) && c.s_blk != t.c0_blk) break;
-      const int rows = t.rows + 2 * c.jac_m - 3;
+      const int rows = t.rows + std::max(2 * c.jac_m - 3, 0);
       int cap = qr_tile_rows_cap(6 * wblk);
       if (w.rows_cap > 0) cap = std::min(w.rows_cap, QR_SMEM_BYTES / 8 / ((6 * wblk + 4) & ~3));
       if (rows > cap) break;
