@@ -217,6 +217,27 @@ int orcvio_measurement_jacobians(const double* clone_R, const double* clone_p, i
                                  const int* feat_off, const int* obs_clone, const double* obs_z,
                                  int n_feat, int flags, double* Hx, double* He, double* Hf, double* r);
 
+/* Hybrid EKF-SLAM feature rows, stage level (feature_idp_dim 1, no Schmidt, no FEJ).
+ * H1, measurementJacobian_ekf_1didp (orcvio.cpp:1356-1478): feature f is anchored in clone anchor[f] with inverse
+ * depth inv_depth[f] along the anchor-frame bearing (f_an[2f], f_an[2f+1], 1); positions[3f..] is its world
+ * position as the map server holds it.  Per observation (CSR feat_off / obs_clone / obs_z), row-major:
+ * H_f (2), H_a (2x6, anchor pose), H_x (2x6, observing clone), H_e (2x6, extrinsics), r (2); an observation taken
+ * by the anchor clone itself returns zeros (:1433-1441). */
+int orcvio_ekf_measurement_jacobians(const double* clone_R, const double* clone_p, int n_clones,
+                                     const double* R_b2c, const double* t_c_b, const int* anchor,
+                                     const double* inv_depth, const double* f_an, const double* positions,
+                                     const int* feat_off, const int* obs_clone, const double* obs_z, int n_feat,
+                                     double* H_f, double* H_a, double* H_x, double* H_e, double* r);
+
+/* H2, featureJacobian_ekf (orcvio.cpp:1575-1651) + gatingTestFeature with dof 2 (:1953-1976): the n_feat features
+ * of the state (feature f = state column 22 + 6 n_clones + f) observed at z_cur[2f..] by the newest clone.
+ * P: D x D covariance, D = 22 + 6 n_clones + n_feat (symmetric: row- or column-major).
+ * Outputs: H (2 n_feat x D, row-major), r (2 n_feat), gamma (n_feat), pass (n_feat). */
+int orcvio_ekf_feature_rows(const double* clone_R, const double* clone_p, int n_clones, const double* R_b2c,
+                            const double* t_c_b, const int* anchor, const double* inv_depth, const double* f_an,
+                            const double* positions, const double* z_cur, int n_feat, const double* P, int D,
+                            double noise_var, double chi2_p, double* H, double* r, double* gamma, int* pass);
+
 /* Stage 3 (O1-O4): keypoint + bbox residuals and Jacobians of one object over T frames.
  * frames_wTc: T x 16 (row-major 4x4), wTo 16, shape 3, kps K x 3, zs T x K x 2 (NaN = not
  * observed), zb T x 4.  flags: bit0 left perturbation, bit1 new bbox residual.

@@ -1,0 +1,113 @@
+"""Oracle (test infrastructure, CPU restatement) for the hybrid EKF-SLAM feature rows of SURVEY 8a:
+
+  H1  measurementJacobian_ekf_1didp            reference src/orcvio.cpp:1356-1478
+  H2  featureJacobian_ekf / featureJacobian_ekf_new   reference src/orcvio.cpp:1575-1651 / 1481-1572
+
+restricted to what every shipped yaml uses: feature_idp_dim == 1 (1-D inverse depth), use_schmidt == 0 (the
+anchor is a clone of the window, never a nuisance state), if_FEJ == 0, estimate_td == 0.
+
+Parity unpinned by the reference (it has no test for these functions): pinned here by central differences of the
+measurement model the formulas differentiate (tests/test_oracle_hybrid_cpu.py) and by the CUDA kernel agreeing
+with this restatement (tests/test_gpu_hybrid.py).  Only tests/ may import this module.
+"""
+import numpy as np
+
+from . import mathutils as mu
+
+LEG_DIM = 22
+
+
+def measurement_jacobian_ekf_1didp(R_bk2w, t_bk_w, R_ba2w, t_ba_w, R_b2c, t_c_b, f_an, inv_depth, p_w, z,
+                                   same_state=False):
+    """:1356-1478.  Clone k observes a feature anchored in clone a with inverse depth `inv_depth` along the
+    anchor-frame bearing f_an = (x, y, 1); p_w is the feature's world position as stored in the map server
+    (the reference reads feature.position, it does not recompute it).  Returns H_f (2x1), H_a (2x6, anchor
+    pose), H_x (2x6, pose of clone k), H_e (2x6, extrinsics), r (2).  `same_state`: state_id == id_anchor,
+    for which the reference returns zeros (:1433-1441)."""
+    R_bk2w, R_ba2w, R_b2c = (np.asarray(a, dtype=float).reshape(3, 3) for a in (R_bk2w, R_ba2w, R_b2c))
+    t_bk_w, t_ba_w, t_c_b, f_an, p_w = (np.asarray(a, dtype=float).reshape(3) for a in (t_bk_w, t_ba_w, t_c_b, f_an, p_w))
+    z = np.asarray(z, dtype=float).reshape(2)
+    R_w2bk = R_bk2w.T
+    R_w2ck = R_b2c @ R_w2bk
+    t_ck_w = t_bk_w + R_bk2w @ t_c_b
+    R_w2ba = R_ba2w.T
+    R_w2ca = R_b2c @ R_w2ba
+    p_ca = np.array([f_an[0] / inv_depth, f_an[1] / inv_depth, 1.0 / inv_depth])
+    p_ck = R_w2ck @ (p_w - t_ck_w)
+    r = z - np.array([p_ck[0] / p_ck[2], p_ck[1] / p_ck[2]])
+    if same_state:
+        return np.zeros((2, 1)), np.zeros((2, 6)), np.zeros((2, 6)), np.zeros((2, 6)), np.zeros(2)
+    J_k = np.zeros((2, 3))
+    J_k[0, 0] = 1 / p_ck[2]
+    J_k[1, 1] = 1 / p_ck[2]
+    J_k[0, 2] = -p_ck[0] / (p_ck[2] * p_ck[2])
+    J_k[1, 2] = -p_ck[1] / (p_ck[2] * p_ck[2])
+    J_d = R_w2ck @ R_w2ca.T @ f_an
+    p_baf_w = p_w - t_ba_w
+    p_bkf_w = p_w - t_bk_w
+    J_xa = np.zeros((3, 6))
+    J_xa[:, :3] = -R_w2ck @ mu.skew(p_baf_w)
+    J_xa[:, 3:] = R_w2ck
+    J_xk = np.zeros((3, 6))
+    J_xk[:, :3] = R_w2ck @ mu.skew(p_bkf_w)
+    J_xk[:, 3:] = -R_w2ck
+    J_e = np.zeros((3, 6))
+    SkewMx = mu.skew(R_w2bk @ p_bkf_w - t_c_b)
+    Mx = R_w2bk @ R_w2ba.T @ mu.skew(R_b2c.T @ p_ca)
+    J_e[:, :3] = R_b2c @ (SkewMx - Mx)
+    J_e[:, 3:] = R_b2c @ (R_w2bk @ R_w2ba.T - np.eye(3))
+    J_rho = -1.0 / (inv_depth * inv_depth)
+    H_f = (J_k @ J_d * J_rho).reshape(2, 1)
+    return H_f, J_k @ J_xa, J_k @ J_xk, J_k @ J_e, r
+
+
+def feature_position_from_anchor(R_ba2w, t_ba_w, R_b2c, t_c_b, f_an, inv_depth):
+    """World position of an inverse-depth feature: p_w = R_ca2w p_ca + t_ca_w (measurementUpdate_hybrid
+    :1866-1877 with orientation_cam = R_b2w R_b2c^T, position_cam = t_b_w + R_b2w t_c_b)."""
+    R_ba2w, R_b2c = np.asarray(R_ba2w, dtype=float).reshape(3, 3), np.asarray(R_b2c, dtype=float).reshape(3, 3)
+    p_ca = np.array([f_an[0] / inv_depth, f_an[1] / inv_depth, 1.0 / inv_depth])
+    return R_ba2w @ R_b2c.T @ p_ca + (np.asarray(t_ba_w, dtype=float) + R_ba2w @ np.asarray(t_c_b, dtype=float))
+
+
+def feature_jacobian_ekf(clone_R, clone_p, R_b2c, t_c_b, k_idx, a_idx, feat_idx, n_feat_states, f_an, inv_depth,
+                         p_w, z):
+    """:1575-1651.  One EKF-SLAM feature already in the state, observed by the newest state (clone k_idx):
+    the 2 x D row block with H_f at the feature's column LEG + 6N + feat_idx, H_a at the anchor clone's block,
+    H_x at the observing clone's block, H_e at columns 15..20.  D = LEG + 6N + n_feat_states."""
+    N = len(clone_R)
+    D = LEG_DIM + 6 * N + n_feat_states
+    H_f, H_a, H_x, H_e, r = measurement_jacobian_ekf_1didp(clone_R[k_idx], clone_p[k_idx], clone_R[a_idx],
+                                                           clone_p[a_idx], R_b2c, t_c_b, f_an, inv_depth, p_w, z,
+                                                           same_state=(k_idx == a_idx))
+    H = np.zeros((2, D))
+    H[:, LEG_DIM + 6 * N + feat_idx] = H_f[:, 0]
+    H[:, LEG_DIM + 6 * a_idx:LEG_DIM + 6 * a_idx + 6] = H_a
+    H[:, LEG_DIM + 6 * k_idx:LEG_DIM + 6 * k_idx + 6] = H_x       # written after H_a like the reference (:1644-1645)
+    H[:, 15:21] = H_e
+    return H, r
+
+
+def feature_jacobian_ekf_new(clone_R, clone_p, R_b2c, t_c_b, obs_clone, obs_z, a_idx, feat_col, n_cols, f_an,
+                             inv_depth, p_w):
+    """:1481-1572.  A feature about to enter the state: rows for every observing clone except the anchor
+    (1-D inverse depth: the anchor observation carries no information, :1497-1498), with H_f at column `feat_col`
+    of an n_cols-wide block."""
+    rows = [(c, z) for c, z in zip(obs_clone, obs_z) if c != a_idx]
+    H = np.zeros((2 * len(rows), n_cols))
+    r = np.zeros(2 * len(rows))
+    for i, (c, z) in enumerate(rows):
+        H_f, H_a, H_x, H_e, r_i = measurement_jacobian_ekf_1didp(clone_R[c], clone_p[c], clone_R[a_idx], clone_p[a_idx],
+                                                                 R_b2c, t_c_b, f_an, inv_depth, p_w, z)
+        H[2 * i:2 * i + 2, feat_col] = H_f[:, 0]
+        H[2 * i:2 * i + 2, LEG_DIM + 6 * a_idx:LEG_DIM + 6 * a_idx + 6] = H_a
+        H[2 * i:2 * i + 2, LEG_DIM + 6 * c:LEG_DIM + 6 * c + 6] = H_x
+        H[2 * i:2 * i + 2, 15:21] = H_e
+        r[2 * i:2 * i + 2] = r_i
+    return H, r
+
+
+def gate_ekf_row(H, r, P, sigma2, chi2_dof2):
+    """gatingTestFeature(H_xj, r_j, 2) (:1953-1976) on one 2 x D block."""
+    S = H @ P @ H.T + sigma2 * np.eye(2)
+    gamma = float(r @ np.linalg.solve(S, r))
+    return gamma, gamma < chi2_dof2

@@ -614,3 +614,50 @@ def chol_probe(A, X=None, reps=10):
 
 def chi2_quantile(p, dof):
     return float(lib().orcvio_chi2_quantile(float(p), int(dof)))
+
+
+def ekf_measurement_jacobians(clone_R, clone_p, R_b2c, t_c_b, anchor, inv_depth, f_an, positions, feat_off,
+                              obs_clone, obs_z):
+    """H1 (measurementJacobian_ekf_1didp, orcvio.cpp:1356-1478) per observation: H_f (n,2), H_a, H_x, H_e (n,2,6), r (n,2)."""
+    L = lib()
+    clone_R, clone_p = _f64(clone_R).reshape(-1, 9), _f64(clone_p).reshape(-1, 3)
+    Rbc, tcb = _f64(R_b2c).reshape(9), _f64(t_c_b).reshape(3)
+    anchor, feat_off, obs_clone = _i32(anchor), _i32(feat_off), _i32(obs_clone)
+    rho, fan, pos, oz = _f64(inv_depth), _f64(f_an).reshape(-1, 2), _f64(positions).reshape(-1, 3), _f64(obs_z).reshape(-1, 2)
+    no = len(obs_clone)
+    out = dict(H_f=np.zeros((no, 2)), H_a=np.zeros((no, 2, 6)), H_x=np.zeros((no, 2, 6)), H_e=np.zeros((no, 2, 6)),
+               r=np.zeros((no, 2)))
+    L.orcvio_ekf_measurement_jacobians.restype = C.c_int
+    L.orcvio_ekf_measurement_jacobians.argtypes = [C.c_void_p, C.c_void_p, C.c_int] + [C.c_void_p] * 9 + [C.c_int] + [C.c_void_p] * 5
+    rc = L.orcvio_ekf_measurement_jacobians(
+        clone_R.ctypes.data, clone_p.ctypes.data, clone_R.shape[0], Rbc.ctypes.data, tcb.ctypes.data, anchor.ctypes.data,
+        rho.ctypes.data, fan.ctypes.data, pos.ctypes.data, feat_off.ctypes.data, obs_clone.ctypes.data, oz.ctypes.data,
+        len(feat_off) - 1, out["H_f"].ctypes.data, out["H_a"].ctypes.data, out["H_x"].ctypes.data, out["H_e"].ctypes.data,
+        out["r"].ctypes.data)
+    if rc != 0:
+        raise RuntimeError(f"orcvio_ekf_measurement_jacobians failed: {rc}")
+    return out
+
+
+def ekf_feature_rows(clone_R, clone_p, R_b2c, t_c_b, anchor, inv_depth, f_an, positions, z_cur, P, noise_var, chi2_p=0.95):
+    """H2 (featureJacobian_ekf, orcvio.cpp:1575-1651) + the dof-2 gate for the features of the state observed by the
+    newest clone: H (2F, D), r (2F), gamma (F), pass (F)."""
+    L = lib()
+    clone_R, clone_p = _f64(clone_R).reshape(-1, 9), _f64(clone_p).reshape(-1, 3)
+    Rbc, tcb = _f64(R_b2c).reshape(9), _f64(t_c_b).reshape(3)
+    anchor = _i32(anchor)
+    rho, fan, pos, z = _f64(inv_depth), _f64(f_an).reshape(-1, 2), _f64(positions).reshape(-1, 3), _f64(z_cur).reshape(-1, 2)
+    F = len(anchor)
+    Pm = np.ascontiguousarray(P, dtype=np.float64)
+    D = Pm.shape[0]
+    out = dict(H=np.zeros((2 * F, D)), r=np.zeros(2 * F), gamma=np.zeros(F), **{"pass": np.zeros(F, dtype=np.int32)})
+    L.orcvio_ekf_feature_rows.restype = C.c_int
+    L.orcvio_ekf_feature_rows.argtypes = ([C.c_void_p, C.c_void_p, C.c_int] + [C.c_void_p] * 7 + [C.c_int, C.c_void_p, C.c_int,
+                                          C.c_double, C.c_double] + [C.c_void_p] * 4)
+    rc = L.orcvio_ekf_feature_rows(
+        clone_R.ctypes.data, clone_p.ctypes.data, clone_R.shape[0], Rbc.ctypes.data, tcb.ctypes.data, anchor.ctypes.data,
+        rho.ctypes.data, fan.ctypes.data, pos.ctypes.data, z.ctypes.data, F, Pm.ctypes.data, D, float(noise_var),
+        float(chi2_p), out["H"].ctypes.data, out["r"].ctypes.data, out["gamma"].ctypes.data, out["pass"].ctypes.data)
+    if rc != 0:
+        raise RuntimeError(f"orcvio_ekf_feature_rows failed: {rc}")
+    return out

@@ -29,6 +29,7 @@ SOURCES = {
     "prop_kernel.cu": [],
     "zupt_kernel.cu": [],
     "obj_kernel.cu": [],
+    "ekf_kernel.cu": [],
     "batch.cu": [],
     "objects.cu": [],
     "capi.cu": [],

@@ -1,0 +1,93 @@
+"""GPU: hybrid EKF-SLAM feature rows at the stage level through the C ABI against the oracle
+restatement (oracle/hybrid.py, itself pinned by central differences in tests/test_oracle_hybrid_cpu.py)."""
+import numpy as np
+import pytest
+
+from oracle import hybrid as hy
+from oracle import mathutils as mu
+from orcvio_b200 import api
+
+pytestmark = pytest.mark.gpu
+
+
+def _window(seed, N):
+    rng = np.random.default_rng(seed)
+    R_b2c, t_c_b = mu.so3_exp(rng.normal(0, 0.8, 3)), rng.normal(0, 0.1, 3)
+    clone_R = [mu.so3_exp(rng.normal(0, 0.08, 3)) for _ in range(N)]
+    clone_p = [np.array([0.25 * i, 0.02 * i, 0.0]) + rng.normal(0, 0.03, 3) for i in range(N)]
+    return rng, R_b2c, t_c_b, clone_R, clone_p
+
+
+def _features(rng, R_b2c, t_c_b, clone_R, clone_p, F, ragged=True):
+    N = len(clone_R)
+    anchor = rng.integers(0, N, F).astype(np.int32)
+    rho = 1.0 / rng.uniform(3.0, 20.0, F)
+    f_an = np.stack([rng.uniform(-0.4, 0.4, F), rng.uniform(-0.3, 0.3, F)], axis=1)
+    pos = np.array([hy.feature_position_from_anchor(clone_R[a], clone_p[a], R_b2c, t_c_b, [fx, fy, 1.0], r)
+                    for a, r, (fx, fy) in zip(anchor, rho, f_an)])
+    feat_off, obs_clone, obs_z = [0], [], []
+    for f in range(F):
+        m = int(rng.integers(1, N + 1)) if ragged else N
+        cl = np.sort(rng.choice(N, m, replace=False))
+        if f % 3 == 0 and anchor[f] not in cl:
+            cl = np.sort(np.append(cl, anchor[f]))            # include the anchor's own observation (zeroed rows)
+        for c in cl:
+            p_ck = R_b2c @ clone_R[c].T @ (pos[f] - (clone_p[c] + clone_R[c] @ t_c_b))
+            obs_clone.append(int(c))
+            obs_z.append(p_ck[:2] / p_ck[2] + rng.normal(0, 0.004, 2))
+        feat_off.append(len(obs_clone))
+    return anchor, rho, f_an, pos, np.array(feat_off, np.int32), np.array(obs_clone, np.int32), np.array(obs_z)
+
+
+@pytest.mark.parametrize("seed,N,F", [(0, 6, 9), (1, 20, 30), (2, 30, 64)])
+def test_ekf_measurement_jacobians(seed, N, F):
+    rng, R_b2c, t_c_b, clone_R, clone_p = _window(seed, N)
+    anchor, rho, f_an, pos, feat_off, obs_clone, obs_z = _features(rng, R_b2c, t_c_b, clone_R, clone_p, F)
+    out = api.ekf_measurement_jacobians(clone_R, clone_p, R_b2c, t_c_b, anchor, rho, f_an, pos, feat_off, obs_clone, obs_z)
+    n_zero = 0
+    for f in range(F):
+        a = int(anchor[f])
+        for o in range(feat_off[f], feat_off[f + 1]):
+            c = int(obs_clone[o])
+            ref = hy.measurement_jacobian_ekf_1didp(clone_R[c], clone_p[c], clone_R[a], clone_p[a], R_b2c, t_c_b,
+                                                    [f_an[f, 0], f_an[f, 1], 1.0], rho[f], pos[f], obs_z[o],
+                                                    same_state=(c == a))
+            n_zero += c == a
+            for got, want in zip((out["H_f"][o].reshape(2, 1), out["H_a"][o], out["H_x"][o], out["H_e"][o], out["r"][o]), ref):
+                scale = max(np.abs(want).max(), 1e-300)
+                assert np.abs(got - want).max() <= 1e-12 * max(scale, 1.0), (f, o)
+    assert n_zero > 0                                           # the zeroed anchor-frame case was exercised
+
+
+@pytest.mark.parametrize("seed,N,F", [(3, 8, 5), (4, 20, 30)])
+def test_ekf_feature_rows_and_gate(seed, N, F):
+    rng, R_b2c, t_c_b, clone_R, clone_p = _window(seed, N)
+    anchor, rho, f_an, pos, _, _, _ = _features(rng, R_b2c, t_c_b, clone_R, clone_p, F)
+    anchor[0] = N - 1                                           # anchored in the observing clone itself: zero rows
+    pos[0] = hy.feature_position_from_anchor(clone_R[N - 1], clone_p[N - 1], R_b2c, t_c_b, [f_an[0, 0], f_an[0, 1], 1.0], rho[0])
+    k = N - 1
+    z = np.zeros((F, 2))
+    for f in range(F):
+        p_ck = R_b2c @ clone_R[k].T @ (pos[f] - (clone_p[k] + clone_R[k] @ t_c_b))
+        z[f] = p_ck[:2] / p_ck[2] + rng.normal(0, 0.01 if f % 4 else 3.0, 2)   # every fourth one is a gross outlier
+    D = 22 + 6 * N + F
+    A = rng.normal(0, 0.03, (D, D))
+    P = A @ A.T * 0.1 + 1e-5 * np.eye(D)
+    P[15:22, :] = 0.0
+    P[:, 15:22] = 0.0
+    sigma2 = 6.4e-5
+    out = api.ekf_feature_rows(clone_R, clone_p, R_b2c, t_c_b, anchor, rho, f_an, pos, z, P, sigma2, 0.95)
+    chi2 = mu.chi2_table(0.95)[2]
+    n_pass = 0
+    for f in range(F):
+        H, r = hy.feature_jacobian_ekf(clone_R, clone_p, R_b2c, t_c_b, k, int(anchor[f]), f, F,
+                                       [f_an[f, 0], f_an[f, 1], 1.0], rho[f], pos[f], z[f])
+        g, ok = hy.gate_ekf_row(H, r, P, sigma2, chi2)
+        assert np.abs(out["H"][2 * f:2 * f + 2] - H).max() <= 1e-12 * max(np.abs(H).max(), 1.0)
+        assert np.abs(out["r"][2 * f:2 * f + 2] - r).max() <= 1e-12
+        assert abs(out["gamma"][f] - g) <= 1e-9 * max(abs(g), 1e-300)
+        if abs(g - chi2) > 1e-9 * chi2:
+            assert bool(out["pass"][f]) == ok
+        n_pass += ok
+    assert 0 < n_pass < F
+    assert np.all(out["H"][0:2] == 0) and out["gamma"][0] == 0.0

@@ -1,0 +1,100 @@
+"""CPU: the oracle restatement of the hybrid EKF-SLAM feature Jacobians (oracle/hybrid.py)
+against central differences of the measurement model -- the reference has no test for these functions, so this
+is what pins the restatement (the reference checks its object Jacobians the same way,
+src/tests/test_object_lm.cpp:493-545)."""
+import numpy as np
+import pytest
+
+from oracle import hybrid as hy
+from oracle import mathutils as mu
+
+
+def _scene(seed):
+    rng = np.random.default_rng(seed)
+    R_a = mu.so3_exp(rng.normal(0, 0.4, 3))
+    R_k = mu.so3_exp(rng.normal(0, 0.05, 3)) @ R_a
+    t_a = rng.normal(0, 1.0, 3)
+    t_k = t_a + rng.normal(0, 0.3, 3)
+    R_b2c = mu.so3_exp(rng.normal(0, 0.8, 3))
+    t_c_b = rng.normal(0, 0.1, 3)
+    f_an = np.array([rng.uniform(-0.3, 0.3), rng.uniform(-0.2, 0.2), 1.0])
+    rho = 1.0 / rng.uniform(3.0, 15.0)
+    z = rng.normal(0, 0.3, 2)
+    return R_k, t_k, R_a, t_a, R_b2c, t_c_b, f_an, rho, z
+
+
+def _predict(R_k, t_k, R_a, t_a, R_b2c, t_c_b, f_an, rho):
+    p_w = hy.feature_position_from_anchor(R_a, t_a, R_b2c, t_c_b, f_an, rho)
+    p_ck = R_b2c @ R_k.T @ (p_w - (t_k + R_k @ t_c_b))
+    return p_ck[:2] / p_ck[2]
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_ekf_1didp_jacobians_match_central_differences(seed):
+    R_k, t_k, R_a, t_a, R_b2c, t_c_b, f_an, rho, z = _scene(seed)
+    p_w = hy.feature_position_from_anchor(R_a, t_a, R_b2c, t_c_b, f_an, rho)
+    H_f, H_a, H_x, H_e, r = hy.measurement_jacobian_ekf_1didp(R_k, t_k, R_a, t_a, R_b2c, t_c_b, f_an, rho, p_w, z)
+    np.testing.assert_allclose(r, z - _predict(R_k, t_k, R_a, t_a, R_b2c, t_c_b, f_an, rho), atol=1e-14)
+    h = 1e-6
+
+    def num(fun):
+        return (fun(h) - fun(-h)) / (2 * h)
+
+    # inverse depth
+    np.testing.assert_allclose(H_f[:, 0], num(lambda e: _predict(R_k, t_k, R_a, t_a, R_b2c, t_c_b, f_an, rho + e)),
+                               rtol=1e-6, atol=1e-8)
+    for j in range(3):
+        d = np.zeros(3)
+        d[j] = 1.0
+        # poses: R <- exp(dtheta) R (world-frame perturbation), p <- p + dp  (the LARVIO error state)
+        np.testing.assert_allclose(H_x[:, j], num(lambda e: _predict(mu.so3_exp(e * d) @ R_k, t_k, R_a, t_a, R_b2c,
+                                                                     t_c_b, f_an, rho)), rtol=1e-6, atol=1e-8)
+        np.testing.assert_allclose(H_x[:, 3 + j], num(lambda e: _predict(R_k, t_k + e * d, R_a, t_a, R_b2c, t_c_b,
+                                                                         f_an, rho)), rtol=1e-6, atol=1e-8)
+        np.testing.assert_allclose(H_a[:, j], num(lambda e: _predict(R_k, t_k, mu.so3_exp(e * d) @ R_a, t_a, R_b2c,
+                                                                     t_c_b, f_an, rho)), rtol=1e-6, atol=1e-8)
+        np.testing.assert_allclose(H_a[:, 3 + j], num(lambda e: _predict(R_k, t_k, R_a, t_a + e * d, R_b2c, t_c_b,
+                                                                         f_an, rho)), rtol=1e-6, atol=1e-8)
+        # extrinsics: R_b2c <- R_b2c exp(-dphi)  (incrementState_IMUCam: R_ic <- R_ic dq^T, :4513-4518),
+        # t_c_b <- t_c_b + dt
+        np.testing.assert_allclose(H_e[:, j], num(lambda e: _predict(R_k, t_k, R_a, t_a, R_b2c @ mu.so3_exp(-e * d),
+                                                                     t_c_b, f_an, rho)), rtol=1e-6, atol=1e-8)
+        np.testing.assert_allclose(H_e[:, 3 + j], num(lambda e: _predict(R_k, t_k, R_a, t_a, R_b2c, t_c_b + e * d,
+                                                                         f_an, rho)), rtol=1e-6, atol=1e-8)
+
+
+def test_anchor_observation_is_zeroed():
+    R_k, t_k, R_a, t_a, R_b2c, t_c_b, f_an, rho, z = _scene(11)
+    p_w = hy.feature_position_from_anchor(R_a, t_a, R_b2c, t_c_b, f_an, rho)
+    out = hy.measurement_jacobian_ekf_1didp(R_a, t_a, R_a, t_a, R_b2c, t_c_b, f_an, rho, p_w, z, same_state=True)
+    assert all(np.all(o == 0) for o in out)
+
+
+def test_stacked_rows_and_gate():
+    rng = np.random.default_rng(5)
+    N, E = 6, 3
+    R_b2c, t_c_b = mu.so3_exp(rng.normal(0, 0.8, 3)), rng.normal(0, 0.1, 3)
+    clone_R = [mu.so3_exp(rng.normal(0, 0.05, 3)) for _ in range(N)]
+    clone_p = [np.array([0.2 * i, 0.0, 0.0]) + rng.normal(0, 0.02, 3) for i in range(N)]
+    a_idx, k_idx, feat_idx = 1, N - 1, 2
+    f_an, rho = np.array([0.1, -0.05, 1.0]), 0.2
+    p_w = hy.feature_position_from_anchor(clone_R[a_idx], clone_p[a_idx], R_b2c, t_c_b, f_an, rho)
+    z = _predict(clone_R[k_idx], clone_p[k_idx], clone_R[a_idx], clone_p[a_idx], R_b2c, t_c_b, f_an, rho) + 1e-3
+    H, r = hy.feature_jacobian_ekf(clone_R, clone_p, R_b2c, t_c_b, k_idx, a_idx, feat_idx, E, f_an, rho, p_w, z)
+    D = 22 + 6 * N + E
+    assert H.shape == (2, D)
+    nz = np.flatnonzero(np.abs(H).sum(axis=0))
+    expect = set(range(15, 21)) | set(range(22 + 6 * a_idx, 28 + 6 * a_idx)) | set(range(22 + 6 * k_idx, 28 + 6 * k_idx))
+    expect.add(22 + 6 * N + feat_idx)
+    assert set(nz) <= expect and (22 + 6 * N + feat_idx) in nz
+    np.testing.assert_allclose(r, [1e-3, 1e-3], atol=1e-12)
+    A = rng.normal(0, 0.05, (D, D))
+    P = A @ A.T + 1e-4 * np.eye(D)
+    g, ok = hy.gate_ekf_row(H, r, P, 6.4e-5, mu.chi2_table(0.95)[2])
+    assert g > 0 and ok
+    # a new feature: rows for every observing clone but the anchor
+    obs_clone = [1, 2, 3, 5]
+    obs_z = [_predict(clone_R[c], clone_p[c], clone_R[a_idx], clone_p[a_idx], R_b2c, t_c_b, f_an, rho) for c in obs_clone]
+    Hn, rn = hy.feature_jacobian_ekf_new(clone_R, clone_p, R_b2c, t_c_b, obs_clone, obs_z, a_idx, D, D + 1, f_an, rho, p_w)
+    assert Hn.shape == (6, D + 1) and np.abs(rn).max() < 1e-12
+    assert np.all(np.abs(Hn[:, D]) > 0)
