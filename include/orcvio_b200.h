@@ -238,6 +238,17 @@ int orcvio_ekf_feature_rows(const double* clone_R, const double* clone_p, int n_
                             const double* positions, const double* z_cur, int n_feat, const double* P, int D,
                             double noise_var, double chi2_p, double* H, double* r, double* gamma, int* pass);
 
+/* H4, updateFeatureCov_1didp (orcvio.cpp:3611-3773): feature feat_idx (state column 22 + 6 n_clones + feat_idx) moves its
+ * anchor from clone old_idx to clone new_idx; p_w is its world position, inv_depth_new its inverse depth already
+ * expressed in the new anchor.  P (D x D, symmetric) is updated in place: the feature's row / column becomes J P
+ * (J P J^T on the diagonal).  J_out (D) optionally receives the 1 x D Jacobian. */
+int orcvio_ekf_update_feature_cov(double* P, int D, const double* clone_R, const double* clone_p, int n_clones,
+                                  const double* R_b2c, const double* t_c_b, int feat_idx, int old_idx, int new_idx,
+                                  const double* p_w, double inv_depth_new, double* J_out);
+
+/* H4, rmLostFeaturesCov (orcvio.cpp:3776-3828): P without the row / column of feature feat_idx, (D-1) x (D-1). */
+int orcvio_ekf_remove_feature_cov(const double* P, int D, int n_clones, int feat_idx, double* P_out);
+
 /* Stage 3 (O1-O4): keypoint + bbox residuals and Jacobians of one object over T frames.
  * frames_wTc: T x 16 (row-major 4x4), wTo 16, shape 3, kps K x 3, zs T x K x 2 (NaN = not
  * observed), zb T x 4.  flags: bit0 left perturbation, bit1 new bbox residual.

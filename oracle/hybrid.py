@@ -111,3 +111,59 @@ def gate_ekf_row(H, r, P, sigma2, chi2_dof2):
     S = H @ P @ H.T + sigma2 * np.eye(2)
     gamma = float(r @ np.linalg.solve(S, r))
     return gamma, gamma < chi2_dof2
+
+
+def reanchor_jacobian(R_old, t_old, R_new, t_new, R_b2c, t_c_b, p_w, inv_depth_new):
+    """updateFeatureCov_1didp (:3611-3699): d(rho_new) with respect to (rho_old, old anchor pose, new anchor pose,
+    extrinsics) when a 1-D inverse-depth feature moves its anchor from clone `old` to clone `new`.  p_w is the
+    feature's world position, inv_depth_new the inverse depth already re-expressed in the new anchor (the caller
+    sets feature.invDepth before the call, :2820-2860).  Returns (H_f, H_old (6), H_new (6), H_e (6))."""
+    R_old, R_new, R_b2c = (np.asarray(a, dtype=float).reshape(3, 3) for a in (R_old, R_new, R_b2c))
+    t_old, t_new, t_c_b, p_w = (np.asarray(a, dtype=float).reshape(3) for a in (t_old, t_new, t_c_b, p_w))
+    R_c2w_old = R_old @ R_b2c.T
+    t_c_w_old = t_old + R_old @ t_c_b
+    p_old = np.linalg.solve(R_c2w_old, p_w - t_c_w_old)       # R_c2w_old.inverse() * (...)
+    inv_old = 1 / p_old[2]
+    f_old = np.array([p_old[0] / p_old[2], p_old[1] / p_old[2], 1.0])
+    R_w2b_new = R_new.T
+    R_c2w_new = R_new @ R_b2c.T
+    R_w2c_new = R_c2w_new.T
+    p_bf_old = p_w - t_old
+    p_bf_new = p_w - t_new
+    J_rho_d_new = -inv_depth_new * inv_depth_new
+    J_d = (R_w2c_new @ R_c2w_old @ f_old)[2]
+    J_theta_old = (-R_w2c_new @ mu.skew(p_bf_old))[2]
+    J_p_old = R_w2c_new[2]
+    J_theta_new = (R_w2c_new @ mu.skew(p_bf_new))[2]
+    J_p_new = -R_w2c_new[2]
+    SkewMx = mu.skew(R_w2b_new @ p_bf_new - t_c_b)
+    Mx = R_w2b_new @ R_old @ mu.skew(R_b2c.T @ p_old)
+    J_e_theta = (R_b2c @ (SkewMx - Mx))[2]
+    J_e_p = (R_b2c @ (R_w2b_new @ R_old - np.eye(3)))[2]
+    J_d_rho_old = -1 / (inv_old * inv_old)
+    H_f = J_rho_d_new * J_d * J_d_rho_old
+    return (H_f, J_rho_d_new * np.concatenate([J_theta_old, J_p_old]),
+            J_rho_d_new * np.concatenate([J_theta_new, J_p_new]), J_rho_d_new * np.concatenate([J_e_theta, J_e_p]))
+
+
+def update_feature_cov_1didp(P, n_clones, feat_idx, old_idx, new_idx, clone_R, clone_p, R_b2c, t_c_b, p_w,
+                             inv_depth_new):
+    """updateFeatureCov_1didp (:3611-3773), use_schmidt == 0: the feature's row / column of P is replaced by J P
+    (J P J^T on the diagonal), J the 1 x D Jacobian above; P is then symmetrised."""
+    P = np.array(P, dtype=float)
+    D = P.shape[0]
+    H_f, H_old, H_new, H_e = reanchor_jacobian(clone_R[old_idx], clone_p[old_idx], clone_R[new_idx], clone_p[new_idx],
+                                               R_b2c, t_c_b, p_w, inv_depth_new)
+    c = LEG_DIM + 6 * n_clones + feat_idx
+    J = np.zeros((1, D))
+    J[0, c] = H_f
+    J[0, LEG_DIM + 6 * old_idx:LEG_DIM + 6 * old_idx + 6] = H_old
+    J[0, LEG_DIM + 6 * new_idx:LEG_DIM + 6 * new_idx + 6] = H_new      # written after the old block (:3714-3717)
+    J[0, 15:21] = H_e
+    Pfleg = J @ P
+    Pff = Pfleg @ J.T
+    out = P.copy()
+    out[c, :] = Pfleg[0]
+    out[:, c] = Pfleg[0]
+    out[c, c] = Pff[0, 0]
+    return (out + out.T) / 2.0, J

@@ -661,3 +661,36 @@ def ekf_feature_rows(clone_R, clone_p, R_b2c, t_c_b, anchor, inv_depth, f_an, po
     if rc != 0:
         raise RuntimeError(f"orcvio_ekf_feature_rows failed: {rc}")
     return out
+
+
+def ekf_update_feature_cov(P, clone_R, clone_p, R_b2c, t_c_b, feat_idx, old_idx, new_idx, p_w, inv_depth_new):
+    """H4 (updateFeatureCov_1didp, orcvio.cpp:3611-3773): returns (P after the anchor change, Jacobian row)."""
+    L = lib()
+    clone_R, clone_p = _f64(clone_R).reshape(-1, 9), _f64(clone_p).reshape(-1, 3)
+    Rbc, tcb, pw = _f64(R_b2c).reshape(9), _f64(t_c_b).reshape(3), _f64(p_w).reshape(3)
+    Pm = np.array(P, dtype=np.float64, order="C")
+    D = Pm.shape[0]
+    J = np.zeros(D)
+    L.orcvio_ekf_update_feature_cov.restype = C.c_int
+    L.orcvio_ekf_update_feature_cov.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
+                                                C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_double, C.c_void_p]
+    rc = L.orcvio_ekf_update_feature_cov(Pm.ctypes.data, D, clone_R.ctypes.data, clone_p.ctypes.data, clone_R.shape[0],
+                                         Rbc.ctypes.data, tcb.ctypes.data, int(feat_idx), int(old_idx), int(new_idx),
+                                         pw.ctypes.data, float(inv_depth_new), J.ctypes.data)
+    if rc != 0:
+        raise RuntimeError(f"orcvio_ekf_update_feature_cov failed: {rc}")
+    return Pm, J
+
+
+def ekf_remove_feature_cov(P, n_clones, feat_idx):
+    """H4 (rmLostFeaturesCov, orcvio.cpp:3776-3828): P without the feature's row / column."""
+    L = lib()
+    Pm = np.ascontiguousarray(P, dtype=np.float64)
+    D = Pm.shape[0]
+    out = np.zeros((D - 1, D - 1))
+    L.orcvio_ekf_remove_feature_cov.restype = C.c_int
+    L.orcvio_ekf_remove_feature_cov.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]
+    rc = L.orcvio_ekf_remove_feature_cov(Pm.ctypes.data, D, int(n_clones), int(feat_idx), out.ctypes.data)
+    if rc != 0:
+        raise RuntimeError(f"orcvio_ekf_remove_feature_cov failed: {rc}")
+    return out

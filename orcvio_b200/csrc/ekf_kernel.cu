@@ -172,6 +172,119 @@ __global__ void __launch_bounds__(64) k_ekf_rows(EkfRowArgs a) {
   a.pass[f] = g < a.chi2 ? 1 : 0;
 }
 
+
+// updateFeatureCov_1didp (src/orcvio.cpp:3611-3773): anchor change of one inverse-depth feature.  One CTA: the
+// 1 x D Jacobian J (19 structurally non-zero entries) is built by thread 0, Pfleg = J P by all threads (one
+// column each), then the feature's row / column of P is replaced (J P J^T on the diagonal).  P stays exactly
+// symmetric (row and column are written from the same values), so the reference's (P + P^T)/2 is the identity.
+struct ReanchorArgs {
+  const double* clones; const double* Rbc; const double* tcb; int N;
+  int feat_idx, old_idx, new_idx;
+  double pw[3]; double rho_new;
+  double* P; int D;
+  double* J_out;                           // optional: the Jacobian row (D)
+};
+
+__global__ void __launch_bounds__(256) k_ekf_reanchor(ReanchorArgs a) {
+  extern __shared__ double sm[];           // J (D), Pfleg (D)
+  double* J = sm;
+  double* Pf = sm + a.D;
+  const int D = a.D, tid = threadIdx.x;
+  for (int i = tid; i < D; i += blockDim.x) J[i] = 0.0;
+  __syncthreads();
+  const int c = ORCVIO_LEG + 6 * a.N + a.feat_idx;
+  if (tid == 0) {
+    const double* Ro = a.clones + (size_t)a.old_idx * CL_STRIDE + CL_R;
+    const double* to = a.clones + (size_t)a.old_idx * CL_STRIDE + CL_P;
+    const double* Rn = a.clones + (size_t)a.new_idx * CL_STRIDE + CL_R;
+    const double* tn = a.clones + (size_t)a.new_idx * CL_STRIDE + CL_P;
+    const double* Rbc = a.Rbc;
+    const double* tcb = a.tcb;
+    double Rc2w_o[9], Rc2w_n[9], Rt[3];
+    m3_mulT(Ro, Rbc, Rc2w_o);              // R_b2w R_b2c^T
+    m3_mulT(Rn, Rbc, Rc2w_n);
+    m3_vec(Ro, tcb, Rt);
+    const double d[3] = {a.pw[0] - (to[0] + Rt[0]), a.pw[1] - (to[1] + Rt[1]), a.pw[2] - (to[2] + Rt[2])};
+    double po[3];
+    m3_Tvec(Rc2w_o, d, po);                // R_c2w_old^-1 (p_w - t_c_w_old): the rotation's inverse is its transpose
+    const double inv_old = 1 / po[2];
+    const double fo[3] = {po[0] / po[2], po[1] / po[2], 1.0};
+    const double pbo[3] = {a.pw[0] - to[0], a.pw[1] - to[1], a.pw[2] - to[2]};
+    const double pbn[3] = {a.pw[0] - tn[0], a.pw[1] - tn[1], a.pw[2] - tn[2]};
+    const double Jrd = -a.rho_new * a.rho_new;
+    double v1[3], v2[3];
+    m3_vec(Rc2w_o, fo, v1);
+    m3_Tvec(Rc2w_n, v1, v2);               // R_w2c_new R_c2w_old f_old
+    const double Jd = v2[2];
+    // bottom rows of 3x3 products with R_w2c_new = Rc2w_n^T: row 2 of R_w2c_new is column 2 of Rc2w_n
+    const double w2[3] = {Rc2w_n[2], Rc2w_n[5], Rc2w_n[8]};
+    double S[9];
+    double Jto[3], Jtn[3];
+    m3_skew(pbo, S);
+    for (int j = 0; j < 3; ++j) Jto[j] = -((w2[0] * S[j] + w2[1] * S[3 + j]) + w2[2] * S[6 + j]);
+    m3_skew(pbn, S);
+    for (int j = 0; j < 3; ++j) Jtn[j] = (w2[0] * S[j] + w2[1] * S[3 + j]) + w2[2] * S[6 + j];
+    // extrinsics
+    double u[3], q[3], Rno[9], Sk1[9], Sk2[9], M[9];
+    m3_Tvec(Rn, pbn, u);
+    u[0] -= tcb[0]; u[1] -= tcb[1]; u[2] -= tcb[2];
+    m3_skew(u, Sk1);
+    m3_Tmul(Rn, Ro, Rno);                  // R_w2b_new R_b2w_old
+    m3_Tvec(Rbc, po, q);
+    m3_skew(q, Sk2);
+    m3_mul(Rno, Sk2, M);
+    for (int i = 0; i < 9; ++i) Sk1[i] -= M[i];
+    Rno[0] -= 1.0; Rno[4] -= 1.0; Rno[8] -= 1.0;
+    double Jet[3], Jep[3];
+    for (int j = 0; j < 3; ++j) {
+      Jet[j] = (Rbc[6] * Sk1[j] + Rbc[7] * Sk1[3 + j]) + Rbc[8] * Sk1[6 + j];
+      Jep[j] = (Rbc[6] * Rno[j] + Rbc[7] * Rno[3 + j]) + Rbc[8] * Rno[6 + j];
+    }
+    const double Jdro = -1 / (inv_old * inv_old);
+    J[c] = Jrd * Jd * Jdro;
+    const int co = ORCVIO_LEG + 6 * a.old_idx, cn = ORCVIO_LEG + 6 * a.new_idx;
+    for (int j = 0; j < 3; ++j) { J[co + j] = Jrd * Jto[j]; J[co + 3 + j] = Jrd * w2[j]; }
+    for (int j = 0; j < 3; ++j) { J[cn + j] = Jrd * Jtn[j]; J[cn + 3 + j] = Jrd * (-w2[j]); }   // after the old block
+    for (int j = 0; j < 3; ++j) { J[15 + j] = Jrd * Jet[j]; J[18 + j] = Jrd * Jep[j]; }
+  }
+  __syncthreads();
+  if (a.J_out)
+    for (int i = tid; i < D; i += blockDim.x) a.J_out[i] = J[i];
+  // Pfleg[j] = sum_i J[i] P[i][j]: J is zero outside 15..20, the two clone blocks and the feature column
+  const int co = ORCVIO_LEG + 6 * a.old_idx, cn = ORCVIO_LEG + 6 * a.new_idx;
+  for (int j = tid; j < D; j += blockDim.x) {
+    double s = 0.0;
+    for (int i = 15; i < 21; ++i) s += J[i] * a.P[(size_t)i * D + j];
+    for (int i = co; i < co + 6; ++i) s += J[i] * a.P[(size_t)i * D + j];
+    if (cn != co)
+      for (int i = cn; i < cn + 6; ++i) s += J[i] * a.P[(size_t)i * D + j];
+    s += J[c] * a.P[(size_t)c * D + j];
+    Pf[j] = s;
+  }
+  __syncthreads();
+  __shared__ double s_pff;
+  if (tid == 0) {
+    double s = 0.0;
+    for (int j = 0; j < D; ++j) s += Pf[j] * J[j];
+    s_pff = s;
+  }
+  __syncthreads();
+  for (int j = tid; j < D; j += blockDim.x) {
+    const double v = (j == c) ? s_pff : Pf[j];
+    a.P[(size_t)c * D + j] = v;
+    a.P[(size_t)j * D + c] = v;
+  }
+}
+
+// rmLostFeaturesCov (src/orcvio.cpp:3776-3828): drop one row / column of P (D x D -> (D-1) x (D-1)).
+__global__ void k_ekf_drop_state(const double* Pin, int D, int col, double* Pout) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  const int Dn = D - 1;
+  if (e >= Dn * Dn) return;
+  const int i = e / Dn, j = e - i * Dn;
+  Pout[e] = Pin[(size_t)(i + (i >= col)) * D + (j + (j >= col))];
+}
+
 namespace {
 struct Dev {
   void* p = nullptr;
@@ -268,4 +381,47 @@ extern "C" int orcvio_ekf_feature_rows(const double* clone_R, const double* clon
        cudaMemcpy(gamma, dg.p, (size_t)n_feat * 8, cudaMemcpyDeviceToHost) == cudaSuccess &&
        cudaMemcpy(pass, dp.p, (size_t)n_feat * 4, cudaMemcpyDeviceToHost) == cudaSuccess;
   return ok ? ORCVIO_OK : ORCVIO_ERR_CUDA;
+}
+
+extern "C" int orcvio_ekf_update_feature_cov(double* P, int D, const double* clone_R, const double* clone_p,
+                                             int n_clones, const double* R_b2c, const double* t_c_b, int feat_idx,
+                                             int old_idx, int new_idx, const double* p_w, double inv_depth_new,
+                                             double* J_out) {
+  using namespace ob;
+  const int E = D - ORCVIO_LEG - 6 * n_clones;
+  if (n_clones < 1 || E < 1 || feat_idx < 0 || feat_idx >= E || old_idx < 0 || old_idx >= n_clones || new_idx < 0 ||
+      new_idx >= n_clones)
+    return ORCVIO_ERR_ARG;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1) return ORCVIO_ERR_NO_DEVICE;
+  const std::vector<double> cl = clone_records(clone_R, clone_p, n_clones);
+  Dev dcl, dR, dt, dP, dJ;
+  bool ok = dcl.put(cl.data(), cl.size()) && dR.put(R_b2c, 9) && dt.put(t_c_b, 3) && dP.put(P, (size_t)D * D) &&
+            dJ.make<double>(D);
+  if (!ok) return ORCVIO_ERR_CUDA;
+  ReanchorArgs a{};
+  a.clones = dcl.as<double>(); a.Rbc = dR.as<double>(); a.tcb = dt.as<double>(); a.N = n_clones;
+  a.feat_idx = feat_idx; a.old_idx = old_idx; a.new_idx = new_idx;
+  for (int k = 0; k < 3; ++k) a.pw[k] = p_w[k];
+  a.rho_new = inv_depth_new;
+  a.P = dP.as<double>(); a.D = D; a.J_out = dJ.as<double>();
+  k_ekf_reanchor<<<1, 256, 2 * (size_t)D * sizeof(double)>>>(a);
+  check_launch("k_ekf_reanchor");
+  ok = cudaMemcpy(P, dP.p, (size_t)D * D * 8, cudaMemcpyDeviceToHost) == cudaSuccess &&
+       (!J_out || cudaMemcpy(J_out, dJ.p, (size_t)D * 8, cudaMemcpyDeviceToHost) == cudaSuccess);
+  return ok ? ORCVIO_OK : ORCVIO_ERR_CUDA;
+}
+
+extern "C" int orcvio_ekf_remove_feature_cov(const double* P, int D, int n_clones, int feat_idx, double* P_out) {
+  using namespace ob;
+  const int E = D - ORCVIO_LEG - 6 * n_clones;
+  if (n_clones < 1 || E < 1 || feat_idx < 0 || feat_idx >= E) return ORCVIO_ERR_ARG;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1) return ORCVIO_ERR_NO_DEVICE;
+  Dev dP, dO;
+  const int Dn = D - 1;
+  if (!dP.put(P, (size_t)D * D) || !dO.make<double>((size_t)Dn * Dn)) return ORCVIO_ERR_CUDA;
+  k_ekf_drop_state<<<(Dn * Dn + 255) / 256, 256>>>(dP.as<double>(), D, ORCVIO_LEG + 6 * n_clones + feat_idx, dO.as<double>());
+  check_launch("k_ekf_drop_state");
+  return cudaMemcpy(P_out, dO.p, (size_t)Dn * Dn * 8, cudaMemcpyDeviceToHost) == cudaSuccess ? ORCVIO_OK : ORCVIO_ERR_CUDA;
 }

@@ -91,3 +91,28 @@ def test_ekf_feature_rows_and_gate(seed, N, F):
         n_pass += ok
     assert 0 < n_pass < F
     assert np.all(out["H"][0:2] == 0) and out["gamma"][0] == 0.0
+
+
+@pytest.mark.parametrize("seed,N,E", [(5, 6, 3), (6, 20, 30)])
+def test_anchor_change_covariance(seed, N, E):
+    """H4: updateFeatureCov_1didp and rmLostFeaturesCov against the oracle."""
+    rng, R_b2c, t_c_b, clone_R, clone_p = _window(seed, N)
+    D = 22 + 6 * N + E
+    A = rng.normal(0, 0.04, (D, D))
+    P = A @ A.T + 1e-5 * np.eye(D)
+    P[15:22, :] = 0.0
+    P[:, 15:22] = 0.0
+    for fidx, old, new in [(0, 0, N - 1), (E - 1, N - 2, 1), (E // 2, 2, 2 if N < 4 else 3)]:
+        f_an, rho = np.array([rng.uniform(-0.3, 0.3), rng.uniform(-0.2, 0.2), 1.0]), 1.0 / rng.uniform(4.0, 15.0)
+        p_w = hy.feature_position_from_anchor(clone_R[old], clone_p[old], R_b2c, t_c_b, f_an, rho)
+        p_c = R_b2c @ clone_R[new].T @ (p_w - (clone_p[new] + clone_R[new] @ t_c_b))
+        rho_new = 1.0 / p_c[2]
+        ref, J_ref = hy.update_feature_cov_1didp(P, N, fidx, old, new, clone_R, clone_p, R_b2c, t_c_b, p_w, rho_new)
+        got, J = api.ekf_update_feature_cov(P, clone_R, clone_p, R_b2c, t_c_b, fidx, old, new, p_w, rho_new)
+        assert np.abs(J - J_ref[0]).max() <= 1e-12 * max(np.abs(J_ref).max(), 1.0)
+        assert np.abs(got - ref).max() <= 1e-12 * np.abs(ref).max()
+        assert np.abs(got - got.T).max() == 0.0
+        P = ref                                                  # chain the anchor changes
+    out = api.ekf_remove_feature_cov(P, N, E // 2)
+    c = 22 + 6 * N + E // 2
+    np.testing.assert_array_equal(out, np.delete(np.delete(P, c, axis=0), c, axis=1))

@@ -98,3 +98,56 @@ def test_stacked_rows_and_gate():
     Hn, rn = hy.feature_jacobian_ekf_new(clone_R, clone_p, R_b2c, t_c_b, obs_clone, obs_z, a_idx, D, D + 1, f_an, rho, p_w)
     assert Hn.shape == (6, D + 1) and np.abs(rn).max() < 1e-12
     assert np.all(np.abs(Hn[:, D]) > 0)
+
+
+def _inv_depth_in(R_anchor, t_anchor, R_b2c, t_c_b, p_w):
+    p_c = R_b2c @ R_anchor.T @ (p_w - (t_anchor + R_anchor @ t_c_b))
+    return 1.0 / p_c[2]
+
+
+@pytest.mark.parametrize("seed", range(4))
+def test_reanchor_jacobian_matches_central_differences(seed):
+    """updateFeatureCov_1didp: rho_new as a function of (rho_old, old anchor pose, new anchor pose, extrinsics)."""
+    R_new, t_new, R_old, t_old, R_b2c, t_c_b, f_an, rho_old, _ = _scene(20 + seed)
+
+    def rho_new(R_o=R_old, t_o=t_old, R_n=R_new, t_n=t_new, Rbc=R_b2c, tcb=t_c_b, rho=rho_old):
+        p_w = hy.feature_position_from_anchor(R_o, t_o, Rbc, tcb, f_an, rho)
+        return _inv_depth_in(R_n, t_n, Rbc, tcb, p_w)
+
+    p_w = hy.feature_position_from_anchor(R_old, t_old, R_b2c, t_c_b, f_an, rho_old)
+    H_f, H_old, H_new, H_e = hy.reanchor_jacobian(R_old, t_old, R_new, t_new, R_b2c, t_c_b, p_w, rho_new())
+    h = 1e-6
+
+    def num(fun):
+        return (fun(h) - fun(-h)) / (2 * h)
+
+    np.testing.assert_allclose(H_f, num(lambda e: rho_new(rho=rho_old + e)), rtol=1e-6, atol=1e-9)
+    for j in range(3):
+        d = np.zeros(3)
+        d[j] = 1.0
+        np.testing.assert_allclose(H_old[j], num(lambda e: rho_new(R_o=mu.so3_exp(e * d) @ R_old)), rtol=1e-6, atol=1e-9)
+        np.testing.assert_allclose(H_old[3 + j], num(lambda e: rho_new(t_o=t_old + e * d)), rtol=1e-6, atol=1e-9)
+        np.testing.assert_allclose(H_new[j], num(lambda e: rho_new(R_n=mu.so3_exp(e * d) @ R_new)), rtol=1e-6, atol=1e-9)
+        np.testing.assert_allclose(H_new[3 + j], num(lambda e: rho_new(t_n=t_new + e * d)), rtol=1e-6, atol=1e-9)
+        np.testing.assert_allclose(H_e[j], num(lambda e: rho_new(Rbc=R_b2c @ mu.so3_exp(-e * d))), rtol=1e-6, atol=1e-9)
+        np.testing.assert_allclose(H_e[3 + j], num(lambda e: rho_new(tcb=t_c_b + e * d)), rtol=1e-6, atol=1e-9)
+
+
+def test_update_feature_cov_is_a_congruence():
+    rng = np.random.default_rng(9)
+    N, E = 5, 3
+    R_b2c, t_c_b = mu.so3_exp(rng.normal(0, 0.8, 3)), rng.normal(0, 0.1, 3)
+    clone_R = [mu.so3_exp(rng.normal(0, 0.05, 3)) for _ in range(N)]
+    clone_p = [np.array([0.2 * i, 0.0, 0.0]) + rng.normal(0, 0.02, 3) for i in range(N)]
+    f_an, rho = np.array([0.1, -0.05, 1.0]), 0.15
+    old, new, fidx = 0, 3, 1
+    p_w = hy.feature_position_from_anchor(clone_R[old], clone_p[old], R_b2c, t_c_b, f_an, rho)
+    rho_n = _inv_depth_in(clone_R[new], clone_p[new], R_b2c, t_c_b, p_w)
+    D = 22 + 6 * N + E
+    A = rng.normal(0, 0.05, (D, D))
+    P = A @ A.T + 1e-4 * np.eye(D)
+    Pn, J = hy.update_feature_cov_1didp(P, N, fidx, old, new, clone_R, clone_p, R_b2c, t_c_b, p_w, rho_n)
+    T = np.eye(D)
+    T[22 + 6 * N + fidx] = J[0]
+    np.testing.assert_allclose(Pn, T @ P @ T.T, rtol=1e-12, atol=1e-15)      # P' = T P T^T: still symmetric PSD
+    assert np.linalg.eigvalsh(Pn).min() > 0
