@@ -415,10 +415,17 @@ class Frame:
         nf = len(inp["feat_off"]) - 1
         if out is None:
             out = self._outputs(inp["N"], nf)
-        rc = self._L.orcvio_frame_update(
-            self._h, _dp(inp["clone_R"]), _dp(inp["clone_p"]), inp["N"], _dp(inp["Rbc"]), _dp(inp["tcb"]),
-            _dp(inp["P"]), _ip(inp["feat_off"]), _ip(inp["obs_clone"]), _dp(inp["obs_z"]), nf,
-            _dp(out["P"]), _dp(out["delta_x"]), _ip(out["status"]), _dp(out["gamma"]), _dp(out["clones"]))
+        # the ctypes pointer objects are cached on the buffers' dicts: building 14 of them costs more than the
+        # GPU spends on a stage of the frame
+        pi = inp.get("_ptrs")
+        if pi is None:
+            pi = inp["_ptrs"] = (_dp(inp["clone_R"]), _dp(inp["clone_p"]), inp["N"], _dp(inp["Rbc"]), _dp(inp["tcb"]),
+                                 _dp(inp["P"]), _ip(inp["feat_off"]), _ip(inp["obs_clone"]), _dp(inp["obs_z"]), nf)
+        po = out.get("_ptrs")
+        if po is None:
+            po = out["_ptrs"] = (_dp(out["P"]), _dp(out["delta_x"]), _ip(out["status"]), _dp(out["gamma"]),
+                                 _dp(out["clones"]))
+        rc = self._L.orcvio_frame_update(self._h, *pi, *po)
         if rc != 0:
             raise RuntimeError(f"orcvio_frame_update failed: {rc}")
         return out

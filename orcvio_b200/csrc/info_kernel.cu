@@ -384,18 +384,22 @@ __global__ void __launch_bounds__(256) k_syrk(UpdArgs a, const double* __restric
 #pragma unroll
     for (int q = 0; q < 16; ++q) s[q] = 0.0;
     int c = first;
-    for (; c + step < last; c += 2 * step) {              // two slots in flight
+    for (; c + 3 * step < last; c += 4 * step) {          // four slots in flight
       const double* p0 = base + (size_t)c * cstride + tid;
-      const double* p1 = p0 + (size_t)step * cstride;
-      double x0[16], x1[16];
+      const size_t ss = (size_t)step * cstride;
+      double x0[16], x1[16], x2[16], x3[16];
 #pragma unroll
       for (int q = 0; q < 16; ++q) x0[q] = __ldcg(p0 + 256 * q);
 #pragma unroll
-      for (int q = 0; q < 16; ++q) x1[q] = __ldcg(p1 + 256 * q);
+      for (int q = 0; q < 16; ++q) x1[q] = __ldcg(p0 + ss + 256 * q);
 #pragma unroll
-      for (int q = 0; q < 16; ++q) s[q] = (s[q] + x0[q]) + x1[q];
+      for (int q = 0; q < 16; ++q) x2[q] = __ldcg(p0 + 2 * ss + 256 * q);
+#pragma unroll
+      for (int q = 0; q < 16; ++q) x3[q] = __ldcg(p0 + 3 * ss + 256 * q);
+#pragma unroll
+      for (int q = 0; q < 16; ++q) s[q] = (((s[q] + x0[q]) + x1[q]) + x2[q]) + x3[q];
     }
-    if (c < last) {
+    for (; c < last; c += step) {
       const double* p0 = base + (size_t)c * cstride + tid;
 #pragma unroll
       for (int q = 0; q < 16; ++q) s[q] += __ldcg(p0 + 256 * q);

@@ -362,7 +362,10 @@ int env_int(const char* name, int dflt) {
 void launch_triangulate(const TriArgs& a, cudaStream_t s) {
   if (a.n_cand <= 0) return;
   int blocks = (a.n_cand + TRI_WARPS - 1) / TRI_WARPS;
-  static const int minb = env_int("ORCVIO_TRI_MINB", 3);
+  // 158 registers (3 CTAs per SM) is the fastest single wave; past two waves of that (measured at 4096 features)
+  // the 128-register build with 4 CTAs per SM wins
+  static const int minb_env = env_int("ORCVIO_TRI_MINB", 0);
+  const int minb = minb_env ? minb_env : (blocks > 888 ? 4 : 3);
   switch (minb) {
     case 4: k_triangulate<4><<<blocks, 32 * TRI_WARPS, 0, s>>>(a); break;
     case 5: k_triangulate<5><<<blocks, 32 * TRI_WARPS, 0, s>>>(a); break;
