@@ -65,6 +65,7 @@ struct Batch::PhaseWork {
   // observation pools already on the device (end-to-end call: uploaded ahead for the early triangulation)
   const int* pre_dOc = nullptr; const double* pre_dOz = nullptr;
   bool obs_preuploaded = false;
+  bool cands_stay_on_host = false;   // direct mode: the kernels read per-feature arrays, the records are not uploaded
   size_t off[8] = {0};           // blob section offsets (stage_pack -> stage_upload)
   size_t n_obs() const { return ext_obs_clone ? ext_nobs : obs_clone.size(); }
   void reset() {                 // keep the vectors' capacity across frames
@@ -75,7 +76,7 @@ struct Batch::PhaseWork {
     any_active = false; d_extra = nullptr;
     dC = nullptr; dOc = nullptr; dOz = nullptr; dTiles = nullptr; dFw = nullptr; dSmall = dLarge = nullptr;
     ext_obs_clone = nullptr; ext_obs_z = nullptr; ext_nobs = 0;
-    pre_dOc = nullptr; pre_dOz = nullptr; obs_preuploaded = false;
+    pre_dOc = nullptr; pre_dOz = nullptr; obs_preuploaded = false; cands_stay_on_host = false;
   }
 };
 
@@ -124,6 +125,10 @@ Batch::Batch(const Params& p, int n) : p_(p), B_(n) {
     int lo = 0, hi = 0;
     cudaDeviceGetStreamPriorityRange(&lo, &hi);
     CK(cudaStreamCreateWithPriority(&stream2_, cudaStreamDefault, hi));
+    CK(cudaStreamCreateWithFlags(&stream_up_, cudaStreamNonBlocking));
+    CK(cudaEventCreateWithFlags(&ev_up_, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&ev_p_, cudaEventDisableTiming));
+    pack_on_worker_ = env_int("ORCVIO_PACK_WORKER", 0) != 0;
   }
   CK(cudaEventCreateWithFlags(&ev_fork_, cudaEventDisableTiming));
   CK(cudaEventCreateWithFlags(&ev_join_, cudaEventDisableTiming));
@@ -194,7 +199,9 @@ Batch::~Batch() {
   cudaFree(dR_); cudaFree(dS_); cudaFree(dRthin_); cudaFree(dYv_); cudaFree(dT_); cudaFree(dDx_);
   cudaFree(dErr_); cudaFree(dFront_); cudaFree(dChi2_);
   cudaFree(dAmat_); cudaFree(dPart_);
-  cudaFree(dStatusF_);
+  cudaFree(dStatusF_); cudaFree(dGammaF_);
+  if (blob_early2_.dev) cudaFree(blob_early2_.dev);
+  if (blob_early2_.pinned) cudaFreeHost(blob_early2_.pinned);
   if (blob_early_.dev) cudaFree(blob_early_.dev);
   if (blob_early_.pinned) cudaFreeHost(blob_early_.pinned);
   cudaFree(dLs_); cudaFree(dTileRows_); cudaFree(dFilterRows_); cudaFree(dSyrkCnt_);
@@ -212,6 +219,9 @@ Batch::~Batch() {
   if (ev_fork_) cudaEventDestroy(ev_fork_);
   if (ev_join_) cudaEventDestroy(ev_join_);
   if (stream2_) cudaStreamDestroy(stream2_);
+  if (stream_up_) cudaStreamDestroy(stream_up_);
+  if (ev_up_) cudaEventDestroy(ev_up_);
+  if (ev_p_) cudaEventDestroy(ev_p_);
   if (stream_) cudaStreamDestroy(stream_);
 }
 
@@ -288,7 +298,15 @@ void Batch::upload_blob() {
     blob_.dev_cap = blob_.used * 2 + 4096;
     CK(cudaMalloc(&blob_.dev, blob_.dev_cap));
   }
-  CK(cudaMemcpyAsync(blob_.dev, blob_.pinned, blob_.used, cudaMemcpyHostToDevice, stream_));
+  if (upload_on_side_stream_) {
+    // kernels of this frame are already queued on stream_ (early triangulation / Jacobian pass): a copy on the
+    // same stream would wait for them, so the blob goes up on its own stream and stream_ joins it afterwards
+    CK(cudaMemcpyAsync(blob_.dev, blob_.pinned, blob_.used, cudaMemcpyHostToDevice, stream_up_));
+    CK(cudaEventRecord(ev_up_, stream_up_));
+    CK(cudaStreamWaitEvent(stream_, ev_up_, 0));
+  } else {
+    CK(cudaMemcpyAsync(blob_.dev, blob_.pinned, blob_.used, cudaMemcpyHostToDevice, stream_));
+  }
 }
 
 void Batch::download_mirrors() {
@@ -319,7 +337,8 @@ void Batch::run_phase(PhaseWork& w, int phase) {
 void Batch::stage_pack(PhaseWork& w) {
   const int nC = (int)w.cands.size();
   blob_.reset();
-  const size_t o_c = blob_.reserve(sizeof(Cand) * std::max(nC, 1));
+  const bool up_c = !w.cands_stay_on_host;
+  const size_t o_c = blob_.reserve(sizeof(Cand) * (up_c ? std::max(nC, 1) : 1));
   const size_t n_obs = w.obs_preuploaded ? 0 : w.n_obs();
   const size_t o_oc = blob_.reserve(sizeof(int) * std::max<size_t>(n_obs, 1));
   const size_t o_oz = blob_.reserve(sizeof(double) * std::max<size_t>(2 * n_obs, 1));
@@ -330,7 +349,7 @@ void Batch::stage_pack(PhaseWork& w) {
   const size_t o_x = blob_.reserve(sizeof(int) * std::max<size_t>(w.extra_ints.size(), 1));
   char* h = blob_.pinned;
   if (!w.extra_ints.empty()) std::memcpy(h + o_x, w.extra_ints.data(), sizeof(int) * w.extra_ints.size());
-  if (nC) std::memcpy(h + o_c, w.cands.data(), sizeof(Cand) * nC);
+  if (nC && up_c) std::memcpy(h + o_c, w.cands.data(), sizeof(Cand) * nC);
   if (n_obs) {
     std::memcpy(h + o_oc, w.ext_obs_clone ? w.ext_obs_clone : w.obs_clone.data(), sizeof(int) * n_obs);
     std::memcpy(h + o_oz, w.ext_obs_z ? w.ext_obs_z : w.obs_z.data(), sizeof(double) * 2 * n_obs);
@@ -455,7 +474,7 @@ void Batch::launch_phase(PhaseWork& w, bool download, bool prior_in_flight) {
     ++nl;
   }
   if (profiling_) CK(cudaEventRecord(e[1], stream_));
-  if (nC > 0 && !skip_jac_) {
+  if (nC > 0 && !skip_jac_ && !jac_done_early_) {
     JacArgs ja{};
     ja.cand = dC;
     ja.clones = dClones_; ja.clone_stride = (size_t)Ncap_ * CL_STRIDE;
@@ -477,6 +496,12 @@ void Batch::launch_phase(PhaseWork& w, bool download, bool prior_in_flight) {
   if (do_update) {
     QrArgs qa{};
     qa.cand = dC; qa.status = dStatus_;
+    qa.status_f = jac_done_early_ ? dStatusF_ : nullptr;
+    if (jac_done_early_ && w.cands_stay_on_host) {
+      qa.order_f = w.d_extra;
+      qa.feat_off = dir_feat_off_; qa.rowoff_f = dir_rowoff_; qa.hblkoff_f = dir_hblkoff_;
+      qa.sblk_f = dir_sblk_; qa.eblk_f = dir_eblk_;
+    }
     qa.hblk = dHblk_; qa.rblk = dRblk_;
     qa.tiles = dTiles; qa.n_tiles = (int)w.tiles.size();
     qa.tile_out = dTileOut_;
@@ -505,9 +530,10 @@ void Batch::launch_phase(PhaseWork& w, bool download, bool prior_in_flight) {
   tri_done_early_ = false;
   if (launch_error_count() > 0) { ok_ = false; err_ = "kernel launch failed"; }
   if (nC > 0 && download) {
-    CK(cudaMemcpyAsync(hStatus_, dStatus_, sizeof(int) * nC, cudaMemcpyDeviceToHost, stream_));
-    CK(cudaMemcpyAsync(hGamma_, dGamma_, sizeof(double) * nC, cudaMemcpyDeviceToHost, stream_));
+    CK(cudaMemcpyAsync(hStatus_, jac_done_early_ ? dStatusF_ : dStatus_, sizeof(int) * nC, cudaMemcpyDeviceToHost, stream_));
+    CK(cudaMemcpyAsync(hGamma_, jac_done_early_ ? dGammaF_ : dGamma_, sizeof(double) * nC, cudaMemcpyDeviceToHost, stream_));
   }
+  jac_done_early_ = false;
 }
 
 // One persistent helper thread for host-side list building (sleeps on a condition variable between frames).
@@ -1295,6 +1321,9 @@ struct Batch::SnapState {
   int* hErr = nullptr;
   bool prior_early = false;
   bool tri_early = false;          // k_triangulate (direct mode) already queued by snapshot_prepare
+  std::vector<int> rowoff_f, hblkoff_f, small_f, large_f;   // per feature (caller's order): offsets, size classes
+  bool jac_early = false;          // k_jac_gate (direct mode) already queued by snapshot_prepare
+  bool by_feature = false;         // status / gamma of the last run are indexed by feature, not by candidate
   int list_err = 0;                // result of the (possibly threaded) work-list build
   std::atomic<int> scan_done{0}, lists_done{0};
   ~SnapState() {
@@ -1357,6 +1386,7 @@ int Batch::snapshot_prepare(const SnapshotIO& io) {
   // observations are referenced in place and copied once, straight into the pinned upload blob
   const int nF = io.n_feat;
   const int nobs_total = io.feat_off[nF];
+  if (nobs_total < 0 || io.feat_off[0] != 0) return ORCVIO_ERR_ARG;
   S.nobs_total = nobs_total;
   w.ext_obs_clone = io.obs_clone; w.ext_obs_z = io.obs_z; w.ext_nobs = (size_t)nobs_total;
   // candidates sorted by first clone block, then feature index: a counting sort (what
@@ -1372,12 +1402,17 @@ int Batch::snapshot_prepare(const SnapshotIO& io) {
   S.list_err = ORCVIO_OK;
   S.scan_done.store(0, std::memory_order_relaxed);
   S.lists_done.store(0, std::memory_order_relaxed);
-  auto build_lists = [this, &S, &w, io, nF, N]() {
+  const bool threaded_pack = pack_on_worker_ && io.early_prior && nF >= 512;
+  auto build_lists = [this, &S, &w, io, nF, N, threaded_pack]() {
     int* err = &S.list_err;
     int bucket[ORCVIO_MAX_OBS + 2] = {0};
     auto scan = [&]() {
       S.sblk.resize(nF);
       S.eblk.resize(nF);
+      S.rowoff_f.resize(nF);
+      S.hblkoff_f.resize(nF);
+      S.small_f.clear();
+      S.large_f.clear();
       for (int f = 0; f < nF; ++f) {
         const int o0 = io.feat_off[f], m = io.feat_off[f + 1] - o0;
         if (m < 1 || m > ORCVIO_MAX_OBS) { *err = ORCVIO_ERR_ARG; return; }
@@ -1390,6 +1425,16 @@ int Batch::snapshot_prepare(const SnapshotIO& io) {
         }
         S.sblk[f] = s; S.eblk[f] = e;
         ++bucket[s + 1];
+        // rows / compact block of the feature, placed in the caller's feature order (any placement works: the
+        // candidate records carry the offsets)
+        const int r = std::max(2 * m - 3, 0), wb = e - s + 1;
+        S.rowoff_f[f] = (int)w.rows_total;
+        S.hblkoff_f[f] = (int)w.hblk_total;
+        w.rows_total += (size_t)r;
+        w.hblk_total += (size_t)r * 6 * wb;
+        w.own_wmax_blk = std::max(w.own_wmax_blk, wb);
+        if (m <= 8) S.small_f.push_back(f);
+        else S.large_f.push_back(f);
       }
     };
     scan();
@@ -1414,16 +1459,13 @@ int Batch::snapshot_prepare(const SnapshotIO& io) {
         c.cm_last_clone = io.obs_clone[o0 + m - 1];
         c.cm_zu = io.obs_z[2 * (size_t)o0];
         c.cm_zv = io.obs_z[2 * (size_t)o0 + 1];
-        const int r = std::max(2 * m - 3, 0), wb = c.e_blk - c.s_blk + 1;
-        c.row_off = (int)w.rows_total;
-        c.hblk_off = (int)w.hblk_total;
-        w.rows_total += (size_t)r;
-        w.hblk_total += (size_t)r * 6 * wb;
-        w.own_wmax_blk = std::max(w.own_wmax_blk, wb);
+        c.row_off = S.rowoff_f[f];
+        c.hblk_off = S.hblkoff_f[f];
         if (m <= 8) w.small_list.push_back(pos);
         else w.large_list.push_back(pos);
       }
       build_tiles(w, 0, 0, nF);
+      if (threaded_pack) stage_pack(w);
     }
     S.lists_done.store(1, std::memory_order_release);
   };
@@ -1437,6 +1479,47 @@ int Batch::snapshot_prepare(const SnapshotIO& io) {
   auto wait_flag = [](std::atomic<int>& f) {
     while (!f.load(std::memory_order_acquire)) std::this_thread::yield();
   };
+  // the caller's observation pools go up first, as they are (nothing has to be sorted for that): by the time the
+  // inputs are validated and the prior factor is started, they are on the device and the early triangulation /
+  // Jacobian pass can start at once
+  size_t e_fo = 0, e_oc = 0, e_oz = 0;
+  if (early_tri) {
+    blob_early_.reset();
+    e_fo = blob_early_.reserve(sizeof(int) * (size_t)(nF + 1));
+    e_oc = blob_early_.reserve(sizeof(int) * (size_t)nobs_total);
+    e_oz = blob_early_.reserve(sizeof(double) * 2 * (size_t)nobs_total);
+    std::memcpy(blob_early_.pinned + e_fo, io.feat_off, sizeof(int) * (size_t)(nF + 1));
+    std::memcpy(blob_early_.pinned + e_oc, io.obs_clone, sizeof(int) * (size_t)nobs_total);
+    std::memcpy(blob_early_.pinned + e_oz, io.obs_z, sizeof(double) * 2 * (size_t)nobs_total);
+    if (blob_early_.used > blob_early_.dev_cap) {
+      if (blob_early_.dev) cudaFree(blob_early_.dev);
+      blob_early_.dev_cap = blob_early_.used * 2 + 4096;
+      CK(cudaMalloc(&blob_early_.dev, blob_early_.dev_cap));
+    }
+    if ((size_t)nF > statusf_cap_) {
+      if (dStatusF_) cudaFree(dStatusF_);
+      statusf_cap_ = (size_t)nF * 2 + 1024;
+      CK(cudaMalloc(&dStatusF_, statusf_cap_ * sizeof(int)));
+    }
+    CK(cudaMemcpyAsync(blob_early_.dev, blob_early_.pinned, blob_early_.used, cudaMemcpyHostToDevice, stream_));
+    g_hp.mark("obs_up");
+    // the early triangulation only needs the inputs to be well formed: check that here (one pass over data this
+    // thread has just read) instead of waiting for the helper thread's full scan
+    bool bad = false;
+    for (int f = 0; f < nF && !bad; ++f) {
+      const int o0 = io.feat_off[f], m = io.feat_off[f + 1] - o0;
+      if (m < 1 || m > ORCVIO_MAX_OBS || o0 < 0 || o0 + m > nobs_total) { bad = true; break; }
+      for (int k = 0; k < m; ++k) {
+        const int ci = io.obs_clone[o0 + k];
+        if (ci < 0 || ci >= N) { bad = true; break; }
+      }
+    }
+    if (bad) {
+      wait_flag(S.lists_done);
+      return ORCVIO_ERR_ARG;
+    }
+    g_hp.mark("validate");
+  }
   // ---- host staging of the window
   double* cl = S.hCl0;
   double* im = S.hIm0;
@@ -1468,69 +1551,24 @@ int Batch::snapshot_prepare(const SnapshotIO& io) {
   // imu record: current state = newest clone (only used by the state increment)
   for (int k = 0; k < 9; ++k) im[IM_R + k] = cl[(size_t)(N - 1) * CL_STRIDE + CL_R + k];
   for (int k = 0; k < 3; ++k) im[IM_P + k] = cl[(size_t)(N - 1) * CL_STRIDE + CL_P + k];
-  // P: the caller's matrix is column-major and symmetric, the device copy row-major with ld
-  if (io.P_in) {
-    for (int i = 0; i < D; ++i) {
-      std::memcpy(S.hP0 + (size_t)i * ldp_, io.P_in + (size_t)i * D, D * sizeof(double));
-      for (int j = D; j < ldp_; ++j) S.hP0[(size_t)i * ldp_ + j] = 0.0;
-    }
-    for (int i = D; i < ldp_; ++i) std::memset(S.hP0 + (size_t)i * ldp_, 0, ldp_ * sizeof(double));
-  } else {
-    std::memset(S.hP0, 0, (size_t)ldp_ * ldp_ * sizeof(double));
-  }
-  g_hp.mark("stageP");
-  CK(cudaMemcpyAsync(S.dP0, S.hP0, (size_t)ldp_ * ldp_ * sizeof(double), cudaMemcpyHostToDevice, stream_));
-  S.prior_early = false;
-  if ((io.stages & 4) && !compress_qr_ && io.early_prior) {
-    // The prior factor needs only P: put P in place and start k_chol_prior on the second stream now, so it
-    // runs while the host is still building and uploading this frame's work lists.
-    S.hFw[0] = FilterWork{};
-    S.hFw[0].N = N; S.hFw[0].D = D; S.hFw[0].active = 1;
-    CK(cudaMemcpyAsync(S.dFw, S.hFw, sizeof(FilterWork), cudaMemcpyHostToDevice, stream_));
-    CK(cudaMemcpyAsync(dP_, S.dP0, (size_t)ldp_ * ldp_ * sizeof(double), cudaMemcpyDeviceToDevice, stream_));
-    CK(cudaEventRecord(ev_fork_, stream_));
-    InfoBufs ib{};
-    ib.Ls = dLs_;
-    launch_info_prior(upd_args(S.dFw), ib, N, stream2_, ev_fork_, ev_join_);
-    ++launches_;
-    S.prior_early = true;
-  }
   CK(cudaMemcpyAsync(S.dCl0, S.hCl0, (size_t)Ncap_ * CL_STRIDE * sizeof(double), cudaMemcpyHostToDevice, stream_));
   CK(cudaMemcpyAsync(S.dIm0, S.hIm0, IM_STRIDE * sizeof(double), cudaMemcpyHostToDevice, stream_));
-  g_hp.mark("prior_launch");
   FilterHost& F = f_[0];
   F.clones.clear();
   for (int c = 0; c < N; ++c) F.clones.push_back(CloneMeta{c, (double)c, 0.0});
 
-  wait_flag(S.scan_done);
-  g_hp.mark("scan_wait");
-  if (S.list_err != ORCVIO_OK) {
-    wait_flag(S.lists_done);
-    return S.list_err;
+  if (!early_tri) {
+    wait_flag(S.scan_done);
+    if (S.list_err != ORCVIO_OK) {
+      wait_flag(S.lists_done);
+      return S.list_err;
+    }
   }
   // Early triangulation (end-to-end call): the inputs are validated, so upload the caller's observation pools
   // as they are and start k_triangulate in direct mode now -- it runs (beside the prior factor) while the host
   // sorts the candidates, builds the tiles and uploads the work lists below.
   S.tri_early = false;
   if (early_tri) {
-    blob_early_.reset();
-    const size_t e_fo = blob_early_.reserve(sizeof(int) * (size_t)(nF + 1));
-    const size_t e_oc = blob_early_.reserve(sizeof(int) * (size_t)nobs_total);
-    const size_t e_oz = blob_early_.reserve(sizeof(double) * 2 * (size_t)nobs_total);
-    std::memcpy(blob_early_.pinned + e_fo, io.feat_off, sizeof(int) * (size_t)(nF + 1));
-    std::memcpy(blob_early_.pinned + e_oc, io.obs_clone, sizeof(int) * (size_t)nobs_total);
-    std::memcpy(blob_early_.pinned + e_oz, io.obs_z, sizeof(double) * 2 * (size_t)nobs_total);
-    if (blob_early_.used > blob_early_.dev_cap) {
-      if (blob_early_.dev) cudaFree(blob_early_.dev);
-      blob_early_.dev_cap = blob_early_.used * 2 + 4096;
-      CK(cudaMalloc(&blob_early_.dev, blob_early_.dev_cap));
-    }
-    if ((size_t)nF > statusf_cap_) {
-      if (dStatusF_) cudaFree(dStatusF_);
-      statusf_cap_ = (size_t)nF * 2 + 1024;
-      CK(cudaMalloc(&dStatusF_, statusf_cap_ * sizeof(int)));
-    }
-    CK(cudaMemcpyAsync(blob_early_.dev, blob_early_.pinned, blob_early_.used, cudaMemcpyHostToDevice, stream_));
     // the window the kernels work on (snapshot_execute skips these restores for this run)
     CK(cudaMemcpyAsync(dClones_, S.dCl0, (size_t)Ncap_ * CL_STRIDE * sizeof(double), cudaMemcpyDeviceToDevice, stream_));
     CK(cudaMemcpyAsync(dImu_, S.dIm0, IM_STRIDE * sizeof(double), cudaMemcpyDeviceToDevice, stream_));
@@ -1550,7 +1588,102 @@ int Batch::snapshot_prepare(const SnapshotIO& io) {
     S.tri_early = true;
     g_hp.mark("tri_early");
   }
+  // P: the caller's matrix is column-major and symmetric, the device copy row-major with ld
+  if (io.P_in) {
+    for (int i = 0; i < D; ++i) {
+      std::memcpy(S.hP0 + (size_t)i * ldp_, io.P_in + (size_t)i * D, D * sizeof(double));
+      for (int j = D; j < ldp_; ++j) S.hP0[(size_t)i * ldp_ + j] = 0.0;
+    }
+    for (int i = D; i < ldp_; ++i) std::memset(S.hP0 + (size_t)i * ldp_, 0, ldp_ * sizeof(double));
+  } else {
+    std::memset(S.hP0, 0, (size_t)ldp_ * ldp_ * sizeof(double));
+  }
+  g_hp.mark("stageP");
+  // when the early triangulation is already queued on stream_, P goes up on the side stream: the prior factor
+  // (which forks off the P upload) must not wait for k_triangulate
+  cudaStream_t sp = S.tri_early ? stream_up_ : stream_;
+  CK(cudaMemcpyAsync(S.dP0, S.hP0, (size_t)ldp_ * ldp_ * sizeof(double), cudaMemcpyHostToDevice, sp));
+  S.prior_early = false;
+  if ((io.stages & 4) && !compress_qr_ && io.early_prior) {
+    // The prior factor needs only P: put P in place and start k_chol_prior on the second stream now, so it
+    // runs while the host is still building and uploading this frame's work lists.
+    S.hFw[0] = FilterWork{};
+    S.hFw[0].N = N; S.hFw[0].D = D; S.hFw[0].active = 1;
+    CK(cudaMemcpyAsync(S.dFw, S.hFw, sizeof(FilterWork), cudaMemcpyHostToDevice, sp));
+    CK(cudaMemcpyAsync(dP_, S.dP0, (size_t)ldp_ * ldp_ * sizeof(double), cudaMemcpyDeviceToDevice, sp));
+    CK(cudaEventRecord(ev_fork_, sp));
+    InfoBufs ib{};
+    ib.Ls = dLs_;
+    launch_info_prior(upd_args(S.dFw), ib, N, stream2_, ev_fork_, ev_join_);
+    ++launches_;
+    S.prior_early = true;
+  }
+  if (sp != stream_) {               // everything queued on stream_ from here on sees P (and dP_)
+    CK(cudaEventRecord(ev_p_, sp));
+    CK(cudaStreamWaitEvent(stream_, ev_p_, 0));
+  }
+  g_hp.mark("prior_launch");
+  S.jac_early = false;
+  if (S.tri_early) {
+    wait_flag(S.scan_done);            // per-feature offsets and size classes (helper thread); inputs already validated
+    g_hp.mark("scan_wait");
+    // ... and the Jacobian / nullspace / gate pass right behind it, also in direct mode: the per-feature
+    // offsets and size classes come out of the validation scan, so nothing of it waits for the sorted lists
+    if (!compress_qr_ && !io.raw_Hx) {
+      ensure_scratch(std::max(nF, 1), std::max<size_t>(w.hblk_total, 1), std::max<size_t>(w.rows_total, 1), 1);
+      if ((size_t)nF > gammaf_cap_) {
+        if (dGammaF_) cudaFree(dGammaF_);
+        gammaf_cap_ = (size_t)nF * 2 + 1024;
+        CK(cudaMalloc(&dGammaF_, gammaf_cap_ * sizeof(double)));
+      }
+      blob_early2_.reset();
+      const size_t e_ro = blob_early2_.reserve(sizeof(int) * (size_t)nF);
+      const size_t e_ho = blob_early2_.reserve(sizeof(int) * (size_t)nF);
+      const size_t e_sb = blob_early2_.reserve(sizeof(int) * (size_t)nF);
+      const size_t e_eb = blob_early2_.reserve(sizeof(int) * (size_t)nF);
+      const size_t e_sm = blob_early2_.reserve(sizeof(int) * std::max<size_t>(S.small_f.size(), 1));
+      const size_t e_lg = blob_early2_.reserve(sizeof(int) * std::max<size_t>(S.large_f.size(), 1));
+      std::memcpy(blob_early2_.pinned + e_ro, S.rowoff_f.data(), sizeof(int) * (size_t)nF);
+      std::memcpy(blob_early2_.pinned + e_ho, S.hblkoff_f.data(), sizeof(int) * (size_t)nF);
+      std::memcpy(blob_early2_.pinned + e_sb, S.sblk.data(), sizeof(int) * (size_t)nF);
+      std::memcpy(blob_early2_.pinned + e_eb, S.eblk.data(), sizeof(int) * (size_t)nF);
+      if (!S.small_f.empty()) std::memcpy(blob_early2_.pinned + e_sm, S.small_f.data(), sizeof(int) * S.small_f.size());
+      if (!S.large_f.empty()) std::memcpy(blob_early2_.pinned + e_lg, S.large_f.data(), sizeof(int) * S.large_f.size());
+      if (blob_early2_.used > blob_early2_.dev_cap) {
+        if (blob_early2_.dev) cudaFree(blob_early2_.dev);
+        blob_early2_.dev_cap = blob_early2_.used * 2 + 4096;
+        CK(cudaMalloc(&blob_early2_.dev, blob_early2_.dev_cap));
+      }
+      CK(cudaMemcpyAsync(blob_early2_.dev, blob_early2_.pinned, blob_early2_.used, cudaMemcpyHostToDevice, stream_));
+      JacArgs ja{};
+      ja.cand = nullptr;
+      ja.clones = dClones_; ja.clone_stride = (size_t)Ncap_ * CL_STRIDE;
+      ja.imu = dImu_; ja.fpos = dFpos_; ja.fcap = Fcap_;
+      ja.P = dP_; ja.p_stride = (size_t)ldp_ * ldp_; ja.ldp = ldp_;
+      ja.obs_clone = w.pre_dOc; ja.obs_z = w.pre_dOz;
+      ja.flags = flags_; ja.sigma2 = p_.feature_observation_noise; ja.chi2 = dChi2_;
+      ja.status = dStatusF_; ja.gamma = dGammaF_;
+      ja.hblk = dHblk_; ja.rblk = dRblk_;
+      ja.feat_off = (const int*)(blob_early_.dev + e_fo);
+      ja.rowoff_f = (const int*)(blob_early2_.dev + e_ro);
+      ja.hblkoff_f = (const int*)(blob_early2_.dev + e_ho);
+      JacArgs js = ja, jl = ja;
+      js.cand_list = (const int*)(blob_early2_.dev + e_sm); js.n_list = (int)S.small_f.size();
+      jl.cand_list = (const int*)(blob_early2_.dev + e_lg); jl.n_list = (int)S.large_f.size();
+      if (!S.prior_early) CK(cudaMemcpyAsync(dP_, S.dP0, (size_t)ldp_ * ldp_ * sizeof(double), cudaMemcpyDeviceToDevice, stream_));
+      launch_jac_gate(js, jl, stream_);
+      launches_ += (js.n_list > 0) + (jl.n_list > 0);
+      S.jac_early = true;
+      // the A-form kernel reads the same per-feature arrays (+ the sorted order): no candidate record is uploaded
+      dir_feat_off_ = ja.feat_off; dir_rowoff_ = ja.rowoff_f; dir_hblkoff_ = ja.hblkoff_f;
+      dir_sblk_ = (const int*)(blob_early2_.dev + e_sb);
+      dir_eblk_ = (const int*)(blob_early2_.dev + e_eb);
+      w.cands_stay_on_host = true;
+    }
+    g_hp.mark("jac_early");
+  }
   wait_flag(S.lists_done);
+  if (w.cands_stay_on_host) w.extra_ints.assign(S.order.begin(), S.order.end());
   g_hp.mark("lists_wait");
   const int nC = nF;
 
@@ -1578,7 +1711,10 @@ int Batch::snapshot_prepare(const SnapshotIO& io) {
   skip_update_ = !(io.stages & 4);
   // (packing the blob on the helper thread as well was measured: the H2D copy of lines last written by
   // another core delays the GPU by ~60 us -- the copy into the pinned blob stays on this thread)
-  stage_phase(w);
+  upload_on_side_stream_ = S.tri_early;
+  if (threaded_pack) stage_upload(w);
+  else stage_phase(w);
+  upload_on_side_stream_ = false;
   g_hp.mark("stage_blob");
   if (skip_tri_ && nC > 0) {
     std::vector<int> st(nC, ST_TRI_VALID);
@@ -1593,10 +1729,13 @@ int Batch::snapshot_execute(bool download) {
   SnapState& S = *snap_;
   const bool prior_in_flight = S.prior_early;      // P restored and k_chol_prior started by snapshot_prepare
   S.prior_early = false;
-  if (!prior_in_flight)
+  if (!prior_in_flight && !(S.tri_early && S.jac_early))
     CK(cudaMemcpyAsync(dP_, S.dP0, (size_t)ldp_ * ldp_ * sizeof(double), cudaMemcpyDeviceToDevice, stream_));
   tri_done_early_ = S.tri_early;                    // window restored and k_triangulate started by snapshot_prepare
+  jac_done_early_ = S.tri_early && S.jac_early;
+  S.by_feature = jac_done_early_;
   S.tri_early = false;
+  S.jac_early = false;
   if (!tri_done_early_) {
     CK(cudaMemcpyAsync(dClones_, S.dCl0, (size_t)Ncap_ * CL_STRIDE * sizeof(double), cudaMemcpyDeviceToDevice, stream_));
     CK(cudaMemcpyAsync(dImu_, S.dIm0, IM_STRIDE * sizeof(double), cudaMemcpyDeviceToDevice, stream_));
@@ -1632,8 +1771,9 @@ int Batch::snapshot_fetch(const SnapshotIO& io) {
   g_hp.mark("gpu_wait");
   if (io.status || io.gamma)
     for (int c = 0; c < nC; ++c) {
-      if (io.status) io.status[S.order[c]] = hStatus_[c];
-      if (io.gamma) io.gamma[S.order[c]] = hGamma_[c];
+      const int f = S.by_feature ? c : S.order[c];
+      if (io.status) io.status[f] = hStatus_[c];
+      if (io.gamma) io.gamma[f] = hGamma_[c];
     }
   if (io.iters || io.cost) {
     std::vector<int> it(2 * (size_t)nC);

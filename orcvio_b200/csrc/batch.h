@@ -228,7 +228,15 @@ class Batch {
   Blob blob_early_;                    // feat_off + observation pools of the end-to-end call, uploaded ahead
   int* dStatusF_ = nullptr;            // triangulation status by feature slot (early direct-mode pass)
   size_t statusf_cap_ = 0;
-  bool tri_done_early_ = false;
+  bool tri_done_early_ = false, jac_done_early_ = false;
+  cudaStream_t stream_up_ = nullptr;   // side stream of the work-list upload when kernels are already queued
+  cudaEvent_t ev_up_ = nullptr, ev_p_ = nullptr;
+  bool upload_on_side_stream_ = false, pack_on_worker_ = false;
+  Blob blob_early2_;                   // per-feature offsets / size-class lists of the early Jacobian pass
+  double* dGammaF_ = nullptr;          // gamma by feature slot (early direct-mode pass)
+  const int *dir_feat_off_ = nullptr, *dir_rowoff_ = nullptr, *dir_hblkoff_ = nullptr, *dir_sblk_ = nullptr,
+            *dir_eblk_ = nullptr;      // device views of the per-feature arrays of the direct-mode passes
+  size_t gammaf_cap_ = 0;
   std::shared_ptr<class HostWorker> worker_;   // helper thread of the end-to-end frame call (batch.cu)
   // pinned download buffers
   int* hStatus_ = nullptr;

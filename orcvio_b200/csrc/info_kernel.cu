@@ -107,7 +107,13 @@ __global__ void __launch_bounds__(AF_THREADS, 3) k_aform(QrArgs a, const double*
     int r = 0;
     if (q < nc) {
       const int c = tl.cand_begin + q;
-      if (a.status[c] & ST_GATE_PASS) r = 2 * a.cand[c].jac_m - 3;
+      if (a.order_f) {                // direct mode: candidate c is feature order_f[c]
+        const int f = a.order_f[c];
+        if (a.status_f[f] & ST_GATE_PASS) r = 2 * (a.feat_off[f + 1] - a.feat_off[f]) - 3;
+      } else {
+        const int st = a.status_f ? a.status_f[a.cand[c].slot] : a.status[c];
+        if (st & ST_GATE_PASS) r = 2 * a.cand[c].jac_m - 3;
+      }
     }
     int incl = r;
     for (int o = 1; o < 32; o <<= 1) {
@@ -132,7 +138,15 @@ __global__ void __launch_bounds__(AF_THREADS, 3) k_aform(QrArgs a, const double*
   for (int q = warp; q < nc; q += nw) {
     if (rowbase[q] < 0) continue;
     const int c = tl.cand_begin + q;
-    const Cand cd = a.cand[c];
+    Cand cd;
+    if (a.order_f) {
+      const int f = a.order_f[c];
+      cd.jac_m = a.feat_off[f + 1] - a.feat_off[f];
+      cd.s_blk = a.sblk_f[f]; cd.e_blk = a.eblk_f[f];
+      cd.hblk_off = a.hblkoff_f[f]; cd.row_off = a.rowoff_f[f];
+    } else {
+      cd = a.cand[c];
+    }
     const int r = 2 * cd.jac_m - 3;
     const int w = 6 * (cd.e_blk - cd.s_blk + 1);
     const int coff = 6 * (cd.s_blk - tl.c0_blk);

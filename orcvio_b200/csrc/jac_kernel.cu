@@ -129,7 +129,23 @@ __global__ void __launch_bounds__(128, MINB) k_jac_gate(JacArgs a) {
   const int li = blockIdx.x * teams_per_block + team;
   if (li >= a.n_list) return;
   const int c = a.cand_list ? a.cand_list[li] : li;
-  const Cand cd = a.cand[c];
+  Cand cd;
+  if (a.feat_off) {                  // direct mode: feature c of the caller's list
+    const int o0 = a.feat_off[c], mm = a.feat_off[c + 1] - o0;
+    int s_ = 1 << 30, e_ = -1;
+    for (int k = 0; k < mm; ++k) {
+      const int ci = a.obs_clone[o0 + k];
+      s_ = min(s_, ci);
+      e_ = max(e_, ci);
+    }
+    cd.filter = 0; cd.slot = c;
+    cd.jac_off = o0; cd.jac_m = mm;
+    cd.s_blk = s_; cd.e_blk = e_;
+    cd.row_off = a.rowoff_f[c];
+    cd.hblk_off = a.hblkoff_f[c];
+  } else {
+    cd = a.cand[c];
+  }
   const int st_in = a.tri_status_f ? a.tri_status_f[cd.slot] : a.status[c];
   if (a.tri_status_f && lane == 0) a.status[c] = st_in;      // status by candidate, as the one-pass flow leaves it
   if (!(st_in & ST_TRI_VALID)) {

@@ -76,6 +76,10 @@ struct JacArgs {
   int flags; double sigma2; const double* chi2;  // chi2[dof], dof < 500
   int* status; double* gamma;
   const int* tri_status_f;                       // != nullptr: triangulation status by feature slot (direct mode)
+  // direct mode (end-to-end frame call): feat_off != nullptr -> list entries are FEATURE indices of the caller's
+  // list, the candidate record is derived on the fly (offsets of the feature's rows / block from rowoff_f /
+  // hblkoff_f), status and gamma are indexed by feature
+  const int* feat_off; const int* rowoff_f; const int* hblkoff_f;
   double* hblk; double* rblk;                    // compact projected blocks / residuals
   // optional raw per-observation outputs (orcvio_measurement_jacobians)
   double* raw_Hx; double* raw_He; double* raw_Hf; double* raw_r;
@@ -104,6 +108,11 @@ struct FilterWork {              // per filter, per update
 
 struct QrArgs {
   const Cand* cand; const int* status;
+  const int* status_f;                           // != nullptr: status by feature slot (direct-mode Jacobian pass)
+  // direct mode (end-to-end frame call): no candidate records on the device at all -- order_f[c] is the feature
+  // behind sorted candidate c, the rest comes from the per-feature arrays the early Jacobian pass already uses
+  const int* order_f; const int* feat_off; const int* rowoff_f; const int* hblkoff_f; const int* sblk_f;
+  const int* eblk_f;
   const double* hblk; const double* rblk;
   const Tile* tiles; int n_tiles;
   double* tile_out;
