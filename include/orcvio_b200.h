@@ -249,6 +249,23 @@ int orcvio_ekf_update_feature_cov(double* P, int D, const double* clone_R, const
 /* H4, rmLostFeaturesCov (orcvio.cpp:3776-3828): P without the row / column of feature feat_idx, (D-1) x (D-1). */
 int orcvio_ekf_remove_feature_cov(const double* P, int D, int n_clones, int feat_idx, double* P_out);
 
+/* H2 + H3: featureJacobian_ekf_new (orcvio.cpp:1481-1572) and the new-feature sparsification of removeLostFeatures
+ * (:2413-2443) for n_feat features about to enter the state (inputs as orcvio_ekf_measurement_jacobians; D = legacy state
+ * dimension).  Per feature the rows of its non-anchor observations are reflected so that its (single-column) feature
+ * part becomes h_2 e_0: H_1 (n_feat x D), h_2 (n_feat: the diagonal of H_2), r_1 (n_feat) are the initialisation rows of
+ * measurementUpdate_hybrid; H_o (rows_out x D) / r_o the remaining, feature-free rows, in feature order. */
+int orcvio_ekf_new_feature_rows(const double* clone_R, const double* clone_p, int n_clones, const double* R_b2c,
+                                const double* t_c_b, const int* anchor, const double* inv_depth, const double* f_an,
+                                const double* positions, const int* feat_off, const int* obs_clone,
+                                const double* obs_z, int n_feat, int D, double* H_1, double* h_2, double* r_1,
+                                double* H_o, double* r_o, int* rows_out);
+
+/* The new-state part of measurementUpdate_hybrid (orcvio.cpp:1823-1832, 1903-1941; no Schmidt): P (D x D) and dx_leg (D)
+ * are the posterior covariance and correction of the legacy state; HH = H_2^-1 H_1, dx_new = -HH dx_leg + H_2^-1 r_1,
+ * P_aug ((D + n_new)^2) = [[P, -P HH^T], [-HH P, HH P HH^T + noise_var (H_2^T H_2)^-1]], symmetrised. */
+int orcvio_ekf_delayed_init(const double* P, int D, const double* dx_leg, const double* H_1, const double* h_2,
+                            const double* r_1, int n_new, double noise_var, double* dx_new, double* P_aug);
+
 /* Stage 3 (O1-O4): keypoint + bbox residuals and Jacobians of one object over T frames.
  * frames_wTc: T x 16 (row-major 4x4), wTo 16, shape 3, kps K x 3, zs T x K x 2 (NaN = not
  * observed), zb T x 4.  flags: bit0 left perturbation, bit1 new bbox residual.

@@ -167,3 +167,39 @@ def update_feature_cov_1didp(P, n_clones, feat_idx, old_idx, new_idx, clone_R, c
     out[:, c] = Pfleg[0]
     out[c, c] = Pff[0, 0]
     return (out + out.T) / 2.0, J
+
+
+def sparsify_new_features(H_ekf_new, r_ekf_new, sz_new):
+    """New-feature sparsification of removeLostFeatures (:2413-2443): W = [V U] with V the left nullspace of
+    H_f_new (full SVD) and U its column space (QR); returns W^T H, W^T r -- the last sz_new rows are (H_1 | H_2),
+    r_1 of measurementUpdate_hybrid, the rows above have a zero feature part."""
+    H = np.asarray(H_ekf_new, dtype=float)
+    r = np.asarray(r_ekf_new, dtype=float)
+    H_f = H[:, H.shape[1] - sz_new:]
+    Us = np.linalg.svd(H_f, full_matrices=True)[0]
+    V = Us[:, sz_new:]
+    Q = np.linalg.qr(H_f, mode="complete")[0]
+    W = np.concatenate([V, Q[:, :sz_new]], axis=1)
+    return W.T @ H, W.T @ r
+
+
+def delayed_initialization(P_post, dx_leg, H_1, H_2, r_1, sigma2):
+    """The new-state part of measurementUpdate_hybrid (:1823-1832, 1903-1941; use_schmidt == 0): given the
+    posterior of the legacy state and the rows (H_1 | H_2), r_1 that carry the new features,
+        HH = H_2^-1 H_1,  dx_new = -HH dx_leg + H_2^-1 r_1,
+        P_aug = [[P, -P HH^T], [-HH P, HH P HH^T + sigma^2 (H_2^T H_2)^-1]]  (then symmetrised).
+    H_2 is diagonal for 1-D inverse-depth features (each new feature's column of H_f has its own rows), which is
+    what makes the reference's H_2.ldlt() -- a factorisation of the lower triangle -- a valid solve."""
+    P = np.asarray(P_post, dtype=float)
+    H_1, H_2 = np.asarray(H_1, dtype=float), np.asarray(H_2, dtype=float)
+    HH = np.linalg.solve(H_2, H_1)
+    dx_new = -HH @ dx_leg + np.linalg.solve(H_2, r_1)
+    nHHP = -HH @ P
+    P22 = -nHHP @ HH.T + sigma2 * np.linalg.inv(H_2.T @ H_2)
+    D, sz = P.shape[0], H_2.shape[0]
+    out = np.zeros((D + sz, D + sz))
+    out[:D, :D] = P
+    out[D:, :D] = nHHP
+    out[:D, D:] = nHHP.T
+    out[D:, D:] = P22
+    return dx_new, (out + out.T) / 2.0

@@ -701,3 +701,45 @@ def ekf_remove_feature_cov(P, n_clones, feat_idx):
     if rc != 0:
         raise RuntimeError(f"orcvio_ekf_remove_feature_cov failed: {rc}")
     return out
+
+
+def ekf_new_feature_rows(clone_R, clone_p, R_b2c, t_c_b, anchor, inv_depth, f_an, positions, feat_off, obs_clone, obs_z, D):
+    """H2 + H3 (featureJacobian_ekf_new + new-feature sparsification): H_1 (F, D), h_2 (F), r_1 (F), H_o (rows, D), r_o."""
+    L = lib()
+    clone_R, clone_p = _f64(clone_R).reshape(-1, 9), _f64(clone_p).reshape(-1, 3)
+    Rbc, tcb = _f64(R_b2c).reshape(9), _f64(t_c_b).reshape(3)
+    anchor, feat_off, obs_clone = _i32(anchor), _i32(feat_off), _i32(obs_clone)
+    rho, fan, pos, oz = _f64(inv_depth), _f64(f_an).reshape(-1, 2), _f64(positions).reshape(-1, 3), _f64(obs_z).reshape(-1, 2)
+    F = len(anchor)
+    cap = 2 * len(obs_clone)
+    out = dict(H_1=np.zeros((F, D)), h_2=np.zeros(F), r_1=np.zeros(F), H_o=np.zeros((cap, D)), r_o=np.zeros(cap))
+    rows = C.c_int(0)
+    L.orcvio_ekf_new_feature_rows.restype = C.c_int
+    L.orcvio_ekf_new_feature_rows.argtypes = ([C.c_void_p, C.c_void_p, C.c_int] + [C.c_void_p] * 9 + [C.c_int, C.c_int] +
+                                              [C.c_void_p] * 5 + [C.POINTER(C.c_int)])
+    rc = L.orcvio_ekf_new_feature_rows(
+        clone_R.ctypes.data, clone_p.ctypes.data, clone_R.shape[0], Rbc.ctypes.data, tcb.ctypes.data, anchor.ctypes.data,
+        rho.ctypes.data, fan.ctypes.data, pos.ctypes.data, feat_off.ctypes.data, obs_clone.ctypes.data, oz.ctypes.data,
+        F, int(D), out["H_1"].ctypes.data, out["h_2"].ctypes.data, out["r_1"].ctypes.data, out["H_o"].ctypes.data,
+        out["r_o"].ctypes.data, C.byref(rows))
+    if rc != 0:
+        raise RuntimeError(f"orcvio_ekf_new_feature_rows failed: {rc}")
+    out["H_o"], out["r_o"] = out["H_o"][:rows.value], out["r_o"][:rows.value]
+    return out
+
+
+def ekf_delayed_init(P, dx_leg, H_1, h_2, r_1, noise_var):
+    """The new-state part of measurementUpdate_hybrid: returns (dx_new, P_aug)."""
+    L = lib()
+    Pm = np.ascontiguousarray(P, dtype=np.float64)
+    D = Pm.shape[0]
+    dx, H1, h2, r1 = _f64(dx_leg), _f64(H_1).reshape(-1, D), _f64(h_2), _f64(r_1)
+    F = len(h2)
+    dx_new, P_aug = np.zeros(F), np.zeros((D + F, D + F))
+    L.orcvio_ekf_delayed_init.restype = C.c_int
+    L.orcvio_ekf_delayed_init.argtypes = [C.c_void_p, C.c_int] + [C.c_void_p] * 4 + [C.c_int, C.c_double, C.c_void_p, C.c_void_p]
+    rc = L.orcvio_ekf_delayed_init(Pm.ctypes.data, D, dx.ctypes.data, H1.ctypes.data, h2.ctypes.data, r1.ctypes.data, F,
+                                   float(noise_var), dx_new.ctypes.data, P_aug.ctypes.data)
+    if rc != 0:
+        raise RuntimeError(f"orcvio_ekf_delayed_init failed: {rc}")
+    return dx_new, P_aug

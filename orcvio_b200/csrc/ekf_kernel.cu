@@ -285,6 +285,147 @@ __global__ void k_ekf_drop_state(const double* Pin, int D, int col, double* Pout
   Pout[e] = Pin[(size_t)(i + (i >= col)) * D + (j + (j >= col))];
 }
 
+// featureJacobian_ekf_new (:1481-1572) + the new-feature sparsification of removeLostFeatures (:2413-2443), one CTA
+// per new feature.  The feature part of a new 1-D inverse-depth feature's rows is ONE column h with its own rows, so
+// W = [V U] is block diagonal per feature and the sparsification is a single Householder reflection that maps h to
+// beta e_0: row 0 of the reflected block is the initialisation row (H_1 | H_2 = beta, r_1), the other 2k - 1 rows
+// have lost their feature part and join H_o.  (Any orthonormal basis gives the same update: SURVEY 0 #1.)
+struct EkfNewArgs {
+  const double* clones; const double* Rbc; const double* tcb; int N; int D;
+  const int* anchor; const double* rho; const double* fan; const double* pos;
+  const int* feat_off; const int* obs_clone; const double* obs_z;
+  const int* row_off;                      // first nullspace row of every feature in Ho
+  double* H1; double* h2; double* r1;      // initialisation rows: F x D, F, F
+  double* Ho; double* ro;                  // nullspace rows: sum(2k - 1) x D, residuals
+  double* scratch;                         // F x 64 x D: unreflected rows
+};
+
+__global__ void __launch_bounds__(128) k_ekf_new_rows(EkfNewArgs a) {
+  __shared__ double hv[64], rv[64];
+  __shared__ int orow[ORCVIO_MAX_OBS];
+  __shared__ double s_tau, s_beta;
+  __shared__ int s_k;
+  const int f = blockIdx.x, tid = threadIdx.x, D = a.D;
+  const int o0 = a.feat_off[f], m = a.feat_off[f + 1] - o0, an = a.anchor[f];
+  if (tid == 0) {
+    int k = 0;
+    for (int i = 0; i < m; ++i)
+      if (a.obs_clone[o0 + i] != an) orow[k++] = o0 + i;     // the anchor frame's own observation is not used
+    s_k = k;
+  }
+  __syncthreads();
+  const int k = s_k, rows = 2 * k;
+  double* M = a.scratch + (size_t)f * 64 * D;
+  for (int e = tid; e < rows * D; e += blockDim.x) M[e] = 0.0;
+  __syncthreads();
+  if (tid < k) {
+    const int o = orow[tid], c = a.obs_clone[o];
+    double Hf[2], Ha[12], Hx[12], He[12], r[2];
+    ekf_jacobian_1didp(a.clones + (size_t)c * CL_STRIDE, a.clones + (size_t)an * CL_STRIDE, a.Rbc, a.tcb, a.fan[2 * f],
+                       a.fan[2 * f + 1], a.rho[f], a.pos + 3 * (size_t)f, a.obs_z[2 * (size_t)o], a.obs_z[2 * (size_t)o + 1],
+                       false, Hf, Ha, Hx, He, r);
+    const int ca = ORCVIO_LEG + 6 * an, cc = ORCVIO_LEG + 6 * c;
+    for (int i = 0; i < 2; ++i) {
+      double* row = M + (size_t)(2 * tid + i) * D;
+      for (int j = 0; j < 6; ++j) row[ca + j] = Ha[6 * i + j];
+      for (int j = 0; j < 6; ++j) row[cc + j] = Hx[6 * i + j];
+      for (int j = 0; j < 6; ++j) row[15 + j] = He[6 * i + j];
+      hv[2 * tid + i] = Hf[i];
+      rv[2 * tid + i] = r[i];
+    }
+  }
+  __syncthreads();
+  if (rows == 0) return;
+  if (tid == 0) {            // Householder vector of h (LAPACK dlarfg convention): (I - tau v v^T) h = beta e_0, v_0 = 1
+    double sig = 0.0;
+    for (int i = 1; i < rows; ++i) sig += hv[i] * hv[i];
+    const double alpha = hv[0];
+    double beta = alpha, tau = 0.0;
+    if (sig > 0.0) {
+      const double nrm = sqrt(alpha * alpha + sig);
+      beta = alpha >= 0.0 ? -nrm : nrm;
+      tau = (beta - alpha) / beta;
+      const double sc = 1.0 / (alpha - beta);
+      for (int i = 1; i < rows; ++i) hv[i] *= sc;
+    }
+    hv[0] = 1.0;
+    s_tau = tau;
+    s_beta = beta;
+  }
+  __syncthreads();
+  const double tau = s_tau;
+  const int ro0 = a.row_off[f];
+  for (int c = tid; c <= D; c += blockDim.x) {               // column D = the residual
+    double dot = 0.0;
+    for (int i = 0; i < rows; ++i) dot += hv[i] * (c < D ? M[(size_t)i * D + c] : rv[i]);
+    dot *= tau;
+    for (int i = 0; i < rows; ++i) {
+      const double v = (c < D ? M[(size_t)i * D + c] : rv[i]) - dot * hv[i];
+      if (i == 0) {
+        if (c < D) a.H1[(size_t)f * D + c] = v;
+        else a.r1[f] = v;
+      } else {
+        if (c < D) a.Ho[(size_t)(ro0 + i - 1) * D + c] = v;
+        else a.ro[ro0 + i - 1] = v;
+      }
+    }
+  }
+  if (tid == 0) a.h2[f] = s_beta;
+}
+
+// The new-state part of measurementUpdate_hybrid (:1823-1832, 1903-1941; no Schmidt): HH = H_2^-1 H_1 (H_2 diagonal),
+// dx_new = -HH dx_leg + H_2^-1 r_1, P_aug = [[P, -P HH^T], [-HH P, HH P HH^T + s^2 (H_2^T H_2)^-1]], symmetrised.
+struct EkfInitArgs {
+  const double* P; int D; int F;
+  const double* dx_leg; const double* H1; const double* h2; const double* r1; double sigma2;
+  double* nHHP;              // F x D scratch
+  double* dx_new; double* Paug;
+};
+
+__global__ void __launch_bounds__(256) k_ekf_init_cross(EkfInitArgs a) {      // grid: F
+  const int j = blockIdx.x, D = a.D, tid = threadIdx.x;
+  extern __shared__ double hh[];               // HH row j
+  const double ih = 1.0 / a.h2[j];
+  for (int i = tid; i < D; i += blockDim.x) hh[i] = a.H1[(size_t)j * D + i] * ih;
+  __syncthreads();
+  for (int c = tid; c < D; c += blockDim.x) {
+    double s = 0.0;
+    for (int i = 0; i < D; ++i) s += hh[i] * a.P[(size_t)i * D + c];
+    a.nHHP[(size_t)j * D + c] = -s;
+  }
+  if (tid == 0) {
+    double s = 0.0;
+    for (int i = 0; i < D; ++i) s += hh[i] * a.dx_leg[i];
+    a.dx_new[j] = -s + a.r1[j] * ih;
+  }
+}
+
+__global__ void __launch_bounds__(256) k_ekf_init_assemble(EkfInitArgs a) {
+  const int D = a.D, F = a.F, Da = D + F;
+  const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= (size_t)Da * Da) return;
+  const int i = (int)(e / Da), j = (int)(e - (size_t)i * Da);
+  double v;
+  if (i < D && j < D) {
+    v = 0.5 * (a.P[(size_t)i * D + j] + a.P[(size_t)j * D + i]);
+  } else if (i >= D && j < D) {
+    v = a.nHHP[(size_t)(i - D) * D + j];
+  } else if (i < D && j >= D) {
+    v = a.nHHP[(size_t)(j - D) * D + i];
+  } else {
+    const int p = i - D, q = j - D;
+    double s0 = 0.0, s1 = 0.0;              // (HH P HH^T)[p][q] and [q][p], then their mean
+    const double ihq = 1.0 / a.h2[q], ihp = 1.0 / a.h2[p];
+    for (int c = 0; c < D; ++c) {
+      s0 -= a.nHHP[(size_t)p * D + c] * (a.H1[(size_t)q * D + c] * ihq);
+      s1 -= a.nHHP[(size_t)q * D + c] * (a.H1[(size_t)p * D + c] * ihp);
+    }
+    v = 0.5 * (s0 + s1);
+    if (p == q) v += a.sigma2 * ihp * ihp;
+  }
+  a.Paug[e] = v;
+}
+
 namespace {
 struct Dev {
   void* p = nullptr;
@@ -424,4 +565,79 @@ extern "C" int orcvio_ekf_remove_feature_cov(const double* P, int D, int n_clone
   k_ekf_drop_state<<<(Dn * Dn + 255) / 256, 256>>>(dP.as<double>(), D, ORCVIO_LEG + 6 * n_clones + feat_idx, dO.as<double>());
   check_launch("k_ekf_drop_state");
   return cudaMemcpy(P_out, dO.p, (size_t)Dn * Dn * 8, cudaMemcpyDeviceToHost) == cudaSuccess ? ORCVIO_OK : ORCVIO_ERR_CUDA;
+}
+
+extern "C" int orcvio_ekf_new_feature_rows(const double* clone_R, const double* clone_p, int n_clones,
+                                           const double* R_b2c, const double* t_c_b, const int* anchor,
+                                           const double* inv_depth, const double* f_an, const double* positions,
+                                           const int* feat_off, const int* obs_clone, const double* obs_z, int n_feat,
+                                           int D, double* H_1, double* h_2, double* r_1, double* H_o, double* r_o,
+                                           int* rows_out) {
+  using namespace ob;
+  if (n_clones < 1 || n_feat < 0 || D < ORCVIO_LEG + 6 * n_clones) return ORCVIO_ERR_ARG;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1) return ORCVIO_ERR_NO_DEVICE;
+  std::vector<int> row_off(n_feat + 1, 0);
+  for (int f = 0; f < n_feat; ++f) {
+    if (anchor[f] < 0 || anchor[f] >= n_clones || !(inv_depth[f] != 0.0)) return ORCVIO_ERR_ARG;
+    const int m = feat_off[f + 1] - feat_off[f];
+    if (m < 1 || m > ORCVIO_MAX_OBS) return ORCVIO_ERR_ARG;
+    int k = 0;
+    for (int o = feat_off[f]; o < feat_off[f + 1]; ++o) {
+      if (obs_clone[o] < 0 || obs_clone[o] >= n_clones) return ORCVIO_ERR_ARG;
+      k += obs_clone[o] != anchor[f];
+    }
+    row_off[f + 1] = row_off[f] + std::max(2 * k - 1, 0);
+  }
+  if (rows_out) *rows_out = row_off[n_feat];
+  if (n_feat == 0) return ORCVIO_OK;
+  const int n_obs = feat_off[n_feat], n_ho = row_off[n_feat];
+  const std::vector<double> cl = clone_records(clone_R, clone_p, n_clones);
+  Dev dcl, dR, dt, dan, drho, dfan, dpos, dfo, doc, doz, dro, dH1, dh2, dr1, dHo, dr, dsc;
+  bool ok = dcl.put(cl.data(), cl.size()) && dR.put(R_b2c, 9) && dt.put(t_c_b, 3) && dan.put(anchor, n_feat) &&
+            drho.put(inv_depth, n_feat) && dfan.put(f_an, 2 * (size_t)n_feat) && dpos.put(positions, 3 * (size_t)n_feat) &&
+            dfo.put(feat_off, n_feat + 1) && doc.put(obs_clone, n_obs) && doz.put(obs_z, 2 * (size_t)n_obs) &&
+            dro.put(row_off.data(), n_feat + 1) && dH1.make<double>((size_t)n_feat * D) && dh2.make<double>(n_feat) &&
+            dr1.make<double>(n_feat) && dHo.make<double>((size_t)n_ho * D) && dr.make<double>(n_ho) &&
+            dsc.make<double>((size_t)n_feat * 64 * D);
+  if (!ok) return ORCVIO_ERR_CUDA;
+  cudaMemset(dH1.p, 0, (size_t)n_feat * D * 8);
+  cudaMemset(dh2.p, 0, (size_t)n_feat * 8);
+  cudaMemset(dr1.p, 0, (size_t)n_feat * 8);
+  EkfNewArgs a{dcl.as<double>(), dR.as<double>(), dt.as<double>(), n_clones, D, dan.as<int>(), drho.as<double>(),
+               dfan.as<double>(), dpos.as<double>(), dfo.as<int>(), doc.as<int>(), doz.as<double>(), dro.as<int>(),
+               dH1.as<double>(), dh2.as<double>(), dr1.as<double>(), dHo.as<double>(), dr.as<double>(), dsc.as<double>()};
+  k_ekf_new_rows<<<n_feat, 128>>>(a);
+  check_launch("k_ekf_new_rows");
+  ok = cudaMemcpy(H_1, dH1.p, (size_t)n_feat * D * 8, cudaMemcpyDeviceToHost) == cudaSuccess &&
+       cudaMemcpy(h_2, dh2.p, (size_t)n_feat * 8, cudaMemcpyDeviceToHost) == cudaSuccess &&
+       cudaMemcpy(r_1, dr1.p, (size_t)n_feat * 8, cudaMemcpyDeviceToHost) == cudaSuccess &&
+       (n_ho == 0 || (cudaMemcpy(H_o, dHo.p, (size_t)n_ho * D * 8, cudaMemcpyDeviceToHost) == cudaSuccess &&
+                      cudaMemcpy(r_o, dr.p, (size_t)n_ho * 8, cudaMemcpyDeviceToHost) == cudaSuccess));
+  return ok ? ORCVIO_OK : ORCVIO_ERR_CUDA;
+}
+
+extern "C" int orcvio_ekf_delayed_init(const double* P, int D, const double* dx_leg, const double* H_1, const double* h_2,
+                                       const double* r_1, int n_new, double noise_var, double* dx_new, double* P_aug) {
+  using namespace ob;
+  if (D < 1 || n_new < 1) return ORCVIO_ERR_ARG;
+  for (int j = 0; j < n_new; ++j)
+    if (!(h_2[j] != 0.0)) return ORCVIO_ERR_ARG;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1) return ORCVIO_ERR_NO_DEVICE;
+  const int Da = D + n_new;
+  Dev dP, ddx, dH1, dh2, dr1, dn, dxn, dPa;
+  bool ok = dP.put(P, (size_t)D * D) && ddx.put(dx_leg, D) && dH1.put(H_1, (size_t)n_new * D) && dh2.put(h_2, n_new) &&
+            dr1.put(r_1, n_new) && dn.make<double>((size_t)n_new * D) && dxn.make<double>(n_new) &&
+            dPa.make<double>((size_t)Da * Da);
+  if (!ok) return ORCVIO_ERR_CUDA;
+  EkfInitArgs a{dP.as<double>(), D, n_new, ddx.as<double>(), dH1.as<double>(), dh2.as<double>(), dr1.as<double>(),
+                noise_var, dn.as<double>(), dxn.as<double>(), dPa.as<double>()};
+  k_ekf_init_cross<<<n_new, 256, (size_t)D * sizeof(double)>>>(a);
+  check_launch("k_ekf_init_cross");
+  k_ekf_init_assemble<<<(int)(((size_t)Da * Da + 255) / 256), 256>>>(a);
+  check_launch("k_ekf_init_assemble");
+  ok = cudaMemcpy(dx_new, dxn.p, (size_t)n_new * 8, cudaMemcpyDeviceToHost) == cudaSuccess &&
+       cudaMemcpy(P_aug, dPa.p, (size_t)Da * Da * 8, cudaMemcpyDeviceToHost) == cudaSuccess;
+  return ok ? ORCVIO_OK : ORCVIO_ERR_CUDA;
 }

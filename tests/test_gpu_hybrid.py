@@ -116,3 +116,57 @@ def test_anchor_change_covariance(seed, N, E):
     out = api.ekf_remove_feature_cov(P, N, E // 2)
     c = 22 + 6 * N + E // 2
     np.testing.assert_array_equal(out, np.delete(np.delete(P, c, axis=0), c, axis=1))
+
+
+@pytest.mark.parametrize("seed,N,F", [(7, 7, 3), (8, 20, 24)])
+def test_new_feature_rows_and_delayed_initialisation(seed, N, F):
+    """H2 (featureJacobian_ekf_new) + H3 (sparsification) + the new-state part of measurementUpdate_hybrid.  The
+    nullspace basis is not unique: the feature-free rows are compared through their Gram invariants,
+    the initialisation through HH = H_2^-1 H_1, H_2^-1 r_1 and the augmented covariance, which are basis independent."""
+    rng, R_b2c, t_c_b, clone_R, clone_p = _window(seed, N)
+    anchor, rho, f_an, pos, feat_off, obs_clone, obs_z = _features(rng, R_b2c, t_c_b, clone_R, clone_p, F)
+    # every feature needs at least two observations that are not the anchor's own
+    keep = [f for f in range(F) if (obs_clone[feat_off[f]:feat_off[f + 1]] != anchor[f]).sum() >= 2]
+    assert len(keep) >= 2
+    fo, oc, oz = [0], [], []
+    for f in keep:
+        oc.extend(obs_clone[feat_off[f]:feat_off[f + 1]])
+        oz.extend(obs_z[feat_off[f]:feat_off[f + 1]])
+        fo.append(len(oc))
+    anchor, rho, f_an, pos = anchor[keep], rho[keep], f_an[keep], pos[keep]
+    feat_off, obs_clone, obs_z = np.array(fo, np.int32), np.array(oc, np.int32), np.array(oz)
+    Fk = len(keep)
+    D = 22 + 6 * N
+    out = api.ekf_new_feature_rows(clone_R, clone_p, R_b2c, t_c_b, anchor, rho, f_an, pos, feat_off, obs_clone, obs_z, D)
+    blocks, rs = [], []
+    for j in range(Fk):
+        sl = slice(feat_off[j], feat_off[j + 1])
+        H, r = hy.feature_jacobian_ekf_new(clone_R, clone_p, R_b2c, t_c_b, obs_clone[sl], obs_z[sl], int(anchor[j]), D + j,
+                                           D + Fk, [f_an[j, 0], f_an[j, 1], 1.0], rho[j], pos[j])
+        blocks.append(H)
+        rs.append(r)
+    H_new, r_new = np.vstack(blocks), np.concatenate(rs)
+    Hs, rs_ = hy.sparsify_new_features(H_new, r_new, Fk)
+    rows = H_new.shape[0]
+    Ho_ref, ro_ref = Hs[:rows - Fk, :D], rs_[:rows - Fk]
+    H1_ref, H2_ref, r1_ref = Hs[rows - Fk:, :D], Hs[rows - Fk:, D:], rs_[rows - Fk:]
+    assert out["H_o"].shape == Ho_ref.shape
+    G, G_ref = out["H_o"].T @ out["H_o"], Ho_ref.T @ Ho_ref
+    assert np.abs(G - G_ref).max() <= 1e-10 * np.abs(G_ref).max()
+    b, b_ref = out["H_o"].T @ out["r_o"], Ho_ref.T @ ro_ref
+    assert np.abs(b - b_ref).max() <= 1e-10 * max(np.abs(b_ref).max(), 1e-300)
+    assert abs(out["r_o"] @ out["r_o"] - ro_ref @ ro_ref) <= 1e-10 * (ro_ref @ ro_ref)
+    HH, HH_ref = out["H_1"] / out["h_2"][:, None], np.linalg.solve(H2_ref, H1_ref)
+    assert np.abs(HH - HH_ref).max() <= 1e-10 * np.abs(HH_ref).max()
+    assert np.abs(out["r_1"] / out["h_2"] - np.linalg.solve(H2_ref, r1_ref)).max() <= 1e-10 * max(np.abs(r1_ref / np.diag(H2_ref)).max(), 1e-300)
+    np.testing.assert_allclose(np.abs(out["h_2"]), np.abs(np.diag(H2_ref)), rtol=1e-12)
+    # delayed initialisation on top of a posterior
+    A = rng.normal(0, 0.02, (D, D))
+    P = A @ A.T + 1e-6 * np.eye(D)
+    dx_leg = rng.normal(0, 1e-3, D)
+    sigma2 = 6.4e-5
+    dx_ref, P_ref = hy.delayed_initialization(P, dx_leg, H1_ref, H2_ref, r1_ref, sigma2)
+    dx_new, P_aug = api.ekf_delayed_init(P, dx_leg, out["H_1"], out["h_2"], out["r_1"], sigma2)
+    assert np.abs(dx_new - dx_ref).max() <= 1e-9 * max(np.abs(dx_ref).max(), 1e-300)
+    assert np.abs(P_aug - P_ref).max() <= 1e-9 * np.abs(P_ref).max()
+    assert np.abs(P_aug - P_aug.T).max() == 0.0

@@ -151,3 +151,47 @@ def test_update_feature_cov_is_a_congruence():
     T[22 + 6 * N + fidx] = J[0]
     np.testing.assert_allclose(Pn, T @ P @ T.T, rtol=1e-12, atol=1e-15)      # P' = T P T^T: still symmetric PSD
     assert np.linalg.eigvalsh(Pn).min() > 0
+
+
+def test_new_feature_rows_decouple_and_initialise():
+    """H3 + the delayed initialisation: for 1-D inverse-depth features the feature part of the stacked new rows has
+    one column per feature with disjoint row supports, so H_2 is diagonal, and the initialised inverse depths
+    reproduce the measurements (noise-free case: dx_new closes the residual exactly to first order)."""
+    rng = np.random.default_rng(3)
+    N = 7
+    R_b2c, t_c_b = mu.so3_exp(rng.normal(0, 0.8, 3)), rng.normal(0, 0.1, 3)
+    clone_R = [mu.so3_exp(rng.normal(0, 0.05, 3)) for _ in range(N)]
+    clone_p = [np.array([0.25 * i, 0.0, 0.0]) + rng.normal(0, 0.02, 3) for i in range(N)]
+    D = 22 + 6 * N
+    feats = [(0, [0, 1, 2, 4], 0.12), (3, [1, 3, 5, 6], 0.2), (6, [2, 4, 5, 6], 0.08)]   # (anchor, observers, rho)
+    sz = len(feats)
+    blocks, rs = [], []
+    for j, (a, obs, rho) in enumerate(feats):
+        f_an = np.array([0.05 * j, -0.03 * j, 1.0])
+        rho_guess = rho * 1.05                                   # linearisation point off by 5 %
+        p_true = hy.feature_position_from_anchor(clone_R[a], clone_p[a], R_b2c, t_c_b, f_an, rho)
+        p_lin = hy.feature_position_from_anchor(clone_R[a], clone_p[a], R_b2c, t_c_b, f_an, rho_guess)
+        zs = []
+        for c in obs:
+            p_ck = R_b2c @ clone_R[c].T @ (p_true - (clone_p[c] + clone_R[c] @ t_c_b))
+            zs.append(p_ck[:2] / p_ck[2])
+        H, r = hy.feature_jacobian_ekf_new(clone_R, clone_p, R_b2c, t_c_b, obs, zs, a, D + j, D + sz, f_an, rho_guess, p_lin)
+        blocks.append(H)
+        rs.append(r)
+    H_new, r_new = np.vstack(blocks), np.concatenate(rs)
+    Hs, rs_ = hy.sparsify_new_features(H_new, r_new, sz)
+    rows = H_new.shape[0]
+    assert np.abs(Hs[:rows - sz, D:]).max() < 1e-12               # the nullspace rows lost their feature part
+    H_1, H_2, r_1 = Hs[rows - sz:, :D], Hs[rows - sz:, D:], rs_[rows - sz:]
+    assert np.abs(H_2 - np.diag(np.diag(H_2))).max() < 1e-12      # diagonal: the reference's ldlt() solve is valid
+    A = rng.normal(0, 0.01, (D, D))
+    P = A @ A.T + 1e-6 * np.eye(D)
+    dx_new, P_aug = hy.delayed_initialization(P, np.zeros(D), H_1, H_2, r_1, 6.4e-5)
+    for j, (a, obs, rho) in enumerate(feats):
+        assert abs((rho * 1.05 + dx_new[j]) - rho) < 2e-3 * rho   # one Gauss-Newton step from 5 % off
+    assert np.linalg.eigvalsh(P_aug).min() > 0 and np.abs(P_aug - P_aug.T).max() == 0
+    # invariance under the basis: any orthogonal mixing of the bottom rows gives the same initialisation
+    Qm = np.linalg.qr(rng.normal(size=(sz, sz)))[0]
+    dx2, P2 = hy.delayed_initialization(P, np.zeros(D), Qm @ H_1, Qm @ H_2, Qm @ r_1, 6.4e-5)
+    np.testing.assert_allclose(dx2, dx_new, rtol=1e-9, atol=1e-15)
+    np.testing.assert_allclose(P2, P_aug, rtol=1e-9, atol=1e-18)
