@@ -266,6 +266,13 @@ int orcvio_ekf_new_feature_rows(const double* clone_R, const double* clone_p, in
 int orcvio_ekf_delayed_init(const double* P, int D, const double* dx_leg, const double* H_1, const double* h_2,
                             const double* r_1, int n_new, double noise_var, double* dx_new, double* P_aug);
 
+/* Legacy-state part of measurementUpdate_hybrid (orcvio.cpp:1808-1820, 1884-1901) on a state WITH inverse-depth feature
+ * states behind the clones: P is D x D (D = 22 + 6 N + E <= 208, symmetric, rows / columns 15..21 zero), H the stacked
+ * H_o (rows x D, row-major; its columns 0..21 are ignored: P is zero under the extrinsic columns and vision rows do not
+ * touch the IMU block), r its residual.  dx = K r (D) and P_out = (I - K H) P, symmetrised (D x D). */
+int orcvio_hybrid_update_dense(const double* P, int D, const double* H, const double* r, int rows, double noise_var,
+                               double* dx, double* P_out);
+
 /* Stage 3 (O1-O4): keypoint + bbox residuals and Jacobians of one object over T frames.
  * frames_wTc: T x 16 (row-major 4x4), wTo 16, shape 3, kps K x 3, zs T x K x 2 (NaN = not
  * observed), zb T x 4.  flags: bit0 left perturbation, bit1 new bbox residual.

@@ -203,3 +203,15 @@ def delayed_initialization(P_post, dx_leg, H_1, H_2, r_1, sigma2):
     out[:D, D:] = nHHP.T
     out[D:, D:] = P22
     return dx_new, (out + out.T) / 2.0
+
+
+def legacy_update(P, H_o, r_o, sigma2):
+    """Legacy-state part of measurementUpdate_hybrid (:1808-1820, 1884-1901; no Schmidt):
+    S = H P H^T + sigma^2 I, K^T = S^-1 H P, dx = K r, P <- (I - K H) P, symmetrised."""
+    P = np.asarray(P, dtype=float)
+    H = np.asarray(H_o, dtype=float)
+    S = H @ P @ H.T + sigma2 * np.eye(H.shape[0])
+    K = np.linalg.solve(S, H @ P).T
+    dx = K @ np.asarray(r_o, dtype=float)
+    Pn = (np.eye(P.shape[0]) - K @ H) @ P
+    return dx, (Pn + Pn.T) / 2.0

@@ -743,3 +743,21 @@ def ekf_delayed_init(P, dx_leg, H_1, h_2, r_1, noise_var):
     if rc != 0:
         raise RuntimeError(f"orcvio_ekf_delayed_init failed: {rc}")
     return dx_new, P_aug
+
+
+def hybrid_update_dense(P, H, r, noise_var):
+    """Legacy-state part of measurementUpdate_hybrid on a state with feature columns: returns (dx, P_posterior)."""
+    L = lib()
+    Pm = np.ascontiguousarray(P, dtype=np.float64)
+    D = Pm.shape[0]
+    Hm = np.ascontiguousarray(H, dtype=np.float64).reshape(-1, D)
+    rv = _f64(r)
+    dx, Po = np.zeros(D), np.zeros((D, D))
+    L.orcvio_hybrid_update_dense.restype = C.c_int
+    L.orcvio_hybrid_update_dense.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_double, C.c_void_p,
+                                             C.c_void_p]
+    rc = L.orcvio_hybrid_update_dense(Pm.ctypes.data, D, Hm.ctypes.data, rv.ctypes.data, Hm.shape[0], float(noise_var),
+                                      dx.ctypes.data, Po.ctypes.data)
+    if rc != 0:
+        raise RuntimeError(f"orcvio_hybrid_update_dense failed: {rc}")
+    return dx, Po

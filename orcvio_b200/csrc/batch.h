@@ -182,6 +182,9 @@ class Batch {
                                  int* rows_out);
   int object_update(int fi, const double* Hx, const double* Hf, const double* res, int rows, int odim,
                     int* status_out, double* gamma_out);
+  // legacy-state part of measurementUpdate_hybrid on a state with feature columns (objects.cu)
+  int dense_update(const double* P_in, int D, const double* H, const double* r, int rows, double* dx_out,
+                   double* P_out);
   // stage 6 stand-alone (objects.cu)
   int propagate_standalone(double* state16, const double* bg, const double* ba, const double* gyro_old,
                            const double* acc_old, const OrcvioImu* imu, int n, double* P, int D,

@@ -269,6 +269,17 @@ static std::unique_ptr<Batch> make_snapshot_batch(int n_clones, int flags, doubl
   return b;
 }
 
+int orcvio_hybrid_update_dense(const double* P, int D, const double* H, const double* r, int rows,
+                               double noise_var, double* dx, double* P_out) {
+  const int n = D - ORCVIO_LEG;
+  if (!P || !H || !r || !dx || !P_out || n < 1 || rows < 1) return ORCVIO_ERR_ARG;
+  const int ncap = (n + 5) / 6;
+  if (ncap > 31) return ORCVIO_ERR_ARG;          // D <= 208: the one-CTA factorisations hold the whole matrix on chip
+  auto b = make_snapshot_batch(ncap, 0, noise_var, 0.95, -1.0, 1e-3, 100.0);
+  if (!b->ok()) return ORCVIO_ERR_NO_DEVICE;
+  return b->dense_update(P, D, H, r, rows, dx, P_out);
+}
+
 int orcvio_triangulate(const double* cam_R, const double* cam_t, int n_clones, const int* feat_off,
                        const int* obs_clone, const double* obs_z, int n_feat, double translation_threshold,
                        double cost_threshold, double init_final_dist_threshold, double* out_pos,

@@ -42,7 +42,7 @@ __global__ void __launch_bounds__(CHOL_THREADS) k_chol_prior(UpdArgs a, double* 
   const int fi = blockIdx.x;
   const FilterWork fw = a.fw[fi];
   if (!fw.active) return;
-  const int D = fw.D, n = 6 * fw.N, L = ORCVIO_LEG;
+  const int D = fw.D, n = fw.D - ORCVIO_LEG, L = ORCVIO_LEG;   // n = 6N (+ E feature states behind the clones)
   const int Tm = (D + 7) >> 3;
   const double* P = a.P + (size_t)fi * a.p_stride;
   double* FT = a.T + (size_t)fi * a.t_stride;
@@ -280,7 +280,7 @@ __global__ void __launch_bounds__(256) k_syrk(UpdArgs a, const double* __restric
     filter_rows[fi] = rows;
   }
   if (!fw.active) return;
-  const int n = 6 * fw.N, n1 = n + 1;
+  const int n = fw.D - ORCVIO_LEG, n1 = n + 1;
   const SyrkPlan pl = syrk_plan(fw, cta_budget);
   if (unit >= pl.total) return;
   // work unit -> pair (I, J), I <= J, and chunk
@@ -459,7 +459,7 @@ __global__ void __launch_bounds__(CHOL_THREADS) k_chol_w_solve(UpdArgs a) {
   const int fi = blockIdx.y;
   const FilterWork fw = a.fw[fi];
   if (!fw.active) return;
-  const int n = 6 * fw.N, D = fw.D;
+  const int n = fw.D - ORCVIO_LEG, D = fw.D;
   const int d0 = blockIdx.x * CS;
   if (d0 >= D) return;
   const int nd = min(CS, D - d0);
@@ -518,7 +518,7 @@ __global__ void __launch_bounds__(PI_THREADS) k_pinfo(UpdArgs a, const double* L
   const int fi = blockIdx.z;
   const FilterWork fw = a.fw[fi];
   if (!fw.active) return;
-  const int n = 6 * fw.N, D = fw.D, L = ORCVIO_LEG;
+  const int n = fw.D - ORCVIO_LEG, D = fw.D, L = ORCVIO_LEG;
   const int tid = threadIdx.x;
   if (blockIdx.y == gridDim.y - 1) {
     if (blockIdx.x != 0) return;
@@ -645,10 +645,10 @@ static void launch_pinfo(const UpdArgs& u, const InfoBufs& ib, int nmax, int B, 
 // prior factor, A = Hp L, W = s^2 I + A^T A, Cholesky with F_1 / v carried.  Leaves Y in u.T,
 // y in u.yv, dx in u.dx and W_aug's corner r'^T r' untouched in u.S[n][n]:
 //   gamma = r'^T (Hp P Hp^T + s^2 I)^-1 r' = (r'^T r' - y^T y) / s^2      (Woodbury).
-void launch_info_dense_factor(const UpdArgs& u, const InfoBufs& ib, const double* Hp, int ldh, int rows, int N,
+void launch_info_dense_factor(const UpdArgs& u, const InfoBufs& ib, const double* Hp, int ldh, int rows, int n,
                               cudaStream_t s) {
   info_attrs();
-  const int n = 6 * N, D = ORCVIO_LEG + n;
+  const int D = ORCVIO_LEG + n;
   const size_t sm_prior = (chol_smem_doubles(D, 0) + (size_t)D + 2) * sizeof(double);
   k_chol_prior<<<1, CHOL_THREADS, sm_prior, s>>>(u, ib.Ls);
   check_launch("k_chol_prior");
@@ -662,9 +662,9 @@ void launch_info_dense_factor(const UpdArgs& u, const InfoBufs& ib, const double
 }
 
 // Object update, second half (after the gate passed): state increment, P+.
-void launch_info_dense_apply(const UpdArgs& u, const InfoBufs& ib, int N, cudaStream_t s) {
+void launch_info_dense_apply(const UpdArgs& u, const InfoBufs& ib, int n, cudaStream_t s) {
   info_attrs();
-  launch_pinfo(u, ib, 6 * N, 1, s);
+  launch_pinfo(u, ib, n, 1, s);
 }
 
 // Prior factor on the second stream: it depends only on P, so it overlaps triangulation / Jacobians

@@ -97,7 +97,7 @@ struct Tile {
 
 struct FilterWork {              // per filter, per update
   int N;                         // clones
-  int D;                         // 22 + 6N
+  int D;                         // 22 + 6N (+ E inverse-depth feature states behind the clones: dense hybrid update)
   int tile_begin, tile_end;      // tiles of this filter, sorted by c0_blk
   int wmax_blk;                  // widest tile window (blocks)
   int active;                    // 0: skip this filter's update entirely
@@ -202,9 +202,9 @@ void launch_info_update(const QrArgs& q, const UpdArgs& u, const InfoBufs& ib, i
                         cudaEvent_t prior_t1 = nullptr);
 void launch_info_prior(const UpdArgs& u, const InfoBufs& ib, int max_N, cudaStream_t s2, cudaEvent_t fork,
                        cudaEvent_t join, cudaEvent_t t0 = nullptr, cudaEvent_t t1 = nullptr);
-void launch_info_dense_factor(const UpdArgs& u, const InfoBufs& ib, const double* Hp, int ldh, int rows, int N,
+void launch_info_dense_factor(const UpdArgs& u, const InfoBufs& ib, const double* Hp, int ldh, int rows, int n,
                               cudaStream_t s);
-void launch_info_dense_apply(const UpdArgs& u, const InfoBufs& ib, int N, cudaStream_t s);
+void launch_info_dense_apply(const UpdArgs& u, const InfoBufs& ib, int n, cudaStream_t s);
 void launch_project_dense(double* M, int rows, int ld, int nelim, int ncols, cudaStream_t s);
 void launch_object_rows(const double* frames_wTc, int T, const double* wTo, const double* shape, const double* kps,
                         int K, const double* zs, const double* zb, int flags, const int* kp_row_off, int rows_kp,
@@ -235,7 +235,7 @@ struct SyrkPlan {
 };
 __host__ __device__ inline SyrkPlan syrk_plan(const FilterWork& fw, int cta_budget) {
   SyrkPlan p;
-  p.nt = (6 * fw.N + 1 + SY_TILE - 1) / SY_TILE;
+  p.nt = (fw.D - ORCVIO_LEG + 1 + SY_TILE - 1) / SY_TILE;
   if (p.nt > SY_MAXT) p.nt = SY_MAXT;
   p.npairs = p.nt * (p.nt + 1) / 2;
   int rowsJ[SY_MAXT];

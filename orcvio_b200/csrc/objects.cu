@@ -262,7 +262,7 @@ int Batch::object_update(int fi, const double* Hx, const double* Hf, const doubl
   ib.max_units = units; ib.cta_budget = n_sm_ * syrk_waves_; ib.group = syrk_group_; ib.syrk_cnt = dSyrkCnt_;
   ib.tile_rows = nullptr; ib.filter_rows = dFilterRows_ + fi;
   const double* Hp = dM.as<double>() + (size_t)odim * ld + odim;
-  launch_info_dense_factor(ua, ib, Hp, ld, prow, N, stream_);
+  launch_info_dense_factor(ua, ib, Hp, ld, prow, n, stream_);
   launches_ += 5;
   std::vector<double> y(n);
   double corner = 0.0;
@@ -282,7 +282,7 @@ int Batch::object_update(int fi, const double* Hx, const double* Hf, const doubl
     for (int k = 0; k < D; ++k)
       if (std::isnan(Hx[(size_t)k * rows + i])) return done(5, 0);
   }
-  launch_info_dense_apply(ua, ib, N, stream_);
+  launch_info_dense_apply(ua, ib, n, stream_);
   launches_ += 1;
   download_mirrors();
   CKO(cudaStreamSynchronize(stream_));
@@ -339,6 +339,71 @@ int Batch::propagate_standalone(double* state16, const double* bg, const double*
   for (int k = 0; k < 3; ++k) { state16[9 + k] = im[IM_V + k]; state16[12 + k] = im[IM_P + k]; }
   state16[15] = im[IM_TIME];
   return ORCVIO_OK;
+}
+
+// measurementUpdate_hybrid, legacy-state part (src/orcvio.cpp:1808-1820, 1884-1901), on a state with E inverse-depth
+// feature states behind the clones (D = 22 + 6 N + E): the stacked H_o may touch every column behind the IMU block,
+// so it goes through the dense whitened update (prior factor, A = H L, W = s^2 I + A^T A, P+ = s^2 Y^T Y + F_2 F_2^T)
+// with n = D - 22 window columns.  Stage-level entry: P and H_o come from the caller, dx and P+ go back.
+int Batch::dense_update(const double* P_in, int D, const double* H, const double* r, int rows, double* dx_out,
+                        double* P_out) {
+  if (!ok_) return ORCVIO_ERR_NO_DEVICE;
+  const int n = D - ORCVIO_LEG;
+  if (n < 1 || D > ldp_ || n > 6 * Ncap_ || rows < 1) return ORCVIO_ERR_ARG;
+  const int fi = 0;
+  CKO(cudaMemsetAsync(dP_, 0, (size_t)ldp_ * ldp_ * sizeof(double), stream_));
+  CKO(cudaMemcpy2DAsync(dP_, ldp_ * sizeof(double), P_in, D * sizeof(double), D * sizeof(double), D,
+                        cudaMemcpyHostToDevice, stream_));
+  const int ld = n + 1;
+  std::vector<double> M((size_t)rows * ld);
+  for (int i = 0; i < rows; ++i) {
+    for (int k = 0; k < n; ++k) M[(size_t)i * ld + k] = H[(size_t)i * D + ORCVIO_LEG + k];
+    M[(size_t)i * ld + n] = r[i];
+  }
+  DevBuf dM, dFw;
+  CKO(dM.alloc(M.size() * sizeof(double)));
+  CKO(cudaMemcpyAsync(dM.p, M.data(), M.size() * sizeof(double), cudaMemcpyHostToDevice, stream_));
+  FilterWork fw{};
+  fw.N = 0;                                              // no clone poses behind this entry: dx is returned, not applied
+  fw.D = D; fw.active = 1; fw.arow0 = 0; fw.arows = rows;
+  const int units = syrk_plan(fw, n_sm_ * syrk_waves_).total;
+  const size_t need_a = ((size_t)rows + 16) * ldr_;
+  if (need_a > amat_cap_) {
+    if (dAmat_) cudaFree(dAmat_);
+    amat_cap_ = need_a * 2;
+    CKO(cudaMalloc(&dAmat_, amat_cap_ * sizeof(double)));
+  }
+  const size_t need_p = (size_t)units * 4096;
+  if (need_p > part_cap_) {
+    if (dPart_) cudaFree(dPart_);
+    part_cap_ = need_p * 2;
+    CKO(cudaMalloc(&dPart_, part_cap_ * sizeof(double)));
+  }
+  CKO(dFw.alloc(sizeof(FilterWork)));
+  CKO(cudaMemcpyAsync(dFw.p, &fw, sizeof(fw), cudaMemcpyHostToDevice, stream_));
+  const size_t r_stride = (size_t)(6 * Ncap_ + 1) * ldr_;
+  UpdArgs ua{};
+  ua.fw = dFw.as<FilterWork>(); ua.n_filters = 1;
+  ua.P = dP_; ua.p_stride = (size_t)ldp_ * ldp_; ua.ldp = ldp_;
+  ua.Rm = dR_; ua.rthin = dRthin_; ua.r_stride = r_stride; ua.ldr = ldr_;
+  ua.T = dT_; ua.S = dS_; ua.t_stride = (size_t)(6 * Ncap_) * ldt_; ua.ldt = ldt_;
+  ua.yv = dYv_;
+  ua.imu = dImu_; ua.clones = dClones_; ua.clone_stride = (size_t)Ncap_ * CL_STRIDE;
+  ua.dx = dDx_; ua.lddx = ldp_;
+  ua.flags = 0; ua.sigma2 = p_.feature_observation_noise;
+  InfoBufs ib{};
+  ib.Ls = dLs_; ib.Amat = dAmat_; ib.part = dPart_;
+  ib.max_units = units; ib.cta_budget = n_sm_ * syrk_waves_; ib.group = syrk_group_; ib.syrk_cnt = dSyrkCnt_;
+  ib.tile_rows = nullptr; ib.filter_rows = dFilterRows_ + fi;
+  CKO(cudaMemsetAsync(dImu_, 0, IM_STRIDE * sizeof(double), stream_));
+  launch_info_dense_factor(ua, ib, dM.as<double>(), ld, rows, n, stream_);
+  launch_info_dense_apply(ua, ib, n, stream_);
+  launches_ += 6;
+  CKO(cudaMemcpyAsync(dx_out, dDx_, D * sizeof(double), cudaMemcpyDeviceToHost, stream_));
+  CKO(cudaMemcpy2DAsync(P_out, D * sizeof(double), dP_, ldp_ * sizeof(double), D * sizeof(double), D,
+                        cudaMemcpyDeviceToHost, stream_));
+  CKO(cudaStreamSynchronize(stream_));
+  return launch_error_count() > 0 ? ORCVIO_ERR_CUDA : ORCVIO_OK;
 }
 
 }  // namespace ob

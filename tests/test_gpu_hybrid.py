@@ -170,3 +170,57 @@ def test_new_feature_rows_and_delayed_initialisation(seed, N, F):
     assert np.abs(dx_new - dx_ref).max() <= 1e-9 * max(np.abs(dx_ref).max(), 1e-300)
     assert np.abs(P_aug - P_ref).max() <= 1e-9 * np.abs(P_ref).max()
     assert np.abs(P_aug - P_aug.T).max() == 0.0
+
+
+@pytest.mark.parametrize("seed,N,F,Fnew", [(9, 8, 4, 3), (10, 20, 24, 8)])
+def test_hybrid_update_with_feature_states(seed, N, F, Fnew):
+    """measurementUpdate_hybrid end to end at the stage level on a state with F inverse-depth features behind the
+    clones: H_o = [MSCKF-like rows; gated rows of the F state features; feature-free rows of Fnew new features] through
+    the dense whitened update with n = 6N + F window columns, then the delayed initialisation of the new features."""
+    rng, R_b2c, t_c_b, clone_R, clone_p = _window(seed, N)
+    D = 22 + 6 * N + F
+    A = rng.normal(0, 0.02, (D, D))
+    P = A @ A.T * 0.05 + 1e-6 * np.eye(D)
+    P[15:22, :] = 0.0
+    P[:, 15:22] = 0.0
+    sigma2 = 6.4e-5
+    # rows of the features already in the state (newest clone observes them)
+    anchor, rho, f_an, pos, _, _, _ = _features(rng, R_b2c, t_c_b, clone_R, clone_p, F)
+    anchor = np.minimum(anchor, N - 2).astype(np.int32)           # not anchored in the observing clone
+    pos = np.array([hy.feature_position_from_anchor(clone_R[a], clone_p[a], R_b2c, t_c_b, [fx, fy, 1.0], r)
+                    for a, r, (fx, fy) in zip(anchor, rho, f_an)])
+    k = N - 1
+    z = np.array([(lambda p_ck: p_ck[:2] / p_ck[2])(R_b2c @ clone_R[k].T @ (pos[f] - (clone_p[k] + clone_R[k] @ t_c_b)))
+                  for f in range(F)]) + rng.normal(0, 0.004, (F, 2))
+    rows_ekf = api.ekf_feature_rows(clone_R, clone_p, R_b2c, t_c_b, anchor, rho, f_an, pos, z, P, sigma2, 0.95)
+    keep = np.repeat(rows_ekf["pass"].astype(bool), 2)
+    H_ekf, r_ekf = rows_ekf["H"][keep], rows_ekf["r"][keep]
+    assert H_ekf.shape[0] >= 2
+    # new features (legacy dimension D): their feature-free rows join H_o
+    a2, rho2, fan2, pos2, fo2, oc2, oz2 = _features(rng, R_b2c, t_c_b, clone_R, clone_p, Fnew + 6)
+    ok = [f for f in range(Fnew + 6) if (oc2[fo2[f]:fo2[f + 1]] != a2[f]).sum() >= 2][:Fnew]
+    fo, oc, oz = [0], [], []
+    for f in ok:
+        oc.extend(oc2[fo2[f]:fo2[f + 1]])
+        oz.extend(oz2[fo2[f]:fo2[f + 1]])
+        fo.append(len(oc))
+    new = api.ekf_new_feature_rows(clone_R, clone_p, R_b2c, t_c_b, a2[ok], rho2[ok], fan2[ok], pos2[ok],
+                                   np.array(fo, np.int32), np.array(oc, np.int32), np.array(oz), D)
+    # a few generic clone-only rows standing in for the compressed MSCKF block
+    H_m = np.zeros((3 * N, D))
+    H_m[:, 22:22 + 6 * N] = rng.normal(0, 1.0, (3 * N, 6 * N))
+    r_m = rng.normal(0, 0.01, 3 * N)
+    H_o = np.vstack([H_m, H_ekf, new["H_o"]])
+    r_o = np.concatenate([r_m, r_ekf, new["r_o"]])
+    dx_ref, P_ref = hy.legacy_update(P, H_o, r_o, sigma2)
+    dx, Pp = api.hybrid_update_dense(P, H_o, r_o, sigma2)
+    assert np.abs(dx - dx_ref).max() <= 1e-9 * np.abs(dx_ref).max()
+    assert np.abs(Pp - P_ref).max() <= 1e-9 * np.abs(P_ref).max()
+    assert np.abs(Pp - Pp.T).max() == 0.0
+    # ... and the new features enter the state
+    H2 = np.diag(new["h_2"])
+    dxn_ref, Pa_ref = hy.delayed_initialization(P_ref, dx_ref, new["H_1"], H2, new["r_1"], sigma2)
+    dxn, Pa = api.ekf_delayed_init(Pp, dx, new["H_1"], new["h_2"], new["r_1"], sigma2)
+    assert np.abs(dxn - dxn_ref).max() <= 1e-8 * max(np.abs(dxn_ref).max(), 1e-300)
+    assert np.abs(Pa - Pa_ref).max() <= 1e-8 * np.abs(Pa_ref).max()
+    assert Pa.shape == (D + len(ok), D + len(ok))
