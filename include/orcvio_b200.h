@@ -266,6 +266,13 @@ int orcvio_ekf_new_feature_rows(const double* clone_R, const double* clone_p, in
 int orcvio_ekf_delayed_init(const double* P, int D, const double* dx_leg, const double* H_1, const double* h_2,
                             const double* r_1, int n_new, double noise_var, double* dx_new, double* P_aug);
 
+/* stateAugmentation (orcvio.cpp:963-1010) / the covariance part of pruneImuStateBuffer (:2916-2940) on a state with
+ * feature states behind the n_clones clones (D = 22 + 6 n_clones + E): the new clone block (J P J^T, J = theta and p of the
+ * IMU state) is inserted BEFORE the feature block -> P_out (D+6)^2, symmetrised; a clone's 6 rows / columns are dropped ->
+ * P_out (D-6)^2. */
+int orcvio_ekf_augment_cov(const double* P, int D, int n_clones, double* P_out);
+int orcvio_ekf_remove_clone_cov(const double* P, int D, int n_clones, int clone_idx, double* P_out);
+
 /* Legacy-state part of measurementUpdate_hybrid (orcvio.cpp:1808-1820, 1884-1901) on a state WITH inverse-depth feature
  * states behind the clones: P is D x D (D = 22 + 6 N + E <= 208, symmetric, rows / columns 15..21 zero), H the stacked
  * H_o (rows x D, row-major; its columns 0..21 are ignored: P is zero under the extrinsic columns and vision rows do not

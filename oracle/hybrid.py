@@ -215,3 +215,29 @@ def legacy_update(P, H_o, r_o, sigma2):
     dx = K @ np.asarray(r_o, dtype=float)
     Pn = (np.eye(P.shape[0]) - K @ H) @ P
     return dx, (Pn + Pn.T) / 2.0
+
+
+def state_augmentation_cov(P, n_clones):
+    """stateAugmentation, covariance part (:963-1010), with E = D - 22 - 6 n_clones feature states behind the clones:
+    P12 = J P, P11 = P12 J^T, the new 6 x 6 block is inserted before the feature block, then (P + P^T)/2."""
+    P = np.asarray(P, dtype=float)
+    D = P.shape[0]
+    pose = LEG_DIM + 6 * n_clones
+    rest = D - pose
+    J = np.zeros((6, D))
+    J[0:3, 0:3] = np.eye(3)
+    J[3:6, 6:9] = np.eye(3)
+    P12 = J @ P
+    P11 = P12 @ J.T
+    out = np.zeros((D + 6, D + 6))
+    out[:pose, :pose] = P[:pose, :pose]
+    out[pose + 6:, :pose] = P[pose:, :pose]
+    out[:pose, pose + 6:] = P[:pose, pose:]
+    out[pose + 6:, pose + 6:] = P[pose:, pose:]
+    out[pose:pose + 6, pose:pose + 6] = P11
+    out[pose:pose + 6, :pose] = P12[:, :pose]
+    out[:pose, pose:pose + 6] = P12[:, :pose].T
+    out[pose:pose + 6, pose + 6:] = P12[:, pose:]
+    out[pose + 6:, pose:pose + 6] = P12[:, pose:].T
+    assert rest >= 0
+    return (out + out.T) / 2.0

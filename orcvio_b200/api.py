@@ -761,3 +761,31 @@ def hybrid_update_dense(P, H, r, noise_var):
     if rc != 0:
         raise RuntimeError(f"orcvio_hybrid_update_dense failed: {rc}")
     return dx, Po
+
+
+def ekf_augment_cov(P, n_clones):
+    """stateAugmentation's covariance step with a feature block behind the clones: (D+6) x (D+6)."""
+    L = lib()
+    Pm = np.ascontiguousarray(P, dtype=np.float64)
+    D = Pm.shape[0]
+    out = np.zeros((D + 6, D + 6))
+    L.orcvio_ekf_augment_cov.restype = C.c_int
+    L.orcvio_ekf_augment_cov.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+    rc = L.orcvio_ekf_augment_cov(Pm.ctypes.data, D, int(n_clones), out.ctypes.data)
+    if rc != 0:
+        raise RuntimeError(f"orcvio_ekf_augment_cov failed: {rc}")
+    return out
+
+
+def ekf_remove_clone_cov(P, n_clones, clone_idx):
+    """Drop one clone's 6 rows / columns of P (pruneImuStateBuffer)."""
+    L = lib()
+    Pm = np.ascontiguousarray(P, dtype=np.float64)
+    D = Pm.shape[0]
+    out = np.zeros((D - 6, D - 6))
+    L.orcvio_ekf_remove_clone_cov.restype = C.c_int
+    L.orcvio_ekf_remove_clone_cov.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]
+    rc = L.orcvio_ekf_remove_clone_cov(Pm.ctypes.data, D, int(n_clones), int(clone_idx), out.ctypes.data)
+    if rc != 0:
+        raise RuntimeError(f"orcvio_ekf_remove_clone_cov failed: {rc}")
+    return out

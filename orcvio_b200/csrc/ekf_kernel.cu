@@ -426,6 +426,28 @@ __global__ void __launch_bounds__(256) k_ekf_init_assemble(EkfInitArgs a) {
   a.Paug[e] = v;
 }
 
+// stateAugmentation with a feature block behind the clones (src/orcvio.cpp:963-1010): the new clone's 6 x 6 block
+// goes in at index c0 = 22 + 6 N, BEFORE the feature states, and equals J P J^T with J selecting theta (0..2) and
+// p (6..8) of the IMU state -- so every entry of the new matrix is an entry of the old one: P'[i][j] = P[m(i)][m(j)].
+__global__ void k_ekf_augment(const double* P, int D, int c0, double* Pn) {
+  const int Dn = D + 6;
+  const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= (size_t)Dn * Dn) return;
+  const int i = (int)(e / Dn), j = (int)(e - (size_t)i * Dn);
+  auto m = [c0](int x) { return x < c0 ? x : (x < c0 + 6 ? (x - c0 < 3 ? x - c0 : x - c0 + 3) : x - 6); };
+  const int mi = m(i), mj = m(j);
+  Pn[e] = 0.5 * (P[(size_t)mi * D + mj] + P[(size_t)mj * D + mi]);
+}
+
+// pruneImuStateBuffer's covariance part for one clone (src/orcvio.cpp:2916-2940): drop its 6 rows / columns.
+__global__ void k_ekf_drop_block(const double* Pin, int D, int c0, int w, double* Pout) {
+  const int Dn = D - w;
+  const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= (size_t)Dn * Dn) return;
+  const int i = (int)(e / Dn), j = (int)(e - (size_t)i * Dn);
+  Pout[e] = Pin[(size_t)(i + (i >= c0 ? w : 0)) * D + (j + (j >= c0 ? w : 0))];
+}
+
 namespace {
 struct Dev {
   void* p = nullptr;
@@ -640,4 +662,32 @@ extern "C" int orcvio_ekf_delayed_init(const double* P, int D, const double* dx_
   ok = cudaMemcpy(dx_new, dxn.p, (size_t)n_new * 8, cudaMemcpyDeviceToHost) == cudaSuccess &&
        cudaMemcpy(P_aug, dPa.p, (size_t)Da * Da * 8, cudaMemcpyDeviceToHost) == cudaSuccess;
   return ok ? ORCVIO_OK : ORCVIO_ERR_CUDA;
+}
+
+extern "C" int orcvio_ekf_augment_cov(const double* P, int D, int n_clones, double* P_out) {
+  using namespace ob;
+  const int c0 = ORCVIO_LEG + 6 * n_clones;
+  if (n_clones < 0 || D < c0) return ORCVIO_ERR_ARG;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1) return ORCVIO_ERR_NO_DEVICE;
+  Dev dP, dO;
+  const int Dn = D + 6;
+  if (!dP.put(P, (size_t)D * D) || !dO.make<double>((size_t)Dn * Dn)) return ORCVIO_ERR_CUDA;
+  k_ekf_augment<<<(int)(((size_t)Dn * Dn + 255) / 256), 256>>>(dP.as<double>(), D, c0, dO.as<double>());
+  check_launch("k_ekf_augment");
+  return cudaMemcpy(P_out, dO.p, (size_t)Dn * Dn * 8, cudaMemcpyDeviceToHost) == cudaSuccess ? ORCVIO_OK : ORCVIO_ERR_CUDA;
+}
+
+extern "C" int orcvio_ekf_remove_clone_cov(const double* P, int D, int n_clones, int clone_idx, double* P_out) {
+  using namespace ob;
+  if (n_clones < 1 || clone_idx < 0 || clone_idx >= n_clones || D < ORCVIO_LEG + 6 * n_clones) return ORCVIO_ERR_ARG;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1) return ORCVIO_ERR_NO_DEVICE;
+  Dev dP, dO;
+  const int Dn = D - 6;
+  if (!dP.put(P, (size_t)D * D) || !dO.make<double>((size_t)Dn * Dn)) return ORCVIO_ERR_CUDA;
+  k_ekf_drop_block<<<(int)(((size_t)Dn * Dn + 255) / 256), 256>>>(dP.as<double>(), D, ORCVIO_LEG + 6 * clone_idx, 6,
+                                                                  dO.as<double>());
+  check_launch("k_ekf_drop_block");
+  return cudaMemcpy(P_out, dO.p, (size_t)Dn * Dn * 8, cudaMemcpyDeviceToHost) == cudaSuccess ? ORCVIO_OK : ORCVIO_ERR_CUDA;
 }

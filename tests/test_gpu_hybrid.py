@@ -224,3 +224,19 @@ def test_hybrid_update_with_feature_states(seed, N, F, Fnew):
     assert np.abs(dxn - dxn_ref).max() <= 1e-8 * max(np.abs(dxn_ref).max(), 1e-300)
     assert np.abs(Pa - Pa_ref).max() <= 1e-8 * np.abs(Pa_ref).max()
     assert Pa.shape == (D + len(ok), D + len(ok))
+
+
+@pytest.mark.parametrize("N,E", [(5, 0), (12, 7), (29, 12)])
+def test_augmentation_and_clone_removal_with_feature_block(N, E):
+    rng = np.random.default_rng(40 + N)
+    D = 22 + 6 * N + E
+    A = rng.normal(0, 0.05, (D, D))
+    P = A @ A.T + 1e-5 * np.eye(D)
+    ref = hy.state_augmentation_cov(P, N)
+    got = api.ekf_augment_cov(P, N)
+    np.testing.assert_array_equal(got, ref)
+    c = N // 2
+    out = api.ekf_remove_clone_cov(got, N + 1, c)
+    idx = np.r_[22 + 6 * c:28 + 6 * c]
+    np.testing.assert_array_equal(out, np.delete(np.delete(got, idx, axis=0), idx, axis=1))
+    assert out.shape == (D, D)

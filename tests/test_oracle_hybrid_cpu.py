@@ -195,3 +195,28 @@ def test_new_feature_rows_decouple_and_initialise():
     dx2, P2 = hy.delayed_initialization(P, np.zeros(D), Qm @ H_1, Qm @ H_2, Qm @ r_1, 6.4e-5)
     np.testing.assert_allclose(dx2, dx_new, rtol=1e-9, atol=1e-15)
     np.testing.assert_allclose(P2, P_aug, rtol=1e-9, atol=1e-18)
+
+
+def test_augmentation_with_feature_block_reduces_to_the_msckf_case():
+    """oracle/hybrid.state_augmentation_cov with E = 0 is what oracle/filter.OracleVIO.stateAugmentation does; with
+    E > 0 it is the same congruence with the new block moved in front of the feature block."""
+    rng = np.random.default_rng(2)
+    N, E = 4, 3
+    D = 22 + 6 * N + E
+    A = rng.normal(0, 0.1, (D, D))
+    P = A @ A.T
+    out = hy.state_augmentation_cov(P, N)
+    T = np.zeros((D + 6, D))
+    pose = 22 + 6 * N
+    T[:pose, :pose] = np.eye(pose)
+    T[pose:pose + 3, 0:3] = np.eye(3)
+    T[pose + 3:pose + 6, 6:9] = np.eye(3)
+    T[pose + 6:, pose:] = np.eye(E)
+    np.testing.assert_allclose(out, T @ P @ T.T, rtol=1e-13, atol=1e-16)
+    P0 = P[:pose, :pose]
+    out0 = hy.state_augmentation_cov(P0, N)
+    J = np.zeros((6, pose))
+    J[0:3, 0:3] = np.eye(3)
+    J[3:6, 6:9] = np.eye(3)
+    ref0 = np.block([[P0, (J @ P0).T], [J @ P0, J @ P0 @ J.T]])
+    np.testing.assert_allclose(out0, (ref0 + ref0.T) / 2, rtol=1e-13, atol=1e-16)
