@@ -1503,22 +1503,6 @@ int Batch::snapshot_prepare(const SnapshotIO& io) {
     }
     CK(cudaMemcpyAsync(blob_early_.dev, blob_early_.pinned, blob_early_.used, cudaMemcpyHostToDevice, stream_));
     g_hp.mark("obs_up");
-    // the early triangulation only needs the inputs to be well formed: check that here (one pass over data this
-    // thread has just read) instead of waiting for the helper thread's full scan
-    bool bad = false;
-    for (int f = 0; f < nF && !bad; ++f) {
-      const int o0 = io.feat_off[f], m = io.feat_off[f + 1] - o0;
-      if (m < 1 || m > ORCVIO_MAX_OBS || o0 < 0 || o0 + m > nobs_total) { bad = true; break; }
-      for (int k = 0; k < m; ++k) {
-        const int ci = io.obs_clone[o0 + k];
-        if (ci < 0 || ci >= N) { bad = true; break; }
-      }
-    }
-    if (bad) {
-      wait_flag(S.lists_done);
-      return ORCVIO_ERR_ARG;
-    }
-    g_hp.mark("validate");
   }
   // ---- host staging of the window
   double* cl = S.hCl0;
@@ -1583,10 +1567,29 @@ int Batch::snapshot_prepare(const SnapshotIO& io) {
     ta.cfg = tricfg_;
     ta.status = dStatusF_;
     ta.feat_off = (const int*)(blob_early_.dev + e_fo);
+    ta.direct_n_clones = N; ta.direct_n_obs = nobs_total;
     launch_triangulate(ta, stream_);
     ++launches_;
     S.tri_early = true;
     g_hp.mark("tri_early");
+    // the kernel guards itself against malformed lists; the host check that turns them into an error code runs
+    // while it is already working
+    bool bad = false;
+    for (int f = 0; f < nF && !bad; ++f) {
+      const int o0 = io.feat_off[f], m = io.feat_off[f + 1] - o0;
+      if (m < 1 || m > ORCVIO_MAX_OBS || o0 < 0 || o0 + m > nobs_total) { bad = true; break; }
+      for (int k = 0; k < m; ++k) {
+        const int ci = io.obs_clone[o0 + k];
+        if (ci < 0 || ci >= N) { bad = true; break; }
+      }
+    }
+    if (bad) {
+      wait_flag(S.lists_done);
+      CK(cudaStreamSynchronize(stream_));
+      S.tri_early = false;
+      return ORCVIO_ERR_ARG;
+    }
+    g_hp.mark("validate");
   }
   // P: the caller's matrix is column-major and symmetric, the device copy row-major with ld
   if (io.P_in) {

@@ -65,6 +65,8 @@ struct TriArgs {
   // their own order (candidate c == feature c, slot c, forced triangulation) without any Cand record, so it can
   // start while the host still sorts the candidates and builds the tiles; status is then indexed by feature
   const int* feat_off;
+  int direct_n_clones, direct_n_obs;   // direct mode: bounds the kernel checks itself (it may start before the host
+                                       // has validated the caller's lists; a malformed feature is just invalid)
 };
 
 struct JacArgs {

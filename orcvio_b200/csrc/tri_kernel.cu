@@ -298,6 +298,14 @@ __global__ void __launch_bounds__(32 * TRI_WARPS, MINB) k_triangulate(TriArgs a)
   Cand cd;
   if (a.feat_off) {                   // direct mode: feature c of the caller's list
     const int o0 = a.feat_off[c], m = a.feat_off[c + 1] - o0;
+    // the host may still be validating these lists: a malformed feature must neither read out of bounds nor be used
+    bool bad = m < 1 || m > ORCVIO_MAX_OBS || o0 < 0 || o0 + m > a.direct_n_obs;
+    if (!bad)
+      for (int k = lane; k < m; k += 32) bad |= (unsigned)a.obs_clone[o0 + k] >= (unsigned)a.direct_n_clones;
+    if (__any_sync(0xffffffffu, bad)) {
+      if (lane == 0) a.status[c] = 0;
+      return;
+    }
     cd.filter = 0; cd.slot = c; cd.gen = c + 1; cd.flags = CAND_FORCE_TRI;
     cd.tri_off = o0; cd.tri_m = m;
     cd.cm_first_clone = a.obs_clone[o0];
