@@ -240,3 +240,26 @@ def test_augmentation_and_clone_removal_with_feature_block(N, E):
     idx = np.r_[22 + 6 * c:28 + 6 * c]
     np.testing.assert_array_equal(out, np.delete(np.delete(got, idx, axis=0), idx, axis=1))
     assert out.shape == (D, D)
+
+
+def test_hybrid_rows_against_the_committed_fixture():
+    """The same entry points against tests/golden/hybrid_rows.npz -- no oracle import on this path."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "hybrid_rows.npz"))
+    N = g["clone_R"].shape[0]
+    out = api.ekf_measurement_jacobians(g["clone_R"], g["clone_p"], g["R_b2c"], g["t_c_b"], g["anchor"], g["inv_depth"],
+                                        g["f_an"], g["positions"], g["feat_off"], g["obs_clone"], g["obs_z"])
+    for k in ("H_f", "H_a", "H_x", "H_e", "r"):
+        assert np.abs(out[k] - g[k]).max() <= 1e-12 * max(np.abs(g[k]).max(), 1.0), k
+    rows = api.ekf_feature_rows(g["clone_R"], g["clone_p"], g["R_b2c"], g["t_c_b"], g["anchor"], g["inv_depth"], g["f_an"],
+                                g["positions"], g["z_cur"], g["P"], float(g["sigma2"]), 0.95)
+    assert np.abs(rows["H"] - g["rows_H"]).max() <= 1e-12 * max(np.abs(g["rows_H"]).max(), 1.0)
+    assert np.abs(rows["r"] - g["rows_r"]).max() <= 1e-12
+    assert np.abs(rows["gamma"] - g["gamma"]).max() <= 1e-9 * np.abs(g["gamma"]).max()
+    np.testing.assert_array_equal(rows["pass"].astype(bool), g["gamma"] < float(g["chi2"]))
+    P_re, J_re = api.ekf_update_feature_cov(g["P"], g["clone_R"], g["clone_p"], g["R_b2c"], g["t_c_b"], int(g["re_fidx"]),
+                                            int(g["re_old"]), int(g["re_new"]), g["positions"][int(g["re_fidx"])],
+                                            float(g["re_rho_new"]))
+    assert np.abs(J_re - g["J_re"]).max() <= 1e-12 * max(np.abs(g["J_re"]).max(), 1.0)
+    assert np.abs(P_re - g["P_re"]).max() <= 1e-12 * np.abs(g["P_re"]).max()
+    assert N == 8

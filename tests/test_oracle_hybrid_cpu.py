@@ -220,3 +220,18 @@ def test_augmentation_with_feature_block_reduces_to_the_msckf_case():
     J[3:6, 6:9] = np.eye(3)
     ref0 = np.block([[P0, (J @ P0).T], [J @ P0, J @ P0 @ J.T]])
     np.testing.assert_allclose(out0, (ref0 + ref0.T) / 2, rtol=1e-13, atol=1e-16)
+
+
+def test_oracle_reproduces_the_committed_hybrid_fixture():
+    """tests/golden/hybrid_rows.npz (made by tests/golden/make_hybrid_golden.py) pins the hybrid restatement."""
+    import importlib.util
+    import os
+    here = os.path.dirname(os.path.abspath(__file__))
+    spec = importlib.util.spec_from_file_location("make_hybrid_golden", os.path.join(here, "golden", "make_hybrid_golden.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    now = mod.build()
+    ref = np.load(os.path.join(here, "golden", "hybrid_rows.npz"))
+    for k in ref.files:
+        np.testing.assert_allclose(np.asarray(now[k], dtype=float), np.asarray(ref[k], dtype=float), rtol=1e-12, atol=1e-14,
+                                   err_msg=k)
