@@ -201,6 +201,7 @@ __device__ void cta_cholesky(double* __restrict__ A, CholShared& cs, const doubl
           ivs[c] = (ivs[c] > 0.0) ? rs : 0.0;
           d[c] *= ivs[c];
         }
+        __syncwarp();   // lanes 8..31 hold redundant copies of the rows: their reads of the tile are done before it is rewritten
         if (lane < CHB) {
 #pragma unroll
           for (int b = 0; b < CHB; b += 2) {
