@@ -128,7 +128,6 @@ Batch::Batch(const Params& p, int n) : p_(p), B_(n) {
     CK(cudaStreamCreateWithFlags(&stream_up_, cudaStreamNonBlocking));
     CK(cudaEventCreateWithFlags(&ev_up_, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&ev_p_, cudaEventDisableTiming));
-    pack_on_worker_ = env_int("ORCVIO_PACK_WORKER", 0) != 0;
   }
   CK(cudaEventCreateWithFlags(&ev_fork_, cudaEventDisableTiming));
   CK(cudaEventCreateWithFlags(&ev_join_, cudaEventDisableTiming));
@@ -1402,8 +1401,7 @@ int Batch::snapshot_prepare(const SnapshotIO& io) {
   S.list_err = ORCVIO_OK;
   S.scan_done.store(0, std::memory_order_relaxed);
   S.lists_done.store(0, std::memory_order_relaxed);
-  const bool threaded_pack = pack_on_worker_ && io.early_prior && nF >= 512;
-  auto build_lists = [this, &S, &w, io, nF, N, threaded_pack]() {
+  auto build_lists = [this, &S, &w, io, nF, N]() {
     int* err = &S.list_err;
     int bucket[ORCVIO_MAX_OBS + 2] = {0};
     auto scan = [&]() {
@@ -1465,7 +1463,6 @@ int Batch::snapshot_prepare(const SnapshotIO& io) {
         else w.large_list.push_back(pos);
       }
       build_tiles(w, 0, 0, nF);
-      if (threaded_pack) stage_pack(w);
     }
     S.lists_done.store(1, std::memory_order_release);
   };
@@ -1715,8 +1712,7 @@ int Batch::snapshot_prepare(const SnapshotIO& io) {
   // (packing the blob on the helper thread as well was measured: the H2D copy of lines last written by
   // another core delays the GPU by ~60 us -- the copy into the pinned blob stays on this thread)
   upload_on_side_stream_ = S.tri_early;
-  if (threaded_pack) stage_upload(w);
-  else stage_phase(w);
+  stage_phase(w);
   upload_on_side_stream_ = false;
   g_hp.mark("stage_blob");
   if (skip_tri_ && nC > 0) {

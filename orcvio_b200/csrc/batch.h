@@ -234,7 +234,7 @@ class Batch {
   bool tri_done_early_ = false, jac_done_early_ = false;
   cudaStream_t stream_up_ = nullptr;   // side stream of the work-list upload when kernels are already queued
   cudaEvent_t ev_up_ = nullptr, ev_p_ = nullptr;
-  bool upload_on_side_stream_ = false, pack_on_worker_ = false;
+  bool upload_on_side_stream_ = false;
   Blob blob_early2_;                   // per-feature offsets / size-class lists of the early Jacobian pass
   double* dGammaF_ = nullptr;          // gamma by feature slot (early direct-mode pass)
   const int *dir_feat_off_ = nullptr, *dir_rowoff_ = nullptr, *dir_hblkoff_ = nullptr, *dir_sblk_ = nullptr,
