@@ -84,7 +84,7 @@ __global__ void __launch_bounds__(512) k_latency(double* out, double seed) {
 // Stand-alone run of the one-CTA Cholesky (chol.cuh) on a caller-supplied SPD matrix: the unit test
 // and the per-phase clock profile of the routine both factorisation kernels are built on.
 namespace ob {
-template <bool PROF, int LAYOUT = 0>
+template <bool PROF>
 __global__ void __launch_bounds__(CHOL_THREADS) k_chol_probe(const double* Ain, const double* Xin, int m, int nx,
                                                              double* Lout, double* Xout, long long* prof) {
   extern __shared__ double sm[];
@@ -101,7 +101,7 @@ __global__ void __launch_bounds__(CHOL_THREADS) k_chol_probe(const double* Ain, 
     const int q = e / m, k = e - q * m;
     A[chol_at(m + q, k, Tm)] = Xin[e];
   }
-  cta_cholesky<PROF, LAYOUT>(A, cs, nullptr, m, nx, prof);
+  cta_cholesky<PROF>(A, cs, nullptr, m, nx, prof);
   chol_for_rows(A, m, nx, 0, [&](int i, int k, double l) {
     if (i < m) Lout[(size_t)i * m + k] = l;
     else Xout[(size_t)(i - m) * m + k] = l;
@@ -127,9 +127,8 @@ extern "C" int orcvio_chol_probe(int m, int nx, const double* A, const double* X
   cudaMemset(dL, 0, nA * 8);
   cudaMemset(dprof, 0, 64 * 8 * sizeof(long long));
   const size_t smem = chol_smem_doubles(m, nx) * sizeof(double);
-  const int layout = env_int("ORCVIO_CHOL_LAYOUT", 0);
-  auto kp = layout ? k_chol_probe<true, 1> : k_chol_probe<true, 0>;
-  auto kf = layout ? k_chol_probe<false, 1> : k_chol_probe<false, 0>;
+  auto kp = k_chol_probe<true>;
+  auto kf = k_chol_probe<false>;
   cudaFuncSetAttribute(kp, cudaFuncAttributeMaxDynamicSharedMemorySize, 193 * 1024);
   cudaFuncSetAttribute(kf, cudaFuncAttributeMaxDynamicSharedMemorySize, 193 * 1024);
   kp<<<1, CHOL_THREADS, smem>>>(dA, dX, m, nx, dL, dXs, dprof);

@@ -20,9 +20,10 @@ for (m, nx) in [(202, 0), (180, 17), (64, 0)]:
     npan = (m + 7) // 8
     p = prof[:npan].astype(np.int64)
     t0 = p[0, 0]
-    print("  panel: start  upd  factor  solve  trail_done  sync   (cycles; deltas)")
+    print("  step: chain [factor  wait_tile  solve+diag_upd  step]   bulk warp 0 [seen_block  solve  col_q+1  bulk_q+2]   (cycles)")
     for k in list(range(0, min(npan, 4))) + list(range(npan // 2, npan // 2 + 2)) + [npan - 2, npan - 1]:
         r = p[k]
-        print(f"  {k:3d}: start {r[0]-t0:7d} upd {r[1]-r[0]:5d} factor {r[2]-r[1]:5d} solve {r[3]-r[2]:5d} "
-              f"trail_done {(r[4]-r[0]) if r[4] else 0:6d} total {r[5]-r[0]:6d}")
-    print(f"  total cycles {p[npan-1,5]-t0}")
+        nxt = p[k + 1, 0] if k + 1 < npan else r[3]
+        print(f"  {k:3d}: start {r[0]-t0:7d} | factor {r[1]-r[0]:5d} wait {max(r[2]-r[1],0):5d} solve_upd {r[3]-max(r[2],r[1]):5d} step {nxt-r[0]:5d}"
+              f" | seen {r[4]-r[1]:5d} solve {r[5]-r[4]:5d} col {r[6]-r[5]:5d} bulk {r[7]-r[6]:5d}")
+    print(f"  total cycles {max(p[npan-1,3], p[npan-1,7])-t0}")
