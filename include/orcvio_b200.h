@@ -311,6 +311,9 @@ const char* orcvio_version(void);
 int orcvio_fp64_peak(double* dfma_tflops, double* dmma_tflops);
 /* dependent-chain latencies in cycles: DFMA, sqrt, divide, rsqrt, shared load, __syncthreads(512), shuffle */
 int orcvio_latency_probe(double* cycles7);
+/* single-warp dependent latencies (cycles): DFMA, DMMA dependent, DMMA with 2 / 4 / 8 independent accumulators
+   (per MMA), 64-bit shuffle + add, 16-byte shared load, fence.acq_rel.cta after a shared store, rcp.approx.f64, 0 */
+int orcvio_latency_probe1(double* cycles10);
 /* test / profiling hook: the one-CTA Cholesky both factorisation kernels are built on (csrc/chol.cuh).
  * A: m x m SPD row-major, X: nx x m carried rows; L: m x m lower factor, Xs = X C^-T; prof: 64 x 8
  * clock64() stamps per 8-column panel (may be NULL); us: mean kernel time over `reps` launches. */

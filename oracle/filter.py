@@ -6,9 +6,12 @@ H P H^T gate, Householder QR compression, P <- (I-KH)P + symmetrise).  Citations
 are src/orcvio.cpp:line unless stated otherwise.
 
 Scope of this restatement: LEG_DIM = 22 (calib_imu_instrinsic = 0, as in every shipped
-config), closed-form covariance propagation, pure-MSCKF feature handling
-(max_features_in_one_grid = 0) plus both ZUPT variants.  The hybrid EKF-SLAM branch
- raises NotImplementedError.
+config), closed-form covariance propagation, both ZUPT variants, and both feature modes:
+pure MSCKF (max_features_in_one_grid = 0) and the hybrid MSCKF / EKF-SLAM mode of
+euroc.yaml / kitti_odom.yaml (max_features_in_one_grid > 0, feature_idp_dim = 1,
+use_schmidt = 0: grid map, initializeInvParamPosition, featureJacobian_ekf[_new],
+new-feature sparsification, measurementUpdate_hybrid with delayed initialisation,
+re-anchoring, rmLostFeaturesCov).  The arithmetic of the hybrid rows lives in hybrid.py.
 
 parity: the reference cannot be built in this image (needs Eigen, SuiteSparse, Boost,
 Sophus, OpenCV C++, Ceres -- none present), so this file is pinned only where the
@@ -24,6 +27,7 @@ import numpy as np
 
 from . import mathutils as mu
 from . import feature as feat
+from . import hybrid as hyb
 from .config import load_params
 
 
@@ -41,6 +45,8 @@ class Feature:
         self.ekf_feature = False
         self.totalObsNum = 0
         self.tri_log = None
+        self.invDepth = 0.0              # 1-D inverse depth in the anchor camera (feature.hpp:243)
+        self.obs_anchor = np.array([0.0, 0.0, 1.0])   # bearing (x, y, 1) in the anchor camera (:246)
 
     def obs_ids(self):
         return sorted(self.observations.keys())
@@ -135,8 +141,12 @@ class OracleVIO:
         self.dcampose_dimupose_fixed_flag = False
         self.dcampose_dimupose_mat = np.eye(6)
         self.pose_log = []             # (t - take_off, p, q[x,y,z,w])  -- state_est_geo_feat.txt
+        self.grid_map = {}             # code -> [feature ids]  (std::map<int, vector>: any code is a valid key)
         if p.max_features * p.grid_rows * p.grid_cols != 0:
-            raise NotImplementedError("hybrid EKF-SLAM features (max_features_in_one_grid>0) not restated")
+            if p.feature_idp_dim != 1:
+                raise NotImplementedError("feature_idp_dim = 3 not restated (every shipped yaml uses 1)")
+            if p.use_schmidt:
+                raise NotImplementedError("use_schmidt = 1 not restated (every shipped yaml uses 0)")
         return True
 
     @staticmethod
@@ -388,7 +398,7 @@ class OracleVIO:
         return Phi
 
     def stateAugmentation(self):
-        """:930-1013 (no EKF-feature / nuisance blocks in this restatement)."""
+        """:930-1013 (no nuisance blocks: use_schmidt = 0)."""
         s = self.imu_state
         self.cur_window_timestamps.append(s.time)
         c = Clone(s.id)
@@ -402,20 +412,10 @@ class OracleVIO:
         R_w2c = s.R_imu_cam0 @ R_b2w.T
         c.orientation_cam = R_w2c.T.copy()
         c.position_cam = s.position + R_b2w @ s.t_cam0_imu
+        n_before = len(self.clones)
         self.clones[s.id] = c
-        P = self.state_cov
-        n = P.shape[0]
-        J = np.zeros((6, n))
-        J[0:3, 0:3] = np.eye(3)
-        J[3:6, 6:9] = np.eye(3)
-        P12 = J @ P
-        P11 = P12 @ J.T
-        Pn = np.zeros((n + 6, n + 6))
-        Pn[:n, :n] = P
-        Pn[n:, n:] = P11
-        Pn[n:, :n] = P12
-        Pn[:n, n:] = P12.T
-        self.state_cov = (Pn + Pn.T) / 2.0
+        # :963-1010: the new 6 x 6 block goes in front of the EKF-feature block
+        self.state_cov = hyb.state_augmentation_cov(self.state_cov, n_before)
 
     # ------------------------------------------------------------------ bookkeeping
     def addFeatureObservations(self, feats):
@@ -488,6 +488,98 @@ class OracleVIO:
             ft.position = np.array(res.position)
             ft.id_anchor = ids[-1]
         return res.valid
+
+    def _initialize_inv_param(self, ft, exclude_id):
+        """Feature::initializeInvParamPosition, feature.hpp:502-554: the same triangulation as
+        initializePosition (observations of `exclude_id` skipped), keeping the 1-D inverse-depth
+        parametrisation in the anchor camera = the last camera used."""
+        Rs, ts, zs, ids = self._cam_poses(ft, exclude_id)
+        res = feat.triangulate(Rs, ts, zs, ft.is_initialized, [float(x) for x in ft.position], self.opt)
+        ft.tri_log = res
+        if res.valid:
+            ft.ekf_feature = True
+            ft.is_initialized = True
+            ft.position = np.array(res.position)
+            ft.id_anchor = ids[-1]
+            fp = res.final_position
+            ft.invDepth = 1 / fp[2]
+            ft.obs_anchor = np.array([fp[0] * ft.invDepth, fp[1] * ft.invDepth, 1.0])
+        return res.valid
+
+    def _grid_code(self, ft):
+        """:2286-2289 / :3841-3845 (int casts truncate toward zero)."""
+        p = self.p
+        xy = ft.observations[self.imu_state.id]
+        row = int((xy[1] - p.y_min) / p.grid_height)
+        col = int((xy[0] - p.x_min) / p.grid_width)
+        return row * p.grid_cols + col
+
+    def updateGridMap(self):
+        """:3831-3850."""
+        p = self.p
+        if p.grid_rows * p.grid_cols == 0:
+            return
+        self.grid_map = {i: [] for i in range(p.grid_rows * p.grid_cols)}
+        for fid in self.feature_states:
+            self.grid_map.setdefault(self._grid_code(self.map_server[fid]), []).append(fid)
+
+    def rmLostFeaturesCov(self, lost_ids):
+        """:3776-3828 (use_schmidt = 0)."""
+        for fid in lost_ids:
+            seq = self.feature_states.index(fid)
+            a = self.LEG_DIM + 6 * len(self.clones) + seq
+            keep = [i for i in range(self.state_cov.shape[0]) if i != a]
+            self.state_cov = self.state_cov[np.ix_(keep, keep)]
+            self.feature_states.pop(seq)
+            del self.map_server[fid]
+
+    def _drop_all_feature_states(self):
+        """checkZUPTFeat :3104-3115 / checkZUPTIMU :3304-3315: a stationary frame removes every EKF feature."""
+        if self.feature_states:
+            E = len(self.feature_states)
+            n = self.state_cov.shape[0] - E
+            self.state_cov = self.state_cov[:n, :n].copy()
+            for fid in self.feature_states:
+                ft = self.map_server[fid]
+                ft.is_initialized = False
+                ft.ekf_feature = False
+                ft.in_state = False
+            self.feature_states = []
+
+    def _update_feature_states(self, delta_x):
+        """The 1-D inverse-depth branch of :1700-1737 / :1843-1882 / :3391-3430: invDepth += its component of
+        delta_x, world position recomputed from the (already updated) anchor clone."""
+        base = self.LEG_DIM + 6 * len(self.clones)
+        for i, fid in enumerate(self.feature_states):
+            ft = self.map_server[fid]
+            c = self.clones[ft.id_anchor]
+            ft.invDepth = ft.invDepth + delta_x[base + i]
+            p_c = np.array([ft.obs_anchor[0] / ft.invDepth, ft.obs_anchor[1] / ft.invDepth, 1 / ft.invDepth])
+            ft.position = c.orientation_cam @ p_c + c.position_cam
+
+    def _ekf_clone_arrays(self):
+        ids = sorted(self.clones.keys())
+        return ids, [self.clones[i].orientation for i in ids], [self.clones[i].position for i in ids]
+
+    def featureJacobian_ekf(self, ft):
+        """:1575-1651 (1-D inverse depth, anchor in the window)."""
+        ids, cR, cp = self._ekf_clone_arrays()
+        s = self.imu_state
+        cur = s.id
+        H, r = hyb.feature_jacobian_ekf(cR, cp, s.R_imu_cam0, s.t_cam0_imu, ids.index(cur), ids.index(ft.id_anchor),
+                                        self.feature_states.index(ft.id), self.state_cov.shape[1] - self.LEG_DIM - 6 * len(ids),
+                                        ft.obs_anchor, ft.invDepth, ft.position, ft.observations[cur])
+        return H, r
+
+    def featureJacobian_ekf_new(self, ft, n_cols):
+        """:1481-1572: rows of every observing clone but the anchor; H_f at LEG + 6N + index in feature_states."""
+        ids, cR, cp = self._ekf_clone_arrays()
+        s = self.imu_state
+        sids = [i for i in ft.obs_ids() if i in self.clones]
+        col = self.LEG_DIM + 6 * len(ids) + self.feature_states.index(ft.id)
+        return hyb.feature_jacobian_ekf_new(cR, cp, s.R_imu_cam0, s.t_cam0_imu, [ids.index(i) for i in sids],
+                                            [ft.observations[i] for i in sids], ids.index(ft.id_anchor), col, n_cols,
+                                            ft.obs_anchor, ft.invDepth, ft.position)
 
     # ------------------------------------------------------------------ stage 2
     def measurementJacobian_msckf(self, state_id, ft):
@@ -590,7 +682,7 @@ class OracleVIO:
         return H, r
 
     def measurementUpdate_msckf(self, H, r):
-        """:1654-1763 (no augmented feature states / Schmidt in this restatement)."""
+        """:1654-1763 (use_schmidt = 0)."""
         if H.shape[0] == 0 or r.shape[0] == 0:
             return
         keep = self.LEG_DIM + 6 * len(self.clones)
@@ -601,29 +693,56 @@ class OracleVIO:
         K = K_T.T
         delta_x = K @ r_thin
         applied = self.incrementState_IMUCam(delta_x)
+        self._update_feature_states(delta_x)
         I_KH = np.eye(K.shape[0], H_thin.shape[1]) - K @ H_thin
         P = I_KH @ P
         self.state_cov = (P + P.T) / 2.0
         self.last_update_time = self.imu_state.time
         self.log.append(dict(kind="update", rows=int(H.shape[0]), delta_x=delta_x.copy(), applied=applied))
 
-    def measurementUpdate_hybrid(self, H_msckf, r_msckf):
-        """:1766-1950 restricted to empty EKF parts (pure MSCKF): H_o = H_msckf,
-        no further compression; same algebra as measurementUpdate_msckf."""
-        if r_msckf.shape[0] == 0:
+    def measurementUpdate_hybrid(self, H_ekf_new, r_ekf_new, H_ekf, r_ekf, H_msckf, r_msckf):
+        """:1766-1950 (feature_idp_dim = 1, use_schmidt = 0).  H_o = [H_msckf; H_ekf; top rows of H_ekf_new] is
+        NOT compressed again here; the last sz_new rows of the sparsified H_ekf_new are (H_1 | H_2), r_1."""
+        D = self.state_cov.shape[1]
+        sz_new = H_ekf_new.shape[1] - D
+        sz_r = r_ekf_new.shape[0] + r_ekf.shape[0] + r_msckf.shape[0]
+        if sz_r == 0:
             return
+        n_top = H_ekf_new.shape[0] - sz_new
+        H_o = np.concatenate([H_msckf, H_ekf, H_ekf_new[:n_top, :D]], axis=0)
+        r_o = np.concatenate([r_msckf, r_ekf, r_ekf_new[:n_top]])
+        H_1 = H_ekf_new[n_top:, :D]
+        H_2 = H_ekf_new[n_top:, D:]
+        r_1 = r_ekf_new[n_top:]
         P = self.state_cov
-        H_o = H_msckf
         S = H_o @ P @ H_o.T + self.p.feature_observation_noise * np.eye(H_o.shape[0])
         K_T = np.linalg.solve(S, H_o @ P)
         K = K_T.T
-        delta_x = K @ r_msckf
+        dx_leg = K @ r_o
+        if sz_new > 0:
+            HH = np.linalg.solve(H_2, H_1)
+            dx_new = -HH @ dx_leg + np.linalg.solve(H_2, r_1)
+            delta_x = np.concatenate([dx_leg, dx_new])
+        else:
+            delta_x = dx_leg
         applied = self.incrementState_IMUCam(delta_x)
+        self._update_feature_states(delta_x)
         I_KH = np.eye(K.shape[0], H_o.shape[1]) - K @ H_o
         P = I_KH @ P
-        self.state_cov = (P + P.T) / 2.0
+        P = (P + P.T) / 2.0
+        if sz_new > 0:
+            nHHP = -HH @ P
+            P22 = -nHHP @ HH.T + self.p.feature_observation_noise * np.linalg.inv(H_2.T @ H_2)
+            Pn = np.zeros((D + sz_new, D + sz_new))
+            Pn[:D, :D] = P
+            Pn[D:, :D] = nHHP
+            Pn[:D, D:] = nHHP.T
+            Pn[D:, D:] = P22
+            P = (Pn + Pn.T) / 2.0
+        self.state_cov = P
         self.last_update_time = self.imu_state.time
-        self.log.append(dict(kind="update", rows=int(H_o.shape[0]), delta_x=delta_x.copy(), applied=applied))
+        self.log.append(dict(kind="update", rows=int(H_o.shape[0]), delta_x=delta_x.copy(), applied=applied,
+                             sz_new=int(sz_new)))
 
     def incrementState_IMUCam(self, delta_x):
         """:4468-4567.  Returns False when the large-update guard discarded the step."""
@@ -657,13 +776,28 @@ class OracleVIO:
 
     # ------------------------------------------------------------------ orchestrators
     def removeLostFeatures(self):
-        """:2196-2579, pure-MSCKF branch."""
+        """:2196-2579 (pure-MSCKF and hybrid branches; use_schmidt = 0, feature_idp_dim = 1)."""
         p = self.p
         cur = self.imu_state.id
         rows = 0
+        rows_new = 0
         invalid, msckf_ids, lost_ids = [], [], []
+        ekf_new_ids, ekf_lost_ids, ekf_ids = [], [], []
+        # features of the state: tracked now -> a 2-row update, lost -> dropped from the state (:2210-2232)
         for fid in sorted(self.map_server.keys()):
             ft = self.map_server[fid]
+            if ft.in_state:
+                if cur in ft.observations:
+                    ekf_ids.append(fid)
+                else:
+                    ekf_lost_ids.append(fid)
+        self.rmLostFeaturesCov(ekf_lost_ids)
+        self.updateGridMap()
+        cap = p.max_features * p.grid_rows * p.grid_cols
+        for fid in sorted(self.map_server.keys()):
+            ft = self.map_server[fid]
+            if ft.in_state:
+                continue
             tracked_now = cur in ft.observations
             if not tracked_now:
                 if len(ft.observations) < p.least_Obs_Num:
@@ -682,23 +816,92 @@ class OracleVIO:
             else:
                 if not (len(ft.observations) >= p.max_track_len):
                     continue
-                if not ft.is_initialized:
-                    if self.checkMotion(ft, tracked_now):
-                        self._initialize(ft, cur)
-                if not ft.is_initialized:
-                    continue
-                rows += 2 * len(ft.observations) - 3
-                msckf_ids.append(fid)
-                lost_ids.append(fid)
+                # :2283-2323: EKF-SLAM feature if its grid cell (and the state) has room, else MSCKF feature
+                code = self._grid_code(ft)
+                cell = self.grid_map.setdefault(code, [])
+                if (len(cell) < p.max_features and self.imu_state.time - self.last_ZUPT_time > 5
+                        and (len(self.feature_states) + len(ekf_new_ids)) < cap):
+                    if not ft.ekf_feature:
+                        ft.is_initialized = False
+                        if self.checkMotion(ft, tracked_now):
+                            self._initialize_inv_param(ft, cur)
+                    if not ft.is_initialized:
+                        continue
+                    rows_new += 2 * (len(ft.observations) - 1)
+                    ekf_new_ids.append(fid)
+                    cell.append(fid)
+                else:
+                    if not ft.is_initialized:
+                        if self.checkMotion(ft, tracked_now):
+                            self._initialize(ft, cur)
+                    if not ft.is_initialized:
+                        continue
+                    rows += 2 * len(ft.observations) - 3
+                    msckf_ids.append(fid)
+                    lost_ids.append(fid)
         for fid in invalid:
             del self.map_server[fid]
         frame_log = dict(kind="removeLostFeatures", state_id=cur, invalid=list(invalid),
-                         candidates=list(msckf_ids), gate={}, zupt=self.if_ZUPT)
+                         candidates=list(msckf_ids), gate={}, zupt=self.if_ZUPT,
+                         ekf_lost=list(ekf_lost_ids), ekf=list(ekf_ids), ekf_new=list(ekf_new_ids),
+                         gate_ekf={}, gate_ekf_new={})
         self.log.append(frame_log)
-        if not msckf_ids:
+        if not msckf_ids and not ekf_new_ids and not ekf_ids:
             return
         if not self.if_ZUPT:
-            cols = self.LEG_DIM + 6 * len(self.clones)
+            L = self.LEG_DIM
+            D = self.state_cov.shape[1]
+            for fid in ekf_new_ids:
+                self.map_server[fid].in_state = True
+                self.feature_states.append(fid)
+            # ---- new EKF-SLAM features (:2343-2446)
+            blocks, invalid_new = [], []
+            for fid in list(ekf_new_ids):
+                ft = self.map_server[fid]
+                sids = ft.obs_ids()
+                H_m, r_m = self.featureJacobian_msckf(ft, sids)        # gate with the MSCKF rows (:2365-2370)
+                g = {}
+                ok = self.gatingTestFeature(H_m, r_m, 2 * len(sids) - 3, g)
+                g["pass"] = ok
+                g["position"] = ft.position.copy()
+                g["inv_depth"] = ft.invDepth
+                frame_log["gate_ekf_new"][fid] = g
+                if not ok:
+                    invalid_new.append(fid)
+            for fid in invalid_new:          # :2384-2411
+                self.map_server[fid].in_state = False
+                self.feature_states.remove(fid)
+                ekf_new_ids.remove(fid)
+            n_new = len(ekf_new_ids)
+            H_ekf_new = np.zeros((0, D + n_new))
+            r_ekf_new = np.zeros(0)
+            if n_new > 0:
+                # the columns of the surviving new features are contiguous behind the old state (the reference
+                # builds the rows first and deletes the columns of the rejected ones afterwards: same matrix)
+                for fid in ekf_new_ids:
+                    H_j, r_j = self.featureJacobian_ekf_new(self.map_server[fid], D + n_new)
+                    blocks.append((H_j, r_j))
+                H_ekf_new = np.concatenate([b[0] for b in blocks], axis=0)
+                r_ekf_new = np.concatenate([b[1] for b in blocks])
+                H_ekf_new, r_ekf_new = hyb.sparsify_new_features(H_ekf_new, r_ekf_new, n_new)
+            # ---- features of the state (:2449-2495)
+            He, re_ = [], []
+            for fid in ekf_ids:
+                ft = self.map_server[fid]
+                H_j, r_j = self.featureJacobian_ekf(ft)
+                g = {}
+                ok = self.gatingTestFeature(H_j, r_j, 2, g)
+                g["pass"] = ok
+                frame_log["gate_ekf"][fid] = g
+                if ok:
+                    He.append(H_j)
+                    re_.append(r_j)
+            H_ekf = np.concatenate(He, axis=0) if He else np.zeros((0, D))
+            r_ekf = np.concatenate(re_) if re_ else np.zeros(0)
+            if not (H_ekf.shape[0] == 0 or H_ekf.shape[0] <= H_ekf.shape[1]):
+                H_ekf, r_ekf = self._compress(H_ekf, r_ekf, D)
+            # ---- MSCKF features (:2498-2560)
+            cols = L + 6 * len(self.clones)
             H = np.zeros((rows, cols))
             r = np.zeros(rows)
             k = 0
@@ -719,9 +922,9 @@ class OracleVIO:
             r = r[:k]
             if not (H.shape[0] == 0 or H.shape[0] <= H.shape[1]):
                 H, r = self._compress(H, r, cols)
-            Hfull = np.zeros((H.shape[0], self.state_cov.shape[1]))
+            Hfull = np.zeros((H.shape[0], D))
             Hfull[:, :H.shape[1]] = H
-            self.measurementUpdate_hybrid(Hfull, r)
+            self.measurementUpdate_hybrid(H_ekf_new, r_ekf_new, H_ekf, r_ekf, Hfull, r)
         else:
             for fid in msckf_ids:
                 self.map_server[fid].is_initialized = False
@@ -752,7 +955,7 @@ class OracleVIO:
         return sorted(rm)
 
     def pruneImuStateBuffer(self):
-        """:2629-2959, pure-MSCKF branch."""
+        """:2629-2959 (use_schmidt = 0, feature_idp_dim = 1)."""
         p = self.p
         cur = self.imu_state.id
         if not self.if_ZUPT:
@@ -763,13 +966,34 @@ class OracleVIO:
             rm_ids = [cur - 1]
         rows = 0
         used = []
+        reanchored = {}
         for fid in sorted(self.map_server.keys()):
             ft = self.map_server[fid]
             involved = [s for s in rm_ids if s in ft.observations]
             if not involved:
                 continue
+            if ft.in_state:
+                # :2665-2722: a feature of the state whose anchor leaves the window moves to a new anchor
+                if ft.id_anchor in involved:
+                    new_id = self.getNewAnchorId(ft, involved)
+                    c = self.clones[new_id]
+                    p_new = np.linalg.solve(c.orientation_cam, ft.position - c.position_cam)
+                    ft.invDepth = 1 / p_new[2]
+                    ft.obs_anchor = np.array([p_new[0] / p_new[2], p_new[1] / p_new[2], ft.obs_anchor[2]])
+                    self.updateFeatureCov_1didp(ft, ft.id_anchor, new_id)
+                    reanchored[fid] = (ft.id_anchor, new_id)
+                    ft.id_anchor = new_id
+                continue
             if ft.is_initialized and ft.id_anchor in involved:
-                ft.id_anchor = self._get_new_anchor(ft, involved)
+                # :2724-2773: initialised feature outside the state: anchor moved, observation NOT corrected
+                new_id = self.getNewAnchorId(ft, involved)
+                c = self.clones[new_id]
+                p_new = np.linalg.solve(c.orientation_cam, ft.position - c.position_cam)
+                ft.invDepth = 1 / p_new[2]
+                if new_id not in ft.observations:
+                    ft.observations[new_id] = np.zeros(2)       # std::map::operator[] default-constructs (:2763)
+                ft.obs_anchor = np.array([ft.observations[new_id][0], ft.observations[new_id][1], ft.obs_anchor[2]])
+                ft.id_anchor = new_id
             if (not self.if_ZUPT) and (not ft.ekf_feature) and len(involved) > 1:
                 tracked = cur in ft.observations
                 if not ft.is_initialized:
@@ -779,7 +1003,8 @@ class OracleVIO:
                         continue
                 used.append(fid)
                 rows += 2 * len(involved) - 3
-        frame_log = dict(kind="prune", state_id=cur, rm_ids=list(rm_ids), candidates=list(used), gate={})
+        frame_log = dict(kind="prune", state_id=cur, rm_ids=list(rm_ids), candidates=list(used), gate={},
+                         reanchored=reanchored)
         self.log.append(frame_log)
         if (not self.if_ZUPT) and used:
             D = self.state_cov.shape[1]
@@ -818,14 +1043,34 @@ class OracleVIO:
             self.cur_window_timestamps = [t for t in self.cur_window_timestamps if t != t_erase]
             del self.clones[sid]
 
-    def _get_new_anchor(self, ft, involved):
-        """getNewAnchorId :3892-3950 is only consulted for initialised non-state features
-        (:2724-2773); the anchor of an MSCKF feature is never read again by the MSCKF
-        path, so only the id bookkeeping is kept: newest observing clone not removed."""
-        for sid in reversed(ft.obs_ids()):
-            if sid not in involved and sid in self.clones:
-                return sid
-        return ft.id_anchor
+    def getNewAnchorId(self, ft, rm_ids):
+        """:3892-3950: among the clones observing the feature (the two newest excluded, the removed ones
+        excluded) the one whose stored observation is closest to the reprojection of feature.position;
+        the newest clone if there is none."""
+        ids = sorted(self.clones.keys())
+        size = len(ids)
+        if size <= 2:
+            return ids[-1]
+        best, min_dis = None, 99999.0
+        for sid in ids[:size - 2]:
+            if sid not in ft.observations or sid in rm_ids:
+                continue
+            c = self.clones[sid]
+            p_new = np.linalg.solve(c.orientation_cam, ft.position - c.position_cam)
+            z = ft.observations[sid]
+            dis = math.sqrt((p_new[0] / p_new[2] - z[0]) ** 2 + (p_new[1] / p_new[2] - z[1]) ** 2)
+            if min_dis > dis:
+                min_dis = dis
+                best = sid
+        return best if best is not None else ids[-1]
+
+    def updateFeatureCov_1didp(self, ft, old_id, new_id):
+        """:3611-3773; ft.invDepth already holds the inverse depth in the new anchor."""
+        ids, cR, cp = self._ekf_clone_arrays()
+        s = self.imu_state
+        self.state_cov, _ = hyb.update_feature_cov_1didp(self.state_cov, len(ids), self.feature_states.index(ft.id),
+                                                         ids.index(old_id), ids.index(new_id), cR, cp, s.R_imu_cam0,
+                                                         s.t_cam0_imu, ft.position, ft.invDepth)
 
     # ------------------------------------------------------------------ ZUPT (Z1)
     def checkZUPTFeat(self):
@@ -837,6 +1082,7 @@ class OracleVIO:
         maxDis = d[-9]
         self.coarse_feature_dis = []
         if maxDis < self.p.zupt_max_feature_dis:
+            self._drop_all_feature_states()
             self.measurementUpdate_ZUPT_vpq()
             return True
         return False
@@ -892,6 +1138,7 @@ class OracleVIO:
         self.zupt_info = (chi2, float(np.linalg.norm(self.imu_state.velocity)))
         if chi2 > chk or np.linalg.norm(self.imu_state.velocity) > 0.25:
             return False
+        self._drop_all_feature_states()
         self.measurementUpdate_ZUPT_vpq()
         return True
 

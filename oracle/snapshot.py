@@ -66,6 +66,8 @@ def oracle_from_snapshot(snap, flags, sigma2, chi2_p=0.95, tri=None):
                         t_cam0_imu=t_c_b.copy())
     vio.imu_state = s
     vio.map_server = {}
+    vio.feature_states = []
+    vio.grid_map = {}
     fo = snap["feat_off"]
     for f in range(len(fo) - 1):
         ft = Feature(f)
@@ -110,7 +112,10 @@ def oracle_snapshot_update(snap, flags, sigma2, chi2_p=0.95, tri=None):
         out["r"] = r
         if H.shape[0] > H.shape[1]:
             H, r = vio._compress(H, r, cols)
-        vio.measurementUpdate_hybrid(H, r)
+        Dn = vio.state_cov.shape[1]
+        Hf = np.zeros((H.shape[0], Dn))
+        Hf[:, :H.shape[1]] = H
+        vio.measurementUpdate_hybrid(np.zeros((0, Dn)), np.zeros(0), np.zeros((0, Dn)), np.zeros(0), Hf, r)
         out["delta_x"] = vio.log[-1]["delta_x"]
         out["applied"] = vio.log[-1]["applied"]
     out["P"] = vio.state_cov

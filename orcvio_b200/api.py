@@ -602,6 +602,19 @@ def latency_probe():
     return dict(zip(["dfma", "sqrt", "div", "rsqrt", "lds", "syncthreads512", "shfl64"], out.tolist()))
 
 
+def latency_probe1():
+    """Single-warp dependent latencies (cycles)."""
+    out = np.zeros(10)
+    L = lib()
+    L.orcvio_latency_probe1.argtypes = [C.POINTER(C.c_double)]
+    L.orcvio_latency_probe1.restype = C.c_int
+    rc = L.orcvio_latency_probe1(_dp(out))
+    if rc != 0:
+        raise RuntimeError(f"orcvio_latency_probe1 failed: {rc}")
+    return dict(zip(["dfma", "dmma_dep", "dmma_x2", "dmma_x4", "dmma_x8", "shfl64", "lds128", "fence_cta", "rcp_approx"],
+                    out.tolist()))
+
+
 def chol_probe(A, X=None, reps=10):
     """Runs csrc/chol.cuh on one SPD matrix: returns (L, X C^-T, per-panel clock stamps, mean us)."""
     A = np.ascontiguousarray(A, dtype=np.float64)

@@ -27,6 +27,16 @@
 //     accumulator per 8 columns).  The hand-offs between the three roles are step counters in shared memory;
 //   * the factor is left in the tiles; callers copy what they need out with chol_for_rows().
 //
+// Measured on B200 (scripts/chol_probe.py, api.latency_probe1): a dependent mma.m8n8k4.f64 costs 26 cycles (16 at
+// the issue limit), a 16-byte shared load 48 cycles and FOUR passes of the 128 B / cycle shared-memory pipe even
+// when every lane reads the same address -- the worker phases are bound by that pipe (the broadcast loads of the
+// diagonal block in the row solve, one operand chunk per MMA pair in the bulk update), not by the tensor pipe.
+// Tried and rejected: a 16-row factor in the chain warp (the tile below has to be final a whole factorisation
+// earlier: the chain then waits for the workers), FMA instead of MMA for the single-tile updates of the chain and
+// frontier warps (more shared-memory passes, slower), 12 accumulators per tile (register spills), an XOR swizzle
+// of the tile rows (conflict-free thread-per-row access, but the row solve is bound by the broadcast loads:
+// no gain), dropping the fences between the roles (wrong results: they are needed).
+//
 // `tol != nullptr`: pivots <= tol[k] are exact zeros (semidefinite prior: the IMU pose duplicates
 // the newest clone after augmentation and rows 15..21 are exactly zero) -> zero column.
 #pragma once

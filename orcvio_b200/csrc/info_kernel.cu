@@ -100,6 +100,12 @@ __global__ void __launch_bounds__(AF_THREADS, 3) k_aform(QrArgs a, const double*
   const int tid = threadIdx.x, nt = blockDim.x;
   const int warp = tid >> 5, lane = tid & 31, nw = nt >> 5;
   const int nc = tl.cand_end - tl.cand_begin;      // host guarantees nc <= 256
+  pdl_launch_dependents();
+  const int rows_ub = tl.rows;                     // <= AFORM_TILE_ROWS
+  const int rows8 = (rows_ub + 7) & ~7;
+  for (int e = tid; e < rows8 * Wp; e += nt) smem[e] = 0.0;
+  if (tid < AFORM_TILE_ROWS) res[tid] = 0.0;
+  pdl_wait();                                      // above: host-built tile records; below: gate results, blocks, factor
   // ---- row bases of the gated candidates (block scan)
   int total = 0;
   for (int base = 0; base < nc; base += nt) {
@@ -130,10 +136,6 @@ __global__ void __launch_bounds__(AF_THREADS, 3) k_aform(QrArgs a, const double*
   }
   const int m = total;
   if (tid == 0) tile_rows[blockIdx.x] = m;
-  const int rows_ub = tl.rows;                     // <= AFORM_TILE_ROWS
-  const int rows8 = (rows_ub + 7) & ~7;
-  for (int e = tid; e < rows8 * Wp; e += nt) smem[e] = 0.0;
-  if (tid < AFORM_TILE_ROWS) res[tid] = 0.0;
   __syncthreads();
   for (int q = warp; q < nc; q += nw) {
     if (rowbase[q] < 0) continue;
@@ -271,6 +273,8 @@ __global__ void __launch_bounds__(256) k_syrk(UpdArgs a, const double* __restric
   const FilterWork fw = a.fw[fi];
   const int tid = threadIdx.x;
   const int unit = blockIdx.x;
+  pdl_launch_dependents();
+  pdl_wait();                                            // tile_rows and A are the previous kernel's output
   if (unit == 0 && tid == 0) {                           // gated rows of this filter (k_pinfo skips P when 0)
     int rows = 0;
     if (fw.active) {
@@ -470,8 +474,10 @@ __global__ void __launch_bounds__(CHOL_THREADS) k_chol_w_solve(UpdArgs a) {
   double* A = sm;
   const int Tm = (n + 7) >> 3;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  pdl_launch_dependents();
   chol_init(A, cs, n, nx);
   __syncthreads();
+  pdl_wait();                                            // W (k_syrk) -- the tiles were zeroed while it was still running
   const int ldr = a.ldr, ldt0 = a.ldt;
   // triangle rows: W;  carried rows: row n + q = F_1[d0 + q][:] = FT[:][d0 + q];  last row: v = S[n][:]
   chol_load_rows(A, n, 0, n + nx, [&](int i, int j) -> const double* {
@@ -520,6 +526,7 @@ __global__ void __launch_bounds__(PI_THREADS) k_pinfo(UpdArgs a, const double* L
   if (!fw.active) return;
   const int n = fw.D - ORCVIO_LEG, D = fw.D, L = ORCVIO_LEG;
   const int tid = threadIdx.x;
+  pdl_wait();
   if (blockIdx.y == gridDim.y - 1) {
     if (blockIdx.x != 0) return;
     double* dxs = sm;
@@ -627,8 +634,8 @@ static void info_attrs() {
 
 static void launch_syrk(const UpdArgs& u, const InfoBufs& ib, int B, const Tile* tiles, cudaStream_t s) {
   dim3 gs(std::max(ib.max_units, 1), B);
-  k_syrk<<<gs, 256, 0, s>>>(u, ib.Amat, u.ldr, ib.part, ib.max_units, ib.cta_budget, ib.group, tiles, ib.tile_rows,
-                            ib.filter_rows, ib.syrk_cnt);
+  launch_pdl(k_syrk, gs, dim3(256), 0, s, u, ib.Amat, u.ldr, ib.part, ib.max_units, ib.cta_budget, ib.group, tiles,
+             ib.tile_rows, ib.filter_rows, ib.syrk_cnt);
   check_launch("k_syrk");
 }
 
@@ -637,7 +644,8 @@ static void launch_pinfo(const UpdArgs& u, const InfoBufs& ib, int nmax, int B, 
   const int g = (Dmax + PT - 1) / PT;
   dim3 g5(g, g + 1, B);                                  // last row of CTAs: the state increment
   const int n4 = (nmax + 3) & ~3;
-  k_pinfo<<<g5, PI_THREADS, ((size_t)2 * n4 * PI_LD + 16 * 32 * 2) * sizeof(double), s>>>(u, ib.Ls, ib.filter_rows);
+  launch_pdl(k_pinfo, g5, dim3(PI_THREADS), ((size_t)2 * n4 * PI_LD + 16 * 32 * 2) * sizeof(double), s, u, ib.Ls,
+             ib.filter_rows);
   check_launch("k_pinfo");
 }
 
@@ -657,7 +665,7 @@ void launch_info_dense_factor(const UpdArgs& u, const InfoBufs& ib, const double
   launch_syrk(u, ib, 1, nullptr, s);
   const size_t sm_w = chol_smem_doubles(n, CS + 1) * sizeof(double);
   dim3 gw((D + CS - 1) / CS, 1);
-  k_chol_w_solve<<<gw, CHOL_THREADS, sm_w, s>>>(u);
+  launch_pdl(k_chol_w_solve, gw, dim3(CHOL_THREADS), sm_w, s, u);
   check_launch("k_chol_w_solve");
 }
 
@@ -696,8 +704,8 @@ void launch_info_update(const QrArgs& q, const UpdArgs& u, const InfoBufs& ib, i
   if (n_tiles > 0) {
     const int rows8 = (std::max(max_tile_rows, 1) + 7) & ~7;
     const int wp = ((6 * max_w_blk + 3) & ~3) + 4;        // >= aform_stride(W) of every tile
-    k_aform<<<n_tiles, AF_THREADS, (size_t)rows8 * wp * sizeof(double), s>>>(q, u.T, u.t_stride, u.ldt, ib.Amat, lda,
-                                                                           ib.tile_rows);
+    launch_pdl(k_aform, dim3(n_tiles), dim3(AF_THREADS), (size_t)rows8 * wp * sizeof(double), s, q, u.T, u.t_stride,
+               u.ldt, ib.Amat, lda, ib.tile_rows);
     check_launch("k_aform");
   }
   if (mid1) cudaEventRecord(mid1, s);
@@ -705,7 +713,7 @@ void launch_info_update(const QrArgs& q, const UpdArgs& u, const InfoBufs& ib, i
   if (mid_syrk) cudaEventRecord(mid_syrk, s);
   const size_t sm_w = chol_smem_doubles(nmax, CS + 1) * sizeof(double);
   dim3 gw((Dmax + CS - 1) / CS, B);
-  k_chol_w_solve<<<gw, CHOL_THREADS, sm_w, s>>>(u);
+  launch_pdl(k_chol_w_solve, gw, dim3(CHOL_THREADS), sm_w, s, u);
   check_launch("k_chol_w_solve");
   if (mid2) cudaEventRecord(mid2, s);
   launch_pinfo(u, ib, nmax, B, s);

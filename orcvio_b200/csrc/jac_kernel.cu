@@ -123,6 +123,7 @@ __global__ void __launch_bounds__(128, MINB) k_jac_gate(JacArgs a) {
   constexpr int LDQ = R2 + 1;
   constexpr int TEAM_DOUBLES = R2 * 6 + R2 * 3 + R2 + 4 + 3 * R2 * LDQ + R2;
   extern __shared__ double smem[];
+  pdl_launch_dependents();
   const int teams_per_block = blockDim.x / TEAM;
   const int team = threadIdx.x / TEAM;
   const int lane = threadIdx.x % TEAM;
@@ -146,6 +147,7 @@ __global__ void __launch_bounds__(128, MINB) k_jac_gate(JacArgs a) {
   } else {
     cd = a.cand[c];
   }
+  pdl_wait();                        // everything above reads host-built lists only; below: triangulation results
   const int st_in = a.tri_status_f ? a.tri_status_f[cd.slot] : a.status[c];
   if (a.tri_status_f && lane == 0) a.status[c] = st_in;      // status by candidate, as the one-pass flow leaves it
   if (!(st_in & ST_TRI_VALID)) {
@@ -366,7 +368,7 @@ static void launch_one(const JacArgs& a, cudaStream_t s) {
     attr_set = true;
   }
   int blocks = (a.n_list + tpb - 1) / tpb;
-  k_jac_gate<TEAM, MAXM, MINB><<<blocks, threads, smem, s>>>(a);
+  launch_pdl(k_jac_gate<TEAM, MAXM, MINB>, dim3(blocks), dim3(threads), smem, s, a);
   check_launch("k_jac_gate");
 }
 

@@ -79,6 +79,102 @@ __global__ void __launch_bounds__(512) k_latency(double* out, double seed) {
   }
 }
 
+
+// Single-warp dependent latencies (cycles per operation; warp 0 of a 64-thread CTA runs alone, the second warp
+// only idles): out[0] DFMA, [1] DMMA m8n8k4 dependent, [2] DMMA with 2 independent accumulators (per MMA),
+// [3] with 4, [4] with 8, [5] 64-bit shuffle + add, [6] 16-byte shared load (pointer chase), [7] fence.acq_rel.cta
+// after a shared store, [8] rcp.approx.ftz.f64, [9] DMMA dependent while the other warp of the scheduler... (unused)
+__global__ void __launch_bounds__(64) k_latency1(double* out, double seed) {
+  __shared__ __align__(16) double sm[128];
+  const int tid = threadIdx.x;
+  sm[tid] = (double)((2 * tid + 2) & 126);
+  sm[tid + 64] = (double)((2 * tid + 2) & 126);
+  __syncthreads();
+  if (tid >= 32) return;
+  const int N = 256;
+  double r[10];
+  long long t0, t1;
+  double x = seed + 1.5;
+  t0 = clock64();
+#pragma unroll 8
+  for (int i = 0; i < N; ++i) x = fma(x, 1.0000001, 1e-9);
+  t1 = clock64();
+  r[0] = (double)(t1 - t0) / N;
+  double a = seed + tid * 1e-3, b = 1.0 + tid * 1e-6;
+  double c[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) c[i] = 0.0;
+  t0 = clock64();
+#pragma unroll 8
+  for (int i = 0; i < N; ++i)
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c[0]), "+d"(c[1]) : "d"(a), "d"(b));
+  t1 = clock64();
+  r[1] = (double)(t1 - t0) / N;
+  t0 = clock64();
+#pragma unroll 4
+  for (int i = 0; i < N; ++i) {
+#pragma unroll
+    for (int u = 0; u < 2; ++u)
+      asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c[2 * u]), "+d"(c[2 * u + 1]) : "d"(a), "d"(b));
+  }
+  t1 = clock64();
+  r[2] = (double)(t1 - t0) / (2 * N);
+  t0 = clock64();
+#pragma unroll 2
+  for (int i = 0; i < N; ++i) {
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+      asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c[2 * u]), "+d"(c[2 * u + 1]) : "d"(a), "d"(b));
+  }
+  t1 = clock64();
+  r[3] = (double)(t1 - t0) / (4 * N);
+  t0 = clock64();
+  for (int i = 0; i < N; ++i) {
+#pragma unroll
+    for (int u = 0; u < 8; ++u)
+      asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c[2 * u]), "+d"(c[2 * u + 1]) : "d"(a), "d"(b));
+  }
+  t1 = clock64();
+  r[4] = (double)(t1 - t0) / (8 * N);
+  double v = x;
+  t0 = clock64();
+#pragma unroll 8
+  for (int i = 0; i < N; ++i) v = __shfl_xor_sync(0xffffffffu, v, 1) + 1.0;
+  t1 = clock64();
+  r[5] = (double)(t1 - t0) / N;
+  int idx = (2 * tid) & 126;
+  t0 = clock64();
+#pragma unroll 8
+  for (int i = 0; i < N; ++i) idx = (int)(*reinterpret_cast<const double2*>(&sm[idx])).x;
+  t1 = clock64();
+  r[6] = (double)(t1 - t0) / N;
+  t0 = clock64();
+  for (int i = 0; i < N; ++i) {
+    sm[tid] = v + i;
+    asm volatile("fence.acq_rel.cta;" ::: "memory");
+  }
+  t1 = clock64();
+  r[7] = (double)(t1 - t0) / N;
+  double y = seed + 3.0;
+  t0 = clock64();
+#pragma unroll 8
+  for (int i = 0; i < N; ++i) {
+    double q;
+    asm volatile("rcp.approx.ftz.f64 %0, %1;" : "=d"(q) : "d"(y));
+    y = q + 2.0;
+  }
+  t1 = clock64();
+  r[8] = (double)(t1 - t0) / N;
+  r[9] = 0.0;
+  double sink = x + v + y + idx + sm[tid];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) sink += c[i];
+  if (tid == 0) {
+    for (int i = 0; i < 10; ++i) out[i] = r[i];
+    out[10] = sink;
+  }
+}
+
 }  // namespace
 
 // Stand-alone run of the one-CTA Cholesky (chol.cuh) on a caller-supplied SPD matrix: the unit test
@@ -161,6 +257,18 @@ extern "C" int orcvio_latency_probe(double* cycles7) {
   cudaMemcpy(h, out, sizeof(h), cudaMemcpyDeviceToHost);
   cudaFree(out);
   for (int i = 0; i < 7; ++i) cycles7[i] = h[i];
+  return cudaGetLastError() == cudaSuccess ? ORCVIO_OK : ORCVIO_ERR_CUDA;
+}
+
+extern "C" int orcvio_latency_probe1(double* cycles10) {
+  double* out = nullptr;
+  if (cudaMalloc(&out, 16 * sizeof(double)) != cudaSuccess) return ORCVIO_ERR_NO_DEVICE;
+  k_latency1<<<1, 64>>>(out, 0.25);
+  k_latency1<<<1, 64>>>(out, 0.25);
+  double h[16];
+  cudaMemcpy(h, out, sizeof(h), cudaMemcpyDeviceToHost);
+  cudaFree(out);
+  for (int i = 0; i < 10; ++i) cycles10[i] = h[i];
   return cudaGetLastError() == cudaSuccess ? ORCVIO_OK : ORCVIO_ERR_CUDA;
 }
 

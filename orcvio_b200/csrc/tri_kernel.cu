@@ -292,6 +292,7 @@ constexpr int TRI_WARPS = 4;
 template <int MINB>
 __global__ void __launch_bounds__(32 * TRI_WARPS, MINB) k_triangulate(TriArgs a) {
   __shared__ double sm_all[TRI_WARPS][32 * TRI_SM_STRIDE];
+  pdl_launch_dependents();            // the Jacobian kernel may be scheduled behind this grid's last wave
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int c = blockIdx.x * TRI_WARPS + warp;
   if (c >= a.n_cand) return;
