@@ -102,6 +102,18 @@ int orcvio_get_cov(orcvio_handle* h, double* P, int cap, int* D);
 int orcvio_get_window(orcvio_handle* h, double* poses12, long long* ids, double* times, int cap);
 /* getMSCKFMapPointPositions, src/orcvio.cpp:3059-3062 */
 int orcvio_get_map_points(orcvio_handle* h, long long* ids, double* xyz, int cap);
+/* state_server.feature_states (hybrid MSCKF / EKF-SLAM mode, max_features_in_one_grid > 0), in state order: feature id,
+ * state id of its anchor clone, inverse depth and obs_anchor (x, y) in the anchor camera (feature.hpp:243-246), world
+ * position.  Column 22 + 6 N + k of the covariance belongs to entry k.  This is what getStableMapPointPositions /
+ * getActiveMapPointPositions (src/orcvio.cpp:3046-3058) are served from. */
+int orcvio_get_feature_states(orcvio_handle* h, long long* ids, long long* anchor_ids, double* inv_depth,
+                              double* obs_anchor, double* xyz, int cap);
+/* EKF-SLAM branches of the last frame (diagnostics / parity surface).  what = 0: features dropped from the state because
+ * they were lost (src/orcvio.cpp:2221-2232; ids);  1: features of the state updated with their 2 rows (:2449-2495; ids,
+ * flags = gate pass, gamma);  2: candidate new features (:2343-2446; ids, flags = entered the state, gamma of the MSCKF
+ * gate);  3: anchor changes in pruneImuStateBuffer (:2665-2722; ids = triples feature id, old anchor, new anchor --
+ * cap counts entries, i.e. 3 per change).  Returns the number of entries written. */
+int orcvio_get_hybrid_log(orcvio_handle* h, int what, long long* ids, int* flags, double* gamma, int cap);
 int orcvio_get_frame_stats(orcvio_handle* h, OrcvioFrameStats* out);
 /* per-candidate log of the last frame: ids, phase (0 lost / 1 prune), status bits
  * (1 = triangulation valid, 2 = gate pass), gamma. */

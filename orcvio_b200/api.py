@@ -73,6 +73,8 @@ def lib():
     L.orcvio_get_frame_stats.argtypes = [vp, C.POINTER(OrcvioFrameStats)]
     L.orcvio_get_map_points.argtypes = [vp, C.POINTER(C.c_longlong), dp, C.c_int]
     L.orcvio_get_candidate_log.argtypes = [vp, C.POINTER(C.c_longlong), ip, ip, dp, C.c_int]
+    L.orcvio_get_feature_states.argtypes = [vp, C.POINTER(C.c_longlong), C.POINTER(C.c_longlong), dp, dp, dp, C.c_int]
+    L.orcvio_get_hybrid_log.argtypes = [vp, C.c_int, C.POINTER(C.c_longlong), ip, dp, C.c_int]
     L.orcvio_batch_create.restype = vp
     L.orcvio_batch_create.argtypes = [C.c_char_p, C.c_int]
     L.orcvio_batch_destroy.argtypes = [vp]
@@ -250,6 +252,46 @@ class OrcVIO:
         n = self._L.orcvio_get_candidate_log(self._h, ids.ctypes.data_as(C.POINTER(C.c_longlong)), _ip(ph),
                                              _ip(st), _dp(g), cap)
         return ids[:n], ph[:n], st[:n], g[:n]
+
+    def feature_states(self, cap=256):
+        """state_server.feature_states (hybrid mode) in state order:
+        (ids, anchor state ids, inverse depths, obs_anchor (n, 2), world positions (n, 3))."""
+        ll = C.POINTER(C.c_longlong)
+        ids = np.zeros(cap, dtype=np.int64)
+        anc = np.zeros(cap, dtype=np.int64)
+        rho = np.zeros(cap)
+        oa = np.zeros((cap, 2))
+        xyz = np.zeros((cap, 3))
+        n = self._L.orcvio_get_feature_states(self._h, ids.ctypes.data_as(ll), anc.ctypes.data_as(ll), _dp(rho),
+                                              _dp(oa), _dp(xyz), cap)
+        return ids[:n], anc[:n], rho[:n], oa[:n], xyz[:n]
+
+    def getStableMapPointPositions(self):
+        """src/orcvio.cpp:3046-3051 (the reference returns its whole `map_points` archive; the features of the state
+        are the ones this path maintains)."""
+        return self.feature_states()[4]
+
+    def getActiveMapPointPositions(self):
+        """src/orcvio.cpp:3053-3058."""
+        return self.feature_states()[4]
+
+    def hybrid_log(self, cap=4096):
+        """EKF-SLAM branches of the last frame: dict(ekf_lost, ekf {id: (pass, gamma)}, new {id: (entered, gamma)},
+        reanchored {id: (old anchor, new anchor)})."""
+        ll = C.POINTER(C.c_longlong)
+        out = {}
+        for what, name in ((0, "ekf_lost"), (1, "ekf"), (2, "new"), (3, "reanchored")):
+            ids = np.zeros(cap, dtype=np.int64)
+            fl = np.zeros(cap, dtype=np.int32)
+            g = np.zeros(cap)
+            n = self._L.orcvio_get_hybrid_log(self._h, what, ids.ctypes.data_as(ll), _ip(fl), _dp(g), cap)
+            if what == 0:
+                out[name] = [int(i) for i in ids[:n]]
+            elif what == 3:
+                out[name] = {int(ids[3 * k]): (int(ids[3 * k + 1]), int(ids[3 * k + 2])) for k in range(n // 3)}
+            else:
+                out[name] = {int(i): (bool(f), float(x)) for i, f, x in zip(ids[:n], fl[:n], g[:n])}
+        return out
 
     # -- object path (stage 3, filter side)
     def setStateCov(self, imu_dim, num_clone):

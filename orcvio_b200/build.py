@@ -30,6 +30,7 @@ SOURCES = {
     "zupt_kernel.cu": [],
     "obj_kernel.cu": [],
     "ekf_kernel.cu": [],
+    "hybrid_kernel.cu": [],
     "batch.cu": [],
     "objects.cu": [],
     "capi.cu": [],

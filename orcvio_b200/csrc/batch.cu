@@ -52,6 +52,13 @@ struct Batch::PhaseWork {
   int own_wmax_blk = 1;
   int wmax_blk = 1;
   int maxN = 0;
+  // hybrid mode: the dense rows of the EKF-SLAM features (hybrid_kernel.cu)
+  std::vector<HybWork> hw;
+  std::vector<HybFeat> hfeats;
+  std::vector<HybNew> hnews;
+  int maxE = 0, max_dense = 0, hyb_phase = -1;   // hyb_phase: 0 lost-feature update, 1 prune update, -1 off
+  size_t dense_total = 0;
+  const HybWork* dHw = nullptr; const HybFeat* dHfeats = nullptr; const HybNew* dHnews = nullptr;
   std::vector<int> cand_begin;   // per filter, size B + 1
   bool any_active = false;
   std::vector<int> extra_ints;   // uploaded alongside (clone removal indices)
@@ -73,6 +80,8 @@ struct Batch::PhaseWork {
     small_list.clear(); large_list.clear(); cand_begin.clear(); extra_ints.clear();
     hblk_total = rows_total = tileout_total = tile_smem_doubles = 0;
     rows_cap = 0; max_tile_rows = 0; arows_total = 0; own_wmax_blk = 1; wmax_blk = 1; maxN = 0;
+    hw.clear(); hfeats.clear(); hnews.clear(); maxE = 0; max_dense = 0; hyb_phase = -1; dense_total = 0;
+    dHw = nullptr; dHfeats = nullptr; dHnews = nullptr;
     any_active = false; d_extra = nullptr;
     dC = nullptr; dOc = nullptr; dOz = nullptr; dTiles = nullptr; dFw = nullptr; dSmall = dLarge = nullptr;
     ext_obs_clone = nullptr; ext_obs_z = nullptr; ext_nobs = 0;
@@ -81,6 +90,47 @@ struct Batch::PhaseWork {
 };
 
 static constexpr int WTILE_MAX_BLK = 8;   // widest clone window a tile may span (blocks)
+
+// Device / pinned buffers of the hybrid MSCKF / EKF-SLAM mode (allocated only when max_features_in_one_grid > 0).
+struct Batch::HybridBufs {
+  double* dSpecPos = nullptr;          // scratch position table of the speculative initializeInvParamPosition pass
+  long long* dSpecGen = nullptr;
+  double* dFinal = nullptr; size_t final_cap = 0;          // 3 per speculative candidate (anchor-frame solution)
+  int* dSpecStatus = nullptr; int* hSpecStatus = nullptr; size_t spec_cap = 0;
+  double* dHd = nullptr; size_t hd_cap = 0;                // dense rows, ldh = ldr
+  double *dH1 = nullptr, *dh2 = nullptr, *dr1 = nullptr, *dScratch = nullptr;
+  int *dEkfPass = nullptr, *dNewOk = nullptr, *dNNew = nullptr;
+  double* dEkfGamma = nullptr;
+  int* hEkfPass = nullptr; double* hEkfGamma = nullptr;    // pinned
+  double *dGather = nullptr, *hGather = nullptr; size_t gather_cap = 0;
+  // upload arena: sections are only appended between two synchronisations of the stream (reset after a sync), so a
+  // queued copy never sees its pinned source rewritten; fixed capacity, so device pointers stay valid
+  char *pin = nullptr, *dev = nullptr; size_t cap = 0, used = 0;
+  template <class T>
+  const T* put(const T* src, size_t n, cudaStream_t s, bool* ok) {
+    const size_t off = (used + 255) & ~size_t(255), bytes = sizeof(T) * std::max<size_t>(n, 1);
+    if (off + bytes > cap) { *ok = false; return nullptr; }
+    if (n) std::memcpy(pin + off, src, sizeof(T) * n);
+    if (n && cudaMemcpyAsync(dev + off, pin + off, sizeof(T) * n, cudaMemcpyHostToDevice, s) != cudaSuccess) *ok = false;
+    used = off + bytes;
+    return reinterpret_cast<const T*>(dev + off);
+  }
+};
+
+void Batch::HybridDeleter::operator()(HybridBufs* h) const {
+  if (!h) return;
+  cudaFree(h->dSpecPos); cudaFree(h->dSpecGen); cudaFree(h->dFinal); cudaFree(h->dSpecStatus);
+  if (h->hSpecStatus) cudaFreeHost(h->hSpecStatus);
+  cudaFree(h->dHd); cudaFree(h->dH1); cudaFree(h->dh2); cudaFree(h->dr1); cudaFree(h->dScratch);
+  cudaFree(h->dEkfPass); cudaFree(h->dNewOk); cudaFree(h->dNNew); cudaFree(h->dEkfGamma);
+  if (h->hEkfPass) cudaFreeHost(h->hEkfPass);
+  if (h->hEkfGamma) cudaFreeHost(h->hEkfGamma);
+  cudaFree(h->dGather);
+  if (h->hGather) cudaFreeHost(h->hGather);
+  cudaFree(h->dev);
+  if (h->pin) cudaFreeHost(h->pin);
+  delete h;
+}
 
 Batch::Batch(const Params& p, int n) : p_(p), B_(n) {
   ok_ = true;
@@ -97,8 +147,11 @@ Batch::Batch(const Params& p, int n) : p_(p), B_(n) {
     ok_ = false;
     return;
   }
-  ldp_ = ((ORCVIO_LEG + 6 * Ncap_ + 7) / 8) * 8;
-  ldr_ = ((6 * Ncap_ + 1 + 7) / 8) * 8;
+  Emax_ = p_.max_features * p_.grid_rows * p_.grid_cols;     // 0: pure MSCKF
+  hybrid_ = Emax_ > 0;
+  nmax_ = 6 * Ncap_ + Emax_;
+  ldp_ = ((ORCVIO_LEG + nmax_ + 7) / 8) * 8;
+  ldr_ = ((nmax_ + 1 + 7) / 8) * 8;
   ldt_ = ldp_;
   Fcap_ = 4096;
   flags_ = (p_.use_larvio_flag ? FL_LARVIO : 0) | (p_.use_left_perturbation_flag ? FL_LEFT : 0) |
@@ -133,7 +186,7 @@ Batch::Batch(const Params& p, int n) : p_(p), B_(n) {
   CK(cudaEventCreateWithFlags(&ev_join_, cudaEventDisableTiming));
   {
     const char* e = std::getenv("ORCVIO_COMPRESS");
-    compress_qr_ = e && std::string(e) == "qr";
+    compress_qr_ = e && std::string(e) == "qr" && !hybrid_;     // the dense EKF-feature rows exist only in the whitened form
   }
   for (auto& e : ev_) CK(cudaEventCreate(&e));
   const size_t nB = (size_t)B_;
@@ -147,7 +200,35 @@ Batch::Batch(const Params& p, int n) : p_(p), B_(n) {
   CK(cudaMemset(dFpos_, 0, nB * Fcap_ * FP_STRIDE * sizeof(double)));
   CK(cudaMalloc(&dFgen_, nB * Fcap_ * sizeof(long long)));
   CK(cudaMemset(dFgen_, 0xFF, nB * Fcap_ * sizeof(long long)));
-  const int ncap = 6 * Ncap_;
+  const int ncap = nmax_;
+  if (hybrid_) {
+    CK(cudaMalloc(&dFidp_, nB * Fcap_ * FI_STRIDE * sizeof(double)));
+    CK(cudaMemset(dFidp_, 0, nB * Fcap_ * FI_STRIDE * sizeof(double)));
+    hyb_.reset(new HybridBufs());
+    HybridBufs& h = *hyb_;
+    CK(cudaMalloc(&h.dSpecPos, nB * Fcap_ * FP_STRIDE * sizeof(double)));
+    CK(cudaMemset(h.dSpecPos, 0, nB * Fcap_ * FP_STRIDE * sizeof(double)));
+    CK(cudaMalloc(&h.dSpecGen, nB * Fcap_ * sizeof(long long)));
+    CK(cudaMemset(h.dSpecGen, 0xFF, nB * Fcap_ * sizeof(long long)));
+    const size_t ne = nB * Emax_;
+    CK(cudaMalloc(&h.dH1, ne * ldr_ * sizeof(double)));
+    CK(cudaMalloc(&h.dh2, ne * sizeof(double)));
+    CK(cudaMalloc(&h.dr1, ne * sizeof(double)));
+    CK(cudaMalloc(&h.dScratch, nB * 64 * ldr_ * sizeof(double)));
+    CK(cudaMalloc(&h.dEkfPass, ne * sizeof(int)));
+    CK(cudaMalloc(&h.dEkfGamma, ne * sizeof(double)));
+    CK(cudaMalloc(&h.dNewOk, ne * sizeof(int)));
+    CK(cudaMalloc(&h.dNNew, nB * sizeof(int)));
+    CK(cudaMemset(h.dNNew, 0, nB * sizeof(int)));
+    CK(cudaMallocHost(&h.hEkfPass, ne * sizeof(int)));
+    CK(cudaMallocHost(&h.hEkfGamma, ne * sizeof(double)));
+    h.gather_cap = 2 * ne + 64;
+    CK(cudaMalloc(&h.dGather, h.gather_cap * 6 * sizeof(double)));
+    CK(cudaMallocHost(&h.hGather, h.gather_cap * 6 * sizeof(double)));
+    h.cap = (size_t)(2 << 20) + nB * (size_t)(64 << 10);
+    CK(cudaMalloc(&h.dev, h.cap));
+    CK(cudaMallocHost(&h.pin, h.cap));
+  }
   CK(cudaMalloc(&dR_, nB * (size_t)(ncap + 1) * ldr_ * sizeof(double)));
   CK(cudaMalloc(&dS_, nB * (size_t)(ncap + 1) * ldr_ * sizeof(double)));
   CK(cudaMalloc(&dRthin_, nB * ldr_ * sizeof(double)));
@@ -198,7 +279,7 @@ Batch::~Batch() {
   cudaFree(dR_); cudaFree(dS_); cudaFree(dRthin_); cudaFree(dYv_); cudaFree(dT_); cudaFree(dDx_);
   cudaFree(dErr_); cudaFree(dFront_); cudaFree(dChi2_);
   cudaFree(dAmat_); cudaFree(dPart_);
-  cudaFree(dStatusF_); cudaFree(dGammaF_);
+  cudaFree(dStatusF_); cudaFree(dGammaF_); cudaFree(dFidp_);
   if (blob_early2_.dev) cudaFree(blob_early2_.dev);
   if (blob_early2_.pinned) cudaFreeHost(blob_early2_.pinned);
   if (blob_early_.dev) cudaFree(blob_early_.dev);
@@ -390,6 +471,20 @@ void Batch::stage_upload(PhaseWork& w) {
       CK(cudaMalloc(&dPart_, part_cap_ * sizeof(double)));
     }
   }
+  if (hybrid_ && w.hyb_phase >= 0) {
+    HybridBufs& hb = *hyb_;
+    const size_t need_h = (w.dense_total + 8) * (size_t)ldr_;
+    if (need_h > hb.hd_cap) {
+      if (hb.dHd) cudaFree(hb.dHd);
+      hb.hd_cap = need_h * 2;
+      CK(cudaMalloc(&hb.dHd, hb.hd_cap * sizeof(double)));
+    }
+    bool okp = true;
+    w.dHw = hb.put(w.hw.data(), w.hw.size(), stream_, &okp);
+    w.dHfeats = hb.put(w.hfeats.data(), w.hfeats.size(), stream_, &okp);
+    w.dHnews = hb.put(w.hnews.data(), w.hnews.size(), stream_, &okp);
+    if (!okp) { ok_ = false; err_ = "hybrid upload arena exhausted"; }
+  }
   upload_blob();
   char* d = blob_.dev;
   w.dC = (const Cand*)(d + o_c);
@@ -411,13 +506,31 @@ UpdArgs Batch::upd_args(const FilterWork* dFw) const {
   UpdArgs ua{};
   ua.fw = dFw; ua.n_filters = B_;
   ua.P = dP_; ua.p_stride = (size_t)ldp_ * ldp_; ua.ldp = ldp_;
-  ua.Rm = dR_; ua.rthin = dRthin_; ua.r_stride = (size_t)(6 * Ncap_ + 1) * ldr_; ua.ldr = ldr_;
-  ua.T = dT_; ua.S = dS_; ua.t_stride = (size_t)(6 * Ncap_) * ldt_; ua.ldt = ldt_;
+  ua.Rm = dR_; ua.rthin = dRthin_; ua.r_stride = (size_t)(nmax_ + 1) * ldr_; ua.ldr = ldr_;
+  ua.T = dT_; ua.S = dS_; ua.t_stride = (size_t)nmax_ * ldt_; ua.ldt = ldt_;
   ua.yv = dYv_;
   ua.imu = dImu_; ua.clones = dClones_; ua.clone_stride = (size_t)Ncap_ * CL_STRIDE;
   ua.dx = dDx_; ua.lddx = ldp_;
   ua.flags = flags_; ua.sigma2 = p_.feature_observation_noise;
   return ua;
+}
+
+HybArgs Batch::hyb_args(const PhaseWork& w) const {
+  const HybridBufs& hb = *hyb_;
+  HybArgs ha{};
+  ha.hw = w.dHw; ha.n_filters = B_; ha.feats = w.dHfeats; ha.news = w.dHnews;
+  ha.clones = dClones_; ha.clone_stride = (size_t)Ncap_ * CL_STRIDE; ha.imu = dImu_;
+  ha.fpos = dFpos_; ha.fidp = dFidp_; ha.fcap = Fcap_;
+  ha.P = dP_; ha.p_stride = (size_t)ldp_ * ldp_; ha.ldp = ldp_;
+  ha.obs_clone = w.dOc; ha.obs_z = w.dOz;
+  ha.status = dStatus_;
+  ha.sigma2 = p_.feature_observation_noise; ha.chi2_dof2 = chi2_host_[2];
+  ha.Hd = hb.dHd; ha.ldh = ldr_;
+  ha.H1 = hb.dH1; ha.h2 = hb.dh2; ha.r1 = hb.dr1; ha.new_cap = Emax_;
+  ha.scratch = hb.dScratch;
+  ha.ekf_pass = hb.dEkfPass; ha.ekf_gamma = hb.dEkfGamma; ha.new_ok = hb.dNewOk; ha.n_new = hb.dNNew;
+  ha.dx = dDx_; ha.lddx = ldp_;
+  return ha;
 }
 
 // Kernel chain of one phase on already staged work lists: triangulate -> Jacobian/nullspace/gate
@@ -439,10 +552,13 @@ void Batch::launch_phase(PhaseWork& w, bool download, bool prior_in_flight) {
     InfoBufs ib{};
     ib.Ls = dLs_;
     launch_info_prior(upd_args(dFw), ib, w.maxN, stream2_, ev_fork_, ev_join_, profiling_ ? e[9] : nullptr,
-                      profiling_ ? e[10] : nullptr);
+                      profiling_ ? e[10] : nullptr, w.maxE);
     ++nl;
     prior_in_flight = true;
   }
+  const bool hyb_on = hybrid_ && w.hyb_phase >= 0 && do_update && !use_qr;
+  HybArgs ha{};
+  if (hyb_on) ha = hyb_args(w);
   if (want_iters_ && (size_t)nC > iters_cap_) {
     if (dIters_) cudaFree(dIters_);
     if (dCost_) cudaFree(dCost_);
@@ -491,6 +607,10 @@ void Batch::launch_phase(PhaseWork& w, bool download, bool prior_in_flight) {
     launch_jac_gate(js, jl, stream_);
     nl += (js.n_list > 0) + (jl.n_list > 0);
   }
+  if (hyb_on && w.hyb_phase == 0) {     // dense rows of the features of the state / of the new features (gated)
+    launch_hybrid_rows(ha, stream_);
+    ++nl;
+  }
   if (profiling_) CK(cudaEventRecord(e[2], stream_));
   if (do_update) {
     QrArgs qa{};
@@ -505,7 +625,7 @@ void Batch::launch_phase(PhaseWork& w, bool download, bool prior_in_flight) {
     qa.tiles = dTiles; qa.n_tiles = (int)w.tiles.size();
     qa.tile_out = dTileOut_;
     qa.fw = dFw; qa.n_filters = B_;
-    qa.Rm = dR_; qa.rthin = dRthin_; qa.r_stride = (size_t)(6 * Ncap_ + 1) * ldr_; qa.ldr = ldr_;
+    qa.Rm = dR_; qa.rthin = dRthin_; qa.r_stride = (size_t)(nmax_ + 1) * ldr_; qa.ldr = ldr_;
     qa.front_scratch = dFront_; qa.front_stride = front_stride_;
     qa.err = dErr_;
     UpdArgs ua = upd_args(dFw);
@@ -521,7 +641,12 @@ void Batch::launch_phase(PhaseWork& w, bool download, bool prior_in_flight) {
       launch_info_update(qa, ua, ib, (int)w.tiles.size(), w.max_tile_rows, w.wmax_blk, w.maxN, stream_,
                          stream2_, ev_fork_, ev_join_, profiling_ ? e[3] : nullptr, profiling_ ? e[4] : nullptr, &nl,
                          prior_in_flight, profiling_ ? e[8] : nullptr, profiling_ ? e[9] : nullptr,
-                         profiling_ ? e[10] : nullptr);
+                         profiling_ ? e[10] : nullptr, w.maxE, hyb_on ? &ha : nullptr, w.max_dense);
+      if (hyb_on) {
+        // feature increments (+ delayed initialisation of this frame's new features), src/orcvio.cpp:1843-1941
+        if (w.hyb_phase == 0) { launch_hybrid_post(ha, stream_); ++nl; }
+        else if (w.maxE > 0) { launch_hybrid_feature_increment(ha, stream_); ++nl; }
+      }
     }
     if (profiling_) CK(cudaEventRecord(e[5], stream_));
   }
@@ -679,7 +804,7 @@ int Batch::process(const double* t_img, const OrcvioFeature* feats, const int* f
   const int L = ORCVIO_LEG;
   // ---------------------------------------------------------------- A: propagation inputs
   std::vector<PropSample> samples;
-  std::vector<int> samp_off(B_ + 1, 0), Dvec(B_, 0), Nvec(B_, 0);
+  std::vector<int> samp_off(B_ + 1, 0), Dvec(B_, 0), Nvec(B_, 0), Evec(B_, 0);
   bool need_imu_upload = false;
   for (int fi = 0; fi < B_; ++fi) {
     FilterHost& F = f_[fi];
@@ -689,6 +814,8 @@ int Batch::process(const double* t_img, const OrcvioFeature* feats, const int* f
     F.cinfo[0].clear(); F.cinfo[1].clear();
     F.cstatus[0].clear(); F.cstatus[1].clear();
     F.cgamma[0].clear(); F.cgamma[1].clear();
+    F.log_ekf_lost.clear(); F.log_ekf_ids.clear(); F.log_new_ids.clear(); F.log_ekf_pass.clear();
+    F.log_new_ok.clear(); F.log_ekf_gamma.clear(); F.log_new_gamma.clear(); F.log_reanchor.clear();
     published[fi] = 0;
     imu_used[fi] = 0;
     samp_off[fi + 1] = (int)samples.size();
@@ -721,6 +848,7 @@ int Batch::process(const double* t_img, const OrcvioFeature* feats, const int* f
       F.gravity_set = true;
       F.imu_time = F.init_t;
       F.take_off_stamp = F.init_t;
+      F.last_zupt_time = F.init_t;       // :556
     }
     // batchImuProcessing :664-724
     const double bound = ti + p_.td;
@@ -743,7 +871,8 @@ int Batch::process(const double* t_img, const OrcvioFeature* feats, const int* f
     F.dt = dt;
     imu_used[fi] = prefix + used;
     Nvec[fi] = (int)F.clones.size();
-    Dvec[fi] = L + 6 * Nvec[fi];
+    Evec[fi] = (int)F.feature_states.size();
+    Dvec[fi] = L + 6 * Nvec[fi] + Evec[fi];
     F.active = true;
     published[fi] = 1;
 
@@ -823,7 +952,9 @@ int Batch::process(const double* t_img, const OrcvioFeature* feats, const int* f
     const size_t o_o = blob_.reserve(sizeof(int) * (B_ + 1));
     const size_t o_d = blob_.reserve(sizeof(int) * B_);
     const size_t o_n = blob_.reserve(sizeof(int) * B_);
+    const size_t o_e = blob_.reserve(sizeof(int) * B_);
     char* h = blob_.pinned;
+    std::memcpy(h + o_e, Evec.data(), sizeof(int) * B_);
     if (!samples.empty()) std::memcpy(h + o_s, samples.data(), sizeof(PropSample) * samples.size());
     std::memcpy(h + o_o, samp_off.data(), sizeof(int) * (B_ + 1));
     std::memcpy(h + o_d, Dvec.data(), sizeof(int) * B_);
@@ -884,6 +1015,7 @@ int Batch::process(const double* t_img, const OrcvioFeature* feats, const int* f
     aa.P = dP_; aa.p_stride = pa.p_stride; aa.ldp = ldp_;
     aa.imu = dImu_; aa.clones = dClones_; aa.clone_stride = (size_t)Ncap_ * CL_STRIDE;
     aa.N = (const int*)(blob_.dev + o_n); aa.n_filters = B_;
+    aa.E = hybrid_ ? (const int*)(blob_.dev + o_e) : nullptr;
     launch_augment(aa, stream_);
     launches_ += 2;
     if (any_zupt) {
@@ -923,6 +1055,17 @@ int Batch::process(const double* t_img, const OrcvioFeature* feats, const int* f
         F.stats.zupt = F.if_zupt ? 1 : 0;
         F.stats.zupt_chi2 = F.zupt_chi2;
         F.stats.zupt_vnorm = F.zupt_vnorm;
+        if (F.if_zupt) {
+          F.last_zupt_time = F.imu_time;                 // :3451
+          // checkZUPTFeat :3104-3115 / checkZUPTIMU :3304-3315: a stationary frame drops every EKF-SLAM feature; the
+          // update itself only touched the leading 22 + 6N block, the feature rows / columns are simply abandoned
+          for (long long id : F.feature_states) {
+            Track& tr = F.map_server.at(id);
+            tr.in_state = tr.ekf_feature = tr.initialized = false;
+            tr.gen = F.next_gen++;                       // the device slot no longer counts as initialised
+          }
+          F.feature_states.clear();
+        }
       }
     }
   }
@@ -932,68 +1075,214 @@ int Batch::process(const double* t_img, const OrcvioFeature* feats, const int* f
   wA.rows_cap = compress_qr_ ? 0 : AFORM_TILE_ROWS;
   wA.fw.assign(B_, FilterWork{});
   wA.cand_begin.assign(B_ + 1, 0);
+  if (hybrid_) { wA.hyb_phase = 0; wA.hw.assign(B_, HybWork{}); }
+  auto clone_index_of = [](const FilterHost& F, long long sid) {
+    for (int k = (int)F.clones.size() - 1; k >= 0; --k)
+      if (F.clones[k].id == sid) return k;
+    return -1;
+  };
+  // one candidate record + its observations in the pools of w (lost / tracked-long feature of removeLostFeatures)
+  auto make_cand = [&](PhaseWork& w, const FilterHost& F, const Track& tr, bool tracked_now, int kind, int flags) {
+    CandBuild x{};
+    x.id = tr.id;
+    x.kind = kind;
+    Cand& c = x.c;
+    c.slot = tr.slot;
+    c.gen = tr.gen;
+    c.flags = flags;
+    c.jac_off = c.tri_off = (int)w.obs_clone.size();
+    int s_blk = 1 << 30, e_blk = -1, cnt = 0;
+    for (const Obs& o : tr.obs) {
+      const int ci = clone_index_of(F, o.sid);
+      if (ci < 0) continue;
+      w.obs_clone.push_back(ci);
+      w.obs_z.push_back(o.z[0]);
+      w.obs_z.push_back(o.z[1]);
+      s_blk = std::min(s_blk, ci);
+      e_blk = std::max(e_blk, ci);
+      ++cnt;
+    }
+    c.jac_m = cnt;
+    c.tri_m = tracked_now ? cnt - 1 : cnt;   // initializePosition skips the current frame (:414)
+    c.s_blk = s_blk;
+    c.e_blk = e_blk;
+    c.cm_first_clone = w.obs_clone[c.jac_off];
+    c.cm_last_clone = w.obs_clone[c.jac_off + (tracked_now ? cnt - 2 : cnt - 1)];
+    c.cm_zu = w.obs_z[2 * (size_t)c.jac_off];
+    c.cm_zv = w.obs_z[2 * (size_t)c.jac_off + 1];
+    return x;
+  };
+  std::vector<std::vector<CandBuild>> cbs(B_);
+  // hybrid mode (:2283-2323): tracked-long features whose grid cell had room when the walk started.  Whether such a
+  // feature becomes an EKF-SLAM feature depends on the triangulation outcome of the ones before it (cells fill up in
+  // id order), so initializeInvParamPosition runs speculatively for all of them into a scratch table; the host then
+  // replays the reference's sequential decision and commits the ones that took the branch.
+  struct PossRec { Track* tr; int code; int spec; long long spec_gen; };
+  std::vector<std::vector<PossRec>> poss(B_);
+  std::vector<std::map<int, int>> cells(B_);
+  std::vector<std::vector<Track*>> news(B_);
+  PhaseWork wS;
+  HybridBufs* hb = hyb_.get();
+  bool hyb_ok = true;
+  if (hybrid_) {
+    hb->used = 0;                          // the stream is idle (synchronised at the end of section B)
+    std::vector<int> newidx, Dold(B_, 0);
+    bool any_compact = false;
+    for (int fi = 0; fi < B_; ++fi) {
+      FilterHost& F = f_[fi];
+      if (!F.active || F.feature_states.empty()) continue;
+      // features of the state: tracked now -> a 2-row update; lost -> dropped (:2210-2232, rmLostFeaturesCov :3776-3828)
+      const int base = L + 6 * (int)F.clones.size(), E0 = (int)F.feature_states.size();
+      std::vector<long long> kept;
+      std::vector<int> map_e(E0, -1);
+      for (int i = 0; i < E0; ++i) {
+        Track& tr = F.map_server.at(F.feature_states[i]);
+        if (!tr.obs.empty() && tr.obs.back().sid == F.state_id) {
+          map_e[i] = (int)kept.size();
+          kept.push_back(tr.id);
+        } else {
+          const long long lost_id = tr.id;
+          F.log_ekf_lost.push_back(lost_id);
+          F.free_slots.push_back(tr.slot);
+          F.map_server.erase(lost_id);
+        }
+      }
+      if ((int)kept.size() != E0) {
+        if (newidx.empty()) newidx.assign((size_t)B_ * ldp_, -1);
+        int* ni = newidx.data() + (size_t)fi * ldp_;
+        for (int j = 0; j < base; ++j) ni[j] = j;
+        for (int i = 0; i < E0; ++i) ni[base + i] = map_e[i] < 0 ? -1 : base + map_e[i];
+        Dold[fi] = base + E0;
+        any_compact = true;
+        F.feature_states = kept;
+      }
+    }
+    if (any_compact) {
+      const int* d_ni = hb->put(newidx.data(), newidx.size(), stream_, &hyb_ok);
+      const int* d_do = hb->put(Dold.data(), Dold.size(), stream_, &hyb_ok);
+      if (hyb_ok) { launch_compact_cov(dP_, (size_t)ldp_ * ldp_, ldp_, d_ni, d_do, B_, stream_); ++launches_; }
+    }
+  }
+  auto grid_code = [&](const Track& tr) {   // :2286-2289 / :3841-3845 (the casts truncate toward zero)
+    const double* z = tr.obs.back().z;
+    const int row = (int)((z[1] - p_.y_min) / p_.grid_height);
+    const int col = (int)((z[0] - p_.x_min) / p_.grid_width);
+    return row * p_.grid_cols + col;
+  };
   for (int fi = 0; fi < B_; ++fi) {
     FilterHost& F = f_[fi];
-    wA.cand_begin[fi] = (int)wA.cands.size();
     FilterWork& fw = wA.fw[fi];
     fw.N = (int)F.clones.size();
-    fw.D = L + 6 * fw.N;
+    fw.D = L + 6 * fw.N + (int)F.feature_states.size();
     fw.active = 0;
     if (!F.active) continue;
     wA.maxN = std::max(wA.maxN, fw.N);
     const long long cur = F.state_id;
-    std::vector<CandBuild> cb;
+    std::vector<CandBuild>& cb = cbs[fi];
     std::vector<long long> invalid;
-    auto clone_index = [&](long long sid) {
-      for (int k = (int)F.clones.size() - 1; k >= 0; --k)
-        if (F.clones[k].id == sid) return k;
-      return -1;
-    };
+    bool ekf_open = false;
+    if (hybrid_) {
+      for (long long id : F.feature_states) cells[fi][grid_code(F.map_server.at(id))]++;   // updateGridMap :3831-3850
+      ekf_open = (F.imu_time - F.last_zupt_time > 5) && (int)F.feature_states.size() < Emax_;
+    }
     for (auto& kv : F.map_server) {
       Track& tr = kv.second;
+      if (tr.in_state) continue;
       const int nobs = (int)tr.obs.size();
       const bool tracked_now = nobs > 0 && tr.obs.back().sid == cur;
       if (!tracked_now) {
         if (nobs < p_.least_Obs_Num) { invalid.push_back(tr.id); continue; }
       } else {
         if (!(nobs >= p_.max_track_len)) continue;
+        if (ekf_open) {
+          const int code = grid_code(tr);
+          auto it = cells[fi].find(code);
+          if ((it == cells[fi].end() ? 0 : it->second) < p_.max_features) {
+            PossRec pr{&tr, code, -1, 0};
+            if (!tr.ekf_feature) {
+              // is_initialized = false (:2296): a fresh serial, so the kernel starts from the two-view guess
+              pr.spec_gen = F.next_gen++;
+              Track probe = tr;
+              probe.gen = pr.spec_gen;
+              CandBuild x = make_cand(wS, F, probe, true, 1, 0);
+              x.c.filter = fi;
+              pr.spec = (int)wS.cands.size();
+              wS.cands.push_back(x.c);
+            }
+            poss[fi].push_back(pr);
+            continue;
+          }
+        }
       }
-      CandBuild x{};
-      x.id = tr.id;
-      x.kind = tracked_now ? 1 : 0;
-      Cand& c = x.c;
-      c.slot = tr.slot;
-      c.gen = tr.gen;
-      c.flags = 0;
-      c.jac_off = c.tri_off = (int)wA.obs_clone.size();
-      int s_blk = 1 << 30, e_blk = -1, cnt = 0;
-      for (const Obs& o : tr.obs) {
-        const int ci = clone_index(o.sid);
-        if (ci < 0) continue;
-        wA.obs_clone.push_back(ci);
-        wA.obs_z.push_back(o.z[0]);
-        wA.obs_z.push_back(o.z[1]);
-        s_blk = std::min(s_blk, ci);
-        e_blk = std::max(e_blk, ci);
-        ++cnt;
-      }
-      c.jac_m = cnt;
-      c.tri_m = tracked_now ? cnt - 1 : cnt;   // initializePosition skips the current frame (:414)
-      c.s_blk = s_blk;
-      c.e_blk = e_blk;
-      c.cm_first_clone = wA.obs_clone[c.jac_off];
-      c.cm_last_clone = wA.obs_clone[c.jac_off + (tracked_now ? cnt - 2 : cnt - 1)];
-      c.cm_zu = wA.obs_z[2 * (size_t)c.jac_off];
-      c.cm_zv = wA.obs_z[2 * (size_t)c.jac_off + 1];
-      cb.push_back(x);
+      cb.push_back(make_cand(wA, F, tr, tracked_now, tracked_now ? 1 : 0, 0));
     }
     for (long long id : invalid) {
       auto it = F.map_server.find(id);
       F.free_slots.push_back(it->second.slot);
       F.map_server.erase(it);
     }
+  }
+  std::vector<CommitRec> commits;
+  if (hybrid_ && !wS.cands.empty()) {
+    const size_t nS = wS.cands.size();
+    if (nS > hb->spec_cap) {
+      cudaFree(hb->dFinal); cudaFree(hb->dSpecStatus);
+      if (hb->hSpecStatus) cudaFreeHost(hb->hSpecStatus);
+      hb->spec_cap = nS * 2 + 64;
+      CK(cudaMalloc(&hb->dFinal, hb->spec_cap * 3 * sizeof(double)));
+      CK(cudaMalloc(&hb->dSpecStatus, hb->spec_cap * sizeof(int)));
+      CK(cudaMallocHost(&hb->hSpecStatus, hb->spec_cap * sizeof(int)));
+    }
+    TriArgs ta{};
+    ta.cand = hb->put(wS.cands.data(), nS, stream_, &hyb_ok); ta.n_cand = (int)nS;
+    ta.clones = dClones_; ta.clone_stride = (size_t)Ncap_ * CL_STRIDE;
+    ta.fpos = hb->dSpecPos; ta.fgen = hb->dSpecGen; ta.fcap = Fcap_;
+    ta.obs_clone = hb->put(wS.obs_clone.data(), wS.obs_clone.size(), stream_, &hyb_ok);
+    ta.obs_z = hb->put(wS.obs_z.data(), wS.obs_z.size(), stream_, &hyb_ok);
+    ta.cfg = tricfg_;
+    ta.status = hb->dSpecStatus;
+    ta.final_pos = hb->dFinal;
+    if (hyb_ok) {
+      launch_triangulate(ta, stream_);
+      ++launches_;
+      CK(cudaMemcpyAsync(hb->hSpecStatus, hb->dSpecStatus, nS * sizeof(int), cudaMemcpyDeviceToHost, stream_));
+      CK(cudaStreamSynchronize(stream_));
+    }
+  }
+  for (int fi = 0; fi < B_; ++fi) {
+    FilterHost& F = f_[fi];
+    wA.cand_begin[fi] = (int)wA.cands.size();
+    FilterWork& fw = wA.fw[fi];
+    if (!F.active) continue;
+    std::vector<CandBuild>& cb = cbs[fi];
+    const int E = (int)F.feature_states.size();
+    if (hybrid_) {
+      // the reference's sequential grid decision (:2291-2323), now that every triangulation outcome is known
+      int n_new = 0;
+      for (PossRec& pr : poss[fi]) {
+        Track& tr = *pr.tr;
+        int& cell = cells[fi][pr.code];
+        if (!(cell < p_.max_features && E + n_new < Emax_)) {       // no room any more: an MSCKF feature
+          cb.push_back(make_cand(wA, F, tr, true, 1, 0));
+          continue;
+        }
+        if (!tr.ekf_feature) {
+          tr.gen = pr.spec_gen;                                      // is_initialized = false
+          tr.initialized = false;
+          if (!(hb->hSpecStatus[pr.spec] & ST_TRI_VALID)) continue;  // checkMotion / triangulation failed (:2297-2303)
+          tr.ekf_feature = true;
+          tr.initialized = true;
+          for (int k = (int)tr.obs.size() - 1; k >= 0; --k)          // anchor = the last camera used (feature.hpp:536)
+            if (tr.obs[k].sid != F.state_id && clone_index_of(F, tr.obs[k].sid) >= 0) { tr.id_anchor = tr.obs[k].sid; break; }
+          commits.push_back(CommitRec{pr.spec, fi * Fcap_ + tr.slot, tr.gen});
+        }
+        news[fi].push_back(&tr);
+        ++cell;
+        ++n_new;
+      }
+    }
     F.stats.n_candidates_lost = (int)cb.size();
-    if (cb.empty()) continue;
+    if (cb.empty() && E == 0 && news[fi].empty()) continue;
     if (F.if_zupt) {
       // :2564-2569: under ZUPT the candidates are still initialised (and the failures erased) but
       // no Jacobian is stacked and no update runs
@@ -1003,12 +1292,94 @@ int Batch::process(const double* t_img, const OrcvioFeature* feats, const int* f
     fw.active = 1;
     wA.any_active = true;
     append_candidates(wA, fi, cb, F.cinfo[0]);
+    if (hybrid_) {
+      HybWork& hw = wA.hw[fi];
+      hw.N = fw.N; hw.E = E; hw.active = 1;
+      hw.feat_begin = (int)wA.hfeats.size();
+      for (long long id : F.feature_states) {
+        const Track& tr = F.map_server.at(id);
+        HybFeat hf{};
+        hf.slot = tr.slot;
+        hf.anchor = clone_index_of(F, tr.id_anchor);
+        hf.zu = tr.obs.back().z[0];
+        hf.zv = tr.obs.back().z[1];
+        if (hf.anchor < 0) { hyb_ok = false; hf.anchor = 0; }
+        wA.hfeats.push_back(hf);
+      }
+      hw.feat_end = (int)wA.hfeats.size();
+      hw.new_begin = (int)wA.hnews.size();
+      int nd = 2 * E;
+      for (Track* trp : news[fi]) {
+        // its MSCKF rows over every observation only decide the gate (:2365-2370); they are not stacked
+        CandBuild x = make_cand(wA, F, *trp, true, 3, CAND_GATE_ONLY);
+        Cand c = x.c;
+        c.filter = fi;
+        const int r = std::max(2 * c.jac_m - 3, 0);
+        c.row_off = (int)wA.rows_total;
+        c.hblk_off = (int)wA.hblk_total;
+        wA.rows_total += (size_t)r;
+        wA.hblk_total += (size_t)r * 6 * (c.e_blk - c.s_blk + 1);
+        wA.own_wmax_blk = std::max(wA.own_wmax_blk, c.e_blk - c.s_blk + 1);
+        const int idx = (int)wA.cands.size();
+        (c.jac_m <= 8 ? wA.small_list : wA.large_list).push_back(idx);
+        wA.cands.push_back(c);
+        F.cinfo[0].push_back(CandInfo{x.id, 3});
+        HybNew hn{};
+        hn.slot = trp->slot;
+        hn.anchor = clone_index_of(F, trp->id_anchor);
+        hn.cand = idx;
+        hn.obs_off = c.jac_off;
+        hn.obs_m = c.jac_m;
+        hn.row_off = nd - 2 * E;
+        if (hn.anchor < 0) { hyb_ok = false; hn.anchor = 0; }
+        nd += 2 * (c.jac_m - 1) - 1;
+        wA.hnews.push_back(hn);
+      }
+      hw.new_end = (int)wA.hnews.size();
+      hw.dense_off = (int)wA.dense_total;
+      hw.n_dense = nd;
+      hw.arow_dense = fw.arows;
+      fw.dense_rows = nd;
+      for (int J = 0; J < SY_MAXT; ++J) fw.jrow0[J] = std::min(fw.jrow0[J], fw.arows);
+      fw.arows += nd;
+      wA.arows_total += (size_t)nd;
+      wA.dense_total += (size_t)nd;
+      wA.max_dense = std::max(wA.max_dense, nd);
+      wA.maxE = std::max(wA.maxE, E);
+    }
   }
   wA.cand_begin[B_] = (int)wA.cands.size();
+  if (hybrid_ && !commits.empty()) {
+    const CommitRec* d_rec = hb->put(commits.data(), commits.size(), stream_, &hyb_ok);
+    if (hyb_ok) {
+      launch_hybrid_commit(d_rec, (int)commits.size(), hb->dFinal, hb->dSpecPos, dFpos_, dFgen_, dFidp_, stream_);
+      ++launches_;
+    }
+  }
+  if (!hyb_ok) { ok_ = false; err_ = "hybrid bookkeeping failed (upload arena / anchor outside the window)"; return ORCVIO_ERR_CUDA; }
   cudaEvent_t* e = ev_;
   run_phase(wA, 0);
+  std::vector<Track*> gather_tracks;
+  if (hybrid_) {
+    for (int fi = 0; fi < B_; ++fi) {       // the features whose host mirror the prune phase may need
+      FilterHost& F = f_[fi];
+      F.ekf_watch.clear();
+      if (!F.active) continue;
+      F.ekf_watch = F.feature_states;
+      for (Track* trp : news[fi]) F.ekf_watch.push_back(trp->id);
+    }
+    hybrid_queue_gather(gather_tracks);
+    if (!wA.hfeats.empty()) {
+      CK(cudaMemcpyAsync(hb->hEkfPass, hb->dEkfPass, wA.hfeats.size() * sizeof(int), cudaMemcpyDeviceToHost, stream_));
+      CK(cudaMemcpyAsync(hb->hEkfGamma, hb->dEkfGamma, wA.hfeats.size() * sizeof(double), cudaMemcpyDeviceToHost, stream_));
+    }
+  }
   download_mirrors();
   CK(cudaStreamSynchronize(stream_));
+  if (hybrid_) {
+    hybrid_apply_gather(gather_tracks);
+    hb->used = 0;
+  }
   auto account = [&](bool had_update) {
     if (!profiling_) return;
     float ms = 0;
@@ -1027,16 +1398,92 @@ int Batch::process(const double* t_img, const OrcvioFeature* feats, const int* f
   wB.rows_cap = compress_qr_ ? 0 : AFORM_TILE_ROWS;
   wB.fw.assign(B_, FilterWork{});
   wB.cand_begin.assign(B_ + 1, 0);
-  std::vector<int> rm_idx(2 * (size_t)B_, -1), Nbefore(B_, 0);
+  if (hybrid_) { wB.hyb_phase = 1; wB.hw.assign(B_, HybWork{}); }
+  std::vector<int> rm_idx(2 * (size_t)B_, -1), Nbefore(B_, 0), Ebefore(B_, 0);
+  std::vector<ReanchorRec> reanchor;
+  std::vector<int> reanchor_off(B_ + 1, 0);
+  // pruneImuStateBuffer :2665-2773: an EKF-SLAM feature (of the state, or initialised and waiting outside it) whose anchor
+  // clone is about to leave the window moves to a new anchor (getNewAnchorId :3892-3950) before anything else happens
+  auto reanchor_tracks = [&](int fi, FilterHost& F, const long long* rm_ids, int n_rm) {
+    if (F.ekf_watch.empty()) return;
+    std::vector<long long> ids = F.ekf_watch;
+    std::sort(ids.begin(), ids.end());
+    auto removed = [&](long long sid) {
+      for (int q = 0; q < n_rm; ++q) if (rm_ids[q] == sid) return true;
+      return false;
+    };
+    for (long long id : ids) {
+      auto it = F.map_server.find(id);
+      if (it == F.map_server.end()) continue;
+      Track& tr = it->second;
+      if (!tr.ekf_feature || !tr.initialized || !removed(tr.id_anchor)) continue;
+      bool anchor_observed = false;
+      for (const Obs& o : tr.obs) anchor_observed |= (o.sid == tr.id_anchor);
+      if (!anchor_observed) continue;                   // `involved` holds only clones the feature was seen from
+      // getNewAnchorId: the observing clone (the two newest and the removed ones excluded) whose stored observation is
+      // closest to the reprojection of the feature; the newest clone when there is none
+      const int n = (int)F.clones.size();
+      long long new_id = F.clones.back().id;
+      if (n > 2) {
+        double min_dis = 99999.0;
+        long long best = -1;
+        for (int k = 0; k < n - 2; ++k) {
+          const long long sid = F.clones[k].id;
+          if (removed(sid)) continue;
+          const Obs* ob = nullptr;
+          for (const Obs& o : tr.obs) if (o.sid == sid) ob = &o;
+          if (!ob) continue;
+          const double* c = F.clone_mirror.data() + (size_t)k * CL_STRIDE;
+          const double d[3] = {tr.mpos[0] - c[CL_PC], tr.mpos[1] - c[CL_PC + 1], tr.mpos[2] - c[CL_PC + 2]};
+          double pn[3];
+          m3_Tvec(c + CL_RC, d, pn);
+          const double du = pn[0] / pn[2] - ob->z[0], dv = pn[1] / pn[2] - ob->z[1];
+          const double dis = std::sqrt(du * du + dv * dv);
+          if (min_dis > dis) { min_dis = dis; best = sid; }
+        }
+        if (best >= 0) new_id = best;
+      }
+      ReanchorRec rc{};
+      rc.filter = fi;
+      rc.slot = tr.slot;
+      rc.col = -1;
+      if (tr.in_state)
+        for (int i = 0; i < (int)F.feature_states.size(); ++i)
+          if (F.feature_states[i] == id) rc.col = i;
+      rc.old_idx = clone_index_of(F, tr.id_anchor);
+      rc.new_idx = clone_index_of(F, new_id);
+      if (!tr.in_state) {
+        // :2762-2764: obs_anchor <- the stored observation in the new anchor (operator[] default-constructs it)
+        const Obs* ob = nullptr;
+        for (const Obs& o : tr.obs) if (o.sid == new_id) ob = &o;
+        if (!ob) {
+          Obs z{};
+          z.sid = new_id;
+          auto pos = std::lower_bound(tr.obs.begin(), tr.obs.end(), new_id,
+                                      [](const Obs& o, long long sid) { return o.sid < sid; });
+          ob = &*tr.obs.insert(pos, z);
+        }
+        rc.zu = ob->z[0];
+        rc.zv = ob->z[1];
+      } else {
+        F.log_reanchor.push_back(id);
+        F.log_reanchor.push_back(tr.id_anchor);
+        F.log_reanchor.push_back(new_id);
+      }
+      tr.id_anchor = new_id;
+      reanchor.push_back(rc);
+    }
+  };
   for (int fi = 0; fi < B_; ++fi) {
     FilterHost& F = f_[fi];
     wB.cand_begin[fi] = (int)wB.cands.size();
+    reanchor_off[fi] = (int)reanchor.size();
     FilterWork& fw = wB.fw[fi];
     fw.N = (int)F.clones.size();
-    fw.D = L + 6 * fw.N;
+    fw.D = L + 6 * fw.N + (int)F.feature_states.size();
     fw.active = 0;
     Nbefore[fi] = fw.N;
-    if (!F.active) continue;
+    if (!F.active) { Ebefore[fi] = (int)F.feature_states.size(); continue; }
     std::memcpy(F.imu_mirror.data(), hImu_ + (size_t)fi * IM_STRIDE, IM_STRIDE * sizeof(double));
     std::memcpy(F.clone_mirror.data(), hClones_ + (size_t)fi * Ncap_ * CL_STRIDE,
                 (size_t)Ncap_ * CL_STRIDE * sizeof(double));
@@ -1047,6 +1494,20 @@ int Batch::process(const double* t_img, const OrcvioFeature* feats, const int* f
       const CandInfo& ci = F.cinfo[0][c - c0];
       F.cstatus[0].push_back(st);
       F.cgamma[0].push_back(hGamma_[c]);
+      if (ci.kind == 3) {
+        // candidate EKF-SLAM feature: in the state iff its MSCKF rows passed the gate (:2371-2411); a rejected one
+        // keeps its inverse-depth record and waits outside the state
+        const bool pass = (st & ST_GATE_PASS) != 0;
+        F.log_new_ids.push_back(ci.id);
+        F.log_new_ok.push_back(pass ? 1 : 0);
+        F.log_new_gamma.push_back(hGamma_[c]);
+        if (pass) {
+          F.map_server.at(ci.id).in_state = true;
+          F.feature_states.push_back(ci.id);
+          ++feature_updates_;
+        }
+        continue;
+      }
       if (!(st & ST_TRI_VALID)) F.stats.n_tri_invalid_lost++;
       if (st & ST_GATE_PASS) { F.stats.n_gate_pass_lost++; ++feature_updates_; }
       // lost features are always erased (:2572-2576); tracked-long ones only when they were
@@ -1059,23 +1520,53 @@ int Batch::process(const double* t_img, const OrcvioFeature* feats, const int* f
         }
       }
     }
+    if (hybrid_ && wA.hw[fi].active) {
+      const HybWork& hw = wA.hw[fi];
+      for (int i = 0; i < hw.E; ++i) {
+        F.log_ekf_ids.push_back(F.feature_states[i]);
+        F.log_ekf_pass.push_back(hb->hEkfPass[hw.feat_begin + i]);
+        F.log_ekf_gamma.push_back(hb->hEkfGamma[hw.feat_begin + i]);
+        if (hb->hEkfPass[hw.feat_begin + i]) ++feature_updates_;
+      }
+    }
+    fw.D = L + 6 * fw.N + (int)F.feature_states.size();
+    Ebefore[fi] = (int)F.feature_states.size();
+    wB.maxE = std::max(wB.maxE, Ebefore[fi]);
+    auto fill_hw = [&]() {              // features of the state with their (possibly new) anchors
+      if (!hybrid_) return;
+      HybWork& hw = wB.hw[fi];
+      hw.N = fw.N; hw.E = Ebefore[fi]; hw.active = fw.active;
+      hw.feat_begin = (int)wB.hfeats.size();
+      for (long long id : F.feature_states) {
+        const Track& tr = F.map_server.at(id);
+        HybFeat hf{};
+        hf.slot = tr.slot;
+        hf.anchor = clone_index_of(F, tr.id_anchor);
+        if (hf.anchor < 0) { hyb_ok = false; hf.anchor = 0; }
+        wB.hfeats.push_back(hf);
+      }
+      hw.feat_end = (int)wB.hfeats.size();
+      hw.new_begin = hw.new_end = 0;
+    };
     // pruneImuStateBuffer :2629-2959
     if (F.if_zupt) {
       // :2633-2639: a stationary frame drops the previous clone (id - 1) and uses nothing
       const int n = (int)F.clones.size();
-      if (n < 2) continue;
+      if (n < 2) { fill_hw(); continue; }
       rm_idx[2 * fi] = n - 2;
       const long long rm_id = F.clones[n - 2].id;
       F.stats.n_removed_clones = 1;
       F.stats.removed_ids[0] = rm_id;
+      if (hybrid_) reanchor_tracks(fi, F, &rm_id, 1);
       for (auto& kv : F.map_server) {
         Track& tr = kv.second;
         tr.obs.erase(std::remove_if(tr.obs.begin(), tr.obs.end(), [&](const Obs& o) { return o.sid == rm_id; }),
                      tr.obs.end());
       }
+      fill_hw();
       continue;
     }
-    if ((int)F.clones.size() < p_.sw_size) continue;
+    if ((int)F.clones.size() < p_.sw_size) { fill_hw(); continue; }
     wB.maxN = std::max(wB.maxN, fw.N);
     // findRedundantImuStates :2582-2626
     const int n = (int)F.clones.size();
@@ -1107,12 +1598,12 @@ int Batch::process(const double* t_img, const OrcvioFeature* feats, const int* f
     F.stats.removed_ids[0] = rm_id0;
     F.stats.removed_ids[1] = rm_id1;
     const long long cur = F.state_id;
+    if (hybrid_) {
+      const long long rms[2] = {rm_id0, rm_id1};
+      reanchor_tracks(fi, F, rms, 2);
+    }
     std::vector<CandBuild> cb;
-    auto clone_index = [&](long long sid) {
-      for (int k = (int)F.clones.size() - 1; k >= 0; --k)
-        if (F.clones[k].id == sid) return k;
-      return -1;
-    };
+    auto clone_index = [&](long long sid) { return clone_index_of(F, sid); };
     for (auto& kv : F.map_server) {
       Track& tr = kv.second;
       int inv0 = -1, inv1 = -1;
@@ -1121,7 +1612,8 @@ int Batch::process(const double* t_img, const OrcvioFeature* feats, const int* f
         if (tr.obs[k].sid == rm_id1) inv1 = k;
       }
       if (inv0 < 0 && inv1 < 0) continue;
-      if (inv0 >= 0 && inv1 >= 0) {
+      // (:2776: EKF-SLAM features never contribute MSCKF rows here)
+      if (inv0 >= 0 && inv1 >= 0 && !tr.in_state && !tr.ekf_feature) {
         const int nobs = (int)tr.obs.size();
         const bool tracked = tr.obs.back().sid == cur;
         CandBuild x{};
@@ -1165,11 +1657,25 @@ int Batch::process(const double* t_img, const OrcvioFeature* feats, const int* f
       wB.any_active = true;
       append_candidates(wB, fi, cb, F.cinfo[1]);
     }
+    fill_hw();
   }
   wB.cand_begin[B_] = (int)wB.cands.size();
+  reanchor_off[B_] = (int)reanchor.size();
   wB.extra_ints = rm_idx;
   wB.extra_ints.insert(wB.extra_ints.end(), Nbefore.begin(), Nbefore.end());
-  run_phase(wB, 1);
+  wB.extra_ints.insert(wB.extra_ints.end(), Ebefore.begin(), Ebefore.end());
+  if (!hyb_ok) { ok_ = false; err_ = "hybrid bookkeeping failed (anchor outside the window)"; return ORCVIO_ERR_CUDA; }
+  stage_phase(wB);
+  if (hybrid_ && !reanchor.empty()) {
+    const ReanchorRec* d_rec = hb->put(reanchor.data(), reanchor.size(), stream_, &hyb_ok);
+    const int* d_off = hb->put(reanchor_off.data(), reanchor_off.size(), stream_, &hyb_ok);
+    if (hyb_ok) {
+      launch_reanchor(d_rec, d_off, B_, wB.dHw, dClones_, (size_t)Ncap_ * CL_STRIDE, dImu_, dFpos_, dFidp_, Fcap_, dP_,
+                      (size_t)ldp_ * ldp_, ldp_, stream_);
+      ++launches_;
+    }
+  }
+  launch_phase(wB, true);
   // remove the pruned clones from P / clone array (:2875-2956)
   bool any_rm = false;
   for (int v : rm_idx) any_rm |= (v >= 0);
@@ -1178,11 +1684,17 @@ int Batch::process(const double* t_img, const OrcvioFeature* feats, const int* f
     ra.P = dP_; ra.p_stride = (size_t)ldp_ * ldp_; ra.ldp = ldp_;
     ra.clones = dClones_; ra.clone_stride = (size_t)Ncap_ * CL_STRIDE;
     ra.rm = wB.d_extra; ra.N = wB.d_extra + 2 * B_; ra.n_filters = B_;
+    ra.E = hybrid_ ? wB.d_extra + 3 * B_ : nullptr;
     launch_remove(ra, stream_);
     ++launches_;
   }
+  if (hybrid_) hybrid_queue_gather(gather_tracks);
   download_mirrors();
   CK(cudaStreamSynchronize(stream_));
+  if (hybrid_) {
+    hybrid_apply_gather(gather_tracks);
+    if (!hyb_ok) { ok_ = false; err_ = "hybrid upload arena exhausted"; }
+  }
   account(wB.any_active);
   int herr = 0;
   CK(cudaMemcpy(&herr, dErr_, sizeof(int), cudaMemcpyDeviceToHost));
@@ -1218,6 +1730,68 @@ int Batch::process(const double* t_img, const OrcvioFeature* feats, const int* f
   return ok_ ? ORCVIO_OK : ORCVIO_ERR_CUDA;
 }
 
+void Batch::hybrid_queue_gather(std::vector<Track*>& tracks) {
+  tracks.clear();
+  HybridBufs& hb = *hyb_;
+  std::vector<int> filt, slots;
+  for (int fi = 0; fi < B_; ++fi) {
+    FilterHost& F = f_[fi];
+    if (!F.active) continue;
+    for (long long id : F.ekf_watch) {
+      auto it = F.map_server.find(id);
+      if (it == F.map_server.end()) continue;
+      tracks.push_back(&it->second);
+      filt.push_back(fi);
+      slots.push_back(it->second.slot);
+    }
+  }
+  const size_t n = tracks.size();
+  if (n == 0) return;
+  if (n > hb.gather_cap) {             // (the previous gather was consumed behind a synchronisation)
+    cudaFree(hb.dGather);
+    cudaFreeHost(hb.hGather);
+    hb.gather_cap = n * 2;
+    CK(cudaMalloc(&hb.dGather, hb.gather_cap * 6 * sizeof(double)));
+    CK(cudaMallocHost(&hb.hGather, hb.gather_cap * 6 * sizeof(double)));
+  }
+  bool okp = true;
+  const int* d_f = hb.put(filt.data(), n, stream_, &okp);
+  const int* d_s = hb.put(slots.data(), n, stream_, &okp);
+  if (!okp) { ok_ = false; err_ = "hybrid upload arena exhausted"; tracks.clear(); return; }
+  launch_hybrid_gather(d_f, d_s, (int)n, dFpos_, dFidp_, Fcap_, hb.dGather, stream_);
+  ++launches_;
+  CK(cudaMemcpyAsync(hb.hGather, hb.dGather, n * 6 * sizeof(double), cudaMemcpyDeviceToHost, stream_));
+}
+
+void Batch::hybrid_apply_gather(const std::vector<Track*>& tracks) {
+  const double* g = hyb_->hGather;
+  for (size_t k = 0; k < tracks.size(); ++k) {
+    Track& tr = *tracks[k];
+    for (int q = 0; q < 3; ++q) tr.mpos[q] = g[6 * k + q];
+    tr.minv = g[6 * k + 3];
+    tr.mobs[0] = g[6 * k + 4];
+    tr.mobs[1] = g[6 * k + 5];
+  }
+}
+
+int Batch::get_feature_states(int i, long long* ids, long long* anchors, double* inv_depth, double* obs_anchor,
+                              double* xyz, int cap) {
+  if (i < 0 || i >= B_) return ORCVIO_ERR_ARG;
+  FilterHost& F = f_[i];
+  int n = 0;
+  for (long long id : F.feature_states) {
+    if (n >= cap) break;
+    const Track& tr = F.map_server.at(id);
+    if (ids) ids[n] = id;
+    if (anchors) anchors[n] = tr.id_anchor;
+    if (inv_depth) inv_depth[n] = tr.minv;
+    if (obs_anchor) { obs_anchor[2 * n] = tr.mobs[0]; obs_anchor[2 * n + 1] = tr.mobs[1]; }
+    if (xyz) for (int q = 0; q < 3; ++q) xyz[3 * n + q] = tr.mpos[q];
+    ++n;
+  }
+  return n;
+}
+
 int Batch::get_state(int i, OrcvioState* out) {
   if (i < 0 || i >= B_) return ORCVIO_ERR_ARG;
   FilterHost& F = f_[i];
@@ -1233,7 +1807,7 @@ int Batch::get_state(int i, OrcvioState* out) {
     out->ba[k] = im[IM_BA + k];
   }
   out->n_clones = (int)F.clones.size();
-  out->dim = ORCVIO_LEG + 6 * out->n_clones;
+  out->dim = ORCVIO_LEG + 6 * out->n_clones + (int)F.feature_states.size();
   out->n_map_features = (int)F.map_server.size();
   double c9[81];
   CK(cudaMemcpy2D(c9, 9 * sizeof(double), dP_ + (size_t)i * ldp_ * ldp_, ldp_ * sizeof(double),
@@ -1252,7 +1826,7 @@ int Batch::get_state(int i, OrcvioState* out) {
 
 int Batch::get_cov(int i, double* P, int cap, int* D) {
   if (i < 0 || i >= B_) return ORCVIO_ERR_ARG;
-  const int d = ORCVIO_LEG + 6 * (int)f_[i].clones.size();
+  const int d = ORCVIO_LEG + 6 * (int)f_[i].clones.size() + (int)f_[i].feature_states.size();
   if (D) *D = d;
   if (!P) return ORCVIO_OK;
   if (cap < d * d) return ORCVIO_ERR_ARG;

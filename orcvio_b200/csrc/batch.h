@@ -27,6 +27,11 @@ struct Track {        // struct Feature, reference include/orcvio/feat/feature.h
   int slot = -1;
   long long gen = 0;
   std::vector<Obs> obs;     // ascending sid (std::map order in the reference)
+  // hybrid mode (feature.hpp:243-264): the idp record itself lives on the device (slot), these are its host twins
+  bool in_state = false, ekf_feature = false;
+  bool initialized = false; // host twin of "fgen[slot] == gen" (only maintained in hybrid mode)
+  long long id_anchor = -1;
+  double mpos[3] = {0, 0, 0}, minv = 0, mobs[2] = {0, 0};   // mirror: world position, inverse depth, obs_anchor
 };
 
 struct CloneMeta {
@@ -65,6 +70,15 @@ struct FilterHost {
   std::vector<CandInfo> cinfo[2];      // phase 0 (lost) / 1 (prune)
   std::vector<int> cstatus[2];
   std::vector<double> cgamma[2];
+  // hybrid MSCKF / EKF-SLAM mode (state_server.feature_states, grid_map, last_ZUPT_time)
+  std::vector<long long> feature_states;
+  std::vector<long long> ekf_watch;     // features of the state + rejected new ones: the tracks with a host mirror
+  double last_zupt_time = 0.0;
+  // per-frame log of the EKF branches (test / diagnostics surface: orcvio_get_hybrid_log)
+  std::vector<long long> log_ekf_lost, log_ekf_ids, log_new_ids;
+  std::vector<int> log_ekf_pass, log_new_ok;
+  std::vector<double> log_ekf_gamma, log_new_gamma;
+  std::vector<long long> log_reanchor;  // triples: feature id, old anchor state id, new anchor state id
   // object-update test hooks (include/orcvio/orcvio.h:101-119)
   int leg_dim_override = -1;
   int num_clone_override = -1;
@@ -127,6 +141,9 @@ class Batch {
   int set_cov(int i, const double* P, int D);
   // getMSCKFMapPointPositions: world positions of the map-server features (NaN = not initialised)
   int get_map_points(int i, long long* ids, double* xyz, int cap);
+  // state_server.feature_states in state order: id, anchor state id, inverse depth, obs_anchor (2), world position (3)
+  int get_feature_states(int i, long long* ids, long long* anchors, double* inv_depth, double* obs_anchor, double* xyz,
+                         int cap);
   FilterHost& filter(int i) { return f_[i]; }
   const Params& params() const { return p_; }
   long long feature_updates() const { return feature_updates_; }
@@ -199,6 +216,12 @@ class Batch {
   std::string err_;
   Params p_;
   int B_ = 0, Ncap_ = 0, ldp_ = 0, Fcap_ = 0, ldr_ = 0, ldt_ = 0;
+  int Emax_ = 0, nmax_ = 0;            // EKF-SLAM feature states (hybrid mode); window columns 6 Ncap + Emax
+  bool hybrid_ = false;
+  double* dFidp_ = nullptr;            // inverse-depth records by feature slot
+  struct HybridBufs;
+  struct HybridDeleter { void operator()(HybridBufs* p) const; };
+  std::unique_ptr<HybridBufs, HybridDeleter> hyb_;
   int flags_ = 0;
   std::vector<FilterHost> f_;
   cudaStream_t stream_ = nullptr, stream2_ = nullptr;
@@ -264,6 +287,10 @@ class Batch {
   void stage_upload(PhaseWork& w);
   void launch_phase(PhaseWork& w, bool download, bool prior_in_flight = false);
   UpdArgs upd_args(const FilterWork* dFw) const;
+  HybArgs hyb_args(const PhaseWork& w) const;
+  // host mirror (position, inverse depth, obs_anchor) of the EKF-SLAM features of every filter: queued on the stream
+  void hybrid_queue_gather(std::vector<Track*>& out_tracks);
+  void hybrid_apply_gather(const std::vector<Track*>& tracks);
   struct SnapState;
   struct SnapDeleter { void operator()(SnapState* p) const; };
   std::unique_ptr<SnapState, SnapDeleter> snap_;

@@ -31,8 +31,12 @@ bool check_supported(const Params& p, std::string& why) {
   if (p.calib_imu) why = "calib_imu_instrinsic=1 (LEG_DIM 46) is not supported";
   else if (p.estimate_extrin || p.estimate_td) why = "estimate_extrin / estimate_td are not supported";
   else if (p.if_FEJ) why = "if_FEJ=1 is not supported";
-  else if (p.max_features * p.grid_rows * p.grid_cols != 0)
-    why = "hybrid EKF-SLAM features (max_features_in_one_grid > 0) are not supported yet";
+  else if (p.max_features * p.grid_rows * p.grid_cols != 0 && p.feature_idp_dim != 1)
+    why = "hybrid EKF-SLAM features with feature_idp_dim = 3 are not supported (every shipped yaml uses 1)";
+  else if (p.max_features * p.grid_rows * p.grid_cols > 64)
+    why = "more than 64 EKF-SLAM feature states are not supported";
+  else if (ORCVIO_LEG + 6 * p.sw_size + p.max_features * p.grid_rows * p.grid_cols > 232)
+    why = "state dimension 22 + 6 sw_size + features exceeds 232 (the one-CTA factorisations hold the matrix on chip)";
   else if (!p.use_larvio_flag && !p.use_closed_form_cov_prop_flag)
     why = "Euler covariance propagation is dimensionally inconsistent in the reference and unsupported";
   else if (p.use_schmidt) why = "use_schmidt=1 is not supported";
@@ -166,6 +170,34 @@ int orcvio_get_map_points(orcvio_handle* h, long long* ids, double* xyz, int cap
   return h->b.batch->get_map_points(0, ids, xyz, cap);
 }
 
+int orcvio_get_feature_states(orcvio_handle* h, long long* ids, long long* anchor_ids, double* inv_depth,
+                              double* obs_anchor, double* xyz, int cap) {
+  if (!h || !h->initialized) return ORCVIO_ERR_ARG;
+  return h->b.batch->get_feature_states(0, ids, anchor_ids, inv_depth, obs_anchor, xyz, cap);
+}
+
+int orcvio_get_hybrid_log(orcvio_handle* h, int what, long long* ids, int* flags, double* gamma, int cap) {
+  if (!h || !h->initialized) return ORCVIO_ERR_ARG;
+  FilterHost& F = h->b.batch->filter(0);
+  const std::vector<long long>* v = nullptr;
+  const std::vector<int>* fl = nullptr;
+  const std::vector<double>* g = nullptr;
+  switch (what) {
+    case 0: v = &F.log_ekf_lost; break;
+    case 1: v = &F.log_ekf_ids; fl = &F.log_ekf_pass; g = &F.log_ekf_gamma; break;
+    case 2: v = &F.log_new_ids; fl = &F.log_new_ok; g = &F.log_new_gamma; break;
+    case 3: v = &F.log_reanchor; break;
+    default: return ORCVIO_ERR_ARG;
+  }
+  const int n = (int)std::min<size_t>(v->size(), (size_t)std::max(cap, 0));
+  for (int k = 0; k < n; ++k) {
+    if (ids) ids[k] = (*v)[k];
+    if (flags) flags[k] = fl ? (*fl)[k] : 0;
+    if (gamma) gamma[k] = g ? (*g)[k] : 0.0;
+  }
+  return n;
+}
+
 int orcvio_get_frame_stats(orcvio_handle* h, OrcvioFrameStats* out) {
   if (!h || !h->initialized || !out) return ORCVIO_ERR_ARG;
   *out = h->b.batch->filter(0).stats;
@@ -179,6 +211,7 @@ int orcvio_get_candidate_log(orcvio_handle* h, long long* ids, int* phase, int* 
   int n = 0;
   for (int ph = 0; ph < 2; ++ph)
     for (size_t k = 0; k < F.cinfo[ph].size() && k < F.cstatus[ph].size(); ++k) {
+      if (F.cinfo[ph][k].kind == 3) continue;      // candidate EKF-SLAM features: orcvio_get_hybrid_log
       if (n >= cap) return n;
       if (ids) ids[n] = F.cinfo[ph][k].id;
       if (phase) phase[n] = ph;

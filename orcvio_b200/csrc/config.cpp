@@ -179,6 +179,23 @@ bool load_params(const std::string& path, Params& p, std::string& err) {
   p.grid_cols = (int)num(y, "aug_grid_cols");
   p.max_features = (int)num(y, "max_features_in_one_grid");
   if (p.max_features < 0) p.max_features = 0;
+  {
+    const double fx = num(y, "intrinsics.fx"), fy = num(y, "intrinsics.fy"), cx = num(y, "intrinsics.cx"),
+                 cy = num(y, "intrinsics.cy");
+    const int U = (int)num(y, "resolution_width"), V = (int)num(y, "resolution_height");
+    if (fx != 0 && fy != 0) {
+      p.x_min = -cx / fx;
+      p.y_min = -cy / fy;
+      const double x_max = (U - cx) / fx, y_max = (V - cy) / fy;
+      if (p.grid_rows * p.grid_cols != 0) {
+        p.grid_width = (x_max - p.x_min) / p.grid_cols;
+        p.grid_height = (y_max - p.y_min) / p.grid_rows;
+      } else {
+        p.grid_width = x_max - p.x_min;
+        p.grid_height = y_max - p.y_min;
+      }
+    }
+  }
   p.feature_idp_dim = (int)num(y, "feature_idp_dim");
   if (p.feature_idp_dim != 1 && p.feature_idp_dim != 3) p.feature_idp_dim = 3;
   p.use_schmidt = (int)num(y, "use_schmidt") != 0;

@@ -34,6 +34,8 @@ struct Params {
   double zupt_max_feature_dis = 2e-3;
   int use_object_residual_update_cam_pose_flag = 0;
   int grid_rows = 0, grid_cols = 0, max_features = 0, feature_idp_dim = 1;
+  // boundary of the normalised image plane and the cell size of the EKF-feature grid (src/orcvio.cpp:293-311)
+  double x_min = 0, y_min = 0, grid_width = 1, grid_height = 1;
   bool use_schmidt = false;
   double chi_square_threshold_feat = 0.95;
   std::string output_dir;

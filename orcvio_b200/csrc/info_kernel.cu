@@ -279,7 +279,10 @@ __global__ void __launch_bounds__(256) k_syrk(UpdArgs a, const double* __restric
     int rows = 0;
     if (fw.active) {
       if (tiles == nullptr) rows = fw.arows;             // dense (object) update: every row counts
-      else for (int t = fw.tile_begin; t < fw.tile_end; ++t) rows += tile_rows[t];
+      else {
+        for (int t = fw.tile_begin; t < fw.tile_end; ++t) rows += tile_rows[t];
+        rows += fw.dense_rows;                           // hybrid mode: rows of the EKF-SLAM features
+      }
     }
     filter_rows[fi] = rows;
   }
@@ -625,9 +628,10 @@ static void info_attrs() {
   static bool attr = false;
   if (attr) return;
   cudaFuncSetAttribute(k_aform, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024);
-  cudaFuncSetAttribute(k_chol_prior, cudaFuncAttributeMaxDynamicSharedMemorySize, 193 * 1024);
-  cudaFuncSetAttribute(k_chol_w_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, 193 * 1024);
-  cudaFuncSetAttribute(k_pinfo, cudaFuncAttributeMaxDynamicSharedMemorySize, 140 * 1024);
+  // hybrid states (30 clones + 30 features: D = 232) need 221 KB of tiles: everything the SM has
+  cudaFuncSetAttribute(k_chol_prior, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024);
+  cudaFuncSetAttribute(k_chol_w_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024);
+  cudaFuncSetAttribute(k_pinfo, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
   check_launch("info attributes");
   attr = true;
 }
@@ -679,8 +683,8 @@ void launch_info_dense_apply(const UpdArgs& u, const InfoBufs& ib, int n, cudaSt
 // (and, in the end-to-end call, the host's work-list build).  `fork` was recorded on the main stream
 // once P was in place; `join` is what the main stream waits for before k_aform.
 void launch_info_prior(const UpdArgs& u, const InfoBufs& ib, int max_N, cudaStream_t s2, cudaEvent_t fork,
-                       cudaEvent_t join, cudaEvent_t t0, cudaEvent_t t1) {
-  const int Dmax = ORCVIO_LEG + 6 * max_N;
+                       cudaEvent_t join, cudaEvent_t t0, cudaEvent_t t1, int max_E) {
+  const int Dmax = ORCVIO_LEG + 6 * max_N + max_E;
   info_attrs();
   cudaStreamWaitEvent(s2, fork, 0);
   if (t0) cudaEventRecord(t0, s2);
@@ -694,11 +698,12 @@ void launch_info_prior(const UpdArgs& u, const InfoBufs& ib, int max_N, cudaStre
 void launch_info_update(const QrArgs& q, const UpdArgs& u, const InfoBufs& ib, int n_tiles, int max_tile_rows,
                         int max_w_blk, int max_N, cudaStream_t s, cudaStream_t s2, cudaEvent_t fork,
                         cudaEvent_t join, cudaEvent_t mid1, cudaEvent_t mid2, int* launches, bool prior_in_flight,
-                        cudaEvent_t mid_syrk, cudaEvent_t prior_t0, cudaEvent_t prior_t1) {
-  const int nmax = 6 * max_N, Dmax = ORCVIO_LEG + nmax;
+                        cudaEvent_t mid_syrk, cudaEvent_t prior_t0, cudaEvent_t prior_t1, int max_E,
+                        const HybArgs* hyb, int max_dense) {
+  const int nmax = 6 * max_N + max_E, Dmax = ORCVIO_LEG + nmax;
   const int B = u.n_filters;
   info_attrs();
-  if (!prior_in_flight) launch_info_prior(u, ib, max_N, s2, fork, join, prior_t0, prior_t1);
+  if (!prior_in_flight) launch_info_prior(u, ib, max_N, s2, fork, join, prior_t0, prior_t1, max_E);
   cudaStreamWaitEvent(s, join, 0);
   const int lda = u.ldr;
   if (n_tiles > 0) {
@@ -707,6 +712,10 @@ void launch_info_update(const QrArgs& q, const UpdArgs& u, const InfoBufs& ib, i
     launch_pdl(k_aform, dim3(n_tiles), dim3(AF_THREADS), (size_t)rows8 * wp * sizeof(double), s, q, u.T, u.t_stride,
                u.ldt, ib.Amat, lda, ib.tile_rows);
     check_launch("k_aform");
+  }
+  if (hyb && max_dense > 0) {      // hybrid mode: the dense rows of the EKF-SLAM features, behind the tiles' rows
+    launch_hybrid_aform(*hyb, u.T, u.t_stride, u.ldt, ib.Amat, lda, u.fw, max_dense, s);
+    if (launches) *launches += 1;
   }
   if (mid1) cudaEventRecord(mid1, s);
   launch_syrk(u, ib, B, q.tiles, s);

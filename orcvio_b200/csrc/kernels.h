@@ -24,6 +24,7 @@ constexpr int IM_R = 0, IM_V = 9, IM_P = 12, IM_BG = 15, IM_BA = 18, IM_RBC = 21
               IM_AOLD = 53, IM_DISCARDS = 56, IM_STRIDE = 64;
 
 constexpr int FP_STRIDE = 4;     // feature position slot: x, y, z, pad
+constexpr int FI_STRIDE = 4;     // inverse-depth record of a slot (hybrid mode): inv depth, obs_anchor x, y, pad
 
 // filter flags
 constexpr int FL_LARVIO = 1, FL_LEFT = 2, FL_DISCARD_LARGE = 4;
@@ -32,6 +33,7 @@ constexpr int FL_LARVIO = 1, FL_LEFT = 2, FL_DISCARD_LARGE = 4;
 constexpr int ST_TRI_VALID = 1, ST_GATE_PASS = 2;
 // candidate flags
 constexpr int CAND_FORCE_TRI = 1;
+constexpr int CAND_GATE_ONLY = 2;   // new EKF-SLAM feature: MSCKF rows only decide its gate (src/orcvio.cpp:2365-2370)
 
 struct TriCfg {                  // Feature::OptimizationConfig, feature.hpp:41-63
   double translation_threshold, huber_epsilon, estimation_precision, initial_damping;
@@ -61,6 +63,8 @@ struct TriArgs {
   const int* obs_clone; const double* obs_z;
   TriCfg cfg;
   int* status; int* iters; double* cost;
+  double* final_pos;             // optional, 3 per candidate: the solution in the last camera used (the anchor frame of
+                                 // initializeInvParamPosition, feature.hpp:536-547)
   // direct mode (end-to-end frame call): when feat_off != nullptr the kernel runs over the caller's features in
   // their own order (candidate c == feature c, slot c, forced triangulation) without any Cand record, so it can
   // start while the host still sorts the candidates and builds the tiles; status is then indexed by feature
@@ -106,6 +110,7 @@ struct FilterWork {              // per filter, per update
   int arow0, arows;              // rows of this filter in the stacked A matrix (upper bound)
   int jrow0[4];                  // staircase of A: first row (relative to arow0) with a structural non-zero in
                                  // column tile J (64 columns) of A; rows above it are skipped by k_syrk
+  int dense_rows;                // dense rows behind the tiles' rows (hybrid mode: rows of the EKF-SLAM features)
 };
 
 struct QrArgs {
@@ -161,6 +166,7 @@ struct AugArgs {
   double* P; size_t p_stride; int ldp;
   const double* imu; double* clones; size_t clone_stride;
   const int* N; int n_filters;                           // N = clones BEFORE augmentation
+  const int* E;                                          // EKF-SLAM feature states behind the clones (nullptr: none)
 };
 
 struct RemoveArgs {
@@ -169,6 +175,7 @@ struct RemoveArgs {
   const int* N;                                          // clones before removal
   const int* rm;                                         // 2 per filter, ascending, -1 = none
   int n_filters;
+  const int* E;                                          // EKF-SLAM feature states behind the clones (nullptr: none)
 };
 
 // Zero-velocity update (zupt_kernel.cu): checkZUPTIMU + measurementUpdate_ZUPT_vpq, src/orcvio.cpp:3129-3454
@@ -185,6 +192,70 @@ struct ZuptArgs {
   int n_filters; int flags;
   double noise_v, noise_p, noise_q;                      // zupt_noise_{v,p,q}^2
 };
+
+// ---------------------------------------------------------------- hybrid MSCKF / EKF-SLAM mode (hybrid_kernel.cu)
+// Features of the state (1-D inverse depth in an anchor clone, src/orcvio.cpp:1356-1651) and candidates for it.
+struct HybFeat {                 // feature i of the state (column 22 + 6N + i), in state order; all are tracked now
+  int slot, anchor;              // feature slot; clone index of the anchor
+  double zu, zv;                 // its observation in the newest clone
+};
+struct HybNew {                  // candidate new EKF-SLAM feature (tracked long, its grid cell has room)
+  int slot, anchor;
+  int cand;                      // its gate-only MSCKF candidate (status decides whether it enters the state)
+  int obs_off, obs_m;            // all of its observations in the observation pool
+  int row_off;                   // first of its 2 (m - 1) - 1 dense rows (relative to the filter's dense rows)
+};
+struct HybWork {                 // per filter and frame
+  int N, E;                      // clones; feature states before this frame's new ones
+  int feat_begin, feat_end;      // HybFeat range (E entries)
+  int new_begin, new_end;        // HybNew range
+  int dense_off;                 // first dense row of this filter in the dense-row buffer
+  int n_dense;                   // dense rows reserved: 2 E + sum over new candidates
+  int arow_dense;                // row of the stacked A matrix where the dense rows go (relative to the filter's rows)
+  int active;
+};
+struct HybArgs {
+  const HybWork* hw; int n_filters;
+  const HybFeat* feats; const HybNew* news;
+  const double* clones; size_t clone_stride; const double* imu;
+  double* fpos; double* fidp; int fcap;
+  double* P; size_t p_stride; int ldp;
+  const int* obs_clone; const double* obs_z;
+  const int* status;             // candidate status (gate of the new candidates)
+  double sigma2; double chi2_dof2;
+  double* Hd; int ldh;           // dense rows [n | r] (window columns 22.., residual in column n = D - 22)
+  double* H1; double* h2; double* r1; int new_cap;   // initialisation rows of the survivors, per filter new_cap
+  double* scratch;               // unreflected rows of one new candidate at a time, per filter 64 x ldh
+  int* ekf_pass; double* ekf_gamma;                  // per HybFeat
+  int* new_ok;                                       // per HybNew: 1 = entered the state
+  int* n_new;                                        // per filter: survivors
+  const double* dx; int lddx;
+};
+void launch_hybrid_rows(const HybArgs& a, cudaStream_t s);
+void launch_hybrid_aform(const HybArgs& a, const double* FT, size_t t_stride, int ldt, double* Amat, int lda,
+                         const FilterWork* fw, int max_dense, cudaStream_t s);
+void launch_hybrid_post(const HybArgs& a, cudaStream_t s);   // feature increments + delayed initialisation
+// features only: invDepth += dx, world positions (after measurementUpdate_msckf of the prune phase)
+void launch_hybrid_feature_increment(const HybArgs& a, cudaStream_t s);
+// initializeInvParamPosition took the branch: the speculative solution of candidate `cand` becomes the position of
+// slot (= filter * fcap + slot), serial gen; idp record <- its anchor-frame solution
+struct CommitRec { int cand, slot; long long gen; };
+void launch_hybrid_commit(const CommitRec* recs, int n, const double* final_pos, const double* spec_pos, double* fpos,
+                          long long* fgen, double* fidp, cudaStream_t s);
+// P <- P[keep, keep]: newidx (per filter ldp ints) maps an old state index to its new one, -1 = dropped
+void launch_compact_cov(double* P, size_t p_stride, int ldp, const int* newidx, const int* D_old, int n_filters,
+                        cudaStream_t s);
+struct ReanchorRec {             // anchor change of one feature (src/orcvio.cpp:2665-2773, 3611-3773)
+  int filter, slot, col;         // col >= 0: feature of the state (covariance row / column replaced); -1: outside
+  int old_idx, new_idx;          // clone indices
+  double zu, zv;                 // col < 0: the stored observation in the new anchor becomes obs_anchor
+};
+void launch_reanchor(const ReanchorRec* recs, const int* rec_off, int n_filters, const HybWork* hw,
+                     const double* clones, size_t clone_stride, const double* imu, const double* fpos, double* fidp,
+                     int fcap, double* P, size_t p_stride, int ldp, cudaStream_t s);
+// host mirror of the EKF features: out[6 k ..] = position (3), inv depth, obs_anchor (2) of slots[k]
+void launch_hybrid_gather(const int* filt, const int* slots, int n, const double* fpos, const double* fidp, int fcap,
+                          double* out, cudaStream_t s);
 
 // Records (and prints) a launch-configuration error; Batch polls launch_error_count().
 void check_launch(const char* name);
@@ -227,9 +298,10 @@ void launch_info_update(const QrArgs& q, const UpdArgs& u, const InfoBufs& ib, i
                         int max_w_blk, int max_N, cudaStream_t s, cudaStream_t s2, cudaEvent_t fork,
                         cudaEvent_t join, cudaEvent_t mid1, cudaEvent_t mid2, int* launches,
                         bool prior_in_flight = false, cudaEvent_t mid_syrk = nullptr, cudaEvent_t prior_t0 = nullptr,
-                        cudaEvent_t prior_t1 = nullptr);
+                        cudaEvent_t prior_t1 = nullptr, int max_E = 0, const struct HybArgs* hyb = nullptr,
+                        int max_dense = 0);
 void launch_info_prior(const UpdArgs& u, const InfoBufs& ib, int max_N, cudaStream_t s2, cudaEvent_t fork,
-                       cudaEvent_t join, cudaEvent_t t0 = nullptr, cudaEvent_t t1 = nullptr);
+                       cudaEvent_t join, cudaEvent_t t0 = nullptr, cudaEvent_t t1 = nullptr, int max_E = 0);
 void launch_info_dense_factor(const UpdArgs& u, const InfoBufs& ib, const double* Hp, int ldh, int rows, int n,
                               cudaStream_t s);
 void launch_info_dense_apply(const UpdArgs& u, const InfoBufs& ib, int n, cudaStream_t s);

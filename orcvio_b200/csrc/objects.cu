@@ -245,13 +245,13 @@ int Batch::object_update(int fi, const double* Hx, const double* Hf, const doubl
   }
   CKO(dFw.alloc(sizeof(FilterWork)));
   CKO(cudaMemcpyAsync(dFw.p, &fw, sizeof(fw), cudaMemcpyHostToDevice, stream_));
-  const size_t r_stride = (size_t)(6 * Ncap_ + 1) * ldr_;
+  const size_t r_stride = (size_t)(nmax_ + 1) * ldr_;
   UpdArgs ua{};
   ua.fw = dFw.as<FilterWork>(); ua.n_filters = 1;
   ua.P = dP_ + (size_t)fi * ldp_ * ldp_; ua.p_stride = (size_t)ldp_ * ldp_; ua.ldp = ldp_;
   ua.Rm = dR_ + (size_t)fi * r_stride; ua.rthin = dRthin_ + (size_t)fi * ldr_; ua.r_stride = r_stride; ua.ldr = ldr_;
-  ua.T = dT_ + (size_t)fi * (6 * Ncap_) * ldt_; ua.S = dS_ + (size_t)fi * r_stride;
-  ua.t_stride = (size_t)(6 * Ncap_) * ldt_; ua.ldt = ldt_;
+  ua.T = dT_ + (size_t)fi * nmax_ * ldt_; ua.S = dS_ + (size_t)fi * r_stride;
+  ua.t_stride = (size_t)nmax_ * ldt_; ua.ldt = ldt_;
   ua.yv = dYv_ + (size_t)fi * ldr_;
   ua.imu = dImu_ + (size_t)fi * IM_STRIDE; ua.clones = dClones_ + (size_t)fi * Ncap_ * CL_STRIDE;
   ua.clone_stride = (size_t)Ncap_ * CL_STRIDE;
@@ -349,7 +349,7 @@ int Batch::dense_update(const double* P_in, int D, const double* H, const double
                         double* P_out) {
   if (!ok_) return ORCVIO_ERR_NO_DEVICE;
   const int n = D - ORCVIO_LEG;
-  if (n < 1 || D > ldp_ || n > 6 * Ncap_ || rows < 1) return ORCVIO_ERR_ARG;
+  if (n < 1 || D > ldp_ || n > nmax_ || rows < 1) return ORCVIO_ERR_ARG;
   const int fi = 0;
   CKO(cudaMemsetAsync(dP_, 0, (size_t)ldp_ * ldp_ * sizeof(double), stream_));
   CKO(cudaMemcpy2DAsync(dP_, ldp_ * sizeof(double), P_in, D * sizeof(double), D * sizeof(double), D,
@@ -381,12 +381,12 @@ int Batch::dense_update(const double* P_in, int D, const double* H, const double
   }
   CKO(dFw.alloc(sizeof(FilterWork)));
   CKO(cudaMemcpyAsync(dFw.p, &fw, sizeof(fw), cudaMemcpyHostToDevice, stream_));
-  const size_t r_stride = (size_t)(6 * Ncap_ + 1) * ldr_;
+  const size_t r_stride = (size_t)(nmax_ + 1) * ldr_;
   UpdArgs ua{};
   ua.fw = dFw.as<FilterWork>(); ua.n_filters = 1;
   ua.P = dP_; ua.p_stride = (size_t)ldp_ * ldp_; ua.ldp = ldp_;
   ua.Rm = dR_; ua.rthin = dRthin_; ua.r_stride = r_stride; ua.ldr = ldr_;
-  ua.T = dT_; ua.S = dS_; ua.t_stride = (size_t)(6 * Ncap_) * ldt_; ua.ldt = ldt_;
+  ua.T = dT_; ua.S = dS_; ua.t_stride = (size_t)nmax_ * ldt_; ua.ldt = ldt_;
   ua.yv = dYv_;
   ua.imu = dImu_; ua.clones = dClones_; ua.clone_stride = (size_t)Ncap_ * CL_STRIDE;
   ua.dx = dDx_; ua.lddx = ldp_;

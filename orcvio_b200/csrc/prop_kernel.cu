@@ -357,12 +357,31 @@ __global__ void __launch_bounds__(256) k_augment(AugArgs a) {
   const int fi = blockIdx.x;
   const int N = a.N[fi];
   if (N < 0) return;                       // filter did not take part in this frame
-  const int D = ORCVIO_LEG + 6 * N;
+  const int D = ORCVIO_LEG + 6 * N;          // the new block goes in at index D, in front of the feature states
+  const int E = a.E ? a.E[fi] : 0;
   const int ldp = a.ldp;
   double* P = a.P + (size_t)fi * a.p_stride;
   const double* imu = a.imu + (size_t)fi * IM_STRIDE;
   double* c = a.clones + (size_t)fi * a.clone_stride + (size_t)N * CL_STRIDE;
   const int tid = threadIdx.x;
+  if (E > 0) {
+    // stateAugmentation :985-994: the feature rows / columns move 6 places down (descending order: in place is safe)
+    const int Dt = D + E;
+    for (int i = Dt - 1; i >= 0; --i) {
+      const int ni = i < D ? i : i + 6;
+      // row i -> row ni with the feature columns shifted; rows < D only shift their feature columns
+      if (i >= D) {
+        for (int j = tid; j < D; j += blockDim.x) P[(size_t)ni * ldp + j] = P[(size_t)i * ldp + j];
+      }
+      __syncthreads();
+      // feature columns of this row, via registers (each thread one column; E <= blockDim.x)
+      double keep = 0.0;
+      if (tid < E) keep = P[(size_t)i * ldp + D + tid];
+      __syncthreads();
+      if (tid < E) P[(size_t)ni * ldp + D + 6 + tid] = keep;
+      __syncthreads();
+    }
+  }
   if (tid == 0) {
     for (int i = 0; i < 9; ++i) c[CL_R + i] = imu[IM_R + i];
     for (int i = 0; i < 3; ++i) c[CL_P + i] = imu[IM_P + i];
@@ -375,6 +394,13 @@ __global__ void __launch_bounds__(256) k_augment(AugArgs a) {
   auto src = [](int q) { return q < 3 ? q : q + 3; };   // theta rows 0..2, p rows 6..8
   for (int e = tid; e < 6 * D; e += blockDim.x) {
     const int q = e / D, j = e % D;
+    const double v = P[(size_t)src(q) * ldp + j];
+    P[(size_t)(D + q) * ldp + j] = v;
+    P[(size_t)j * ldp + D + q] = v;
+  }
+  // cross terms with the (shifted) feature states: J P over the feature columns
+  for (int e = tid; e < 6 * E; e += blockDim.x) {
+    const int q = e / E, j = D + 6 + e % E;
     const double v = P[(size_t)src(q) * ldp + j];
     P[(size_t)(D + q) * ldp + j] = v;
     P[(size_t)j * ldp + D + q] = v;
@@ -397,19 +423,19 @@ __global__ void __launch_bounds__(256) k_remove(RemoveArgs a) {
   const int r0 = a.rm[2 * fi], r1 = a.rm[2 * fi + 1];
   if (r0 < 0 && r1 < 0) return;
   const int N = a.N[fi];
-  const int D = ORCVIO_LEG + 6 * N;
+  const int D = ORCVIO_LEG + 6 * N + (a.E ? a.E[fi] : 0);
   const int ldp = a.ldp;
   double* P = a.P + (size_t)fi * a.p_stride;
   double* clones = a.clones + (size_t)fi * a.clone_stride;
   const int tid = threadIdx.x, nt = blockDim.x;
   auto removed = [&](int idx) {           // idx = state index; true if inside a removed clone block
-    if (idx < ORCVIO_LEG) return false;
+    if (idx < ORCVIO_LEG || idx >= ORCVIO_LEG + 6 * N) return false;
     const int c = (idx - ORCVIO_LEG) / 6;
     return c == r0 || c == r1;
   };
   auto newidx = [&](int idx) {
     if (idx < ORCVIO_LEG) return idx;
-    const int c = (idx - ORCVIO_LEG) / 6;
+    const int c = idx >= ORCVIO_LEG + 6 * N ? N : (idx - ORCVIO_LEG) / 6;   // feature states sit behind every clone
     int shift = 0;
     if (r0 >= 0 && c > r0) shift += 6;
     if (r1 >= 0 && c > r1) shift += 6;

@@ -126,7 +126,7 @@ constexpr int TRI_SM_STRIDE = 13;   // 12 contributions per observation, padded:
 __device__ int triangulate_feature(const double* __restrict__ clones, int m,
                                    const int* __restrict__ oc, const double* __restrict__ oz,
                                    bool is_init, double* pos_io, const TriCfg& cfg, int* iters,
-                                   double* cost_out, double* __restrict__ sm) {
+                                   double* cost_out, double* __restrict__ sm, double* fin_out = nullptr) {
   const int lane = threadIdx.x & 31;
   const bool act = lane < m;
   const double* cl = clones + (size_t)oc[m - 1] * CL_STRIDE;
@@ -262,6 +262,7 @@ __device__ int triangulate_feature(const double* __restrict__ clones, int m,
     pos_io[0] = pw[0] + tl[0];
     pos_io[1] = pw[1] + tl[1];
     pos_io[2] = pw[2] + tl[2];
+    if (fin_out) { fin_out[0] = fin[0]; fin_out[1] = fin[1]; fin_out[2] = fin[2]; }
   }
   return valid;
 }
@@ -337,11 +338,14 @@ __global__ void __launch_bounds__(32 * TRI_WARPS, MINB) k_triangulate(TriArgs a)
     if (motion && m >= 1) {
       double pos[3] = {fp[0], fp[1], fp[2]};
       __syncwarp();
-      int v = triangulate_feature(clones, m, oc, oz, is_init, pos, a.cfg, iters, &cost, sm_all[warp]);
+      double fin[3] = {0.0, 0.0, 0.0};
+      int v = triangulate_feature(clones, m, oc, oz, is_init, pos, a.cfg, iters, &cost, sm_all[warp],
+                                  a.final_pos ? fin : nullptr);
       if (v) {
         if (lane == 0) {
           fp[0] = pos[0]; fp[1] = pos[1]; fp[2] = pos[2];
           *fgen = cd.gen;
+          if (a.final_pos) { a.final_pos[3 * (size_t)c] = fin[0]; a.final_pos[3 * (size_t)c + 1] = fin[1]; a.final_pos[3 * (size_t)c + 2] = fin[2]; }
         }
         status = ST_TRI_VALID;
       }

@@ -193,9 +193,11 @@ def test_free_running_vs_intrinsic_sensitivity():
 
 def test_unsupported_config_fails_loudly():
     from orcvio_b200 import configs
-    path = H.write_cfg(configs.make("euroc"))        # hybrid + ZUPT on: not supported yet
-    vio = api.OrcVIO(path)
-    assert not vio.initialize()
+    for bad in (dict(feature_idp_dim=3), dict(use_schmidt=1), dict(if_FEJ=1), dict(estimate_extrin=1),
+                dict(calib_imu_instrinsic=1)):
+        path = H.write_cfg(configs.make("euroc", **bad))
+        vio = api.OrcVIO(path)
+        assert not vio.initialize(), bad
 
 
 def test_not_initialised_returns_false():
