@@ -81,6 +81,10 @@ typedef struct orcvio_batch orcvio_batch;
 
 /* ---- orcvio::OrcVIO class mirror ------------------------------------------------- */
 /* OrcVIO::OrcVIO(std::string& config_file), src/orcvio.cpp:45-50 */
+/* Parses a config/*.yaml with the reader orcvio_initialize uses (OrcVIO::loadParameters, src/orcvio.cpp:62-415) and
+ * says whether this path runs it: ORCVIO_OK, ORCVIO_ERR_CONFIG (unreadable) or ORCVIO_ERR_UNSUPPORTED, with the reason
+ * in `why`.  Needs no device. */
+int orcvio_config_check(const char* config_yaml_path, char* why, int why_cap);
 orcvio_handle* orcvio_create(const char* config_yaml_path);
 void orcvio_destroy(orcvio_handle* h);
 /* OrcVIO::initialize(), src/orcvio.cpp:418-497.  1 = ok, 0 = yaml unreadable/unsupported. */

@@ -1436,7 +1436,7 @@ int Batch::process(const double* t_img, const OrcvioFeature* feats, const int* f
           const double* c = F.clone_mirror.data() + (size_t)k * CL_STRIDE;
           const double d[3] = {tr.mpos[0] - c[CL_PC], tr.mpos[1] - c[CL_PC + 1], tr.mpos[2] - c[CL_PC + 2]};
           double pn[3];
-          m3_Tvec(c + CL_RC, d, pn);
+          m3_inv_vec(c + CL_RC, d, pn);
           const double du = pn[0] / pn[2] - ob->z[0], dv = pn[1] / pn[2] - ob->z[1];
           const double dis = std::sqrt(du * du + dv * dv);
           if (min_dis > dis) { min_dis = dis; best = sid; }

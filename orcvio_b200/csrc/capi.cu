@@ -87,6 +87,16 @@ const char* orcvio_version(void) { return "orcvio_b200 0.1 (sm_100a)"; }
 
 double orcvio_chi2_quantile(double p, int dof) { return chi2_quantile(p, dof); }
 
+int orcvio_config_check(const char* config_yaml_path, char* why, int why_cap) {
+  Params p;
+  std::string err, reason;
+  int rc = ORCVIO_OK;
+  if (!load_params(config_yaml_path ? config_yaml_path : "", p, err)) { rc = ORCVIO_ERR_CONFIG; reason = err; }
+  else if (!check_supported(p, reason)) rc = ORCVIO_ERR_UNSUPPORTED;
+  if (why && why_cap > 0) std::snprintf(why, (size_t)why_cap, "%s", reason.c_str());
+  return rc;
+}
+
 orcvio_handle* orcvio_create(const char* config_yaml_path) {
   orcvio_handle* h = new orcvio_handle();
   h->config_path = config_yaml_path ? config_yaml_path : "";

@@ -30,6 +30,19 @@ HD void m3_Tmul(const double* A, const double* B, double* C) {  // C = A^T B
 HD void m3_vec(const double* A, const double* v, double* o) {  // o = A v
   for (int i = 0; i < 3; ++i) o[i] = (A[3 * i] * v[0] + A[3 * i + 1] * v[1]) + A[3 * i + 2] * v[2];
 }
+// o = A^-1 v by cofactors (Eigen's fixed-size 3 x 3 `.inverse()`): the reference inverts camera rotations that are only
+// orthonormal to the digits of the yaml extrinsics (src/orcvio.cpp:2707, 3638), so the transpose is not a substitute
+HD void m3_inv_vec(const double* A, const double* v, double* o) {
+  const double c00 = A[4] * A[8] - A[5] * A[7], c01 = A[5] * A[6] - A[3] * A[8], c02 = A[3] * A[7] - A[4] * A[6];
+  const double det = (A[0] * c00 + A[1] * c01) + A[2] * c02;
+  const double id = 1.0 / det;
+  const double i00 = c00 * id, i01 = (A[2] * A[7] - A[1] * A[8]) * id, i02 = (A[1] * A[5] - A[2] * A[4]) * id;
+  const double i10 = c01 * id, i11 = (A[0] * A[8] - A[2] * A[6]) * id, i12 = (A[2] * A[3] - A[0] * A[5]) * id;
+  const double i20 = c02 * id, i21 = (A[1] * A[6] - A[0] * A[7]) * id, i22 = (A[0] * A[4] - A[1] * A[3]) * id;
+  o[0] = (i00 * v[0] + i01 * v[1]) + i02 * v[2];
+  o[1] = (i10 * v[0] + i11 * v[1]) + i12 * v[2];
+  o[2] = (i20 * v[0] + i21 * v[1]) + i22 * v[2];
+}
 HD void m3_Tvec(const double* A, const double* v, double* o) {  // o = A^T v
   for (int i = 0; i < 3; ++i) o[i] = (A[i] * v[0] + A[3 + i] * v[1]) + A[6 + i] * v[2];
 }

@@ -97,7 +97,7 @@ __device__ __forceinline__ void ekf_reanchor_jacobian(const double* clo, const d
   m3_vec(Ro, tcb, Rt);
   const double d[3] = {pw[0] - (to[0] + Rt[0]), pw[1] - (to[1] + Rt[1]), pw[2] - (to[2] + Rt[2])};
   double po[3];
-  m3_Tvec(Rc2w_o, d, po);                // R_c2w_old^-1 (p_w - t_c_w_old): the rotation's inverse is its transpose
+  m3_inv_vec(Rc2w_o, d, po);             // R_c2w_old.inverse() * (p_w - t_c_w_old), :3638
   const double inv_old = 1 / po[2];
   const double fo[3] = {po[0] / po[2], po[1] / po[2], 1.0};
   const double pbo[3] = {pw[0] - to[0], pw[1] - to[1], pw[2] - to[2]};

@@ -404,7 +404,7 @@ __global__ void __launch_bounds__(256) k_reanchor(const ReanchorRec* recs, const
       // new inverse depth (and, for a feature of the state, the corrected anchor observation): p_new = R_c2w_new^-1 (p_w - t)
       const double d[3] = {pw[0] - cln[CL_PC], pw[1] - cln[CL_PC + 1], pw[2] - cln[CL_PC + 2]};
       double pn[3];
-      m3_Tvec(cln + CL_RC, d, pn);
+      m3_inv_vec(cln + CL_RC, d, pn);                    // R_c2w_new.inverse() (:2707)
       const double rho = 1 / pn[2];
       fid[0] = rho;
       if (rc.col >= 0) {

@@ -82,6 +82,32 @@ def test_configs_match_reference_yaml_when_mounted():
         assert abs(T.ravel() - cfg["T_cam_imu"]).max() < 1e-12
 
 
+def test_product_reader_on_the_reference_yaml_files():
+    """The product's own yaml reader (csrc/config.cpp) on every file of the reference's config/ directory, unmodified:
+    which ones this path runs and which it refuses, with the reason (orcvio_initialize refuses the same ones loudly)."""
+    ref = "/root/reference/config"
+    if not os.path.isdir(ref):
+        pytest.skip("reference not mounted (GPU box)")
+    import ctypes as C
+    from orcvio_b200 import api
+    L = api.lib()
+    L.orcvio_config_check.argtypes = [C.c_char_p, C.c_char_p, C.c_int]
+    expect_ok = {"euroc.yaml", "kitti.yaml", "kitti_odom.yaml", "kitti_raw.yaml", "erl.yaml", "indemind.yaml",
+                 "mesa.yaml", "realsense.yaml", "unity.yaml", "warthog.yaml"}
+    seen = {}
+    for fname in sorted(os.listdir(ref)):
+        buf = C.create_string_buffer(512)
+        rc = L.orcvio_config_check(os.path.join(ref, fname).encode(), buf, 512)
+        seen[fname] = (rc, buf.value.decode())
+    ok = {f for f, (rc, _) in seen.items() if rc == 0}
+    # the object_feat_*.yaml files configure the object front-end (no filter keys): the filter reader refuses them
+    assert expect_ok <= ok, {f: seen[f] for f in expect_ok - ok}
+    for f, (rc, why) in seen.items():
+        assert rc == 0 or why, (f, rc)
+    # the hybrid MSCKF / EKF-SLAM configurations are among the accepted ones
+    assert seen["euroc.yaml"][0] == 0 and seen["kitti_odom.yaml"][0] == 0
+
+
 def test_syrk_plan_covers_every_row_once_and_fits_the_budget():
     """Host logic of the staircase split-K plan (csrc/kernels.h syrk_plan), no device involved: every tile pair
     (I <= J) covers exactly the rows [jrow0[J], arows) in whole chunks of kc rows, kc is a multiple of 32 and >= 128,
