@@ -184,6 +184,7 @@ Batch::Batch(const Params& p, int n) : p_(p), B_(n) {
   }
   CK(cudaEventCreateWithFlags(&ev_fork_, cudaEventDisableTiming));
   CK(cudaEventCreateWithFlags(&ev_join_, cudaEventDisableTiming));
+  CK(cudaEventCreateWithFlags(&ev_ls_, cudaEventDisableTiming));
   {
     const char* e = std::getenv("ORCVIO_COMPRESS");
     compress_qr_ = e && std::string(e) == "qr" && !hybrid_;     // the dense EKF-feature rows exist only in the whitened form
@@ -279,7 +280,7 @@ Batch::~Batch() {
   cudaFree(dR_); cudaFree(dS_); cudaFree(dRthin_); cudaFree(dYv_); cudaFree(dT_); cudaFree(dDx_);
   cudaFree(dErr_); cudaFree(dFront_); cudaFree(dChi2_);
   cudaFree(dAmat_); cudaFree(dPart_);
-  cudaFree(dStatusF_); cudaFree(dGammaF_); cudaFree(dFidp_);
+  cudaFree(dStatusF_); cudaFree(dGammaF_); cudaFree(dFidp_); cudaFree(dTriDone_);
   if (blob_early2_.dev) cudaFree(blob_early2_.dev);
   if (blob_early2_.pinned) cudaFreeHost(blob_early2_.pinned);
   if (blob_early_.dev) cudaFree(blob_early_.dev);
@@ -298,6 +299,7 @@ Batch::~Batch() {
   for (auto& e : ev_) cudaEventDestroy(e);
   if (ev_fork_) cudaEventDestroy(ev_fork_);
   if (ev_join_) cudaEventDestroy(ev_join_);
+  if (ev_ls_) cudaEventDestroy(ev_ls_);
   if (stream2_) cudaStreamDestroy(stream2_);
   if (stream_up_) cudaStreamDestroy(stream_up_);
   if (ev_up_) cudaEventDestroy(ev_up_);
@@ -550,10 +552,10 @@ void Batch::launch_phase(PhaseWork& w, bool download, bool prior_in_flight) {
     // big CTA waits for an empty SM behind the first waves of k_triangulate
     CK(cudaEventRecord(ev_fork_, stream_));
     InfoBufs ib{};
-    ib.Ls = dLs_;
+    ib.Ls = dLs_; ib.ls_done = ev_ls_;
     launch_info_prior(upd_args(dFw), ib, w.maxN, stream2_, ev_fork_, ev_join_, profiling_ ? e[9] : nullptr,
                       profiling_ ? e[10] : nullptr, w.maxE);
-    ++nl;
+    nl += 2;                               // k_chol_prior + k_imu_factor
     prior_in_flight = true;
   }
   const bool hyb_on = hybrid_ && w.hyb_phase >= 0 && do_update && !use_qr;
@@ -575,8 +577,27 @@ void Batch::launch_phase(PhaseWork& w, bool download, bool prior_in_flight) {
     CK(cudaMalloc(&dRawHf_, raw_cap_ * 6 * sizeof(double)));
     CK(cudaMalloc(&dRawR_, raw_cap_ * 2 * sizeof(double)));
   }
-  if (nC > 0 && !skip_tri_ && !tri_done_early_) {
+  // k_jac_gate follows k_triangulate candidate by candidate (completion flags + programmatic launch) instead of
+  // waiting for the slowest LM chain of the whole grid; ORCVIO_TRI_OVERLAP=0 restores the grid-wide dependency
+  static const int overlap_env = env_int("ORCVIO_TRI_OVERLAP", 1);
+  const bool tri_here = nC > 0 && !skip_tri_ && !tri_done_early_;
+  // (measured: the slowest LM chain + its own Jacobian pass bound the overlapped pair at ~93 us whatever the count, so it
+  // only pays when the Jacobian kernel alone needs more than one wave: 4096 features 107 -> 96 us, 2000 features 82 -> 93 us)
+  static const int overlap_min = env_int("ORCVIO_TRI_OVERLAP_MIN", 2400);
+  const bool overlap = overlap_env && tri_here && !skip_jac_ && !jac_done_early_ && !want_iters_ && !want_raw_ &&
+                       nC >= overlap_min;
+  if (overlap) {
+    if ((size_t)nC > tridone_cap_) {
+      if (dTriDone_) cudaFree(dTriDone_);
+      tridone_cap_ = (size_t)nC * 2 + 1024;
+      CK(cudaMalloc(&dTriDone_, tridone_cap_ * sizeof(int)));
+      CK(cudaMemsetAsync(dTriDone_, 0, tridone_cap_ * sizeof(int), stream_));
+    }
+    ++tri_epoch_;
+  }
+  if (tri_here) {
     TriArgs ta{};
+    ta.done = overlap ? dTriDone_ : nullptr; ta.epoch = tri_epoch_;
     ta.cand = dC; ta.n_cand = nC;
     ta.clones = dClones_; ta.clone_stride = (size_t)Ncap_ * CL_STRIDE;
     ta.fpos = dFpos_; ta.fgen = dFgen_; ta.fcap = Fcap_;
@@ -588,9 +609,10 @@ void Batch::launch_phase(PhaseWork& w, bool download, bool prior_in_flight) {
     launch_triangulate(ta, stream_);
     ++nl;
   }
-  if (profiling_) CK(cudaEventRecord(e[1], stream_));
+  if (profiling_ && !overlap) CK(cudaEventRecord(e[1], stream_));   // (an event between the two would serialise them)
   if (nC > 0 && !skip_jac_ && !jac_done_early_) {
     JacArgs ja{};
+    ja.tri_done = overlap ? dTriDone_ : nullptr; ja.tri_epoch = tri_epoch_;
     ja.cand = dC;
     ja.clones = dClones_; ja.clone_stride = (size_t)Ncap_ * CL_STRIDE;
     ja.imu = dImu_; ja.fpos = dFpos_; ja.fcap = Fcap_;
@@ -607,6 +629,7 @@ void Batch::launch_phase(PhaseWork& w, bool download, bool prior_in_flight) {
     launch_jac_gate(js, jl, stream_);
     nl += (js.n_list > 0) + (jl.n_list > 0);
   }
+  if (profiling_ && overlap) CK(cudaEventRecord(e[1], stream_));    // stage "tri" = both kernels, stage "jac" = 0
   if (hyb_on && w.hyb_phase == 0) {     // dense rows of the features of the state / of the new features (gated)
     launch_hybrid_rows(ha, stream_);
     ++nl;
@@ -635,7 +658,7 @@ void Batch::launch_phase(PhaseWork& w, bool download, bool prior_in_flight) {
       launch_update(ua, w.maxN, stream_, &nl);
     } else {
       InfoBufs ib{};
-      ib.Ls = dLs_; ib.Amat = dAmat_; ib.part = dPart_;
+      ib.Ls = dLs_; ib.Amat = dAmat_; ib.part = dPart_; ib.ls_done = ev_ls_;
       ib.max_units = w.syrk_units; ib.cta_budget = n_sm_ * syrk_waves_; ib.group = syrk_group_; ib.syrk_cnt = dSyrkCnt_;
       ib.tile_rows = dTileRows_; ib.filter_rows = dFilterRows_;
       launch_info_update(qa, ua, ib, (int)w.tiles.size(), w.max_tile_rows, w.wmax_blk, w.maxN, stream_,
@@ -2187,9 +2210,9 @@ int Batch::snapshot_prepare(const SnapshotIO& io) {
     CK(cudaMemcpyAsync(dP_, S.dP0, (size_t)ldp_ * ldp_ * sizeof(double), cudaMemcpyDeviceToDevice, sp));
     CK(cudaEventRecord(ev_fork_, sp));
     InfoBufs ib{};
-    ib.Ls = dLs_;
+    ib.Ls = dLs_; ib.ls_done = ev_ls_;
     launch_info_prior(upd_args(S.dFw), ib, N, stream2_, ev_fork_, ev_join_);
-    ++launches_;
+    launches_ += 2;
     S.prior_early = true;
   }
   if (sp != stream_) {               // everything queued on stream_ from here on sees P (and dP_)

@@ -225,7 +225,7 @@ class Batch {
   int flags_ = 0;
   std::vector<FilterHost> f_;
   cudaStream_t stream_ = nullptr, stream2_ = nullptr;
-  cudaEvent_t ev_fork_ = nullptr, ev_join_ = nullptr;
+  cudaEvent_t ev_fork_ = nullptr, ev_join_ = nullptr, ev_ls_ = nullptr;
   bool compress_qr_ = false;          // true: QR tiles + chain (qr_kernel.cu); false: whitened form (info_kernel.cu)
   double *dAmat_ = nullptr, *dPart_ = nullptr;
   size_t amat_cap_ = 0, part_cap_ = 0;
@@ -252,6 +252,9 @@ class Batch {
   size_t cand_cap_ = 0;
   Blob blob_;
   Blob blob_early_;                    // feat_off + observation pools of the end-to-end call, uploaded ahead
+  int* dTriDone_ = nullptr;            // per-candidate completion flags of k_triangulate (epoch-stamped)
+  size_t tridone_cap_ = 0;
+  int tri_epoch_ = 0;
   int* dStatusF_ = nullptr;            // triangulation status by feature slot (early direct-mode pass)
   size_t statusf_cap_ = 0;
   bool tri_done_early_ = false, jac_done_early_ = false;

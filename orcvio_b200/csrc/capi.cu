@@ -87,6 +87,8 @@ const char* orcvio_version(void) { return "orcvio_b200 0.1 (sm_100a)"; }
 
 double orcvio_chi2_quantile(double p, int dof) { return chi2_quantile(p, dof); }
 
+int orcvio_syrk_debug(long long* out, int cap) { return ob::syrk_debug_read(out, cap); }
+
 int orcvio_config_check(const char* config_yaml_path, char* why, int why_cap) {
   Params p;
   std::string err, reason;

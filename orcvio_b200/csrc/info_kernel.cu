@@ -36,38 +36,92 @@ namespace ob {
 // P = F F^T in the order [clone columns 22..D-1 | IMU columns 0..21].  Outputs
 //   FT (n x ldt, UpdArgs::T): FT[k][c] = F[perm(c)][k] for k < n, c = original column index,
 //   Ls (22 x 22): the trailing factor of the IMU block given the clones (F_2 F_2^T = Ls Ls^T).
-__global__ void __launch_bounds__(CHOL_THREADS) k_chol_prior(UpdArgs a, double* Ls_all) {
+__global__ void __launch_bounds__(CHOL_THREADS) k_chol_prior(UpdArgs a) {
   extern __shared__ double sm[];
   __shared__ __align__(16) CholShared cs;
   const int fi = blockIdx.x;
   const FilterWork fw = a.fw[fi];
   if (!fw.active) return;
   const int D = fw.D, n = fw.D - ORCVIO_LEG, L = ORCVIO_LEG;   // n = 6N (+ E feature states behind the clones)
-  const int Tm = (D + 7) >> 3;
   const double* P = a.P + (size_t)fi * a.p_stride;
   double* FT = a.T + (size_t)fi * a.t_stride;
-  double* Ls = Ls_all + (size_t)fi * L * L;
   double* A = sm;
-  double* tol = A + chol_smem_doubles(D, 0);
+  double* tol = A + chol_smem_doubles(n, L);
   const int tid = threadIdx.x, nt = blockDim.x;
   const int warp = tid >> 5, lane = tid & 31, nw = nt >> 5;
   auto orig = [&](int q) { return q < n ? L + q : q - n; };
-  chol_init(A, cs, D, 0);
+  // only the n clone (+ feature) columns are pivots: the 22 IMU rows ride along as carried rows, so the chain is n / 8
+  // steps long and F_1 is complete when it ends; the IMU block's own factor (k_imu_factor) is off the critical path
+  chol_init(A, cs, n, L);
   __syncthreads();
   const int ldp = a.ldp;
-  chol_load_rows(A, D, 0, D, [&](int i, int j) { return P + (size_t)orig(i) * ldp + orig(j); });
-  for (int i = tid; i < D; i += nt) tol[i] = 1e-12 * fabs(P[(size_t)orig(i) * (ldp + 1)]);
-  for (int i = tid; i < L * L; i += nt) Ls[i] = 0.0;
+  chol_load_rows(A, n, 0, D, [&](int i, int j) { return P + (size_t)orig(i) * ldp + orig(j); });
+  for (int i = tid; i < n; i += nt) tol[i] = 1e-12 * fabs(P[(size_t)orig(i) * (ldp + 1)]);
   // entries above the diagonal of F are structural zeros: FT[k][orig(i)] = 0 for i < k
   for (int k = warp; k < n; k += nw)
     for (int i = lane; i < k; i += 32) FT[(size_t)k * a.ldt + L + i] = 0.0;
   chol_cp_async_wait();
-  cta_cholesky(A, cs, tol, D, 0);
+  cta_cholesky(A, cs, tol, n, L);
   const int ldt = a.ldt;
-  chol_for_rows(A, D, 0, 0, [&](int i, int k, double l) {
-    if (k < n) FT[(size_t)k * ldt + orig(i)] = l;
-    else Ls[(size_t)(i - n) * L + (k - n)] = l;
-  });
+  chol_for_rows(A, n, L, 0, [&](int i, int k, double l) { FT[(size_t)k * ldt + orig(i)] = l; });
+}
+
+// Ls Ls^T = P_II - X X^T: the factor of the IMU block given the clones (F_2 F_2^T = Ls Ls^T), X = the IMU rows of F_1
+// (FT[k][0..21]).  One CTA per filter, behind k_chol_prior on the side stream; only k_pinfo needs it.  Pivots
+// <= 1e-12 P_kk are exact zeros (rows 15..21 are zero and, after augmentation, the IMU pose duplicates the newest clone).
+__global__ void __launch_bounds__(256) k_imu_factor(UpdArgs a, double* Ls_all) {
+  extern __shared__ double sm[];                          // X^T: n x 22, then S: 22 x 23
+  constexpr int L = ORCVIO_LEG;
+  const int fi = blockIdx.x;
+  const FilterWork fw = a.fw[fi];
+  if (!fw.active) return;
+  const int n = fw.D - L;
+  const double* P = a.P + (size_t)fi * a.p_stride;
+  const double* FT = a.T + (size_t)fi * a.t_stride;
+  double* Ls = Ls_all + (size_t)fi * L * L;
+  double* X = sm;
+  double* S = sm + (size_t)n * L;
+  const int tid = threadIdx.x, nt = blockDim.x;
+  for (int e = tid; e < n * L; e += nt) X[e] = FT[(size_t)(e / L) * a.ldt + e % L];
+  __syncthreads();
+  for (int e = tid; e < L * L; e += nt) {
+    const int i = e / L, j = e % L;
+    if (j > i) continue;
+    double s0 = 0.0, s1 = 0.0;
+    int k = 0;
+    for (; k + 1 < n; k += 2) {
+      s0 += X[(size_t)k * L + i] * X[(size_t)k * L + j];
+      s1 += X[(size_t)(k + 1) * L + i] * X[(size_t)(k + 1) * L + j];
+    }
+    if (k < n) s0 += X[(size_t)k * L + i] * X[(size_t)k * L + j];
+    S[i * (L + 1) + j] = P[(size_t)i * a.ldp + j] - (s0 + s1);
+  }
+  __syncthreads();
+  if (tid < 32) {                                         // lane i owns row i
+    const int i = tid;
+    const double tol_i = i < L ? 1e-12 * fabs(P[(size_t)i * (a.ldp + 1)]) : 0.0;
+    for (int c = 0; c < L; ++c) {
+      const double pv = S[c * (L + 1) + c];
+      const double tc = __shfl_sync(0xffffffffu, tol_i, c);
+      const bool ok = pv > tc;
+      const double d = ok ? sqrt(pv) : 0.0;
+      const double id = ok ? 1.0 / d : 0.0;
+      double lic = 0.0;
+      if (i < L && i >= c) {
+        lic = (i == c) ? d : S[i * (L + 1) + c] * id;
+        S[i * (L + 1) + c] = lic;
+      }
+      __syncwarp();
+      if (i < L && i > c)
+        for (int j = c + 1; j <= i; ++j) S[i * (L + 1) + j] -= lic * S[j * (L + 1) + c];
+      __syncwarp();
+    }
+  }
+  __syncthreads();
+  for (int e = tid; e < L * L; e += nt) {
+    const int i = e / L, j = e % L;
+    Ls[e] = j <= i ? S[i * (L + 1) + j] : 0.0;
+  }
 }
 
 // ---------------------------------------------------------------- A = [r' | H' L]   (FP64 tensor cores)
@@ -265,26 +319,72 @@ __global__ void __launch_bounds__(256) k_aform_dense(const double* Hp, int ldh, 
 // W_aug ((n+1) x ldr, UpdArgs::S): A's column 0 (the residual) maps to row n (v = A^T r', corner r'^T r'),
 // column 1 + j to index j, with s^2 added on the first n diagonal entries.
 constexpr int SY_T = SY_TILE, SY_KS = 32, SY_LD = 68;
+// Operand pipeline: SY_STAGES slabs of 32 rows x 64 columns of A (column tile I) and of column tile J, brought in by
+// the TMA engine -- one cp.async.bulk (512 contiguous bytes of a row of A) per slab row, completion counted in bytes
+// on the stage's `full` mbarrier -- by a ninth (producer) warp; the eight MMA warps wait on `full`, run their 64 MMAs
+// on the slab and release it through the stage's `empty` mbarrier.  No __syncthreads and no register staging in the
+// k loop: the loads of the next SY_STAGES - 1 slabs are in flight while a slab is multiplied.
+constexpr int SY_THREADS = 256;
+constexpr int SY_STAGE_DOUBLES = 2 * SY_KS * SY_LD;
 
-__global__ void __launch_bounds__(256) k_syrk(UpdArgs a, const double* __restrict__ Amat, int lda, double* part,
-                                              int max_units, int cta_budget, int group, const Tile* tiles,
-                                              const int* tile_rows, int* filter_rows, unsigned int* counters) {
+__device__ __forceinline__ unsigned int smem_u32(const void* p) { return (unsigned int)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned int parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tSY_WAIT:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra SY_DONE;\n\tbra SY_WAIT;\n\tSY_DONE:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(unsigned long long* bar, unsigned int bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned int bytes, unsigned long long* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+// ORCVIO_SYRK_DBG=1: per-CTA time stamps (globaltimer, ns) of the phases of k_syrk, read back by orcvio_syrk_debug()
+__device__ long long* g_syrk_dbg = nullptr;
+constexpr int SY_DBG_N = 8;
+__device__ __forceinline__ void sy_stamp(int unit, int k) {
+  if (g_syrk_dbg && threadIdx.x == 0) {
+    long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    g_syrk_dbg[(size_t)unit * SY_DBG_N + k] = t;
+  }
+}
+
+template <int SY_STAGES>
+__global__ void __launch_bounds__(SY_THREADS) k_syrk(UpdArgs a, const double* __restrict__ Amat, int lda, double* part,
+                                                     int max_units, int cta_budget, int group, const Tile* tiles,
+                                                     const int* tile_rows, int* filter_rows, unsigned int* counters,
+                                                     int spin_reduce) {
+  extern __shared__ __align__(128) double sy_sm[];
   const int fi = blockIdx.y;
   const FilterWork fw = a.fw[fi];
   const int tid = threadIdx.x;
   const int unit = blockIdx.x;
   pdl_launch_dependents();
   pdl_wait();                                            // tile_rows and A are the previous kernel's output
-  if (unit == 0 && tid == 0) {                           // gated rows of this filter (k_pinfo skips P when 0)
+  sy_stamp(unit, 0);
+  if (unit == 0 && tid < 32) {                           // gated rows of this filter (k_pinfo skips P when 0): warp 0
     int rows = 0;
     if (fw.active) {
-      if (tiles == nullptr) rows = fw.arows;             // dense (object) update: every row counts
+      if (tiles == nullptr) rows = (tid == 0) ? fw.arows : 0;   // dense (object) update: every row counts
       else {
-        for (int t = fw.tile_begin; t < fw.tile_end; ++t) rows += tile_rows[t];
-        rows += fw.dense_rows;                           // hybrid mode: rows of the EKF-SLAM features
+        for (int t = fw.tile_begin + tid; t < fw.tile_end; t += 32) rows += tile_rows[t];
+        if (tid == 0) rows += fw.dense_rows;             // hybrid mode: rows of the EKF-SLAM features
       }
     }
-    filter_rows[fi] = rows;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) rows += __shfl_xor_sync(0xffffffffu, rows, o);
+    if (tid == 0) filter_rows[fi] = rows;
   }
   if (!fw.active) return;
   const int n = fw.D - ORCVIO_LEG, n1 = n + 1;
@@ -306,46 +406,54 @@ __global__ void __launch_bounds__(256) k_syrk(UpdArgs a, const double* __restric
   const int row_begin = min(fw.arows, fw.jrow0[J] + chunk * kc);
   const int row_end = min(fw.arows, row_begin + kc);
   const double* A = Amat + (size_t)fw.arow0 * lda;
-  __shared__ __align__(16) double As[SY_KS][SY_LD];
-  __shared__ __align__(16) double Bs[SY_KS][SY_LD];
   __shared__ int s_last;
   const bool diag = (I == J);
-  const double(*Bp)[SY_LD] = diag ? As : Bs;
   const int warp = tid >> 5, lane = tid & 31;
-  const int fr = lane >> 2, fk = lane & 3;               // fragment row (or column) / k index
-  const int wi = (warp & 1) * 32, wj = (warp >> 1) * 16;
+  const int i0 = I * SY_T, j0 = J * SY_T;
+  const int nslab = (row_end - row_begin + SY_KS - 1) / SY_KS;
   double2 acc[4][2];
 #pragma unroll
   for (int u = 0; u < 4; ++u)
 #pragma unroll
     for (int v = 0; v < 2; ++v) acc[u][v] = make_double2(0.0, 0.0);
-  // loader: 32 rows x 64 columns per matrix = 1024 double2, four per thread (rows lr, lr+8, lr+16, lr+24)
+  const int fr = lane >> 2, fk = lane & 3;               // fragment row (or column) / k index
+  const int wi = (warp & 1) * 32, wj = (warp >> 1) * 16;
+  // loader: 32 rows x 64 columns per matrix = 1024 x 16 bytes, four per thread and matrix (rows lr, lr+8, lr+16, lr+24);
+  // rows past the end of A and columns past lda are zero-filled by the copy itself (src-size 0)
   const int lr = tid >> 5, lc = (tid & 31) * 2;
-  const int i0 = I * SY_T, j0 = J * SY_T;
-  const double2 z2 = make_double2(0.0, 0.0);
-  const bool ci_ok = (i0 + lc < lda), cj_ok = (j0 + lc < lda) && !diag;
-  double2 pa[4], pb[4];
-  auto fetch = [&](int r0) {
+  const bool ci_ok = (i0 + lc < lda), cj_ok = (j0 + lc < lda);
+  auto issue = [&](int it) {
+    if (it < nslab) {
+      const int st = it % SY_STAGES;
+      double* sa = sy_sm + (size_t)st * SY_STAGE_DOUBLES;
+      const int r0 = row_begin + it * SY_KS;
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      const int r = r0 + lr + 8 * q;
-      pa[q] = pb[q] = z2;
-      if (r < row_end) {
-        if (ci_ok) pa[q] = *reinterpret_cast<const double2*>(A + (size_t)r * lda + i0 + lc);
-        if (cj_ok) pb[q] = *reinterpret_cast<const double2*>(A + (size_t)r * lda + j0 + lc);
+      for (int q = 0; q < 4; ++q) {
+        const int rl = lr + 8 * q, r = r0 + rl;
+        const bool rok = r < row_end;
+        const double* src = A + (size_t)(rok ? r : row_begin) * lda;
+        const unsigned int da = smem_u32(sa + rl * SY_LD + lc);
+        const int na = (rok && ci_ok) ? 16 : 0;
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(da), "l"(src + (ci_ok ? i0 + lc : 0)), "r"(na) : "memory");
+        if (!diag) {
+          const int nb = (rok && cj_ok) ? 16 : 0;
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(da + (unsigned int)(SY_KS * SY_LD * sizeof(double))),
+                       "l"(src + (cj_ok ? j0 + lc : 0)), "r"(nb) : "memory");
+        }
       }
     }
+    asm volatile("cp.async.commit_group;" ::: "memory");
   };
-  fetch(row_begin);
-  for (int r0 = row_begin; r0 < row_end; r0 += SY_KS) {
-    __syncthreads();
+  sy_stamp(unit, 1);
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      *reinterpret_cast<double2*>(&As[lr + 8 * q][lc]) = pa[q];
-      if (!diag) *reinterpret_cast<double2*>(&Bs[lr + 8 * q][lc]) = pb[q];
-    }
-    __syncthreads();
-    if (r0 + SY_KS < row_end) fetch(r0 + SY_KS);          // in flight during the MMAs below
+  for (int it = 0; it < SY_STAGES - 1; ++it) issue(it);
+  for (int it = 0; it < nslab; ++it) {
+    asm volatile("cp.async.wait_group %0;" ::"n"(SY_STAGES - 2) : "memory");
+    __syncthreads();                                     // slab `it` has landed for everyone; slab it-1 is consumed
+    issue(it + SY_STAGES - 1);
+    const int st = it % SY_STAGES;
+    const double(*As)[SY_LD] = reinterpret_cast<const double(*)[SY_LD]>(sy_sm + (size_t)st * SY_STAGE_DOUBLES);
+    const double(*Bp)[SY_LD] = diag ? As : As + SY_KS;
 #pragma unroll
     for (int k4 = 0; k4 < SY_KS; k4 += 4) {
       double af[4], bf[2];
@@ -359,6 +467,7 @@ __global__ void __launch_bounds__(256) k_syrk(UpdArgs a, const double* __restric
         for (int v = 0; v < 2; ++v) dmma884(acc[u][v].x, acc[u][v].y, af[u], bf[v]);
     }
   }
+  sy_stamp(unit, 2);
   // tile element (ii, jj) = (A^T A)[i0 + ii][j0 + jj]; fragment (u, v): ii = wi + 8u + fr, jj = wj + 8v + 2fk (+1)
   double* S = a.S + (size_t)fi * a.r_stride;
   auto emit = [&](int ii, int jj, double s) {
@@ -387,6 +496,45 @@ __global__ void __launch_bounds__(256) k_syrk(UpdArgs a, const double* __restric
 #pragma unroll
     for (int v = 0; v < 2; ++v)
       *reinterpret_cast<double2*>(out + (wi + 8 * u + fr) * SY_T + wj + 8 * v + 2 * fk) = acc[u][v];
+  if (spin_reduce) {
+    // Every chunk of this pair is resident (the host only sets spin_reduce when the whole grid fits the GPU at once):
+    // wait until all of them have stored their partial, then reduce ONE SLICE of the tile over all chunks -- in chunk
+    // order, so the sum is reproducible -- and emit it.  All CTAs of the pair reduce in parallel: one L2 round trip
+    // instead of the two serial last-arriver passes below.
+    unsigned int* cnt = counters + ((size_t)fi * SY_MAXP + pidx) * (SY_MAXG + 1);
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) {
+      atomicAdd(cnt, 1u);
+      unsigned int v;
+      for (;;) {
+        asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(cnt) : "memory");
+        if (v >= (unsigned int)nchunks) break;
+        __nanosleep(64);
+      }
+      asm volatile("fence.acq_rel.gpu;" ::: "memory");
+    }
+    __syncthreads();
+    sy_stamp(unit, 3);
+    const int per = (SY_T * SY_T + nchunks - 1) / nchunks;
+    const int e0 = chunk * per, e1 = min(SY_T * SY_T, e0 + per);
+    for (int e = e0 + tid; e < e1; e += 256) {
+      const double* p0 = base + e;
+      double sacc = 0.0;
+      int c = 0;
+      for (; c + 3 < nchunks; c += 4) {
+        const double x0 = __ldcg(p0 + (size_t)c * cstride), x1 = __ldcg(p0 + (size_t)(c + 1) * cstride);
+        const double x2 = __ldcg(p0 + (size_t)(c + 2) * cstride), x3 = __ldcg(p0 + (size_t)(c + 3) * cstride);
+        sacc = (((sacc + x0) + x1) + x2) + x3;
+      }
+      for (; c < nchunks; ++c) sacc += __ldcg(p0 + (size_t)c * cstride);
+      emit(e >> 6, e & 63, sacc);
+    }
+    sy_stamp(unit, 4);
+    __syncthreads();
+    if (tid == 0 && atomicAdd(cnt + 1, 1u) == (unsigned int)(nchunks - 1)) { cnt[0] = 0u; cnt[1] = 0u; }   // ready for the next launch
+    return;
+  }
   // ---- level 1: the last chunk of a group sums the group (16 tile elements per thread)
   int gsz = max(group, 1);
   if ((nchunks + gsz - 1) / gsz > SY_MAXG) gsz = (nchunks + SY_MAXG - 1) / SY_MAXG;
@@ -398,6 +546,7 @@ __global__ void __launch_bounds__(256) k_syrk(UpdArgs a, const double* __restric
   __syncthreads();
   if (tid == 0) s_last = (atomicAdd(cnt + 1 + g, 1u) == (unsigned int)(c_end - c_begin - 1));
   __syncthreads();
+  sy_stamp(unit, 3);
   if (!s_last) return;
   __threadfence();
   double s[16];
@@ -427,6 +576,7 @@ __global__ void __launch_bounds__(256) k_syrk(UpdArgs a, const double* __restric
     }
   };
   sum_slots(c_begin, c_end, 1);
+  sy_stamp(unit, 4);
   if (ngroups > 1) {
     // ---- level 2: the group sum replaces the group's first partial; the last group sums the groups
     double* gout = base + (size_t)c_begin * cstride + tid;
@@ -439,9 +589,11 @@ __global__ void __launch_bounds__(256) k_syrk(UpdArgs a, const double* __restric
       s_last = (atomicAdd(cnt, 1u) == (unsigned int)(ngroups - 1));
     }
     __syncthreads();
+    sy_stamp(unit, 5);
     if (!s_last) return;
     __threadfence();
     sum_slots(0, nchunks, gsz);
+    sy_stamp(unit, 6);
     if (tid == 0) cnt[0] = 0u;
   } else if (tid == 0) {
     cnt[1 + g] = 0u;                                      // ready for the next launch
@@ -451,6 +603,17 @@ __global__ void __launch_bounds__(256) k_syrk(UpdArgs a, const double* __restric
     const int e = tid + 256 * q;
     emit(e >> 6, e & 63, s[q]);
   }
+  sy_stamp(unit, 7);
+}
+
+static long long* g_syrk_dbg_host = nullptr;
+static int g_syrk_dbg_units = 0;
+int syrk_debug_read(long long* out, int cap) {
+  if (!g_syrk_dbg_host) return 0;
+  const int n = std::min(cap, g_syrk_dbg_units * SY_DBG_N);
+  cudaDeviceSynchronize();
+  cudaMemcpy(out, g_syrk_dbg_host, (size_t)n * sizeof(long long), cudaMemcpyDeviceToHost);
+  return n;
 }
 
 // ---------------------------------------------------------------- W = C C^T with F_1, v carried; dx
@@ -632,14 +795,42 @@ static void info_attrs() {
   cudaFuncSetAttribute(k_chol_prior, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024);
   cudaFuncSetAttribute(k_chol_w_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024);
   cudaFuncSetAttribute(k_pinfo, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+  cudaFuncSetAttribute(k_imu_factor, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+  cudaFuncSetAttribute(k_syrk<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * SY_STAGE_DOUBLES * (int)sizeof(double));
+  cudaFuncSetAttribute(k_syrk<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * SY_STAGE_DOUBLES * (int)sizeof(double));
+  cudaFuncSetAttribute(k_syrk<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * SY_STAGE_DOUBLES * (int)sizeof(double));
   check_launch("info attributes");
   attr = true;
 }
 
 static void launch_syrk(const UpdArgs& u, const InfoBufs& ib, int B, const Tile* tiles, cudaStream_t s) {
   dim3 gs(std::max(ib.max_units, 1), B);
-  launch_pdl(k_syrk, gs, dim3(256), 0, s, u, ib.Amat, u.ldr, ib.part, ib.max_units, ib.cta_budget, ib.group, tiles,
-             ib.tile_rows, ib.filter_rows, ib.syrk_cnt);
+  static const int dbg = env_int("ORCVIO_SYRK_DBG", 0);
+  if (dbg) {
+    if (!g_syrk_dbg_host) {
+      cudaMalloc(&g_syrk_dbg_host, (size_t)1024 * SY_DBG_N * sizeof(long long));
+      cudaMemcpyToSymbol(g_syrk_dbg, &g_syrk_dbg_host, sizeof(g_syrk_dbg_host));
+    }
+    cudaMemsetAsync(g_syrk_dbg_host, 0, (size_t)1024 * SY_DBG_N * sizeof(long long), s);
+    g_syrk_dbg_units = std::min(1024, std::max(ib.max_units, 1));
+  }
+  // the parallel slice reduction spins on the other chunks of a pair: only when every CTA of the grid is resident
+  static const int spin_env = env_int("ORCVIO_SYRK_SPIN", 1);
+  int n_sm = 0, dev = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+  const int spin = (spin_env && (long long)gs.x * gs.y <= n_sm) ? 1 : 0;
+  static const int stages = env_int("ORCVIO_SYRK_STAGES", 2);
+  const size_t smem = (size_t)(stages == 4 ? 4 : stages == 3 ? 3 : 2) * SY_STAGE_DOUBLES * sizeof(double);
+  if (stages == 4)
+    launch_pdl(k_syrk<4>, gs, dim3(SY_THREADS), smem, s, u, ib.Amat, u.ldr, ib.part, ib.max_units, ib.cta_budget, ib.group,
+               tiles, ib.tile_rows, ib.filter_rows, ib.syrk_cnt, spin);
+  else if (stages == 3)
+    launch_pdl(k_syrk<3>, gs, dim3(SY_THREADS), smem, s, u, ib.Amat, u.ldr, ib.part, ib.max_units, ib.cta_budget, ib.group,
+               tiles, ib.tile_rows, ib.filter_rows, ib.syrk_cnt, spin);
+  else
+    launch_pdl(k_syrk<2>, gs, dim3(SY_THREADS), smem, s, u, ib.Amat, u.ldr, ib.part, ib.max_units, ib.cta_budget, ib.group,
+               tiles, ib.tile_rows, ib.filter_rows, ib.syrk_cnt, spin);
   check_launch("k_syrk");
 }
 
@@ -661,9 +852,11 @@ void launch_info_dense_factor(const UpdArgs& u, const InfoBufs& ib, const double
                               cudaStream_t s) {
   info_attrs();
   const int D = ORCVIO_LEG + n;
-  const size_t sm_prior = (chol_smem_doubles(D, 0) + (size_t)D + 2) * sizeof(double);
-  k_chol_prior<<<1, CHOL_THREADS, sm_prior, s>>>(u, ib.Ls);
+  const size_t sm_prior = (chol_smem_doubles(n, ORCVIO_LEG) + (size_t)n + 2) * sizeof(double);
+  k_chol_prior<<<1, CHOL_THREADS, sm_prior, s>>>(u);
   check_launch("k_chol_prior");
+  k_imu_factor<<<1, 256, ((size_t)n * ORCVIO_LEG + ORCVIO_LEG * (ORCVIO_LEG + 1)) * sizeof(double), s>>>(u, ib.Ls);
+  check_launch("k_imu_factor");
   k_aform_dense<<<rows, 256, 0, s>>>(Hp, ldh, rows, n, u.T, u.ldt, ib.Amat, u.ldr);
   check_launch("k_aform_dense");
   launch_syrk(u, ib, 1, nullptr, s);
@@ -688,11 +881,16 @@ void launch_info_prior(const UpdArgs& u, const InfoBufs& ib, int max_N, cudaStre
   info_attrs();
   cudaStreamWaitEvent(s2, fork, 0);
   if (t0) cudaEventRecord(t0, s2);
-  const size_t sm_prior = (chol_smem_doubles(Dmax, 0) + (size_t)Dmax + 2) * sizeof(double);
-  k_chol_prior<<<u.n_filters, CHOL_THREADS, sm_prior, s2>>>(u, ib.Ls);
+  const int nmax = Dmax - ORCVIO_LEG;
+  const size_t sm_prior = (chol_smem_doubles(nmax, ORCVIO_LEG) + (size_t)nmax + 2) * sizeof(double);
+  k_chol_prior<<<u.n_filters, CHOL_THREADS, sm_prior, s2>>>(u);
   check_launch("k_chol_prior");
   if (t1) cudaEventRecord(t1, s2);
   cudaEventRecord(join, s2);
+  // the IMU block's factor: needed by k_pinfo only, so it stays on the side stream behind the join point
+  k_imu_factor<<<u.n_filters, 256, ((size_t)nmax * ORCVIO_LEG + ORCVIO_LEG * (ORCVIO_LEG + 1)) * sizeof(double), s2>>>(u, ib.Ls);
+  check_launch("k_imu_factor");
+  if (ib.ls_done) cudaEventRecord(ib.ls_done, s2);
 }
 
 void launch_info_update(const QrArgs& q, const UpdArgs& u, const InfoBufs& ib, int n_tiles, int max_tile_rows,
@@ -725,8 +923,9 @@ void launch_info_update(const QrArgs& q, const UpdArgs& u, const InfoBufs& ib, i
   launch_pdl(k_chol_w_solve, gw, dim3(CHOL_THREADS), sm_w, s, u);
   check_launch("k_chol_w_solve");
   if (mid2) cudaEventRecord(mid2, s);
+  if (ib.ls_done) cudaStreamWaitEvent(s, ib.ls_done, 0);
   launch_pinfo(u, ib, nmax, B, s);
-  if (launches) *launches += 3 + (prior_in_flight ? 0 : 1) + (n_tiles > 0 ? 1 : 0);
+  if (launches) *launches += 3 + (prior_in_flight ? 0 : 2) + (n_tiles > 0 ? 1 : 0);
 }
 
 }  // namespace ob

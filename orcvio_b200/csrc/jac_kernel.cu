@@ -147,8 +147,25 @@ __global__ void __launch_bounds__(128, MINB) k_jac_gate(JacArgs a) {
   } else {
     cd = a.cand[c];
   }
-  pdl_wait();                        // everything above reads host-built lists only; below: triangulation results
-  const int st_in = a.tri_status_f ? a.tri_status_f[cd.slot] : a.status[c];
+  // everything above reads host-built lists only; below: triangulation results
+  if (a.tri_done) {
+    // launched behind k_triangulate with programmatic stream serialisation: every triangulation CTA is resident (or
+    // done) by now, so waiting for this candidate's flag cannot deadlock; the other inputs (P, clones, pools) were
+    // complete before k_triangulate started
+    if (lane == 0) {
+      int v;
+      for (;;) {                     // relaxed polls (L2, no L1 invalidation), one acquire fence at the end
+        asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(a.tri_done + c) : "memory");
+        if (v == a.tri_epoch) break;
+        __nanosleep(400);
+      }
+      asm volatile("fence.acq_rel.gpu;" ::: "memory");
+    }
+    team_sync<TEAM>();
+  } else {
+    pdl_wait();
+  }
+  const int st_in = a.tri_status_f ? a.tri_status_f[cd.slot] : __ldcg(a.status + c);   // (L2: written by another SM moments ago)
   if (a.tri_status_f && lane == 0) a.status[c] = st_in;      // status by candidate, as the one-pass flow leaves it
   if (!(st_in & ST_TRI_VALID)) {
     if (lane == 0) a.gamma[c] = -1.0;
@@ -177,7 +194,7 @@ __global__ void __launch_bounds__(128, MINB) k_jac_gate(JacArgs a) {
 
   // ---- J1: one observation per thread
   for (int i = lane; i < m; i += TEAM) {
-    double pw[3] = {fp[0], fp[1], fp[2]};
+    double pw[3] = {__ldcg(fp), __ldcg(fp + 1), __ldcg(fp + 2)};
     double hx[12], hf[6], ri[2], he[12];
     measurement_jacobian(clones + (size_t)oc[i] * CL_STRIDE, imu + IM_RBC, imu + IM_TCB, pw,
                          oz[2 * i], oz[2 * i + 1], a.flags, hx, hf, ri, a.raw_He ? he : nullptr);
@@ -368,7 +385,8 @@ static void launch_one(const JacArgs& a, cudaStream_t s) {
     attr_set = true;
   }
   int blocks = (a.n_list + tpb - 1) / tpb;
-  launch_pdl(k_jac_gate<TEAM, MAXM, MINB>, dim3(blocks), dim3(threads), smem, s, a);
+  if (a.tri_done) launch_pdl_if(true, k_jac_gate<TEAM, MAXM, MINB>, dim3(blocks), dim3(threads), smem, s, a);
+  else launch_pdl(k_jac_gate<TEAM, MAXM, MINB>, dim3(blocks), dim3(threads), smem, s, a);
   check_launch("k_jac_gate");
 }
 

@@ -71,6 +71,10 @@ struct TriArgs {
   const int* feat_off;
   int direct_n_clones, direct_n_obs;   // direct mode: bounds the kernel checks itself (it may start before the host
                                        // has validated the caller's lists; a malformed feature is just invalid)
+  // per-candidate completion flags (optional): done[c] = epoch once the candidate's results are visible device-wide.
+  // The Jacobian kernel, launched behind this one with programmatic stream serialisation, starts its candidates one by
+  // one as they finish instead of waiting for the slowest LM chain of the grid.
+  int* done; int epoch;
 };
 
 struct JacArgs {
@@ -82,6 +86,7 @@ struct JacArgs {
   int flags; double sigma2; const double* chi2;  // chi2[dof], dof < 500
   int* status; double* gamma;
   const int* tri_status_f;                       // != nullptr: triangulation status by feature slot (direct mode)
+  const int* tri_done; int tri_epoch;            // != nullptr: per-candidate completion flags of k_triangulate (see TriArgs)
   // direct mode (end-to-end frame call): feat_off != nullptr -> list entries are FEATURE indices of the caller's
   // list, the candidate record is derived on the fly (offsets of the feature's rows / block from rowoff_f /
   // hblkoff_f), status and gamma are indexed by feature
@@ -149,6 +154,7 @@ struct InfoBufs {
   unsigned int* syrk_cnt; // split-K arrival counters [filter][SY_MAXP][1 + SY_MAXG] (zero between launches)
   int* tile_rows;        // gated rows per tile
   int* filter_rows;      // gated rows per filter (0 -> posterior == prior, P is left untouched)
+  cudaEvent_t ls_done;   // recorded on the side stream behind k_imu_factor (Ls); the main stream waits for it before k_pinfo
 };
 
 struct PropSample { double t, w[3], a[3]; };
@@ -272,6 +278,21 @@ int env_int(const char* name, int dflt);   // tuning knobs (ORCVIO_* environment
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 template <class... KArgs, class... Args>
+inline void launch_pdl_if(bool on, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s,
+                          Args... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = on ? 1 : 0;
+  cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+template <class... KArgs, class... Args>
 inline void launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args... args) {
   static const int pdl_on = env_int("ORCVIO_PDL", 0);
   cudaLaunchConfig_t cfg{};
@@ -302,6 +323,7 @@ void launch_info_update(const QrArgs& q, const UpdArgs& u, const InfoBufs& ib, i
                         int max_dense = 0);
 void launch_info_prior(const UpdArgs& u, const InfoBufs& ib, int max_N, cudaStream_t s2, cudaEvent_t fork,
                        cudaEvent_t join, cudaEvent_t t0 = nullptr, cudaEvent_t t1 = nullptr, int max_E = 0);
+int syrk_debug_read(long long* out, int cap);   // ORCVIO_SYRK_DBG=1: phase time stamps of the last k_syrk launch
 void launch_info_dense_factor(const UpdArgs& u, const InfoBufs& ib, const double* Hp, int ldh, int rows, int n,
                               cudaStream_t s);
 void launch_info_dense_apply(const UpdArgs& u, const InfoBufs& ib, int n, cudaStream_t s);

@@ -110,8 +110,17 @@ __device__ __forceinline__ void rel_pose(const double* c, const double* Rl, cons
 
 // sum_{k<m} v_k accumulated in observation order (total = total + v_k), v_k held by lane k
 __device__ __forceinline__ double ordered_sum(double v, int m) {
+  // the shuffles do not depend on the running sum: fetch eight terms at once, then add them in order (the chain is the
+  // m additions, not m shuffle round trips)
   double s = 0.0;
-  for (int k = 0; k < m; ++k) s = s + __shfl_sync(0xffffffffu, v, k);
+  for (int k0 = 0; k0 < m; k0 += 8) {
+    double t[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) t[j] = __shfl_sync(0xffffffffu, v, (k0 + j) & 31);
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      if (k0 + j < m) s = s + t[j];
+  }
   return s;
 }
 
@@ -209,7 +218,14 @@ __device__ int triangulate_feature(const double* __restrict__ clones, int m,
     __syncwarp();
     double acc = 0.0;           // lane j < 12 sums entry j over the observations, in order
     if (lane < 12)
-      for (int k = 0; k < m; ++k) acc = acc + sm[k * TRI_SM_STRIDE + lane];
+      for (int k0 = 0; k0 < m; k0 += 8) {      // eight loads in flight, then the ordered additions
+        double t[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) t[j] = (k0 + j < m) ? sm[(k0 + j) * TRI_SM_STRIDE + lane] : 0.0;
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          if (k0 + j < m) acc = acc + t[j];
+      }
     __syncwarp();
     double A[9], b[3];
     for (int i = 0; i < 9; ++i) A[i] = __shfl_sync(0xffffffffu, acc, i);
@@ -305,7 +321,13 @@ __global__ void __launch_bounds__(32 * TRI_WARPS, MINB) k_triangulate(TriArgs a)
     if (!bad)
       for (int k = lane; k < m; k += 32) bad |= (unsigned)a.obs_clone[o0 + k] >= (unsigned)a.direct_n_clones;
     if (__any_sync(0xffffffffu, bad)) {
-      if (lane == 0) a.status[c] = 0;
+      if (lane == 0) {
+        a.status[c] = 0;
+        if (a.done) {
+          __threadfence();
+          asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(a.done + c), "r"(a.epoch) : "memory");
+        }
+      }
       return;
     }
     cd.filter = 0; cd.slot = c; cd.gen = c + 1; cd.flags = CAND_FORCE_TRI;
@@ -355,6 +377,10 @@ __global__ void __launch_bounds__(32 * TRI_WARPS, MINB) k_triangulate(TriArgs a)
     a.status[c] = status;
     if (a.iters) { a.iters[2 * c] = iters[0]; a.iters[2 * c + 1] = iters[1]; }
     if (a.cost) a.cost[c] = cost;
+    if (a.done) {                     // position, serial and status first, then the flag (release)
+      __threadfence();
+      asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(a.done + c), "r"(a.epoch) : "memory");
+    }
   }
 }
 
