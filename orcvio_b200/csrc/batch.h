@@ -176,6 +176,7 @@ class Batch {
   // persistent three-step form used by the orcvio_frame_* entry points
   int snapshot_prepare(const SnapshotIO& io);
   int snapshot_execute(bool download);
+  int snapshot_execute_plain(bool download, bool prior_in_flight);
   int snapshot_fetch(const SnapshotIO& io);
   void snapshot_stage_times(float* us6);
   float last_syrk_us() const { return last_syrk_us_; }     // k_syrk / k_chol_prior of the last profiled run
@@ -255,6 +256,7 @@ class Batch {
   int* dTriDone_ = nullptr;            // per-candidate completion flags of k_triangulate (epoch-stamped)
   size_t tridone_cap_ = 0;
   int tri_epoch_ = 0;
+  bool graph_capturing_ = false;
   int* dStatusF_ = nullptr;            // triangulation status by feature slot (early direct-mode pass)
   size_t statusf_cap_ = 0;
   bool tri_done_early_ = false, jac_done_early_ = false;
