@@ -165,6 +165,230 @@ def reference_arm(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
+def _time_frame(api, torch, snap, n_clones, steps, warmup, l2_flush):
+    """Device time (CUDA events, L2 flushed) and end-to-end wall time of one frozen frame."""
+    fr = api.Frame(n_clones, 0, NOISE_VAR, 0.95, -1.0, TRI["cost_threshold"], TRI["init_final_dist_threshold"])
+    inp = fr.prepare_inputs(snap)
+    out = fr.update(inp)
+    fr.load(snap)
+    for _ in range(warmup):
+        l2_flush()
+        fr.run(1)
+    us = 0.0
+    for _ in range(steps):
+        l2_flush()
+        us += fr.run(1)
+    for _ in range(3):
+        fr.update(inp, out)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        fr.update(inp, out)
+    torch.cuda.synchronize()
+    e2e = (time.perf_counter() - t0) / steps * 1e6
+    m = np.diff(np.asarray(snap["feat_off"]))
+    passed = (out["status"] & 2) != 0
+    return dict(us_per_frame=us / steps, e2e_us_per_frame=e2e, features=int(len(m)), gated_in=int(passed.sum()),
+                gated_rows=int((2 * m - 3)[passed].sum()), state_dim=22 + 6 * n_clones)
+
+
+def _process_features_leg(api, configs_mod, synth, cfg_name, overrides, n_frames, feats, n_landmarks, skip):
+    """Wall time of OrcVIO::processFeatures (propagation + augmentation + ZUPT test + both update chains + pruning),
+    host buffers in, host state out, on a synthetic sequence of the given shape; the first `skip` frames (window
+    filling up) are left out."""
+    import tempfile
+    seq = synth.make_sequence(synth.SynthSpec(config=cfg_name, seed=0, n_frames=n_frames, feats_per_frame=feats,
+                                              overrides=overrides, n_landmarks=n_landmarks))
+    path = os.path.join(tempfile.mkdtemp(prefix="orcvio_bench_"), "cfg.yaml")
+    configs_mod.write_yaml(path, seq["cfg"])
+    vio = api.OrcVIO(path)
+    if not vio.initialize():
+        return dict(error="initialize failed")
+    k, times, n_states, cand = 0, [], 0, 0
+    for fi, (t_img, f) in enumerate(seq["frames"]):
+        k1 = k
+        while k1 < len(seq["imu"]) and seq["imu"][k1][0] <= t_img + 0.02:
+            k1 += 1
+        vio.push_imu(seq["imu"][k:k1])
+        k = k1
+        t0 = time.perf_counter()
+        ok = vio.processFeatures(t_img, f)
+        dt = time.perf_counter() - t0
+        if not ok:
+            return dict(error=f"frame {fi} not published")
+        if fi >= skip:
+            times.append(dt)
+            st = vio.frame_stats()
+            cand += st.n_candidates_lost + st.n_candidates_prune
+            n_states = max(n_states, len(vio.feature_states()[0]))
+    st = vio.state()
+    return dict(us_per_call_median=float(np.median(times)) * 1e6, us_per_call_mean=float(np.mean(times)) * 1e6,
+                frames=len(times), features_per_frame=feats, clones=int(st.n_clones), state_dim=int(st.dim),
+                candidates_per_frame=cand / max(len(times), 1), max_ekf_feature_states=int(n_states),
+                config=f"{cfg_name}.yaml shape" + (f" with {overrides}" if overrides else " as shipped"))
+
+
+def _object_leg(api, configs_mod, synth):
+    """BASELINE configs[1]: Unity-shaped filter, one object (12 keypoints, 5 views) -- the stage-3 rows, their
+    projection onto the window (constructObjectResidualJacobians) and the object update (removeLostObjects)."""
+    import tempfile
+    gold = os.path.join(ROOT, "tests", "golden", "one_car.npz")
+    if not os.path.exists(gold):
+        return dict(error="tests/golden/one_car.npz missing")
+    g = np.load(gold)
+    seq = synth.make_sequence(synth.SynthSpec(config="unity", seed=4, n_frames=26, feats_per_frame=100,
+                                              overrides=dict(if_ZUPT_valid=0)))
+    path = os.path.join(tempfile.mkdtemp(prefix="orcvio_bench_"), "cfg.yaml")
+    configs_mod.write_yaml(path, seq["cfg"])
+    vio = api.OrcVIO(path)
+    if not vio.initialize():
+        return dict(error="initialize failed")
+    k = 0
+    t_feat = []
+    for (t_img, f) in seq["frames"]:
+        k1 = k
+        while k1 < len(seq["imu"]) and seq["imu"][k1][0] <= t_img + 0.02:
+            k1 += 1
+        vio.push_imu(seq["imu"][k:k1])
+        k = k1
+        t0 = time.perf_counter()
+        vio.processFeatures(t_img, f)
+        t_feat.append(time.perf_counter() - t0)
+    poses, ids, times = vio.window()
+    N = len(ids)
+    T = np.array(seq["cfg"]["T_cam_imu"]).reshape(4, 4)
+    Rbc = T[:3, :3]
+    tcb = -Rbc.T @ T[:3, 3]
+    frames, ts = [], []
+    for c in [2, 4, 5, 7, N - 2]:
+        R, p = poses[c][:9].reshape(3, 3), poses[c][9:]
+        wTc = np.eye(4)
+        wTc[:3, :3] = R @ Rbc.T
+        wTc[:3, 3] = p + R @ tcb
+        frames.append(wTc)
+        ts.append(float(times[c]))
+    frames = np.array(frames)
+    kps = g["mean_shape"][0]
+    shape = g["ellipsoid_shape"][0].ravel()
+    wTo = np.eye(4)
+    wTo[:3, 3] = frames[2][:3, 3] + frames[2][:3, :3] @ np.array([0.3, 0.1, 9.0])
+    rng = np.random.default_rng(3)
+    zs, zb = [], []
+    for wTc in frames:
+        pc = (np.linalg.inv(wTc) @ wTo @ np.hstack([kps, np.ones((len(kps), 1))]).T)[:3]
+        uv = (pc[:2] / pc[2]).T
+        zs.append(uv + rng.normal(0, 0.004, uv.shape))
+        zb.append(np.array([uv[:, 0].min(), uv[:, 1].min(), uv[:, 0].max(), uv[:, 1].max()]) + rng.normal(0, 0.004, 4))
+    zs, zb = np.array(zs), np.array(zb)
+    P0 = vio.cov()
+    reps, t_rows, t_con, t_upd, status = 10, 0.0, 0.0, 0.0, None
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        rows = api.object_residuals(frames, wTo, shape, kps, zs, zb, left=False, new_residual=True)
+        t1 = time.perf_counter()
+        flag, Hx, Hf, res = vio.constructObjectResidualJacobians(rows["fjac_cam"], ts, rows["fjac_obj"], rows["fvec"],
+                                                                 rows["zs_num"], rows["cam_pose_se3"])
+        t2 = time.perf_counter()
+        status, gamma = vio.removeLostObjects(Hx, Hf, res)
+        t3 = time.perf_counter()
+        t_rows += t1 - t0
+        t_con += t2 - t1
+        t_upd += t3 - t2
+    return dict(msckf_process_features_us_median=float(np.median(t_feat[10:])) * 1e6, object_rows_us=t_rows / reps * 1e6,
+                construct_jacobians_us=t_con / reps * 1e6, remove_lost_objects_us=t_upd / reps * 1e6,
+                object_rows=int(Hx.shape[0]), keypoints=int(len(kps)), views=int(len(frames)), clones=int(N),
+                last_status=int(status), state_dim=int(P0.shape[0]),
+                timing="wall clock around the C-ABI calls, host buffers in and out")
+
+
+def extra_legs(api, torch, args, l2_flush):
+    """the other cases of the measurement row, rank 0 only, bounded (a few seconds each)."""
+    from orcvio_b200 import synth, configs as configs_mod
+    out = {}
+    steps = max(10, min(args.steps, 50))
+    try:
+        # case 4b: every feature seen by all 30 clones (m = N = 30): M = 4096 x 57 = 233 k gated rows; the flop bound of
+        # the compression alone is M (n+1)(n+2) / DMMA peak ~ 0.2 ms, the whitening A = H' L as much again
+        snap = synth.stress_snapshot(N_CLONES, N_FEATURES, MAX_TRACK, seed=0, full_tracks=True)
+        r = _time_frame(api, torch, snap, N_CLONES, max(5, steps // 5), 3, l2_flush)
+        flops = r["gated_rows"] * (6 * N_CLONES + 1) * (6 * N_CLONES + 2)
+        r["syrk_flop_bound_us"] = flops / (api.fp64_peak()[1] * 1e12) * 1e6
+        out["case_4b_full_tracks"] = r
+    except Exception as e:
+        out["case_4b_full_tracks"] = dict(error=str(e))
+    for key, cfg, ncl, nf in (("C1_euroc_frame", "euroc", 20, 300), ("C3_kitti_frame", "kitti_odom", 30, 1000)):
+        try:
+            snap = synth.stress_snapshot(ncl, nf, MAX_TRACK, seed=0, config=cfg)
+            out[key] = _time_frame(api, torch, snap, ncl, steps, 3, l2_flush)
+        except Exception as e:
+            out[key] = dict(error=str(e))
+    try:
+        out["C2_unity_object_update"] = _object_leg(api, configs_mod, synth)
+    except Exception as e:
+        out["C2_unity_object_update"] = dict(error=str(e))
+    for key, cfg, ov, nfr, feats, nlm, skip in (
+            ("process_features_euroc", "euroc", {}, 90, 300, 8000, 60),
+            ("process_features_kitti", "kitti_odom", {}, 70, 1000, 30000, 45)):
+        try:
+            out[key] = _process_features_leg(api, configs_mod, synth, cfg, ov, nfr, feats, nlm, skip)
+        except Exception as e:
+            out[key] = dict(error=str(e))
+    return out
+
+
+def multi_trajectory_leg(api, torch, dist, args, rank, world, dev):
+    """BASELINE configs[4]: `--mc-traj` independent EuRoC-shaped trajectories x `--mc-frames` frames, sharded over the
+    ranks (trajectory t -> rank t mod world), no data-path collective: every rank replays its share through
+    orcvio_batch_replay, split into one batch per host thread; NCCL gathers the per-trajectory records."""
+    from orcvio_b200 import montecarlo as mc, configs as configs_mod
+    import tempfile
+    cores = os.cpu_count() or 1
+    per_rank = max(1, cores // world)
+    mine = mc.shard(args.mc_traj, rank, world)
+    t0 = time.perf_counter()
+    seqs = mc.make_sequences("euroc", mine, args.mc_frames, args.mc_feats, {}, n_landmarks=3000, workers=per_rank)
+    t_gen = time.perf_counter() - t0
+    path = os.path.join(tempfile.mkdtemp(prefix="orcvio_mc_"), "cfg.yaml")
+    configs_mod.write_yaml(path, seqs[0]["cfg"])
+    util = ClockSampler(int(os.environ.get("LOCAL_RANK", "0")))
+    util.FIELDS = "utilization.gpu,clocks.sm"
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    if rank == 0:
+        util.start()
+    rec, info = mc.run_replay(path, seqs, mine, n_threads=per_rank)
+    torch.cuda.synchronize()
+    busy = None
+    if rank == 0 and util.proc:
+        time.sleep(0.12)
+        util.proc.terminate()
+        vals = []
+        for r in util.rows:
+            try:
+                vals.append(float(r[0]))
+            except Exception:
+                pass
+        busy = float(np.mean(vals)) if vals else None
+    secs = torch.tensor([info["seconds"]], dtype=torch.float64, device=dev)
+    counts = torch.tensor([float(info["feature_updates"]), float(info["kernel_launches"])], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(secs, op=dist.ReduceOp.MAX)
+        dist.all_reduce(counts, op=dist.ReduceOp.SUM)
+    allrec = mc.gather_records(rec, args.mc_traj, rank, world, device=dev)
+    s = secs.item()
+    return dict(
+        workload=f"Monte-Carlo replay: {args.mc_traj} independent euroc.yaml-shaped trajectories (hybrid MSCKF/EKF-SLAM + ZUPT as "
+                 f"shipped) x {args.mc_frames} frames, ~{args.mc_feats} features per frame, trajectory t -> rank t mod {world}",
+        n_gpus=world, trajectories=args.mc_traj, frames=args.mc_frames, host_threads_per_rank=per_rank, host_cores=cores,
+        seconds=s, trajectory_frames_per_sec=args.mc_traj * args.mc_frames / s,
+        feature_updates_per_sec=counts[0].item() / s, feature_updates=counts[0].item(), kernel_launches=counts[1].item(),
+        all_published=bool(np.all(allrec[:, 7] == 1.0)), ate_m_mean=float(allrec[:, 5].mean()),
+        ate_m_max=float(allrec[:, 5].max()), ate_checksum=float(np.sum(allrec[:, 5] * (1 + np.arange(len(allrec))))),
+        gpu_utilization_pct_rank0=busy, sequence_generation_s_per_rank=t_gen, scaling="strong",
+        timing="wall clock around the replay threads of a rank (host bookkeeping + uploads + kernels + read-backs), "
+               "barrier + synchronize on both sides, max over ranks; trajectory metrics by orcvio_trajectory_metrics on the device")
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -175,6 +399,11 @@ def main():
     ap.add_argument("--ref-repeats", type=int, default=6, help="frames per host thread in the cpu_baseline leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-flush", action="store_true", help="skip the L2 flush (profiling runs only)")
+    ap.add_argument("--no-extra", action="store_true", help="skip the other SURVEY 8d cases (4b, C1-C3, processFeatures)")
+    ap.add_argument("--no-mc", action="store_true", help="skip the multi-trajectory replay (BASELINE configs[4])")
+    ap.add_argument("--mc-traj", type=int, default=1024)
+    ap.add_argument("--mc-frames", type=int, default=200)
+    ap.add_argument("--mc-feats", type=int, default=150)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -272,6 +501,19 @@ def main():
                                     pinfo_increment=round(st_t["update"], 2), total=round(st_t["total"], 2)))
         del fr_t
 
+    extras = None
+    if rank == 0 and not args.no_extra:
+        extras = extra_legs(api, torch, args, l2_flush)
+    del flush
+    mc_leg = None
+    if not args.no_mc:
+        try:
+            mc_leg = multi_trajectory_leg(api, torch, dist, args, rank, world, dev)
+        except Exception as e:
+            mc_leg = dict(error=repr(e))
+            if world > 1:
+                raise
+
     counts = torch.tensor([float(n_pass), float(N_FEATURES)], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t_val, op=dist.ReduceOp.MAX)
@@ -327,6 +569,8 @@ def main():
                               algorithmic_bytes=jac_bytes, kernel_us=stages["jac_gate"], peak_source=peak_src,
                               note="one frame's working set is L2-resident: latency-bound, not HBM-bound (SURVEY 8d)"),
             north_star_frame=target,
+            other_cases=extras,
+            multi_trajectory=mc_leg,
             clocks=clocks)
         if not args.no_cpu_baseline:
             try:

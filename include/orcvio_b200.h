@@ -104,6 +104,12 @@ int orcvio_get_state(orcvio_handle* h, OrcvioState* out);
 int orcvio_get_cov(orcvio_handle* h, double* P, int cap, int* D);
 /* getSwPoses, src/orcvio.cpp:3030-3042: per clone R (9, row-major) + p (3); ids optional. */
 int orcvio_get_window(orcvio_handle* h, double* poses12, long long* ids, double* times, int cap);
+/* getTcw, src/orcvio.cpp:2978-2988: camera pose (camera -> world rotation, row-major, and camera position) of the
+ * clone of the current state id. */
+int orcvio_get_tcw(orcvio_handle* h, double R_c2w[9], double t_c_w[3]);
+/* The pose log processFeatures appends to (output_dir + "state_est_geo_feat.txt", src/orcvio.cpp:422, 640-645): one
+ * "t tx ty tz qx qy qz qw" line per published frame, t relative to take-off.  path = NULL or "" closes it. */
+int orcvio_set_pose_log(orcvio_handle* h, const char* path);
 /* getMSCKFMapPointPositions, src/orcvio.cpp:3059-3062 */
 int orcvio_get_map_points(orcvio_handle* h, long long* ids, double* xyz, int cap);
 /* state_server.feature_states (hybrid MSCKF / EKF-SLAM mode, max_features_in_one_grid > 0), in state order: feature id,
@@ -155,6 +161,20 @@ int orcvio_batch_set_initial_state(orcvio_batch* b, int i, double t, const doubl
 int orcvio_batch_process(orcvio_batch* b, const double* t_img, const OrcvioFeature* feats,
                          const int* feat_off, const OrcvioImu* imu, const int* imu_off, int* imu_used,
                          int* published);
+/* Whole-sequence replay of every filter of the batch (Monte-Carlo / multi-sequence replay): the lock-step
+ * loop over the frames runs inside the library, one orcvio_batch_process per frame.  Filter i: frames t_img[i*n_frames + f],
+ * features feats[i][feat_off[i*(n_frames+1) + f] .. feat_off[i*(n_frames+1) + f + 1]), IMU stream imu[i][0 .. n_imu[i]);
+ * before frame f the samples up to t_img + imu_window are offered, the filter consumes a prefix.  poses_out:
+ * n_filters x n_frames x 7 (p, q xyzw -- a line of the reference's state_est_geo_feat.txt); ok_out[i] = every frame
+ * published.  Several batches may replay concurrently from different host threads. */
+int orcvio_batch_replay(orcvio_batch* b, int n_frames, const double* t_img, const OrcvioFeature* const* feats,
+                        const int* feat_off, const OrcvioImu* const* imu, const int* n_imu, double imu_window,
+                        double* poses_out, int* ok_out);
+/* The reference's trajectory logger (System::publishGroundtruth, ros_wrapper/src/orcvio/src/System.cpp:885-943) for a
+ * batch of trajectories, on the device: first-pose SE(3) alignment, then per trajectory the mean orientation error
+ * (deg), mean position error (m), position RMSE (m) and final position error (m) -> out4 (n_traj x 4).  Poses are
+ * n_traj x n_frames x 7 (p, q xyzw, Hamilton), host pointers. */
+int orcvio_trajectory_metrics(const double* est_pose7, const double* gt_pose7, int n_traj, int n_frames, double* out4);
 int orcvio_batch_get_state(orcvio_batch* b, int i, OrcvioState* out);
 int orcvio_batch_get_cov(orcvio_batch* b, int i, double* P, int cap, int* D);
 int orcvio_batch_get_frame_stats(orcvio_batch* b, int i, OrcvioFrameStats* out);

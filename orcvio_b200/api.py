@@ -81,6 +81,10 @@ def lib():
     L.orcvio_batch_set_initial_state.argtypes = [vp, C.c_int, C.c_double, dp, dp, dp, dp, dp]
     L.orcvio_batch_process.argtypes = [vp, dp, vp, ip, vp, ip, ip, ip]
     L.orcvio_batch_get_state.argtypes = [vp, C.c_int, C.POINTER(OrcvioState)]
+    L.orcvio_batch_replay.argtypes = [vp, C.c_int, dp, vp, ip, vp, ip, C.c_double, dp, ip]
+    L.orcvio_trajectory_metrics.argtypes = [dp, dp, C.c_int, C.c_int, dp]
+    L.orcvio_get_tcw.argtypes = [vp, dp, dp]
+    L.orcvio_set_pose_log.argtypes = [vp, C.c_char_p]
     L.orcvio_batch_get_cov.argtypes = [vp, C.c_int, dp, C.c_int, ip]
     L.orcvio_batch_get_frame_stats.argtypes = [vp, C.c_int, C.POINTER(OrcvioFrameStats)]
     L.orcvio_batch_feature_updates.restype = C.c_longlong
@@ -253,6 +257,18 @@ class OrcVIO:
                                              _ip(st), _dp(g), cap)
         return ids[:n], ph[:n], st[:n], g[:n]
 
+    def getTcw(self):
+        """src/orcvio.cpp:2978-2988 -> (R camera->world 3x3, camera position)."""
+        R = np.zeros(9)
+        t = np.zeros(3)
+        if self._L.orcvio_get_tcw(self._h, _dp(R), _dp(t)) != 0:
+            raise RuntimeError("orcvio_get_tcw failed")
+        return R.reshape(3, 3), t
+
+    def set_pose_log(self, path):
+        """The state_est_geo_feat.txt side effect of processFeatures (src/orcvio.cpp:422, 640-645)."""
+        return self._L.orcvio_set_pose_log(self._h, None if path is None else str(path).encode())
+
     def feature_states(self, cap=256):
         """state_server.feature_states (hybrid mode) in state order:
         (ids, anchor state ids, inverse depths, obs_anchor (n, 2), world positions (n, 3))."""
@@ -376,6 +392,25 @@ class Batch:
         if rc != 0:
             raise RuntimeError(f"orcvio_batch_process failed: {rc}")
         return used, pub
+
+    def replay(self, t_img, feats, feat_off, imus, imu_window=0.02):
+        """Whole-sequence replay (orcvio_batch_replay).  t_img (n, F); feats: list of n struct arrays (all frames of a
+        filter concatenated); feat_off (n, F + 1); imus: list of n struct arrays.  Returns (poses (n, F, 7), ok (n,)).
+        The call releases the GIL: several batches replay concurrently from Python threads."""
+        t_img = np.ascontiguousarray(t_img, dtype=np.float64)
+        n, F = t_img.shape
+        assert n == self.n
+        feat_off = np.ascontiguousarray(feat_off, dtype=np.int32)
+        fptr = (C.c_void_p * n)(*[f.ctypes.data for f in feats])
+        iptr = (C.c_void_p * n)(*[m.ctypes.data for m in imus])
+        n_imu = np.array([len(m) for m in imus], dtype=np.int32)
+        poses = np.zeros((n, F, 7))
+        ok = np.zeros(n, dtype=np.int32)
+        rc = self._L.orcvio_batch_replay(self._h, F, _dp(t_img), fptr, _ip(feat_off), iptr, _ip(n_imu), float(imu_window),
+                                         _dp(poses), _ip(ok))
+        if rc != 0:
+            raise RuntimeError(f"orcvio_batch_replay failed: {rc}")
+        return poses, ok
 
     def state(self, i):
         s = OrcvioState()
@@ -519,6 +554,20 @@ class Frame:
 
 
 # ---------------------------------------------------------------- stage-level calls
+def trajectory_metrics(est_pose7, gt_pose7):
+    """System::publishGroundtruth on the device for a batch of trajectories (orcvio_trajectory_metrics):
+    (n, F, 7) poses (p, q xyzw) -> (n, 4): mean orientation error (deg), mean position error, position RMSE, final
+    position error after first-pose alignment."""
+    e = np.ascontiguousarray(est_pose7, dtype=np.float64)
+    g = np.ascontiguousarray(gt_pose7, dtype=np.float64)
+    assert e.shape == g.shape and e.ndim == 3 and e.shape[2] == 7
+    out = np.zeros((e.shape[0], 4))
+    rc = lib().orcvio_trajectory_metrics(_dp(e), _dp(g), e.shape[0], e.shape[1], _dp(out))
+    if rc != 0:
+        raise RuntimeError(f"orcvio_trajectory_metrics failed: {rc}")
+    return out
+
+
 def object_residuals(frames_wTc, wTo, shape, kps, zs, zb, left=True, new_residual=False):
     """Stage 3 functor evaluation (O1-O4): returns dict(fvec, fjac_cam, fjac_obj, zs_num, cam_pose_se3)."""
     L = lib()

@@ -31,6 +31,7 @@ SOURCES = {
     "obj_kernel.cu": [],
     "ekf_kernel.cu": [],
     "hybrid_kernel.cu": [],
+    "metrics_kernel.cu": [],
     "batch.cu": [],
     "objects.cu": [],
     "capi.cu": [],

@@ -825,8 +825,102 @@ static void append_candidates(Batch::PhaseWork& w, int fi, std::vector<CandBuild
 
 int Batch::process(const double* t_img, const OrcvioFeature* feats, const int* feat_off,
                    const OrcvioImu* imu, const int* imu_off, int* imu_used, int* published) {
+  std::vector<const OrcvioFeature*> fp(B_);
+  std::vector<const OrcvioImu*> ip(B_);
+  std::vector<int> nf(B_), ni(B_);
+  for (int fi = 0; fi < B_; ++fi) {
+    fp[fi] = feats + feat_off[fi];
+    nf[fi] = feat_off[fi + 1] - feat_off[fi];
+    ip[fi] = imu + imu_off[fi];
+    ni[fi] = imu_off[fi + 1] - imu_off[fi];
+  }
+  return process_ptrs(t_img, fp.data(), nf.data(), ip.data(), ni.data(), imu_used, published);
+}
+
+// rotationToQuaternion, include/orcvio/utils/math_utils.hpp:188-227 (Hamilton, x y z w, w >= 0)
+void rotation_to_quat_xyzw(const double* R, double* q) {
+  const double tr = R[0] + R[4] + R[8];
+  const double score[4] = {R[0], R[4], R[8], tr};
+  int best = 0;
+  for (int i = 1; i < 4; ++i)
+    if (score[i] > score[best]) best = i;
+  if (best == 0) {
+    q[0] = std::sqrt(1 + 2 * R[0] - tr) / 2.0;
+    q[1] = (R[1] + R[3]) / (4 * q[0]); q[2] = (R[2] + R[6]) / (4 * q[0]); q[3] = (R[7] - R[5]) / (4 * q[0]);
+  } else if (best == 1) {
+    q[1] = std::sqrt(1 + 2 * R[4] - tr) / 2.0;
+    q[0] = (R[1] + R[3]) / (4 * q[1]); q[2] = (R[5] + R[7]) / (4 * q[1]); q[3] = (R[2] - R[6]) / (4 * q[1]);
+  } else if (best == 2) {
+    q[2] = std::sqrt(1 + 2 * R[8] - tr) / 2.0;
+    q[0] = (R[2] + R[6]) / (4 * q[2]); q[1] = (R[5] + R[7]) / (4 * q[2]); q[3] = (R[3] - R[1]) / (4 * q[2]);
+  } else {
+    q[3] = std::sqrt(1 + tr) / 2.0;
+    q[0] = (R[7] - R[5]) / (4 * q[3]); q[1] = (R[2] - R[6]) / (4 * q[3]); q[2] = (R[3] - R[1]) / (4 * q[3]);
+  }
+  if (q[3] < 0)
+    for (int i = 0; i < 4; ++i) q[i] = -q[i];
+  const double n = std::sqrt((q[0] * q[0] + q[1] * q[1]) + (q[2] * q[2] + q[3] * q[3]));
+  for (int i = 0; i < 4; ++i) q[i] /= n;
+}
+
+// Whole-sequence replay (Monte-Carlo / multi-sequence batches): every filter's IMU stream and frames are
+// handed over once; the lock-step loop over the frames runs here, so a replay costs the caller one call (the callers
+// drive several batches from as many host threads).  poses_out: n_filters x n_frames x 7, the IMU pose after every
+// frame (position, quaternion x y z w: one line of the reference's state_est_geo_feat.txt log, src/orcvio.cpp:643-645);
+// ok_out[i] = 0 when some frame of filter i was not published.
+int Batch::replay(int n_frames, const double* t_img, const OrcvioFeature* const* feats, const int* feat_off,
+                  const OrcvioImu* const* imu, const int* n_imu, double imu_window, double* poses_out, int* ok_out) {
+  std::vector<const OrcvioFeature*> fp(B_);
+  std::vector<const OrcvioImu*> ip(B_);
+  std::vector<int> nf(B_), ni(B_), cursor(B_, 0), used(B_), pub(B_);
+  std::vector<double> tt(B_);
+  for (int i = 0; i < B_; ++i) ok_out[i] = 1;
+  for (int f = 0; f < n_frames; ++f) {
+    for (int i = 0; i < B_; ++i) {
+      const int* fo = feat_off + (size_t)i * (n_frames + 1);
+      tt[i] = t_img[(size_t)i * n_frames + f];
+      fp[i] = feats[i] + fo[f];
+      nf[i] = fo[f + 1] - fo[f];
+      // the samples up to the image stamp (+ a margin): what a driver would have queued by now; the filter consumes a
+      // prefix of them (batchImuProcessing :664-724) and the rest is offered again with the next frame
+      int k1 = cursor[i];
+      while (k1 < n_imu[i] && imu[i][k1].t <= tt[i] + imu_window) ++k1;
+      ip[i] = imu[i] + cursor[i];
+      ni[i] = k1 - cursor[i];
+    }
+    const int rc = process_ptrs(tt.data(), fp.data(), nf.data(), ip.data(), ni.data(), used.data(), pub.data());
+    if (rc != ORCVIO_OK) return rc;
+    for (int i = 0; i < B_; ++i) {
+      cursor[i] += used[i];
+      if (!pub[i]) ok_out[i] = 0;
+      const double* im = f_[i].imu_mirror.data();
+      double* o = poses_out + ((size_t)i * n_frames + f) * 7;
+      for (int k = 0; k < 3; ++k) o[k] = im[IM_P + k];
+      rotation_to_quat_xyzw(im + IM_R, o + 3);
+    }
+  }
+  return ORCVIO_OK;
+}
+
+int Batch::process_ptrs(const double* t_img, const OrcvioFeature* const* featp, const int* nfeat,
+                        const OrcvioImu* const* imup, const int* nimu_v, int* imu_used, int* published) {
   if (!ok_) return ORCVIO_ERR_CUDA;
   const int L = ORCVIO_LEG;
+  // Capacity is checked before anything is touched: a frame either runs on every filter or leaves all of them as
+  // they were (a failure in the middle of the per-filter loop would leave host bookkeeping and device state apart).
+  if (!p_.prediction_only_flag)
+    for (int fi = 0; fi < B_; ++fi) {
+      const FilterHost& F = f_[fi];
+      const OrcvioFeature* ft = featp[fi];
+      const int nf = nfeat[fi];
+      size_t fresh = 0;
+      for (int k = 0; k < nf; ++k) fresh += F.map_server.count((long long)ft[k].id) ? 0 : 1;
+      if (fresh > F.free_slots.size()) {
+        std::fprintf(stderr, "[orcvio_b200] feature table full (capacity %d live tracks per filter, filter %d needs %zu more)\n",
+                     Fcap_, fi, fresh - F.free_slots.size());
+        return ORCVIO_ERR_CAPACITY;
+      }
+    }
   // ---------------------------------------------------------------- A: propagation inputs
   std::vector<PropSample> samples;
   std::vector<int> samp_off(B_ + 1, 0), Dvec(B_, 0), Nvec(B_, 0), Evec(B_, 0);
@@ -844,8 +938,8 @@ int Batch::process(const double* t_img, const OrcvioFeature* feats, const int* f
     published[fi] = 0;
     imu_used[fi] = 0;
     samp_off[fi + 1] = (int)samples.size();
-    const OrcvioImu* im = imu + imu_off[fi];
-    const int nimu = imu_off[fi + 1] - imu_off[fi];
+    const OrcvioImu* im = imup[fi];
+    const int nimu = nimu_v[fi];
     const double ti = t_img[fi];
     if (!F.first_features) {   // :504-510
       if (nimu > 0 && (im[0].t - ti - p_.td <= 0.0)) F.first_features = true;
@@ -903,8 +997,8 @@ int Batch::process(const double* t_img, const OrcvioFeature* feats, const int* f
 
     // addFeatureObservations :1016-1068
     if (!p_.prediction_only_flag) {
-      const OrcvioFeature* ft = feats + feat_off[fi];
-      const int nf = feat_off[fi + 1] - feat_off[fi];
+      const OrcvioFeature* ft = featp[fi];
+      const int nf = nfeat[fi];
       const long long sid = F.state_id;
       const int curr_feature_num = (int)F.map_server.size();
       int tracked = 0;
@@ -913,8 +1007,10 @@ int Batch::process(const double* t_img, const OrcvioFeature* feats, const int* f
         const long long id = (long long)m.id;
         auto it = F.map_server.find(id);
         if (it == F.map_server.end()) {
-          if (F.free_slots.empty()) {
+          if (F.free_slots.empty()) {      // (cannot happen after the pre-pass; if it does the batch is unusable)
             std::fprintf(stderr, "[orcvio_b200] feature table full (capacity %d)\n", Fcap_);
+            ok_ = false;
+            err_ = "feature table overflow in the middle of a frame";
             return ORCVIO_ERR_CAPACITY;
           }
           Track tr;
@@ -1724,7 +1820,10 @@ int Batch::process(const double* t_img, const OrcvioFeature* feats, const int* f
   int herr = 0;
   CK(cudaMemcpy(&herr, dErr_, sizeof(int), cudaMemcpyDeviceToHost));
   if (herr) {
+    // the frame's update is incomplete on the device while the host bookkeeping has moved on: later calls fail loudly
     std::fprintf(stderr, "[orcvio_b200] QR front overflow\n");
+    ok_ = false;
+    err_ = "QR front overflow";
     return ORCVIO_ERR_CAPACITY;
   }
   for (int fi = 0; fi < B_; ++fi) {
@@ -1883,7 +1982,20 @@ int Batch::get_map_points(int i, long long* ids, double* xyz, int cap) {
 }
 
 int Batch::set_cov(int i, const double* P, int D) {
-  if (i < 0 || i >= B_ || D > ldp_) return ORCVIO_ERR_ARG;
+  if (i < 0 || i >= B_ || D > ldp_ || !P) return ORCVIO_ERR_ARG;
+  {
+    // the update path only uses the window columns of H: that equals the reference as long as the extrinsic / time-offset
+    // block of P (rows / columns 15..21) is zero (estimate_extrin = estimate_td = 0), so a covariance that breaks it is
+    // refused instead of silently diverging; D must be the filter's current dimension (or the setStateCov override)
+    const FilterHost& F = f_[i];
+    const int d_now = ORCVIO_LEG + 6 * (int)F.clones.size() + (int)F.feature_states.size();
+    const int d_ovr = (F.leg_dim_override >= 0 && F.num_clone_override >= 0) ? F.leg_dim_override + 6 * F.num_clone_override : -1;
+    if (D != d_now && D != d_ovr) return ORCVIO_ERR_ARG;
+    if (D == d_now && D != d_ovr)            // (the setStateCov hook re-defines the layout: LEG_DIM may be 15 there)
+      for (int r = 15; r < ORCVIO_LEG; ++r)
+        for (int c = 0; c < D; ++c)
+          if (P[(size_t)r * D + c] != 0.0 || P[(size_t)c * D + r] != 0.0) return ORCVIO_ERR_ARG;
+  }
   CK(cudaMemcpy2D(dP_ + (size_t)i * ldp_ * ldp_, ldp_ * sizeof(double), P, D * sizeof(double),
                   D * sizeof(double), D, cudaMemcpyHostToDevice));
   return ORCVIO_OK;

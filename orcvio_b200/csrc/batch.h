@@ -136,6 +136,10 @@ class Batch {
                          const double* bg, const double* ba);
   int process(const double* t_img, const OrcvioFeature* feats, const int* feat_off,
               const OrcvioImu* imu, const int* imu_off, int* imu_used, int* published);
+  int process_ptrs(const double* t_img, const OrcvioFeature* const* feats, const int* n_feats,
+                   const OrcvioImu* const* imu, const int* n_imu, int* imu_used, int* published);
+  int replay(int n_frames, const double* t_img, const OrcvioFeature* const* feats, const int* feat_off,
+             const OrcvioImu* const* imu, const int* n_imu, double imu_window, double* poses_out, int* ok_out);
   int get_state(int i, OrcvioState* out);
   int get_cov(int i, double* P, int cap, int* D);
   int set_cov(int i, const double* P, int D);
@@ -305,6 +309,8 @@ class Batch {
   void download_mirrors();
   void init_filter_device(int i);
 };
+
+void rotation_to_quat_xyzw(const double* R, double* q);
 
 int object_residuals(const double* frames_wTc, int T, const double* wTo, const double* shape, const double* kps,
                      int K, const double* zs, const double* zb, int flags, double* fvec, double* fjac_cam,

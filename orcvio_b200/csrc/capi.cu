@@ -21,6 +21,8 @@ struct orcvio_handle {
   orcvio_batch b;
   bool initialized = false;
   bool has_init = false;
+  std::FILE* pose_log = nullptr;           // state_est_geo_feat.txt (src/orcvio.cpp:422, 643-645)
+  ~orcvio_handle() { if (pose_log) std::fclose(pose_log); }
   double init_t = 0, init_q[4] = {0, 0, 0, 1}, init_p[3] = {0, 0, 0}, init_v[3] = {0, 0, 0},
          init_bg[3] = {0, 0, 0}, init_ba[3] = {0, 0, 0};
 };
@@ -119,7 +121,9 @@ int orcvio_initialize(orcvio_handle* h) {
 
 int orcvio_set_initial_state(orcvio_handle* h, double t, const double q[4], const double p[3],
                              const double v[3], const double bg[3], const double ba[3]) {
-  if (!h) return ORCVIO_ERR_ARG;
+  if (!h || !q || !p || !v) return ORCVIO_ERR_ARG;
+  // (once the filter has initialised itself -- gravity set -- a new initial state is ignored, like a second
+  // initial_use_gt block would be in the reference: :513 only runs while !is_gravity_set)
   h->has_init = true;
   h->init_t = t;
   std::memcpy(h->init_q, q, 4 * sizeof(double));
@@ -141,6 +145,16 @@ int orcvio_process_features(orcvio_handle* h, double t_img, const OrcvioFeature*
   if (used > 0) {   // erase the consumed prefix like the reference does (src/orcvio.cpp:718-719)
     std::memmove(imu, imu + used, sizeof(OrcvioImu) * (size_t)(*n_imu - used));
     *n_imu -= used;
+  }
+  if (pub && h->pose_log) {
+    // "timestamp tx ty tz qx qy qz qw", time relative to take-off (src/orcvio.cpp:640-645; default ostream precision)
+    FilterHost& F = h->b.batch->filter(0);
+    const double* im = F.imu_mirror.data();
+    double q[4];
+    rotation_to_quat_xyzw(im + IM_R, q);
+    std::fprintf(h->pose_log, "%.6g %.6g %.6g %.6g %.6g %.6g %.6g %.6g\n", F.imu_time - F.take_off_stamp, im[IM_P], im[IM_P + 1],
+                 im[IM_P + 2], q[0], q[1], q[2], q[3]);
+    std::fflush(h->pose_log);
   }
   return pub;
 }
@@ -175,6 +189,25 @@ int orcvio_get_window(orcvio_handle* h, double* poses12, long long* ids, double*
     if (times) times[c] = F.clones[c].time;
   }
   return n;
+}
+
+int orcvio_get_tcw(orcvio_handle* h, double R_c2w[9], double t_c_w[3]) {
+  if (!h || !h->initialized || !R_c2w || !t_c_w) return ORCVIO_ERR_ARG;
+  FilterHost& F = h->b.batch->filter(0);
+  if (F.clones.empty()) return ORCVIO_ERR_ARG;
+  // getTcw (src/orcvio.cpp:2978-2988): camera pose of the clone of the current state id = the newest clone
+  const double* c = F.clone_mirror.data() + (F.clones.size() - 1) * CL_STRIDE;
+  for (int k = 0; k < 9; ++k) R_c2w[k] = c[CL_RC + k];
+  for (int k = 0; k < 3; ++k) t_c_w[k] = c[CL_PC + k];
+  return ORCVIO_OK;
+}
+
+int orcvio_set_pose_log(orcvio_handle* h, const char* path) {
+  if (!h) return ORCVIO_ERR_ARG;
+  if (h->pose_log) { std::fclose(h->pose_log); h->pose_log = nullptr; }
+  if (!path || !*path) return ORCVIO_OK;
+  h->pose_log = std::fopen(path, "w");      // (ofstream::trunc, src/orcvio.cpp:422)
+  return h->pose_log ? ORCVIO_OK : ORCVIO_ERR_ARG;
 }
 
 int orcvio_get_map_points(orcvio_handle* h, long long* ids, double* xyz, int cap) {
@@ -258,6 +291,18 @@ int orcvio_batch_process(orcvio_batch* b, const double* t_img, const OrcvioFeatu
                          const OrcvioImu* imu, const int* imu_off, int* imu_used, int* published) {
   if (!b) return ORCVIO_ERR_ARG;
   return b->batch->process(t_img, feats, feat_off, imu, imu_off, imu_used, published);
+}
+
+int orcvio_batch_replay(orcvio_batch* b, int n_frames, const double* t_img, const OrcvioFeature* const* feats,
+                        const int* feat_off, const OrcvioImu* const* imu, const int* n_imu, double imu_window,
+                        double* poses_out, int* ok_out) {
+  if (!b || n_frames < 0 || !t_img || !feats || !feat_off || !imu || !n_imu || !poses_out || !ok_out) return ORCVIO_ERR_ARG;
+  return b->batch->replay(n_frames, t_img, feats, feat_off, imu, n_imu, imu_window, poses_out, ok_out);
+}
+
+int orcvio_trajectory_metrics(const double* est_pose7, const double* gt_pose7, int n_traj, int n_frames, double* out4) {
+  if (!est_pose7 || !gt_pose7 || !out4) return ORCVIO_ERR_ARG;
+  return ob::trajectory_metrics(est_pose7, gt_pose7, n_traj, n_frames, out4);
 }
 
 int orcvio_batch_get_state(orcvio_batch* b, int i, OrcvioState* out) {

@@ -39,10 +39,96 @@ def pack_frame(seqs, fi, imu_cursor):
             np.array(feat_off, dtype=np.int32), np.concatenate(imus), np.array(imu_off, dtype=np.int32))
 
 
-def make_sequences(config, traj_ids, n_frames, feats_per_frame, overrides, n_landmarks=3000):
-    return [synth.make_sequence(synth.SynthSpec(config=config, seed=int(t), n_frames=n_frames,
-                                                feats_per_frame=feats_per_frame, overrides=overrides,
-                                                n_landmarks=n_landmarks)) for t in traj_ids]
+def _make_one(args):
+    config, t, n_frames, feats_per_frame, overrides, n_landmarks = args
+    return synth.make_sequence(synth.SynthSpec(config=config, seed=int(t), n_frames=n_frames,
+                                               feats_per_frame=feats_per_frame, overrides=overrides,
+                                               n_landmarks=n_landmarks))
+
+
+def make_sequences(config, traj_ids, n_frames, feats_per_frame, overrides, n_landmarks=3000, workers=1):
+    """Synthetic sequences of the given trajectories (seed = trajectory id); `workers` > 1 spreads the (pure Python)
+    generator over processes."""
+    jobs = [(config, int(t), n_frames, feats_per_frame, overrides, n_landmarks) for t in traj_ids]
+    if workers <= 1 or len(jobs) < 4:
+        return [_make_one(j) for j in jobs]
+    from concurrent.futures import ProcessPoolExecutor
+    import multiprocessing as mp
+    with ProcessPoolExecutor(max_workers=workers, mp_context=mp.get_context("fork")) as ex:
+        return list(ex.map(_make_one, jobs, chunksize=max(1, len(jobs) // (4 * workers))))
+
+
+def pack_replay(seqs, n_frames):
+    """Arrays of a whole-sequence replay (api.Batch.replay) for the given sequences."""
+    n = len(seqs)
+    t_img = np.zeros((n, n_frames))
+    feat_off = np.zeros((n, n_frames + 1), dtype=np.int32)
+    feats, imus = [], []
+    for i, s in enumerate(seqs):
+        fr = s["frames"][:n_frames]
+        t_img[i] = [t for t, _ in fr]
+        feat_off[i, 1:] = np.cumsum([len(f) for _, f in fr])
+        feats.append(api.feats_array(np.concatenate([f for _, f in fr]) if fr else np.zeros((0, 9))))
+        imus.append(api.imu_array(s["imu"]))
+    return t_img, feats, feat_off, imus
+
+
+def gt_poses(seqs, n_frames):
+    g = np.zeros((len(seqs), n_frames, 7))
+    for i, s in enumerate(seqs):
+        for f, (_, p, q) in enumerate(s["gt"][:n_frames]):
+            g[i, f, :3] = p
+            g[i, f, 3:] = q
+    return g
+
+
+def run_replay(cfg_path, seqs, traj_ids, n_threads=1):
+    """The local trajectories, split into `n_threads` batches that replay concurrently from as many host threads (the
+    host bookkeeping of a filter is serial code: the batches are what spreads it over the cores, and their kernels
+    overlap on the device).  Returns (records, dict(seconds, feature_updates, kernel_launches, poses))."""
+    import threading
+    import time
+    n = len(seqs)
+    n_frames = min(len(s["frames"]) for s in seqs)
+    n_threads = max(1, min(n_threads, n))
+    groups = [list(range(k, n, n_threads)) for k in range(n_threads)]
+    batches, packs = [], []
+    for g in groups:
+        b = api.Batch(cfg_path, len(g))
+        for j, i in enumerate(g):
+            it = seqs[i]["init"]
+            b.set_initial_state(j, it["t"], it["quat"], it["pos"], it["vel"], it["bg"], it["ba"])
+        batches.append(b)
+        packs.append(pack_replay([seqs[i] for i in g], n_frames))
+    poses = np.zeros((n, n_frames, 7))
+    ok = np.zeros(n)
+    errors = []
+
+    def work(k):
+        try:
+            p, o = batches[k].replay(*packs[k])
+            poses[groups[k]] = p
+            ok[groups[k]] = o
+        except Exception as e:       # surfaced after the join
+            errors.append(e)
+
+    t0 = time.perf_counter()
+    threads = [threading.Thread(target=work, args=(k,)) for k in range(n_threads)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    seconds = time.perf_counter() - t0
+    if errors:
+        raise errors[0]
+    met = api.trajectory_metrics(poses, gt_poses(seqs, n_frames))      # on the device (System.cpp:885-943)
+    rec = np.zeros((n, len(RECORD)))
+    fu = sum(b.feature_updates() for b in batches)
+    for i in range(n):
+        rec[i] = [traj_ids[i], n_frames, *poses[i, -1, :3], met[i, 1], fu / max(n, 1), ok[i]]
+    info = dict(seconds=seconds, feature_updates=fu, kernel_launches=sum(b.kernel_launches() for b in batches),
+                poses=poses, metrics=met, n_frames=n_frames, n_batches=n_threads)
+    return rec, info
 
 
 def run_local(cfg_path, seqs, traj_ids):

@@ -37,3 +37,81 @@ def test_batch_equals_single_filters():
         assert rec[i, 5] < 0.5                       # ATE vs synthetic ground truth [m]
     out = mc.gather_records(rec, len(ids), 0, 1)
     np.testing.assert_array_equal(out[:, 0], np.arange(len(ids)))
+
+
+def _metrics_numpy(est, gt):
+    """System::publishGroundtruth restated (ros_wrapper/src/orcvio/src/System.cpp:885-943), one trajectory."""
+    from oracle import mathutils as mu
+
+    def q2R(q):
+        x, y, z, w = q
+        return np.array([[1 - 2 * (y * y + z * z), 2 * (x * y - w * z), 2 * (x * z + w * y)],
+                         [2 * (x * y + w * z), 1 - 2 * (x * x + z * z), 2 * (y * z - w * x)],
+                         [2 * (x * z - w * y), 2 * (y * z + w * x), 1 - 2 * (x * x + y * y)]])
+
+    def T(p7):
+        M = np.eye(4)
+        M[:3, :3] = q2R(p7[3:])
+        M[:3, 3] = p7[:3]
+        return M
+
+    A = T(gt[0]) @ np.linalg.inv(T(est[0]))
+    e_ori, e_pos = [], []
+    for k in range(len(est)):
+        Tc = A @ T(est[k])
+        e_pos.append(np.linalg.norm(Tc[:3, 3] - gt[k, :3]))
+        Rd = Tc[:3, :3] @ q2R(gt[k, 3:]).T                     # q_corrected (x) q_gt^-1
+        ang = np.arccos(np.clip((np.trace(Rd) - 1) / 2, -1, 1))
+        e_ori.append(np.degrees(2 * np.sin(ang / 2)))          # 2 |vec(q)| of a rotation by `ang`
+    e_pos = np.array(e_pos)
+    return np.array([np.mean(e_ori), e_pos.mean(), np.sqrt((e_pos ** 2).mean()), e_pos[-1]])
+
+
+def test_threaded_replay_equals_lock_step_loop_and_device_metrics():
+    """orcvio_batch_replay from several host threads (one batch each) == the per-frame orcvio_batch_process loop, bit
+    for bit; the on-device trajectory metrics == the reference logger's arithmetic."""
+    ids = [0, 1, 2, 3, 4, 5, 6]
+    seqs = mc.make_sequences("unity", ids, 24, 60, dict(if_ZUPT_valid=0), n_landmarks=3000, workers=2)
+    cfg = H.write_cfg(seqs[0]["cfg"])
+    rec0, b = mc.run_local(cfg, seqs, ids)
+    rec1, info = mc.run_replay(cfg, seqs, ids, n_threads=3)
+    assert info["n_batches"] == 3 and np.all(rec1[:, 7] == 1.0)
+    np.testing.assert_array_equal(rec1[:, 2:5], rec0[:, 2:5])              # final positions: identical
+    assert info["feature_updates"] == b.feature_updates()
+    gt = mc.gt_poses(seqs, info["n_frames"])
+    for i in range(len(ids)):
+        ref = _metrics_numpy(info["poses"][i], gt[i])
+        np.testing.assert_allclose(info["metrics"][i, 1:], ref[1:], rtol=1e-9, atol=1e-9)
+        # (the restatement goes through arccos of the trace, which loses digits at small angles)
+        np.testing.assert_allclose(info["metrics"][i, 0], ref[0], rtol=1e-5, atol=1e-7)
+        # position part == the first-pose translation-only alignment only when the first poses agree in rotation
+        assert info["metrics"][i, 1] < 0.5
+
+
+def test_tcw_and_pose_log(tmp_path):
+    seq = mc.make_sequences("unity", [0], 8, 40, dict(if_ZUPT_valid=0), n_landmarks=1500)[0]
+    vio = api.OrcVIO(H.write_cfg(seq["cfg"]))
+    assert vio.initialize()
+    log = tmp_path / "state_est_geo_feat.txt"
+    assert vio.set_pose_log(log) == 0
+    k = 0
+    for (t_img, feats) in seq["frames"]:
+        k1 = k
+        while k1 < len(seq["imu"]) and seq["imu"][k1][0] <= t_img + 0.02:
+            k1 += 1
+        vio.push_imu(seq["imu"][k:k1])
+        k = k1
+        assert vio.processFeatures(t_img, feats)
+    st = vio.state()
+    R, t = vio.getTcw()
+    Rb = np.array(st.R).reshape(3, 3)
+    T = np.array(seq["cfg"]["T_cam_imu"]).reshape(4, 4)
+    R_b2c = T[:3, :3]
+    t_c_b = -R_b2c.T @ T[:3, 3]
+    np.testing.assert_allclose(R, Rb @ R_b2c.T, atol=1e-12)              # orientation_cam = R_b2w R_b2c^T (:950-955)
+    np.testing.assert_allclose(t, np.array(st.p) + Rb @ t_c_b, atol=1e-12)
+    vio.set_pose_log(None)
+    rows = np.loadtxt(log)
+    assert rows.shape == (len(seq["frames"]), 8)
+    np.testing.assert_allclose(rows[-1, 1:4], np.array(st.p), rtol=1e-5, atol=1e-5)
+    assert abs(np.linalg.norm(rows[-1, 4:]) - 1) < 1e-4 and np.all(np.diff(rows[:, 0]) > 0)

@@ -69,3 +69,17 @@ def test_gather_records_world2_gloo():
         np.testing.assert_array_equal(out[:, 0], np.arange(n_traj))
         np.testing.assert_allclose(out[:, 5], 1e-3 * (np.arange(n_traj) + 1))
     np.testing.assert_array_equal(results[0], results[1])
+
+
+def test_pack_replay_layout():
+    seqs = mc.make_sequences("unity", [0, 1, 2], 4, 12, dict(if_ZUPT_valid=0), n_landmarks=800, workers=2)
+    t_img, feats, feat_off, imus = mc.pack_replay(seqs, 4)
+    assert t_img.shape == (3, 4) and feat_off.shape == (3, 5) and len(feats) == len(imus) == 3
+    for i, s in enumerate(seqs):
+        assert feat_off[i, 0] == 0 and feat_off[i, -1] == len(feats[i])
+        for f, (t, fr) in enumerate(s["frames"][:4]):
+            assert t_img[i, f] == t
+            np.testing.assert_array_equal(feats[i]["id"][feat_off[i, f]:feat_off[i, f + 1]], fr[:, 0].astype(np.uint64))
+        assert len(imus[i]) == len(s["imu"])
+    g = mc.gt_poses(seqs, 4)
+    assert g.shape == (3, 4, 7) and np.allclose(np.linalg.norm(g[..., 3:], axis=-1), 1.0)
