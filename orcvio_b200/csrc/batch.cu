@@ -185,6 +185,7 @@ Batch::Batch(const Params& p, int n) : p_(p), B_(n) {
   CK(cudaEventCreateWithFlags(&ev_fork_, cudaEventDisableTiming));
   CK(cudaEventCreateWithFlags(&ev_join_, cudaEventDisableTiming));
   CK(cudaEventCreateWithFlags(&ev_ls_, cudaEventDisableTiming));
+  if (env_int("ORCVIO_BLOCKING_SYNC", 0)) CK(cudaEventCreateWithFlags(&ev_block_, cudaEventDisableTiming | cudaEventBlockingSync));
   {
     const char* e = std::getenv("ORCVIO_COMPRESS");
     compress_qr_ = e && std::string(e) == "qr" && !hybrid_;     // the dense EKF-feature rows exist only in the whitened form
@@ -251,6 +252,8 @@ Batch::Batch(const Params& p, int n) : p_(p), B_(n) {
   }
   CK(cudaMalloc(&dErr_, sizeof(int)));
   CK(cudaMemset(dErr_, 0, sizeof(int)));
+  CK(cudaMallocHost(&hErrPin_, sizeof(int)));
+  *hErrPin_ = 0;
   // global fallback front for very wide windows (long tracks): 2*(6 Ncap)+8 rows
   front_stride_ = (size_t)(2 * ncap + 8) * (size_t)(256 + 2);
   CK(cudaMalloc(&dFront_, nB * front_stride_ * sizeof(double)));
@@ -272,6 +275,59 @@ Batch::Batch(const Params& p, int n) : p_(p), B_(n) {
   CK(cudaMallocHost(&hClones_, nB * Ncap_ * CL_STRIDE * sizeof(double)));
   CK(cudaMallocHost(&hDx_, nB * ldp_ * sizeof(double)));
   std::memset(hImu_, 0, nB * IM_STRIDE * sizeof(double));
+  if (B_ > 1) prereserve();
+}
+
+// Multi-trajectory batches: size the growable buffers for a typical frame up front.  Growing them later works (x 2
+// policy) but every growth is a cudaFree / cudaMallocHost, i.e. a device-wide synchronisation -- with several batches
+// replaying from as many host threads those stalls hit every thread at once.
+// End of a phase of process(): the host needs the downloaded results.  A single filter spins (lowest latency); the
+// batches of a multi-trajectory replay block on an event instead, so that a thread waiting for its kernels leaves its
+// core to the bookkeeping of another batch.
+void Batch::wait_stream() {
+  if (B_ > 1 && ev_block_) {
+    CK(cudaEventRecord(ev_block_, stream_));
+    CK(cudaEventSynchronize(ev_block_));
+  } else {
+    CK(cudaStreamSynchronize(stream_));
+  }
+}
+
+void Batch::prereserve() {
+  const size_t nB = (size_t)B_;
+  const size_t cands = nB * 192, rows = cands * 9, obs = cands * 6;
+  ensure_scratch(cands, rows * 36, rows, nB * 40 * 36 * 37);
+  const size_t tiles = nB * 48;
+  if (tiles > tilerows_cap_) {
+    tilerows_cap_ = tiles;
+    CK(cudaMalloc(&dTileRows_, tilerows_cap_ * sizeof(int)));
+  }
+  const size_t need_a = (rows + 64 * nB + 16) * (size_t)ldr_;
+  if (need_a > amat_cap_) {
+    amat_cap_ = need_a;
+    CK(cudaMalloc(&dAmat_, amat_cap_ * sizeof(double)));
+  }
+  const size_t need_p = nB * 12 * 4096;
+  if (need_p > part_cap_) {
+    part_cap_ = need_p;
+    CK(cudaMalloc(&dPart_, part_cap_ * sizeof(double)));
+  }
+  const size_t blob_bytes = cands * sizeof(Cand) + obs * (sizeof(int) + 2 * sizeof(double)) + tiles * sizeof(Tile) +
+                            nB * (sizeof(FilterWork) + 64) + cands * 2 * sizeof(int) + (size_t)(64 << 10);
+  blob_.ensure_pinned(blob_bytes);
+  if (blob_bytes > blob_.dev_cap) {
+    blob_.dev_cap = blob_bytes;
+    CK(cudaMalloc(&blob_.dev, blob_.dev_cap));
+  }
+  if (hybrid_) {
+    HybridBufs& hb = *hyb_;
+    hb.hd_cap = nB * (size_t)(2 * Emax_ + 16 * 9) * ldr_;
+    CK(cudaMalloc(&hb.dHd, hb.hd_cap * sizeof(double)));
+    hb.spec_cap = nB * 64;
+    CK(cudaMalloc(&hb.dFinal, hb.spec_cap * 3 * sizeof(double)));
+    CK(cudaMalloc(&hb.dSpecStatus, hb.spec_cap * sizeof(int)));
+    CK(cudaMallocHost(&hb.hSpecStatus, hb.spec_cap * sizeof(int)));
+  }
 }
 
 Batch::~Batch() {
@@ -294,12 +350,14 @@ Batch::~Batch() {
   if (blob_.dev) cudaFree(blob_.dev);
   if (blob_.pinned) cudaFreeHost(blob_.pinned);
   cudaFreeHost(hImu_); cudaFreeHost(hClones_); cudaFreeHost(hDx_);
+  if (hErrPin_) cudaFreeHost(hErrPin_);
   if (hStatus_) cudaFreeHost(hStatus_);
   if (hGamma_) cudaFreeHost(hGamma_);
   for (auto& e : ev_) cudaEventDestroy(e);
   if (ev_fork_) cudaEventDestroy(ev_fork_);
   if (ev_join_) cudaEventDestroy(ev_join_);
   if (ev_ls_) cudaEventDestroy(ev_ls_);
+  if (ev_block_) cudaEventDestroy(ev_block_);
   if (stream2_) cudaStreamDestroy(stream2_);
   if (stream_up_) cudaStreamDestroy(stream_up_);
   if (ev_up_) cudaEventDestroy(ev_up_);
@@ -395,6 +453,7 @@ void Batch::download_mirrors() {
   CK(cudaMemcpyAsync(hImu_, dImu_, (size_t)B_ * IM_STRIDE * sizeof(double), cudaMemcpyDeviceToHost, stream_));
   CK(cudaMemcpyAsync(hClones_, dClones_, (size_t)B_ * Ncap_ * CL_STRIDE * sizeof(double),
                      cudaMemcpyDeviceToHost, stream_));
+  CK(cudaMemcpyAsync(hErrPin_, dErr_, sizeof(int), cudaMemcpyDeviceToHost, stream_));
 }
 
 // ---------------------------------------------------------------------------------------
@@ -1160,7 +1219,7 @@ int Batch::process_ptrs(const double* t_img, const OrcvioFeature* const* featp, 
       CK(cudaEventRecord(ev_[7], stream_));
     }
     // the blob is reused by the next phase: wait for the upload + kernels reading it
-    CK(cudaStreamSynchronize(stream_));
+    wait_stream();
     if (profiling_) {
       float ms = 0;
       cudaEventElapsedTime(&ms, ev_[6], ev_[7]);
@@ -1367,7 +1426,7 @@ int Batch::process_ptrs(const double* t_img, const OrcvioFeature* const* featp, 
       launch_triangulate(ta, stream_);
       ++launches_;
       CK(cudaMemcpyAsync(hb->hSpecStatus, hb->dSpecStatus, nS * sizeof(int), cudaMemcpyDeviceToHost, stream_));
-      CK(cudaStreamSynchronize(stream_));
+      wait_stream();
     }
   }
   for (int fi = 0; fi < B_; ++fi) {
@@ -1496,7 +1555,7 @@ int Batch::process_ptrs(const double* t_img, const OrcvioFeature* const* featp, 
     }
   }
   download_mirrors();
-  CK(cudaStreamSynchronize(stream_));
+  wait_stream();
   if (hybrid_) {
     hybrid_apply_gather(gather_tracks);
     hb->used = 0;
@@ -1811,14 +1870,13 @@ int Batch::process_ptrs(const double* t_img, const OrcvioFeature* const* featp, 
   }
   if (hybrid_) hybrid_queue_gather(gather_tracks);
   download_mirrors();
-  CK(cudaStreamSynchronize(stream_));
+  wait_stream();
   if (hybrid_) {
     hybrid_apply_gather(gather_tracks);
     if (!hyb_ok) { ok_ = false; err_ = "hybrid upload arena exhausted"; }
   }
   account(wB.any_active);
-  int herr = 0;
-  CK(cudaMemcpy(&herr, dErr_, sizeof(int), cudaMemcpyDeviceToHost));
+  const int herr = *hErrPin_;          // came down with the mirrors (download_mirrors)
   if (herr) {
     // the frame's update is incomplete on the device while the host bookkeeping has moved on: later calls fail loudly
     std::fprintf(stderr, "[orcvio_b200] QR front overflow\n");

@@ -230,7 +230,7 @@ class Batch {
   int flags_ = 0;
   std::vector<FilterHost> f_;
   cudaStream_t stream_ = nullptr, stream2_ = nullptr;
-  cudaEvent_t ev_fork_ = nullptr, ev_join_ = nullptr, ev_ls_ = nullptr;
+  cudaEvent_t ev_fork_ = nullptr, ev_join_ = nullptr, ev_ls_ = nullptr, ev_block_ = nullptr;
   bool compress_qr_ = false;          // true: QR tiles + chain (qr_kernel.cu); false: whitened form (info_kernel.cu)
   double *dAmat_ = nullptr, *dPart_ = nullptr;
   size_t amat_cap_ = 0, part_cap_ = 0;
@@ -249,6 +249,7 @@ class Batch {
   double* dFront_ = nullptr;
   size_t front_stride_ = 0;
   int* dErr_ = nullptr;
+  int* hErrPin_ = nullptr;             // pinned twin of dErr_
   // growable device scratch
   double *dHblk_ = nullptr, *dRblk_ = nullptr, *dTileOut_ = nullptr;
   size_t hblk_cap_ = 0, rblk_cap_ = 0, tileout_cap_ = 0;
@@ -288,6 +289,8 @@ class Batch {
   int* dZuptDec_ = nullptr; double* dZuptInfo_ = nullptr;
   int* hZuptDec_ = nullptr; double* hZuptInfo_ = nullptr;
 
+  void prereserve();
+  void wait_stream();
   void upload_blob();
   void ensure_scratch(size_t n_cand, size_t hblk, size_t rblk, size_t tileout);
   void run_phase(PhaseWork& w, int phase);
