@@ -141,6 +141,7 @@ Batch::Batch(const Params& p, int n) : p_(p), B_(n) {
     ok_ = false;
     return;
   }
+  cudaGetDevice(&dev_);               // the device of the creating thread; worker threads re-select it on entry
   Ncap_ = p_.sw_size + 1;
   if (Ncap_ > ORCVIO_MAX_OBS) {
     err_ = "sw_size too large (max 31)";
@@ -275,7 +276,7 @@ Batch::Batch(const Params& p, int n) : p_(p), B_(n) {
   CK(cudaMallocHost(&hClones_, nB * Ncap_ * CL_STRIDE * sizeof(double)));
   CK(cudaMallocHost(&hDx_, nB * ldp_ * sizeof(double)));
   std::memset(hImu_, 0, nB * IM_STRIDE * sizeof(double));
-  if (B_ > 1) prereserve();
+  if (B_ > 1 || env_int("ORCVIO_PRERESERVE", 0)) prereserve();
 }
 
 // Multi-trajectory batches: size the growable buffers for a typical frame up front.  Growing them later works (x 2
@@ -964,6 +965,7 @@ int Batch::replay(int n_frames, const double* t_img, const OrcvioFeature* const*
 int Batch::process_ptrs(const double* t_img, const OrcvioFeature* const* featp, const int* nfeat,
                         const OrcvioImu* const* imup, const int* nimu_v, int* imu_used, int* published) {
   if (!ok_) return ORCVIO_ERR_CUDA;
+  cudaSetDevice(dev_);                // the current device is per host thread (replays run on worker threads)
   const int L = ORCVIO_LEG;
   // Capacity is checked before anything is touched: a frame either runs on every filter or leaves all of them as
   // they were (a failure in the middle of the per-filter loop would leave host bookkeeping and device state apart).

@@ -220,7 +220,7 @@ class Batch {
   bool ok_ = false;
   std::string err_;
   Params p_;
-  int B_ = 0, Ncap_ = 0, ldp_ = 0, Fcap_ = 0, ldr_ = 0, ldt_ = 0;
+  int B_ = 0, Ncap_ = 0, ldp_ = 0, Fcap_ = 0, ldr_ = 0, ldt_ = 0, dev_ = 0;
   int Emax_ = 0, nmax_ = 0;            // EKF-SLAM feature states (hybrid mode); window columns 6 Ncap + Emax
   bool hybrid_ = false;
   double* dFidp_ = nullptr;            // inverse-depth records by feature slot

@@ -518,17 +518,27 @@ __global__ void __launch_bounds__(SY_THREADS) k_syrk(UpdArgs a, const double* __
     sy_stamp(unit, 3);
     const int per = (SY_T * SY_T + nchunks - 1) / nchunks;
     const int e0 = chunk * per, e1 = min(SY_T * SY_T, e0 + per);
+    // same association as the two-level path below (chunks in order inside a group of gsz, then the group sums in
+    // order), so a filter gives the same bits whichever of the two reductions its batch ends up with
+    int gsz = max(group, 1);
+    if ((nchunks + gsz - 1) / gsz > SY_MAXG) gsz = (nchunks + SY_MAXG - 1) / SY_MAXG;
+    const int ngroups = (nchunks + gsz - 1) / gsz;
     for (int e = e0 + tid; e < e1; e += 256) {
       const double* p0 = base + e;
-      double sacc = 0.0;
-      int c = 0;
-      for (; c + 3 < nchunks; c += 4) {
-        const double x0 = __ldcg(p0 + (size_t)c * cstride), x1 = __ldcg(p0 + (size_t)(c + 1) * cstride);
-        const double x2 = __ldcg(p0 + (size_t)(c + 2) * cstride), x3 = __ldcg(p0 + (size_t)(c + 3) * cstride);
-        sacc = (((sacc + x0) + x1) + x2) + x3;
+      double total = 0.0;
+      for (int g0 = 0; g0 < nchunks; g0 += gsz) {
+        const int g1 = min(nchunks, g0 + gsz);
+        double gs = 0.0;
+        int c = g0;
+        for (; c + 3 < g1; c += 4) {
+          const double x0 = __ldcg(p0 + (size_t)c * cstride), x1 = __ldcg(p0 + (size_t)(c + 1) * cstride);
+          const double x2 = __ldcg(p0 + (size_t)(c + 2) * cstride), x3 = __ldcg(p0 + (size_t)(c + 3) * cstride);
+          gs = (((gs + x0) + x1) + x2) + x3;
+        }
+        for (; c < g1; ++c) gs += __ldcg(p0 + (size_t)c * cstride);
+        total = (ngroups > 1) ? total + gs : gs;
       }
-      for (; c < nchunks; ++c) sacc += __ldcg(p0 + (size_t)c * cstride);
-      emit(e >> 6, e & 63, sacc);
+      emit(e >> 6, e & 63, total);
     }
     sy_stamp(unit, 4);
     __syncthreads();
@@ -718,14 +728,14 @@ __global__ void __launch_bounds__(PI_THREADS) k_pinfo(UpdArgs a, const double* L
       const int k = e / (PT / 2), c = 2 * (e - k * (PT / 2));
       double* di_ = Ys_i + (size_t)k * PI_LD + c;
       double* dj_ = Ys_j + (size_t)k * PI_LD + c;
-      if (k < n && i0 + c < ldt) {
+      if (k < n && i0 + c < D) {                         // (columns past D of Y are never written)
         const unsigned int d = (unsigned int)__cvta_generic_to_shared(di_);
         asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(Y + (size_t)k * ldt + i0 + c) : "memory");
       } else {
         *reinterpret_cast<double2*>(di_) = make_double2(0.0, 0.0);
       }
       if (same) continue;
-      if (k < n && j0 + c < ldt) {
+      if (k < n && j0 + c < D) {
         const unsigned int d = (unsigned int)__cvta_generic_to_shared(dj_);
         asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(Y + (size_t)k * ldt + j0 + c) : "memory");
       } else {
@@ -920,10 +930,12 @@ void launch_info_update(const QrArgs& q, const UpdArgs& u, const InfoBufs& ib, i
   if (mid_syrk) cudaEventRecord(mid_syrk, s);
   const size_t sm_w = chol_smem_doubles(nmax, CS + 1) * sizeof(double);
   dim3 gw((Dmax + CS - 1) / CS, B);
+  // k_chol_w_solve overwrites F_1 (u.T) with Y in place, and k_imu_factor on the side stream still reads the IMU
+  // columns of F_1: it must be done first (it is, by tens of microseconds, unless other work delays the side stream)
+  if (ib.ls_done) cudaStreamWaitEvent(s, ib.ls_done, 0);
   launch_pdl(k_chol_w_solve, gw, dim3(CHOL_THREADS), sm_w, s, u);
   check_launch("k_chol_w_solve");
   if (mid2) cudaEventRecord(mid2, s);
-  if (ib.ls_done) cudaStreamWaitEvent(s, ib.ls_done, 0);
   launch_pinfo(u, ib, nmax, B, s);
   if (launches) *launches += 3 + (prior_in_flight ? 0 : 2) + (n_tiles > 0 ? 1 : 0);
 }
