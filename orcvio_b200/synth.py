@@ -135,6 +135,7 @@ class SynthSpec:
     acc_bias: tuple = (0.02, 0.01, -0.015)
     overrides: dict = field(default_factory=dict)
     stops: tuple = ()                # stand-still intervals (ZUPT test sequences)
+    feat_noise_scale: float = 1.0    # true pixel noise = scale x the noise the filter assumes (0: noise-free tracks)
 
 
 def _extrinsics(cfg):
@@ -163,6 +164,7 @@ def make_sequence(spec: SynthSpec):
     sig_f = float(base["noise_feature"])
     if spec.config == "kitti_odom":
         sig_f = 0.002                      # pixel-level noise; the filter still assumes sigma = 1
+    sig_f *= spec.feat_noise_scale
     bg = np.array(spec.gyro_bias)
     ba = np.array(spec.acc_bias)
 

@@ -237,3 +237,52 @@ def test_oracle_filter_tracks_truth_and_is_chaotic():
     assert d[0] < 1e-11
     assert len(a.clones) <= 20 and any(l["kind"] == "prune" for l in a.log)
     print("self-sensitivity: first %.1e last %.1e max %.1e" % (d[0], d[-1], d.max()))
+
+
+def test_msckf_jacobians_match_central_differences_of_the_measurement_model():
+    """measurementJacobian_msckf (src/orcvio.cpp:1071-1168) against central differences of r = z - pi(p_c) under the
+    filter's own retraction (incrementState_IMUCam :4468-4567: R <- exp(dtheta) R for LARVIO / left perturbation,
+    R <- R exp(dtheta) for right perturbation, p <- p + dp), all three perturbation modes, plus H_f against the
+    feature position.  A pin that does not depend on how the formulas were transcribed (parity #1)."""
+    import helpers as H
+    from orcvio_b200 import synth
+    from oracle import mathutils as mu
+    snap = synth.stress_snapshot(8, 10, 6, seed=2)
+    tri = dict(translation_threshold=-1.0, cost_threshold=1e-3, init_final_dist_threshold=100.0)
+    eps = 1e-6
+    for flags in (H.FL_LARVIO, H.FL_LEFT, 0):
+        vio = H.oracle_from_snapshot(snap, flags, 1e-4, tri=tri)
+        left = bool(flags & (H.FL_LARVIO | H.FL_LEFT))
+        checked = 0
+        for fid, ft in list(vio.map_server.items())[:6]:
+            assert vio._initialize(ft, None)
+            for sid in ft.obs_ids()[:3]:
+                Hx, He, Hf, r0 = vio.measurementJacobian_msckf(sid, ft)
+                c = vio.clones[sid]
+                R0, p0 = c.orientation.copy(), c.position.copy()
+                J = np.zeros((2, 6))
+                for k in range(6):
+                    rs = []
+                    for sgn in (+1, -1):
+                        d = np.zeros(6)
+                        d[k] = sgn * eps
+                        Rt = mu.so3_exp(d[:3])
+                        c.orientation = Rt @ R0 if left else R0 @ Rt
+                        c.position = p0 + d[3:]
+                        rs.append(vio.measurementJacobian_msckf(sid, ft)[3])
+                    J[:, k] = -(rs[0] - rs[1]) / (2 * eps)          # r(x + d) = r(x) - H d
+                c.orientation, c.position = R0, p0
+                pw = ft.position.copy()
+                Jf = np.zeros((2, 3))
+                for k in range(3):
+                    rs = []
+                    for sgn in (+1, -1):
+                        ft.position = pw.copy()
+                        ft.position[k] += sgn * eps
+                        rs.append(vio.measurementJacobian_msckf(sid, ft)[3])
+                    Jf[:, k] = -(rs[0] - rs[1]) / (2 * eps)
+                ft.position = pw
+                assert np.abs(J - Hx).max() <= 2e-6 * np.abs(Hx).max(), (flags, fid, sid)
+                assert np.abs(Jf - Hf).max() <= 2e-6 * np.abs(Hf).max(), (flags, fid, sid)
+                checked += 1
+        assert checked >= 12
