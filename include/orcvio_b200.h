@@ -363,6 +363,31 @@ double orcvio_chi2_quantile(double p, int dof);
 int orcvio_batch_set_profiling(orcvio_batch* b, int on);
 int orcvio_batch_get_phase_times(orcvio_batch* b, double* ms6, long long* n6);
 
+/* ---- on-disk and wire formats either side of the path (host code, no device needed) ------------------------------
+ * EuRoC / ASL csv files as the reference's app reads them (include/utils/DataReader.hpp:30-140): header line skipped,
+ * time stamps in ns -> s, IMU rows "t, wx, wy, wz, ax, ay, az".  Return the number of rows in the file (rows beyond
+ * `cap` are counted, not stored), or a negative error code. */
+int orcvio_read_imu_csv(const char* path, OrcvioImu* out, int cap);
+int orcvio_read_image_list_csv(const char* path, double* t_out, char* names, int name_stride, int cap);
+/* Ground-truth csv (DatasetReader::load_gt_file, include/orcvio/dataset_reader.h:64-101): rows of 17 doubles
+ * [t (s), q (4), p (3), v (3), b_gyro (3), b_accel (3)]; orcvio_gt_lookup is get_gt_state (:111-140): the state whose
+ * stamp is closest to t when that is within 5 ms, else only an exact match; returns 1 when found. */
+int orcvio_read_gt_csv(const char* path, double* out17, int cap);
+int orcvio_gt_lookup(const double* gt17, int n, double t, double out17[17]);
+/* The pose log of processFeatures (src/orcvio.cpp:640-645; written by orcvio_set_pose_log): rows of 8 doubles. */
+int orcvio_read_pose_log(const char* path, double* out8, int cap);
+/* orcvio_ros_msgs/ObjectLM (ros_wrapper/src/orcvio_ros_msgs/msg/ObjectLM.msg) in ROS 1 wire serialisation, matrices
+ * as tf::matrixEigenToMsg lays them out (two dimensions, row-major): residual (rows x 1), jacobian_wrt_object_state
+ * (rows x odim), jacobian_wrt_sensor_state (rows x 6), valid_camera_pose_mat (6 x n_poses), timestamps, zs_num --
+ * exactly the arguments of constructObjectResidualJacobians.  pack returns the message length (buf may be NULL to
+ * size it); unpack checks the layout and returns ORCVIO_OK. */
+int orcvio_objectlm_pack(long long object_id, const double* residual, int rows, const double* jac_object, int odim,
+                         const double* jac_sensor, const double* cam_pose_se3, int n_poses, const double* timestamps,
+                         int n_ts, const int* zs_num, int n_zs, unsigned char* buf, int cap);
+int orcvio_objectlm_unpack(const unsigned char* buf, int len, long long* object_id, double* residual, int* rows,
+                           double* jac_object, int* odim, double* jac_sensor, double* cam_pose_se3, int* n_poses,
+                           double* timestamps, int* n_ts, int* zs_num, int* n_zs, int cap_rows, int cap_odim, int cap_n);
+
 #ifdef __cplusplus
 }
 #endif

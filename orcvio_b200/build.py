@@ -36,6 +36,7 @@ SOURCES = {
     "objects.cu": [],
     "capi.cu": [],
     "config.cpp": [],
+    "formats.cpp": [],
 }
 
 
