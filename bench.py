@@ -42,10 +42,37 @@ N_CLONES, N_FEATURES, MAX_TRACK = 30, 4096, 6
 TARGET_FEATURES = 2000      # BASELINE.json north_star: "30-clone, 2000-feature frame runs under 200 us"
 NOISE_VAR = 1.6e-5          # (2 x 0.002)^2: synthetic pixel noise of the KITTI-shaped generator
 TRI = dict(cost_threshold=1e-3, init_final_dist_threshold=100.0)
-# dram__bytes_read.sum + dram__bytes_write.sum of one k_syrk launch from the committed `ncu --set full`
-# capture (profiles/); None until a capture of the current kernel exists
-SYRK_NCU_TRAFFIC = 28_166_400          # 28.130 MB read + 36 KB written (profiles/r1_ncu_full_summary.csv): less than the
-                                       # dense 8 M (n+1) B because the zero part of A's staircase is never read
+
+
+def ncu_capture(kernel="k_syrk"):
+    """dram__bytes_read.sum + dram__bytes_write.sum (bytes per launch) and the measured DMMA-pipe activity of one launch
+    of `kernel`, read from the newest committed `ncu --set full` summary under profiles/ (scripts/ncu_summary.py)."""
+    import csv
+    import glob
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_ncu_full_summary.csv")))
+    if not files:
+        return None
+    rows = list(csv.reader(open(files[-1])))
+    hdr, units = rows[0], rows[1]
+    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    for r in rows[2:]:
+        if kernel in r[0]:
+            def col(name):
+                if name not in hdr:
+                    return None, None
+                i = hdr.index(name)
+                return float(r[i]), units[i]
+            rd, ru = col("dram__bytes_read.sum")
+            wr, wu = col("dram__bytes_write.sum")
+            pipe, _ = col("smsp__pipe_tensor_subpipe_dmma_cycles_active.avg.pct_of_peak_sustained_active")
+            inst, _ = col("sm__inst_executed_pipe_tensor_subpipe_dmma.sum")
+            us, _ = col("gpu__time_duration.sum")
+            return dict(traffic=int(rd * scale.get(ru, 1.0) + wr * scale.get(wu, 1.0)) if rd is not None else None,
+                        dmma_pipe_active_pct=pipe, dmma_instructions=inst, capture_us=us,
+                        source=os.path.relpath(files[-1], ROOT))
+    return None
+
+
 WORKLOAD = f"stress frame: {N_CLONES}-clone window, {N_FEATURES} features, max_track_len {MAX_TRACK} (SURVEY 8d C4a)"
 
 
@@ -475,6 +502,15 @@ def main():
     torch.cuda.synchronize()
     t_e2e = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
     barrier()
+    # the same call when the covariance stays on the device (pose / velocity covariance block back instead of all of P)
+    for _ in range(args.warmup):
+        fr.update(inp, out, full_P=False)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        fr.update(inp, out, full_P=False)
+    torch.cuda.synchronize()
+    t_e2e_lite = time.perf_counter() - t0
+    barrier()
     clocks = sampler.stop() if rank == 0 else None
 
     # ---- the north star's target frame (30 clones, 2000 features, target < 200 us), rank 0 only: same chain, same
@@ -539,6 +575,7 @@ def main():
         # roofline kernel: k_syrk, the one kernel of the chain with GEMM-sized work (the FP64 tensor-core
         # compression GEMM of the north star); the other kernels are latency chains
         dfma_peak, dmma_peak = api.fp64_peak()
+        cap = ncu_capture("k_syrk")
         flops, M_rows = syrk_flops(snap, out["status"])
         achieved = flops / (kt["syrk"] * 1e-6) / 1e12
         jac_bytes = algorithmic_bytes(snap, out["status"], "jac_gate")
@@ -555,11 +592,19 @@ def main():
                         timing="CUDA events on the launching stream per iteration, max over ranks"),
             us_per_frame=1e6 * secs / args.steps,
             stage_us={k: round(v, 2) for k, v in stage_named.items()},
+            stage_us_note="stage times come from a separate run with event records between the kernels (launched one by "
+                          "one); the timed steps replay one CUDA graph of the whole chain, so their sum exceeds us_per_frame",
             e2e=dict(value=total_pass * args.steps / secs_e2e, unit=UNIT, h2d_bytes_per_step=int(h2d),
-                     d2h_bytes_per_step=int(d2h), us_per_frame=1e6 * secs_e2e / args.steps),
+                     d2h_bytes_per_step=int(d2h), us_per_frame=1e6 * secs_e2e / args.steps,
+                     pose_cov_only=dict(us_per_frame=1e6 * t_e2e_lite / args.steps,
+                                        d2h_bytes_per_step=int(d2h - out["P"].nbytes + 81 * 8),
+                                        note="orcvio_frame_update_pose_cov: the leading 9 x 9 block of P comes back "
+                                             "instead of all of it (rank 0)")),
             gpu_launches=int(launches),
-            roofline=dict(bound="tensor", kernel="k_syrk (W = s^2 I + A^T A, staircase-sparse split-K, mma.sync m8n8k4 f64)", achieved=achieved,
-                          peak=dmma_peak, unit="TFLOP/s", frac=achieved / dmma_peak, traffic=SYRK_NCU_TRAFFIC,
+            roofline=dict(bound="tensor", kernel="k_syrk (W = s^2 I + A^T A: staircase-sparse split-K, cp.async operand pipeline, "
+                                                 "mma.sync m8n8k4 f64, parallel slice reduction)", achieved=achieved,
+                          peak=dmma_peak, unit="TFLOP/s", frac=achieved / dmma_peak, traffic=(cap or {}).get("traffic"),
+                          ncu=cap,
                           algorithmic_flops=flops, gated_rows=M_rows, kernel_us=kt["syrk"],
                           peak_source="FP64 DMMA peak measured live on this GPU (orcvio_fp64_peak: mma.sync m8n8k4 "
                                       "micro-kernel; MEASURED_PEAKS.json carries only bf16 / HBM)",

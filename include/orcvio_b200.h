@@ -231,6 +231,13 @@ int orcvio_frame_update(orcvio_frame* f, const double* clone_R, const double* cl
                         const double* R_b2c, const double* t_c_b, const double* P_in, const int* feat_off,
                         const int* obs_clone, const double* obs_z, int n_feat, double* P_out,
                         double* delta_x, int* status, double* gamma, double* clone_out);
+/* Same call when the caller keeps the covariance on the device between frames: instead of the whole posterior
+ * (D x D: 326 KB at 30 clones) only its leading 9 x 9 block comes back -- what getPpose / getPvel
+ * (src/orcvio.cpp:3000-3027) are computed from -- row-major into P_lead9 (81 doubles). */
+int orcvio_frame_update_pose_cov(orcvio_frame* f, const double* clone_R, const double* clone_p, int n_clones,
+                                 const double* R_b2c, const double* t_c_b, const double* P_in, const int* feat_off,
+                                 const int* obs_clone, const double* obs_z, int n_feat, double* P_lead9,
+                                 double* delta_x, int* status, double* gamma, double* clone_out);
 int orcvio_frame_load(orcvio_frame* f, const double* clone_R, const double* clone_p, int n_clones,
                       const double* R_b2c, const double* t_c_b, const double* P_in, const int* feat_off,
                       const int* obs_clone, const double* obs_z, int n_feat);

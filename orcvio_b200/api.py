@@ -122,6 +122,7 @@ def lib():
     L.orcvio_frame_create.argtypes = [C.c_int, C.c_int] + [C.c_double] * 5
     L.orcvio_frame_destroy.argtypes = [vp]
     L.orcvio_frame_update.argtypes = [vp, dp, dp, C.c_int, dp, dp, dp, ip, ip, dp, C.c_int, dp, dp, ip, dp, dp]
+    L.orcvio_frame_update_pose_cov.argtypes = [vp, dp, dp, C.c_int, dp, dp, dp, ip, ip, dp, C.c_int, dp, dp, ip, dp, dp]
     L.orcvio_frame_load.argtypes = [vp, dp, dp, C.c_int, dp, dp, dp, ip, ip, dp, C.c_int]
     L.orcvio_frame_run.argtypes = [vp, C.c_int, fpt, fpt]
     L.orcvio_frame_fetch.argtypes = [vp, dp, dp, ip, dp, dp]
@@ -485,13 +486,29 @@ class Frame:
     def prepare_inputs(self, snap):
         return self._inputs(snap)
 
-    def update(self, inp, out=None):
-        """Host buffers in -> host buffers out (the per-frame call of a host integration)."""
+    def update(self, inp, out=None, full_P=True):
+        """Host buffers in -> host buffers out (the per-frame call of a host integration).  full_P=False: only the
+        leading 9 x 9 block of the posterior comes back (out["P_lead9"]), orcvio_frame_update_pose_cov."""
         if not isinstance(inp, dict) or "Rbc" not in inp:
             inp = self._inputs(inp)
         nf = len(inp["feat_off"]) - 1
         if out is None:
             out = self._outputs(inp["N"], nf)
+        if not full_P:
+            if "P_lead9" not in out:
+                out["P_lead9"] = np.zeros((9, 9))
+            pi = inp.get("_ptrs")
+            if pi is None:
+                pi = inp["_ptrs"] = (_dp(inp["clone_R"]), _dp(inp["clone_p"]), inp["N"], _dp(inp["Rbc"]), _dp(inp["tcb"]),
+                                     _dp(inp["P"]), _ip(inp["feat_off"]), _ip(inp["obs_clone"]), _dp(inp["obs_z"]), nf)
+            pl = out.get("_ptrs_lite")
+            if pl is None:
+                pl = out["_ptrs_lite"] = (_dp(out["P_lead9"]), _dp(out["delta_x"]), _ip(out["status"]), _dp(out["gamma"]),
+                                          _dp(out["clones"]))
+            rc = self._L.orcvio_frame_update_pose_cov(self._h, *pi, *pl)
+            if rc != 0:
+                raise RuntimeError(f"orcvio_frame_update_pose_cov failed: {rc}")
+            return out
         # the ctypes pointer objects are cached on the buffers' dicts: building 14 of them costs more than the
         # GPU spends on a stage of the frame
         pi = inp.get("_ptrs")

@@ -2594,6 +2594,7 @@ int Batch::snapshot_fetch(const SnapshotIO& io) {
   double* hCl = hDx + ldp_;
   double* hR = hCl + (size_t)Ncap_ * CL_STRIDE;
   if (io.P_out) CK(cudaMemcpyAsync(hP, dP_, (size_t)D * ldp_ * sizeof(double), cudaMemcpyDeviceToHost, stream_));
+  else if (io.P_lead9) CK(cudaMemcpyAsync(hP, dP_, (size_t)9 * ldp_ * sizeof(double), cudaMemcpyDeviceToHost, stream_));
   if (io.delta_x) CK(cudaMemcpyAsync(hDx, dDx_, ldp_ * sizeof(double), cudaMemcpyDeviceToHost, stream_));
   if (io.clone_out) CK(cudaMemcpyAsync(hCl, dClones_, (size_t)N * CL_STRIDE * sizeof(double), cudaMemcpyDeviceToHost, stream_));
   if (io.R_thin) CK(cudaMemcpyAsync(hR, dR_, (size_t)n * ldr_ * sizeof(double), cudaMemcpyDeviceToHost, stream_));
@@ -2630,6 +2631,8 @@ int Batch::snapshot_fetch(const SnapshotIO& io) {
     if (io.raw_Hf) CK(cudaMemcpy(io.raw_Hf, dRawHf_, no * 6 * sizeof(double), cudaMemcpyDeviceToHost));
     if (io.raw_r) CK(cudaMemcpy(io.raw_r, dRawR_, no * 2 * sizeof(double), cudaMemcpyDeviceToHost));
   }
+  if (io.P_lead9)
+    for (int i = 0; i < 9; ++i) std::memcpy(io.P_lead9 + 9 * i, hP + (size_t)i * ldp_, 9 * sizeof(double));
   if (io.P_out)   // the posterior is exactly symmetric: row-major with ld == column-major D x D
     for (int i = 0; i < D; ++i) std::memcpy(io.P_out + (size_t)i * D, hP + (size_t)i * ldp_, D * sizeof(double));
   if (io.delta_x) std::memcpy(io.delta_x, hDx, D * sizeof(double));

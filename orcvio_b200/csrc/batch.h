@@ -171,6 +171,7 @@ class Batch {
     int stages = 0;                         // bit0 tri, bit1 jac+gate, bit2 qr+update
     bool early_prior = false;               // start k_chol_prior as soon as P is uploaded (end-to-end call)
     int repeat = 1;
+    double* P_lead9 = nullptr;               // leading 9 x 9 block of the posterior (what getPpose / getPvel read)
     double* P_out = nullptr; double* delta_x = nullptr; int* status = nullptr; double* gamma = nullptr;
     double* positions = nullptr; double* R_thin = nullptr; double* r_thin = nullptr;
     double* clone_out = nullptr; float* timings_us = nullptr; int* iters = nullptr; double* cost = nullptr;

@@ -507,6 +507,22 @@ int orcvio_frame_update(orcvio_frame* f, const double* clone_R, const double* cl
   return rc;
 }
 
+int orcvio_frame_update_pose_cov(orcvio_frame* f, const double* clone_R, const double* clone_p, int n_clones,
+                                 const double* R_b2c, const double* t_c_b, const double* P_in, const int* feat_off,
+                                 const int* obs_clone, const double* obs_z, int n_feat, double* P_lead9,
+                                 double* delta_x, int* status, double* gamma, double* clone_out) {
+  if (!f || !feat_off || !obs_clone || !obs_z || !clone_R || !clone_p) return ORCVIO_ERR_ARG;
+  Batch::SnapshotIO io = frame_io(clone_R, clone_p, n_clones, R_b2c, t_c_b, P_in, feat_off, obs_clone, obs_z, n_feat);
+  io.P_lead9 = P_lead9; io.delta_x = delta_x; io.status = status; io.gamma = gamma; io.clone_out = clone_out;
+  io.early_prior = true;
+  int rc = f->b->snapshot_prepare(io);
+  if (rc != ORCVIO_OK) return rc;
+  f->loaded = true;
+  rc = f->b->snapshot_execute(true);
+  if (rc != ORCVIO_OK) return rc;
+  return f->b->snapshot_fetch(io);
+}
+
 int orcvio_frame_host_times(orcvio_frame* f, float* us4) {
   if (!f || !us4) return ORCVIO_ERR_ARG;
   for (int k = 0; k < 4; ++k) us4[k] = f->host_us[k];

@@ -10,7 +10,9 @@ import sys
 COLS = ["gpu__time_duration.sum", "launch__grid_size", "launch__block_size", "launch__registers_per_thread",
         "sm__warps_active.avg.pct_of_peak_sustained_active", "smsp__issue_active.avg.pct_of_peak_sustained_active",
         "sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active",
-        "sm__inst_executed_pipe_tensor_op_dmma.sum" , "sm__throughput.avg.pct_of_peak_sustained_elapsed",
+        "smsp__pipe_tensor_subpipe_dmma_cycles_active.avg.pct_of_peak_sustained_active",
+        "smsp__pipe_tensor_subpipe_dmma_cycles_active.sum", "sm__inst_executed_pipe_tensor_subpipe_dmma.sum",
+        "sm__throughput.avg.pct_of_peak_sustained_elapsed",
         "dram__bytes_read.sum", "dram__bytes_write.sum", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
         "lts__t_bytes.sum", "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "smsp__inst_executed.sum",
         "launch__waves_per_multiprocessor"]

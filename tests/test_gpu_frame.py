@@ -52,3 +52,13 @@ def test_frame_handle_equals_snapshot_entry(n_clones, n_feat, max_len, full):
                                 init_final_dist_threshold=TRI["init_final_dist_threshold"])
     _same(fr.update(other), ref_o)           # a different frame through the same handle
     _same(fr.update(inp), ref)
+
+
+def test_pose_cov_only_variant_matches_the_full_call():
+    snap = synth.stress_snapshot(20, 300, 6, seed=31)
+    fr = api.Frame(20, 0, 1.6e-5, 0.95, -1.0, 1e-3, 100.0)
+    full = {k: (v.copy() if hasattr(v, "copy") else v) for k, v in fr.update(snap).items()}
+    lite = fr.update(snap, full_P=False)
+    np.testing.assert_array_equal(lite["P_lead9"], full["P"][:9, :9])
+    for key in ("delta_x", "status", "gamma", "clones"):
+        np.testing.assert_array_equal(lite[key], full[key])
