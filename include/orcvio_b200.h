@@ -170,6 +170,14 @@ int orcvio_batch_process(orcvio_batch* b, const double* t_img, const OrcvioFeatu
 int orcvio_batch_replay(orcvio_batch* b, int n_frames, const double* t_img, const OrcvioFeature* const* feats,
                         const int* feat_off, const OrcvioImu* const* imu, const int* n_imu, double imu_window,
                         double* poses_out, int* ok_out);
+/* Object pose initialisation, first step (ObjectFeatureInitializer::single_object_initialization without RANSAC,
+ * src/obj/ObjectFeatureInitializer.cpp:99-111): findTransform (:265-341) -- similarity fit of the mean-shape keypoints
+ * onto the triangulated ones, scale from the polyline lengths, rotation by Kabsch -- and, with se2_flag,
+ * poseSE32SE2 (include/orcvio/utils/se3_ops.hpp:272-300) for a batch of objects on the device.  Points: 3 doubles
+ * each, object o owns [off[o], off[o+1]); wTq16_out: row-major 4 x 4 per object; ok_out[o] = 0 for a degenerate
+ * object (fewer than two points, zero-length polyline).  Host pointers. */
+int orcvio_object_kabsch_init(const double* mean_pts, const double* world_pts, const int* off, int n_obj, int se2_flag,
+                              double* wTq16_out, int* ok_out);
 /* The reference's trajectory logger (System::publishGroundtruth, ros_wrapper/src/orcvio/src/System.cpp:885-943) for a
  * batch of trajectories, on the device: first-pose SE(3) alignment, then per trajectory the mean orientation error
  * (deg), mean position error (m), position RMSE (m) and final position error (m) -> out4 (n_traj x 4).  Poses are

@@ -248,3 +248,49 @@ def object_lm_rows(frames_wTc, wTo, shape, kps, zs_all, zb_all, left, new_residu
     fjac = np.vstack([np.vstack(J_kp) * residual_weights[0],
                       np.vstack(J_bb) * residual_weights[1]])
     return fvec, fjac
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Object pose initialisation (first step): ObjectFeatureInitializer::single_object_initialization
+# without RANSAC (use_kabsch_with_ransac_flag = false, src/obj/ObjectFeatureInitializer.cpp:25-31, 99-111).
+# Pinned by the reference's own known-answer tests src/tests/test_kabsch.cpp:10-87 (tests/test_oracle_cpu.py).
+def find_transform(pts_in, pts_out):
+    """findTransform, src/obj/ObjectFeatureInitializer.cpp:265-341: similarity transform (scale * R, t) that maps the
+    3 x n points `pts_in` onto `pts_out` -- scale from the ratio of the polyline lengths, rotation by Kabsch (SVD of
+    in * out^T with the reflection fix on the last singular direction).  Returns the 4 x 4 matrix."""
+    a = np.array(pts_in, dtype=float)
+    b = np.array(pts_out, dtype=float)
+    assert a.shape == b.shape and a.shape[0] == 3
+    n = a.shape[1]
+    dist_in = sum(np.linalg.norm(a[:, c + 1] - a[:, c]) for c in range(n - 1))
+    dist_out = sum(np.linalg.norm(b[:, c + 1] - b[:, c]) for c in range(n - 1))
+    scale = dist_out / dist_in
+    b = b / scale
+    in_ctr = a.sum(axis=1) / n
+    out_ctr = b.sum(axis=1) / n
+    a = a - in_ctr[:, None]
+    b = b - out_ctr[:, None]
+    U, _, Vt = np.linalg.svd(a @ b.T)
+    V = Vt.T
+    d = 1.0 if np.linalg.det(V @ U.T) > 0 else -1.0
+    R = V @ np.diag([1.0, 1.0, d]) @ U.T
+    T = np.eye(4)
+    T[:3, :3] = scale * R
+    T[:3, 3] = scale * (out_ctr - R @ in_ctr)
+    return T
+
+
+def pose_se3_to_se2(T):
+    """poseSE32SE2, include/orcvio/utils/se3_ops.hpp:272-300, literally: yaw = pi / atan2(r21, r11) (sic), z = 0."""
+    out = np.eye(4)
+    den = math.atan2(T[1, 0], T[0, 0])
+    yaw = math.pi / den if den != 0.0 else float("inf")
+    if not math.isfinite(yaw):
+        yaw = 0.0
+    out[0, 0] = math.cos(yaw)
+    out[0, 1] = -math.sin(yaw)
+    out[0, 3] = T[0, 3]
+    out[1, 0] = math.sin(yaw)
+    out[1, 1] = math.cos(yaw)
+    out[1, 3] = T[1, 3]
+    return out

@@ -571,6 +571,24 @@ class Frame:
 
 
 # ---------------------------------------------------------------- stage-level calls
+def object_kabsch_init(mean_pts, world_pts, se2=False):
+    """findTransform (+ poseSE32SE2) for a batch of objects: lists of (n_i, 3) arrays -> ((n_obj, 4, 4), ok)."""
+    L = lib()
+    L.orcvio_object_kabsch_init.argtypes = [C.POINTER(C.c_double)] * 2 + [C.POINTER(C.c_int), C.c_int, C.c_int,
+                                                                        C.POINTER(C.c_double), C.POINTER(C.c_int)]
+    off = np.zeros(len(mean_pts) + 1, dtype=np.int32)
+    off[1:] = np.cumsum([len(m) for m in mean_pts])
+    a = np.ascontiguousarray(np.concatenate([np.asarray(m, dtype=np.float64).reshape(-1, 3) for m in mean_pts]))
+    b = np.ascontiguousarray(np.concatenate([np.asarray(w, dtype=np.float64).reshape(-1, 3) for w in world_pts]))
+    assert a.shape == b.shape
+    T = np.zeros((len(mean_pts), 4, 4))
+    ok = np.zeros(len(mean_pts), dtype=np.int32)
+    rc = L.orcvio_object_kabsch_init(_dp(a), _dp(b), _ip(off), len(mean_pts), int(bool(se2)), _dp(T), _ip(ok))
+    if rc != 0:
+        raise RuntimeError(f"orcvio_object_kabsch_init failed: {rc}")
+    return T, ok
+
+
 def trajectory_metrics(est_pose7, gt_pose7):
     """System::publishGroundtruth on the device for a batch of trajectories (orcvio_trajectory_metrics):
     (n, F, 7) poses (p, q xyzw) -> (n, 4): mean orientation error (deg), mean position error, position RMSE, final

@@ -32,6 +32,7 @@ SOURCES = {
     "ekf_kernel.cu": [],
     "hybrid_kernel.cu": [],
     "metrics_kernel.cu": [],
+    "kabsch_kernel.cu": [],
     "batch.cu": [],
     "objects.cu": [],
     "capi.cu": [],

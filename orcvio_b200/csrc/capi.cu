@@ -300,6 +300,11 @@ int orcvio_batch_replay(orcvio_batch* b, int n_frames, const double* t_img, cons
   return b->batch->replay(n_frames, t_img, feats, feat_off, imu, n_imu, imu_window, poses_out, ok_out);
 }
 
+int orcvio_object_kabsch_init(const double* mean_pts, const double* world_pts, const int* off, int n_obj, int se2_flag,
+                              double* wTq16_out, int* ok_out) {
+  return ob::kabsch_init(mean_pts, world_pts, off, n_obj, se2_flag, wTq16_out, ok_out);
+}
+
 int orcvio_trajectory_metrics(const double* est_pose7, const double* gt_pose7, int n_traj, int n_frames, double* out4) {
   if (!est_pose7 || !gt_pose7 || !out4) return ORCVIO_ERR_ARG;
   return ob::trajectory_metrics(est_pose7, gt_pose7, n_traj, n_frames, out4);

@@ -247,3 +247,37 @@ def test_propagate_matches_oracle(config):
     np.testing.assert_allclose(v1, ref.imu_state.velocity, rtol=1e-12, atol=1e-12)
     np.testing.assert_allclose(p1, ref.imu_state.position, rtol=1e-12, atol=1e-12)
     assert np.abs(P1 - ref.state_cov).max() <= 1e-12 * np.abs(ref.state_cov).max()
+
+
+def test_kabsch_init_matches_reference_known_answers_and_oracle():
+    """orcvio_object_kabsch_init: the reference's own known-answer tests (src/tests/test_kabsch.cpp, 1e-13) through the
+    C ABI, a batch of random objects against the oracle, the SE(2) projection, a degenerate object."""
+    from test_oracle_cpu import _kabsch_kat
+    rng = np.random.default_rng(5)
+    means, worlds, want = [], [], []
+    for planar in (False, True):
+        pin, pout, sR, S = _kabsch_kat(planar)
+        means.append(pin.T)
+        worlds.append(pout.T)
+        want.append((sR, S))
+    g = np.load(os.path.join(GOLD, "one_car.npz"))
+    kps = g["mean_shape"][0]
+    for k in range(30):
+        sel = np.sort(rng.choice(12, size=int(rng.integers(4, 13)), replace=False))
+        R = mu.so3_exp(rng.normal(0, 1.0, 3))
+        t = rng.normal(0, 5.0, 3)
+        w = (R @ kps[sel].T).T + t + rng.normal(0, 0.02, (len(sel), 3))
+        means.append(kps[sel])
+        worlds.append(w)
+    T, ok = api.object_kabsch_init(means, worlds)
+    assert np.all(ok == 1)
+    for i, (sR, S) in enumerate(want):
+        assert np.abs(T[i, :3, :3] - sR).max() <= 1e-13 and np.abs(T[i, :3, 3] - S).max() <= 1e-13
+    for i in range(2, len(means)):
+        ref = obj.find_transform(means[i].T, worlds[i].T)
+        np.testing.assert_allclose(T[i], ref, rtol=0, atol=1e-11)
+    T2, ok2 = api.object_kabsch_init(means, worlds, se2=True)
+    for i in range(len(means)):
+        np.testing.assert_allclose(T2[i], obj.pose_se3_to_se2(T[i]), rtol=0, atol=1e-9)
+    T3, ok3 = api.object_kabsch_init([kps[:1], kps[:5]], [kps[:1], np.tile(kps[:1], (5, 1))])
+    assert list(ok3) == [0, 0]

@@ -286,3 +286,29 @@ def test_msckf_jacobians_match_central_differences_of_the_measurement_model():
                 assert np.abs(Jf - Hf).max() <= 2e-6 * np.abs(Hf).max(), (flags, fid, sid)
                 checked += 1
         assert checked >= 12
+
+
+def _kabsch_kat(planar):
+    """The data of src/tests/test_kabsch.cpp:10-87: points with a known scale * R, t."""
+    w, x, y, z = np.array([1.0, 3.0, 5.0, 2.0]) / np.linalg.norm([1.0, 3.0, 5.0, 2.0])      # Eigen::Quaternion(w, x, y, z)
+    R = np.array([[1 - 2 * (y * y + z * z), 2 * (x * y - w * z), 2 * (x * z + w * y)],
+                  [2 * (x * y + w * z), 1 - 2 * (x * x + z * z), 2 * (y * z - w * x)],
+                  [2 * (x * z - w * y), 2 * (y * z + w * x), 1 - 2 * (x * x + y * y)]])
+    if planar:
+        pin = np.array([[-1.25, 0, -1.25], [1.25, 0, -1.25], [1.25, 0, 1.25], [-1.25, 0, 1.25]]).T
+    else:
+        pin = np.array([[np.log(2 * r + 10.0) / np.sqrt(1.0 * c + 4.0) + np.sqrt(c * 1.0) / (r + 1.0) for c in range(100)]
+                        for r in range(3)])
+    S = np.array([-5.0, 6.0, -27.0])
+    return pin, 2.0 * R @ pin + S[:, None], 2.0 * R, S
+
+
+def test_find_transform_reproduces_the_reference_known_answers():
+    """oracle.objects.find_transform against src/tests/test_kabsch.cpp (test_random, test_planar): 1e-13 like the test."""
+    from oracle import objects as obj
+    for planar in (False, True):
+        pin, pout, sR, S = _kabsch_kat(planar)
+        T = obj.find_transform(pin, pout)
+        assert np.abs(T[:3, :3] - sR).max() <= 1e-13 and np.abs(T[:3, 3] - S).max() <= 1e-13
+    T2 = obj.pose_se3_to_se2(T)
+    assert T2[2, 3] == 0 and abs(np.linalg.det(T2[:2, :2]) - 1) < 1e-15 and T2[0, 3] == T[0, 3]
