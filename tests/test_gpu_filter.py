@@ -207,3 +207,26 @@ def test_not_initialised_returns_false():
     assert vio.initialize()
     vio.push_imu(np.array([[0.0, 0, 0, 0, 0, 0, 9.81], [0.005, 0, 0, 0, 0, 0, 9.81]]))
     assert vio.processFeatures(0.004, np.zeros((0, 9))) is False
+
+
+@pytest.mark.parametrize("config,overrides,n_frames,feats,n_landmarks", [
+    ("unity", dict(if_ZUPT_valid=0), 100, 120, 6000),
+    ("euroc", {}, 100, 120, 6000),                       # as shipped: hybrid MSCKF / EKF-SLAM + ZUPT
+    ("kitti_odom", {}, 80, 250, 20000),                  # as shipped
+])
+def test_free_running_ate_within_the_north_star_bound(config, overrides, n_frames, feats, n_landmarks):
+    """BASELINE north_star: "trajectory ATE within 1e-6 m over a full sequence" -- the GPU filter and the oracle, both
+    free-running from the same initial state on the same inputs (measured 1e-9 .. 5e-8 m: profiles/r2_free_running_ate.json)."""
+    seq = synth.make_sequence(synth.SynthSpec(config=config, seed=2, n_frames=n_frames, feats_per_frame=feats,
+                                              overrides=overrides, n_landmarks=n_landmarks))
+    vio = api.OrcVIO(H.write_cfg(seq["cfg"]))
+    assert vio.initialize()
+    it = H.run_oracle_sequence(seq)
+    state = dict(k=0)
+    d = []
+    for fi in range(n_frames):
+        _feed(vio, seq, fi, state)
+        ref = next(it)
+        d.append(np.linalg.norm(np.array(vio.state().p) - ref.imu_state.position))
+    print(f"{config}: free-running ATE gpu-vs-oracle {np.mean(d):.3e} m, max {np.max(d):.3e} m")
+    assert np.mean(d) < 1e-6
