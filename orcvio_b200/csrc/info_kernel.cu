@@ -102,6 +102,7 @@ __global__ void __launch_bounds__(256) k_imu_factor(UpdArgs a, double* Ls_all) {
     const double tol_i = i < L ? 1e-12 * fabs(P[(size_t)i * (a.ldp + 1)]) : 0.0;
     for (int c = 0; c < L; ++c) {
       const double pv = S[c * (L + 1) + c];
+      __syncwarp();                                       // every lane has the pivot before lane c overwrites it
       const double tc = __shfl_sync(0xffffffffu, tol_i, c);
       const bool ok = pv > tc;
       const double d = ok ? sqrt(pv) : 0.0;
