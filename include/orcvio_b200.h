@@ -178,6 +178,40 @@ int orcvio_batch_replay(orcvio_batch* b, int n_frames, const double* t_img, cons
  * object (fewer than two points, zero-length polyline).  Host pointers. */
 int orcvio_object_kabsch_init(const double* mean_pts, const double* world_pts, const int* off, int n_obj, int se2_flag,
                               double* wTq16_out, int* ok_out);
+/* Object state optimiser, the step immediately before stage 3, for a batch of n_obj objects of ONE
+ * class (K <= 12 keypoints).  Object o owns the frames [frame_off[o], frame_off[o+1]): frames_wTc (16 doubles each,
+ * row-major camera-to-world), zs (K x 2 per frame, NaN = keypoint not observed), zb (xmin ymin xmax ymax per frame).
+ * Host pointers.
+ *
+ * orcvio_object_init = ObjectFeatureInitializer::single_object_initialization without RANSAC
+ * (src/obj/ObjectFeatureInitializer.cpp:33-111): every keypoint observed in more than 3 frames is triangulated linearly
+ * with the last observing frame as the anchor (single_triangulation_common, src/feat/FeatureInitializer.cpp:6-110);
+ * with more than 3 such keypoints wTq = findTransform(mean, world) [poseSE32SE2 with se2_flag], else identity and
+ * ok = 0.  kp_world_out (n_obj x K x 3, NaN where not triangulated) and kp_valid_out (n_obj x K) may be NULL. */
+int orcvio_object_init(int n_obj, const int* frame_off, const double* frames_wTc, const double* zs, int K,
+                       const double* kps_mean, int se2_flag, double* wTq16_out, int* ok_out, double* kp_world_out,
+                       int* kp_valid_out);
+/* orcvio_object_lm = ObjectFeatureInitializer::single_levenberg_marquardt up to the optimum (:346-381): minimises the
+ * ObjectLM functor (keypoint reprojection, bounding-box / quadric, deformation and shape regularisers, weights4,
+ * src/obj/ObjectLM.cpp:761-816) over (wTo, shape, keypoints) with the reference's Levenberg-Marquardt (factor 10),
+ * started from (wTo_init, mean_shape, kps_mean).  flags: bit0 left perturbation, bit1 new bbox residual.
+ * Outputs per object: wTo (16), shape (3), keypoints in the object frame (K x 3) and in the world frame
+ * (transform_mean_keypoints_to_global; may be NULL), status = LevenbergMarquardtSpace::Status (success = not 0 / 5),
+ * nfev, njev, |f| (each may be NULL), rounds_out = lock-step rounds = kernel launches (may be NULL).  The rows the
+ * filter consumes at the optimum come from orcvio_object_residuals. */
+int orcvio_object_lm(int n_obj, const int* frame_off, const double* frames_wTc, const double* zs, const double* zb, int K,
+                     const double* kps_mean, const double* mean_shape, const double* weights4, int flags,
+                     const double* wTo_init, double* wTo_out, double* shape_out, double* kps_out, double* kps_world_out,
+                     int* status_out, int* nfev_out, int* njev_out, double* fnorm_out, int* rounds_out);
+/* One evaluation of the ObjectLM model at given states (n_obj x [wTo 16 | shape 3 | keypoints 3K]):
+ * out = n_obj x [|f| | J^T f (n) | J^T J (n x n)], n = 9 + 3K -- ObjectLM::operator() and ::df reduced to what the
+ * optimiser consumes. */
+int orcvio_object_lm_eval(int n_obj, const int* frame_off, const double* frames_wTc, const double* zs, const double* zb,
+                          int K, const double* kps_mean, const double* mean_shape, const double* weights4, int flags,
+                          const double* states, double* out);
+/* The reference's two Levenberg-Marquardt known-answer problems (src/tests/test_levenberg_marquardt.cpp:64-140) through
+ * the library's driver; which = 0: lmder1 example (x_out 3), 1: the quadratic (x_out 1).  Needs no device. */
+int orcvio_lm_known_answer(int which, double* x_out, int* status, int* nfev, int* njev, double* fnorm);
 /* The reference's trajectory logger (System::publishGroundtruth, ros_wrapper/src/orcvio/src/System.cpp:885-943) for a
  * batch of trajectories, on the device: first-pose SE(3) alignment, then per trajectory the mean orientation error
  * (deg), mean position error (m), position RMSE (m) and final position error (m) -> out4 (n_traj x 4).  Poses are

@@ -231,14 +231,22 @@ def camera_lm(frames_wTc, wTo, shape, kps, zs_all, zb_all, left, new_residual,
 
 
 def object_lm_rows(frames_wTc, wTo, shape, kps, zs_all, zb_all, left, new_residual,
-                   residual_weights=(1.0, 1.0)):
+                   residual_weights=(1.0, 1.0), clone_pose_inverse=False):
     """Keypoint + bbox rows of ObjectLM::operator()/df (ObjectLM.cpp:761-816), i.e. what
-    ObjectFeatureInitializer.cpp:424-432 keeps for the filter: (fvec, fjac rows x (9+3K))."""
+    ObjectFeatureInitializer.cpp:424-432 keeps for the filter: (fvec, fjac rows x (9+3K)).
+    clone_pose_inverse: cTw = [R^T | -R^T p] as ClonePose::getTransformGlobalToCam builds it
+    (FeatureInitializer.h:51-81) instead of the matrix inverse -- they differ when R is only
+    orthonormal to single precision, like the camera poses of the reference's one_car data."""
     K = kps.shape[0]
     kps_h = np.hstack([kps, np.ones((K, 1))])
     f_kp, J_kp, f_bb, J_bb = [], [], [], []
     for f, wTc in enumerate(frames_wTc):
-        cTw = np.linalg.inv(wTc)
+        if clone_pose_inverse:
+            cTw = np.eye(4)
+            cTw[:3, :3] = wTc[:3, :3].T
+            cTw[:3, 3] = -wTc[:3, :3].T @ wTc[:3, 3]
+        else:
+            cTw = np.linalg.inv(wTc)
         f_kp.append(kp_residual(cTw, wTo, kps_h, zs_all[f]))
         J_kp.append(kp_jac_object(cTw, wTo, kps_h, zs_all[f], left))
         f_bb.append(bbox_residual(cTw, wTo, shape, zb_all[f], new_residual))
@@ -294,3 +302,122 @@ def pose_se3_to_se2(T):
     out[1, 1] = math.cos(yaw)
     out[1, 3] = T[1, 3]
     return out
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Object LM optimiser: the full ObjectLM functor (4 blocks), the keypoint triangulation of
+# single_object_initialization and single_levenberg_marquardt.  Pinned by the reference's goldens
+# test_error_deform_reg.h5 / test_error_mean_shape_reg.h5 (src/tests/test_object_lm.cpp:233-295) and by the assertions
+# of its multi-frame tests on one_car/*.h5 (src/tests/test_object_lm_multiframe.cpp:61-125,
+# test_object_init_multiframe.cpp:24-86) -- tests/test_oracle_cpu.py.
+def deform_reg(kps, kps_mean, T):
+    """ErrorDeformRegularization::operator()/df, src/obj/ObjectLM.cpp:652-718: (kps - mean), keypoint-major, repeated
+    once per frame; Jacobian = identity on the keypoint's own columns."""
+    K = kps.shape[0]
+    f1 = (kps - kps_mean).reshape(-1)
+    J1 = np.zeros((3 * K, 9 + 3 * K))
+    J1[:, 9:] = np.eye(3 * K)
+    return np.tile(f1, T), np.tile(J1, (T, 1))
+
+
+def quadv_reg(shape, mean_shape, T, K):
+    """ErrorQuadVRegularization::operator()/df, src/obj/ObjectLM.cpp:732-760."""
+    J1 = np.zeros((3, 9 + 3 * K))
+    J1[:, 6:9] = np.eye(3)
+    return np.tile(np.asarray(shape, float) - mean_shape, T), np.tile(J1, (T, 1))
+
+
+def object_lm_full(frames_wTc, wTo, shape, kps, zs_all, zb_all, left, new_residual, kps_mean, mean_shape, weights):
+    """ObjectLM::operator() and ::df with all four functors (src/obj/ObjectLM.cpp:761-816), Huber epsilon = inf."""
+    K = kps.shape[0]
+    T = len(frames_wTc)
+    f01, J01 = object_lm_rows(frames_wTc, wTo, shape, kps, zs_all, zb_all, left, new_residual,
+                              residual_weights=(weights[0], weights[1]), clone_pose_inverse=True)
+    f2, J2 = deform_reg(kps, kps_mean, T)
+    f3, J3 = quadv_reg(shape, mean_shape, T, K)
+    return (np.concatenate([f01, weights[2] * f2, weights[3] * f3]),
+            np.vstack([J01, weights[2] * J2, weights[3] * J3]))
+
+
+def object_state_plus(x, dx):
+    """operator+(LMObjectState, Tangent), src/obj/ObjectLM.cpp:63-70, 211-227: the pose is ALWAYS retracted on the left
+    (exp(dx) * wTo), whatever use_left_perturbation_flag says."""
+    wTo, shape, kps = x
+    return (mu.se3_exp(dx[:6]) @ wTo, shape + dx[6:9], kps + dx[9:].reshape(-1, 3))
+
+
+def object_state_scaled_norm(diag, x):
+    """LMObjectState::scaled_norm, include/orcvio/obj/ObjectLM.h:236-249: a SUM of the blocks' norms."""
+    wTo, shape, kps = x
+    s = float(np.linalg.norm(diag[:6] * mu.se3_log(wTo)))
+    s += float(np.linalg.norm(diag[6:9] * shape))
+    for k in range(kps.shape[0]):
+        s += float(np.linalg.norm(kps[k] * diag[9 + 3 * k:12 + 3 * k]))
+    return s
+
+
+def triangulate_linear(uvs, wTcs):
+    """single_triangulation_common, src/feat/FeatureInitializer.cpp:6-110: anchor = the LAST observing frame; rows
+    B_perp(b_i) p = B_perp(b_i) p_CiinA with b_i the unit bearing rotated into the anchor frame; least squares."""
+    R_GtoA = wTcs[-1][:3, :3].T
+    p_AinG = wTcs[-1][:3, 3]
+    A, b = [], []
+    for uv, wTc in zip(uvs, wTcs):
+        R_AtoCi = wTc[:3, :3].T @ R_GtoA.T
+        p_CiinA = R_GtoA @ (wTc[:3, 3] - p_AinG)
+        bi = R_AtoCi.T @ np.array([uv[0], uv[1], 1.0])
+        bi = bi / np.linalg.norm(bi)
+        Bp = np.array([[-bi[2], 0.0, bi[0]], [0.0, bi[2], -bi[1]]])
+        A.append(Bp)
+        b.append(Bp @ p_CiinA)
+    p_f = np.linalg.lstsq(np.vstack(A), np.concatenate(b), rcond=None)[0]
+    return R_GtoA.T @ p_f + p_AinG
+
+
+def single_object_initialization(frames_wTc, zs_all, kps_mean, se2=True, min_obs=3):
+    """ObjectFeatureInitializer::single_object_initialization without RANSAC (src/obj/ObjectFeatureInitializer.cpp:
+    33-111): every keypoint seen in MORE than `min_obs` frames (ObjectFeature.cpp:86-127) is triangulated; with more
+    than 3 such keypoints the pose is findTransform(mean, world) [+ poseSE32SE2].  Returns (ok, wTq, ids, points)."""
+    ids, pts = [], []
+    for k in range(kps_mean.shape[0]):
+        fr = [f for f in range(len(frames_wTc)) if np.all(np.isfinite(zs_all[f][k]))]
+        if len(fr) > min_obs:
+            ids.append(k)
+            pts.append(triangulate_linear([zs_all[f][k] for f in fr], [frames_wTc[f] for f in fr]))
+    if len(ids) <= 3:
+        return False, np.eye(4), ids, np.array(pts)
+    T = find_transform(kps_mean[ids].T, np.array(pts).T)
+    if se2:
+        T = pose_se3_to_se2(T)
+    return True, T, ids, np.array(pts)
+
+
+def single_levenberg_marquardt(frames_wTc, zs_all, zb_all, wTo0, kps_mean, mean_shape, weights, left, new_residual):
+    """ObjectFeatureInitializer::single_levenberg_marquardt, src/obj/ObjectFeatureInitializer.cpp:346-440: factor 10,
+    start = (initial pose, mean shape, mean keypoints).  Returns the oracle.lm result dict (x = (wTo, shape, kps))
+    plus `success` (lm.info() == Success: every status but ImproperInputParameters and TooManyFunctionEvaluation,
+    LMonestep.h:90, 165-198)."""
+    from . import lm
+
+    def fun(x):
+        return object_lm_full(frames_wTc, x[0], x[1], x[2], zs_all, zb_all, left, new_residual, kps_mean, mean_shape,
+                              weights)[0]
+
+    def jac(x):
+        return object_lm_full(frames_wTc, x[0], x[1], x[2], zs_all, zb_all, left, new_residual, kps_mean, mean_shape,
+                              weights)[1]
+
+    x0 = (np.array(wTo0, float), np.array(mean_shape, float).ravel(), np.array(kps_mean, float))
+    res = lm.minimize(fun, jac, x0, plus=object_state_plus, scaled_norm=object_state_scaled_norm, factor=10.0)
+    res["success"] = res["status"] not in (lm.IMPROPER, lm.TOO_MANY_FEV)
+    return res
+
+
+def keypoints_to_global(kps, wTo):
+    """transform_mean_keypoints_to_global, src/obj/ObjectState.cpp:15-40."""
+    return kps @ wTo[:3, :3].T + wTo[:3, 3]
+
+
+def displacement(T1, T2):
+    """include/orcvio/utils/se3_ops.hpp:485-497."""
+    return (3.0 - np.trace(T1[:3, :3].T @ T2[:3, :3])) / 2.0, float(np.linalg.norm(T1[:3, 3] - T2[:3, 3]))

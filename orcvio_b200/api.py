@@ -589,6 +589,111 @@ def object_kabsch_init(mean_pts, world_pts, se2=False):
     return T, ok
 
 
+def _object_batch(frames_list, zs_list, zb_list=None):
+    """Flattens per-object (T_i, 4, 4) / (T_i, K, 2) / (T_i, 4) arrays into the batch layout of the C ABI."""
+    off = np.zeros(len(frames_list) + 1, dtype=np.int32)
+    off[1:] = np.cumsum([len(f) for f in frames_list])
+    frames = np.ascontiguousarray(np.concatenate([_f64(f).reshape(-1, 16) for f in frames_list]))
+    K = np.asarray(zs_list[0]).shape[1]
+    zs = np.ascontiguousarray(np.concatenate([_f64(z).reshape(-1, K, 2) for z in zs_list]))
+    zb = None if zb_list is None else np.ascontiguousarray(np.concatenate([_f64(b).reshape(-1, 4) for b in zb_list]))
+    return off, frames, zs, zb, K
+
+
+class ObjectFeatureInitializer:
+    """Mirror of orcvio::ObjectFeatureInitializer (include/orcvio/obj/ObjectFeatureInitializer.h) for a batch of objects
+    of one class: same constructor arguments (mean ellipsoid shape, mean keypoints, residual weights; the camera
+    intrinsics are the identity as everywhere in the reference) and the two methods the object branch calls."""
+
+    def __init__(self, object_mean_shape, object_keypoints_mean, residual_weights=(1.0, 1.0, 1.0, 1.0)):
+        self.mean_shape = _f64(object_mean_shape).reshape(3)
+        self.kps_mean = _f64(object_keypoints_mean).reshape(-1, 3)
+        self.weights = _f64(residual_weights).reshape(4)
+        self.estimate_SE2_pose_flag = True       # hard-coded in the reference (ObjectFeatureInitializer.cpp:29)
+
+    def single_object_initialization(self, frames_list, zs_list):
+        """-> (ok (n_obj), wTq (n_obj, 4, 4), kp_world (n_obj, K, 3), kp_valid (n_obj, K))."""
+        L = lib()
+        off, frames, zs, _, K = _object_batch(frames_list, zs_list)
+        assert K == len(self.kps_mean)
+        n = len(frames_list)
+        T = np.zeros((n, 4, 4))
+        ok = np.zeros(n, dtype=np.int32)
+        kw = np.zeros((n, K, 3))
+        kv = np.zeros((n, K), dtype=np.int32)
+        L.orcvio_object_init.argtypes = [C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_int,
+                                         C.POINTER(C.c_double), C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_int),
+                                         C.POINTER(C.c_double), C.POINTER(C.c_int)]
+        rc = L.orcvio_object_init(n, _ip(off), _dp(frames), _dp(zs), K, _dp(self.kps_mean),
+                                  int(self.estimate_SE2_pose_flag), _dp(T), _ip(ok), _dp(kw), _ip(kv))
+        if rc != 0:
+            raise RuntimeError(f"orcvio_object_init failed: {rc}")
+        return ok, T, kw, kv
+
+    def _lm_args(self, frames_list, zs_list, zb_list):
+        off, frames, zs, zb, K = _object_batch(frames_list, zs_list, zb_list)
+        assert K == len(self.kps_mean)
+        return off, frames, zs, zb, K
+
+    def single_levenberg_marquardt(self, frames_list, zs_list, zb_list, wTo_init, use_left_perturbation_flag=True,
+                                   use_new_bbox_residual_flag=False):
+        """-> dict(success, status, nfev, njev, fnorm, wTo, shape, kps, kps_world, rounds), arrays over the objects."""
+        L = lib()
+        off, frames, zs, zb, K = self._lm_args(frames_list, zs_list, zb_list)
+        n = len(frames_list)
+        w0 = np.ascontiguousarray(_f64(wTo_init).reshape(n, 16))
+        out = dict(wTo=np.zeros((n, 4, 4)), shape=np.zeros((n, 3)), kps=np.zeros((n, K, 3)), kps_world=np.zeros((n, K, 3)),
+                   status=np.zeros(n, dtype=np.int32), nfev=np.zeros(n, dtype=np.int32), njev=np.zeros(n, dtype=np.int32),
+                   fnorm=np.zeros(n))
+        rounds = C.c_int(0)
+        dp, ip = C.POINTER(C.c_double), C.POINTER(C.c_int)
+        L.orcvio_object_lm.argtypes = [C.c_int, ip, dp, dp, dp, C.c_int, dp, dp, dp, C.c_int, dp, dp, dp, dp, dp, ip, ip, ip,
+                                       dp, ip]
+        flags = (1 if use_left_perturbation_flag else 0) | (2 if use_new_bbox_residual_flag else 0)
+        rc = L.orcvio_object_lm(n, _ip(off), _dp(frames), _dp(zs), _dp(zb), K, _dp(self.kps_mean), _dp(self.mean_shape),
+                                _dp(self.weights), flags, _dp(w0), _dp(out["wTo"]), _dp(out["shape"]), _dp(out["kps"]),
+                                _dp(out["kps_world"]), _ip(out["status"]), _ip(out["nfev"]), _ip(out["njev"]),
+                                _dp(out["fnorm"]), C.byref(rounds))
+        if rc != 0:
+            raise RuntimeError(f"orcvio_object_lm failed: {rc}")
+        out["rounds"] = rounds.value
+        out["success"] = (out["status"] != 0) & (out["status"] != 5)
+        return out
+
+    def lm_eval(self, frames_list, zs_list, zb_list, states, use_left_perturbation_flag=True,
+                use_new_bbox_residual_flag=False):
+        """|f|, J^T f, J^T J of the ObjectLM model at `states` = list of (wTo, shape, kps)."""
+        L = lib()
+        off, frames, zs, zb, K = self._lm_args(frames_list, zs_list, zb_list)
+        n = len(frames_list)
+        nn = 9 + 3 * K
+        xs = np.ascontiguousarray(np.stack([np.concatenate([_f64(w).reshape(16), _f64(s).reshape(3), _f64(k).reshape(3 * K)])
+                                            for (w, s, k) in states]))
+        out = np.zeros((n, 1 + nn + nn * nn))
+        dp, ip = C.POINTER(C.c_double), C.POINTER(C.c_int)
+        L.orcvio_object_lm_eval.argtypes = [C.c_int, ip, dp, dp, dp, C.c_int, dp, dp, dp, C.c_int, dp, dp]
+        flags = (1 if use_left_perturbation_flag else 0) | (2 if use_new_bbox_residual_flag else 0)
+        rc = L.orcvio_object_lm_eval(n, _ip(off), _dp(frames), _dp(zs), _dp(zb), K, _dp(self.kps_mean), _dp(self.mean_shape),
+                                     _dp(self.weights), flags, _dp(xs), _dp(out))
+        if rc != 0:
+            raise RuntimeError(f"orcvio_object_lm_eval failed: {rc}")
+        return out[:, 0], out[:, 1:1 + nn], out[:, 1 + nn:].reshape(n, nn, nn)
+
+
+def lm_known_answer(which):
+    """The reference's Levenberg-Marquardt known-answer problems through the library's driver (no device needed)."""
+    L = lib()
+    x = np.zeros(3)
+    st, nf, nj = C.c_int(0), C.c_int(0), C.c_int(0)
+    fn = C.c_double(0)
+    L.orcvio_lm_known_answer.argtypes = [C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_int), C.POINTER(C.c_int),
+                                         C.POINTER(C.c_int), C.POINTER(C.c_double)]
+    rc = L.orcvio_lm_known_answer(which, _dp(x), C.byref(st), C.byref(nf), C.byref(nj), C.byref(fn))
+    if rc != 0:
+        raise RuntimeError(f"orcvio_lm_known_answer failed: {rc}")
+    return dict(x=x[:3 if which == 0 else 1], status=st.value, nfev=nf.value, njev=nj.value, fnorm=fn.value)
+
+
 def trajectory_metrics(est_pose7, gt_pose7):
     """System::publishGroundtruth on the device for a batch of trajectories (orcvio_trajectory_metrics):
     (n, F, 7) poses (p, q xyzw) -> (n, 4): mean orientation error (deg), mean position error, position RMSE, final

@@ -33,6 +33,8 @@ SOURCES = {
     "hybrid_kernel.cu": [],
     "metrics_kernel.cu": [],
     "kabsch_kernel.cu": [],
+    "objlm_kernel.cu": [],
+    "lm.cpp": [],
     "batch.cu": [],
     "objects.cu": [],
     "capi.cu": [],

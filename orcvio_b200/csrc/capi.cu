@@ -305,6 +305,33 @@ int orcvio_object_kabsch_init(const double* mean_pts, const double* world_pts, c
   return ob::kabsch_init(mean_pts, world_pts, off, n_obj, se2_flag, wTq16_out, ok_out);
 }
 
+int orcvio_object_init(int n_obj, const int* frame_off, const double* frames_wTc, const double* zs, int K,
+                       const double* kps_mean, int se2_flag, double* wTq16_out, int* ok_out, double* kp_world_out,
+                       int* kp_valid_out) {
+  // min_triangulation_observations_num = 3 (include/orcvio/obj/ObjectFeature.h:77)
+  return ob::object_init(n_obj, frame_off, frames_wTc, zs, K, kps_mean, se2_flag, 3, wTq16_out, ok_out, kp_world_out,
+                         kp_valid_out);
+}
+
+int orcvio_object_lm(int n_obj, const int* frame_off, const double* frames_wTc, const double* zs, const double* zb, int K,
+                     const double* kps_mean, const double* mean_shape, const double* weights4, int flags,
+                     const double* wTo_init, double* wTo_out, double* shape_out, double* kps_out, double* kps_world_out,
+                     int* status_out, int* nfev_out, int* njev_out, double* fnorm_out, int* rounds_out) {
+  return ob::object_lm(n_obj, frame_off, frames_wTc, zs, zb, K, kps_mean, mean_shape, weights4, flags, wTo_init, wTo_out,
+                       shape_out, kps_out, kps_world_out, status_out, nfev_out, njev_out, fnorm_out, rounds_out);
+}
+
+int orcvio_object_lm_eval(int n_obj, const int* frame_off, const double* frames_wTc, const double* zs, const double* zb,
+                          int K, const double* kps_mean, const double* mean_shape, const double* weights4, int flags,
+                          const double* states, double* out) {
+  return ob::object_lm_eval(n_obj, frame_off, frames_wTc, zs, zb, K, kps_mean, mean_shape, weights4, flags, states, out);
+}
+
+int orcvio_lm_known_answer(int which, double* x_out, int* status, int* nfev, int* njev, double* fnorm) {
+  if (!x_out) return ORCVIO_ERR_ARG;
+  return ob::lm_known_answer(which, x_out, status, nfev, njev, fnorm);
+}
+
 int orcvio_trajectory_metrics(const double* est_pose7, const double* gt_pose7, int n_traj, int n_frames, double* out4) {
   if (!est_pose7 || !gt_pose7 || !out4) return ORCVIO_ERR_ARG;
   return ob::trajectory_metrics(est_pose7, gt_pose7, n_traj, n_frames, out4);

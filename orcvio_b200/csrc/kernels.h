@@ -327,6 +327,17 @@ void launch_info_prior(const UpdArgs& u, const InfoBufs& ib, int max_N, cudaStre
 int trajectory_metrics(const double* est_pose7, const double* gt_pose7, int n_traj, int n_frames, double* out4);
 // findTransform (+ poseSE32SE2) for a batch of objects (kabsch_kernel.cu); host pointers
 int kabsch_init(const double* mean_pts, const double* world_pts, const int* off, int n_obj, int se2, double* wTq16, int* ok);
+// object state optimiser (objlm_kernel.cu); host pointers
+int object_init(int n_obj, const int* frame_off, const double* frames_wTc, const double* zs, int K, const double* kps_mean,
+                int se2, int min_obs, double* wTq16, int* ok, double* kp_world, int* kp_valid);
+int object_lm(int n_obj, const int* frame_off, const double* frames_wTc, const double* zs, const double* zb, int K,
+              const double* kps_mean, const double* mean_shape, const double* weights4, int flags, const double* wTo_init,
+              double* wTo_out, double* shape_out, double* kps_out, double* kps_world_out, int* status, int* nfev,
+              int* njev, double* fnorm, int* rounds_out);
+int object_lm_eval(int n_obj, const int* frame_off, const double* frames_wTc, const double* zs, const double* zb, int K,
+                   const double* kps_mean, const double* mean_shape, const double* weights4, int flags, const double* xs,
+                   double* out);
+int lm_known_answer(int which, double* x_out, int* status, int* nfev, int* njev, double* fnorm);
 int syrk_debug_read(long long* out, int cap);   // ORCVIO_SYRK_DBG=1: phase time stamps of the last k_syrk launch
 void launch_info_dense_factor(const UpdArgs& u, const InfoBufs& ib, const double* Hp, int ldh, int rows, int n,
                               cudaStream_t s);

@@ -148,3 +148,15 @@ def test_syrk_plan_covers_every_row_once_and_fits_the_budget():
     L.orcvio_syrk_plan_probe(24447, j.ctypes.data, 30, 148, a.ctypes.data)
     L.orcvio_syrk_plan_probe(24447, j.ctypes.data, 30, 148, b.ctypes.data)
     assert np.array_equal(a, b) and a[3] <= 148
+
+
+def test_library_lm_driver_reproduces_the_reference_known_answers():
+    """orcvio_lm_known_answer: src/tests/test_levenberg_marquardt.cpp:64-140 through the library's own driver (normal
+    equations + pivoted Cholesky instead of the column-pivoted QR): same info, nfev, njev, |f| and x."""
+    import numpy as np
+    r = api.lm_known_answer(0)
+    assert (r["status"], r["nfev"], r["njev"]) == (1, 6, 5)
+    assert abs(r["fnorm"] - 0.09063596) < 1e-6
+    assert np.linalg.norm(r["x"] - np.array([0.08241058, 1.133037, 2.343695])) < 1e-6
+    r = api.lm_known_answer(1)
+    assert (r["status"], r["nfev"], r["njev"]) == (4, 2, 2) and abs(r["fnorm"]) < 1e-6 and abs(r["x"][0] - 10.0) < 1e-6

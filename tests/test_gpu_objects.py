@@ -281,3 +281,89 @@ def test_kabsch_init_matches_reference_known_answers_and_oracle():
         np.testing.assert_allclose(T2[i], obj.pose_se3_to_se2(T[i]), rtol=0, atol=1e-9)
     T3, ok3 = api.object_kabsch_init([kps[:1], kps[:5]], [kps[:1], np.tile(kps[:1], (5, 1))])
     assert list(ok3) == [0, 0]
+
+
+# ------------------------------------------------------------------ object state optimiser
+def _lm_scenes(n, seed=3):
+    """Objects of one class seen over 5..14 frames with dropped keypoints; plus the reference's one_car sequence."""
+    from test_oracle_cpu import _one_car
+    d = _one_car()
+    scenes = [(d["frames"], d["zs"], d["zb"])]
+    for i in range(n):
+        fr, wTo, shape, kps, zs, zb = _object_scene(T=5 + (3 * i) % 10, seed=seed + i, drop=True)
+        scenes.append((fr, zs, zb))
+    return d, scenes
+
+
+@pytest.mark.parametrize("left", [True, False])
+@pytest.mark.parametrize("new_residual", [False, True])
+def test_object_lm_normal_equations_match_oracle(left, new_residual):
+    """k_object_lm_eval: |f|, J^T f, J^T J of the four-block ObjectLM functor against the oracle's stacked Jacobian
+    (1e-12 relative to the largest entry), ragged observations, weights all different."""
+    d, scenes = _lm_scenes(6)
+    rng = np.random.default_rng(11)
+    w = [1.0, 3e-2, 0.7, 1.3]
+    init = api.ObjectFeatureInitializer(d["mean_shape"], d["kps_mean"], w)
+    states = []
+    for (fr, zs, zb) in scenes:
+        ok, T0, _, _ = obj.single_object_initialization(fr, zs, d["kps_mean"], se2=False)
+        T0[:3, :3] /= np.cbrt(np.linalg.det(T0[:3, :3]))
+        states.append((mu.se3_exp(rng.normal(0, 0.03, 6)) @ T0, d["mean_shape"] + rng.normal(0, 0.05, 3),
+                       d["kps_mean"] + rng.normal(0, 0.02, (12, 3))))
+    fn, g, A = init.lm_eval([s[0] for s in scenes], [s[1] for s in scenes], [s[2] for s in scenes], states, left,
+                            new_residual)
+    for i, ((fr, zs, zb), x) in enumerate(zip(scenes, states)):
+        f, J = obj.object_lm_full(fr, x[0], x[1], x[2], zs, zb, left, new_residual, d["kps_mean"], d["mean_shape"], w)
+        assert abs(fn[i] - np.linalg.norm(f)) <= 1e-12 * np.linalg.norm(f)
+        JtJ, Jtf = J.T @ J, J.T @ f
+        assert np.abs(A[i] - JtJ).max() <= 1e-12 * np.abs(JtJ).max(), i
+        assert np.abs(g[i] - Jtf).max() <= 1e-12 * np.abs(Jtf).max(), i
+
+
+def test_object_initialisation_matches_oracle():
+    """orcvio_object_init (keypoint triangulation + Kabsch + poseSE32SE2) against the oracle on the reference's two
+    sequences and on ragged synthetic objects, incl. one with too few triangulable keypoints."""
+    from test_oracle_cpu import _one_car
+    d, scenes = _lm_scenes(8)
+    scenes.append((_one_car("one_car_no_zb")["frames"], _one_car("one_car_no_zb")["zs"], None))
+    few = np.array(scenes[1][1], copy=True)
+    few[:, 3:, :] = np.nan                       # only 3 keypoints left: no pose
+    scenes.append((scenes[1][0], few, None))
+    init = api.ObjectFeatureInitializer(d["mean_shape"], d["kps_mean"])
+    for se2 in (True, False):
+        init.estimate_SE2_pose_flag = se2
+        ok, T, kw, kv = init.single_object_initialization([s[0] for s in scenes], [s[1] for s in scenes])
+        for i, (fr, zs, _) in enumerate(scenes):
+            ok_o, T_o, ids, pts = obj.single_object_initialization(fr, zs, d["kps_mean"], se2=se2)
+            assert bool(ok[i]) == ok_o and list(np.nonzero(kv[i])[0]) == ids
+            if len(ids):
+                np.testing.assert_allclose(kw[i][ids], pts, rtol=0, atol=1e-9 * max(1.0, np.abs(pts).max()))
+            np.testing.assert_allclose(T[i], T_o, rtol=0, atol=1e-8)
+    assert list(ok[-1:]) == [0]
+
+
+@pytest.mark.parametrize("left,new_residual", [(True, False), (False, False), (True, True)])
+def test_object_lm_matches_oracle(left, new_residual):
+    """orcvio_object_lm for a batch in lock-step against the oracle's restatement of the reference optimiser run one
+    object at a time: same status, nfev, njev; optimum within 1e-7 (the two differ by a column-pivoted QR of J against
+    a pivoted Cholesky of J^T J and stop on sqrt(eps) tests)."""
+    d, scenes = _lm_scenes(5)
+    w = [1.0, 3e-2, 1.0, 1.0]
+    init = api.ObjectFeatureInitializer(d["mean_shape"], d["kps_mean"], w)
+    ok, T0, _, _ = init.single_object_initialization([s[0] for s in scenes], [s[1] for s in scenes])
+    assert np.all(ok == 1)
+    out = init.single_levenberg_marquardt([s[0] for s in scenes], [s[1] for s in scenes], [s[2] for s in scenes], T0,
+                                          left, new_residual)
+    assert out["rounds"] == out["nfev"].max()
+    for i, (fr, zs, zb) in enumerate(scenes):
+        res = obj.single_levenberg_marquardt(fr, zs, zb, T0[i], d["kps_mean"], d["mean_shape"], w, left, new_residual)
+        assert bool(out["success"][i]) == res["success"]
+        assert (out["status"][i], out["nfev"][i], out["njev"][i]) == (res["status"], res["nfev"], res["njev"]), i
+        assert abs(out["fnorm"][i] - res["fnorm"]) <= 1e-9 * max(1.0, res["fnorm"])
+        np.testing.assert_allclose(out["wTo"][i], res["x"][0], rtol=0, atol=1e-7)
+        np.testing.assert_allclose(out["shape"][i], res["x"][1], rtol=0, atol=1e-7)
+        np.testing.assert_allclose(out["kps"][i], res["x"][2], rtol=0, atol=1e-7)
+        np.testing.assert_allclose(out["kps_world"][i], obj.keypoints_to_global(res["x"][2], res["x"][0]), rtol=0, atol=1e-6)
+    # the reference's own assertion on its sequence (test_object_lm_multiframe.cpp:115-123)
+    dR, dt = obj.displacement(d["wTq"], out["wTo"][0])
+    assert abs(dR) < 0.5 and dt < 0.05 * np.linalg.norm(d["wTq"][:3, 3])

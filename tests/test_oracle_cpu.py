@@ -312,3 +312,79 @@ def test_find_transform_reproduces_the_reference_known_answers():
         assert np.abs(T[:3, :3] - sR).max() <= 1e-13 and np.abs(T[:3, 3] - S).max() <= 1e-13
     T2 = obj.pose_se3_to_se2(T)
     assert T2[2, 3] == 0 and abs(np.linalg.det(T2[:2, :2]) - 1) < 1e-15 and T2[0, 3] == T[0, 3]
+
+
+# ------------------------------------------------------------------ object LM optimiser
+def test_lm_oracle_reproduces_the_reference_known_answers():
+    """oracle.lm against src/tests/test_levenberg_marquardt.cpp:64-140 (exact counts, 1e-6 like the test)."""
+    from oracle import lm
+    r = lm.lmder1(lm.kat_fun, lm.kat_jac, np.ones(3))
+    assert (r["status"], r["nfev"], r["njev"]) == (1, 6, 5)
+    assert abs(r["fnorm"] - 0.09063596) < 1e-6
+    assert np.linalg.norm(r["x"] - np.array([0.08241058, 1.133037, 2.343695])) < 1e-6
+    r = lm.minimize(lambda x: x - 10.0, lambda x: np.array([[1.0]]), np.ones(1))
+    assert (r["status"], r["nfev"], r["njev"]) == (lm.COS_TOO_SMALL, 2, 2)
+    assert abs(r["fnorm"]) < 1e-6 and abs(r["x"][0] - 10.0) < 1e-6
+
+
+def test_regulariser_goldens():
+    """ErrorDeformRegularization / ErrorQuadVRegularization against the reference's golden vectors
+    (src/tests/test_object_lm.cpp:233-295, 1e-6 like the tests)."""
+    g = _gold("test_error_deform_reg")
+    f, J = obj.deform_reg(g["M"][:, :3] / g["M"][:, 3:4], g["Mhat"], 1)
+    assert np.linalg.norm(f - g["error"]) < 1e-6 and np.linalg.norm(J - g["jacobian"]) < 1e-6
+    g = _gold("test_error_mean_shape_reg")
+    f, J = obj.quadv_reg(g["v"], g["mean_v"], 1, 12)
+    assert np.linalg.norm(f - g["error"]) < 1e-6 and np.linalg.norm(J - g["jacobian"]) < 1e-6
+
+
+def _one_car(name="one_car"):
+    g = _gold(name)
+    zb = None
+    if "zb" in g.files:                      # x, y, width, height -> xmin ymin xmax ymax (test_utils.cpp:100-106)
+        xywh = g["zb"][:, 0, :]
+        zb = np.column_stack([xywh[:, 0], xywh[:, 1], xywh[:, 0] + xywh[:, 2], xywh[:, 1] + xywh[:, 3]])
+    return dict(frames=g["wTo"], zs=g["zs"], zb=zb, kps_mean=g["mean_shape"][-1],
+                mean_shape=g["ellipsoid_shape"][-1].ravel(), wTq=g["wTq"][-1])
+
+
+def test_object_initialisation_and_lm_on_the_reference_sequences():
+    """The assertions of the reference's multi-frame tests on its own data (src/tests/test_object_init_multiframe.cpp:
+    24-86, test_object_lm_multiframe.cpp:61-125).  The rotation bounds (0.5) hold as written.  The initialisation's
+    translation bound (0.35 m) holds for the SE(3) fit (0.19 m) and NOT for the pose the reference ships: with its
+    hard-coded estimate_SE2_pose_flag = true, poseSE32SE2 zeroes z (ground truth: -0.68 m), i.e. 0.71 m -- recorded
+    here as the reference's behaviour.  After the LM the test's bound (5 % of |t|) holds from that start."""
+    for name in ("one_car_no_zb", "one_car"):
+        d = _one_car(name)
+        ok, T3, ids, pts = obj.single_object_initialization(d["frames"], d["zs"], d["kps_mean"], se2=False)
+        assert ok and len(ids) == 12
+        dR, dt = obj.displacement(d["wTq"], T3)
+        assert dt < 3.5e-1
+        ok, T2, _, _ = obj.single_object_initialization(d["frames"], d["zs"], d["kps_mean"], se2=True)
+        dR, dt = obj.displacement(d["wTq"], T2)
+        assert ok and abs(dR) < 0.5 and 0.6 < dt < 0.8 and T2[2, 3] == 0.0
+    res = obj.single_levenberg_marquardt(d["frames"], d["zs"], d["zb"], T2, d["kps_mean"], d["mean_shape"],
+                                         [1.0, 3e-2, 1.0, 1.0], True, False)
+    assert res["success"] and res["status"] == 1
+    dR, dt = obj.displacement(d["wTq"], res["x"][0])
+    assert abs(dR) < 0.5 and dt < 0.05 * np.linalg.norm(d["wTq"][:3, 3])
+
+
+def test_object_lm_jacobian_matches_central_differences_under_its_own_retraction():
+    """ObjectLM::df against central differences of ObjectLM::operator() under operator+ (left retraction) -- the check
+    of src/tests/test_object_lm.cpp:297-368 on the full four-block functor."""
+    d = _one_car()
+    rng = np.random.default_rng(5)
+    x = (mu.se3_exp(rng.normal(0, 0.05, 6)) @ d["wTq"], d["mean_shape"] + rng.normal(0, 0.05, 3),
+         d["kps_mean"] + rng.normal(0, 0.02, (12, 3)))
+    w = [1.0, 3e-2, 0.7, 1.3]
+    fr, zs, zb = d["frames"][:9], d["zs"][:9], d["zb"][:9]
+    f0, J = obj.object_lm_full(fr, x[0], x[1], x[2], zs, zb, True, False, d["kps_mean"], d["mean_shape"], w)
+    assert f0.shape[0] == 9 * 24 + 9 * 4 + 9 * 36 + 9 * 3 and J.shape[1] == 45
+    h = 1e-6
+    for c in range(45):
+        e = np.zeros(45)
+        e[c] = h
+        fp = obj.object_lm_full(fr, *obj.object_state_plus(x, e), zs, zb, True, False, d["kps_mean"], d["mean_shape"], w)[0]
+        fm = obj.object_lm_full(fr, *obj.object_state_plus(x, -e), zs, zb, True, False, d["kps_mean"], d["mean_shape"], w)[0]
+        assert np.abs((fp - fm) / (2 * h) - J[:, c]).max() <= 2e-6 * max(1.0, np.abs(J[:, c]).max()), c
