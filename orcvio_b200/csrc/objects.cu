@@ -31,6 +31,47 @@ struct DevBuf {
   cudaError_t alloc(size_t bytes) { return cudaMalloc(&p, bytes ? bytes : 8); }
 };
 
+// Scratch of the calling thread for the per-object entries: ONE grow-only device block and ONE pinned host block,
+// carved by bump pointers.  The entries are called once per object and frame; a cudaMalloc / cudaFree pair per buffer
+// (about ten per call, each a device-wide synchronisation) and a blocking copy per argument were most of their time.
+// A call stages its inputs in the pinned block, uploads them with one copy, runs, and brings its outputs back with one.
+struct Scratch {
+  char *dev = nullptr, *pin = nullptr;
+  size_t dcap = 0, pcap = 0, dused = 0, pused = 0;
+  int device = -1;
+  ~Scratch() {}                                       // (thread exit: the context outlives us; nothing to do safely)
+  bool begin(size_t dbytes, size_t pbytes) {
+    int cur = 0;
+    if (cudaGetDevice(&cur) != cudaSuccess) return false;
+    if (cur != device) { dev = nullptr; pin = nullptr; dcap = pcap = 0; device = cur; }   // (another context's block)
+    dbytes += 4096; pbytes += 4096;
+    if (dbytes > dcap) {
+      if (dev) cudaFree(dev);
+      dcap = dbytes * 2;
+      if (cudaMalloc(&dev, dcap) != cudaSuccess) { dev = nullptr; dcap = 0; return false; }
+    }
+    if (pbytes > pcap) {
+      if (pin) cudaFreeHost(pin);
+      pcap = pbytes * 2;
+      if (cudaMallocHost(&pin, pcap) != cudaSuccess) { pin = nullptr; pcap = 0; return false; }
+    }
+    dused = pused = 0;
+    return true;
+  }
+  template <class T> T* d(size_t n) {
+    T* r = (T*)(dev + dused);
+    dused += (n * sizeof(T) + 255) & ~(size_t)255;
+    return r;
+  }
+  template <class T> T* h(size_t n) {
+    T* r = (T*)(pin + pused);
+    pused += (n * sizeof(T) + 255) & ~(size_t)255;
+    return r;
+  }
+};
+thread_local Scratch g_scr;
+inline size_t al(size_t bytes) { return (bytes + 255) & ~(size_t)255; }
+
 // Sophus::SE3d::exp([upsilon, omega]) (call site src/orcvio.cpp:2083): R (row-major 3x3), t
 void se3_exp_host(const double* xi, double* R, double* t) {
   const double* ups = xi;
@@ -99,29 +140,38 @@ int object_residuals(const double* frames_wTc, int T, const double* wTo, const d
     rows_kp += 2 * k;
   }
   const int rows = rows_kp + 4 * T, odim = 9 + 3 * K;
-  DevBuf dT, dW, dS, dK, dZs, dZb, dOff, dF, dJc, dJo, dXi;
-  CKO(dT.alloc(sizeof(double) * 16 * T)); CKO(dW.alloc(sizeof(double) * 16)); CKO(dS.alloc(sizeof(double) * 3));
-  CKO(dK.alloc(sizeof(double) * 3 * K)); CKO(dZs.alloc(sizeof(double) * 2 * K * T)); CKO(dZb.alloc(sizeof(double) * 4 * T));
-  CKO(dOff.alloc(sizeof(int) * T)); CKO(dF.alloc(sizeof(double) * rows)); CKO(dJc.alloc(sizeof(double) * rows * 6));
-  CKO(dJo.alloc(sizeof(double) * rows * odim)); CKO(dXi.alloc(sizeof(double) * 6 * T));
-  CKO(cudaMemcpy(dT.p, frames_wTc, sizeof(double) * 16 * T, cudaMemcpyHostToDevice));
-  CKO(cudaMemcpy(dW.p, wTo, sizeof(double) * 16, cudaMemcpyHostToDevice));
-  CKO(cudaMemcpy(dS.p, shape, sizeof(double) * 3, cudaMemcpyHostToDevice));
-  CKO(cudaMemcpy(dK.p, kps, sizeof(double) * 3 * K, cudaMemcpyHostToDevice));
-  CKO(cudaMemcpy(dZs.p, zs, sizeof(double) * 2 * K * T, cudaMemcpyHostToDevice));
-  CKO(cudaMemcpy(dZb.p, zb, sizeof(double) * 4 * T, cudaMemcpyHostToDevice));
-  CKO(cudaMemcpy(dOff.p, off.data(), sizeof(int) * T, cudaMemcpyHostToDevice));
-  CKO(cudaMemset(dJc.p, 0, sizeof(double) * rows * 6));
-  CKO(cudaMemset(dJo.p, 0, sizeof(double) * rows * odim));
-  launch_object_rows(dT.as<double>(), T, dW.as<double>(), dS.as<double>(), dK.as<double>(), K, dZs.as<double>(),
-                     dZb.as<double>(), flags, dOff.as<int>(), rows_kp, rows, dF.as<double>(), dJc.as<double>(),
-                     dJo.as<double>(), dXi.as<double>(), 0);
-  CKO(cudaDeviceSynchronize());
+  // inputs: [frames | wTo | shape | kps | zs | zb | off] in one upload; outputs [fvec | Jc | Jo | xi] in one download
+  const size_t n_in = (size_t)16 * T + 16 + 3 + 3 * K + (size_t)2 * K * T + 4 * T;
+  const size_t n_out = (size_t)rows * (1 + 6 + odim) + 6 * T;
+  const size_t in_bytes = al(n_in * sizeof(double)) + al(sizeof(int) * T), out_bytes = al(n_out * sizeof(double));
+  if (!g_scr.begin(in_bytes + out_bytes, in_bytes + out_bytes)) return ORCVIO_ERR_CUDA;
+  double* hin = g_scr.h<double>(n_in);
+  int* hoff = g_scr.h<int>(T);
+  double* hout = g_scr.h<double>(n_out);
+  double* din = g_scr.d<double>(n_in);
+  int* doff = g_scr.d<int>(T);
+  double* dout = g_scr.d<double>(n_out);
+  double* q = hin;
+  std::memcpy(q, frames_wTc, sizeof(double) * 16 * T); q += 16 * T;
+  std::memcpy(q, wTo, sizeof(double) * 16); q += 16;
+  std::memcpy(q, shape, sizeof(double) * 3); q += 3;
+  std::memcpy(q, kps, sizeof(double) * 3 * K); q += 3 * K;
+  std::memcpy(q, zs, sizeof(double) * 2 * K * T); q += (size_t)2 * K * T;
+  std::memcpy(q, zb, sizeof(double) * 4 * T);
+  std::memcpy(hoff, off.data(), sizeof(int) * T);
+  // (hin and hoff are adjacent in both blocks: one copy)
+  CKO(cudaMemcpyAsync(din, hin, in_bytes, cudaMemcpyHostToDevice, 0));
+  const double *dT = din, *dW = dT + 16 * T, *dS = dW + 16, *dK = dS + 3, *dZs = dK + 3 * K, *dZb = dZs + (size_t)2 * K * T;
+  double *dF = dout, *dJc = dF + rows, *dJo = dJc + (size_t)rows * 6, *dXi = dJo + (size_t)rows * odim;
+  CKO(cudaMemsetAsync(dJc, 0, sizeof(double) * rows * (6 + odim), 0));
+  launch_object_rows(dT, T, dW, dS, dK, K, dZs, dZb, flags, doff, rows_kp, rows, dF, dJc, dJo, dXi, 0);
+  CKO(cudaMemcpyAsync(hout, dout, n_out * sizeof(double), cudaMemcpyDeviceToHost, 0));
+  CKO(cudaStreamSynchronize(0));
   if (launch_error_count() > 0) return ORCVIO_ERR_CUDA;
-  if (fvec) CKO(cudaMemcpy(fvec, dF.p, sizeof(double) * rows, cudaMemcpyDeviceToHost));
-  if (fjac_cam) CKO(cudaMemcpy(fjac_cam, dJc.p, sizeof(double) * rows * 6, cudaMemcpyDeviceToHost));
-  if (fjac_obj) CKO(cudaMemcpy(fjac_obj, dJo.p, sizeof(double) * rows * odim, cudaMemcpyDeviceToHost));
-  if (cam_pose_se3) CKO(cudaMemcpy(cam_pose_se3, dXi.p, sizeof(double) * 6 * T, cudaMemcpyDeviceToHost));
+  if (fvec) std::memcpy(fvec, hout, sizeof(double) * rows);
+  if (fjac_cam) std::memcpy(fjac_cam, hout + rows, sizeof(double) * rows * 6);
+  if (fjac_obj) std::memcpy(fjac_obj, hout + (size_t)rows * 7, sizeof(double) * rows * odim);
+  if (cam_pose_se3) std::memcpy(cam_pose_se3, hout + (size_t)rows * (7 + odim), sizeof(double) * 6 * T);
   if (zs_num) std::memcpy(zs_num, num.data(), sizeof(int) * T);
   if (rows_out) *rows_out = rows;
   return ORCVIO_OK;
@@ -179,27 +229,34 @@ int Batch::construct_object_jacobians(int fi, const double* jac_sensor, int rows
   }
   if (rows_out) *rows_out = row;
   if (kept == 0) return 0;
-  DevBuf dJs, dHf, dRes, dMap, dJac, dHx, dHfo, dReso;
-  CKO(dJs.alloc(sizeof(double) * rows * 6)); CKO(dHf.alloc(sizeof(double) * rows * odim));
-  CKO(dRes.alloc(sizeof(double) * rows)); CKO(dMap.alloc(sizeof(int) * map5.size()));
-  CKO(dJac.alloc(sizeof(double) * jac.size())); CKO(dHx.alloc(sizeof(double) * rows * D));
-  CKO(dHfo.alloc(sizeof(double) * rows * odim)); CKO(dReso.alloc(sizeof(double) * rows));
-  CKO(cudaMemcpy(dJs.p, jac_sensor, sizeof(double) * rows * 6, cudaMemcpyHostToDevice));
-  CKO(cudaMemcpy(dHf.p, Hf, sizeof(double) * rows * odim, cudaMemcpyHostToDevice));
-  CKO(cudaMemcpy(dRes.p, res, sizeof(double) * rows, cudaMemcpyHostToDevice));
-  CKO(cudaMemcpy(dMap.p, map5.data(), sizeof(int) * map5.size(), cudaMemcpyHostToDevice));
-  CKO(cudaMemcpy(dJac.p, jac.data(), sizeof(double) * jac.size(), cudaMemcpyHostToDevice));
-  CKO(cudaMemset(dHx.p, 0, sizeof(double) * rows * D));
-  CKO(cudaMemset(dHfo.p, 0, sizeof(double) * rows * odim));
-  CKO(cudaMemset(dReso.p, 0, sizeof(double) * rows));
-  launch_object_construct(dJs.as<double>(), dHf.as<double>(), dRes.as<double>(), rows, odim, dMap.as<int>(),
-                          dJac.as<double>(), kept, leg, D, rows, dHx.as<double>(), dHfo.as<double>(),
-                          dReso.as<double>(), stream_);
+  // inputs [jac_sensor | Hf | res | dcam/dimu | map5] in one upload, outputs [Hx | Hf | res] in one download
+  const size_t n_in = (size_t)rows * (6 + odim + 1) + jac.size();
+  const size_t n_out = (size_t)rows * (D + odim + 1);
+  const size_t in_bytes = al(n_in * sizeof(double)) + al(sizeof(int) * map5.size()), out_bytes = al(n_out * sizeof(double));
+  if (!g_scr.begin(in_bytes + out_bytes, in_bytes + out_bytes)) return ORCVIO_ERR_CUDA;
+  double* hin = g_scr.h<double>(n_in);
+  int* hmap = g_scr.h<int>(map5.size());
+  double* hout = g_scr.h<double>(n_out);
+  double* din = g_scr.d<double>(n_in);
+  int* dmap = g_scr.d<int>(map5.size());
+  double* dout = g_scr.d<double>(n_out);
+  double* q = hin;
+  std::memcpy(q, jac_sensor, sizeof(double) * rows * 6); q += (size_t)rows * 6;
+  std::memcpy(q, Hf, sizeof(double) * rows * odim); q += (size_t)rows * odim;
+  std::memcpy(q, res, sizeof(double) * rows); q += rows;
+  std::memcpy(q, jac.data(), sizeof(double) * jac.size());
+  std::memcpy(hmap, map5.data(), sizeof(int) * map5.size());
+  CKO(cudaMemcpyAsync(din, hin, in_bytes, cudaMemcpyHostToDevice, stream_));
+  CKO(cudaMemsetAsync(dout, 0, n_out * sizeof(double), stream_));
+  const double *dJs = din, *dHf = dJs + (size_t)rows * 6, *dRes = dHf + (size_t)rows * odim, *dJac = dRes + rows;
+  double *dHx = dout, *dHfo = dHx + (size_t)rows * D, *dReso = dHfo + (size_t)rows * odim;
+  launch_object_construct(dJs, dHf, dRes, rows, odim, dmap, dJac, kept, leg, D, rows, dHx, dHfo, dReso, stream_);
+  CKO(cudaMemcpyAsync(hout, dout, n_out * sizeof(double), cudaMemcpyDeviceToHost, stream_));
   CKO(cudaStreamSynchronize(stream_));
   ++launches_;
-  if (Hx_out) CKO(cudaMemcpy(Hx_out, dHx.p, sizeof(double) * rows * D, cudaMemcpyDeviceToHost));
-  if (Hf_out) CKO(cudaMemcpy(Hf_out, dHfo.p, sizeof(double) * rows * odim, cudaMemcpyDeviceToHost));
-  if (res_out) CKO(cudaMemcpy(res_out, dReso.p, sizeof(double) * rows, cudaMemcpyDeviceToHost));
+  if (Hx_out) std::memcpy(Hx_out, hout, sizeof(double) * rows * D);
+  if (Hf_out) std::memcpy(Hf_out, hout + (size_t)rows * D, sizeof(double) * rows * odim);
+  if (res_out) std::memcpy(res_out, hout + (size_t)rows * (D + odim), sizeof(double) * rows);
   return 1;
 }
 
@@ -216,17 +273,20 @@ int Batch::object_update(int fi, const double* Hx, const double* Hf, const doubl
   const int N = (int)F.clones.size(), n = 6 * N, D = ORCVIO_LEG + n;
   if (N < 1) return done(1, 0);
   const int ld = odim + n + 1;
-  std::vector<double> M((size_t)rows * ld);
+  const size_t nM = (size_t)rows * ld;
+  const size_t up_bytes = al(nM * sizeof(double)) + al(sizeof(FilterWork));
+  if (!g_scr.begin(up_bytes, up_bytes + al((n + 1) * sizeof(double)))) return ORCVIO_ERR_CUDA;
+  double* M = g_scr.h<double>(nM);
+  FilterWork* hFw = g_scr.h<FilterWork>(1);
+  double* hy = g_scr.h<double>(n + 1);
+  double* dM = g_scr.d<double>(nM);
+  FilterWork* dFw = g_scr.d<FilterWork>(1);
   for (int i = 0; i < rows; ++i) {
-    double* r = M.data() + (size_t)i * ld;
+    double* r = M + (size_t)i * ld;
     for (int c = 0; c < odim; ++c) r[c] = Hf[(size_t)c * rows + i];
     for (int k = 0; k < n; ++k) r[odim + k] = Hx[(size_t)(ORCVIO_LEG + k) * rows + i];
     r[ld - 1] = res[i];
   }
-  DevBuf dM, dFw;
-  CKO(dM.alloc(M.size() * sizeof(double)));
-  CKO(cudaMemcpyAsync(dM.p, M.data(), M.size() * sizeof(double), cudaMemcpyHostToDevice, stream_));
-  launch_project_dense(dM.as<double>(), rows, ld, odim, ld, stream_);            // nullspace_project_inplace_svd
   const int prow = rows - odim;
   FilterWork fw{};                                       // jrow0 = 0: a dense block has no staircase
   fw.N = N; fw.D = D; fw.active = 1; fw.arow0 = 0; fw.arows = prow;
@@ -243,11 +303,12 @@ int Batch::object_update(int fi, const double* Hx, const double* Hf, const doubl
     part_cap_ = need_p * 2;
     CKO(cudaMalloc(&dPart_, part_cap_ * sizeof(double)));
   }
-  CKO(dFw.alloc(sizeof(FilterWork)));
-  CKO(cudaMemcpyAsync(dFw.p, &fw, sizeof(fw), cudaMemcpyHostToDevice, stream_));
+  *hFw = fw;
+  CKO(cudaMemcpyAsync(dM, M, up_bytes, cudaMemcpyHostToDevice, stream_));        // M and the work record: one copy
+  launch_project_dense(dM, rows, ld, odim, ld, stream_);                          // nullspace_project_inplace_svd
   const size_t r_stride = (size_t)(nmax_ + 1) * ldr_;
   UpdArgs ua{};
-  ua.fw = dFw.as<FilterWork>(); ua.n_filters = 1;
+  ua.fw = dFw; ua.n_filters = 1;
   ua.P = dP_ + (size_t)fi * ldp_ * ldp_; ua.p_stride = (size_t)ldp_ * ldp_; ua.ldp = ldp_;
   ua.Rm = dR_ + (size_t)fi * r_stride; ua.rthin = dRthin_ + (size_t)fi * ldr_; ua.r_stride = r_stride; ua.ldr = ldr_;
   ua.T = dT_ + (size_t)fi * nmax_ * ldt_; ua.S = dS_ + (size_t)fi * r_stride;
@@ -261,17 +322,16 @@ int Batch::object_update(int fi, const double* Hx, const double* Hf, const doubl
   ib.Ls = dLs_ + (size_t)fi * ORCVIO_LEG * ORCVIO_LEG; ib.Amat = dAmat_; ib.part = dPart_;
   ib.max_units = units; ib.cta_budget = n_sm_ * syrk_waves_; ib.group = syrk_group_; ib.syrk_cnt = dSyrkCnt_;
   ib.tile_rows = nullptr; ib.filter_rows = dFilterRows_ + fi;
-  const double* Hp = dM.as<double>() + (size_t)odim * ld + odim;
+  const double* Hp = dM + (size_t)odim * ld + odim;
   launch_info_dense_factor(ua, ib, Hp, ld, prow, n, stream_);
   launches_ += 5;
-  std::vector<double> y(n);
-  double corner = 0.0;
-  CKO(cudaMemcpyAsync(y.data(), ua.yv, n * sizeof(double), cudaMemcpyDeviceToHost, stream_));
-  CKO(cudaMemcpyAsync(&corner, ua.S + (size_t)n * ldr_ + n, sizeof(double), cudaMemcpyDeviceToHost, stream_));
+  CKO(cudaMemcpyAsync(hy, ua.yv, n * sizeof(double), cudaMemcpyDeviceToHost, stream_));
+  CKO(cudaMemcpyAsync(hy + n, ua.S + (size_t)n * ldr_ + n, sizeof(double), cudaMemcpyDeviceToHost, stream_));
   CKO(cudaStreamSynchronize(stream_));
   if (launch_error_count() > 0) return ORCVIO_ERR_CUDA;
+  const double corner = hy[n];
   double yy = 0.0;
-  for (int k = 0; k < n; ++k) yy += y[k] * y[k];
+  for (int k = 0; k < n; ++k) yy += hy[k] * hy[k];
   const double gamma = (corner - yy) / p_.feature_observation_noise;              // Woodbury, see info_kernel.cu
   if (gamma_out) *gamma_out = gamma;
   // gatingTestFeature with dof = rows (:2172-2175); dof >= 500 computes the quantile on the fly (:1962-1968)

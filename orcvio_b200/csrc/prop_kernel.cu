@@ -416,8 +416,11 @@ void launch_augment(const AugArgs& a, cudaStream_t s) {
   check_launch("k_augment");
 }
 
-// Delete the rows/columns of up to two clones from P and compact the clone array.
-__global__ void __launch_bounds__(256) k_remove(RemoveArgs a) {
+// Delete the rows/columns of up to two clones from P and compact the clone array.  In place, RM_ROWS rows at a time
+// through shared memory: a row moves up and its entries move left, so a chunk only overwrites rows that were already
+// staged (two barriers per chunk instead of two per row: 116 -> ~20 us at D = 202).
+constexpr int RM_ROWS = 24, RM_THREADS = 512;
+__global__ void __launch_bounds__(RM_THREADS) k_remove(RemoveArgs a) {
   extern __shared__ double rowbuf[];
   const int fi = blockIdx.x;
   const int r0 = a.rm[2 * fi], r1 = a.rm[2 * fi + 1];
@@ -441,13 +444,17 @@ __global__ void __launch_bounds__(256) k_remove(RemoveArgs a) {
     if (r1 >= 0 && c > r1) shift += 6;
     return idx - shift;
   };
-  for (int i = 0; i < D; ++i) {
-    if (removed(i)) continue;                 // uniform across the CTA
-    const int ni = newidx(i);
-    for (int j = tid; j < D; j += nt) rowbuf[j] = P[(size_t)i * ldp + j];
+  for (int i0 = 0; i0 < D; i0 += RM_ROWS) {
+    const int nr = min(RM_ROWS, D - i0);
+    for (int e = tid; e < nr * D; e += nt) {
+      const int r = e / D, j = e - r * D;
+      rowbuf[r * ldp + j] = P[(size_t)(i0 + r) * ldp + j];
+    }
     __syncthreads();
-    for (int j = tid; j < D; j += nt)
-      if (!removed(j)) P[(size_t)ni * ldp + newidx(j)] = rowbuf[j];
+    for (int e = tid; e < nr * D; e += nt) {
+      const int r = e / D, j = e - r * D;
+      if (!removed(i0 + r) && !removed(j)) P[(size_t)newidx(i0 + r) * ldp + newidx(j)] = rowbuf[r * ldp + j];
+    }
     __syncthreads();
   }
   // clone array (24 doubles per clone), ascending order so in-place is safe row by row
@@ -463,8 +470,8 @@ __global__ void __launch_bounds__(256) k_remove(RemoveArgs a) {
 }
 
 void launch_remove(const RemoveArgs& a, cudaStream_t s) {
-  size_t smem = (size_t)a.ldp * sizeof(double);
-  k_remove<<<a.n_filters, 256, smem, s>>>(a);
+  size_t smem = (size_t)RM_ROWS * a.ldp * sizeof(double);
+  k_remove<<<a.n_filters, RM_THREADS, smem, s>>>(a);
   check_launch("k_remove");
 }
 
