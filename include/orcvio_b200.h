@@ -383,7 +383,8 @@ int orcvio_propagate(double* state16, const double* bg, const double* ba, const 
                      const double* noise4);
 
 /* Host-side probe of the split-K plan of the compression GEMM (no device needed): out[0] rows per chunk, out[1] column
- * tiles, out[2] tile pairs, out[3] work units, out[4 .. 4 + pairs] first unit of every pair followed by the total. */
+ * tiles, out[2] tile pairs, out[3] work units, out[4 .. 4 + pairs] first unit of every pair followed by the total,
+ * out[15] rows per chunk of a diagonal pair (16 ints). */
 int orcvio_syrk_plan_probe(int arows, const int* jrow0, int n_clones, int cta_budget, int* out);
 
 /* device / build info */

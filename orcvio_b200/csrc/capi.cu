@@ -392,7 +392,7 @@ static std::unique_ptr<Batch> make_snapshot_batch(int n_clones, int flags, doubl
 }
 
 int orcvio_syrk_plan_probe(int arows, const int* jrow0, int n_clones, int cta_budget, int* out) {
-  // host-side view of the split-K plan of k_syrk (kernels.h syrk_plan): out[0] = rows per chunk, out[1] = column
+  // host-side view of the split-K plan of k_syrk (kernels.h syrk_plan): out[0] = rows per chunk (out[15]: of a diagonal pair), out[1] = column
   // tiles, out[2] = tile pairs, out[3] = work units, out[4 ..] = first unit of every pair (+ the total)
   if (!jrow0 || !out || arows < 0 || n_clones < 1 || cta_budget < 1) return ORCVIO_ERR_ARG;
   FilterWork fw{};
@@ -401,6 +401,7 @@ int orcvio_syrk_plan_probe(int arows, const int* jrow0, int n_clones, int cta_bu
   const SyrkPlan p = syrk_plan(fw, cta_budget);
   out[0] = p.kc; out[1] = p.nt; out[2] = p.npairs; out[3] = p.total;
   for (int q = 0; q <= p.npairs; ++q) out[4 + q] = p.first[q];
+  out[15] = p.kcd;                                       // rows per chunk of a diagonal pair
   return ORCVIO_OK;
 }
 

@@ -361,6 +361,16 @@ __device__ __forceinline__ void sy_stamp(int unit, int k) {
   }
 }
 
+// Diagonal pair (I, I): of the 8 x 8 grid of 8 x 8 fragments only those with fragment row <= fragment column hold an
+// element that is ever emitted -- 36 of 64.  They are dealt to the warps so that the two warps of a scheduler (w and
+// w + 4) carry 9 of them (fragment rows 0 + 7, 1 + 6, 2 + 5, 3 + 4): the tensor pipe is per scheduler, so a diagonal
+// unit does 9/16 of the DMMA work of an off-diagonal one per slab and gets 7/4 as many rows (syrk_plan).
+// Entry = fragment row << 4 | fragment column; 0xff = none.
+__constant__ unsigned char SY_DIAG_FRAG[8][5] = {
+    {0x00, 0x01, 0x02, 0x03, 0x04}, {0x11, 0x12, 0x13, 0x14, 0x15}, {0x22, 0x23, 0x24, 0x25, 0x26},
+    {0x33, 0x34, 0x35, 0x36, 0x37}, {0x05, 0x06, 0x07, 0x77, 0xff}, {0x16, 0x17, 0x66, 0x67, 0xff},
+    {0x27, 0x55, 0x56, 0x57, 0xff}, {0x44, 0x45, 0x46, 0x47, 0xff}};
+
 template <int SY_STAGES>
 __global__ void __launch_bounds__(SY_THREADS) k_syrk(UpdArgs a, const double* __restrict__ Amat, int lda, double* part,
                                                      int max_units, int cta_budget, int group, const Tile* tiles,
@@ -403,15 +413,17 @@ __global__ void __launch_bounds__(SY_THREADS) k_syrk(UpdArgs a, const double* __
   }
   const int chunk = unit - pl.first[pidx];
   const int nchunks = pl.first[pidx + 1] - pl.first[pidx];
-  const int kc = pl.kc;
+  const bool diag = (I == J);
+  const int kc = diag ? pl.kcd : pl.kc;
   const int row_begin = min(fw.arows, fw.jrow0[J] + chunk * kc);
   const int row_end = min(fw.arows, row_begin + kc);
   const double* A = Amat + (size_t)fw.arow0 * lda;
   __shared__ int s_last;
-  const bool diag = (I == J);
   const int warp = tid >> 5, lane = tid & 31;
   const int i0 = I * SY_T, j0 = J * SY_T;
-  const int nslab = (row_end - row_begin + SY_KS - 1) / SY_KS;
+  // a diagonal pair needs one matrix, so its stage holds 64 rows of it (the A half and the B half) per barrier
+  const int slab_rows = diag ? 2 * SY_KS : SY_KS;
+  const int nslab = (row_end - row_begin + slab_rows - 1) / slab_rows;
   double2 acc[4][2];
 #pragma unroll
   for (int u = 0; u < 4; ++u)
@@ -419,6 +431,13 @@ __global__ void __launch_bounds__(SY_THREADS) k_syrk(UpdArgs a, const double* __
     for (int v = 0; v < 2; ++v) acc[u][v] = make_double2(0.0, 0.0);
   const int fr = lane >> 2, fk = lane & 3;               // fragment row (or column) / k index
   const int wi = (warp & 1) * 32, wj = (warp >> 1) * 16;
+  int du[5], dv[5];                                      // diagonal pair: this warp's fragments (acc[t >> 1][t & 1])
+#pragma unroll
+  for (int t = 0; t < 5; ++t) {
+    const int f = SY_DIAG_FRAG[warp][t];
+    du[t] = (f == 0xff) ? -1 : 8 * (f >> 4);
+    dv[t] = (f == 0xff) ? 0 : 8 * (f & 15);
+  }
   // loader: 32 rows x 64 columns per matrix = 1024 x 16 bytes, four per thread and matrix (rows lr, lr+8, lr+16, lr+24);
   // rows past the end of A and columns past lda are zero-filled by the copy itself (src-size 0)
   const int lr = tid >> 5, lc = (tid & 31) * 2;
@@ -427,7 +446,7 @@ __global__ void __launch_bounds__(SY_THREADS) k_syrk(UpdArgs a, const double* __
     if (it < nslab) {
       const int st = it % SY_STAGES;
       double* sa = sy_sm + (size_t)st * SY_STAGE_DOUBLES;
-      const int r0 = row_begin + it * SY_KS;
+      const int r0 = row_begin + it * slab_rows;
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
         const int rl = lr + 8 * q, r = r0 + rl;
@@ -440,6 +459,12 @@ __global__ void __launch_bounds__(SY_THREADS) k_syrk(UpdArgs a, const double* __
           const int nb = (rok && cj_ok) ? 16 : 0;
           asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(da + (unsigned int)(SY_KS * SY_LD * sizeof(double))),
                        "l"(src + (cj_ok ? j0 + lc : 0)), "r"(nb) : "memory");
+        } else {                                         // rows 32 .. 63 of the slab, same columns
+          const bool rok2 = r + SY_KS < row_end;
+          const double* src2 = A + (size_t)(rok2 ? r + SY_KS : row_begin) * lda;
+          const int nb = (rok2 && ci_ok) ? 16 : 0;
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(da + (unsigned int)(SY_KS * SY_LD * sizeof(double))),
+                       "l"(src2 + (ci_ok ? i0 + lc : 0)), "r"(nb) : "memory");
         }
       }
     }
@@ -454,7 +479,22 @@ __global__ void __launch_bounds__(SY_THREADS) k_syrk(UpdArgs a, const double* __
     issue(it + SY_STAGES - 1);
     const int st = it % SY_STAGES;
     const double(*As)[SY_LD] = reinterpret_cast<const double(*)[SY_LD]>(sy_sm + (size_t)st * SY_STAGE_DOUBLES);
-    const double(*Bp)[SY_LD] = diag ? As : As + SY_KS;
+    if (diag) {
+#pragma unroll 8
+      for (int k4 = 0; k4 < 2 * SY_KS; k4 += 4) {
+        double af[5], bf[5];
+#pragma unroll
+        for (int t = 0; t < 5; ++t) {
+          af[t] = As[k4 + fk][max(du[t], 0) + fr];
+          bf[t] = As[k4 + fk][dv[t] + fr];
+        }
+#pragma unroll
+        for (int t = 0; t < 5; ++t)
+          if (du[t] >= 0) dmma884(acc[t >> 1][t & 1].x, acc[t >> 1][t & 1].y, af[t], bf[t]);
+      }
+      continue;
+    }
+    const double(*Bp)[SY_LD] = As + SY_KS;
 #pragma unroll
     for (int k4 = 0; k4 < SY_KS; k4 += 4) {
       double af[4], bf[2];
@@ -480,6 +520,15 @@ __global__ void __launch_bounds__(SY_THREADS) k_syrk(UpdArgs a, const double* __
   };
   (void)n1;
   if (nchunks == 1) {
+    if (diag) {
+#pragma unroll
+      for (int t = 0; t < 5; ++t)
+        if (du[t] >= 0) {
+          emit(du[t] + fr, dv[t] + 2 * fk, acc[t >> 1][t & 1].x);
+          emit(du[t] + fr, dv[t] + 2 * fk + 1, acc[t >> 1][t & 1].y);
+        }
+      return;
+    }
 #pragma unroll
     for (int u = 0; u < 4; ++u)
 #pragma unroll
@@ -492,11 +541,17 @@ __global__ void __launch_bounds__(SY_THREADS) k_syrk(UpdArgs a, const double* __
   double* base = part + ((size_t)fi * max_units + pl.first[pidx]) * (SY_T * SY_T);
   const size_t cstride = (size_t)(SY_T * SY_T);
   double* out = base + (size_t)chunk * cstride;
+  if (diag) {                                            // (the fragments below the diagonal are never stored nor read)
 #pragma unroll
-  for (int u = 0; u < 4; ++u)
+    for (int t = 0; t < 5; ++t)
+      if (du[t] >= 0) *reinterpret_cast<double2*>(out + (du[t] + fr) * SY_T + dv[t] + 2 * fk) = acc[t >> 1][t & 1];
+  } else {
 #pragma unroll
-    for (int v = 0; v < 2; ++v)
-      *reinterpret_cast<double2*>(out + (wi + 8 * u + fr) * SY_T + wj + 8 * v + 2 * fk) = acc[u][v];
+    for (int u = 0; u < 4; ++u)
+#pragma unroll
+      for (int v = 0; v < 2; ++v)
+        *reinterpret_cast<double2*>(out + (wi + 8 * u + fr) * SY_T + wj + 8 * v + 2 * fk) = acc[u][v];
+  }
   if (spin_reduce) {
     // Every chunk of this pair is resident (the host only sets spin_reduce when the whole grid fits the GPU at once):
     // wait until all of them have stored their partial, then reduce ONE SLICE of the tile over all chunks -- in chunk
@@ -525,6 +580,7 @@ __global__ void __launch_bounds__(SY_THREADS) k_syrk(UpdArgs a, const double* __
     if ((nchunks + gsz - 1) / gsz > SY_MAXG) gsz = (nchunks + SY_MAXG - 1) / SY_MAXG;
     const int ngroups = (nchunks + gsz - 1) / gsz;
     for (int e = e0 + tid; e < e1; e += 256) {
+      if (diag && ((e >> 6) >> 3) > ((e & 63) >> 3)) continue;   // a fragment below the diagonal: nothing was stored
       const double* p0 = base + e;
       double total = 0.0;
       for (int g0 = 0; g0 < nchunks; g0 += gsz) {
@@ -561,6 +617,14 @@ __global__ void __launch_bounds__(SY_THREADS) k_syrk(UpdArgs a, const double* __
   if (!s_last) return;
   __threadfence();
   double s[16];
+  unsigned int need = 0xffffu;                            // diagonal pair: elements of fragments that were stored
+  if (diag) {
+    need = 0u;
+#pragma unroll
+    for (int q = 0; q < 16; ++q)
+      if ((((tid >> 6) + 4 * q) >> 3) <= ((tid & 63) >> 3)) need |= 1u << q;
+  }
+  auto ldp = [&](const double* p, int q) { return ((need >> q) & 1u) ? __ldcg(p) : 0.0; };
   auto sum_slots = [&](int first, int last, int step) {   // slots first, first + step, ... < last, in order
 #pragma unroll
     for (int q = 0; q < 16; ++q) s[q] = 0.0;
@@ -570,20 +634,20 @@ __global__ void __launch_bounds__(SY_THREADS) k_syrk(UpdArgs a, const double* __
       const size_t ss = (size_t)step * cstride;
       double x0[16], x1[16], x2[16], x3[16];
 #pragma unroll
-      for (int q = 0; q < 16; ++q) x0[q] = __ldcg(p0 + 256 * q);
+      for (int q = 0; q < 16; ++q) x0[q] = ldp(p0 + 256 * q, q);
 #pragma unroll
-      for (int q = 0; q < 16; ++q) x1[q] = __ldcg(p0 + ss + 256 * q);
+      for (int q = 0; q < 16; ++q) x1[q] = ldp(p0 + ss + 256 * q, q);
 #pragma unroll
-      for (int q = 0; q < 16; ++q) x2[q] = __ldcg(p0 + 2 * ss + 256 * q);
+      for (int q = 0; q < 16; ++q) x2[q] = ldp(p0 + 2 * ss + 256 * q, q);
 #pragma unroll
-      for (int q = 0; q < 16; ++q) x3[q] = __ldcg(p0 + 3 * ss + 256 * q);
+      for (int q = 0; q < 16; ++q) x3[q] = ldp(p0 + 3 * ss + 256 * q, q);
 #pragma unroll
       for (int q = 0; q < 16; ++q) s[q] = (((s[q] + x0[q]) + x1[q]) + x2[q]) + x3[q];
     }
     for (; c < last; c += step) {
       const double* p0 = base + (size_t)c * cstride + tid;
 #pragma unroll
-      for (int q = 0; q < 16; ++q) s[q] += __ldcg(p0 + 256 * q);
+      for (int q = 0; q < 16; ++q) s[q] += ldp(p0 + 256 * q, q);
     }
   };
   sum_slots(c_begin, c_end, 1);
@@ -592,7 +656,8 @@ __global__ void __launch_bounds__(SY_THREADS) k_syrk(UpdArgs a, const double* __
     // ---- level 2: the group sum replaces the group's first partial; the last group sums the groups
     double* gout = base + (size_t)c_begin * cstride + tid;
 #pragma unroll
-    for (int q = 0; q < 16; ++q) __stcg(gout + 256 * q, s[q]);
+    for (int q = 0; q < 16; ++q)
+      if ((need >> q) & 1u) __stcg(gout + 256 * q, s[q]);
     __threadfence();
     __syncthreads();
     if (tid == 0) {

@@ -367,29 +367,34 @@ constexpr int AFORM_TILE_ROWS = 64;     // row cap of a tile of the whitened-for
 // gives bit-identical results whether it runs alone or inside a batch.
 constexpr int SY_TILE = 64, SY_MAXT = 4, SY_MAXP = 10, SY_MAXG = 32;
 struct SyrkPlan {
-  int kc, nt, npairs, total;
+  int kc, kcd, nt, npairs, total;   // rows per chunk of an off-diagonal / a diagonal pair
   int first[SY_MAXP + 1];        // first work unit of every pair (pair order: I outer, J >= I inner)
 };
+// A diagonal pair (I, I) only computes the 36 of its 64 8 x 8 fragments that are ever emitted (k_syrk), so its chunks
+// are longer for the same time: 13/8 as measured (a 64-row slab of a diagonal unit costs 1.13 x its share of DMMAs).
+__host__ __device__ inline int syrk_kcd(int kc) { return (kc * 13 / 8 + 31) / 32 * 32; }
 __host__ __device__ inline SyrkPlan syrk_plan(const FilterWork& fw, int cta_budget) {
   SyrkPlan p;
   p.nt = (fw.D - ORCVIO_LEG + 1 + SY_TILE - 1) / SY_TILE;
   if (p.nt > SY_MAXT) p.nt = SY_MAXT;
   p.npairs = p.nt * (p.nt + 1) / 2;
   int rowsJ[SY_MAXT];
-  long long tot = 0;
+  long long tot16 = 0;
   for (int J = 0; J < p.nt; ++J) {
     rowsJ[J] = fw.arows - fw.jrow0[J];
     if (rowsJ[J] < 0) rowsJ[J] = 0;
-    tot += (long long)rowsJ[J] * (J + 1);
+    tot16 += (long long)rowsJ[J] * (16 * J + 10);      // J off-diagonal pairs + 8/13 of a diagonal one
   }
-  int kc = (int)((tot + cta_budget - 1) / cta_budget);
+  int kc = (int)((tot16 + 16LL * cta_budget - 1) / (16LL * cta_budget));
   kc = (kc + 31) / 32 * 32;
   if (kc < 128) kc = 128;
   for (;;) {
+    const int kcd = syrk_kcd(kc);
     int total = 0, q = 0;
     for (int I = 0; I < p.nt; ++I)
       for (int J = I; J < p.nt; ++J) {
-        int c = (rowsJ[J] + kc - 1) / kc;
+        const int k = (I == J) ? kcd : kc;
+        int c = (rowsJ[J] + k - 1) / k;
         if (c < 1) c = 1;
         p.first[q++] = total;
         total += c;
@@ -400,6 +405,7 @@ __host__ __device__ inline SyrkPlan syrk_plan(const FilterWork& fw, int cta_budg
     kc += 32;
   }
   p.kc = kc;
+  p.kcd = syrk_kcd(kc);
   return p;
 }
 inline int qr_tile_rows_cap(int w_cols) {                // rows that fit beside (w_cols+1) columns

@@ -24,3 +24,5 @@ for k in range(8):
     ok = col > 0
     if ok.any():
         print(f"{names[k]:15s} n={ok.sum():4d}  min {np.min(col[ok]-t0)/1e3:7.2f}  median {np.median(col[ok]-t0)/1e3:7.2f}  max {np.max(col[ok]-t0)/1e3:7.2f} us")
+dur = (t[:, 2] - t[:, 1]) / 1e3
+print("mainloop us per unit:", " ".join(f"{x:.1f}" for x in dur))

@@ -110,8 +110,9 @@ def test_product_reader_on_the_reference_yaml_files():
 
 def test_syrk_plan_covers_every_row_once_and_fits_the_budget():
     """Host logic of the staircase split-K plan (csrc/kernels.h syrk_plan), no device involved: every tile pair
-    (I <= J) covers exactly the rows [jrow0[J], arows) in whole chunks of kc rows, kc is a multiple of 32 and >= 128,
-    and the work units fit the CTA budget whenever the pairs themselves do."""
+    (I <= J) covers exactly the rows [jrow0[J], arows) in whole chunks of kc rows (kcd = 13/8 kc for a diagonal pair, which
+    computes 36 of its 64 fragments), both multiples of 32 and >= 128, and the work units fit the CTA budget whenever the
+    pairs themselves do."""
     import ctypes as C
     import numpy as np
     from orcvio_b200 import api
@@ -129,7 +130,8 @@ def test_syrk_plan_covers_every_row_once_and_fits_the_budget():
         assert L.orcvio_syrk_plan_probe(arows, j.ctypes.data, N, budget, out.ctypes.data) == 0
         kc, nt, npairs, total = out[:4]
         assert nt == min((6 * N + 1 + 63) // 64, 4) and npairs == nt * (nt + 1) // 2
-        assert kc % 32 == 0 and kc >= 128
+        kcd = int(out[15])
+        assert kc % 32 == 0 and kc >= 128 and kcd % 32 == 0 and kc < kcd <= 2 * kc
         first = out[4:4 + npairs + 1]
         assert first[0] == 0 and first[-1] == total and np.all(np.diff(first) >= 1)
         q = 0
@@ -137,7 +139,8 @@ def test_syrk_plan_covers_every_row_once_and_fits_the_budget():
             for J in range(I, nt):
                 rows = max(arows - int(j[J]), 0)
                 chunks = first[q + 1] - first[q]
-                assert chunks == max(-(-rows // kc), 1)            # whole chunks, at least one (empty pairs emit zeros)
+                k = kcd if I == J else int(kc)
+                assert chunks == max(-(-rows // k), 1)             # whole chunks, at least one (empty pairs emit zeros)
                 q += 1
         assert total <= budget or total == npairs or kc == 128 or True
         if npairs <= budget:
