@@ -364,7 +364,7 @@ __device__ __forceinline__ void sy_stamp(int unit, int k) {
 // Diagonal pair (I, I): of the 8 x 8 grid of 8 x 8 fragments only those with fragment row <= fragment column hold an
 // element that is ever emitted -- 36 of 64.  They are dealt to the warps so that the two warps of a scheduler (w and
 // w + 4) carry 9 of them (fragment rows 0 + 7, 1 + 6, 2 + 5, 3 + 4): the tensor pipe is per scheduler, so a diagonal
-// unit does 9/16 of the DMMA work of an off-diagonal one per slab and gets 7/4 as many rows (syrk_plan).
+// unit does 9/16 of the DMMA work of an off-diagonal one per slab and gets 13/8 as many rows (syrk_plan).
 // Entry = fragment row << 4 | fragment column; 0xff = none.
 __constant__ unsigned char SY_DIAG_FRAG[8][5] = {
     {0x00, 0x01, 0x02, 0x03, 0x04}, {0x11, 0x12, 0x13, 0x14, 0x15}, {0x22, 0x23, 0x24, 0x25, 0x26},
@@ -471,6 +471,11 @@ __global__ void __launch_bounds__(SY_THREADS) k_syrk(UpdArgs a, const double* __
     asm volatile("cp.async.commit_group;" ::: "memory");
   };
   sy_stamp(unit, 1);
+  if (g_syrk_dbg && tid == 0 && spin_reduce) {             // (slots 5 .. 7 are free in the spin path)
+    g_syrk_dbg[(size_t)unit * SY_DBG_N + 5] = row_end - row_begin;
+    g_syrk_dbg[(size_t)unit * SY_DBG_N + 6] = I * 16 + J;
+    g_syrk_dbg[(size_t)unit * SY_DBG_N + 7] = fw.jrow0[J];
+  }
 #pragma unroll
   for (int it = 0; it < SY_STAGES - 1; ++it) issue(it);
   for (int it = 0; it < nslab; ++it) {

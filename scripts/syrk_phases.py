@@ -19,10 +19,13 @@ t = t[t[:, 0] > 0]
 t0 = t[:, 0].min()
 names = ["start", "prologue", "mainloop", "partial+atomic", "level1", "grp atomic", "level2", "emit"]
 print("units", len(t))
-for k in range(8):
+for k in range(5):
     col = t[:, k]
     ok = col > 0
     if ok.any():
         print(f"{names[k]:15s} n={ok.sum():4d}  min {np.min(col[ok]-t0)/1e3:7.2f}  median {np.median(col[ok]-t0)/1e3:7.2f}  max {np.max(col[ok]-t0)/1e3:7.2f} us")
 dur = (t[:, 2] - t[:, 1]) / 1e3
 print("mainloop us per unit:", " ".join(f"{x:.1f}" for x in dur))
+print("rows per unit:", " ".join(str(int(x)) for x in t[:, 5]))
+print("pair (I*16+J) per unit:", " ".join(str(int(x)) for x in t[:, 6]))
+print("jrow0[J] per unit:", " ".join(str(int(x)) for x in t[:, 7]))
