@@ -320,7 +320,28 @@ def _object_leg(api, configs_mod, synth):
         t_rows += t1 - t0
         t_con += t2 - t1
         t_upd += t3 - t2
+    # the object state optimiser in front of stage 3 (ObjectFeatureInitializer): the reference's one_car sequence (47
+    # frames x 12 keypoints) as a batch of 64 objects advanced in lock-step
+    lm = {}
+    try:
+        xywh = g["zb"][:, 0, :]
+        zb47 = np.column_stack([xywh[:, 0], xywh[:, 1], xywh[:, 0] + xywh[:, 2], xywh[:, 1] + xywh[:, 3]])
+        init = api.ObjectFeatureInitializer(g["ellipsoid_shape"][-1].ravel(), g["mean_shape"][-1], [1.0, 3e-2, 1.0, 1.0])
+        nobj = 64
+        fl, zl, bl = [g["wTo"]] * nobj, [g["zs"]] * nobj, [zb47] * nobj
+        init.single_object_initialization(fl, zl)
+        t0 = time.perf_counter()
+        ok, T0, _, _ = init.single_object_initialization(fl, zl)
+        t1 = time.perf_counter()
+        res = init.single_levenberg_marquardt(fl, zl, bl, T0, True, False)
+        t2 = time.perf_counter()
+        lm = dict(objects=nobj, frames_per_object=int(len(g["wTo"])), init_us_per_object=(t1 - t0) / nobj * 1e6,
+                  lm_us_per_object=(t2 - t1) / nobj * 1e6, lm_rounds=int(res["rounds"]), lm_nfev=int(res["nfev"][0]),
+                  lm_status=int(res["status"][0]), all_success=bool(np.all(res["success"])))
+    except Exception as e:
+        lm = dict(error=str(e))
     return dict(msckf_process_features_us_median=float(np.median(t_feat[10:])) * 1e6, object_rows_us=t_rows / reps * 1e6,
+                object_optimiser=lm,
                 construct_jacobians_us=t_con / reps * 1e6, remove_lost_objects_us=t_upd / reps * 1e6,
                 object_rows=int(Hx.shape[0]), keypoints=int(len(kps)), views=int(len(frames)), clones=int(N),
                 last_status=int(status), state_dim=int(P0.shape[0]),
@@ -333,12 +354,23 @@ def extra_legs(api, torch, args, l2_flush):
     out = {}
     steps = max(10, min(args.steps, 50))
     try:
-        # case 4b: every feature seen by all 30 clones (m = N = 30): M = 4096 x 57 = 233 k gated rows; the flop bound of
-        # the compression alone is M (n+1)(n+2) / DMMA peak ~ 0.2 ms, the whitening A = H' L as much again
+        # case 4b: every feature seen by all 30 clones (m = N = 30): M = 4096 x 57 = 233 k candidate rows.  The frame is
+        # flop-bound by the GATE, not by the compression: gamma = r^T (H P H^T + s^2 I)^-1 r needs the 57 x 180 block of
+        # every feature against the 180 x 180 window of P (2 r w^2 + 2 r^2 w = 4.9 Mflop per feature, 20 Gflop per frame,
+        # plain DFMA), then the whitening A = H' L (2 M w n / 2, L lower triangular) and W = A^T A (M (n+1)(n+2)) on the
+        # FP64 tensor cores
         snap = synth.stress_snapshot(N_CLONES, N_FEATURES, MAX_TRACK, seed=0, full_tracks=True)
         r = _time_frame(api, torch, snap, N_CLONES, max(5, steps // 5), 3, l2_flush)
-        flops = r["gated_rows"] * (6 * N_CLONES + 1) * (6 * N_CLONES + 2)
-        r["syrk_flop_bound_us"] = flops / (api.fp64_peak()[1] * 1e12) * 1e6
+        dfma, dmma = api.fp64_peak()
+        m, w, n = N_CLONES, 6 * N_CLONES, 6 * N_CLONES
+        rr = 2 * m - 3
+        gate = r["features"] * (2.0 * rr * w * w + 2.0 * rr * rr * w)
+        aform = r["gated_rows"] * 2.0 * w * n / 2
+        syrk = r["gated_rows"] * (n + 1.0) * (n + 2.0)
+        r["flop_bound_us"] = dict(gate_dfma=gate / (dfma * 1e12) * 1e6, aform_dmma=aform / (dmma * 1e12) * 1e6,
+                                  syrk_dmma=syrk / (dmma * 1e12) * 1e6)
+        r["flop_bound_us"]["total"] = sum(r["flop_bound_us"].values())
+        r["frac_of_flop_bound"] = r["flop_bound_us"]["total"] / r["us_per_frame"]
         out["case_4b_full_tracks"] = r
     except Exception as e:
         out["case_4b_full_tracks"] = dict(error=str(e))

@@ -962,9 +962,40 @@ int Batch::replay(int n_frames, const double* t_img, const OrcvioFeature* const*
   return ORCVIO_OK;
 }
 
+// ORCVIO_HOST_PROF=2: wall clock of the sections of processFeatures' host side, summed over calls and printed every
+// 2000 filter-frames (diagnostic of the multi-trajectory replay, which is bound by this bookkeeping)
+struct SecProf {
+  static constexpr int K = 12;
+  double acc[K] = {0};
+  long long calls = 0, filters = 0;
+  std::chrono::steady_clock::time_point t;
+  const bool on = env_int("ORCVIO_HOST_PROF", 0) == 2;
+  void start() { if (on) t = std::chrono::steady_clock::now(); }
+  void mark(int k) {
+    if (!on) return;
+    const auto now = std::chrono::steady_clock::now();
+    acc[k] += std::chrono::duration<double, std::micro>(now - t).count();
+    t = now;
+  }
+  void done(int B) {
+    if (!on) return;
+    ++calls;
+    filters += B;
+    if (filters < 2000) return;
+    static const char* nm[K] = {"capacity", "imu+addObs", "prop_launch", "prop_wait", "lost_scan", "spec_tri", "lost_build",
+                                "phaseA_launch", "phaseA_wait", "prune_build", "phaseB_launch", "phaseB_wait+post"};
+    std::fprintf(stderr, "[host prof] us per filter-frame:");
+    for (int i = 0; i < K; ++i) { std::fprintf(stderr, " %s %.2f", nm[i], acc[i] / filters); acc[i] = 0; }
+    std::fprintf(stderr, "  (%lld calls)\n", calls);
+    calls = filters = 0;
+  }
+};
+static thread_local SecProf g_sp;
+
 int Batch::process_ptrs(const double* t_img, const OrcvioFeature* const* featp, const int* nfeat,
                         const OrcvioImu* const* imup, const int* nimu_v, int* imu_used, int* published) {
   if (!ok_) return ORCVIO_ERR_CUDA;
+  g_sp.start();
   cudaSetDevice(dev_);                // the current device is per host thread (replays run on worker threads)
   const int L = ORCVIO_LEG;
   // Capacity is checked before anything is touched: a frame either runs on every filter or leaves all of them as
@@ -974,14 +1005,16 @@ int Batch::process_ptrs(const double* t_img, const OrcvioFeature* const* featp, 
       const FilterHost& F = f_[fi];
       const OrcvioFeature* ft = featp[fi];
       const int nf = nfeat[fi];
+      if ((size_t)nf <= F.free_slots.size()) continue;     // even if every feature is new there is room
       size_t fresh = 0;
-      for (int k = 0; k < nf; ++k) fresh += F.map_server.count((long long)ft[k].id) ? 0 : 1;
+      for (int k = 0; k < nf; ++k) fresh += F.find_track((long long)ft[k].id) ? 0 : 1;
       if (fresh > F.free_slots.size()) {
         std::fprintf(stderr, "[orcvio_b200] feature table full (capacity %d live tracks per filter, filter %d needs %zu more)\n",
                      Fcap_, fi, fresh - F.free_slots.size());
         return ORCVIO_ERR_CAPACITY;
       }
     }
+  g_sp.mark(0);
   // ---------------------------------------------------------------- A: propagation inputs
   std::vector<PropSample> samples;
   std::vector<int> samp_off(B_ + 1, 0), Dvec(B_, 0), Nvec(B_, 0), Evec(B_, 0);
@@ -1066,8 +1099,8 @@ int Batch::process_ptrs(const double* t_img, const OrcvioFeature* const* featp, 
       for (int k = 0; k < nf; ++k) {
         const OrcvioFeature& m = ft[k];
         const long long id = (long long)m.id;
-        auto it = F.map_server.find(id);
-        if (it == F.map_server.end()) {
+        Track* found = F.find_track(id);
+        if (!found) {
           if (F.free_slots.empty()) {      // (cannot happen after the pre-pass; if it does the batch is unusable)
             std::fprintf(stderr, "[orcvio_b200] feature table full (capacity %d)\n", Fcap_);
             ok_ = false;
@@ -1099,23 +1132,25 @@ int Batch::process_ptrs(const double* t_img, const OrcvioFeature* const* featp, 
           o.z[1] = m.v + m.v_vel * dt;
           o.vel[0] = m.u_vel; o.vel[1] = m.v_vel;
           tr.obs.push_back(o);
-          F.map_server.emplace(id, std::move(tr));
+          F.add_track(std::move(tr));
         } else {
           Obs o{};
           o.sid = sid;
           o.z[0] = m.u + m.u_vel * dt;
           o.z[1] = m.v + m.v_vel * dt;
           o.vel[0] = m.u_vel; o.vel[1] = m.v_vel;
-          Track& tr = it->second;
+          Track& tr = *found;
           if (!tr.obs.empty() && tr.obs.back().sid == sid) tr.obs.back() = o;
           else tr.obs.push_back(o);
           ++tracked;
           if (p_.if_ZUPT_valid && p_.if_use_feature_zupt_flag) {     // :1052-1058
-            for (const Obs& po : tr.obs)
-              if (po.sid == sid - 1) {
-                const double du = m.u - po.z[0], dv = m.v - po.z[1];
-                F.coarse_feature_dis.push_back(std::sqrt(du * du + dv * dv));
-              }
+            // (the observations are in ascending state-id order and end with this frame's: the previous frame's, if
+            // there is one, is the one before it)
+            if (tr.obs.size() >= 2 && tr.obs[tr.obs.size() - 2].sid == sid - 1) {
+              const Obs& po = tr.obs[tr.obs.size() - 2];
+              const double du = m.u - po.z[0], dv = m.v - po.z[1];
+              F.coarse_feature_dis.push_back(std::sqrt(du * du + dv * dv));
+            }
           }
         }
       }
@@ -1126,6 +1161,7 @@ int Batch::process_ptrs(const double* t_img, const OrcvioFeature* const* featp, 
     F.clones.push_back(CloneMeta{F.state_id, F.imu_time, F.dt});
   }
   (void)need_imu_upload;
+  g_sp.mark(1);
 
   // ---------------------------------------------------------------- B: propagate + augment
   {
@@ -1159,7 +1195,8 @@ int Batch::process_ptrs(const double* t_img, const OrcvioFeature* const* featp, 
         if (p_.if_use_feature_zupt_flag) {
           std::vector<double>& d = F.coarse_feature_dis;
           if (d.size() >= 20) {
-            std::sort(d.begin(), d.end());
+            // (the reference sorts and reads element size - 9: the same order statistic without the full sort)
+            std::nth_element(d.begin(), d.end() - 9, d.end());
             if (d[d.size() - 9] < p_.zupt_max_feature_dis) zmode[fi] = 1;
           }
           d.clear();
@@ -1221,7 +1258,9 @@ int Batch::process_ptrs(const double* t_img, const OrcvioFeature* const* featp, 
       CK(cudaEventRecord(ev_[7], stream_));
     }
     // the blob is reused by the next phase: wait for the upload + kernels reading it
+    g_sp.mark(2);
     wait_stream();
+    g_sp.mark(3);
     if (profiling_) {
       float ms = 0;
       cudaEventElapsedTime(&ms, ev_[6], ev_[7]);
@@ -1242,7 +1281,7 @@ int Batch::process_ptrs(const double* t_img, const OrcvioFeature* const* featp, 
           // checkZUPTFeat :3104-3115 / checkZUPTIMU :3304-3315: a stationary frame drops every EKF-SLAM feature; the
           // update itself only touched the leading 22 + 6N block, the feature rows / columns are simply abandoned
           for (long long id : F.feature_states) {
-            Track& tr = F.map_server.at(id);
+            Track& tr = *F.find_track(id);
             tr.in_state = tr.ekf_feature = tr.initialized = false;
             tr.gen = F.next_gen++;                       // the device slot no longer counts as initialised
           }
@@ -1318,7 +1357,7 @@ int Batch::process_ptrs(const double* t_img, const OrcvioFeature* const* featp, 
       std::vector<long long> kept;
       std::vector<int> map_e(E0, -1);
       for (int i = 0; i < E0; ++i) {
-        Track& tr = F.map_server.at(F.feature_states[i]);
+        Track& tr = *F.find_track(F.feature_states[i]);
         if (!tr.obs.empty() && tr.obs.back().sid == F.state_id) {
           map_e[i] = (int)kept.size();
           kept.push_back(tr.id);
@@ -1326,7 +1365,7 @@ int Batch::process_ptrs(const double* t_img, const OrcvioFeature* const* featp, 
           const long long lost_id = tr.id;
           F.log_ekf_lost.push_back(lost_id);
           F.free_slots.push_back(tr.slot);
-          F.map_server.erase(lost_id);
+          F.erase_track(lost_id);
         }
       }
       if ((int)kept.size() != E0) {
@@ -1364,7 +1403,7 @@ int Batch::process_ptrs(const double* t_img, const OrcvioFeature* const* featp, 
     std::vector<long long> invalid;
     bool ekf_open = false;
     if (hybrid_) {
-      for (long long id : F.feature_states) cells[fi][grid_code(F.map_server.at(id))]++;   // updateGridMap :3831-3850
+      for (long long id : F.feature_states) cells[fi][grid_code(*F.find_track(id))]++;   // updateGridMap :3831-3850
       ekf_open = (F.imu_time - F.last_zupt_time > 5) && (int)F.feature_states.size() < Emax_;
     }
     for (auto& kv : F.map_server) {
@@ -1399,11 +1438,11 @@ int Batch::process_ptrs(const double* t_img, const OrcvioFeature* const* featp, 
       cb.push_back(make_cand(wA, F, tr, tracked_now, tracked_now ? 1 : 0, 0));
     }
     for (long long id : invalid) {
-      auto it = F.map_server.find(id);
-      F.free_slots.push_back(it->second.slot);
-      F.map_server.erase(it);
+      F.free_slots.push_back(F.find_track(id)->slot);
+      F.erase_track(id);
     }
   }
+  g_sp.mark(4);
   std::vector<CommitRec> commits;
   if (hybrid_ && !wS.cands.empty()) {
     const size_t nS = wS.cands.size();
@@ -1431,6 +1470,7 @@ int Batch::process_ptrs(const double* t_img, const OrcvioFeature* const* featp, 
       wait_stream();
     }
   }
+  g_sp.mark(5);
   for (int fi = 0; fi < B_; ++fi) {
     FilterHost& F = f_[fi];
     wA.cand_begin[fi] = (int)wA.cands.size();
@@ -1479,7 +1519,7 @@ int Batch::process_ptrs(const double* t_img, const OrcvioFeature* const* featp, 
       hw.N = fw.N; hw.E = E; hw.active = 1;
       hw.feat_begin = (int)wA.hfeats.size();
       for (long long id : F.feature_states) {
-        const Track& tr = F.map_server.at(id);
+        const Track& tr = *F.find_track(id);
         HybFeat hf{};
         hf.slot = tr.slot;
         hf.anchor = clone_index_of(F, tr.id_anchor);
@@ -1540,6 +1580,7 @@ int Batch::process_ptrs(const double* t_img, const OrcvioFeature* const* featp, 
   }
   if (!hyb_ok) { ok_ = false; err_ = "hybrid bookkeeping failed (upload arena / anchor outside the window)"; return ORCVIO_ERR_CUDA; }
   cudaEvent_t* e = ev_;
+  g_sp.mark(6);
   run_phase(wA, 0);
   std::vector<Track*> gather_tracks;
   if (hybrid_) {
@@ -1557,7 +1598,9 @@ int Batch::process_ptrs(const double* t_img, const OrcvioFeature* const* featp, 
     }
   }
   download_mirrors();
+  g_sp.mark(7);
   wait_stream();
+  g_sp.mark(8);
   if (hybrid_) {
     hybrid_apply_gather(gather_tracks);
     hb->used = 0;
@@ -1595,9 +1638,9 @@ int Batch::process_ptrs(const double* t_img, const OrcvioFeature* const* featp, 
       return false;
     };
     for (long long id : ids) {
-      auto it = F.map_server.find(id);
-      if (it == F.map_server.end()) continue;
-      Track& tr = it->second;
+      Track* trp = F.find_track(id);
+      if (!trp) continue;
+      Track& tr = *trp;
       if (!tr.ekf_feature || !tr.initialized || !removed(tr.id_anchor)) continue;
       bool anchor_observed = false;
       for (const Obs& o : tr.obs) anchor_observed |= (o.sid == tr.id_anchor);
@@ -1684,7 +1727,7 @@ int Batch::process_ptrs(const double* t_img, const OrcvioFeature* const* featp, 
         F.log_new_ok.push_back(pass ? 1 : 0);
         F.log_new_gamma.push_back(hGamma_[c]);
         if (pass) {
-          F.map_server.at(ci.id).in_state = true;
+          F.find_track(ci.id)->in_state = true;
           F.feature_states.push_back(ci.id);
           ++feature_updates_;
         }
@@ -1695,10 +1738,9 @@ int Batch::process_ptrs(const double* t_img, const OrcvioFeature* const* featp, 
       // lost features are always erased (:2572-2576); tracked-long ones only when they were
       // initialised and therefore used (:2310-2319)
       if (ci.kind == 0 || (st & ST_TRI_VALID)) {
-        auto it = F.map_server.find(ci.id);
-        if (it != F.map_server.end()) {
-          F.free_slots.push_back(it->second.slot);
-          F.map_server.erase(it);
+        if (Track* gone = F.find_track(ci.id)) {
+          F.free_slots.push_back(gone->slot);
+          F.erase_track(ci.id);
         }
       }
     }
@@ -1720,7 +1762,7 @@ int Batch::process_ptrs(const double* t_img, const OrcvioFeature* const* featp, 
       hw.N = fw.N; hw.E = Ebefore[fi]; hw.active = fw.active;
       hw.feat_begin = (int)wB.hfeats.size();
       for (long long id : F.feature_states) {
-        const Track& tr = F.map_server.at(id);
+        const Track& tr = *F.find_track(id);
         HybFeat hf{};
         hf.slot = tr.slot;
         hf.anchor = clone_index_of(F, tr.id_anchor);
@@ -1847,6 +1889,7 @@ int Batch::process_ptrs(const double* t_img, const OrcvioFeature* const* featp, 
   wB.extra_ints.insert(wB.extra_ints.end(), Nbefore.begin(), Nbefore.end());
   wB.extra_ints.insert(wB.extra_ints.end(), Ebefore.begin(), Ebefore.end());
   if (!hyb_ok) { ok_ = false; err_ = "hybrid bookkeeping failed (anchor outside the window)"; return ORCVIO_ERR_CUDA; }
+  g_sp.mark(9);
   stage_phase(wB);
   if (hybrid_ && !reanchor.empty()) {
     const ReanchorRec* d_rec = hb->put(reanchor.data(), reanchor.size(), stream_, &hyb_ok);
@@ -1872,6 +1915,7 @@ int Batch::process_ptrs(const double* t_img, const OrcvioFeature* const* featp, 
   }
   if (hybrid_) hybrid_queue_gather(gather_tracks);
   download_mirrors();
+  g_sp.mark(10);
   wait_stream();
   if (hybrid_) {
     hybrid_apply_gather(gather_tracks);
@@ -1911,6 +1955,8 @@ int Batch::process_ptrs(const double* t_img, const OrcvioFeature* const* featp, 
     std::memcpy(F.clone_mirror.data(), hClones_ + (size_t)fi * Ncap_ * CL_STRIDE,
                 (size_t)Ncap_ * CL_STRIDE * sizeof(double));
   }
+  g_sp.mark(11);
+  g_sp.done(B_);
   return ok_ ? ORCVIO_OK : ORCVIO_ERR_CUDA;
 }
 

@@ -6,6 +6,7 @@
 
 #include <cstring>
 #include <map>
+#include <unordered_map>
 #include <memory>
 #include <string>
 #include <vector>
@@ -46,7 +47,22 @@ struct CandInfo {     // host-side twin of a device candidate
 };
 
 struct FilterHost {
-  std::map<long long, Track> map_server;
+  std::map<long long, Track> map_server;              // ordered by id: the reference walks its std::map in this order
+  std::unordered_map<long long, Track*> track_index;  // id -> node of map_server (node addresses are stable): the lookups
+  Track* find_track(long long id) const {
+    auto it = track_index.find(id);
+    return it == track_index.end() ? nullptr : it->second;
+  }
+  Track& add_track(Track&& tr) {
+    const long long id = tr.id;
+    Track& t = map_server.emplace(id, std::move(tr)).first->second;
+    track_index[id] = &t;
+    return t;
+  }
+  void erase_track(long long id) {
+    track_index.erase(id);
+    map_server.erase(id);
+  }
   std::vector<CloneMeta> clones;
   std::vector<int> free_slots;
   long long next_state_id = 0;
