@@ -367,3 +367,34 @@ def test_object_lm_matches_oracle(left, new_residual):
     # the reference's own assertion on its sequence (test_object_lm_multiframe.cpp:115-123)
     dR, dt = obj.displacement(d["wTq"], out["wTo"][0])
     assert abs(dR) < 0.5 and dt < 0.05 * np.linalg.norm(d["wTq"][:3, 3])
+
+
+@pytest.mark.parametrize("K", [4, 8])
+def test_object_optimiser_with_smaller_keypoint_classes(K):
+    """The reference's classes have 12, 4 and 8 keypoints (config/object_feat_*.yaml): the first K keypoints of the
+    car shape as a class of its own -- initialisation, normal equations and the optimum against the oracle."""
+    d, scenes = _lm_scenes(4)
+    kps_mean = d["kps_mean"][:K]
+    scenes = [(fr, zs[:, :K], zb) for (fr, zs, zb) in scenes]
+    w = [1.0, 3e-2, 1.0, 1.0]
+    init = api.ObjectFeatureInitializer(d["mean_shape"], kps_mean, w)
+    ok, T0, kw, kv = init.single_object_initialization([s[0] for s in scenes], [s[1] for s in scenes])
+    for i, (fr, zs, _) in enumerate(scenes):
+        ok_o, T_o, ids, pts = obj.single_object_initialization(fr, zs, kps_mean)
+        assert bool(ok[i]) == ok_o and list(np.nonzero(kv[i])[0]) == ids
+        np.testing.assert_allclose(T0[i], T_o, rtol=0, atol=1e-8)
+    sel = [i for i in range(len(scenes)) if ok[i]]
+    assert len(sel) >= 2
+    fl, zl, bl = [scenes[i][0] for i in sel], [scenes[i][1] for i in sel], [scenes[i][2] for i in sel]
+    out = init.single_levenberg_marquardt(fl, zl, bl, T0[sel], True, False)
+    n = 9 + 3 * K
+    fn, g, A = init.lm_eval(fl, zl, bl, [(out["wTo"][j], out["shape"][j], out["kps"][j]) for j in range(len(sel))])
+    for j, i in enumerate(sel):
+        fr, zs, zb = scenes[i]
+        res = obj.single_levenberg_marquardt(fr, zs, zb, T0[i], kps_mean, d["mean_shape"], w, True, False)
+        assert (out["status"][j], out["nfev"][j], out["njev"][j]) == (res["status"], res["nfev"], res["njev"]), i
+        np.testing.assert_allclose(out["wTo"][j], res["x"][0], rtol=0, atol=1e-7)
+        np.testing.assert_allclose(out["kps"][j], res["x"][2], rtol=0, atol=1e-7)
+        f, J = obj.object_lm_full(fr, out["wTo"][j], out["shape"][j], out["kps"][j], zs, zb, True, False, kps_mean,
+                                  d["mean_shape"], w)
+        assert A[j].shape == (n, n) and np.abs(A[j] - J.T @ J).max() <= 1e-12 * np.abs(J.T @ J).max()
