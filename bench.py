@@ -160,11 +160,19 @@ class ClockSampler:
                     samples=len(sm))
 
 
-def run_cpu_reference(n_threads, n_feat, repeats, seed0=0):
+def run_cpu_reference(n_threads, n_feat, repeats, seed0=0, variant="o3"):
     """Times the CPU restatement of the reference algorithm on `n_threads` independent frames
-    (one per thread).  Returns (features gated in, seconds, kind)."""
+    (one per thread).  Returns (features gated in, seconds, kind).  variant "o3" = the -O3 / AVX2 + FMA build of the
+    restatement (what a vectorised Release build of the reference's Eigen code would get; the default of both CPU legs,
+    the favourable choice for the CPU), "" = the -O2 generic x86-64 build the parity tests use."""
     from oracle import cpu_ref
-    return cpu_ref.time_frames(N_CLONES, n_feat, MAX_TRACK, NOISE_VAR, TRI, n_threads, repeats, seed0)
+    if variant == "o3" and not os.path.exists(cpu_ref._SO_O3):
+        variant = ""
+    return cpu_ref.time_frames(N_CLONES, n_feat, MAX_TRACK, NOISE_VAR, TRI, n_threads, repeats, seed0, variant=variant)
+
+
+CPU_BUILD = ("C++ restatement of the reference algorithm (kind: port), g++ -O3 -march=x86-64-v3 (AVX2 + FMA); the -O2 "
+             "generic x86-64 build used by the parity tests is reported as value_o2_generic")
 
 
 def reference_arm(args, rank, world):
@@ -181,13 +189,15 @@ def reference_arm(args, rank, world):
         feats += f
         secs += s
     value = feats / secs
+    f2, s2, _ = run_cpu_reference(cores, n_feat, 1, seed0=7, variant="")
     sample = (f"{cores} independent frames per step (one per thread), each {N_CLONES} clones x {n_feat} features, "
               f"m in [3,{MAX_TRACK}]; dense per-feature H P H^T gate, Householder QR compression, dense EKF update")
     line = dict(metric=METRIC, value=value, unit=UNIT, impl="reference", n_gpus=args.gpus, steps=args.steps,
                 warmup=args.warmup, ms_per_step=1e3 * secs / args.steps, higher_is_better=True, scaling="weak",
                 vs_baseline=None, dtype="f64", data="synthetic",
                 config=dict(workload=WORKLOAD, sample=sample),
-                cpu_baseline=dict(value=value, unit=UNIT, cores=cores, kind=kind, sample=sample),
+                cpu_baseline=dict(value=value, unit=UNIT, cores=cores, kind=kind, sample=sample, build=CPU_BUILD,
+                                  value_o2_generic=f2 / s2),
                 e2e=dict(value=value, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0))
     print(json.dumps(line), flush=True)
 
@@ -653,8 +663,9 @@ def main():
             try:
                 cores = os.cpu_count() or 1
                 f, s, kind = run_cpu_reference(cores, args.ref_features, args.ref_repeats)
+                f2, s2, _ = run_cpu_reference(cores, args.ref_features, 1, seed0=7, variant="")
                 line["cpu_baseline"] = dict(
-                    value=f / s, unit=UNIT, cores=cores, kind=kind,
+                    value=f / s, unit=UNIT, cores=cores, kind=kind, build=CPU_BUILD, value_o2_generic=f2 / s2,
                     sample=f"{cores * args.ref_repeats} independent frames ({args.ref_repeats} per host thread), each "
                            f"{N_CLONES} clones x {args.ref_features} features, m in [3,{MAX_TRACK}]; "
                            f"{s * cores:.1f} core-seconds of CPU work")

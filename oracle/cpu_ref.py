@@ -15,6 +15,7 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _SO = os.path.join(_HERE, "_build", "libcpu_ref.so")
+_SO_O3 = os.path.join(_HERE, "_build", "libcpu_ref_o3.so")     # -O3 -march=x86-64-v3 build of the same file (timing only)
 
 
 def _numpy_worker(args):
@@ -27,11 +28,12 @@ def _numpy_worker(args):
     return int(((out["status"] & 2) != 0).sum()), time.perf_counter() - t0
 
 
-def load():
-    """The C++ restatement's shared object, or None when it has not been built."""
-    if not os.path.exists(_SO):
+def load(variant=""):
+    """The C++ restatement's shared object (variant "o3": the -O3 / AVX2 build), or None when it has not been built."""
+    so = _SO_O3 if variant == "o3" else _SO
+    if not os.path.exists(so):
         return None
-    L = C.CDLL(_SO)
+    L = C.CDLL(so)
     dp, ip = C.POINTER(C.c_double), C.POINTER(C.c_int)
     L.cpu_ref_frame_update.restype = C.c_int
     L.cpu_ref_frame_update.argtypes = [dp, dp, C.c_int, dp, dp, dp, ip, ip, dp, C.c_int, C.c_int, C.c_double,
@@ -43,9 +45,9 @@ def load():
     return L
 
 
-def frame_update(snap, flags, sigma2, chi2_p=0.95, tri=None):
+def frame_update(snap, flags, sigma2, chi2_p=0.95, tri=None, variant=""):
     """Runs the C++ restatement on one frame; same outputs as oracle_snapshot_update."""
-    L = load()
+    L = load(variant)
     if L is None:
         raise RuntimeError("oracle/_build/libcpu_ref.so not built (make -C oracle)")
     tri = tri or {}
@@ -72,19 +74,23 @@ def frame_update(snap, flags, sigma2, chi2_p=0.95, tri=None):
     return out
 
 
-def _cpp_worker(args):
+def _cpp_worker(args, variant=""):
     n_clones, n_feat, max_len, sigma2, tri, seed = args
     from orcvio_b200 import synth
     snap = synth.stress_snapshot(n_clones, n_feat, max_len, seed=seed)
     t0 = time.perf_counter()
-    out = frame_update(snap, 0, sigma2, tri=dict(translation_threshold=-1.0, **tri))
+    out = frame_update(snap, 0, sigma2, tri=dict(translation_threshold=-1.0, **tri), variant=variant)
     return int(((out["status"] & 2) != 0).sum()), time.perf_counter() - t0
 
 
-def time_frames(n_clones, n_feat, max_len, sigma2, tri, n_threads, repeats=1, seed0=0):
+def _cpp_worker_o3(args):
+    return _cpp_worker(args, "o3")
+
+
+def time_frames(n_clones, n_feat, max_len, sigma2, tri, n_threads, repeats=1, seed0=0, variant=""):
     """(features gated in, wall seconds of the slowest worker chain, kind)."""
-    have_cpp = os.path.exists(_SO)
-    worker = _cpp_worker if have_cpp else _numpy_worker
+    have_cpp = os.path.exists(_SO_O3 if variant == "o3" else _SO)
+    worker = (_cpp_worker_o3 if variant == "o3" else _cpp_worker) if have_cpp else _numpy_worker
     jobs = [(n_clones, n_feat, max_len, sigma2, tri, seed0 + k) for k in range(n_threads * repeats)]
     feats, per_worker = 0, 0.0
     with ProcessPoolExecutor(max_workers=n_threads) as ex:
