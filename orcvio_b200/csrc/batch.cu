@@ -1132,6 +1132,7 @@ int Batch::process_ptrs(const double* t_img, const OrcvioFeature* const* featp, 
           o.z[1] = m.v + m.v_vel * dt;
           o.vel[0] = m.u_vel; o.vel[1] = m.v_vel;
           tr.obs.push_back(o);
+          tr.touch();
           F.add_track(std::move(tr));
         } else {
           Obs o{};
@@ -1142,6 +1143,7 @@ int Batch::process_ptrs(const double* t_img, const OrcvioFeature* const* featp, 
           Track& tr = *found;
           if (!tr.obs.empty() && tr.obs.back().sid == sid) tr.obs.back() = o;
           else tr.obs.push_back(o);
+          tr.touch();
           ++tracked;
           if (p_.if_ZUPT_valid && p_.if_use_feature_zupt_flag) {     // :1052-1058
             // (the observations are in ascending state-id order and end with this frame's: the previous frame's, if
@@ -1410,7 +1412,7 @@ int Batch::process_ptrs(const double* t_img, const OrcvioFeature* const* featp, 
       Track& tr = kv.second;
       if (tr.in_state) continue;
       const int nobs = (int)tr.obs.size();
-      const bool tracked_now = nobs > 0 && tr.obs.back().sid == cur;
+      const bool tracked_now = nobs > 0 && tr.last_sid == cur;
       if (!tracked_now) {
         if (nobs < p_.least_Obs_Num) { invalid.push_back(tr.id); continue; }
       } else {
@@ -1687,6 +1689,7 @@ int Batch::process_ptrs(const double* t_img, const OrcvioFeature* const* featp, 
           auto pos = std::lower_bound(tr.obs.begin(), tr.obs.end(), new_id,
                                       [](const Obs& o, long long sid) { return o.sid < sid; });
           ob = &*tr.obs.insert(pos, z);
+          tr.touch();
         }
         rc.zu = ob->z[0];
         rc.zv = ob->z[1];
@@ -1784,8 +1787,10 @@ int Batch::process_ptrs(const double* t_img, const OrcvioFeature* const* featp, 
       if (hybrid_) reanchor_tracks(fi, F, &rm_id, 1);
       for (auto& kv : F.map_server) {
         Track& tr = kv.second;
+        if (tr.first_sid > rm_id || tr.last_sid < rm_id) continue;     // (ascending ids: it cannot hold the clone)
         tr.obs.erase(std::remove_if(tr.obs.begin(), tr.obs.end(), [&](const Obs& o) { return o.sid == rm_id; }),
                      tr.obs.end());
+        tr.touch();
       }
       fill_hw();
       continue;
@@ -1830,6 +1835,7 @@ int Batch::process_ptrs(const double* t_img, const OrcvioFeature* const* featp, 
     auto clone_index = [&](long long sid) { return clone_index_of(F, sid); };
     for (auto& kv : F.map_server) {
       Track& tr = kv.second;
+      if (tr.first_sid > rm_id1 || tr.last_sid < rm_id0) continue;     // (rm_id0 < rm_id1: neither clone observed it)
       int inv0 = -1, inv1 = -1;
       for (int k = 0; k < (int)tr.obs.size(); ++k) {
         if (tr.obs[k].sid == rm_id0) inv0 = k;
@@ -1874,6 +1880,7 @@ int Batch::process_ptrs(const double* t_img, const OrcvioFeature* const* featp, 
       tr.obs.erase(std::remove_if(tr.obs.begin(), tr.obs.end(),
                                   [&](const Obs& o) { return o.sid == rm_id0 || o.sid == rm_id1; }),
                    tr.obs.end());
+      tr.touch();
     }
     F.stats.n_candidates_prune = (int)cb.size();
     if (!cb.empty()) {

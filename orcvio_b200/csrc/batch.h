@@ -28,6 +28,13 @@ struct Track {        // struct Feature, reference include/orcvio/feat/feature.h
   int slot = -1;
   long long gen = 0;
   std::vector<Obs> obs;     // ascending sid (std::map order in the reference)
+  // first / last observing state id, kept beside the node so that the per-frame walks over every track can skip a
+  // track without touching its observation array (touch() after every change of obs)
+  long long first_sid = 0x7fffffffffffffffLL, last_sid = -1;
+  void touch() {
+    first_sid = obs.empty() ? 0x7fffffffffffffffLL : obs.front().sid;
+    last_sid = obs.empty() ? -1 : obs.back().sid;
+  }
   // hybrid mode (feature.hpp:243-264): the idp record itself lives on the device (slot), these are its host twins
   bool in_state = false, ekf_feature = false;
   bool initialized = false; // host twin of "fgen[slot] == gen" (only maintained in hybrid mode)
