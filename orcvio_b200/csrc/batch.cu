@@ -308,7 +308,9 @@ void Batch::prereserve() {
     amat_cap_ = need_a;
     CK(cudaMalloc(&dAmat_, amat_cap_ * sizeof(double)));
   }
-  const size_t need_p = nB * 12 * 4096;
+  // split-K partial tiles: up to ~18 work units per filter were seen on EuRoC-shaped frames (6 tile pairs x chunks of
+  // >= 128 rows); 32 covers ~2500 stacked rows per filter without a growth in the middle of a replay
+  const size_t need_p = nB * 32 * 4096;
   if (need_p > part_cap_) {
     part_cap_ = need_p;
     CK(cudaMalloc(&dPart_, part_cap_ * sizeof(double)));
@@ -352,6 +354,7 @@ Batch::~Batch() {
   if (blob_.pinned) cudaFreeHost(blob_.pinned);
   cudaFreeHost(hImu_); cudaFreeHost(hClones_); cudaFreeHost(hDx_);
   if (hErrPin_) cudaFreeHost(hErrPin_);
+  if (hDiag_) cudaFreeHost(hDiag_);
   if (hStatus_) cudaFreeHost(hStatus_);
   if (hGamma_) cudaFreeHost(hGamma_);
   for (auto& e : ev_) cudaEventDestroy(e);
@@ -396,14 +399,27 @@ void Batch::init_filter_device(int i) {
   for (int k = 0; k < 9; ++k) im[IM_RBC + k] = p_.R_imu_cam0[k];
   im[IM_TD] = p_.td;
   im[IM_TIME] = F.init_t;
-  std::vector<double> P((size_t)ldp_ * ldp_, 0.0);
-  auto diag = [&](int a, int b, double v) { for (int k = a; k < b; ++k) P[(size_t)k * ldp_ + k] = v; };
-  diag(0, 3, p_.cov_orientation);
-  diag(3, 6, p_.cov_velocity);
-  diag(6, 9, p_.cov_position);
-  diag(9, 12, p_.cov_gyro_bias);
-  diag(12, 15, p_.cov_acc_bias);
-  CK(cudaMemcpy(dP_ + (size_t)i * ldp_ * ldp_, P.data(), P.size() * sizeof(double), cudaMemcpyHostToDevice));
+  // Initial covariance: 15 diagonal entries, the rest zero.  Stream-ordered (a memset + one strided copy of the pinned
+  // diagonal) -- a synchronous cudaMemcpy here runs on the legacy default stream, i.e. it waits for and blocks the
+  // streams of EVERY batch of the process: with 16-32 replay threads initialising 64 filters each that was thousands of
+  // device-wide serialisation points and first frames of up to 1.5 s (ORCVIO_HOST_PROF=3).
+  if (!hDiag_) {
+    CK(cudaMallocHost(&hDiag_, 16 * sizeof(double)));
+    const double v[5] = {p_.cov_orientation, p_.cov_velocity, p_.cov_position, p_.cov_gyro_bias, p_.cov_acc_bias};
+    for (int k = 0; k < 15; ++k) hDiag_[k] = v[k / 3];
+    hDiag_[15] = 0.0;
+  }
+  double* dPi = dP_ + (size_t)i * ldp_ * ldp_;
+  CK(cudaMemsetAsync(dPi, 0, (size_t)ldp_ * ldp_ * sizeof(double), stream_));
+  CK(cudaMemcpy2DAsync(dPi, (size_t)(ldp_ + 1) * sizeof(double), hDiag_, sizeof(double), sizeof(double), 15,
+                       cudaMemcpyHostToDevice, stream_));
+}
+
+// ORCVIO_HOST_PROF=3: every growth of a device / pinned buffer after construction (a device-wide synchronisation that
+// stalls all the batches of the process) is reported
+static void note_growth(const char* what, size_t bytes) {
+  static const bool on = env_int("ORCVIO_HOST_PROF", 0) == 3;
+  if (on) std::fprintf(stderr, "[replay prof] growth: %s -> %.1f MB\n", what, bytes / 1048576.0);
 }
 
 void Batch::ensure_scratch(size_t n_cand, size_t hblk, size_t rblk, size_t tileout) {
@@ -411,6 +427,7 @@ void Batch::ensure_scratch(size_t n_cand, size_t hblk, size_t rblk, size_t tileo
     if (need <= cap) return;
     if (ptr) cudaFree(ptr);
     cap = need * 2 + 1024;
+    note_growth("hblk / rblk / tile out", cap * sizeof(double));
     CK(cudaMalloc(&ptr, cap * sizeof(double)));
   };
   grow(dHblk_, hblk_cap_, hblk);
@@ -420,6 +437,7 @@ void Batch::ensure_scratch(size_t n_cand, size_t hblk, size_t rblk, size_t tileo
     if (dStatus_) cudaFree(dStatus_);
     if (dGamma_) cudaFree(dGamma_);
     cand_cap_ = n_cand * 2 + 1024;
+    note_growth("candidate status", cand_cap_ * 12);
     CK(cudaMalloc(&dStatus_, cand_cap_ * sizeof(int)));
     CK(cudaMalloc(&dGamma_, cand_cap_ * sizeof(double)));
   }
@@ -427,6 +445,7 @@ void Batch::ensure_scratch(size_t n_cand, size_t hblk, size_t rblk, size_t tileo
     if (hStatus_) cudaFreeHost(hStatus_);
     if (hGamma_) cudaFreeHost(hGamma_);
     hcand_cap_ = n_cand * 2 + 1024;
+    note_growth("candidate status (pinned)", hcand_cap_ * 12);
     CK(cudaMallocHost(&hStatus_, hcand_cap_ * sizeof(int)));
     CK(cudaMallocHost(&hGamma_, hcand_cap_ * sizeof(double)));
   }
@@ -437,6 +456,7 @@ void Batch::upload_blob() {
   if (blob_.used > blob_.dev_cap) {
     if (blob_.dev) cudaFree(blob_.dev);
     blob_.dev_cap = blob_.used * 2 + 4096;
+    note_growth("work-list blob", blob_.dev_cap);
     CK(cudaMalloc(&blob_.dev, blob_.dev_cap));
   }
   if (upload_on_side_stream_) {
@@ -515,6 +535,7 @@ void Batch::stage_upload(PhaseWork& w) {
     if (w.tiles.size() > tilerows_cap_) {
       if (dTileRows_) cudaFree(dTileRows_);
       tilerows_cap_ = w.tiles.size() * 2 + 64;
+      note_growth("tile rows", tilerows_cap_ * sizeof(int));
       CK(cudaMalloc(&dTileRows_, tilerows_cap_ * sizeof(int)));
     }
     int units = 1;
@@ -524,12 +545,14 @@ void Batch::stage_upload(PhaseWork& w) {
     if (need_a > amat_cap_) {
       if (dAmat_) cudaFree(dAmat_);
       amat_cap_ = need_a * 2;
+      note_growth("A", amat_cap_ * sizeof(double));
       CK(cudaMalloc(&dAmat_, amat_cap_ * sizeof(double)));
     }
     const size_t need_p = (size_t)B_ * units * 4096;
     if (need_p > part_cap_) {
       if (dPart_) cudaFree(dPart_);
       part_cap_ = need_p * 2;
+      note_growth("split-K partials", part_cap_ * sizeof(double));
       CK(cudaMalloc(&dPart_, part_cap_ * sizeof(double)));
     }
   }
@@ -539,6 +562,7 @@ void Batch::stage_upload(PhaseWork& w) {
     if (need_h > hb.hd_cap) {
       if (hb.dHd) cudaFree(hb.dHd);
       hb.hd_cap = need_h * 2;
+      note_growth("hybrid dense rows", hb.hd_cap * sizeof(double));
       CK(cudaMalloc(&hb.dHd, hb.hd_cap * sizeof(double)));
     }
     bool okp = true;
@@ -923,6 +947,61 @@ void rotation_to_quat_xyzw(const double* R, double* q) {
   for (int i = 0; i < 4; ++i) q[i] /= n;
 }
 
+// ORCVIO_HOST_PROF=2: wall clock of the sections of processFeatures' host side, summed over calls and printed every
+// 2000 filter-frames (diagnostic of the multi-trajectory replay, which is bound by this bookkeeping)
+struct SecProf {
+  static constexpr int K = 12;
+  double acc[K] = {0}, cur[K] = {0}, worst[K] = {0};
+  double worst_sum = 0.0;
+  long long calls = 0, filters = 0;
+  std::chrono::steady_clock::time_point t;
+  const int mode = env_int("ORCVIO_HOST_PROF", 0);
+  const bool on = mode == 2 || mode == 3;
+  static const char* name(int i) {
+    static const char* nm[K] = {"capacity", "imu+addObs", "prop_launch", "prop_wait", "lost_scan", "spec_tri", "lost_build",
+                                "phaseA_launch", "phaseA_wait", "prune_build", "phaseB_launch", "phaseB_wait+post"};
+    return nm[i];
+  }
+  void start() {
+    if (!on) return;
+    t = std::chrono::steady_clock::now();
+    for (double& c : cur) c = 0.0;
+  }
+  void mark(int k) {
+    if (!on) return;
+    const auto now = std::chrono::steady_clock::now();
+    const double us = std::chrono::duration<double, std::micro>(now - t).count();
+    acc[k] += us;
+    cur[k] += us;
+    t = now;
+  }
+  void done(int B) {
+    if (!on) return;
+    double sum = 0.0;
+    for (double c : cur) sum += c;
+    if (sum > worst_sum) {                     // the slowest call of this thread so far: where did it spend its time
+      worst_sum = sum;
+      for (int i = 0; i < K; ++i) worst[i] = cur[i];
+    }
+    ++calls;
+    filters += B;
+    if (mode != 2 || filters < 2000) return;
+    std::fprintf(stderr, "[host prof] us per filter-frame:");
+    for (int i = 0; i < K; ++i) { std::fprintf(stderr, " %s %.2f", name(i), acc[i] / filters); acc[i] = 0; }
+    std::fprintf(stderr, "  (%lld calls)\n", calls);
+    calls = filters = 0;
+  }
+  void report_worst() {
+    if (mode != 3) return;
+    std::fprintf(stderr, "[replay prof] slowest call %.1f ms:", worst_sum / 1e3);
+    for (int i = 0; i < K; ++i)
+      if (worst[i] > 0.02 * worst_sum) std::fprintf(stderr, " %s %.1f ms", name(i), worst[i] / 1e3);
+    std::fprintf(stderr, "\n");
+    worst_sum = 0.0;
+  }
+};
+static thread_local SecProf g_sp;
+
 // Whole-sequence replay (Monte-Carlo / multi-sequence batches): every filter's IMU stream and frames are
 // handed over once; the lock-step loop over the frames runs here, so a replay costs the caller one call (the callers
 // drive several batches from as many host threads).  poses_out: n_filters x n_frames x 7, the IMU pose after every
@@ -935,6 +1014,9 @@ int Batch::replay(int n_frames, const double* t_img, const OrcvioFeature* const*
   std::vector<int> nf(B_), ni(B_), cursor(B_, 0), used(B_), pub(B_);
   std::vector<double> tt(B_);
   for (int i = 0; i < B_; ++i) ok_out[i] = 1;
+  // ORCVIO_HOST_PROF=3: wall clock of every frame of this batch (stalls of a replay thread show up as outliers)
+  static const bool frame_prof = env_int("ORCVIO_HOST_PROF", 0) == 3;
+  std::vector<double> frame_ms;
   for (int f = 0; f < n_frames; ++f) {
     for (int i = 0; i < B_; ++i) {
       const int* fo = feat_off + (size_t)i * (n_frames + 1);
@@ -948,8 +1030,10 @@ int Batch::replay(int n_frames, const double* t_img, const OrcvioFeature* const*
       ip[i] = imu[i] + cursor[i];
       ni[i] = k1 - cursor[i];
     }
+    const auto tf0 = std::chrono::steady_clock::now();
     const int rc = process_ptrs(tt.data(), fp.data(), nf.data(), ip.data(), ni.data(), used.data(), pub.data());
     if (rc != ORCVIO_OK) return rc;
+    if (frame_prof) frame_ms.push_back(std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tf0).count());
     for (int i = 0; i < B_; ++i) {
       cursor[i] += used[i];
       if (!pub[i]) ok_out[i] = 0;
@@ -959,38 +1043,23 @@ int Batch::replay(int n_frames, const double* t_img, const OrcvioFeature* const*
       rotation_to_quat_xyzw(im + IM_R, o + 3);
     }
   }
+  if (frame_prof && !frame_ms.empty()) {
+    std::vector<double> v = frame_ms;
+    std::sort(v.begin(), v.end());
+    double sum = 0.0;
+    for (double x : v) sum += x;
+    int slow = 0;
+    for (double x : v) slow += x > 3.0 * v[v.size() / 2];
+    std::fprintf(stderr, "[replay prof] %d filters x %zu frames: total %.1f ms, per frame min %.2f median %.2f p90 %.2f max %.2f ms, "
+                 "%d frames above 3 x median; first 5:", B_, v.size(), sum, v.front(), v[v.size() / 2], v[v.size() * 9 / 10],
+                 v.back(), slow);
+    for (size_t i = 0; i < std::min<size_t>(5, frame_ms.size()); ++i) std::fprintf(stderr, " %.2f", frame_ms[i]);
+    std::fprintf(stderr, "\n");
+    g_sp.report_worst();
+  }
   return ORCVIO_OK;
 }
 
-// ORCVIO_HOST_PROF=2: wall clock of the sections of processFeatures' host side, summed over calls and printed every
-// 2000 filter-frames (diagnostic of the multi-trajectory replay, which is bound by this bookkeeping)
-struct SecProf {
-  static constexpr int K = 12;
-  double acc[K] = {0};
-  long long calls = 0, filters = 0;
-  std::chrono::steady_clock::time_point t;
-  const bool on = env_int("ORCVIO_HOST_PROF", 0) == 2;
-  void start() { if (on) t = std::chrono::steady_clock::now(); }
-  void mark(int k) {
-    if (!on) return;
-    const auto now = std::chrono::steady_clock::now();
-    acc[k] += std::chrono::duration<double, std::micro>(now - t).count();
-    t = now;
-  }
-  void done(int B) {
-    if (!on) return;
-    ++calls;
-    filters += B;
-    if (filters < 2000) return;
-    static const char* nm[K] = {"capacity", "imu+addObs", "prop_launch", "prop_wait", "lost_scan", "spec_tri", "lost_build",
-                                "phaseA_launch", "phaseA_wait", "prune_build", "phaseB_launch", "phaseB_wait+post"};
-    std::fprintf(stderr, "[host prof] us per filter-frame:");
-    for (int i = 0; i < K; ++i) { std::fprintf(stderr, " %s %.2f", nm[i], acc[i] / filters); acc[i] = 0; }
-    std::fprintf(stderr, "  (%lld calls)\n", calls);
-    calls = filters = 0;
-  }
-};
-static thread_local SecProf g_sp;
 
 int Batch::process_ptrs(const double* t_img, const OrcvioFeature* const* featp, const int* nfeat,
                         const OrcvioImu* const* imup, const int* nimu_v, int* imu_used, int* published) {
@@ -1055,7 +1124,7 @@ int Batch::process_ptrs(const double* t_img, const OrcvioFeature* const* featp, 
         hm[IM_GOLD + k] = im[useful].gyro[k];
         hm[IM_AOLD + k] = im[useful].acc[k];
       }
-      CK(cudaMemcpy(dImu_ + (size_t)fi * IM_STRIDE, hm, IM_STRIDE * sizeof(double), cudaMemcpyHostToDevice));
+      CK(cudaMemcpyAsync(dImu_ + (size_t)fi * IM_STRIDE, hm, IM_STRIDE * sizeof(double), cudaMemcpyHostToDevice, stream_));
       need_imu_upload = true;
       prefix = useful;
       F.gravity_set = true;
@@ -1452,6 +1521,7 @@ int Batch::process_ptrs(const double* t_img, const OrcvioFeature* const* featp, 
       cudaFree(hb->dFinal); cudaFree(hb->dSpecStatus);
       if (hb->hSpecStatus) cudaFreeHost(hb->hSpecStatus);
       hb->spec_cap = nS * 2 + 64;
+      note_growth("speculative triangulation (device + pinned)", hb->spec_cap * 28);
       CK(cudaMalloc(&hb->dFinal, hb->spec_cap * 3 * sizeof(double)));
       CK(cudaMalloc(&hb->dSpecStatus, hb->spec_cap * sizeof(int)));
       CK(cudaMallocHost(&hb->hSpecStatus, hb->spec_cap * sizeof(int)));
@@ -1988,6 +2058,7 @@ void Batch::hybrid_queue_gather(std::vector<Track*>& tracks) {
     cudaFree(hb.dGather);
     cudaFreeHost(hb.hGather);
     hb.gather_cap = n * 2;
+    note_growth("hybrid gather (device + pinned)", hb.gather_cap * 6 * sizeof(double));
     CK(cudaMalloc(&hb.dGather, hb.gather_cap * 6 * sizeof(double)));
     CK(cudaMallocHost(&hb.hGather, hb.gather_cap * 6 * sizeof(double)));
   }

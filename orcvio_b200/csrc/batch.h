@@ -5,6 +5,8 @@
 #include <cuda_runtime.h>
 
 #include <cstring>
+#include <cstdio>
+#include <cstdlib>
 #include <map>
 #include <unordered_map>
 #include <memory>
@@ -121,6 +123,8 @@ struct Blob {                 // one pinned host blob + device twin, carved into
     if (used > pinned_cap) {
       char* np = nullptr;
       const size_t ncap = used * 2 + 4096;
+      if (getenv("ORCVIO_HOST_PROF") && atoi(getenv("ORCVIO_HOST_PROF")) == 3)
+        fprintf(stderr, "[replay prof] growth: pinned blob -> %.1f MB\n", ncap / 1048576.0);
       if (cudaMallocHost(&np, ncap) != cudaSuccess) { used = old_used; return 0; }
       if (pinned) {
         if (old_used) std::memcpy(np, pinned, old_used);
@@ -242,6 +246,7 @@ class Batch {
  private:
   friend struct CApi;
   bool ok_ = false;
+  double* hDiag_ = nullptr;      // pinned: the 15 diagonal entries of the initial covariance
   std::string err_;
   Params p_;
   int B_ = 0, Ncap_ = 0, ldp_ = 0, Fcap_ = 0, ldr_ = 0, ldt_ = 0, dev_ = 0;

@@ -12,7 +12,7 @@ seqs = mc.make_sequences("euroc", ids, n_frames, 150, ov, n_landmarks=3000, work
 print("gen", round(time.perf_counter() - t0, 1), "s", "cores", os.cpu_count(), flush=True)
 path = os.path.join(tempfile.mkdtemp(), "cfg.yaml")
 configs.write_yaml(path, seqs[0]["cfg"])
-for th in (1, 2, 4, 8, 16, 32):
+for th in ([int(x) for x in os.environ['MC_THREADS'].split(',')] if os.environ.get('MC_THREADS') else (1, 2, 4, 8, 16, 32)):
     if th > n_traj:
         break
     rec, info = mc.run_replay(path, seqs, ids, n_threads=th)
