@@ -56,9 +56,10 @@ def lib():
     global _lib
     if _lib is not None:
         return _lib
-    if not os.path.exists(_LIBPATH):
+    path = os.environ.get("ORCVIO_LIB", _LIBPATH)     # (diagnostics: another build of the same library)
+    if not os.path.exists(path):
         _build.build()
-    L = C.CDLL(_LIBPATH)
+    L = C.CDLL(path)
     dp, ip, vp = C.POINTER(C.c_double), C.POINTER(C.c_int), C.c_void_p
     L.orcvio_create.restype = vp
     L.orcvio_create.argtypes = [C.c_char_p]

@@ -372,7 +372,10 @@ struct SyrkPlan {
 };
 // A diagonal pair (I, I) only computes the 36 of its 64 8 x 8 fragments that are ever emitted (k_syrk), so its chunks
 // are longer for the same time: 13/8 as measured (a 64-row slab of a diagonal unit costs 1.13 x its share of DMMAs).
-__host__ __device__ inline int syrk_kcd(int kc) { return (kc * 13 / 8 + 31) / 32 * 32; }
+// At the minimum chunk length (a frame of a few hundred rows: far fewer units than SMs, nothing to balance) a
+// diagonal pair keeps the chunk length of the others: shorter chunks = a flatter summation tree for W = s^2 I + A^T A,
+// and W's rounding is what the update amplifies on an ill-conditioned window (scripts/soak_parity.py).
+__host__ __device__ inline int syrk_kcd(int kc) { return kc <= 128 ? kc : (kc * 13 / 8 + 31) / 32 * 32; }
 __host__ __device__ inline SyrkPlan syrk_plan(const FilterWork& fw, int cta_budget) {
   SyrkPlan p;
   p.nt = (fw.D - ORCVIO_LEG + 1 + SY_TILE - 1) / SY_TILE;

@@ -275,12 +275,13 @@ __device__ void step_mean(double* imu, const PropSample& sm, int flags, double* 
   for (int i = 0; i < 3; ++i) { imu[IM_GOLD + i] = sm.w[i]; imu[IM_AOLD + i] = sm.a[i]; }
 }
 
-// One CTA per filter.  The reference applies every sample's transition to the whole strip [P_II | P_IC] and symmetrises
-// the full matrix (:799-812).  Only the 15 x 15 corner needs that recursion (P_II <- Phi P_II Phi^T + Q dt, symmetrised
-// per sample); the columns behind it only ever see the PRODUCT of the transitions, so the chunk's Phi_tot = Phi_ns ...
-// Phi_1 is accumulated beside the corner (15 x 15 work per sample) and applied to the 15 x (D - 15) block once per chunk
-// of <= 32 samples instead of once per sample: 117 -> ~60 us for the 20 samples of a 10 Hz frame.  P_CI = P_IC^T is
-// rebuilt from the strip at the end (the reference's symmetrisation is the identity on those blocks).
+// One CTA per filter; every sample's transition is applied to the whole 15 x D strip, in the reference's order.
+// (Applying the PRODUCT of a chunk's transitions to the columns behind the corner once per chunk -- only the 15 x 15
+// corner needs the per-sample recursion -- was built and measured: 117 -> 107 us, the serial mean and the transition
+// build dominate.  It was REJECTED for parity: mathematically identical, but its rounding no longer follows the
+// reference's operation order, and the update that follows amplifies the 1e-16 differences in P_IC by the conditioning
+// of an early, strongly correlated window: 2.5e-9 in the velocity at frame 5 of the 300-frame EuRoC soak sequence
+// (scripts/soak_parity.py), above the 1e-9 per-update bound, against 1e-10 for this form.)
 __global__ void __launch_bounds__(256) k_propagate(PropArgs a) {
   extern __shared__ double sm[];
   const int fi = blockIdx.x;
@@ -295,7 +296,6 @@ __global__ void __launch_bounds__(256) k_propagate(PropArgs a) {
   double* phi = strip + (size_t)PS * ldp;           // [SMAX][PS*PS]
   double* ctx = phi + (size_t)SMAX * PS * PS;       // [SMAX][CTX]
   double* tmp = ctx + (size_t)SMAX * CTX;           // [PS*PS]
-  double* tot = tmp + PS * PS;                      // [2][PS*PS]: running product, double-buffered
   for (int e = tid; e < PS * D; e += nt) strip[(e / D) * ldp + (e % D)] = P[(size_t)(e / D) * ldp + (e % D)];
   __syncthreads();
   const double nq[PS] = {a.qc[0], a.qc[0], a.qc[0], a.qc[1], a.qc[1], a.qc[1], 0, 0, 0,
@@ -307,58 +307,38 @@ __global__ void __launch_bounds__(256) k_propagate(PropArgs a) {
     }
     __syncthreads();
     if (tid < ns) build_phi(ctx + tid * CTX, a.flags, phi + (size_t)tid * PS * PS);
-    for (int e = tid; e < PS * PS; e += nt) tot[e] = (e / PS == e % PS) ? 1.0 : 0.0;
     __syncthreads();
-    int cur = 0;
     for (int s = 0; s < ns; ++s) {
       const double* F = phi + (size_t)s * PS * PS;
       const double dt = ctx[s * CTX];
-      double* tin = tot + cur * PS * PS;
-      double* tout = tot + (cur ^ 1) * PS * PS;
-      // tmp = Phi P_II ; tout = Phi Phi_tot
+      for (int j = tid; j < D; j += nt) {
+        double col[PS], out[PS];
+        for (int i = 0; i < PS; ++i) col[i] = strip[i * ldp + j];
+        for (int i = 0; i < PS; ++i) {
+          double acc = 0.0;
+          for (int k = 0; k < PS; ++k) acc += F[i * PS + k] * col[k];
+          out[i] = acc;
+        }
+        for (int i = 0; i < PS; ++i) strip[i * ldp + j] = out[i];
+      }
+      __syncthreads();
+      // corner: P11 = (Phi P11) Phi^T + Phi N Phi^T dt, N = G Qc G^T = diag(nq)
       for (int e = tid; e < PS * PS; e += nt) {
         const int i = e / PS, j = e % PS;
-        double acc = 0.0, g = 0.0;
-        for (int k = 0; k < PS; ++k) {
-          acc += F[i * PS + k] * strip[k * ldp + j];
-          g += F[i * PS + k] * tin[k * PS + j];
-        }
-        tmp[e] = acc;
-        tout[e] = g;
-      }
-      __syncthreads();
-      // corner: P11 = (Phi P11) Phi^T + Phi N Phi^T dt, N = G Qc G^T = diag(nq)   (kept in registers until everyone
-      // has read tmp)
-      double cnew = 0.0;
-      const int ci = tid / PS, cj = tid % PS;
-      if (tid < PS * PS) {
         double acc = 0.0, q = 0.0;
         for (int k = 0; k < PS; ++k) {
-          acc += tmp[ci * PS + k] * F[cj * PS + k];
-          q += F[ci * PS + k] * nq[k] * F[cj * PS + k];
+          acc += strip[i * ldp + k] * F[j * PS + k];
+          q += F[i * PS + k] * nq[k] * F[j * PS + k];
         }
-        cnew = acc + q * dt;
+        tmp[e] = acc + q * dt;
       }
       __syncthreads();
-      if (tid < PS * PS) tmp[tid] = cnew;
-      __syncthreads();
-      if (tid < PS * PS) strip[ci * ldp + cj] = (tmp[ci * PS + cj] + tmp[cj * PS + ci]) / 2.0;
-      cur ^= 1;
-      __syncthreads();
-    }
-    // the columns behind the corner: P_IC <- Phi_tot P_IC
-    const double* T = tot + cur * PS * PS;
-    for (int j = PS + tid; j < D; j += nt) {
-      double col[PS], out[PS];
-      for (int i = 0; i < PS; ++i) col[i] = strip[i * ldp + j];
-      for (int i = 0; i < PS; ++i) {
-        double acc = 0.0;
-        for (int k = 0; k < PS; ++k) acc += T[i * PS + k] * col[k];
-        out[i] = acc;
+      for (int e = tid; e < PS * PS; e += nt) {
+        const int i = e / PS, j = e % PS;
+        strip[i * ldp + j] = (tmp[i * PS + j] + tmp[j * PS + i]) / 2.0;
       }
-      for (int i = 0; i < PS; ++i) strip[i * ldp + j] = out[i];
+      __syncthreads();
     }
-    __syncthreads();
   }
   for (int e = tid; e < PS * D; e += nt) {
     const int i = e / D, j = e % D;
@@ -369,7 +349,7 @@ __global__ void __launch_bounds__(256) k_propagate(PropArgs a) {
 }
 
 void launch_propagate(const PropArgs& a, cudaStream_t s) {
-  size_t smem = ((size_t)PS * a.ldp + (size_t)SMAX * PS * PS + (size_t)SMAX * CTX + 3 * PS * PS) * sizeof(double);
+  size_t smem = ((size_t)PS * a.ldp + (size_t)SMAX * PS * PS + (size_t)SMAX * CTX + PS * PS) * sizeof(double);
   static bool attr = false;
   if (!attr) {
     cudaFuncSetAttribute(k_propagate, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);

@@ -226,8 +226,9 @@ def test_free_running_ate_within_the_north_star_bound(config, overrides, n_frame
     are 3e-6 m apart one frame later (scripts/free_running_trace.py).  So the bound is asserted for as long as every
     decision of the two runs is identical -- the whole sequence unless such a knife edge occurs -- and the knife edge
     must not come before the states themselves have drifted apart by rounding only.  Which frame that is depends on
-    the rounding of the build: any change of a summation order (e.g. the split-K chunking of k_syrk) moves it -- frames
-    23 .. 35 on the two EuRoC-shaped sequences, none on the Unity- and KITTI-shaped ones."""
+    the rounding of the build: a change of a summation order moves it (with 13/8-longer split-K chunks for the diagonal
+    tile pairs of k_syrk on these small frames it came at frames 23 .. 35 on the EuRoC-shaped sequences; the plan
+    keeps the short chunks there, kernels.h syrk_kcd)."""
     seq = synth.make_sequence(synth.SynthSpec(config=config, seed=2, n_frames=n_frames, feats_per_frame=feats,
                                               overrides=overrides, n_landmarks=n_landmarks))
     vio = api.OrcVIO(H.write_cfg(seq["cfg"]))
@@ -240,10 +241,9 @@ def test_free_running_ate_within_the_north_star_bound(config, overrides, n_frame
         _feed(vio, seq, fi, state)
         ref = next(it)
         try:
-            # the gate VALUE is compared at 1e-6 here (teacher-forced: 1e-7): two free-running states a few 1e-10 m apart
-            # put the gamma of a low-parallax feature that far apart, while a flipped LM accept / reject inside a
-            # triangulation -- a decision the candidate log does not show -- moves it by 1e-5 and more
-            _compare_decisions(fi, vio, ref, gamma_rtol=1e-6)
+            # (the gate VALUE is part of the comparison, at the teacher-forced 1e-7: a flipped LM accept / reject inside a
+            # triangulation -- a decision the candidate log does not show -- moves it by 1e-5 and more)
+            _compare_decisions(fi, vio, ref)
         except AssertionError as e:
             flipped = fi
             why = str(e).splitlines()[0]
@@ -251,6 +251,6 @@ def test_free_running_ate_within_the_north_star_bound(config, overrides, n_frame
         d.append(np.linalg.norm(np.array(vio.state().p) - ref.imu_state.position))
     print(f"{config} {n_frames}: free-running ATE gpu-vs-oracle {np.mean(d):.3e} m, max {np.max(d):.3e} m over {len(d)} frames"
           + (f"; first differing decision at frame {flipped}: {why}" if flipped is not None else ""))
-    assert len(d) >= 20 and np.max(d) < 1e-6
+    assert len(d) >= 25 and np.max(d) < 1e-6
     if flipped is None:
         assert np.mean(d) < 1e-6
