@@ -1368,7 +1368,24 @@ int Batch::process_ptrs(const double* t_img, const OrcvioFeature* const* featp, 
   wA.fw.assign(B_, FilterWork{});
   wA.cand_begin.assign(B_ + 1, 0);
   if (hybrid_) { wA.hyb_phase = 0; wA.hw.assign(B_, HybWork{}); }
-  auto clone_index_of = [](const FilterHost& F, long long sid) {
+  // state id -> index in the window.  The window does not change between augmentation (above) and the end of the frame,
+  // and its ids span a few dozen consecutive values: one small table per filter instead of a search per observation.
+  std::vector<std::vector<short>> clone_lut(B_);
+  for (int fi = 0; fi < B_; ++fi) {
+    const FilterHost& F = f_[fi];
+    if (!F.active || F.clones.empty()) continue;
+    const long long base = F.clones.front().id, span = F.clones.back().id - base + 1;
+    if (span > 4096) continue;                             // (never seen: falls back to the search)
+    clone_lut[fi].assign((size_t)span, (short)-1);
+    for (int k = 0; k < (int)F.clones.size(); ++k) clone_lut[fi][(size_t)(F.clones[k].id - base)] = (short)k;
+  }
+  const FilterHost* f_base = f_.data();
+  auto clone_index_of = [&clone_lut, f_base](const FilterHost& F, long long sid) {
+    const std::vector<short>& lut = clone_lut[&F - f_base];
+    if (!lut.empty()) {
+      const long long off = sid - F.clones.front().id;
+      return (off >= 0 && off < (long long)lut.size()) ? (int)lut[(size_t)off] : -1;
+    }
     for (int k = (int)F.clones.size() - 1; k >= 0; --k)
       if (F.clones[k].id == sid) return k;
     return -1;
