@@ -425,7 +425,7 @@ void launch_augment(const AugArgs& a, cudaStream_t s) {
 
 // Delete the rows/columns of up to two clones from P and compact the clone array.  In place, RM_ROWS rows at a time
 // through shared memory: a row moves up and its entries move left, so a chunk only overwrites rows that were already
-// staged (two barriers per chunk instead of two per row: 116 -> ~20 us at D = 202).
+// staged (two barriers per chunk instead of two per row, warps over rows and lanes over columns: 116 -> 45 -> ~20 us at D = 202).
 constexpr int RM_ROWS = 24, RM_THREADS = 512;
 __global__ void __launch_bounds__(RM_THREADS) k_remove(RemoveArgs a) {
   extern __shared__ double rowbuf[];
@@ -451,16 +451,27 @@ __global__ void __launch_bounds__(RM_THREADS) k_remove(RemoveArgs a) {
     if (r1 >= 0 && c > r1) shift += 6;
     return idx - shift;
   };
+  // new index of every row / column (-1 = removed), once; then warps over rows, lanes over columns (no divisions)
+  __shared__ short nidx[256];
+  for (int j = tid; j < D; j += nt) nidx[j] = removed(j) ? (short)-1 : (short)newidx(j);
+  __syncthreads();
+  const int warp = tid >> 5, lane = tid & 31, nw = nt >> 5;
   for (int i0 = 0; i0 < D; i0 += RM_ROWS) {
     const int nr = min(RM_ROWS, D - i0);
-    for (int e = tid; e < nr * D; e += nt) {
-      const int r = e / D, j = e - r * D;
-      rowbuf[r * ldp + j] = P[(size_t)(i0 + r) * ldp + j];
+    for (int r = warp; r < nr; r += nw) {
+      if (nidx[i0 + r] < 0) continue;
+      const double* src = P + (size_t)(i0 + r) * ldp;
+      for (int j = lane; j < D; j += 32) rowbuf[r * ldp + j] = src[j];
     }
     __syncthreads();
-    for (int e = tid; e < nr * D; e += nt) {
-      const int r = e / D, j = e - r * D;
-      if (!removed(i0 + r) && !removed(j)) P[(size_t)newidx(i0 + r) * ldp + newidx(j)] = rowbuf[r * ldp + j];
+    for (int r = warp; r < nr; r += nw) {
+      const int ni = nidx[i0 + r];
+      if (ni < 0) continue;
+      double* dst = P + (size_t)ni * ldp;
+      for (int j = lane; j < D; j += 32) {
+        const int nj = nidx[j];
+        if (nj >= 0) dst[nj] = rowbuf[r * ldp + j];
+      }
     }
     __syncthreads();
   }
