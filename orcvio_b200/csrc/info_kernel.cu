@@ -320,11 +320,10 @@ __global__ void __launch_bounds__(256) k_aform_dense(const double* Hp, int ldh, 
 // W_aug ((n+1) x ldr, UpdArgs::S): A's column 0 (the residual) maps to row n (v = A^T r', corner r'^T r'),
 // column 1 + j to index j, with s^2 added on the first n diagonal entries.
 constexpr int SY_T = SY_TILE, SY_KS = 32, SY_LD = 68;
-// Operand pipeline: SY_STAGES slabs of 32 rows x 64 columns of A (column tile I) and of column tile J, brought in by
-// the TMA engine -- one cp.async.bulk (512 contiguous bytes of a row of A) per slab row, completion counted in bytes
-// on the stage's `full` mbarrier -- by a ninth (producer) warp; the eight MMA warps wait on `full`, run their 64 MMAs
-// on the slab and release it through the stage's `empty` mbarrier.  No __syncthreads and no register staging in the
-// k loop: the loads of the next SY_STAGES - 1 slabs are in flight while a slab is multiplied.
+// Operand pipeline: SY_STAGES slabs of 32 rows x 64 columns of A (column tile I) and of column tile J (a diagonal pair:
+// 64 rows of its one tile), brought in by cp.async (LDGSTS, 16 bytes per copy, zero-fill past the end of the chunk) one
+// slab ahead of the MMAs; one __syncthreads per slab.  (A TMA variant -- one cp.async.bulk per slab row, mbarrier
+// producer warp -- was built and measured slower, and 64-row slabs for every unit change nothing: DESIGN.md.)
 constexpr int SY_THREADS = 256;
 constexpr int SY_STAGE_DOUBLES = 2 * SY_KS * SY_LD;
 
