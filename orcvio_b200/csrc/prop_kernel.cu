@@ -186,100 +186,12 @@ __device__ void build_phi(const double* ctx, int flags, double* Phi /*15x15 row-
   }
 }
 
-// phase 1: one IMU step of the mean (thread 0).  Writes the sample context.
-__device__ void step_mean(double* imu, const PropSample& sm, int flags, double* ctx) {
-  double acc[3], gyro[3], gyro_old[3];
-  for (int i = 0; i < 3; ++i) {
-    acc[i] = sm.a[i] - imu[IM_BA + i];
-    gyro[i] = sm.w[i] - imu[IM_BG + i];
-    gyro_old[i] = imu[IM_GOLD + i] - imu[IM_BG + i];
-  }
-  const double dt = sm.t - imu[IM_TIME];
-  ctx[0] = dt;
-  for (int i = 0; i < 3; ++i) { ctx[1 + i] = gyro[i]; ctx[4 + i] = acc[i]; ctx[28 + i] = gyro_old[i]; }
-  for (int i = 0; i < 9; ++i) ctx[7 + i] = imu[IM_R + i];
-  for (int i = 0; i < 3; ++i) { ctx[16 + i] = imu[IM_V + i]; ctx[19 + i] = imu[IM_P + i]; }
-  const double g[3] = {0.0, 0.0, -9.81};
-  double* R = imu + IM_R;
-  double* v = imu + IM_V;
-  double* p = imu + IM_P;
-  if (!(flags & FL_LARVIO)) {
-    // predictNewStateOrcVIO :899-928
-    double dg[3] = {dt * gyro[0], dt * gyro[1], dt * gyro[2]};
-    double Hl[9], Jl[9], t1[3], t2[3];
-    Hl_op(dg, Hl);
-    m3_vec(Hl, acc, t1);
-    m3_vec(R, t1, t2);
-    for (int i = 0; i < 3; ++i) p[i] = p[i] + dt * v[i] + g[i] * (dt * dt / 2) + t2[i] * (dt * dt);
-    Jl_op(dg, Jl);
-    m3_vec(Jl, acc, t1);
-    m3_vec(R, t1, t2);
-    for (int i = 0; i < 3; ++i) v[i] = v[i] + g[i] * dt + t2[i] * dt;
-    double E[9], Rn[9];
-    so3_exp(dg, E);
-    m3_mul(R, E, Rn);
-    for (int i = 0; i < 9; ++i) R[i] = Rn[i];
-  } else {
-    // predictNewStateLARVIO :825-897
-    const double gn = v3_norm(gyro);
-    double q[4];
-    R_to_quat_xyzw(R, q);
-    // Omega * q
-    auto omq = [&](const double* qq, double* o) {
-      const double wx = gyro[0], wy = gyro[1], wz = gyro[2];
-      // Omega = [[-skew(w), w],[-w^T, 0]]
-      o[0] = (0 * qq[0] + wz * qq[1] - wy * qq[2]) + wx * qq[3];
-      o[1] = (-wz * qq[0] + 0 * qq[1] + wx * qq[2]) + wy * qq[3];
-      o[2] = (wy * qq[0] - wx * qq[1] + 0 * qq[2]) + wz * qq[3];
-      o[3] = -wx * qq[0] - wy * qq[1] - wz * qq[2];
-    };
-    double oq[4], dq1[4], dq2[4];
-    omq(q, oq);
-    if (gn > 1e-5) {
-      const double c1 = cos(gn * dt * 0.5), s1 = 1 / gn * sin(gn * dt * 0.5);
-      const double c2 = cos(gn * dt * 0.25), s2 = 1 / gn * sin(gn * dt * 0.25);
-      for (int i = 0; i < 4; ++i) { dq1[i] = c1 * q[i] + s1 * oq[i]; dq2[i] = c2 * q[i] + s2 * oq[i]; }
-    } else {
-      const double c1 = cos(gn * dt * 0.5), c2 = cos(gn * dt * 0.25);
-      for (int i = 0; i < 4; ++i) {
-        dq1[i] = (q[i] + 0.5 * dt * oq[i]) * c1;
-        dq2[i] = (q[i] + 0.25 * dt * oq[i]) * c2;
-      }
-    }
-    double R1[9], R2[9], R0[9];
-    quat_wxyz_to_R(dq1[3], dq1[0], dq1[1], dq1[2], R1);
-    quat_wxyz_to_R(dq2[3], dq2[0], dq2[1], dq2[2], R2);
-    quat_wxyz_to_R(q[3], q[0], q[1], q[2], R0);
-    double k1v[3], k2v[3], k4v[3], t1[3];
-    m3_vec(R0, acc, t1);
-    for (int i = 0; i < 3; ++i) k1v[i] = t1[i] + g[i];
-    m3_vec(R2, acc, t1);
-    for (int i = 0; i < 3; ++i) k2v[i] = t1[i] + g[i];
-    m3_vec(R1, acc, t1);
-    for (int i = 0; i < 3; ++i) k4v[i] = t1[i] + g[i];
-    double vn[3], pn[3];
-    for (int i = 0; i < 3; ++i) {
-      const double k1_v = v[i] + k1v[i] * dt / 2;
-      const double k2_v = v[i] + k2v[i] * dt / 2;
-      const double k3_v = v[i] + k2v[i] * dt;          // k3_v_dot == k2_v_dot in the reference
-      vn[i] = v[i] + dt / 6 * (k1v[i] + 2 * k2v[i] + 2 * k2v[i] + k4v[i]);
-      pn[i] = p[i] + dt / 6 * (v[i] + 2 * k1_v + 2 * k2_v + k3_v);
-    }
-    double nq = sqrt(dq1[0] * dq1[0] + dq1[1] * dq1[1] + dq1[2] * dq1[2] + dq1[3] * dq1[3]);
-    double qn[4] = {dq1[0] / nq, dq1[1] / nq, dq1[2] / nq, dq1[3] / nq};
-    for (int i = 0; i < 3; ++i) { v[i] = vn[i]; p[i] = pn[i]; }
-    quat_xyzw_to_R(qn, R);
-  }
-  for (int i = 0; i < 3; ++i) { ctx[22 + i] = v[i]; ctx[25 + i] = p[i]; }
-  imu[IM_TIME] = sm.t;
-  for (int i = 0; i < 3; ++i) { imu[IM_GOLD + i] = sm.w[i]; imu[IM_AOLD + i] = sm.a[i]; }
-}
-
+// Mean step (predictNewStateOrcVIO :899-928 / predictNewStateLARVIO :825-897), in two phases per chunk of samples.
 // The closed-form (OrcVIO) mean step split in two: what depends on the SAMPLE only -- bias-corrected rates, dt, the
 // operators Hl(dt w) a, Jl(dt w) a and exp(dt w), i.e. every transcendental of the step -- is computed by one thread
 // per sample (mean_pre), and thread 0 only runs the short recursion R, v, p through them (mean_seq): the same operations
-// on the same values as step_mean, so the results are identical bit for bit, with ~0.4 us instead of ~2.2 us per sample on
-// the serial thread.  (The LARVIO branch keeps step_mean: its quaternion recursion is the bulk of the step.)
+// on the same values as a single serial step, so the results are identical bit for bit, with ~0.4 us instead of ~2.2 us per sample on
+// the serial thread.
 constexpr int PRE = 16;       // per-sample doubles handed from mean_pre to mean_seq
 __device__ void mean_pre(const double* imu, const PropSample* smp, int k, bool first, double* ctx, double* pre) {
   const PropSample& sm = smp[k];
@@ -320,6 +232,89 @@ __device__ void mean_seq(double* imu, const PropSample& sm, double* ctx, const d
   for (int i = 0; i < 3; ++i) { imu[IM_GOLD + i] = sm.w[i]; imu[IM_AOLD + i] = sm.a[i]; }
 }
 
+// The same split for the LARVIO step: the sample-only part is the rates, dt, |w| and the four trigonometric factors of
+// the two quaternion increments; the quaternion / Runge-Kutta recursion itself stays on the serial thread, expression
+// for expression as in a single serial step (bit-identical results).
+__device__ void mean_pre_larvio(const double* imu, const PropSample* smp, int k, bool first, double* ctx, double* pre) {
+  const PropSample& sm = smp[k];
+  double gyro[3];
+  for (int i = 0; i < 3; ++i) {
+    ctx[4 + i] = sm.a[i] - imu[IM_BA + i];
+    gyro[i] = sm.w[i] - imu[IM_BG + i];
+    ctx[1 + i] = gyro[i];
+    ctx[28 + i] = (first ? imu[IM_GOLD + i] : smp[k - 1].w[i]) - imu[IM_BG + i];
+  }
+  const double dt = sm.t - (first ? imu[IM_TIME] : smp[k - 1].t);
+  ctx[0] = dt;
+  const double gn = v3_norm(gyro);
+  pre[0] = gn;
+  pre[1] = cos(gn * dt * 0.5);
+  pre[3] = cos(gn * dt * 0.25);
+  if (gn > 1e-5) {
+    pre[2] = 1 / gn * sin(gn * dt * 0.5);
+    pre[4] = 1 / gn * sin(gn * dt * 0.25);
+  }
+}
+__device__ void mean_seq_larvio(double* imu, const PropSample& sm, double* ctx, const double* pre) {
+  const double dt = ctx[0];
+  const double gyro[3] = {ctx[1], ctx[2], ctx[3]}, acc[3] = {ctx[4], ctx[5], ctx[6]};
+  for (int i = 0; i < 9; ++i) ctx[7 + i] = imu[IM_R + i];
+  for (int i = 0; i < 3; ++i) { ctx[16 + i] = imu[IM_V + i]; ctx[19 + i] = imu[IM_P + i]; }
+  const double g[3] = {0.0, 0.0, -9.81};
+  double* R = imu + IM_R;
+  double* v = imu + IM_V;
+  double* p = imu + IM_P;
+  const double gn = pre[0];
+  double q[4];
+  R_to_quat_xyzw(R, q);
+  auto omq = [&](const double* qq, double* o) {
+    const double wx = gyro[0], wy = gyro[1], wz = gyro[2];
+    o[0] = (0 * qq[0] + wz * qq[1] - wy * qq[2]) + wx * qq[3];
+    o[1] = (-wz * qq[0] + 0 * qq[1] + wx * qq[2]) + wy * qq[3];
+    o[2] = (wy * qq[0] - wx * qq[1] + 0 * qq[2]) + wz * qq[3];
+    o[3] = -wx * qq[0] - wy * qq[1] - wz * qq[2];
+  };
+  double oq[4], dq1[4], dq2[4];
+  omq(q, oq);
+  if (gn > 1e-5) {
+    const double c1 = pre[1], s1 = pre[2];
+    const double c2 = pre[3], s2 = pre[4];
+    for (int i = 0; i < 4; ++i) { dq1[i] = c1 * q[i] + s1 * oq[i]; dq2[i] = c2 * q[i] + s2 * oq[i]; }
+  } else {
+    const double c1 = pre[1], c2 = pre[3];
+    for (int i = 0; i < 4; ++i) {
+      dq1[i] = (q[i] + 0.5 * dt * oq[i]) * c1;
+      dq2[i] = (q[i] + 0.25 * dt * oq[i]) * c2;
+    }
+  }
+  double R1[9], R2[9], R0[9];
+  quat_wxyz_to_R(dq1[3], dq1[0], dq1[1], dq1[2], R1);
+  quat_wxyz_to_R(dq2[3], dq2[0], dq2[1], dq2[2], R2);
+  quat_wxyz_to_R(q[3], q[0], q[1], q[2], R0);
+  double k1v[3], k2v[3], k4v[3], t1[3];
+  m3_vec(R0, acc, t1);
+  for (int i = 0; i < 3; ++i) k1v[i] = t1[i] + g[i];
+  m3_vec(R2, acc, t1);
+  for (int i = 0; i < 3; ++i) k2v[i] = t1[i] + g[i];
+  m3_vec(R1, acc, t1);
+  for (int i = 0; i < 3; ++i) k4v[i] = t1[i] + g[i];
+  double vn[3], pn[3];
+  for (int i = 0; i < 3; ++i) {
+    const double k1_v = v[i] + k1v[i] * dt / 2;
+    const double k2_v = v[i] + k2v[i] * dt / 2;
+    const double k3_v = v[i] + k2v[i] * dt;          // k3_v_dot == k2_v_dot in the reference
+    vn[i] = v[i] + dt / 6 * (k1v[i] + 2 * k2v[i] + 2 * k2v[i] + k4v[i]);
+    pn[i] = p[i] + dt / 6 * (v[i] + 2 * k1_v + 2 * k2_v + k3_v);
+  }
+  double nq = sqrt(dq1[0] * dq1[0] + dq1[1] * dq1[1] + dq1[2] * dq1[2] + dq1[3] * dq1[3]);
+  double qn[4] = {dq1[0] / nq, dq1[1] / nq, dq1[2] / nq, dq1[3] / nq};
+  for (int i = 0; i < 3; ++i) { v[i] = vn[i]; p[i] = pn[i]; }
+  quat_xyzw_to_R(qn, R);
+  for (int i = 0; i < 3; ++i) { ctx[22 + i] = v[i]; ctx[25 + i] = p[i]; }
+  imu[IM_TIME] = sm.t;
+  for (int i = 0; i < 3; ++i) { imu[IM_GOLD + i] = sm.w[i]; imu[IM_AOLD + i] = sm.a[i]; }
+}
+
 // One CTA per filter; every sample's transition is applied to the whole 15 x D strip, in the reference's order.
 // (Applying the PRODUCT of a chunk's transitions to the columns behind the corner once per chunk -- only the 15 x 15
 // corner needs the per-sample recursion -- was built and measured: 117 -> 107 us, the serial mean and the transition
@@ -348,14 +343,17 @@ __global__ void __launch_bounds__(256) k_propagate(PropArgs a) {
                          a.qc[2], a.qc[2], a.qc[2], a.qc[3], a.qc[3], a.qc[3]};
   for (int c0 = s0; c0 < s1; c0 += SMAX) {
     const int ns = min(SMAX, s1 - c0);
-    if (!(a.flags & FL_LARVIO)) {
-      if (tid < ns) mean_pre(imu, a.samples, c0 + tid, tid == 0, ctx + tid * CTX, pre + tid * PRE);
-      __syncthreads();
-      if (tid == 0) {
-        for (int s = 0; s < ns; ++s) mean_seq(imu, a.samples[c0 + s], ctx + s * CTX, pre + s * PRE);
+    const bool larvio = (a.flags & FL_LARVIO) != 0;
+    if (tid < ns) {
+      if (larvio) mean_pre_larvio(imu, a.samples, c0 + tid, tid == 0, ctx + tid * CTX, pre + tid * PRE);
+      else mean_pre(imu, a.samples, c0 + tid, tid == 0, ctx + tid * CTX, pre + tid * PRE);
+    }
+    __syncthreads();
+    if (tid == 0) {
+      for (int s = 0; s < ns; ++s) {
+        if (larvio) mean_seq_larvio(imu, a.samples[c0 + s], ctx + s * CTX, pre + s * PRE);
+        else mean_seq(imu, a.samples[c0 + s], ctx + s * CTX, pre + s * PRE);
       }
-    } else if (tid == 0) {
-      for (int s = 0; s < ns; ++s) step_mean(imu, a.samples[c0 + s], a.flags, ctx + s * CTX);
     }
     __syncthreads();
     if (tid < ns) build_phi(ctx + tid * CTX, a.flags, phi + (size_t)tid * PS * PS);
