@@ -210,7 +210,9 @@ int orcvio_object_lm_eval(int n_obj, const int* frame_off, const double* frames_
                           int K, const double* kps_mean, const double* mean_shape, const double* weights4, int flags,
                           const double* states, double* out);
 /* The reference's two Levenberg-Marquardt known-answer problems (src/tests/test_levenberg_marquardt.cpp:64-140) through
- * the library's driver; which = 0: lmder1 example (x_out 3), 1: the quadratic (x_out 1).  Needs no device. */
+ * the library's driver; which = 0: lmder1 example (x_out 3), 1: the quadratic (x_out 1); 2 / 3: MINPACK's Rosenbrock and
+ * Freudenstein-Roth test functions from their standard starting points with lmder1's settings (x_out 2), whose answers
+ * the CPU tests take from the real MINPACK (scipy.optimize.leastsq).  Needs no device. */
 int orcvio_lm_known_answer(int which, double* x_out, int* status, int* nfev, int* njev, double* fnorm);
 /* The reference's trajectory logger (System::publishGroundtruth, ros_wrapper/src/orcvio/src/System.cpp:885-943) for a
  * batch of trajectories, on the device: first-pose SE(3) alignment, then per trajectory the mean orientation error

@@ -684,7 +684,7 @@ class ObjectFeatureInitializer:
 def lm_known_answer(which):
     """The reference's Levenberg-Marquardt known-answer problems through the library's driver (no device needed)."""
     L = lib()
-    x = np.zeros(3)
+    x = np.zeros(4)
     st, nf, nj = C.c_int(0), C.c_int(0), C.c_int(0)
     fn = C.c_double(0)
     L.orcvio_lm_known_answer.argtypes = [C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_int), C.POINTER(C.c_int),
@@ -692,7 +692,7 @@ def lm_known_answer(which):
     rc = L.orcvio_lm_known_answer(which, _dp(x), C.byref(st), C.byref(nf), C.byref(nj), C.byref(fn))
     if rc != 0:
         raise RuntimeError(f"orcvio_lm_known_answer failed: {rc}")
-    return dict(x=x[:3 if which == 0 else 1], status=st.value, nfev=nf.value, njev=nj.value, fnorm=fn.value)
+    return dict(x=x[:{0: 3, 1: 1}.get(which, 2)], status=st.value, nfev=nf.value, njev=nj.value, fnorm=fn.value)
 
 
 def trajectory_metrics(est_pose7, gt_pose7):

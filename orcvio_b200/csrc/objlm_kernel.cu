@@ -572,6 +572,31 @@ int lm_known_answer(int which, double* x_out, int* status, int* nfev, int* njev,
       return std::fabs(x[0] - 10.0);
     };
     res = lm_minimize(1, eval, x, opt, plus, norm);
+  } else if (which == 2 || which == 3) {
+    // two of MINPACK's own test functions, for which the real MINPACK (scipy.optimize.leastsq -> lmder) gives the
+    // answer on the CPU test side: Rosenbrock (n = m = 2, start (-1.2, 1)) and Freudenstein-Roth (start (0.5, -2));
+    // lmder1 settings (tol = sqrt(eps), maxfev = 100 (n + 1), factor 100)
+    const bool rosen = which == 2;
+    x = rosen ? std::vector<double>{-1.2, 1.0} : std::vector<double>{0.5, -2.0};
+    opt.maxfev = 100 * (2 + 1);
+    EvalFn eval = [rosen](const std::vector<double>& x, double* JtJ, double* Jtf) {
+      double f[2], J[2][2];
+      if (rosen) {
+        f[0] = 10 * (x[1] - x[0] * x[0]); f[1] = 1 - x[0];
+        J[0][0] = -20 * x[0]; J[0][1] = 10.0; J[1][0] = -1.0; J[1][1] = 0.0;
+      } else {
+        f[0] = -13 + x[0] + ((5 - x[1]) * x[1] - 2) * x[1];
+        f[1] = -29 + x[0] + ((x[1] + 1) * x[1] - 14) * x[1];
+        J[0][0] = 1.0; J[0][1] = 10 * x[1] - 3 * x[1] * x[1] - 2;
+        J[1][0] = 1.0; J[1][1] = 3 * x[1] * x[1] + 2 * x[1] - 14;
+      }
+      for (int a = 0; a < 2; ++a) {
+        for (int b = 0; b < 2; ++b) JtJ[2 * a + b] = J[0][a] * J[0][b] + J[1][a] * J[1][b];
+        Jtf[a] = J[0][a] * f[0] + J[1][a] * f[1];
+      }
+      return std::sqrt(f[0] * f[0] + f[1] * f[1]);
+    };
+    res = lm_minimize(2, eval, x, opt, plus, norm);
   } else {
     return ORCVIO_ERR_ARG;
   }

@@ -163,3 +163,27 @@ def test_library_lm_driver_reproduces_the_reference_known_answers():
     assert np.linalg.norm(r["x"] - np.array([0.08241058, 1.133037, 2.343695])) < 1e-6
     r = api.lm_known_answer(1)
     assert (r["status"], r["nfev"], r["njev"]) == (4, 2, 2) and abs(r["fnorm"]) < 1e-6 and abs(r["x"][0] - 10.0) < 1e-6
+
+
+def test_library_lm_driver_against_the_real_minpack():
+    """The library's driver (normal equations + pivoted Cholesky) on two of MINPACK's own test functions against
+    scipy.optimize.leastsq = MINPACK's lmder with the same settings.  Freudenstein-Roth: the same x, |f|, nfev, njev and
+    info.  Rosenbrock (exact zero residual at the solution): the same x and |f|; the last step lands on the solution one
+    evaluation later than MINPACK's (rounding of Q^T f at |f| ~ 1e-16), so the stop is xtol instead of an exactly
+    orthogonal f."""
+    import numpy as np
+    from scipy.optimize import leastsq
+    from test_oracle_cpu import _minpack_problems
+    tol = np.sqrt(np.finfo(float).eps)
+    prob = {n: (f, j, x0) for n, f, j, x0 in _minpack_problems()}
+    for which, name in ((2, "rosenbrock"), (3, "freudenstein_roth")):
+        f, j, x0 = prob[name]
+        xs, _, info, _, ier = leastsq(f, x0, Dfun=j, full_output=True, ftol=tol, xtol=tol, gtol=0.0, maxfev=300, factor=100.0)
+        r = api.lm_known_answer(which)
+        np.testing.assert_allclose(r["x"], xs, rtol=1e-12, atol=1e-14)
+        assert abs(r["fnorm"] - np.linalg.norm(info["fvec"])) <= 1e-13 * max(1.0, r["fnorm"])
+        assert r["njev"] == info["njev"] and abs(r["nfev"] - info["nfev"]) <= 1
+        if name == "freudenstein_roth":
+            assert (r["nfev"], r["status"]) == (info["nfev"], ier)
+        else:
+            assert r["status"] in (2, 4)

@@ -388,3 +388,41 @@ def test_object_lm_jacobian_matches_central_differences_under_its_own_retraction
         fp = obj.object_lm_full(fr, *obj.object_state_plus(x, e), zs, zb, True, False, d["kps_mean"], d["mean_shape"], w)[0]
         fm = obj.object_lm_full(fr, *obj.object_state_plus(x, -e), zs, zb, True, False, d["kps_mean"], d["mean_shape"], w)[0]
         assert np.abs((fp - fm) / (2 * h) - J[:, c]).max() <= 2e-6 * max(1.0, np.abs(J[:, c]).max()), c
+
+
+def _minpack_problems():
+    """Three of MINPACK's own test functions with their standard starting points."""
+    s5, s10 = np.sqrt(5.0), np.sqrt(10.0)
+    return [
+        ("rosenbrock", lambda x: np.array([10 * (x[1] - x[0] ** 2), 1 - x[0]]),
+         lambda x: np.array([[-20 * x[0], 10.0], [-1.0, 0.0]]), np.array([-1.2, 1.0])),
+        ("freudenstein_roth", lambda x: np.array([-13 + x[0] + ((5 - x[1]) * x[1] - 2) * x[1],
+                                                  -29 + x[0] + ((x[1] + 1) * x[1] - 14) * x[1]]),
+         lambda x: np.array([[1.0, 10 * x[1] - 3 * x[1] ** 2 - 2], [1.0, 3 * x[1] ** 2 + 2 * x[1] - 14]]),
+         np.array([0.5, -2.0])),
+        ("powell_singular", lambda x: np.array([x[0] + 10 * x[1], s5 * (x[2] - x[3]), (x[1] - 2 * x[2]) ** 2,
+                                                s10 * (x[0] - x[3]) ** 2]),
+         lambda x: np.array([[1, 10, 0, 0], [0, 0, s5, -s5], [0, 2 * (x[1] - 2 * x[2]), -4 * (x[1] - 2 * x[2]), 0],
+                             [2 * s10 * (x[0] - x[3]), 0, 0, -2 * s10 * (x[0] - x[3])]], dtype=float),
+         np.array([3.0, -1.0, 0.0, 1.0])),
+    ]
+
+
+def test_lm_oracle_against_the_real_minpack():
+    """The vendored EigenLevenbergMarquardt is a port of MINPACK's lmder; scipy.optimize.leastsq IS MINPACK's lmder.  On
+    MINPACK's own test functions the oracle's restatement reproduces it evaluation for evaluation: same x, |f|, nfev, njev
+    and info (the two share the numbering 1..8).  Powell's singular function ends at a residual of 1e-30 where the two
+    part ways in the last few steps: only the solution is compared there."""
+    from scipy.optimize import leastsq
+    from oracle import lm
+    tol = np.sqrt(np.finfo(float).eps)
+    for name, f, j, x0 in _minpack_problems():
+        xs, _, info, _, ier = leastsq(f, x0, Dfun=j, full_output=True, ftol=tol, xtol=tol, gtol=0.0,
+                                      maxfev=100 * (len(x0) + 1), factor=100.0)
+        r = lm.lmder1(f, j, x0)
+        if name == "powell_singular":
+            assert np.abs(r["x"]).max() < 1e-12 and np.abs(xs).max() < 1e-12
+            continue
+        assert (r["nfev"], r["njev"], r["status"]) == (info["nfev"], info["njev"], ier), name
+        np.testing.assert_allclose(r["x"], xs, rtol=1e-12, atol=1e-14)
+        assert abs(r["fnorm"] - np.linalg.norm(info["fvec"])) <= 1e-13 * max(1.0, r["fnorm"])
