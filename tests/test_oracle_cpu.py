@@ -9,6 +9,7 @@ Pins:
   * nullspace SVD == QR projection property (reference test_state_update.cpp:106-212).
 """
 import copy
+import math
 import os
 
 import numpy as np
@@ -426,3 +427,40 @@ def test_lm_oracle_against_the_real_minpack():
         assert (r["nfev"], r["njev"], r["status"]) == (info["nfev"], info["njev"], ier), name
         np.testing.assert_allclose(r["x"], xs, rtol=1e-12, atol=1e-14)
         assert abs(r["fnorm"] - np.linalg.norm(info["fvec"])) <= 1e-13 * max(1.0, r["fnorm"])
+
+
+def test_lie_group_helpers_against_the_matrix_exponential():
+    """Sophus (SO3 / SE3 exp and log; third party, absent from the reference tree: its published closed forms are what
+    oracle/mathutils.py restates) pinned by the definition itself: exp(hat(xi)) by scipy.linalg.expm, log by logm, over
+    small, generic and near-pi rotations; Jl_operator against its series sum_k hat(w)^k / (k + 1)!."""
+    from scipy.linalg import expm, logm
+
+    def hat6(xi):
+        M = np.zeros((4, 4))
+        M[:3, :3] = mu.skew(xi[3:])
+        M[:3, 3] = xi[:3]
+        return M
+
+    rng = np.random.default_rng(1)
+    for scale in (1e-12, 1e-6, 0.3, 2.0, 3.1):
+        for _ in range(5):
+            w = rng.normal(size=3)
+            w = scale * w / np.linalg.norm(w)
+            xi = np.concatenate([rng.normal(size=3), w])
+            R = mu.so3_exp(w)
+            np.testing.assert_allclose(R, expm(mu.skew(w)), rtol=0, atol=5e-15)
+            T = mu.se3_exp(xi)
+            # (below 1e-10 rad Sophus takes V = R, an O(theta) approximation of the translation part: restated as it is)
+            # and above it evaluates (1 - cos t) / t^2 as written: cancellation of ~1e-16 / t in the translation part)
+            np.testing.assert_allclose(T, expm(hat6(xi)), rtol=0, atol=2e-14 + (4 * scale if scale < 1e-10 else 1e-15 / scale))
+            np.testing.assert_allclose(mu.se3_log(T), xi, rtol=0,
+                                       atol=1e-9 if scale > 3 else 1e-12 + (4 * scale if scale < 1e-10 else 1e-15 / scale))
+            if 1e-3 < scale < 3:
+                np.testing.assert_allclose(hat6(mu.se3_log(T)), np.real(logm(T)), rtol=0, atol=1e-12)
+            # Jl = sum_k hat(w)^k / (k + 1)!
+            S, term, Jl = mu.skew(w), np.eye(3), np.zeros((3, 3))
+            for k in range(40):
+                Jl = Jl + term / math.factorial(k + 1)
+                term = term @ S
+            # (below 1e-5 rad the reference's Jl_operator returns the identity, math_utils.hpp:255-257: restated as it is)
+            np.testing.assert_allclose(mu.Jl_operator(w), Jl, rtol=0, atol=scale if scale < 1e-5 else 1e-13)
