@@ -545,3 +545,59 @@ def test_transition_matrix_against_central_differences_of_the_mean_propagation()
     for (r, c) in blocks.values():
         mask[r:r + 3, c:c + 3] = False
     assert np.abs((Phi - N)[mask]).max() <= 1e-9
+
+
+def test_msckf_update_equals_the_bayesian_marginal_over_the_features():
+    """Stages 2, 4 and 5 pinned by the theory they implement rather than by their transcription: projecting every
+    feature's rows onto the left nullspace of its H_f, stacking, compressing (QR) and applying the covariance-form EKF
+    update (nullspace_project_inplace_svd, measurementUpdate_msckf :1654-1763) must give the posterior of the window that
+    the JOINT linear-Gaussian problem over [window, features] gives when the features have a flat prior and are
+    marginalised (information form + Schur complement) -- dx and P+ to 1e-9."""
+    seq = synth.make_sequence(synth.SynthSpec(config="unity", seed=3, n_frames=8, feats_per_frame=40,
+                                              overrides=dict(if_ZUPT_valid=0), n_landmarks=2000))
+    it = H.run_oracle_sequence(seq)
+    for _ in range(8):
+        vio = next(it)
+    N = len(vio.clones)
+    D = 22 + 6 * N
+    rng = np.random.default_rng(9)
+    act = np.r_[0:15, 22:D]                       # rows / columns 15..21 (extrinsics, td) are not estimated: zero
+    A = rng.normal(size=(len(act), len(act)))
+    Pa = A @ A.T / len(act) + 0.05 * np.eye(len(act))
+    P = np.zeros((D, D))
+    P[np.ix_(act, act)] = Pa
+    sigma2 = vio.p.feature_observation_noise
+    Hs, rs, joint = [], [], []
+    for f in range(12):
+        m = int(rng.integers(3, 7))
+        first = int(rng.integers(0, N - m + 1))
+        Hx = np.zeros((2 * m, D))
+        Hx[:, 22 + 6 * first:22 + 6 * (first + m)] = rng.normal(size=(2 * m, 6 * m))
+        Hf = rng.normal(size=(2 * m, 3))
+        r = rng.normal(scale=0.05, size=2 * m)
+        ok, Hp, rp = nullspace_project_inplace_svd(Hf, Hx, r)
+        assert ok and Hp.shape[0] == 2 * m - 3
+        Hs.append(Hp)
+        rs.append(rp)
+        joint.append((Hx[:, act], Hf, r))
+    v = copy.deepcopy(vio)
+    v.state_cov = P.copy()
+    v.measurementUpdate_msckf(np.vstack(Hs), np.concatenate(rs))
+    dx = [l for l in v.log if l["kind"] == "update"][-1]["delta_x"]
+    # the joint problem: information form over [window (active), 3 F feature coordinates], flat prior on the features
+    na, F = len(act), len(joint)
+    L = np.zeros((na + 3 * F, na + 3 * F))
+    eta = np.zeros(na + 3 * F)
+    L[:na, :na] = np.linalg.inv(Pa)
+    for f, (Hx, Hf, r) in enumerate(joint):
+        J = np.zeros((Hx.shape[0], na + 3 * F))
+        J[:, :na] = Hx
+        J[:, na + 3 * f:na + 3 * f + 3] = Hf
+        L += J.T @ J / sigma2
+        eta += J.T @ r / sigma2
+    Lxx, Lxf, Lff = L[:na, :na], L[:na, na:], L[na:, na:]
+    Pp = np.linalg.inv(Lxx - Lxf @ np.linalg.solve(Lff, Lxf.T))
+    dxp = Pp @ (eta[:na] - Lxf @ np.linalg.solve(Lff, eta[na:]))
+    assert np.abs(v.state_cov[np.ix_(act, act)] - Pp).max() <= 1e-9 * np.abs(Pp).max()
+    assert np.abs(dx[act] - dxp).max() <= 1e-9 * max(1.0, np.abs(dxp).max())
+    assert np.abs(v.state_cov[15:22]).max() == 0.0 and np.abs(dx[15:22]).max() == 0.0
