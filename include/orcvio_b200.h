@@ -219,6 +219,14 @@ int orcvio_lm_known_answer(int which, double* x_out, int* status, int* nfev, int
  * (deg), mean position error (m), position RMSE (m) and final position error (m) -> out4 (n_traj x 4).  Poses are
  * n_traj x n_frames x 7 (p, q xyzw, Hamilton), host pointers. */
 int orcvio_trajectory_metrics(const double* est_pose7, const double* gt_pose7, int n_traj, int n_frames, double* out4);
+/* The reference's KITTI-style relative error (python_scripts/trajectory_eval/traj_eval.py:61-90 -> the vendored
+ * rpg_trajectory_evaluation: compute_trajectory_errors.py:10-67, trajectory.py:341-377, 309-339) for a batch of
+ * trajectories on the device: for every sub-trajectory length the pairs (start, first pose closest to start + length
+ * along the ground truth, tolerance 0.2 length) and the error of the relative motion.  out4: n_traj x n_len x 4 =
+ * (samples, mean translation error in % of the length, mean rotation error in deg / m, mean translation error in m);
+ * trans_error_pct (n_traj, may be NULL): write_kitti_errors_to_yaml's "TransError(%)".  Poses as above, n_frames <= 4096. */
+int orcvio_kitti_relative_error(const double* est_pose7, const double* gt_pose7, int n_traj, int n_frames,
+                                const double* lengths, int n_len, double* out4, double* trans_error_pct);
 int orcvio_batch_get_state(orcvio_batch* b, int i, OrcvioState* out);
 int orcvio_batch_get_cov(orcvio_batch* b, int i, double* P, int cap, int* D);
 int orcvio_batch_get_frame_stats(orcvio_batch* b, int i, OrcvioFrameStats* out);

@@ -709,6 +709,23 @@ def trajectory_metrics(est_pose7, gt_pose7):
     return out
 
 
+def kitti_relative_error(est_pose7, gt_pose7, lengths):
+    """The reference's KITTI-style relative error on the device (orcvio_kitti_relative_error): (n, F, 7) poses ->
+    ((n, n_len, 4): samples, mean translation %, mean rotation deg / m, mean translation m;  (n,): TransError(%))."""
+    e = np.ascontiguousarray(est_pose7, dtype=np.float64)
+    g = np.ascontiguousarray(gt_pose7, dtype=np.float64)
+    L = np.ascontiguousarray(lengths, dtype=np.float64)
+    assert e.shape == g.shape and e.ndim == 3 and e.shape[2] == 7
+    out = np.zeros((e.shape[0], len(L), 4))
+    summ = np.zeros(e.shape[0])
+    f = lib().orcvio_kitti_relative_error
+    f.argtypes = [C.POINTER(C.c_double)] * 2 + [C.c_int, C.c_int, C.POINTER(C.c_double), C.c_int] + [C.POINTER(C.c_double)] * 2
+    rc = f(_dp(e), _dp(g), e.shape[0], e.shape[1], _dp(L), len(L), _dp(out), _dp(summ))
+    if rc != 0:
+        raise RuntimeError(f"orcvio_kitti_relative_error failed: {rc}")
+    return out, summ
+
+
 def object_residuals(frames_wTc, wTo, shape, kps, zs, zb, left=True, new_residual=False):
     """Stage 3 functor evaluation (O1-O4): returns dict(fvec, fjac_cam, fjac_obj, zs_num, cam_pose_se3)."""
     L = lib()

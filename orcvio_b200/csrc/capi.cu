@@ -337,6 +337,12 @@ int orcvio_trajectory_metrics(const double* est_pose7, const double* gt_pose7, i
   return ob::trajectory_metrics(est_pose7, gt_pose7, n_traj, n_frames, out4);
 }
 
+int orcvio_kitti_relative_error(const double* est_pose7, const double* gt_pose7, int n_traj, int n_frames,
+                                const double* lengths, int n_len, double* out4, double* trans_error_pct) {
+  if (!est_pose7 || !gt_pose7 || !lengths || !out4) return ORCVIO_ERR_ARG;
+  return ob::kitti_relative_error(est_pose7, gt_pose7, n_traj, n_frames, lengths, n_len, out4, trans_error_pct);
+}
+
 int orcvio_batch_get_state(orcvio_batch* b, int i, OrcvioState* out) {
   if (!b || !out) return ORCVIO_ERR_ARG;
   return b->batch->get_state(i, out);

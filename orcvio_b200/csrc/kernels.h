@@ -325,6 +325,9 @@ void launch_info_prior(const UpdArgs& u, const InfoBufs& ib, int max_N, cudaStre
                        cudaEvent_t join, cudaEvent_t t0 = nullptr, cudaEvent_t t1 = nullptr, int max_E = 0);
 // System::publishGroundtruth for a batch of trajectories (metrics_kernel.cu); host pointers, pose = p (3) + q xyzw (4)
 int trajectory_metrics(const double* est_pose7, const double* gt_pose7, int n_traj, int n_frames, double* out4);
+// KITTI-style relative error (rpg_trajectory_evaluation as the reference's traj_eval.py calls it); host pointers
+int kitti_relative_error(const double* est_pose7, const double* gt_pose7, int n_traj, int n_frames, const double* lengths,
+                         int n_len, double* out4, double* trans_error_pct);
 // findTransform (+ poseSE32SE2) for a batch of objects (kabsch_kernel.cu); host pointers
 int kabsch_init(const double* mean_pts, const double* world_pts, const int* off, int n_obj, int se2, double* wTq16, int* ok);
 // object state optimiser (objlm_kernel.cu); host pointers

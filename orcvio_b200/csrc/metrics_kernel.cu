@@ -132,4 +132,158 @@ int trajectory_metrics(const double* est_pose7, const double* gt_pose7, int n_tr
   return e == cudaSuccess ? ORCVIO_OK : ORCVIO_ERR_CUDA;
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// KITTI-style relative error for a batch of trajectories (second half): what the reference's
+// python_scripts/trajectory_eval/traj_eval.py:61-90 computes through its vendored rpg_trajectory_evaluation
+// (compute_trajectory_errors.py:10-67 compute_relative_error with T_cm = I and scale 1, trajectory_utils.py:11-37,
+// trajectory.py:341-377 with max_dist_diff = 0.2 x length, :309-339 for the "TransError(%)" summary).
+// One CTA per (sub-trajectory length, trajectory):
+//   1. distance from the start along the GROUND TRUTH (a sequential cumulative sum, as numpy.cumsum);
+//   2. for every start index the FIRST later index whose distance is closest to d + length within the tolerance
+//      (threads over the starts, each scans forward until the distances pass the tolerance);
+//   3. the matches are compacted IN ORDER and entry k is paired with start k -- the reference drops the starts without a
+//      match from the list and then enumerates it (compute_trajectory_errors.py:30-31); kept as it is;
+//   4. per pair E = (T_gt1^-1 T_gt2)^-1 (T_es1^-1 T_es2): |t(E)|, |t(E)| / length in %, angle(E) in degrees and per
+//      metre (the rotation of E into the world frame, :45-48, changes neither); summed in sample order by one thread.
+// Fewer than two samples: nothing is computed (the reference returns empty arrays).
+// out: n_traj x n_len x 4 = (samples, mean translation error %, mean rotation error deg / m, mean translation error m).
+namespace {
+
+__device__ __forceinline__ void quat_to_R_rpg(const double* q, double* R) {      // transformations.py:1410-1429, x y z w
+  double v[4] = {q[0], q[1], q[2], q[3]};
+  const double nq = (v[0] * v[0] + v[1] * v[1]) + (v[2] * v[2] + v[3] * v[3]);
+  if (nq < 8.881784197001252e-16) {                                              // _EPS = 4 eps
+    for (int i = 0; i < 9; ++i) R[i] = (i % 4 == 0) ? 1.0 : 0.0;
+    return;
+  }
+  const double sc = sqrt(2.0 / nq);
+  for (int i = 0; i < 4; ++i) v[i] *= sc;
+  auto Q = [&](int i, int j) { return v[i] * v[j]; };
+  R[0] = 1.0 - Q(1, 1) - Q(2, 2); R[1] = Q(0, 1) - Q(2, 3); R[2] = Q(0, 2) + Q(1, 3);
+  R[3] = Q(0, 1) + Q(2, 3); R[4] = 1.0 - Q(0, 0) - Q(2, 2); R[5] = Q(1, 2) - Q(0, 3);
+  R[6] = Q(0, 2) - Q(1, 3); R[7] = Q(1, 2) + Q(0, 3); R[8] = 1.0 - Q(0, 0) - Q(1, 1);
+}
+
+// relative motion T1^-1 T2 of two poses (p, q): R = R1^T R2, t = R1^T (p2 - p1)
+__device__ __forceinline__ void rel_motion(const double* a, const double* b, double* R, double* t) {
+  double R1[9], R2[9];
+  quat_to_R_rpg(a + 3, R1);
+  quat_to_R_rpg(b + 3, R2);
+  m3_Tmul(R1, R2, R);
+  const double d[3] = {b[0] - a[0], b[1] - a[1], b[2] - a[2]};
+  m3_Tvec(R1, d, t);
+}
+
+}  // namespace
+
+__global__ void __launch_bounds__(256) k_kitti_relative_error(const double* __restrict__ est, const double* __restrict__ gt,
+                                                              int n_frames, const double* __restrict__ lengths, int n_len,
+                                                              double* __restrict__ out) {
+  extern __shared__ double ksm[];
+  double* dist = ksm;                               // [n_frames]
+  double* v_perc = dist + n_frames;                 // [n_frames] per-sample values, summed in order at the end
+  double* v_rot = v_perc + n_frames;
+  double* v_tr = v_rot + n_frames;
+  int* match = reinterpret_cast<int*>(v_tr + n_frames);   // [n_frames]
+  int* comps = match + n_frames;                    // [n_frames]
+  __shared__ int s_k;
+  const int li = blockIdx.x, tr = blockIdx.y, tid = threadIdx.x, nt = blockDim.x;
+  const double* E = est + (size_t)tr * n_frames * 7;
+  const double* G = gt + (size_t)tr * n_frames * 7;
+  const double L = lengths[li], tol = 0.2 * L;
+  if (tid == 0) {
+    double acc = 0.0;
+    dist[0] = 0.0;
+    for (int k = 1; k < n_frames; ++k) {
+      const double dx = G[7 * k] - G[7 * (k - 1)], dy = G[7 * k + 1] - G[7 * (k - 1) + 1], dz = G[7 * k + 2] - G[7 * (k - 1) + 2];
+      acc += sqrt((dx * dx + dy * dy) + dz * dz);
+      dist[k] = acc;
+    }
+  }
+  __syncthreads();
+  for (int idx = tid; idx < n_frames; idx += nt) {
+    const double target = dist[idx] + L;
+    int best = -1;
+    double err = tol;
+    for (int i = idx; i < n_frames; ++i) {
+      const double e = fabs(dist[i] - target);
+      if (e < err) { best = i; err = e; }
+      else if (dist[i] - target > err) break;
+    }
+    match[idx] = best;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    int k = 0;
+    for (int idx = 0; idx < n_frames; ++idx)
+      if (match[idx] >= 0) comps[k++] = match[idx];
+    s_k = k;
+  }
+  __syncthreads();
+  const int K = s_k;
+  double* o = out + ((size_t)tr * n_len + li) * 4;
+  if (K < 2) {
+    if (tid == 0) { o[0] = 0.0; o[1] = 0.0; o[2] = 0.0; o[3] = 0.0; }
+    return;
+  }
+  for (int k = tid; k < K; k += nt) {
+    const int c = comps[k];
+    double Rc[9], tc[3], Rm[9], tm[3];
+    rel_motion(E + 7 * (size_t)k, E + 7 * (size_t)c, Rc, tc);       // T_c1_c2
+    rel_motion(G + 7 * (size_t)k, G + 7 * (size_t)c, Rm, tm);       // T_m1_m2
+    // E = T_m1_m2^-1 T_c1_c2: R = Rm^T Rc, t = Rm^T (tc - tm)
+    double Re[9], te[3];
+    m3_Tmul(Rm, Rc, Re);
+    const double d[3] = {tc[0] - tm[0], tc[1] - tm[1], tc[2] - tm[2]};
+    m3_Tvec(Rm, d, te);
+    const double tn = sqrt((te[0] * te[0] + te[1] * te[1]) + te[2] * te[2]);
+    const double ang = acos(fmin(1.0, fmax(-1.0, ((Re[0] + Re[4] + Re[8]) - 1.0) / 2.0))) * 180.0 / 3.14159265358979323846;
+    v_tr[k] = tn;
+    v_perc[k] = tn / L * 100.0;
+    v_rot[k] = ang / L;
+  }
+  __syncthreads();
+  if (tid < 3) {
+    const double* v = tid == 0 ? v_perc : tid == 1 ? v_rot : v_tr;
+    double s = 0.0;
+    for (int k = 0; k < K; ++k) s += v[k];
+    o[1 + tid] = s / K;
+  }
+  if (tid == 3) o[0] = (double)K;
+}
+
+int kitti_relative_error(const double* est_pose7, const double* gt_pose7, int n_traj, int n_frames, const double* lengths,
+                         int n_len, double* out4, double* trans_error_pct) {
+  if (n_traj < 1 || n_frames < 2 || n_len < 1 || n_frames > 4096) return ORCVIO_ERR_ARG;
+  const size_t nb = (size_t)n_traj * n_frames * 7 * sizeof(double);
+  double *dE = nullptr, *dG = nullptr, *dL = nullptr, *dO = nullptr;
+  const size_t no = (size_t)n_traj * n_len * 4;
+  if (cudaMalloc(&dE, nb) != cudaSuccess || cudaMalloc(&dG, nb) != cudaSuccess ||
+      cudaMalloc(&dL, n_len * sizeof(double)) != cudaSuccess || cudaMalloc(&dO, no * sizeof(double)) != cudaSuccess) {
+    cudaFree(dE); cudaFree(dG); cudaFree(dL); cudaFree(dO);
+    return ORCVIO_ERR_CUDA;
+  }
+  cudaMemcpy(dE, est_pose7, nb, cudaMemcpyHostToDevice);
+  cudaMemcpy(dG, gt_pose7, nb, cudaMemcpyHostToDevice);
+  cudaMemcpy(dL, lengths, n_len * sizeof(double), cudaMemcpyHostToDevice);
+  const size_t smem = (size_t)n_frames * (4 * sizeof(double) + 2 * sizeof(int));
+  cudaFuncSetAttribute(k_kitti_relative_error, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  k_kitti_relative_error<<<dim3(n_len, n_traj), 256, smem>>>(dE, dG, n_frames, dL, n_len, dO);
+  check_launch("k_kitti_relative_error");
+  const cudaError_t e = cudaMemcpy(out4, dO, no * sizeof(double), cudaMemcpyDeviceToHost);
+  cudaFree(dE); cudaFree(dG); cudaFree(dL); cudaFree(dO);
+  if (e != cudaSuccess) return ORCVIO_ERR_CUDA;
+  if (trans_error_pct)                 // write_kitti_errors_to_yaml: sum of the per-length means / (valid lengths + 1e-5)
+    for (int t = 0; t < n_traj; ++t) {
+      double tot = 0.0;
+      int valid = 0;
+      for (int l = 0; l < n_len; ++l) {
+        const double* o = out4 + ((size_t)t * n_len + l) * 4;
+        if (o[0] > 0.0) { ++valid; tot += o[1]; }
+      }
+      trans_error_pct[t] = tot / (valid + 1e-5);
+    }
+  return ORCVIO_OK;
+}
+
 }  // namespace ob

@@ -134,3 +134,27 @@ def test_results_do_not_depend_on_batch_composition_or_concurrency():
             ref = info["poses"]
         else:
             np.testing.assert_array_equal(info["poses"], ref)
+
+
+def test_kitti_relative_error_matches_the_reference_package_and_oracle():
+    """orcvio_kitti_relative_error: the device kernel against the golden outputs of the reference's own
+    vendored rpg_trajectory_evaluation and against the oracle, incl. a batch of trajectories, a length without samples
+    and the "TransError(%)" summary."""
+    from oracle import trajmetrics as tm
+    from test_oracle_cpu import _kitti_cases
+    mk, g = _kitti_cases()
+    for name, n, step, seed, lengths in mk.CASES:
+        gt, es = mk.synth(n, seed, step)
+        gt2, es2 = mk.synth(n, seed + 10, step)
+        L = list(lengths) + [1e6]                           # the last length has no sample
+        out, summ = api.kitti_relative_error(np.stack([es, es2]), np.stack([gt, gt2]), L)
+        for li, ln in enumerate(lengths):
+            st = g[f"{name}_{ln}_stats"]
+            assert int(out[0, li, 0]) == int(st[0])
+            assert abs(out[0, li, 1] - st[1]) <= 1e-11 and abs(out[0, li, 3] - st[3]) <= 1e-11
+            assert abs(out[0, li, 2] - st[2]) <= 1e-9
+        assert np.all(out[:, -1, :] == 0.0)
+        for t, (e_, g_) in enumerate(((es, gt), (es2, gt2))):
+            rows, s_ref = tm.kitti_summary(e_, g_, L)
+            np.testing.assert_allclose(out[t], rows, rtol=0, atol=1e-9)
+            assert abs(summ[t] - s_ref) <= 1e-10

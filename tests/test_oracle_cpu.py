@@ -601,3 +601,31 @@ def test_msckf_update_equals_the_bayesian_marginal_over_the_features():
     assert np.abs(v.state_cov[np.ix_(act, act)] - Pp).max() <= 1e-9 * np.abs(Pp).max()
     assert np.abs(dx[act] - dxp).max() <= 1e-9 * max(1.0, np.abs(dxp).max())
     assert np.abs(v.state_cov[15:22]).max() == 0.0 and np.abs(dx[15:22]).max() == 0.0
+
+
+def _kitti_cases():
+    import sys
+    sys.path.insert(0, GOLD)
+    import make_kitti_rel_golden as mk      # only its deterministic `synth` and CASES: the reference package is not imported
+    return mk, _gold("kitti_rel_error")
+
+
+def test_kitti_relative_error_oracle_against_the_reference_package():
+    """oracle/trajmetrics.py against outputs of the reference's own vendored rpg_trajectory_evaluation (what
+    python_scripts/trajectory_eval/traj_eval.py calls), generated by tests/golden/make_kitti_rel_golden.py: sample counts,
+    per-length means, every 16th sample."""
+    from oracle import trajmetrics as tm
+    mk, g = _kitti_cases()
+    for name, n, step, seed, lengths in mk.CASES:
+        gt, es = mk.synth(n, seed, step)
+        assert np.array_equal(np.array([gt.sum(), es.sum()]), g[name + "_checksum"]), "inputs differ from the fixture's"
+        for L in lengths:
+            r = tm.relative_error(es, gt, float(L))
+            st = g[f"{name}_{L}_stats"]
+            assert len(r["trans"]) == int(st[0])
+            assert abs(r["trans_perc"].mean() - st[1]) <= 1e-12 and abs(r["trans"].mean() - st[3]) <= 1e-12
+            assert abs(r["rot_deg_per_m"].mean() - st[2]) <= 1e-10 and abs(r["rot_deg"].mean() - st[4]) <= 1e-9
+            np.testing.assert_allclose(r["trans_perc"][::16], g[f"{name}_{L}_perc16"], rtol=0, atol=1e-12)
+            np.testing.assert_allclose(r["rot_deg"][::16], g[f"{name}_{L}_rot16"], rtol=0, atol=1e-9)
+    # too few samples: nothing is computed
+    assert len(tm.relative_error(es[:40], gt[:40], 1000.0)["trans"]) == 0
