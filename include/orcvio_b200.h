@@ -224,9 +224,18 @@ int orcvio_trajectory_metrics(const double* est_pose7, const double* gt_pose7, i
  * trajectories on the device: for every sub-trajectory length the pairs (start, first pose closest to start + length
  * along the ground truth, tolerance 0.2 length) and the error of the relative motion.  out4: n_traj x n_len x 4 =
  * (samples, mean translation error in % of the length, mean rotation error in deg / m, mean translation error in m);
- * trans_error_pct (n_traj, may be NULL): write_kitti_errors_to_yaml's "TransError(%)".  Poses as above, n_frames <= 4096. */
+ * trans_error_pct (n_traj, may be NULL): write_kitti_errors_to_yaml's "TransError(%)".  scale (n_traj, may be NULL = 1):
+ * the scale of the alignment, which the package applies to the estimated relative translation (sim3 only).  Poses as
+ * above, n_frames <= 4096. */
 int orcvio_kitti_relative_error(const double* est_pose7, const double* gt_pose7, int n_traj, int n_frames,
-                                const double* lengths, int n_len, double* out4, double* trans_error_pct);
+                                const double* lengths, int n_len, const double* scale, double* out4,
+                                double* trans_error_pct);
+/* Trajectory.align_trajectory + the translation part of compute_absolute_error of the same package (trajectory.py:211-275,
+ * align_trajectory.py:27-79): Umeyama alignment gt ~ s R est + t over all frames, method 0 = "sim3", 1 = "se3" (s = 1),
+ * for a batch of trajectories on the device.  out15 per trajectory: s, R (9, row-major), t (3), mean and rmse of the
+ * absolute translation error (the mean is the "RMSE(m)" of write_kitti_errors_to_yaml). */
+int orcvio_trajectory_align_ate(const double* est_pose7, const double* gt_pose7, int n_traj, int n_frames, int method,
+                                double* out15);
 int orcvio_batch_get_state(orcvio_batch* b, int i, OrcvioState* out);
 int orcvio_batch_get_cov(orcvio_batch* b, int i, double* P, int cap, int* D);
 int orcvio_batch_get_frame_stats(orcvio_batch* b, int i, OrcvioFrameStats* out);

@@ -50,8 +50,33 @@ def comparison_indices(distances, dist, max_dist_diff):
     return comps
 
 
-def relative_error(pose_es, pose_gt, dist, max_dist_diff=None):
-    """compute_relative_error with T_cm = I, scale = 1.  pose: (n, 7) = p, q xyzw.  Returns dict(trans, trans_perc,
+def align_umeyama(p_gt, p_es, known_scale):
+    """align_trajectory.py:27-79 (yaw_only = False) as align_utils.alignSIM3 / alignSE3 call it: gt = s R est + t."""
+    mu_m, mu_d = p_gt.mean(0), p_es.mean(0)
+    M, Dd = p_gt - mu_m, p_es - mu_d
+    n = p_gt.shape[0]
+    Cm = 1.0 / n * (M.T @ Dd)
+    sigma2 = 1.0 / n * float(np.sum(Dd * Dd))
+    U, Dv, Vt = np.linalg.svd(Cm)
+    V = Vt.T
+    S = np.eye(3)
+    if np.linalg.det(U) * np.linalg.det(V) < 0:
+        S[2, 2] = -1
+    R = U @ S @ V.T
+    s = 1.0 if known_scale else 1.0 / sigma2 * float(np.trace(np.diag(Dv) @ S))
+    return s, R, mu_m - s * (R @ mu_d)
+
+
+def absolute_error(pose_es, pose_gt, method):
+    """Trajectory.align_trajectory (trajectory.py:211-246, all frames) + compute_absolute_error's translation part
+    (compute_trajectory_errors.py:70-72) + results_writer.compute_statistics: (s, R, t, mean, rmse)."""
+    s, R, t = align_umeyama(pose_gt[:, :3], pose_es[:, :3], known_scale=(method == "se3"))
+    e = np.sqrt(np.sum((pose_gt[:, :3] - (s * (pose_es[:, :3] @ R.T) + t)) ** 2, axis=1))
+    return s, R, t, float(np.mean(e)), float(np.sqrt(e @ e / len(e)))
+
+
+def relative_error(pose_es, pose_gt, dist, max_dist_diff=None, scale=1.0):
+    """compute_relative_error with T_cm = I (scale: the alignment's, 1 unless sim3).  pose: (n, 7) = p, q xyzw.  Returns dict(trans, trans_perc,
     rot_deg, rot_deg_per_m) of per-sample arrays (empty when fewer than two samples)."""
     if max_dist_diff is None:
         max_dist_diff = 0.2 * dist
@@ -68,6 +93,7 @@ def relative_error(pose_es, pose_gt, dist, max_dist_diff=None):
 
     for idx, c in enumerate(comps):
         T_c1_c2 = np.linalg.inv(T(pose_es[idx])) @ T(pose_es[c])
+        T_c1_c2[:3, 3] *= scale
         T_m1_m2 = np.linalg.inv(T(pose_gt[idx])) @ T(pose_gt[c])
         E = np.linalg.inv(T_m1_m2) @ T_c1_c2
         tn = float(np.linalg.norm(E[:3, 3]))            # (the rotation into the world frame does not change the norm)
@@ -79,13 +105,13 @@ def relative_error(pose_es, pose_gt, dist, max_dist_diff=None):
     return {k: np.array(v) for k, v in out.items()}
 
 
-def kitti_summary(pose_es, pose_gt, lengths):
+def kitti_summary(pose_es, pose_gt, lengths, scale=1.0):
     """Per length (samples, mean trans %, mean rot deg/m, mean trans m) and write_kitti_errors_to_yaml's
     "TransError(%)" = sum of the per-length means over the lengths with samples / (their number + 1e-5)."""
     rows = []
     tot, valid = 0.0, 0
     for L in lengths:
-        r = relative_error(pose_es, pose_gt, float(L))
+        r = relative_error(pose_es, pose_gt, float(L), scale=scale)
         n = len(r["trans"])
         if n:
             rows.append([n, float(np.mean(r["trans_perc"])), float(np.mean(r["rot_deg_per_m"])), float(np.mean(r["trans"]))])

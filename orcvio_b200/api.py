@@ -709,7 +709,22 @@ def trajectory_metrics(est_pose7, gt_pose7):
     return out
 
 
-def kitti_relative_error(est_pose7, gt_pose7, lengths):
+def trajectory_align_ate(est_pose7, gt_pose7, method="sim3"):
+    """Umeyama alignment + absolute translation error (orcvio_trajectory_align_ate): (n, F, 7) -> dict(s (n), R (n, 3, 3),
+    t (n, 3), mean (n), rmse (n))."""
+    e = np.ascontiguousarray(est_pose7, dtype=np.float64)
+    g = np.ascontiguousarray(gt_pose7, dtype=np.float64)
+    assert e.shape == g.shape and e.ndim == 3 and e.shape[2] == 7
+    out = np.zeros((e.shape[0], 15))
+    f = lib().orcvio_trajectory_align_ate
+    f.argtypes = [C.POINTER(C.c_double)] * 2 + [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_double)]
+    rc = f(_dp(e), _dp(g), e.shape[0], e.shape[1], {"sim3": 0, "se3": 1}[method], _dp(out))
+    if rc != 0:
+        raise RuntimeError(f"orcvio_trajectory_align_ate failed: {rc}")
+    return dict(s=out[:, 0], R=out[:, 1:10].reshape(-1, 3, 3), t=out[:, 10:13], mean=out[:, 13], rmse=out[:, 14])
+
+
+def kitti_relative_error(est_pose7, gt_pose7, lengths, scale=None):
     """The reference's KITTI-style relative error on the device (orcvio_kitti_relative_error): (n, F, 7) poses ->
     ((n, n_len, 4): samples, mean translation %, mean rotation deg / m, mean translation m;  (n,): TransError(%))."""
     e = np.ascontiguousarray(est_pose7, dtype=np.float64)
@@ -719,8 +734,9 @@ def kitti_relative_error(est_pose7, gt_pose7, lengths):
     out = np.zeros((e.shape[0], len(L), 4))
     summ = np.zeros(e.shape[0])
     f = lib().orcvio_kitti_relative_error
-    f.argtypes = [C.POINTER(C.c_double)] * 2 + [C.c_int, C.c_int, C.POINTER(C.c_double), C.c_int] + [C.POINTER(C.c_double)] * 2
-    rc = f(_dp(e), _dp(g), e.shape[0], e.shape[1], _dp(L), len(L), _dp(out), _dp(summ))
+    f.argtypes = [C.POINTER(C.c_double)] * 2 + [C.c_int, C.c_int, C.POINTER(C.c_double), C.c_int] + [C.POINTER(C.c_double)] * 3
+    sc = None if scale is None else np.ascontiguousarray(scale, dtype=np.float64)
+    rc = f(_dp(e), _dp(g), e.shape[0], e.shape[1], _dp(L), len(L), None if sc is None else _dp(sc), _dp(out), _dp(summ))
     if rc != 0:
         raise RuntimeError(f"orcvio_kitti_relative_error failed: {rc}")
     return out, summ

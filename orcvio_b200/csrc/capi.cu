@@ -338,9 +338,16 @@ int orcvio_trajectory_metrics(const double* est_pose7, const double* gt_pose7, i
 }
 
 int orcvio_kitti_relative_error(const double* est_pose7, const double* gt_pose7, int n_traj, int n_frames,
-                                const double* lengths, int n_len, double* out4, double* trans_error_pct) {
+                                const double* lengths, int n_len, const double* scale, double* out4,
+                                double* trans_error_pct) {
   if (!est_pose7 || !gt_pose7 || !lengths || !out4) return ORCVIO_ERR_ARG;
-  return ob::kitti_relative_error(est_pose7, gt_pose7, n_traj, n_frames, lengths, n_len, out4, trans_error_pct);
+  return ob::kitti_relative_error(est_pose7, gt_pose7, n_traj, n_frames, lengths, n_len, scale, out4, trans_error_pct);
+}
+
+int orcvio_trajectory_align_ate(const double* est_pose7, const double* gt_pose7, int n_traj, int n_frames, int method,
+                                double* out15) {
+  if (!est_pose7 || !gt_pose7 || !out15 || (method != 0 && method != 1)) return ORCVIO_ERR_ARG;
+  return ob::umeyama_ate(est_pose7, gt_pose7, n_traj, n_frames, method == 1, out15);
 }
 
 int orcvio_batch_get_state(orcvio_batch* b, int i, OrcvioState* out) {

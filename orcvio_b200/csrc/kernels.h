@@ -327,7 +327,8 @@ void launch_info_prior(const UpdArgs& u, const InfoBufs& ib, int max_N, cudaStre
 int trajectory_metrics(const double* est_pose7, const double* gt_pose7, int n_traj, int n_frames, double* out4);
 // KITTI-style relative error (rpg_trajectory_evaluation as the reference's traj_eval.py calls it); host pointers
 int kitti_relative_error(const double* est_pose7, const double* gt_pose7, int n_traj, int n_frames, const double* lengths,
-                         int n_len, double* out4, double* trans_error_pct);
+                         int n_len, const double* scale, double* out4, double* trans_error_pct);
+int umeyama_ate(const double* est_pose7, const double* gt_pose7, int n_traj, int n_frames, int known_scale, double* out15);
 // findTransform (+ poseSE32SE2) for a batch of objects (kabsch_kernel.cu); host pointers
 int kabsch_init(const double* mean_pts, const double* world_pts, const int* off, int n_obj, int se2, double* wTq16, int* ok);
 // object state optimiser (objlm_kernel.cu); host pointers

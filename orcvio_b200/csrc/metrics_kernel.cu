@@ -10,6 +10,7 @@
 // position RMSE (m), final position error (m).
 #include "../../include/orcvio_b200.h"
 #include "kernels.h"
+#include "svd3.cuh"
 
 namespace ob {
 
@@ -178,7 +179,7 @@ __device__ __forceinline__ void rel_motion(const double* a, const double* b, dou
 
 __global__ void __launch_bounds__(256) k_kitti_relative_error(const double* __restrict__ est, const double* __restrict__ gt,
                                                               int n_frames, const double* __restrict__ lengths, int n_len,
-                                                              double* __restrict__ out) {
+                                                              const double* __restrict__ scale, double* __restrict__ out) {
   extern __shared__ double ksm[];
   double* dist = ksm;                               // [n_frames]
   double* v_perc = dist + n_frames;                 // [n_frames] per-sample values, summed in order at the end
@@ -230,6 +231,7 @@ __global__ void __launch_bounds__(256) k_kitti_relative_error(const double* __re
     const int c = comps[k];
     double Rc[9], tc[3], Rm[9], tm[3];
     rel_motion(E + 7 * (size_t)k, E + 7 * (size_t)c, Rc, tc);       // T_c1_c2
+    if (scale) { const double sc = scale[tr]; tc[0] *= sc; tc[1] *= sc; tc[2] *= sc; }     // (the sim3 alignment's scale, :33)
     rel_motion(G + 7 * (size_t)k, G + 7 * (size_t)c, Rm, tm);       // T_m1_m2
     // E = T_m1_m2^-1 T_c1_c2: R = Rm^T Rc, t = Rm^T (tc - tm)
     double Re[9], te[3];
@@ -253,25 +255,27 @@ __global__ void __launch_bounds__(256) k_kitti_relative_error(const double* __re
 }
 
 int kitti_relative_error(const double* est_pose7, const double* gt_pose7, int n_traj, int n_frames, const double* lengths,
-                         int n_len, double* out4, double* trans_error_pct) {
+                         int n_len, const double* scale, double* out4, double* trans_error_pct) {
   if (n_traj < 1 || n_frames < 2 || n_len < 1 || n_frames > 4096) return ORCVIO_ERR_ARG;
   const size_t nb = (size_t)n_traj * n_frames * 7 * sizeof(double);
-  double *dE = nullptr, *dG = nullptr, *dL = nullptr, *dO = nullptr;
+  double *dE = nullptr, *dG = nullptr, *dL = nullptr, *dO = nullptr, *dS = nullptr;
   const size_t no = (size_t)n_traj * n_len * 4;
   if (cudaMalloc(&dE, nb) != cudaSuccess || cudaMalloc(&dG, nb) != cudaSuccess ||
-      cudaMalloc(&dL, n_len * sizeof(double)) != cudaSuccess || cudaMalloc(&dO, no * sizeof(double)) != cudaSuccess) {
-    cudaFree(dE); cudaFree(dG); cudaFree(dL); cudaFree(dO);
+      cudaMalloc(&dL, n_len * sizeof(double)) != cudaSuccess || cudaMalloc(&dO, no * sizeof(double)) != cudaSuccess ||
+      cudaMalloc(&dS, n_traj * sizeof(double)) != cudaSuccess) {
+    cudaFree(dE); cudaFree(dG); cudaFree(dL); cudaFree(dO); cudaFree(dS);
     return ORCVIO_ERR_CUDA;
   }
+  if (scale) cudaMemcpy(dS, scale, n_traj * sizeof(double), cudaMemcpyHostToDevice);
   cudaMemcpy(dE, est_pose7, nb, cudaMemcpyHostToDevice);
   cudaMemcpy(dG, gt_pose7, nb, cudaMemcpyHostToDevice);
   cudaMemcpy(dL, lengths, n_len * sizeof(double), cudaMemcpyHostToDevice);
   const size_t smem = (size_t)n_frames * (4 * sizeof(double) + 2 * sizeof(int));
   cudaFuncSetAttribute(k_kitti_relative_error, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-  k_kitti_relative_error<<<dim3(n_len, n_traj), 256, smem>>>(dE, dG, n_frames, dL, n_len, dO);
+  k_kitti_relative_error<<<dim3(n_len, n_traj), 256, smem>>>(dE, dG, n_frames, dL, n_len, scale ? dS : nullptr, dO);
   check_launch("k_kitti_relative_error");
   const cudaError_t e = cudaMemcpy(out4, dO, no * sizeof(double), cudaMemcpyDeviceToHost);
-  cudaFree(dE); cudaFree(dG); cudaFree(dL); cudaFree(dO);
+  cudaFree(dE); cudaFree(dG); cudaFree(dL); cudaFree(dO); cudaFree(dS);
   if (e != cudaSuccess) return ORCVIO_ERR_CUDA;
   if (trans_error_pct)                 // write_kitti_errors_to_yaml: sum of the per-length means / (valid lengths + 1e-5)
     for (int t = 0; t < n_traj; ++t) {
@@ -284,6 +288,106 @@ int kitti_relative_error(const double* est_pose7, const double* gt_pose7, int n_
       trans_error_pct[t] = tot / (valid + 1e-5);
     }
   return ORCVIO_OK;
+}
+
+// Umeyama alignment of an estimated trajectory onto its ground truth over all frames and the absolute translation
+// error behind it -- Trajectory.align_trajectory / compute_absolute_error of the same package (trajectory.py:211-275,
+// align_utils.py:79-110, align_trajectory.py:27-79, compute_trajectory_errors.py:70-72): gt ~ s R est + t with s = 1
+// for "se3".  One CTA per trajectory: means, the 3 x 3 correlation and sigma^2 by fixed-order reductions, the SVD on
+// one thread, then the errors.  out15 per trajectory: s, R (9, row-major), t (3), mean |e|, rmse |e| -- the mean is what
+// write_kitti_errors_to_yaml labels "RMSE(m)".
+__global__ void __launch_bounds__(128) k_umeyama_ate(const double* __restrict__ est, const double* __restrict__ gt, int n_frames,
+                                                     int known_scale, double* __restrict__ out) {
+  __shared__ double red[13][128];
+  __shared__ double sh[32];
+  const int tr = blockIdx.x, tid = threadIdx.x;
+  const double* E = est + (size_t)tr * n_frames * 7;
+  const double* G = gt + (size_t)tr * n_frames * 7;
+  auto reduce = [&](int nq) {                       // red[q][0] <- sum over the threads, fixed tree
+    __syncthreads();
+    for (int o = 64; o > 0; o >>= 1) {
+      if (tid < o)
+        for (int q = 0; q < nq; ++q) red[q][tid] += red[q][tid + o];
+      __syncthreads();
+    }
+  };
+  double a[13];
+  for (int q = 0; q < 6; ++q) a[q] = 0.0;
+  for (int k = tid; k < n_frames; k += 128)
+    for (int c = 0; c < 3; ++c) { a[c] += G[7 * (size_t)k + c]; a[3 + c] += E[7 * (size_t)k + c]; }
+  for (int q = 0; q < 6; ++q) red[q][tid] = a[q];
+  reduce(6);
+  if (tid < 6) sh[tid] = red[tid][0] / n_frames;    // mu_M (gt), mu_D (est)
+  __syncthreads();
+  const double mm[3] = {sh[0], sh[1], sh[2]}, md[3] = {sh[3], sh[4], sh[5]};
+  for (int q = 0; q < 10; ++q) a[q] = 0.0;
+  for (int k = tid; k < n_frames; k += 128) {
+    double m[3], d[3];
+    for (int c = 0; c < 3; ++c) { m[c] = G[7 * (size_t)k + c] - mm[c]; d[c] = E[7 * (size_t)k + c] - md[c]; }
+    for (int i = 0; i < 3; ++i)
+      for (int j = 0; j < 3; ++j) a[3 * i + j] += m[i] * d[j];
+    a[9] += (d[0] * d[0] + d[1] * d[1]) + d[2] * d[2];
+  }
+  __syncthreads();
+  for (int q = 0; q < 10; ++q) red[q][tid] = a[q];
+  reduce(10);
+  if (tid == 0) {
+    double Cm[9], U[9], S[3], V[9], VUt[9];
+    for (int i = 0; i < 9; ++i) Cm[i] = red[i][0] / n_frames;
+    const double sigma2 = red[9][0] / n_frames;
+    svd3::svd3_hestenes(Cm, U, S, V);               // C = U diag(S) V^T
+    // det(U) det(V) < 0 -> flip the last singular direction; R = U diag(1, 1, f) V^T
+    const double f = (svd3::det3(U) * svd3::det3(V) < 0) ? -1.0 : 1.0;
+    double R[9];
+    for (int i = 0; i < 3; ++i)
+      for (int j = 0; j < 3; ++j) R[3 * i + j] = (U[3 * i] * V[3 * j] + U[3 * i + 1] * V[3 * j + 1]) + f * U[3 * i + 2] * V[3 * j + 2];
+    const double sc = known_scale ? 1.0 : ((S[0] + S[1]) + f * S[2]) / sigma2;
+    double Rd[3];
+    m3_vec(R, md, Rd);
+    sh[6] = sc;
+    for (int i = 0; i < 9; ++i) sh[7 + i] = R[i];
+    for (int i = 0; i < 3; ++i) sh[16 + i] = mm[i] - sc * Rd[i];
+    (void)VUt;
+  }
+  __syncthreads();
+  const double sc = sh[6];
+  double s1 = 0.0, s2 = 0.0;
+  for (int k = tid; k < n_frames; k += 128) {
+    double pe[3], Rp[3];
+    for (int c = 0; c < 3; ++c) pe[c] = E[7 * (size_t)k + c];
+    m3_vec(sh + 7, pe, Rp);
+    double e2 = 0.0;
+    for (int c = 0; c < 3; ++c) { const double d = G[7 * (size_t)k + c] - (sc * Rp[c] + sh[16 + c]); e2 += d * d; }
+    s1 += sqrt(e2);
+    s2 += e2;
+  }
+  __syncthreads();
+  red[0][tid] = s1; red[1][tid] = s2;
+  reduce(2);
+  if (tid == 0) {
+    double* o = out + 15 * (size_t)tr;
+    for (int i = 0; i < 13; ++i) o[i] = sh[6 + i];
+    o[13] = red[0][0] / n_frames;
+    o[14] = sqrt(red[1][0] / n_frames);
+  }
+}
+
+int umeyama_ate(const double* est_pose7, const double* gt_pose7, int n_traj, int n_frames, int known_scale, double* out15) {
+  if (n_traj < 1 || n_frames < 3) return ORCVIO_ERR_ARG;
+  const size_t nb = (size_t)n_traj * n_frames * 7 * sizeof(double);
+  double *dE = nullptr, *dG = nullptr, *dO = nullptr;
+  if (cudaMalloc(&dE, nb) != cudaSuccess || cudaMalloc(&dG, nb) != cudaSuccess ||
+      cudaMalloc(&dO, (size_t)n_traj * 15 * sizeof(double)) != cudaSuccess) {
+    cudaFree(dE); cudaFree(dG); cudaFree(dO);
+    return ORCVIO_ERR_CUDA;
+  }
+  cudaMemcpy(dE, est_pose7, nb, cudaMemcpyHostToDevice);
+  cudaMemcpy(dG, gt_pose7, nb, cudaMemcpyHostToDevice);
+  k_umeyama_ate<<<n_traj, 128>>>(dE, dG, n_frames, known_scale, dO);
+  check_launch("k_umeyama_ate");
+  const cudaError_t e = cudaMemcpy(out15, dO, (size_t)n_traj * 15 * sizeof(double), cudaMemcpyDeviceToHost);
+  cudaFree(dE); cudaFree(dG); cudaFree(dO);
+  return e == cudaSuccess ? ORCVIO_OK : ORCVIO_ERR_CUDA;
 }
 
 }  // namespace ob

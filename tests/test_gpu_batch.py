@@ -158,3 +158,17 @@ def test_kitti_relative_error_matches_the_reference_package_and_oracle():
             rows, s_ref = tm.kitti_summary(e_, g_, L)
             np.testing.assert_allclose(out[t], rows, rtol=0, atol=1e-9)
             assert abs(summ[t] - s_ref) <= 1e-10
+        # Umeyama alignment + absolute error (orcvio_trajectory_align_ate) against the package's outputs, and the relative
+        # error with the sim3 scale
+        for method in ("sim3", "se3"):
+            al = api.trajectory_align_ate(np.stack([es, es2]), np.stack([gt, gt2]), method)
+            ref = g[f"{name}_{method}"]
+            assert abs(al["s"][0] - ref[0]) <= 1e-12 and np.abs(al["R"][0].ravel() - ref[1:10]).max() <= 1e-11
+            assert np.abs(al["t"][0] - ref[10:13]).max() <= 1e-9
+            assert abs(al["mean"][0] - ref[13]) <= 1e-11 and abs(al["rmse"][0] - ref[14]) <= 1e-11
+            s2, R2, t2, mean2, rmse2 = tm.absolute_error(es2, gt2, method)
+            assert abs(al["s"][1] - s2) <= 1e-12 and abs(al["mean"][1] - mean2) <= 1e-11
+        al = api.trajectory_align_ate(np.stack([es, es2]), np.stack([gt, gt2]), "sim3")
+        out_s, _ = api.kitti_relative_error(np.stack([es, es2]), np.stack([gt, gt2]), [lengths[0]], scale=al["s"])
+        st = g[f"{name}_{lengths[0]}_sim3scale_stats"]
+        assert int(out_s[0, 0, 0]) == int(st[0]) and abs(out_s[0, 0, 1] - st[1]) <= 1e-11

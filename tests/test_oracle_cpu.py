@@ -627,5 +627,14 @@ def test_kitti_relative_error_oracle_against_the_reference_package():
             assert abs(r["rot_deg_per_m"].mean() - st[2]) <= 1e-10 and abs(r["rot_deg"].mean() - st[4]) <= 1e-9
             np.testing.assert_allclose(r["trans_perc"][::16], g[f"{name}_{L}_perc16"], rtol=0, atol=1e-12)
             np.testing.assert_allclose(r["rot_deg"][::16], g[f"{name}_{L}_rot16"], rtol=0, atol=1e-9)
+        # Umeyama alignment (sim3 / se3) + absolute translation error, and the relative error with the sim3 scale
+        for method in ("sim3", "se3"):
+            s_, R_, t_, mean, rmse = tm.absolute_error(es, gt, method)
+            ref = g[f"{name}_{method}"]
+            assert abs(s_ - ref[0]) <= 1e-14 and np.abs(R_.ravel() - ref[1:10]).max() <= 1e-13
+            assert np.abs(t_ - ref[10:13]).max() <= 1e-11 and abs(mean - ref[13]) <= 1e-13 and abs(rmse - ref[14]) <= 1e-13
+        st = g[f"{name}_{lengths[0]}_sim3scale_stats"]
+        r = tm.relative_error(es, gt, float(lengths[0]), scale=tm.absolute_error(es, gt, "sim3")[0])
+        assert len(r["trans"]) == int(st[0]) and abs(r["trans_perc"].mean() - st[1]) <= 1e-12
     # too few samples: nothing is computed
     assert len(tm.relative_error(es[:40], gt[:40], 1000.0)["trans"]) == 0
